@@ -1,0 +1,284 @@
+"""ctypes bindings for the CPU oracle (oracle/libndb_oracle.so) and, when present, the
+reference's own operator sources compiled under oracle/pgshim (oracle/_ref/*.so).
+
+TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product (neurondb_b200/) never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+L2, COSINE, IP = 1, 2, 3
+ARITH_OP_F64, ARITH_AVX2, ARITH_AVX512, ARITH_IVF_F32, ARITH_HNSW = 0, 1, 2, 3, 4
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
+
+
+def _load(name="libndb_oracle.so"):
+    path = os.path.join(ORACLE_DIR, name)
+    if not os.path.exists(path):
+        build_oracle()
+    lib = C.CDLL(path)
+    f = lib.orc_check_vector; f.restype = C.c_int; f.argtypes = [_f32p, C.c_int]
+    for nm in ("orc_l2_distance", "orc_inner_product_distance", "orc_inner_product_op",
+               "orc_cosine_distance", "orc_kmeans_l2sq"):
+        f = getattr(lib, nm); f.restype = C.c_float; f.argtypes = [_f32p, _f32p, C.c_int]
+    for nm in ("orc_l2_avx", "orc_ip_avx", "orc_cosine_avx", "orc_ivf_distance", "orc_hnsw_distance"):
+        f = getattr(lib, nm); f.restype = C.c_float; f.argtypes = [_f32p, _f32p, C.c_int, C.c_int]
+    f = lib.orc_distance; f.restype = C.c_float; f.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int]
+    f = lib.orc_distance_pairs; f.restype = None
+    f.argtypes = [_f32p, _f32p, _f32p, C.c_int64, C.c_int, C.c_int, C.c_int]
+    f = lib.orc_knn_exact; f.restype = None
+    f.argtypes = [_f32p, C.c_void_p, C.c_int64, C.c_int, _f32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                  _f32p, _i64p, C.c_int]
+    f = lib.orc_kmeans_train; f.restype = C.c_int
+    f.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _f32p, _i32p, _i32p,
+                  C.POINTER(C.c_float)]
+    f = lib.orc_kmeans_assign; f.restype = None
+    f.argtypes = [_f32p, C.c_int64, C.c_int, _f32p, C.c_int, _i32p, C.c_int]
+    f = lib.orc_kmeans_update; f.restype = None
+    f.argtypes = [_f32p, _i32p, C.c_int64, C.c_int, C.c_int, _f32p, _i32p]
+    f = lib.orc_ivf_train_samples; f.restype = C.c_int; f.argtypes = [C.c_int64, C.c_int]
+    f = lib.orc_ivf_assign; f.restype = None
+    f.argtypes = [_f32p, C.c_int64, C.c_int, _f32p, C.c_int, _i32p, C.c_int]
+    f = lib.orc_ivf_select_clusters; f.restype = None
+    f.argtypes = [_f32p, C.c_int, _f32p, C.c_int, C.c_int, _i32p]
+    f = lib.orc_ivf_search; f.restype = None
+    f.argtypes = [_f32p, C.c_void_p, C.c_int, _f32p, C.c_int, _i64p, _i64p, _f32p, C.c_int, C.c_int,
+                  C.c_int, C.c_int, C.c_int, _f32p, _i64p, _i32p, C.c_int]
+    f = lib.orc_hnsw_create; f.restype = C.c_void_p
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int64]
+    f = lib.orc_hnsw_free; f.restype = None; f.argtypes = [C.c_void_p]
+    f = lib.orc_hnsw_random_level; f.restype = C.c_int; f.argtypes = [C.c_float]
+    f = lib.orc_hnsw_build; f.restype = None
+    f.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_void_p, C.c_int]
+    f = lib.orc_hnsw_search; f.restype = None
+    f.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u32p, _f32p,
+                  _i32p, C.c_int]
+    f = lib.orc_hnsw_size; f.restype = C.c_int64; f.argtypes = [C.c_void_p]
+    f = lib.orc_hnsw_upper_slots; f.restype = C.c_int64; f.argtypes = [C.c_void_p]
+    f = lib.orc_hnsw_distance_evals; f.restype = C.c_int64; f.argtypes = []
+    f = lib.orc_hnsw_meta; f.restype = None
+    f.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    f = lib.orc_hnsw_export; f.restype = None
+    f.argtypes = [C.c_void_p, _i32p, _u32p, _i16p, _i64p, _u32p]
+    f = lib.orc_recall_at_k; f.restype = C.c_double; f.argtypes = [_i64p, _i64p, C.c_int, C.c_int]
+    f = lib.orc_merge_topk; f.restype = None
+    f.argtypes = [_f32p, _i64p, C.c_int, C.c_int, C.c_int, _f32p, _i64p]
+    return lib
+
+
+_LIBS = {}
+
+
+def lib(native=False):
+    name = "libndb_oracle_native.so" if native else "libndb_oracle.so"
+    if name not in _LIBS:
+        _LIBS[name] = _load(name)
+    return _LIBS[name]
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ---- convenience wrappers -------------------------------------------------------------
+def distance_pairs(A, B, metric, arith):
+    A, B = f32(A), f32(B)
+    out = np.empty(A.shape[0], np.float32)
+    lib().orc_distance_pairs(A, B, out, A.shape[0], A.shape[1], metric, arith)
+    return out
+
+
+def knn_exact(X, Q, k, metric=L2, arith=ARITH_OP_F64, ids=None, nthreads=8, native=False):
+    X, Q = f32(X), f32(Q)
+    d = np.empty((Q.shape[0], k), np.float32)
+    i = np.empty((Q.shape[0], k), np.int64)
+    idp = None if ids is None else np.ascontiguousarray(ids, np.int64).ctypes.data
+    lib(native).orc_knn_exact(X, idp, X.shape[0], X.shape[1], Q, Q.shape[0], k, metric, arith, d, i, nthreads)
+    return d, i
+
+
+def kmeans_train(X, k, max_iter=50, threshold=0.001):
+    X = f32(X)
+    n, dim = X.shape
+    Cn = np.zeros((k, dim), np.float32)
+    assign = np.zeros(n, np.int32)
+    counts = np.zeros(k, np.int32)
+    cost = C.c_float(0)
+    iters = lib().orc_kmeans_train(X, n, dim, k, max_iter, threshold, Cn, assign, counts, C.byref(cost))
+    return Cn, assign, counts, iters, cost.value
+
+
+def kmeans_assign(X, Cn, nthreads=8):
+    X, Cn = f32(X), f32(Cn)
+    out = np.empty(X.shape[0], np.int32)
+    lib().orc_kmeans_assign(X, X.shape[0], X.shape[1], Cn, Cn.shape[0], out, nthreads)
+    return out
+
+
+def kmeans_update(X, assign, k):
+    X = f32(X)
+    Cn = np.zeros((k, X.shape[1]), np.float32)
+    counts = np.zeros(k, np.int32)
+    lib().orc_kmeans_update(X, np.ascontiguousarray(assign, np.int32), X.shape[0], X.shape[1], k, Cn, counts)
+    return Cn, counts
+
+
+def ivf_assign(X, Cn, nthreads=8, native=False):
+    X, Cn = f32(X), f32(Cn)
+    out = np.empty(X.shape[0], np.int32)
+    lib(native).orc_ivf_assign(X, X.shape[0], X.shape[1], Cn, Cn.shape[0], out, nthreads)
+    return out
+
+
+def lists_from_assignment(assign, nlists):
+    """CSR over insertion order: what a sequence of ivfinsert calls in row order produces."""
+    assign = np.asarray(assign)
+    order = np.argsort(assign, kind="stable").astype(np.int64)
+    counts = np.bincount(assign, minlength=nlists)
+    off = np.zeros(nlists + 1, np.int64)
+    off[1:] = np.cumsum(counts)
+    return off, order
+
+
+def ivf_search(X, Cn, list_off, list_rows, Q, nprobe, k, strategy=L2, literal=False, ids=None,
+               nthreads=8, native=False):
+    X, Cn, Q = f32(X), f32(Cn), f32(Q)
+    nq = Q.shape[0]
+    d = np.empty((nq, k), np.float32)
+    i = np.empty((nq, k), np.int64)
+    cnt = np.empty(nq, np.int32)
+    idp = None if ids is None else np.ascontiguousarray(ids, np.int64).ctypes.data
+    lib(native).orc_ivf_search(X, idp, X.shape[1], Cn, Cn.shape[0],
+                               np.ascontiguousarray(list_off, np.int64),
+                               np.ascontiguousarray(list_rows, np.int64), Q, nq, nprobe, k,
+                               strategy, 1 if literal else 0, d, i, cnt, nthreads)
+    return d, i, cnt
+
+
+def select_clusters(q, Cn, nprobe):
+    q, Cn = f32(q), f32(Cn)
+    out = np.full(min(nprobe, Cn.shape[0]), -1, np.int32)
+    lib().orc_ivf_select_clusters(q, q.shape[0], Cn, Cn.shape[0], nprobe, out)
+    return out
+
+
+class Hnsw:
+    def __init__(self, dim, m=16, ef_construction=64, ef_search=40, ml=0.36, capacity=0, native=False):
+        self.l = lib(native)
+        self.dim, self.m = dim, m
+        self.h = self.l.orc_hnsw_create(dim, m, ef_construction, ef_search, ml, capacity)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.l.orc_hnsw_free(self.h)
+            self.h = None
+
+    def build(self, X, levels, mode=0):
+        X = f32(X)
+        lv = np.ascontiguousarray(levels, np.int32)
+        self.l.orc_hnsw_build(self.h, X, X.shape[0], lv.ctypes.data, mode)
+
+    def search(self, Q, ef, k, strategy=L2, search_mode=0, nthreads=8):
+        Q = f32(Q)
+        nq = Q.shape[0]
+        nodes = np.empty((nq, k), np.uint32)
+        d = np.empty((nq, k), np.float32)
+        cnt = np.empty(nq, np.int32)
+        self.l.orc_hnsw_search(self.h, Q, nq, strategy, ef, k, search_mode, nodes, d, cnt, nthreads)
+        return d, nodes, cnt
+
+    def distance_evals(self):
+        return self.l.orc_hnsw_distance_evals()
+
+    def export(self):
+        n = self.l.orc_hnsw_size(self.h)
+        levels = np.empty(n, np.int32)
+        nbr0 = np.empty((n, 2 * self.m), np.uint32)
+        cnt = np.empty((n, 16), np.int16)
+        uoff = np.empty(n + 1, np.int64)
+        upper = np.empty(max(1, self.l.orc_hnsw_upper_slots(self.h)), np.uint32)
+        self.l.orc_hnsw_export(self.h, levels, nbr0, cnt, uoff, upper)
+        ep, el, ml = C.c_uint32(), C.c_int(), C.c_int()
+        self.l.orc_hnsw_meta(self.h, C.byref(ep), C.byref(el), C.byref(ml))
+        return dict(levels=levels, nbr0=nbr0, cnt=cnt, upper_off=uoff, upper=upper,
+                    entry_point=ep.value, entry_level=el.value, max_level=ml.value)
+
+
+def hnsw_levels(n, ml=0.36, seed=42):
+    """hnswGetRandomLevel over libc random(), seeded (the reference never seeds: SURVEY Q14)."""
+    libc = C.CDLL(None)
+    libc.srandom(C.c_uint(seed))
+    l = lib()
+    return np.array([l.orc_hnsw_random_level(ml) for _ in range(n)], np.int32)
+
+
+def recall_at_k(found, truth):
+    found = np.ascontiguousarray(found, np.int64)
+    truth = np.ascontiguousarray(truth, np.int64)
+    return lib().orc_recall_at_k(found, truth, found.shape[0], found.shape[1])
+
+
+def merge_topk(dist, ids):
+    dist = f32(dist); ids = np.ascontiguousarray(ids, np.int64)
+    s, nq, k = dist.shape
+    od = np.empty((nq, k), np.float32); oi = np.empty((nq, k), np.int64)
+    lib().orc_merge_topk(dist, ids, s, nq, k, od, oi)
+    return od, oi
+
+
+# ---- the reference itself (operator distances), compiled under oracle/pgshim ------------
+def ref_lib(avx2=False):
+    name = "libndb_ref_distance_avx2.so" if avx2 else "libndb_ref_distance.so"
+    path = os.path.join(ORACLE_DIR, "_ref", name)
+    if not os.path.exists(path):
+        return None
+    key = "ref:" + name
+    if key not in _LIBS:
+        l = C.CDLL(path)
+        l.ndb_ref_distance.restype = C.c_int
+        l.ndb_ref_distance.argtypes = [C.c_int, _f32p, C.c_int, _f32p, C.c_int, C.POINTER(C.c_float)]
+        l.ndb_ref_distance_pairs.restype = C.c_int
+        l.ndb_ref_distance_pairs.argtypes = [C.c_int, _f32p, _f32p, _f32p, C.c_long, C.c_int]
+        l.ndb_ref_last_error.restype = C.c_char_p
+        l.ndb_ref_table_create.restype = C.c_void_p
+        l.ndb_ref_table_create.argtypes = [_f32p, C.c_long, C.c_int]
+        l.ndb_ref_table_free.restype = None
+        l.ndb_ref_table_free.argtypes = [C.c_void_p]
+        l.ndb_ref_seqscan.restype = C.c_int
+        l.ndb_ref_seqscan.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p]
+        _LIBS[key] = l
+    return _LIBS[key]
+
+
+def ref_distance(metric, a, b, avx2=False):
+    """Returns (rc, value, error message) from the reference's fmgr function."""
+    l = ref_lib(avx2)
+    a, b = f32(a), f32(b)
+    out = C.c_float(0)
+    rc = l.ndb_ref_distance(metric, a if a.size else np.zeros(1, np.float32), a.size,
+                            b if b.size else np.zeros(1, np.float32), b.size, C.byref(out))
+    return rc, out.value, (l.ndb_ref_last_error() or b"").decode()
+
+
+def ref_distance_pairs(metric, A, B, avx2=False):
+    l = ref_lib(avx2)
+    A, B = f32(A), f32(B)
+    out = np.empty(A.shape[0], np.float32)
+    rc = l.ndb_ref_distance_pairs(metric, A, B, out, A.shape[0], A.shape[1])
+    assert rc == 0, l.ndb_ref_last_error()
+    return out
