@@ -1,0 +1,31 @@
+# Top-level build: libndb_b200.so (sm_100a only) + the oracle (test infrastructure).
+NVCC      ?= /usr/local/cuda/bin/nvcc
+HOSTCXX   ?= /usr/bin/g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -ccbin $(HOSTCXX) \
+             --expt-relaxed-constexpr -Xptxas -warn-spills
+SRCDIR    := neurondb_b200/csrc
+LIBDIR    := neurondb_b200/lib
+OBJDIR    := build/obj
+SRCS      := $(wildcard $(SRCDIR)/*.cu)
+OBJS      := $(patsubst $(SRCDIR)/%.cu,$(OBJDIR)/%.o,$(SRCS))
+HDRS      := $(wildcard $(SRCDIR)/*.cuh) include/ndb_b200.h
+
+all: $(LIBDIR)/libndb_b200.so oracle
+
+$(OBJDIR)/%.o: $(SRCDIR)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIBDIR)/libndb_b200.so: $(OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $@ $(OBJS)
+
+oracle:
+	$(MAKE) -s -C oracle
+
+clean:
+	rm -rf build $(LIBDIR)/*.so
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

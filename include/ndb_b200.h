@@ -1,0 +1,224 @@
+/*
+ * ndb_b200.h -- C ABI of the B200-native vector-search hot path for NeuronDB.
+ *
+ * This is the drop-in boundary: a C-ABI shared library
+ * (neurondb_b200/lib/libndb_b200.so) with plain pointers and sizes.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference
+ * repository root).  INTEGRATION.md shows the reference-side binding: the
+ * `ndb_gpu_backend` vtable instance and the index-AM call sites.
+ *
+ * Conventions (the reference's own, NeuronDB/include/neurondb_gpu_backend.h:24-27):
+ *   - return 0 on success, a negative NDB_B200_E* code on failure; never throws, never
+ *     ereport()s; the caller turns a failure into ereport(ERROR).  There is NO CPU
+ *     fallback: a missing GPU is NDB_B200_ENOTINIT / NDB_B200_ECUDA.
+ *   - all `const float *` / output arguments without a `_dev` suffix are HOST pointers,
+ *     row-major fp32, caller-owned; they are copied in/out before the call returns and
+ *     never retained.  `_dev` entry points take DEVICE pointers and a cudaStream_t
+ *     (passed as void *) and return without synchronising.
+ *   - handles are opaque, owned by the library, freed explicitly or at shutdown; one
+ *     handle may be used by one thread at a time (one PostgreSQL backend = one thread).
+ *   - k-nearest results are sorted by (distance ASC, id ASC), the reference's only
+ *     explicit tie rule (NeuronDB/src/util/distributed.c:425-438); missing results are
+ *     (+inf, -1).
+ *   - "arith" selects which of the reference's arithmetic variants is reproduced
+ *     bit for bit (see NDB_ARITH_*); NDB_ARITH_FAST / NDB_ARITH_TENSOR are the
+ *     tolerance-bounded fast paths (1e-5 / 1e-3 relative, BASELINE.json north_star).
+ */
+#ifndef NDB_B200_H
+#define NDB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDB_B200_ABI_VERSION 1
+
+/* error codes */
+#define NDB_B200_OK        0
+#define NDB_B200_EINVAL   (-1)   /* bad argument (NULL, n <= 0, k out of range ...)          */
+#define NDB_B200_ECUDA    (-2)   /* CUDA runtime failure; see ndb_b200_last_error()          */
+#define NDB_B200_ENOTINIT (-3)   /* ndb_b200_init() not called / no device                   */
+#define NDB_B200_EVECTOR  (-4)   /* NaN/Inf in a vector (vector_distance.c:55-73 raises)     */
+#define NDB_B200_EDIM     (-5)   /* dimension mismatch (vector_distance.c:42-47)             */
+#define NDB_B200_ENOMEM   (-6)
+#define NDB_B200_ESTATE   (-7)   /* index not trained / empty / wrong handle kind            */
+#define NDB_B200_ERANGE   (-8)   /* result NaN/Inf (vector_distance.c:117-120)               */
+
+/* metrics: the AMs' sk_strategy numbering (hnsw_am.c:1312-1337, ivf_am.c:1561-1591) */
+#define NDB_L2      1
+#define NDB_COSINE  2
+#define NDB_IP      3
+
+/* arithmetic variants of the reference that the kernels reproduce bit for bit */
+#define NDB_ARITH_OP_F64   0  /* <->,<=>,<#> default build: fp64, Kahan for L2
+                                 (src/vector/vector_distance.c:93-122,145-157,180-213);
+                                 <#> yields +dot (vector_distance_simd.c:557)                  */
+#define NDB_ARITH_IVF_F32  3  /* ivfComputeDistance: f32 sequential (ivf_am.c:1550-1592);
+                                 NDB_IP = -dot f32 sequential (not in the reference, Q5)     */
+#define NDB_ARITH_HNSW     4  /* hnswComputeDistance: f32 op, f64 accumulate
+                                 (hnsw_am.c:1301-1345)                                        */
+#define NDB_ARITH_FAST     5  /* fp32 FFMA, several accumulators: <= 1e-5 relative          */
+#define NDB_ARITH_TENSOR   6  /* bf16 tcgen05 tiles, fp32 accumulate: <= 1e-3 relative      */
+
+/* IVF search modes */
+#define NDB_IVF_FULL     0    /* scan every probed list completely                             */
+#define NDB_IVF_LITERAL  1    /* ivfCollectCandidates as written: stop after k*10 candidates in
+                                 probe order, selection-sort ties (ivf_am.c:1743,1861-1881)   */
+/* HNSW search / build modes */
+#define NDB_HNSW_BESTFIRST 1  /* search_layer with beam ef (what hnsw_scan.c intends)        */
+#define NDB_HNSW_LITERAL   0  /* hnswSearch as written: BFS until ef candidates (Q12)        */
+
+typedef struct ndb_b200_dataset ndb_b200_dataset;   /* rows resident in HBM (seq-scan target)  */
+typedef struct ndb_b200_ivf     ndb_b200_ivf;       /* IVF index: centroids + inverted lists   */
+typedef struct ndb_b200_hnsw    ndb_b200_hnsw;      /* HNSW graph                              */
+
+/* ---- lifecycle: ndb_gpu_backend.init/.shutdown/.is_available/.device_count/.set_device
+ *      (include/neurondb_gpu_backend.h:38-45; CUDA instance src/gpu/cuda/gpu_backend_cuda.c:162-260) */
+int         ndb_b200_init(int device);
+void        ndb_b200_shutdown(void);
+int         ndb_b200_is_available(void);
+int         ndb_b200_device_count(void);
+int         ndb_b200_abi_version(void);
+const char *ndb_b200_last_error(void);
+/* device facts for NDBGpuDeviceInfo (include/neurondb_gpu_types.h) */
+int         ndb_b200_device_info(int device, char *name, size_t name_len, size_t *total_mem,
+                                 size_t *free_mem, int *cc_major, int *cc_minor, int *sm_count);
+/* ndb_gpu_backend.mem_alloc/.mem_free/.memcpy_h2d/.memcpy_d2h (neurondb_gpu_backend.h:48-51) */
+int         ndb_b200_mem_alloc(void **ptr, size_t bytes);
+int         ndb_b200_mem_free(void *ptr);
+int         ndb_b200_memcpy_h2d(void *dst, const void *src, size_t bytes);
+int         ndb_b200_memcpy_d2h(void *dst, const void *src, size_t bytes);
+int         ndb_b200_host_alloc_pinned(void **ptr, size_t bytes);
+int         ndb_b200_host_free_pinned(void *ptr);
+/* ndb_gpu_backend.stream_create/.stream_destroy/.stream_synchronize (:351-353) */
+int         ndb_b200_stream_create(void **stream);
+int         ndb_b200_stream_destroy(void *stream);
+int         ndb_b200_stream_synchronize(void *stream);
+
+/* ---- b2 vtable launchers: paired rows, out[i] = dist(A_i, B_i), host pointers
+ *      .launch_l2_distance / .launch_cosine (neurondb_gpu_backend.h:54-65; replaces the
+ *      per-pair cuBLAS path gpu_backend_cuda.c:387-537).  fp32, sqrtf; cosine clamps to
+ *      [-1,1] and returns 1.0 on a non-positive norm, as the CUDA backend does (:518-529). */
+int ndb_b200_launch_l2_distance(const float *A, const float *B, float *out, int n, int d, void *stream);
+int ndb_b200_launch_cosine(const float *A, const float *B, float *out, int n, int d, void *stream);
+/* .launch_kmeans_assign / .launch_kmeans_update (:66-79; gpu_kmeans_kernels.cu:53-155,
+ * gpu_backend_cuda.c:677-710): argmin squared L2 with strict <, per-cluster mean */
+int ndb_b200_launch_kmeans_assign(const float *X, const float *C, int *idx, int n, int d, int k, void *stream);
+int ndb_b200_launch_kmeans_update(const float *X, const int *idx, float *C, int n, int d, int k, void *stream);
+
+/* ---- operator backends: vector_l2_distance_op / vector_cosine_distance_op /
+ *      vector_inner_product_distance_op (src/index/opclass.c:53-161) and the SQL batch
+ *      functions vector_*_distance_batch / vector_*_distance_gpu (src/vector/vector_batch.c:37-160,
+ *      src/gpu/common/gpu_sql.c:90-160), n pairs at once.  NDB_B200_EVECTOR on NaN/Inf input. */
+int ndb_b200_distance_pairs(int metric, int arith, const float *A, const float *B, float *out,
+                            int64_t n, int dim);
+/* one query against n rows (ORDER BY v <-> q without LIMIT; neurondb_gpu_batch_l2_distance,
+ * src/gpu/common/gpu_batch.c:55-81) */
+int ndb_b200_distance_rows(int metric, int arith, const float *X, int64_t n, int dim,
+                           const float *q, float *out);
+
+/* ---- dataset: the heap column a SeqScan reads ------------------------------- */
+int ndb_b200_dataset_create(int dim, ndb_b200_dataset **out);
+int ndb_b200_dataset_append(ndb_b200_dataset *ds, const float *rows, const int64_t *ids, int64_t n);
+int ndb_b200_dataset_append_dev(ndb_b200_dataset *ds, const float *rows_dev, const int64_t *ids_dev,
+                                int64_t n, void *stream);
+int64_t ndb_b200_dataset_size(const ndb_b200_dataset *ds);
+void ndb_b200_dataset_free(ndb_b200_dataset *ds);
+/* exact kNN = SeqScan + top-N sort over `metric` evaluated with `arith`
+ * (SELECT ... ORDER BY v <-> q LIMIT k; opclass.c:53-83 -> vector_distance.c:93-122) */
+int ndb_b200_knn_exact(ndb_b200_dataset *ds, int metric, int arith, const float *Q, int nq, int k,
+                       float *dist, int64_t *ids);
+int ndb_b200_knn_exact_dev(ndb_b200_dataset *ds, int metric, int arith, const float *Q_dev, int nq,
+                           int k, float *dist_dev, int64_t *ids_dev, void *stream);
+
+/* ---- IVF k-means: kmeans_init/run/assign/update_centroids/compute_cost
+ *      (src/index/ivf_am.c:2070-2294).  Literal semantics: centroids := first k rows,
+ *      <= max_iter Lloyd steps, stop when |prevCost - cost| < tol, f32 sequential sums.
+ *      C is k*d, assign n, counts k (any may be NULL).  Returns iterations in *iters. */
+int ndb_b200_kmeans_train(const float *X, int n, int d, int k, int max_iter, float tol,
+                          float *C, int *assign, int *counts, int *iters, float *cost);
+
+/* ---- IVF index: ivfbuild / ivfinsert / ivfrescan+ivfgettuple (src/index/ivf_am.c) -------- */
+int ndb_b200_ivf_create(int dim, int nlists, int metric, ndb_b200_ivf **out);
+void ndb_b200_ivf_free(ndb_b200_ivf *ix);
+/* ivfbuild (:501-745): k-means on the first min(10000, nlists*100) rows (:580) */
+int ndb_b200_ivf_train(ndb_b200_ivf *ix, const float *rows, int64_t n);
+int ndb_b200_ivf_set_centroids(ndb_b200_ivf *ix, const float *C);          /* nlists*dim */
+int ndb_b200_ivf_get_centroids(const ndb_b200_ivf *ix, float *C);
+/* ivfinsert (:797-1167) for n rows in order: nearest centroid by sqrtf(sum f32 diff^2),
+ * strict < (:906-935), append to that list.  out_list (may be NULL) receives the list ids. */
+int ndb_b200_ivf_insert(ndb_b200_ivf *ix, const float *rows, const int64_t *ids, int64_t n, int *out_list);
+/* assignment only (the :906-935 loop), host in / host out */
+int ndb_b200_ivf_assign(const ndb_b200_ivf *ix, const float *rows, int64_t n, int *out_list);
+/* load an index relation image: block 0 = IvfMetaPageData, centroid page, list page chains
+ * (layouts ivf_am.c:75-106,241-261; PostgreSQL page header/line pointers).  Pages are staged
+ * through pinned memory and decoded on the device. */
+int ndb_b200_ivf_load_relation(ndb_b200_ivf *ix, const void *blocks, uint32_t nblocks);
+int64_t ndb_b200_ivf_size(const ndb_b200_ivf *ix);
+int ndb_b200_ivf_list_sizes(const ndb_b200_ivf *ix, int64_t *sizes /* nlists */);
+/* ivfrescan + ivfgettuple for a batch (:1439-1545,1911-2027): ivfSelectClusters (:1597-1717,
+ * always L2) then ivfCollectCandidates (:1722-1909) with the index metric.
+ * mode NDB_IVF_FULL | NDB_IVF_LITERAL; arith NDB_ARITH_IVF_F32 | _FAST | _TENSOR. */
+int ndb_b200_ivf_search(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, int k, int mode,
+                        int arith, float *dist, int64_t *ids);
+int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int nprobe, int k, int mode,
+                            int arith, float *dist_dev, int64_t *ids_dev, void *stream);
+/* ivfSelectClusters alone: probe lists per query, nq*nprobe ints, -1 = none (:1597-1717) */
+int ndb_b200_ivf_select_clusters(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, int *probes);
+/* multi-GPU: keep only the lists l with l % world == rank (lists partition across ranks,
+ * centroids stay replicated) -- call before insert/load */
+int ndb_b200_ivf_set_shard(ndb_b200_ivf *ix, int rank, int world);
+
+/* ---- HNSW: hnswbuild/hnswinsert/hnswInsertNode, hnswrescan/hnswgettuple/hnswSearch
+ *      (src/index/hnsw_am.c:343-538, 904-1056, 1545-2080, 2091-2670) ------------------------ */
+int ndb_b200_hnsw_create(int dim, int m, int ef_construction, int ef_search, int metric,
+                         ndb_b200_hnsw **out);
+void ndb_b200_hnsw_free(ndb_b200_hnsw *h);
+/* build from rows; node id = row index (the reference's BlockNumber - 1).  levels: optional
+ * n ints (hnswGetRandomLevel draws, :1143-1161); NULL = draw with libc random() seeded by seed.
+ * batch = insertion batch size (1 = the sequential algorithm, id-exact with the oracle). */
+int ndb_b200_hnsw_build(ndb_b200_hnsw *h, const float *rows, const int64_t *ids, int64_t n,
+                        const int *levels, unsigned seed, int batch);
+/* load a prebuilt graph (flat arrays as exported by the oracle / decoded from node pages) */
+int ndb_b200_hnsw_load_graph(ndb_b200_hnsw *h, const float *rows, const int64_t *ids, int64_t n,
+                             const int *levels, const uint32_t *nbr0, const int16_t *cnt,
+                             const int64_t *upper_off, const uint32_t *upper,
+                             uint32_t entry_point, int entry_level);
+int ndb_b200_hnsw_export_graph(const ndb_b200_hnsw *h, int *levels, uint32_t *nbr0, int16_t *cnt,
+                               int64_t *upper_off, uint32_t *upper, int64_t upper_cap,
+                               uint32_t *entry_point, int *entry_level);
+int64_t ndb_b200_hnsw_size(const ndb_b200_hnsw *h);
+/* load node pages (one HnswNodeData per 8 KB page, hnsw_am.c:124-181) + the meta page */
+int ndb_b200_hnsw_load_relation(ndb_b200_hnsw *h, const void *blocks, uint32_t nblocks);
+/* hnswSearch for a batch: strategy = metric (the AMs always pass 1, Q4), ef, k;
+ * out nodes are row ids (heap TIDs in the reference come from a second page read, :1025-1052) */
+int ndb_b200_hnsw_search(ndb_b200_hnsw *h, const float *Q, int nq, int strategy, int ef, int k,
+                         int mode, float *dist, int64_t *ids);
+int ndb_b200_hnsw_search_dev(ndb_b200_hnsw *h, const float *Q_dev, int nq, int strategy, int ef, int k,
+                             int mode, float *dist_dev, int64_t *ids_dev, void *stream);
+/* distance evaluations of the last search batch (for the bytes-per-query roofline) */
+int64_t ndb_b200_hnsw_last_evals(const ndb_b200_hnsw *h);
+
+/* ---- multi-GPU merge: merge_distributed_results (src/util/distributed.c:320-487) ---------
+ * dist/ids are [nshards][nq][k] device arrays (the NCCL all-gather result); output [nq][k]
+ * sorted by (dist, id). */
+int ndb_b200_merge_topk_dev(const float *dist_dev, const int64_t *ids_dev, int nshards, int nq, int k,
+                            float *out_dist_dev, int64_t *out_ids_dev, void *stream);
+int ndb_b200_merge_topk(const float *dist, const int64_t *ids, int nshards, int nq, int k,
+                        float *out_dist, int64_t *out_ids);
+
+/* ---- instrumentation --------------------------------------------------------------------- */
+/* kernels launched by this library since init (bench.py's gpu_launches) */
+int64_t ndb_b200_launch_count(void);
+/* device time (ms, CUDA events on the library's stream) of the dominant kernel of the last
+ * search call and the algorithmic bytes it streamed; 0 if timing is disabled */
+int ndb_b200_set_timing(int enabled);
+int ndb_b200_last_kernel_stats(double *ms, double *algo_bytes, int64_t *distance_evals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDB_B200_H */

@@ -1,0 +1,313 @@
+"""Host-side mirror of the reference's interface for the vector-search hot path.
+
+Names follow the reference (NeuronDB/src/index/ivf_am.c, hnsw_am.c, opclass.c): the operator
+procedures, `ivfbuild` / `ivfinsert` / `ivfgettuple`-style index objects.  Everything here calls
+the C ABI in include/ndb_b200.h; nothing is computed in Python and there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import (ARITH_FAST, ARITH_HNSW, ARITH_IVF_F32, ARITH_OP_F64, COSINE, HNSW_BESTFIRST, HNSW_LITERAL, IP,
+                   IVF_FULL, IVF_LITERAL, L2, NdbError, check, f32, ptr)
+
+_initialised = {"device": None}
+
+
+def init(device=0):
+    check(L.load().ndb_b200_init(device))
+    _initialised["device"] = device
+
+
+def shutdown():
+    L.load().ndb_b200_shutdown()
+    _initialised["device"] = None
+
+
+def is_available():
+    return bool(L.load().ndb_b200_is_available())
+
+
+def launch_count():
+    return int(L.load().ndb_b200_launch_count())
+
+
+def set_timing(on):
+    check(L.load().ndb_b200_set_timing(1 if on else 0))
+
+
+def last_kernel_stats():
+    ms, b, ev = C.c_double(), C.c_double(), C.c_int64()
+    check(L.load().ndb_b200_last_kernel_stats(C.byref(ms), C.byref(b), C.byref(ev)))
+    return ms.value, b.value, ev.value
+
+
+# ---- operator procedures (opclass.c:53-161): <->, <=>, <#> over n pairs ------------------------
+def distance_pairs(A, B, metric=L2, arith=ARITH_OP_F64):
+    A, B = f32(A), f32(B)
+    if A.ndim == 1:
+        A, B = A[None, :], B[None, :]
+    if A.shape != B.shape:
+        raise NdbError(-5, "vector dimensions must match: %s vs %s" % (A.shape, B.shape))
+    out = np.empty(A.shape[0], np.float32)
+    check(L.load().ndb_b200_distance_pairs(metric, arith, ptr(A), ptr(B), ptr(out), A.shape[0], A.shape[1]))
+    return out
+
+
+def vector_l2_distance_op(a, b):
+    return distance_pairs(a, b, L2)
+
+
+def vector_cosine_distance_op(a, b):
+    return distance_pairs(a, b, COSINE)
+
+
+def vector_inner_product_distance_op(a, b):
+    return distance_pairs(a, b, IP)
+
+
+def distance_rows(X, q, metric=L2, arith=ARITH_OP_F64):
+    X, q = f32(X), f32(q)
+    out = np.empty(X.shape[0], np.float32)
+    check(L.load().ndb_b200_distance_rows(metric, arith, ptr(X), X.shape[0], X.shape[1], ptr(q), ptr(out)))
+    return out
+
+
+# ---- ndb_gpu_backend launchers (neurondb_gpu_backend.h:54-79) -----------------------------------
+def launch_l2_distance(A, B):
+    A, B = f32(A), f32(B)
+    out = np.empty(A.shape[0], np.float32)
+    check(L.load().ndb_b200_launch_l2_distance(ptr(A), ptr(B), ptr(out), A.shape[0], A.shape[1], None))
+    return out
+
+
+def launch_cosine(A, B):
+    A, B = f32(A), f32(B)
+    out = np.empty(A.shape[0], np.float32)
+    check(L.load().ndb_b200_launch_cosine(ptr(A), ptr(B), ptr(out), A.shape[0], A.shape[1], None))
+    return out
+
+
+def launch_kmeans_assign(X, Cn):
+    X, Cn = f32(X), f32(Cn)
+    idx = np.empty(X.shape[0], np.int32)
+    check(L.load().ndb_b200_launch_kmeans_assign(ptr(X), ptr(Cn), ptr(idx), X.shape[0], X.shape[1], Cn.shape[0], None))
+    return idx
+
+
+def launch_kmeans_update(X, idx, k):
+    X = f32(X)
+    idx = np.ascontiguousarray(idx, np.int32)
+    Cn = np.zeros((k, X.shape[1]), np.float32)
+    check(L.load().ndb_b200_launch_kmeans_update(ptr(X), ptr(idx), ptr(Cn), X.shape[0], X.shape[1], k, None))
+    return Cn
+
+
+def kmeans_train(X, k, max_iter=50, tol=0.001):
+    """kmeans_init + kmeans_run (ivf_am.c:2070-2159). Returns (C, assign, counts, iters, cost)."""
+    X = f32(X)
+    n, d = X.shape
+    Cn = np.zeros((k, d), np.float32)
+    assign = np.zeros(n, np.int32)
+    counts = np.zeros(k, np.int32)
+    iters, cost = C.c_int(), C.c_float()
+    check(L.load().ndb_b200_kmeans_train(ptr(X), n, d, k, max_iter, tol, ptr(Cn), ptr(assign), ptr(counts),
+                                         C.byref(iters), C.byref(cost)))
+    return Cn, assign, counts, iters.value, cost.value
+
+
+def merge_topk(dist, ids):
+    dist = f32(dist)
+    ids = np.ascontiguousarray(ids, np.int64)
+    s, nq, k = dist.shape
+    od = np.empty((nq, k), np.float32)
+    oi = np.empty((nq, k), np.int64)
+    check(L.load().ndb_b200_merge_topk(ptr(dist), ptr(ids), s, nq, k, ptr(od), ptr(oi)))
+    return od, oi
+
+
+class _Handle:
+    _free = None
+
+    def __init__(self):
+        self.h = C.c_void_p()
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            getattr(L.load(), self._free)(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Dataset(_Handle):
+    """The heap column a SeqScan reads; exact kNN = ORDER BY v <op> q LIMIT k."""
+    _free = "ndb_b200_dataset_free"
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+        check(L.load().ndb_b200_dataset_create(dim, C.byref(self.h)))
+
+    def append(self, rows, ids=None):
+        rows = f32(rows)
+        idp = None if ids is None else np.ascontiguousarray(ids, np.int64)
+        check(L.load().ndb_b200_dataset_append(self.h, ptr(rows), ptr(idp), rows.shape[0]))
+
+    def append_dev(self, rows_ptr, n, ids_ptr=None, stream=None):
+        check(L.load().ndb_b200_dataset_append_dev(self.h, ptr(rows_ptr), ptr(ids_ptr), n, ptr(stream)))
+
+    def __len__(self):
+        return int(L.load().ndb_b200_dataset_size(self.h))
+
+    def knn(self, Q, k, metric=L2, arith=ARITH_OP_F64):
+        Q = f32(Q)
+        d = np.empty((Q.shape[0], k), np.float32)
+        i = np.empty((Q.shape[0], k), np.int64)
+        check(L.load().ndb_b200_knn_exact(self.h, metric, arith, ptr(Q), Q.shape[0], k, ptr(d), ptr(i)))
+        return d, i
+
+    def knn_dev(self, q_ptr, nq, k, dist_ptr, ids_ptr, metric=L2, arith=ARITH_OP_F64, stream=None):
+        check(L.load().ndb_b200_knn_exact_dev(self.h, metric, arith, ptr(q_ptr), nq, k, ptr(dist_ptr), ptr(ids_ptr),
+                                              ptr(stream)))
+
+
+class IvfIndex(_Handle):
+    """CREATE INDEX ... USING ivf (v vector_l2_ops) WITH (lists = L)  (ivf_am.c)."""
+    _free = "ndb_b200_ivf_free"
+
+    def __init__(self, dim, lists=100, metric=L2):
+        super().__init__()
+        self.dim, self.lists, self.metric = dim, lists, metric
+        check(L.load().ndb_b200_ivf_create(dim, lists, metric, C.byref(self.h)))
+
+    def set_shard(self, rank, world):
+        check(L.load().ndb_b200_ivf_set_shard(self.h, rank, world))
+
+    def ivfbuild(self, rows):
+        """ivfbuild (:501-745): k-means on the first min(10000, lists*100) rows; no list assignment (Q6)."""
+        rows = f32(rows)
+        check(L.load().ndb_b200_ivf_train(self.h, ptr(rows), rows.shape[0]))
+
+    def set_centroids(self, Cn):
+        Cn = f32(Cn)
+        assert Cn.shape == (self.lists, self.dim)
+        check(L.load().ndb_b200_ivf_set_centroids(self.h, ptr(Cn)))
+
+    def centroids(self):
+        Cn = np.empty((self.lists, self.dim), np.float32)
+        check(L.load().ndb_b200_ivf_get_centroids(self.h, ptr(Cn)))
+        return Cn
+
+    def ivfinsert(self, rows, ids=None):
+        """ivfinsert (:797-1167) for each row in order; returns the list id of every row."""
+        rows = f32(rows)
+        idp = None if ids is None else np.ascontiguousarray(ids, np.int64)
+        out = np.empty(rows.shape[0], np.int32)
+        check(L.load().ndb_b200_ivf_insert(self.h, ptr(rows), ptr(idp), rows.shape[0], ptr(out)))
+        return out
+
+    def assign(self, rows):
+        rows = f32(rows)
+        out = np.empty(rows.shape[0], np.int32)
+        check(L.load().ndb_b200_ivf_assign(self.h, ptr(rows), rows.shape[0], ptr(out)))
+        return out
+
+    def load_relation(self, blocks):
+        blocks = np.ascontiguousarray(blocks, np.uint8)
+        check(L.load().ndb_b200_ivf_load_relation(self.h, ptr(blocks), blocks.size // 8192))
+
+    def __len__(self):
+        return int(L.load().ndb_b200_ivf_size(self.h))
+
+    def list_sizes(self):
+        out = np.empty(self.lists, np.int64)
+        check(L.load().ndb_b200_ivf_list_sizes(self.h, ptr(out)))
+        return out
+
+    def select_clusters(self, Q, nprobe):
+        Q = f32(Q)
+        out = np.empty((Q.shape[0], nprobe), np.int32)
+        check(L.load().ndb_b200_ivf_select_clusters(self.h, ptr(Q), Q.shape[0], nprobe, ptr(out)))
+        return out
+
+    def search(self, Q, nprobe=10, k=10, mode=IVF_FULL, arith=ARITH_IVF_F32):
+        """ivfrescan + ivfgettuple for a batch of queries (:1439-1545, 1911-2027)."""
+        Q = f32(Q)
+        d = np.empty((Q.shape[0], k), np.float32)
+        i = np.empty((Q.shape[0], k), np.int64)
+        check(L.load().ndb_b200_ivf_search(self.h, ptr(Q), Q.shape[0], nprobe, k, mode, arith, ptr(d), ptr(i)))
+        return d, i
+
+    def search_dev(self, q_ptr, nq, dist_ptr, ids_ptr, nprobe=10, k=10, mode=IVF_FULL, arith=ARITH_IVF_F32,
+                   stream=None):
+        check(L.load().ndb_b200_ivf_search_dev(self.h, ptr(q_ptr), nq, nprobe, k, mode, arith, ptr(dist_ptr),
+                                               ptr(ids_ptr), ptr(stream)))
+
+
+class HnswIndex(_Handle):
+    """CREATE INDEX ... USING hnsw (v ...) WITH (m, ef_construction, ef_search)  (hnsw_am.c)."""
+    _free = "ndb_b200_hnsw_free"
+
+    def __init__(self, dim, m=16, ef_construction=200, ef_search=64, metric=L2):
+        super().__init__()
+        self.dim, self.m, self.efc, self.efs, self.metric = dim, m, ef_construction, ef_search, metric
+        check(L.load().ndb_b200_hnsw_create(dim, m, ef_construction, ef_search, metric, C.byref(self.h)))
+
+    def hnswbuild(self, rows, ids=None, levels=None, seed=0, batch=0):
+        rows = f32(rows)
+        idp = None if ids is None else np.ascontiguousarray(ids, np.int64)
+        lv = None if levels is None else np.ascontiguousarray(levels, np.int32)
+        check(L.load().ndb_b200_hnsw_build(self.h, ptr(rows), ptr(idp), rows.shape[0], ptr(lv), seed, batch))
+
+    def load_graph(self, rows, g, ids=None):
+        rows = f32(rows)
+        idp = None if ids is None else np.ascontiguousarray(ids, np.int64)
+        self._keep = [np.ascontiguousarray(g["levels"], np.int32), np.ascontiguousarray(g["nbr0"], np.uint32),
+                      np.ascontiguousarray(g["cnt"], np.int16), np.ascontiguousarray(g["upper_off"], np.int64),
+                      np.ascontiguousarray(g["upper"], np.uint32)]
+        lv, n0, cn, uo, up = self._keep
+        check(L.load().ndb_b200_hnsw_load_graph(self.h, ptr(rows), ptr(idp), rows.shape[0], ptr(lv), ptr(n0), ptr(cn),
+                                                ptr(uo), ptr(up), int(g["entry_point"]), int(g["entry_level"])))
+
+    def export_graph(self):
+        n = len(self)
+        levels = np.empty(n, np.int32)
+        nbr0 = np.empty((n, 2 * self.m), np.uint32)
+        cnt = np.empty((n, 16), np.int16)
+        uoff = np.empty(n + 1, np.int64)
+        cap = max(1, n * 2 * self.m)        # generous: sum(level) * 2m <= n * 2m for ml = 0.36
+        upper = np.empty(cap, np.uint32)
+        ep, el = C.c_uint32(), C.c_int()
+        check(L.load().ndb_b200_hnsw_export_graph(self.h, ptr(levels), ptr(nbr0), ptr(cnt), ptr(uoff), ptr(upper), cap,
+                                                  C.byref(ep), C.byref(el)))
+        return dict(levels=levels, nbr0=nbr0, cnt=cnt, upper_off=uoff, upper=upper[:max(1, int(uoff[n]))],
+                    entry_point=ep.value, entry_level=el.value)
+
+    def load_relation(self, blocks):
+        blocks = np.ascontiguousarray(blocks, np.uint8)
+        check(L.load().ndb_b200_hnsw_load_relation(self.h, ptr(blocks), blocks.size // 8192))
+
+    def __len__(self):
+        return int(L.load().ndb_b200_hnsw_size(self.h))
+
+    def search(self, Q, ef=None, k=10, strategy=None, mode=HNSW_BESTFIRST):
+        """hnswrescan + hnswgettuple for a batch (:904-1056); ef defaults to the index's ef_search."""
+        Q = f32(Q)
+        d = np.empty((Q.shape[0], k), np.float32)
+        i = np.empty((Q.shape[0], k), np.int64)
+        check(L.load().ndb_b200_hnsw_search(self.h, ptr(Q), Q.shape[0], strategy or self.metric, ef or self.efs, k,
+                                            mode, ptr(d), ptr(i)))
+        return d, i
+
+    def search_dev(self, q_ptr, nq, dist_ptr, ids_ptr, ef=None, k=10, strategy=None, mode=HNSW_BESTFIRST, stream=None):
+        check(L.load().ndb_b200_hnsw_search_dev(self.h, ptr(q_ptr), nq, strategy or self.metric, ef or self.efs, k, mode,
+                                                ptr(dist_ptr), ptr(ids_ptr), ptr(stream)))
+
+    def last_evals(self):
+        return int(L.load().ndb_b200_hnsw_last_evals(self.h))

@@ -1,0 +1,623 @@
+// ivf.cu -- IVF index: ivfbuild (train), ivfinsert (assign + append), ivfrescan/ivfgettuple
+// (ivfSelectClusters + ivfCollectCandidates) of NeuronDB/src/index/ivf_am.c, for query batches.
+//
+// Device layout.  Centroids: one IL32 store of nlists vectors (replicated on every rank).
+// Inverted lists: one IL32 store; list l occupies the 32-vector blocks
+// [list_blk[l], list_blk[l] + ceil(len/32)), entries sorted by id inside a list so that the
+// (dist, slot) order the scan keeps equals the (dist, id) order inside one list.  ids[] maps
+// slot -> heap id; lit_order[] maps (list, j-th inserted) -> slot for the literal mode, whose
+// candidate cut-off depends on insertion (page/offset) order.
+//
+// Search = 4 launches on one stream, no host round trip:
+//   1. dense scan queries x centroids, k = nprobe, always L2          (ivfSelectClusters :1597-1717)
+//   2. bucket the (query, probed list) pairs by list -> work items     (build_items_*)
+//   3. list-mode scan: each list block is fetched once per 8 queries   (ivfCollectCandidates :1722-1909)
+//   4. merge the nprobe partial top-k lists per query by (dist, id)
+#include "kmeans.cuh"
+#include "scan.cuh"
+
+#include <algorithm>
+#include <numeric>
+#include <cub/block/block_scan.cuh>
+
+using namespace ndb;
+
+struct ndb_b200_ivf {
+    int dim = 0, dimp = 0, nlists = 0, metric = NDB_L2;
+    bool trained = false;
+    int rank = 0, world = 1;
+    std::vector<float> C_host;
+    KMeansWork kw;                       // kw.C = centroids row-major on device, kw.cstore = IL32
+    // arena: rows kept by this shard, row-major, insertion order
+    DevBuf arena;
+    int64_t nrows = 0;
+    std::vector<int64_t> row_id;
+    std::vector<int32_t> row_list;
+    // laid-out lists
+    bool dirty = true;
+    VecStore store;
+    DevBuf ids, vnorm_ivf, vnorm_fast, lit_order, d_list_len, d_list_blk;
+    bool vnorm_ivf_ok = false, vnorm_fast_ok = false;
+    std::vector<uint32_t> list_len, list_blk;
+    // scratch
+    ScanScratch cscr, scr;
+    DevBuf probe, cnt, fill, qoff, item_off, qmap, items, nitems, stats, tmp_rows, tmp_assign, tmp_keep;
+    DevBuf qbuf, outd, outi, cdist;
+    int64_t last_scanned = 0;
+};
+
+namespace ndb {
+
+// ---- work-item construction -----------------------------------------------------------------
+__global__ void ivf_hist_kernel(const uint32_t *__restrict__ probe, int64_t npairs, const uint32_t *__restrict__ list_len,
+                                int nlists, uint32_t *__restrict__ cnt)
+{
+    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const uint32_t l = probe[p];
+    if (l < (uint32_t) nlists && list_len[l] > 0) atomicAdd(&cnt[l], 1u);
+}
+
+// single CTA: exclusive scans of cnt (-> qoff) and of ceil(cnt/QT) (-> item_off); totals
+__global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ list_len,
+                                                           int nlists, int qt, uint32_t *__restrict__ qoff,
+                                                           uint32_t *__restrict__ item_off, uint32_t *__restrict__ nitems,
+                                                           unsigned long long *__restrict__ scanned)
+{
+    typedef cub::BlockScan<uint32_t, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ unsigned long long s_scanned;
+    const int ipt = (nlists + 1023) / 1024;
+    const int b = threadIdx.x * ipt, e = min(nlists, b + ipt);
+    if (threadIdx.x == 0) s_scanned = 0;
+    uint32_t sq = 0, st = 0;
+    unsigned long long sc = 0;
+    for (int l = b; l < e; l++) {
+        sq += cnt[l];
+        st += (cnt[l] + qt - 1) / qt;
+        sc += (unsigned long long) cnt[l] * list_len[l];
+    }
+    uint32_t oq, ot;
+    Scan(tmp).ExclusiveSum(sq, oq);
+    __syncthreads();
+    Scan(tmp).ExclusiveSum(st, ot);
+    __syncthreads();
+    atomicAdd(&s_scanned, sc);
+    for (int l = b; l < e; l++) {
+        qoff[l] = oq;
+        item_off[l] = ot;
+        oq += cnt[l];
+        ot += (cnt[l] + qt - 1) / qt;
+    }
+    if (threadIdx.x == 1023) *nitems = ot;   // last thread's running total == grand total
+    __syncthreads();
+    if (threadIdx.x == 0) *scanned = s_scanned;
+}
+
+__global__ void ivf_scatter_kernel(const uint32_t *__restrict__ probe, int64_t npairs, const uint32_t *__restrict__ list_len,
+                                   int nlists, const uint32_t *__restrict__ qoff, uint32_t *__restrict__ fill,
+                                   uint32_t *__restrict__ qmap)
+{
+    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const uint32_t l = probe[p];
+    if (l < (uint32_t) nlists && list_len[l] > 0) qmap[qoff[l] + atomicAdd(&fill[l], 1u)] = (uint32_t) p;
+}
+
+__global__ void ivf_items_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ qoff,
+                                 const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len,
+                                 const uint32_t *__restrict__ list_blk, int nlists, int qt, WorkItem *__restrict__ items)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlists) return;
+    const uint32_t c = cnt[l];
+    const uint32_t tiles = (c + qt - 1) / qt;
+    for (uint32_t t = 0; t < tiles; t++) {
+        WorkItem it;
+        it.blk_begin = list_blk[l];
+        it.nvec = list_len[l];
+        it.qoff = qoff[l] + t * qt;
+        it.nq = min((uint32_t) qt, c - t * qt);
+        it.part = 0;
+        items[item_off[l] + t] = it;
+    }
+}
+
+// ---- literal ivfCollectCandidates (:1722-1909): warp per query ----------------------------------
+// candidates = the first k*10 entries met walking the probed lists in probe order and each
+// list in insertion order; then the reference's selection sort over an index array (strict <,
+// swap), which fixes the order of exact ties.
+template <class P>
+__global__ void __launch_bounds__(128) ivf_literal_kernel(const float4 *__restrict__ vecs, const float *__restrict__ vnorm,
+                                                          const float *__restrict__ Q, const uint32_t *__restrict__ probe,
+                                                          const uint32_t *__restrict__ list_len, const uint32_t *__restrict__ list_blk,
+                                                          const uint32_t *__restrict__ lit_order, const int64_t *__restrict__ ids,
+                                                          int nq, int nprobe, int nlists, int dim, int dimp, int k,
+                                                          float *__restrict__ out_dist, int64_t *__restrict__ out_ids)
+{
+    extern __shared__ unsigned char lit_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q = blockIdx.x * 4 + w;
+    const int maxc = k * 10;
+    float *cd = reinterpret_cast<float *>(lit_smem) + (size_t) w * maxc;
+    uint32_t *cs = reinterpret_cast<uint32_t *>(lit_smem + sizeof(float) * 4 * (size_t) maxc) + (size_t) w * maxc;
+    int *idx = reinterpret_cast<int *>(lit_smem + 8 * 4 * (size_t) maxc) + (size_t) w * maxc;
+    if (q >= nq) return;
+    const float *qv = Q + (size_t) q * dim;
+    // gather candidate slots
+    int cc = 0;
+    for (int i = 0; i < nprobe && cc < maxc; i++) {
+        const uint32_t l = probe[(size_t) q * nprobe + i];
+        if (l >= (uint32_t) nlists) continue;
+        const uint32_t len = list_len[l], base = list_blk[l] * 32;
+        const int take = min((int) len, maxc - cc);
+        for (int j = lane; j < take; j += 32) cs[cc + j] = lit_order[base + j];
+        cc += take;
+    }
+    __syncwarp();
+    // distances: lane per candidate, sequential over the dimensions
+    typename P::N qn = 0;
+    if (P::NORMS) for (int j = 0; j < dim; j++) P::nstep(qn, qv[j]);
+    for (int c = lane; c < cc; c += 32) {
+        const uint32_t slot = cs[c];
+        const float4 *vp = vecs + (size_t) (slot >> 5) * (8 * (size_t) dimp) + (slot & 31);
+        typename P::Acc acc;
+        P::init(acc);
+        for (int j = 0; j < dim; j += 4) {
+            const float4 x = vp[(size_t) (j >> 2) * 32];
+            P::step(acc, x.x, qv[j]);
+            if (j + 1 < dim) P::step(acc, x.y, qv[j + 1]);
+            if (j + 2 < dim) P::step(acc, x.z, qv[j + 2]);
+            if (j + 3 < dim) P::step(acc, x.w, qv[j + 3]);
+        }
+        cd[c] = P::finish(acc, P::NORMS ? vnorm[slot] : 0, qn);
+        idx[c] = c;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const int actualK = min(k, cc);
+        for (int i = 0; i < actualK; i++) {
+            int bestIdx = i;
+            float bestDist = cd[idx[i]];
+            for (int j = i + 1; j < cc; j++)
+                if (cd[idx[j]] < bestDist) { bestDist = cd[idx[j]]; bestIdx = j; }
+            if (bestIdx != i) { const int t = idx[i]; idx[i] = idx[bestIdx]; idx[bestIdx] = t; }
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) {
+        const bool have = i < cc;
+        out_dist[(size_t) q * k + i] = have ? cd[idx[i]] : INFINITY;
+        out_ids[(size_t) q * k + i] = have ? ids[cs[idx[i]]] : -1;
+    }
+}
+
+__global__ void copy_kept_rows_kernel(const float *__restrict__ rows, const uint32_t *__restrict__ keep, int64_t nkeep,
+                                      int dim, float *__restrict__ arena)
+{
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nkeep * dim) return;
+    const int64_t i = t / dim;
+    const int j = (int) (t - i * dim);
+    arena[t] = rows[(size_t) keep[i] * dim + j];
+}
+
+static int ivf_sync_centroids(ndb_b200_ivf *ix, cudaStream_t s)
+{
+    NDB_CHECK(ix->kw.C.reserve((size_t) ix->nlists * ix->dim * 4));
+    NDB_CUDA(cudaMemcpyAsync(ix->kw.C.p, ix->C_host.data(), (size_t) ix->nlists * ix->dim * 4, cudaMemcpyHostToDevice, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    return NDB_B200_OK;
+}
+
+// (re)build the IL32 list store from the arena
+static int ivf_layout(ndb_b200_ivf *ix, cudaStream_t s)
+{
+    if (!ix->dirty) return NDB_B200_OK;
+    const int64_t n = ix->nrows;
+    const int L = ix->nlists;
+    ix->list_len.assign(L, 0);
+    for (int64_t r = 0; r < n; r++) ix->list_len[ix->row_list[r]]++;
+    ix->list_blk.assign(L, 0);
+    uint64_t blk = 0;
+    for (int l = 0; l < L; l++) {
+        ix->list_blk[l] = (uint32_t) blk;
+        blk += (ix->list_len[l] + 31) / 32;
+    }
+    NDB_REQUIRE(blk * 32 < 0xfffffff0ull, NDB_B200_EINVAL, "ivf: too many slots for 32-bit slot ids");
+    const int64_t nslots = (int64_t) blk * 32;
+    // rows of each list in insertion order, then ranked by id inside the list
+    std::vector<uint32_t> by_list(n);
+    {
+        std::vector<uint32_t> pos(L, 0);
+        std::vector<uint64_t> start(L + 1, 0);
+        for (int l = 0; l < L; l++) start[l + 1] = start[l] + ix->list_len[l];
+        for (int64_t r = 0; r < n; r++) {
+            const int l = ix->row_list[r];
+            by_list[start[l] + pos[l]++] = (uint32_t) r;
+        }
+        std::vector<uint32_t> slot_of_row(n);
+        std::vector<int64_t> ids_by_slot(nslots > 0 ? nslots : 1, -1);
+        std::vector<uint32_t> lit(nslots > 0 ? nslots : 1, INVALID_SLOT);
+        std::vector<uint32_t> order;
+        for (int l = 0; l < L; l++) {
+            const uint32_t len = ix->list_len[l];
+            const uint32_t *rows = by_list.data() + start[l];
+            order.assign(rows, rows + len);
+            bool sorted = true;
+            for (uint32_t j = 1; j < len && sorted; j++) sorted = ix->row_id[order[j - 1]] <= ix->row_id[order[j]];
+            if (!sorted)
+                std::stable_sort(order.begin(), order.end(),
+                                 [&](uint32_t a, uint32_t b) { return ix->row_id[a] < ix->row_id[b]; });
+            const uint32_t base = ix->list_blk[l] * 32;
+            for (uint32_t j = 0; j < len; j++) {
+                slot_of_row[order[j]] = base + j;
+                ids_by_slot[base + j] = ix->row_id[order[j]];
+            }
+            for (uint32_t j = 0; j < len; j++) lit[base + j] = slot_of_row[rows[j]];
+        }
+        ix->store.dim = ix->dim;
+        ix->store.dimp = ix->dimp;
+        ix->store.nblk = (int64_t) blk;
+        const size_t bytes = ix->store.bytes_for((int64_t) blk);
+        NDB_CHECK(ix->store.data.reserve(bytes ? bytes : 16));
+        NDB_CHECK(ix->ids.reserve((size_t) (nslots ? nslots : 1) * 8));
+        NDB_CHECK(ix->lit_order.reserve((size_t) (nslots ? nslots : 1) * 4));
+        NDB_CHECK(ix->tmp_assign.reserve((size_t) (n ? n : 1) * 4));
+        NDB_CHECK(ix->d_list_len.reserve((size_t) L * 4));
+        NDB_CHECK(ix->d_list_blk.reserve((size_t) L * 4));
+        if (bytes) NDB_CUDA(cudaMemsetAsync(ix->store.data.p, 0, bytes, s));
+        NDB_CUDA(cudaMemcpyAsync(ix->ids.p, ids_by_slot.data(), (size_t) (nslots ? nslots : 1) * 8, cudaMemcpyHostToDevice, s));
+        NDB_CUDA(cudaMemcpyAsync(ix->lit_order.p, lit.data(), (size_t) (nslots ? nslots : 1) * 4, cudaMemcpyHostToDevice, s));
+        if (n) NDB_CUDA(cudaMemcpyAsync(ix->tmp_assign.p, slot_of_row.data(), (size_t) n * 4, cudaMemcpyHostToDevice, s));
+        NDB_CUDA(cudaMemcpyAsync(ix->d_list_len.p, ix->list_len.data(), (size_t) L * 4, cudaMemcpyHostToDevice, s));
+        NDB_CUDA(cudaMemcpyAsync(ix->d_list_blk.p, ix->list_blk.data(), (size_t) L * 4, cudaMemcpyHostToDevice, s));
+        NDB_CHECK(il32_scatter(ix->arena.as<float>(), n, ix->dim, ix->dimp, ix->tmp_assign.as<uint32_t>(), 0,
+                               ix->store.ptr(), s));
+        NDB_CUDA(cudaStreamSynchronize(s));     // host vectors above go out of scope
+    }
+    ix->vnorm_ivf_ok = ix->vnorm_fast_ok = false;
+    ix->dirty = false;
+    return NDB_B200_OK;
+}
+
+static int ivf_vnorm(ndb_b200_ivf *ix, int arith, const void **out, cudaStream_t s)
+{
+    DevBuf &b = arith == NDB_ARITH_FAST ? ix->vnorm_fast : ix->vnorm_ivf;
+    bool &ok = arith == NDB_ARITH_FAST ? ix->vnorm_fast_ok : ix->vnorm_ivf_ok;
+    const int64_t nslots = ix->store.nblk * 32;
+    if (!ok) {
+        NDB_CHECK(b.reserve((size_t) (nslots ? nslots : 1) * 4));
+        NDB_CHECK(slot_norms(arith, ix->store.ptr(), nslots, ix->dim, ix->dimp, b.p, s));
+        ok = true;
+    }
+    *out = b.p;
+    return NDB_B200_OK;
+}
+
+// nearest centroid per row (ivfinsert :906-935): sqrtf'd L2, strict <, lowest index
+static int ivf_assign_dev(ndb_b200_ivf *ix, const float *d_rows, int64_t n, int *d_out, cudaStream_t s)
+{
+    return kmeans_assign_dev(ix->kw, d_rows, n, ix->dim, ix->nlists, NDB_L2, d_out, s);
+}
+
+// probe lists per query into ix->probe ([nq][np] uint32, INVALID_SLOT = none)
+static int ivf_coarse(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np, int arith, cudaStream_t s)
+{
+    const int carith = arith == NDB_ARITH_FAST ? NDB_ARITH_FAST : NDB_ARITH_IVF_F32;
+    int nparts = 1;
+    NDB_CHECK(dense_scan(ix->kw.cstore.as<float>(), nullptr, ix->nlists, ix->dim, ix->dimp, NDB_L2, carith, Q_dev, nq, np,
+                         ix->cscr, &nparts, s));
+    NDB_CHECK(ix->probe.reserve((size_t) nq * np * 4));
+    NDB_CHECK(ix->cdist.reserve((size_t) nq * np * 4));
+    return launch_merge_parts(ix->cscr.pdist.as<float>(), ix->cscr.pslot.as<uint32_t>(), nullptr, nq, nparts, np,
+                              ix->cdist.as<float>(), nullptr, ix->probe.as<uint32_t>(), s);
+}
+
+static int ivf_ready(ndb_b200_ivf *ix, cudaStream_t s)
+{
+    NDB_REQUIRE(ix->trained, NDB_B200_ESTATE, "ivf: index has no centroids (train or set_centroids first)");
+    NDB_CHECK(ivf_layout(ix, s));
+    return NDB_B200_OK;
+}
+
+}  // namespace ndb
+
+extern "C" {
+
+int ndb_b200_ivf_create(int dim, int nlists, int metric, ndb_b200_ivf **out)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(out && dim > 0 && dim <= 16000, NDB_B200_EINVAL, "ivf_create: dim must be 1..16000");
+    NDB_REQUIRE(nlists >= 1 && nlists <= 1000000, NDB_B200_EINVAL, "ivf_create: lists out of range");
+    NDB_REQUIRE(metric >= NDB_L2 && metric <= NDB_IP, NDB_B200_EINVAL, "ivf_create: unknown metric %d", metric);
+    ndb_b200_ivf *ix = new ndb_b200_ivf();
+    ix->dim = dim;
+    ix->dimp = round_up(dim, 4);
+    ix->nlists = nlists;
+    ix->metric = metric;
+    *out = ix;
+    return NDB_B200_OK;
+}
+
+void ndb_b200_ivf_free(ndb_b200_ivf *ix)
+{
+    if (!ix) return;
+    if (ctx().initialized) { cudaSetDevice(ctx().device); cudaStreamSynchronize(ctx().stream); }
+    delete ix;
+}
+
+int ndb_b200_ivf_set_shard(ndb_b200_ivf *ix, int rank, int world)
+{
+    NDB_REQUIRE(ix && world >= 1 && rank >= 0 && rank < world, NDB_B200_EINVAL, "ivf_set_shard: bad rank/world");
+    NDB_REQUIRE(ix->nrows == 0, NDB_B200_ESTATE, "ivf_set_shard: must be called before rows are inserted");
+    ix->rank = rank;
+    ix->world = world;
+    return NDB_B200_OK;
+}
+
+static int ivf_install_centroids(ndb_b200_ivf *ix, cudaStream_t s)
+{
+    // kw.C holds the row-major centroids; build the IL32 copy used by every scan
+    const int64_t blocks = (ix->nlists + 31) / 32;
+    const size_t bytes = (size_t) blocks * 32 * ix->dimp * 4;
+    NDB_CHECK(ix->kw.cstore.reserve(bytes));
+    NDB_CUDA(cudaMemsetAsync(ix->kw.cstore.p, 0, bytes, s));
+    NDB_CHECK(il32_scatter(ix->kw.C.as<float>(), ix->nlists, ix->dim, ix->dimp, nullptr, 0, ix->kw.cstore.as<float>(), s));
+    ix->trained = true;
+    return NDB_B200_OK;
+}
+
+int ndb_b200_ivf_train(ndb_b200_ivf *ix, const float *rows, int64_t n)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix && rows && n > 0, NDB_B200_EINVAL, "ivf_train: NULL or empty input");
+    // maxSamples = Min(10000, nlists * 100), first rows in heap order (:580, :485-495)
+    int64_t ns = (int64_t) ix->nlists * 100;
+    if (ns > 10000) ns = 10000;
+    if (ns > n) ns = n;
+    // "ivf: not enough sample vectors" (:596-603)
+    NDB_REQUIRE(ns >= ix->nlists, NDB_B200_ESTATE, "ivf: not enough sample vectors (%lld < %d)", (long long) ns, ix->nlists);
+    NDB_REQUIRE(find_nonfinite(rows, ns * ix->dim) < 0, NDB_B200_EVECTOR, "ivf_train: NaN/Inf in samples");
+    cudaStream_t s = ctx().stream;
+    NDB_CHECK(ix->kw.X.reserve((size_t) ns * ix->dim * 4));
+    NDB_CUDA(cudaMemcpyAsync(ix->kw.X.p, rows, (size_t) ns * ix->dim * 4, cudaMemcpyHostToDevice, s));
+    int iters = 0;
+    float cost = 0.0f;
+    // IVF_MAX_ITERATIONS 50, IVF_CONVERGENCE_THRESHOLD 0.001 (:56-57)
+    NDB_CHECK(kmeans_run_dev(ix->kw, (int) ns, ix->dim, ix->nlists, 50, 0.001f, &iters, &cost, s));
+    ix->C_host.resize((size_t) ix->nlists * ix->dim);
+    NDB_CUDA(cudaMemcpyAsync(ix->C_host.data(), ix->kw.C.p, ix->C_host.size() * 4, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    return ivf_install_centroids(ix, s);
+}
+
+int ndb_b200_ivf_set_centroids(ndb_b200_ivf *ix, const float *C)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix && C, NDB_B200_EINVAL, "ivf_set_centroids: NULL input");
+    ix->C_host.assign(C, C + (size_t) ix->nlists * ix->dim);
+    cudaStream_t s = ctx().stream;
+    NDB_CHECK(ivf_sync_centroids(ix, s));
+    return ivf_install_centroids(ix, s);
+}
+
+int ndb_b200_ivf_get_centroids(const ndb_b200_ivf *ix, float *C)
+{
+    NDB_REQUIRE(ix && C && ix->trained, NDB_B200_ESTATE, "ivf_get_centroids: index not trained");
+    memcpy(C, ix->C_host.data(), ix->C_host.size() * 4);
+    return NDB_B200_OK;
+}
+
+int ndb_b200_ivf_assign(const ndb_b200_ivf *cix, const float *rows, int64_t n, int *out_list)
+{
+    ndb_b200_ivf *ix = const_cast<ndb_b200_ivf *>(cix);
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix && rows && out_list && n > 0, NDB_B200_EINVAL, "ivf_assign: NULL or empty input");
+    NDB_REQUIRE(ix->trained, NDB_B200_ESTATE, "ivf_assign: index not trained");
+    cudaStream_t s = ctx().stream;
+    const int64_t chunk = 1 << 20;
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t m = n - off < chunk ? n - off : chunk;
+        NDB_CHECK(ix->tmp_rows.reserve((size_t) m * ix->dim * 4));
+        NDB_CHECK(ix->tmp_assign.reserve((size_t) m * 4));
+        NDB_CUDA(cudaMemcpyAsync(ix->tmp_rows.p, rows + (size_t) off * ix->dim, (size_t) m * ix->dim * 4, cudaMemcpyHostToDevice, s));
+        NDB_CHECK(ivf_assign_dev(ix, ix->tmp_rows.as<float>(), m, ix->tmp_assign.as<int>(), s));
+        NDB_CUDA(cudaMemcpyAsync(out_list + off, ix->tmp_assign.p, (size_t) m * 4, cudaMemcpyDeviceToHost, s));
+        NDB_CUDA(cudaStreamSynchronize(s));
+    }
+    return NDB_B200_OK;
+}
+
+int ndb_b200_ivf_insert(ndb_b200_ivf *ix, const float *rows, const int64_t *ids, int64_t n, int *out_list)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix && rows && n > 0, NDB_B200_EINVAL, "ivf_insert: NULL or empty input");
+    NDB_REQUIRE(ix->trained, NDB_B200_ESTATE, "ivf_insert: index has no centroids block");
+    NDB_REQUIRE(find_nonfinite(rows, n * ix->dim) < 0, NDB_B200_EVECTOR, "ivf_insert: NaN/Inf in rows");
+    cudaStream_t s = ctx().stream;
+    const int64_t chunk = 1 << 20;
+    std::vector<int> assign;
+    std::vector<uint32_t> keep;
+    int64_t next_default_id = 0;
+    for (int64_t r = 0; r < (int64_t) ix->row_id.size(); r++) next_default_id = std::max(next_default_id, ix->row_id[r] + 1);
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t m = n - off < chunk ? n - off : chunk;
+        NDB_CHECK(ix->tmp_rows.reserve((size_t) m * ix->dim * 4));
+        NDB_CHECK(ix->tmp_assign.reserve((size_t) m * 4));
+        NDB_CUDA(cudaMemcpyAsync(ix->tmp_rows.p, rows + (size_t) off * ix->dim, (size_t) m * ix->dim * 4, cudaMemcpyHostToDevice, s));
+        NDB_CHECK(ivf_assign_dev(ix, ix->tmp_rows.as<float>(), m, ix->tmp_assign.as<int>(), s));
+        assign.resize(m);
+        NDB_CUDA(cudaMemcpyAsync(assign.data(), ix->tmp_assign.p, (size_t) m * 4, cudaMemcpyDeviceToHost, s));
+        NDB_CUDA(cudaStreamSynchronize(s));
+        keep.clear();
+        for (int64_t i = 0; i < m; i++) {
+            if (out_list) out_list[off + i] = assign[i];
+            if (assign[i] % ix->world != ix->rank) continue;      // list owned by another rank
+            keep.push_back((uint32_t) i);
+            ix->row_list.push_back(assign[i]);
+            ix->row_id.push_back(ids ? ids[off + i] : next_default_id + off + i);
+        }
+        const int64_t nk = (int64_t) keep.size();
+        if (nk) {
+            NDB_CHECK(ix->arena.grow((size_t) (ix->nrows + nk) * ix->dim * 4, (size_t) ix->nrows * ix->dim * 4, s));
+            NDB_CHECK(ix->tmp_keep.reserve((size_t) nk * 4));
+            NDB_CUDA(cudaMemcpyAsync(ix->tmp_keep.p, keep.data(), (size_t) nk * 4, cudaMemcpyHostToDevice, s));
+            copy_kept_rows_kernel<<<(unsigned) ((nk * ix->dim + 255) / 256), 256, 0, s>>>(
+                ix->tmp_rows.as<float>(), ix->tmp_keep.as<uint32_t>(), nk, ix->dim, ix->arena.as<float>() + (size_t) ix->nrows * ix->dim);
+            count_launch();
+            NDB_CUDA(cudaGetLastError());
+            NDB_CUDA(cudaStreamSynchronize(s));
+            ix->nrows += nk;
+            ix->dirty = true;
+        }
+    }
+    return NDB_B200_OK;
+}
+
+int64_t ndb_b200_ivf_size(const ndb_b200_ivf *ix) { return ix ? ix->nrows : 0; }
+
+int ndb_b200_ivf_list_sizes(const ndb_b200_ivf *ix, int64_t *sizes)
+{
+    NDB_REQUIRE(ix && sizes, NDB_B200_EINVAL, "ivf_list_sizes: NULL input");
+    for (int l = 0; l < ix->nlists; l++) sizes[l] = 0;
+    for (int64_t r = 0; r < ix->nrows; r++) sizes[ix->row_list[r]]++;
+    return NDB_B200_OK;
+}
+
+int ndb_b200_ivf_select_clusters(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, int *probes)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix && Q && probes && nq > 0 && nprobe > 0, NDB_B200_EINVAL, "ivf_select_clusters: bad argument");
+    NDB_REQUIRE(ix->trained, NDB_B200_ESTATE, "ivf_select_clusters: index not trained");
+    cudaStream_t s = ctx().stream;
+    const int np = nprobe < ix->nlists ? nprobe : ix->nlists;
+    NDB_REQUIRE(np <= 128, NDB_B200_EINVAL, "ivf: nprobe > 128 is not supported");
+    NDB_CHECK(ix->qbuf.reserve((size_t) nq * ix->dim * 4));
+    NDB_CUDA(cudaMemcpyAsync(ix->qbuf.p, Q, (size_t) nq * ix->dim * 4, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(ivf_coarse(ix, ix->qbuf.as<float>(), nq, np, NDB_ARITH_IVF_F32, s));
+    std::vector<uint32_t> h((size_t) nq * np);
+    NDB_CUDA(cudaMemcpyAsync(h.data(), ix->probe.p, h.size() * 4, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    for (int q = 0; q < nq; q++)
+        for (int i = 0; i < nprobe; i++)
+            probes[(size_t) q * nprobe + i] = (i < np && h[(size_t) q * np + i] != INVALID_SLOT) ? (int) h[(size_t) q * np + i] : -1;
+    return NDB_B200_OK;
+}
+
+int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int nprobe, int k, int mode, int arith,
+                            float *dist_dev, int64_t *ids_dev, void *stream)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix && Q_dev && dist_dev && ids_dev && nq > 0 && nprobe > 0, NDB_B200_EINVAL, "ivf_search: bad argument");
+    NDB_REQUIRE(k >= 1 && k <= 128, NDB_B200_EINVAL, "ivf_search: k=%d out of range 1..128", k);
+    NDB_REQUIRE(arith == NDB_ARITH_IVF_F32 || arith == NDB_ARITH_FAST, NDB_B200_EINVAL, "ivf_search: arith %d unsupported", arith);
+    cudaStream_t s = stream ? (cudaStream_t) stream : ctx().stream;
+    NDB_CHECK(ivf_ready(ix, s));
+    const int np = nprobe < ix->nlists ? nprobe : ix->nlists;
+    NDB_REQUIRE(np <= 128, NDB_B200_EINVAL, "ivf: nprobe > 128 is not supported");
+    const int L = ix->nlists;
+    const int64_t npairs = (int64_t) nq * np;
+
+    // 1. ivfSelectClusters
+    NDB_CHECK(ivf_coarse(ix, Q_dev, nq, np, arith, s));
+    const void *vnorm = nullptr;
+    if (ix->metric == NDB_COSINE) NDB_CHECK(ivf_vnorm(ix, arith, &vnorm, s));
+
+    if (mode == NDB_IVF_LITERAL) {
+        NDB_REQUIRE(k * 10 <= 2560, NDB_B200_EINVAL, "ivf literal mode: k too large");
+        const size_t smem = (size_t) 12 * 4 * k * 10;
+        const unsigned grid = (unsigned) ((nq + 3) / 4);
+#define NDB_LIT(M) ivf_literal_kernel<Arith<M, NDB_ARITH_IVF_F32>><<<grid, 128, smem, s>>>( \
+        reinterpret_cast<const float4 *>(ix->store.ptr()), (const float *) vnorm, Q_dev, ix->probe.as<uint32_t>(), \
+        ix->d_list_len.as<uint32_t>(), ix->d_list_blk.as<uint32_t>(), ix->lit_order.as<uint32_t>(), ix->ids.as<int64_t>(), \
+        nq, np, L, ix->dim, ix->dimp, k, dist_dev, ids_dev)
+        if (ix->metric == NDB_L2) NDB_LIT(NDB_L2);
+        else if (ix->metric == NDB_COSINE) NDB_LIT(NDB_COSINE);
+        else NDB_LIT(NDB_IP);
+#undef NDB_LIT
+        count_launch();
+        NDB_CUDA(cudaGetLastError());
+        return NDB_B200_OK;
+    }
+
+    // 2. bucket pairs by list
+    const int qt = scan_pick_qt(arith, ix->dim, k);
+    NDB_REQUIRE(qt > 0, NDB_B200_EINVAL, "ivf_search: unsupported shape dim=%d k=%d", ix->dim, k);
+    const size_t max_items = (size_t) npairs / qt + L + 1;
+    NDB_CHECK(ix->cnt.reserve((size_t) L * 4 * 2));
+    NDB_CHECK(ix->qoff.reserve((size_t) L * 4));
+    NDB_CHECK(ix->item_off.reserve((size_t) L * 4));
+    NDB_CHECK(ix->qmap.reserve((size_t) npairs * 4));
+    NDB_CHECK(ix->items.reserve(max_items * sizeof(WorkItem)));
+    NDB_CHECK(ix->nitems.reserve(64));
+    NDB_CHECK(ix->stats.reserve(64));
+    uint32_t *cnt = ix->cnt.as<uint32_t>(), *fill = cnt + L;
+    NDB_CUDA(cudaMemsetAsync(cnt, 0, (size_t) L * 4 * 2, s));
+    ivf_hist_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L, cnt);
+    ivf_offsets_kernel<<<1, 1024, 0, s>>>(cnt, ix->d_list_len.as<uint32_t>(), L, qt, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
+                                          ix->nitems.as<uint32_t>(), ix->stats.as<unsigned long long>());
+    ivf_scatter_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L,
+                                                                        ix->qoff.as<uint32_t>(), fill, ix->qmap.as<uint32_t>());
+    ivf_items_kernel<<<(unsigned) ((L + 127) / 128), 128, 0, s>>>(cnt, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
+                                                                 ix->d_list_len.as<uint32_t>(), ix->d_list_blk.as<uint32_t>(), L, qt,
+                                                                 ix->items.as<WorkItem>());
+    count_launch(4);
+    NDB_CUDA(cudaGetLastError());
+
+    // 3. list scan with fused top-k
+    NDB_CHECK(ix->scr.ensure((size_t) npairs, k, nq, ix->metric == NDB_COSINE ? 4 : 0));
+    if (ix->metric == NDB_COSINE) NDB_CHECK(row_norms(arith, Q_dev, nq, ix->dim, ix->scr.qnorm.p, s));
+    NDB_CUDA(cudaMemsetAsync(ix->scr.pslot.p, 0xff, (size_t) npairs * k * 4, s));
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.vecs = reinterpret_cast<const float4 *>(ix->store.ptr());
+    p.vnorm = vnorm;
+    p.Q = Q_dev;
+    p.qnorm = ix->metric == NDB_COSINE ? ix->scr.qnorm.p : nullptr;
+    p.dim = ix->dim; p.dimp = ix->dimp; p.k = k;
+    p.items = ix->items.as<WorkItem>();
+    p.n_items_ptr = ix->nitems.as<uint32_t>();
+    p.qmap = ix->qmap.as<uint32_t>();
+    p.nprobe = (uint32_t) np;
+    p.counter = ix->scr.counter.as<uint32_t>();
+    p.pdist = ix->scr.pdist.as<float>();
+    p.pslot = ix->scr.pslot.as<uint32_t>();
+    Context &c = ctx();
+    if (c.timing) NDB_CUDA(cudaEventRecord(c.ev0, s));
+    NDB_CHECK(launch_scan(ix->metric, arith, qt, p, (uint32_t) max_items, s));
+    if (c.timing) {
+        NDB_CUDA(cudaEventRecord(c.ev1, s));
+        c.last_ms = -1.0;
+        c.last_bytes = -1.0;          // resolved from ix->stats in last_kernel_stats
+        c.last_evals = -1;
+        c.stats_src = ix->stats.p;
+        c.stats_dim = ix->dim;
+    }
+
+    // 4. merge the probed lists' partial results by (dist, id)
+    return launch_merge_parts(ix->scr.pdist.as<float>(), ix->scr.pslot.as<uint32_t>(), ix->ids.as<int64_t>(), nq, np, k,
+                              dist_dev, ids_dev, nullptr, s);
+}
+
+int ndb_b200_ivf_search(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, int k, int mode, int arith, float *dist,
+                        int64_t *ids)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix && Q && dist && ids && nq > 0, NDB_B200_EINVAL, "ivf_search: NULL or empty input");
+    NDB_REQUIRE(find_nonfinite(Q, (int64_t) nq * ix->dim) < 0, NDB_B200_EVECTOR, "ivf_search: NaN/Inf in query");
+    cudaStream_t s = ctx().stream;
+    const size_t qb = (size_t) nq * ix->dim * 4, m = (size_t) nq * k;
+    NDB_CHECK(ix->qbuf.reserve(qb));
+    NDB_CHECK(ix->outd.reserve(m * 4));
+    NDB_CHECK(ix->outi.reserve(m * 8));
+    NDB_CUDA(cudaMemcpyAsync(ix->qbuf.p, Q, qb, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(ndb_b200_ivf_search_dev(ix, ix->qbuf.as<float>(), nq, nprobe, k, mode, arith, ix->outd.as<float>(),
+                                      ix->outi.as<int64_t>(), s));
+    NDB_CUDA(cudaMemcpyAsync(dist, ix->outd.p, m * 4, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaMemcpyAsync(ids, ix->outi.p, m * 8, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    return NDB_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+// kmeans.cu -- IVF k-means training (kmeans_init/run/assign/update_centroids/compute_cost,
+// NeuronDB/src/index/ivf_am.c:2070-2294) and the ndb_gpu_backend k-means launchers.
+//
+// Literal semantics, reproduced bit for bit:
+//   assign : argmin_c sum_f32 (x-c)^2, strict <, lowest index wins        -> fused scan, k = 1
+//   update : per cluster, f32 running sum over its members IN SAMPLE ORDER, divided by the
+//            int count; empty clusters stay at zero                        -> segmented sequential sum
+//   cost   : f32 running sum over samples IN ORDER of the squared L2        -> one sequential chain
+// Order matters for f32 sums, so the update groups samples by cluster with a stable sort and
+// each (cluster, dimension) pair is one thread walking its members in ascending sample index.
+#include "kmeans.cuh"
+#include "scan.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cfloat>
+
+namespace ndb {
+
+__global__ void iota_u32_kernel(uint32_t *out, int64_t n)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t) i;
+}
+
+__global__ void slot_to_assign_kernel(const uint32_t *slot, int *assign, int64_t n)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) assign[i] = slot[i] == INVALID_SLOT ? 0 : (int) slot[i];   // best starts at 0 (:2277)
+}
+
+// segment boundaries of the sorted cluster keys: start[c] = first position with key >= c
+__global__ void segment_starts_kernel(const int *sorted_keys, int64_t n, int k, int *start)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const int cur = i < n ? sorted_keys[i] : k;
+    const int prev = i > 0 ? sorted_keys[i - 1] : -1;
+    for (int c = prev + 1; c <= cur && c <= k; c++) start[c] = (int) i;
+}
+
+// one thread per (cluster, dimension): sequential f32 sum over the cluster's members in
+// ascending sample order, then sum / (float) count  (ivf_am.c:2189-2212)
+__global__ void kmeans_update_kernel(const float *__restrict__ X, const uint32_t *__restrict__ members,
+                                     const int *__restrict__ start, int dim, int k, float *__restrict__ C,
+                                     int *__restrict__ counts)
+{
+    const int c = blockIdx.x;
+    const int b = start[c], e = start[c + 1];
+    if (threadIdx.x == 0 && blockIdx.y == 0 && counts) counts[c] = e - b;
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= dim) return;
+    float sum = 0.0f;
+    for (int t = b; t < e; t++) sum = __fadd_rn(sum, X[(size_t) members[t] * dim + j]);
+    if (e > b) sum = __fdiv_rn(sum, (float) (e - b));
+    C[(size_t) c * dim + j] = sum;
+}
+
+// squared L2 of each sample to its centroid, lane-per-sample through a transposed smem tile
+__global__ void __launch_bounds__(128) kmeans_sample_cost_kernel(const float *__restrict__ X, const float *__restrict__ C,
+                                                                  const int *__restrict__ assign, int64_t n, int dim,
+                                                                  float *__restrict__ out)
+{
+    __shared__ float ta[4][32][33];
+    __shared__ float tb[4][32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t p0 = ((int64_t) blockIdx.x * 4 + w) * 32;
+    if (p0 >= n) return;
+    const int np = (int) (n - p0 < 32 ? n - p0 : 32);
+    float acc = 0.0f;
+    for (int c0 = 0; c0 < dim; c0 += 32) {
+        const int cw = dim - c0 < 32 ? dim - c0 : 32;
+        for (int r = 0; r < np; r++) {
+            if (lane < cw) {
+                ta[w][r][lane] = X[(size_t) (p0 + r) * dim + c0 + lane];
+                tb[w][r][lane] = C[(size_t) assign[p0 + r] * dim + c0 + lane];
+            }
+        }
+        __syncwarp();
+        if (lane < np)
+            for (int j = 0; j < cw; j++) {
+                const float diff = __fsub_rn(ta[w][lane][j], tb[w][lane][j]);
+                acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+            }
+        __syncwarp();
+    }
+    if (lane < np) out[p0 + lane] = acc;
+}
+
+// cost += d_i in sample order: one dependent f32 chain (ivf_am.c:2218-2233); values are
+// staged through shared memory so the chain never waits on DRAM
+__global__ void sequential_sum_kernel(const float *__restrict__ v, int64_t n, float *out)
+{
+    __shared__ float buf[1024];
+    float acc = 0.0f;
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int m = (int) (n - base < 1024 ? n - base : 1024);
+        if ((int) threadIdx.x < m) buf[threadIdx.x] = v[base + threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int i = 0; i < m; i++) acc = __fadd_rn(acc, buf[i]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = acc;
+}
+
+static int centroids_to_store(KMeansWork &w, int k, int dim, int dimp, cudaStream_t s)
+{
+    const int64_t blocks = (k + 31) / 32;
+    const size_t bytes = (size_t) blocks * 32 * dimp * sizeof(float);
+    NDB_CHECK(w.cstore.reserve(bytes));
+    NDB_CUDA(cudaMemsetAsync(w.cstore.p, 0, bytes, s));
+    return il32_scatter(w.C.as<float>(), k, dim, dimp, nullptr, 0, w.cstore.as<float>(), s);
+}
+
+// assign[i] = nearest centroid of row i (dX row-major); metric selects the squared (k-means,
+// :2274-2294) or the sqrtf'd (ivfinsert, :906-935) comparison
+int kmeans_assign_dev(KMeansWork &w, const float *dX, int64_t n, int dim, int k, int metric, int *d_assign,
+                      cudaStream_t s)
+{
+    const int dimp = round_up(dim, 4);
+    NDB_CHECK(centroids_to_store(w, k, dim, dimp, s));
+    const int64_t chunk = 1 << 22;
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int m = (int) (n - off < chunk ? n - off : chunk);
+        int nparts = 1;
+        NDB_CHECK(dense_scan(w.cstore.as<float>(), nullptr, k, dim, dimp, metric, NDB_ARITH_IVF_F32,
+                             dX + (size_t) off * dim, m, 1, w.scr, &nparts, s));
+        if (nparts == 1) {
+            slot_to_assign_kernel<<<(unsigned) ((m + 255) / 256), 256, 0, s>>>(w.scr.pslot.as<uint32_t>(), d_assign + off, m);
+            count_launch();
+        } else {
+            // more than one segment of centroids: merge by (dist, index) first
+            DevBuf md, msl;
+            NDB_CHECK(md.reserve((size_t) m * 4)); NDB_CHECK(msl.reserve((size_t) m * 4));
+            NDB_CHECK(launch_merge_parts(w.scr.pdist.as<float>(), w.scr.pslot.as<uint32_t>(), nullptr, m, nparts, 1,
+                                         md.as<float>(), nullptr, msl.as<uint32_t>(), s));
+            slot_to_assign_kernel<<<(unsigned) ((m + 255) / 256), 256, 0, s>>>(msl.as<uint32_t>(), d_assign + off, m);
+            count_launch();
+            NDB_CUDA(cudaStreamSynchronize(s));
+        }
+        NDB_CUDA(cudaGetLastError());
+    }
+    return NDB_B200_OK;
+}
+
+int kmeans_update_dev(KMeansWork &w, const float *dX, const int *d_assign, int64_t n, int dim, int k, float *dC,
+                      int *d_counts, cudaStream_t s)
+{
+    NDB_REQUIRE(n < (int64_t) 0x7fffffff, NDB_B200_EINVAL, "kmeans_update: n too large");
+    NDB_CHECK(w.keys_sorted.reserve((size_t) n * 4));
+    NDB_CHECK(w.vals_in.reserve((size_t) n * 4));
+    NDB_CHECK(w.vals_sorted.reserve((size_t) n * 4));
+    NDB_CHECK(w.start.reserve((size_t) (k + 2) * 4));
+    iota_u32_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(w.vals_in.as<uint32_t>(), n);
+    count_launch();
+    int bits = 1;
+    while ((1 << bits) < k) bits++;
+    size_t tmp_bytes = 0;
+    NDB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_assign, w.keys_sorted.as<int>(), w.vals_in.as<uint32_t>(),
+                                             w.vals_sorted.as<uint32_t>(), (int) n, 0, bits, s));
+    NDB_CHECK(w.cub_tmp.reserve(tmp_bytes));
+    // LSD radix sort is stable: members of a cluster stay in ascending sample order
+    NDB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, tmp_bytes, d_assign, w.keys_sorted.as<int>(), w.vals_in.as<uint32_t>(),
+                                             w.vals_sorted.as<uint32_t>(), (int) n, 0, bits, s));
+    count_launch(3);
+    segment_starts_kernel<<<(unsigned) ((n + 1 + 255) / 256), 256, 0, s>>>(w.keys_sorted.as<int>(), n, k, w.start.as<int>());
+    count_launch();
+    dim3 grid((unsigned) k, (unsigned) ((dim + 127) / 128));
+    kmeans_update_kernel<<<grid, 128, 0, s>>>(dX, w.vals_sorted.as<uint32_t>(), w.start.as<int>(), dim, k, dC, d_counts);
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
+}
+
+// kmeans_init + kmeans_run (:2070-2159) on w.X (n*d row-major, already on the device).
+// Leaves centroids in w.C, assignments in w.assign, counts in w.counts.
+int kmeans_run_dev(KMeansWork &w, int n, int d, int k, int max_iter, float tol, int *iters, float *cost_out,
+                   cudaStream_t s)
+{
+    const size_t cb = (size_t) k * d * 4;
+    NDB_CHECK(w.C.reserve(cb)); NDB_CHECK(w.assign.reserve((size_t) n * 4));
+    NDB_CHECK(w.counts.reserve((size_t) k * 4)); NDB_CHECK(w.dcost.reserve((size_t) n * 4)); NDB_CHECK(w.cost.reserve(16));
+    // kmeans_init: centroid i := sample i for i < n, zero otherwise
+    NDB_CUDA(cudaMemsetAsync(w.C.p, 0, cb, s));
+    NDB_CUDA(cudaMemcpyAsync(w.C.p, w.X.p, (size_t) (k < n ? k : n) * d * 4, cudaMemcpyDeviceToDevice, s));
+    NDB_CUDA(cudaMemsetAsync(w.counts.p, 0, (size_t) k * 4, s));
+    float prevCost = FLT_MAX, cost = 0.0f;
+    int iter;
+    for (iter = 0; iter < max_iter; iter++) {
+        NDB_CHECK(kmeans_assign_dev(w, w.X.as<float>(), n, d, k, METRIC_L2SQ, w.assign.as<int>(), s));
+        NDB_CHECK(kmeans_update_dev(w, w.X.as<float>(), w.assign.as<int>(), n, d, k, w.C.as<float>(), w.counts.as<int>(), s));
+        kmeans_sample_cost_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(w.X.as<float>(), w.C.as<float>(),
+                                                                              w.assign.as<int>(), n, d, w.dcost.as<float>());
+        sequential_sum_kernel<<<1, 1024, 0, s>>>(w.dcost.as<float>(), n, w.cost.as<float>());
+        count_launch(2);
+        NDB_CUDA(cudaMemcpyAsync(&cost, w.cost.p, 4, cudaMemcpyDeviceToHost, s));
+        NDB_CUDA(cudaStreamSynchronize(s));
+        // if (fabs(prevCost - cost) < state->threshold) break;   (:2141)
+        if (fabs(prevCost - cost) < tol) { iter++; break; }
+        prevCost = cost;
+    }
+    *iters = iter;
+    *cost_out = cost;
+    return NDB_B200_OK;
+}
+
+}  // namespace ndb
+
+using namespace ndb;
+
+extern "C" {
+
+int ndb_b200_kmeans_train(const float *X, int n, int d, int k, int max_iter, float tol, float *C, int *assign,
+                          int *counts, int *iters, float *cost_out)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(X && n > 0 && d > 0 && k > 0 && max_iter >= 0, NDB_B200_EINVAL, "kmeans_train: bad argument");
+    NDB_REQUIRE(find_nonfinite(X, (int64_t) n * d) < 0, NDB_B200_EVECTOR, "kmeans_train: NaN/Inf in samples");
+    cudaStream_t s = ctx().stream;
+    KMeansWork w;
+    const size_t xb = (size_t) n * d * 4, cb = (size_t) k * d * 4;
+    NDB_CHECK(w.X.reserve(xb));
+    NDB_CUDA(cudaMemcpyAsync(w.X.p, X, xb, cudaMemcpyHostToDevice, s));
+    int iter = 0;
+    float cost = 0.0f;
+    NDB_CHECK(kmeans_run_dev(w, n, d, k, max_iter, tol, &iter, &cost, s));
+    if (C) NDB_CUDA(cudaMemcpyAsync(C, w.C.p, cb, cudaMemcpyDeviceToHost, s));
+    if (assign) NDB_CUDA(cudaMemcpyAsync(assign, w.assign.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
+    if (counts) NDB_CUDA(cudaMemcpyAsync(counts, w.counts.p, (size_t) k * 4, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    if (iters) *iters = iter;
+    if (cost_out) *cost_out = cost;
+    return NDB_B200_OK;
+}
+
+int ndb_b200_launch_kmeans_assign(const float *X, const float *C, int *idx, int n, int d, int k, void *stream)
+{
+    (void) stream;
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(X && C && idx && n > 0 && d > 0 && k > 0, NDB_B200_EINVAL, "kmeans_assign: bad argument");
+    cudaStream_t s = ctx().stream;
+    KMeansWork w;
+    NDB_CHECK(w.X.reserve((size_t) n * d * 4)); NDB_CHECK(w.C.reserve((size_t) k * d * 4)); NDB_CHECK(w.assign.reserve((size_t) n * 4));
+    NDB_CUDA(cudaMemcpyAsync(w.X.p, X, (size_t) n * d * 4, cudaMemcpyHostToDevice, s));
+    NDB_CUDA(cudaMemcpyAsync(w.C.p, C, (size_t) k * d * 4, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(kmeans_assign_dev(w, w.X.as<float>(), n, d, k, METRIC_L2SQ, w.assign.as<int>(), s));
+    NDB_CUDA(cudaMemcpyAsync(idx, w.assign.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    return NDB_B200_OK;
+}
+
+int ndb_b200_launch_kmeans_update(const float *X, const int *idx, float *C, int n, int d, int k, void *stream)
+{
+    (void) stream;
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(X && C && idx && n > 0 && d > 0 && k > 0, NDB_B200_EINVAL, "kmeans_update: bad argument");
+    for (int i = 0; i < n; i++)
+        NDB_REQUIRE(idx[i] >= 0 && idx[i] < k, NDB_B200_EINVAL, "kmeans_update: assignment %d out of range at %d", idx[i], i);
+    cudaStream_t s = ctx().stream;
+    KMeansWork w;
+    NDB_CHECK(w.X.reserve((size_t) n * d * 4)); NDB_CHECK(w.C.reserve((size_t) k * d * 4)); NDB_CHECK(w.assign.reserve((size_t) n * 4));
+    NDB_CUDA(cudaMemcpyAsync(w.X.p, X, (size_t) n * d * 4, cudaMemcpyHostToDevice, s));
+    NDB_CUDA(cudaMemcpyAsync(w.assign.p, idx, (size_t) n * 4, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(kmeans_update_dev(w, w.X.as<float>(), w.assign.as<int>(), n, d, k, w.C.as<float>(), nullptr, s));
+    NDB_CUDA(cudaMemcpyAsync(C, w.C.p, (size_t) k * d * 4, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    return NDB_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+// knn.cu -- resident dataset + exact kNN (the SeqScan + top-N sort of SURVEY 3.1 as one
+// fused scan, evaluated with the arithmetic the `<->`/`<=>`/`<#>` operators really execute).
+#include "layout.cuh"
+#include "scan.cuh"
+
+namespace ndb {
+
+struct NormCache {
+    DevBuf buf;
+    int64_t valid_for = -1;    // number of vectors the cache covers
+};
+
+}  // namespace ndb
+
+using namespace ndb;
+
+struct ndb_b200_dataset {
+    int dim = 0, dimp = 0;
+    int64_t n = 0;
+    VecStore store;
+    DevBuf ids;                 // int64 per slot
+    NormCache norm_f32_ivf, norm_f32_fast, norm_f64;
+    ScanScratch scratch;
+    DevBuf tmp_rows, tmp_ids, qbuf, outd, outi;
+};
+
+namespace ndb {
+
+__global__ void iota_i64_kernel(int64_t *out, int64_t base, int64_t n)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = base + i;
+}
+
+static int dataset_reserve(ndb_b200_dataset *ds, int64_t total, cudaStream_t s)
+{
+    const int64_t blocks = (total + 31) / 32;
+    const size_t old_bytes = ds->store.bytes_for((ds->n + 31) / 32);
+    const size_t need = ds->store.bytes_for(blocks);
+    if (need > ds->store.data.cap) {
+        const size_t before = ds->store.data.cap;
+        NDB_CHECK(ds->store.data.grow(need, old_bytes, s));
+        // fresh capacity must be zero: pad lanes of the last block are read (and masked) by the scan
+        NDB_CUDA(cudaMemsetAsync((char *) ds->store.data.p + old_bytes, 0, ds->store.data.cap - old_bytes, s));
+        (void) before;
+    }
+    NDB_CHECK(ds->ids.grow((size_t) total * sizeof(int64_t), (size_t) ds->n * sizeof(int64_t), s));
+    return NDB_B200_OK;
+}
+
+static int dataset_append_dev(ndb_b200_dataset *ds, const float *rows_dev, const int64_t *ids_dev, int64_t n,
+                              cudaStream_t s)
+{
+    NDB_REQUIRE(ds->n + n < (int64_t) 0xfffffff0ll, NDB_B200_EINVAL, "dataset too large for 32-bit slots");
+    NDB_CHECK(dataset_reserve(ds, ds->n + n, s));
+    NDB_CHECK(il32_scatter(rows_dev, n, ds->dim, ds->dimp, nullptr, (uint32_t) ds->n, ds->store.ptr(), s));
+    if (ids_dev) {
+        NDB_CUDA(cudaMemcpyAsync(ds->ids.as<int64_t>() + ds->n, ids_dev, (size_t) n * sizeof(int64_t),
+                                 cudaMemcpyDeviceToDevice, s));
+    } else {
+        iota_i64_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(ds->ids.as<int64_t>() + ds->n, ds->n, n);
+        count_launch();
+        NDB_CUDA(cudaGetLastError());
+    }
+    ds->n += n;
+    ds->store.nblk = (ds->n + 31) / 32;
+    return NDB_B200_OK;
+}
+
+static int dataset_norms(ndb_b200_dataset *ds, int arith, const void **out, cudaStream_t s)
+{
+    NormCache &c = arith == NDB_ARITH_OP_F64 ? ds->norm_f64 : (arith == NDB_ARITH_FAST ? ds->norm_f32_fast : ds->norm_f32_ivf);
+    if (c.valid_for != ds->n) {
+        NDB_CHECK(c.buf.reserve((size_t) ds->n * norm_elem_size(arith)));
+        NDB_CHECK(slot_norms(arith, ds->store.ptr(), ds->n, ds->dim, ds->dimp, c.buf.p, s));
+        c.valid_for = ds->n;
+    }
+    *out = c.buf.p;
+    return NDB_B200_OK;
+}
+
+// shared with ivf.cu / kmeans.cu: dense scan of `nq` row-major queries against an IL32 store
+int dense_scan(const float *store, const void *vnorm, int64_t nvec, int dim, int dimp, int metric, int arith,
+               const float *Q_dev, int nq, int k, ScanScratch &scr, int *out_nparts, cudaStream_t s)
+{
+    const int qt = scan_pick_qt(arith, dim, k);
+    NDB_REQUIRE(qt > 0, NDB_B200_EINVAL, "unsupported scan shape: dim=%d k=%d (k must be 1..128)", dim, k);
+    const int64_t B = (nvec + 31) / 32;
+    const int ntiles = (nq + qt - 1) / qt;
+    const int64_t target_items = (int64_t) ctx().sm_count * 8;
+    int64_t nseg = (target_items + ntiles - 1) / ntiles;
+    if (nseg < 1) nseg = 1;
+    int64_t seg_blocks = (B + nseg - 1) / nseg;
+    if (seg_blocks < 32) seg_blocks = 32;          // >= 4 blocks per warp
+    if (seg_blocks > B) seg_blocks = B > 0 ? B : 1;
+    nseg = B > 0 ? (B + seg_blocks - 1) / seg_blocks : 1;
+    const size_t norm_bytes = (metric == NDB_COSINE) ? norm_elem_size(arith) : 0;
+    NDB_CHECK(scr.ensure((size_t) nq * nseg, k, nq, norm_bytes));
+    if (norm_bytes) NDB_CHECK(row_norms(arith, Q_dev, nq, dim, scr.qnorm.p, s));
+    NDB_CUDA(cudaMemsetAsync(scr.pslot.p, 0xff, (size_t) nq * nseg * k * sizeof(uint32_t), s));
+
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.vecs = reinterpret_cast<const float4 *>(store);
+    p.vnorm = vnorm;
+    p.Q = Q_dev;
+    p.qnorm = norm_bytes ? scr.qnorm.p : nullptr;
+    p.dim = dim; p.dimp = dimp; p.k = k;
+    p.dense_ntiles = (uint32_t) ntiles;
+    p.dense_items = (uint32_t) (nseg * ntiles);
+    p.dense_seg_blocks = (uint32_t) seg_blocks;
+    p.dense_nq = (uint32_t) nq;
+    p.dense_nparts = (uint32_t) nseg;
+    p.dense_nvec = (uint64_t) nvec;
+    p.counter = scr.counter.as<uint32_t>();
+    p.pdist = scr.pdist.as<float>();
+    p.pslot = scr.pslot.as<uint32_t>();
+    Context &c = ctx();
+    if (c.timing) NDB_CUDA(cudaEventRecord(c.ev0, s));
+    NDB_CHECK(launch_scan(metric, arith, qt, p, p.dense_items, s));
+    if (c.timing) {
+        NDB_CUDA(cudaEventRecord(c.ev1, s));
+        c.last_bytes = (double) nvec * dim * 4.0 * ntiles;     // each tile streams the store once
+        c.last_evals = (int64_t) nvec * nq;
+        c.last_ms = -1.0;                                      // resolved lazily
+    }
+    *out_nparts = (int) nseg;
+    return NDB_B200_OK;
+}
+
+}  // namespace ndb
+
+extern "C" {
+
+int ndb_b200_dataset_create(int dim, ndb_b200_dataset **out)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(out && dim > 0 && dim <= 16000, NDB_B200_EINVAL, "dataset_create: dim must be 1..16000 (VECTOR_MAX_DIM)");
+    ndb_b200_dataset *ds = new ndb_b200_dataset();
+    ds->dim = dim;
+    ds->dimp = round_up(dim, 4);
+    ds->store.dim = dim;
+    ds->store.dimp = ds->dimp;
+    *out = ds;
+    return NDB_B200_OK;
+}
+
+void ndb_b200_dataset_free(ndb_b200_dataset *ds)
+{
+    if (!ds) return;
+    if (ctx().initialized) { cudaSetDevice(ctx().device); cudaStreamSynchronize(ctx().stream); }
+    delete ds;
+}
+
+int64_t ndb_b200_dataset_size(const ndb_b200_dataset *ds) { return ds ? ds->n : 0; }
+
+int ndb_b200_dataset_append(ndb_b200_dataset *ds, const float *rows, const int64_t *ids, int64_t n)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ds && rows && n > 0, NDB_B200_EINVAL, "dataset_append: NULL or empty input");
+    const int64_t bad = find_nonfinite(rows, n * ds->dim);
+    NDB_REQUIRE(bad < 0, NDB_B200_EVECTOR, "vector contains NaN or Infinity at row %lld index %lld",
+                (long long) (bad / ds->dim), (long long) (bad % ds->dim));
+    cudaStream_t s = ctx().stream;
+    const int64_t chunk = 1 << 20;
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t m = n - off < chunk ? n - off : chunk;
+        NDB_CHECK(ds->tmp_rows.reserve((size_t) m * ds->dim * sizeof(float)));
+        NDB_CUDA(cudaMemcpyAsync(ds->tmp_rows.p, rows + (size_t) off * ds->dim, (size_t) m * ds->dim * sizeof(float),
+                                 cudaMemcpyHostToDevice, s));
+        const int64_t *idp = nullptr;
+        if (ids) {
+            NDB_CHECK(ds->tmp_ids.reserve((size_t) m * sizeof(int64_t)));
+            NDB_CUDA(cudaMemcpyAsync(ds->tmp_ids.p, ids + off, (size_t) m * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+            idp = ds->tmp_ids.as<int64_t>();
+        }
+        NDB_CHECK(dataset_append_dev(ds, ds->tmp_rows.as<float>(), idp, m, s));
+        NDB_CUDA(cudaStreamSynchronize(s));
+    }
+    return NDB_B200_OK;
+}
+
+int ndb_b200_dataset_append_dev(ndb_b200_dataset *ds, const float *rows_dev, const int64_t *ids_dev, int64_t n,
+                                void *stream)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ds && rows_dev && n > 0, NDB_B200_EINVAL, "dataset_append_dev: NULL or empty input");
+    return dataset_append_dev(ds, rows_dev, ids_dev, n, stream ? (cudaStream_t) stream : ctx().stream);
+}
+
+int ndb_b200_knn_exact_dev(ndb_b200_dataset *ds, int metric, int arith, const float *Q_dev, int nq, int k,
+                           float *dist_dev, int64_t *ids_dev, void *stream)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ds && Q_dev && dist_dev && ids_dev && nq > 0, NDB_B200_EINVAL, "knn_exact: NULL or empty input");
+    NDB_REQUIRE(k >= 1 && k <= 128, NDB_B200_EINVAL, "knn_exact: k=%d out of range 1..128", k);
+    NDB_REQUIRE(metric >= NDB_L2 && metric <= NDB_IP, NDB_B200_EINVAL, "knn_exact: unknown metric %d", metric);
+    NDB_REQUIRE(arith == NDB_ARITH_OP_F64 || arith == NDB_ARITH_IVF_F32 || arith == NDB_ARITH_FAST, NDB_B200_EINVAL,
+                "knn_exact: arith %d not available for the scan", arith);
+    cudaStream_t s = stream ? (cudaStream_t) stream : ctx().stream;
+    const void *vnorm = nullptr;
+    if (metric == NDB_COSINE) NDB_CHECK(dataset_norms(ds, arith, &vnorm, s));
+    int nparts = 1;
+    NDB_CHECK(dense_scan(ds->store.ptr(), vnorm, ds->n, ds->dim, ds->dimp, metric, arith, Q_dev, nq, k, ds->scratch,
+                         &nparts, s));
+    return launch_merge_parts(ds->scratch.pdist.as<float>(), ds->scratch.pslot.as<uint32_t>(), ds->ids.as<int64_t>(), nq,
+                              nparts, k, dist_dev, ids_dev, nullptr, s);
+}
+
+int ndb_b200_knn_exact(ndb_b200_dataset *ds, int metric, int arith, const float *Q, int nq, int k, float *dist,
+                       int64_t *ids)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ds && Q && dist && ids && nq > 0, NDB_B200_EINVAL, "knn_exact: NULL or empty input");
+    const int64_t bad = find_nonfinite(Q, (int64_t) nq * ds->dim);
+    NDB_REQUIRE(bad < 0, NDB_B200_EVECTOR, "vector contains NaN or Infinity at index %lld", (long long) (bad % ds->dim));
+    cudaStream_t s = ctx().stream;
+    const size_t qb = (size_t) nq * ds->dim * sizeof(float), m = (size_t) nq * k;
+    NDB_CHECK(ds->qbuf.reserve(qb));
+    NDB_CHECK(ds->outd.reserve(m * sizeof(float)));
+    NDB_CHECK(ds->outi.reserve(m * sizeof(int64_t)));
+    NDB_CUDA(cudaMemcpyAsync(ds->qbuf.p, Q, qb, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(ndb_b200_knn_exact_dev(ds, metric, arith, ds->qbuf.as<float>(), nq, k, ds->outd.as<float>(),
+                                     ds->outi.as<int64_t>(), s));
+    NDB_CUDA(cudaMemcpyAsync(dist, ds->outd.p, m * sizeof(float), cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaMemcpyAsync(ids, ds->outi.p, m * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    return NDB_B200_OK;
+}
+
+}  // extern "C"

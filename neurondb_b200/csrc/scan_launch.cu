@@ -1,0 +1,144 @@
+// scan_launch.cu -- instantiation and launch of the fused scan + top-k kernel (scan.cuh).
+#include "layout.cuh"
+#include "scan.cuh"
+
+namespace ndb {
+
+static size_t scan_smem_bytes(size_t qelem, int qt, int kr, int dimp)
+{
+    return qelem * (size_t) qt * dimp + (size_t) SCAN_NW * qt * kr * 32 * 8;
+}
+
+static size_t qelem_size(int arith) { return arith == NDB_ARITH_OP_F64 ? 8 : 4; }
+
+static int kr_for(int k) { return k <= 32 ? 1 : (k <= 128 ? 4 : 0); }
+
+int scan_pick_qt(int arith, int dim, int k)
+{
+    const int kr = kr_for(k);
+    if (kr == 0 || dim <= 0) return 0;
+    const int dimp = round_up(dim, 4);
+    const size_t limit = ctx().smem_optin ? ctx().smem_optin - 1024 : 200 * 1024;
+    if (scan_smem_bytes(qelem_size(arith), 8, kr, dimp) <= limit) return 8;
+    if (scan_smem_bytes(qelem_size(arith), 1, kr, dimp) <= limit) return 1;
+    return 0;
+}
+
+template <class P, int QT, int KR>
+static int launch_one(const ScanParams &prm, uint32_t items_upper, cudaStream_t s)
+{
+    auto kern = scan_topk_kernel<P, QT, KR>;
+    const size_t smem = scan_smem_bytes(sizeof(typename P::Q), QT, KR, prm.dimp);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        NDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        configured = smem;
+    }
+    int per_sm = 0;
+    NDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SCAN_NW * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (uint32_t) ctx().sm_count * (uint32_t) per_sm;
+    if (items_upper < grid) grid = items_upper;
+    if (grid == 0) return NDB_B200_OK;
+    NDB_CUDA(cudaMemsetAsync(prm.counter, 0, sizeof(uint32_t), s));
+    kern<<<grid, SCAN_NW * 32, smem, s>>>(prm);
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
+}
+
+template <class P> static int launch_policy(int qt, const ScanParams &prm, uint32_t items_upper, cudaStream_t s)
+{
+    const int kr = kr_for(prm.k);
+    if (qt == 8 && kr == 1) return launch_one<P, 8, 1>(prm, items_upper, s);
+    if (qt == 8 && kr == 4) return launch_one<P, 8, 4>(prm, items_upper, s);
+    if (qt == 1 && kr == 1) return launch_one<P, 1, 1>(prm, items_upper, s);
+    if (qt == 1 && kr == 4) return launch_one<P, 1, 4>(prm, items_upper, s);
+    set_error("scan: unsupported tile/k combination qt=%d k=%d", qt, prm.k);
+    return NDB_B200_EINVAL;
+}
+
+int launch_scan(int metric, int arith, int qt, const ScanParams &prm, uint32_t items_upper, cudaStream_t s)
+{
+#define NDB_SCAN_CASE(M, A) \
+    if (metric == M && arith == A) return launch_policy<Arith<M, A>>(qt, prm, items_upper, s);
+    NDB_SCAN_CASE(NDB_L2, NDB_ARITH_IVF_F32)
+    NDB_SCAN_CASE(METRIC_L2SQ, NDB_ARITH_IVF_F32)
+    NDB_SCAN_CASE(NDB_COSINE, NDB_ARITH_IVF_F32)
+    NDB_SCAN_CASE(NDB_IP, NDB_ARITH_IVF_F32)
+    NDB_SCAN_CASE(NDB_L2, NDB_ARITH_OP_F64)
+    NDB_SCAN_CASE(NDB_COSINE, NDB_ARITH_OP_F64)
+    NDB_SCAN_CASE(NDB_IP, NDB_ARITH_OP_F64)
+    NDB_SCAN_CASE(NDB_L2, NDB_ARITH_FAST)
+    NDB_SCAN_CASE(METRIC_L2SQ, NDB_ARITH_FAST)
+    NDB_SCAN_CASE(NDB_COSINE, NDB_ARITH_FAST)
+    NDB_SCAN_CASE(NDB_IP, NDB_ARITH_FAST)
+#undef NDB_SCAN_CASE
+    set_error("scan: unsupported metric/arith %d/%d", metric, arith);
+    return NDB_B200_EINVAL;
+}
+
+int launch_merge_parts(const float *pdist, const uint32_t *pslot, const int64_t *ids, int nq, int nparts, int k,
+                       float *out_dist, int64_t *out_ids, uint32_t *out_slot, cudaStream_t s)
+{
+    if (nq <= 0) return NDB_B200_OK;
+    const int kr = kr_for(k);
+    const unsigned grid = (unsigned) ((nq + 3) / 4);
+    if (kr == 1) merge_parts_kernel<1><<<grid, 128, 0, s>>>(pdist, pslot, ids, nq, nparts, k, out_dist, out_ids, out_slot);
+    else if (kr == 4) merge_parts_kernel<4><<<grid, 128, 0, s>>>(pdist, pslot, ids, nq, nparts, k, out_dist, out_ids, out_slot);
+    else { set_error("merge: k=%d out of range (1..128)", k); return NDB_B200_EINVAL; }
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
+}
+
+int launch_merge_shards(const float *dist, const int64_t *ids, int nshards, int nq, int k, float *out_dist,
+                        int64_t *out_ids, cudaStream_t s)
+{
+    if (nq <= 0) return NDB_B200_OK;
+    const int kr = kr_for(k);
+    const unsigned grid = (unsigned) ((nq + 3) / 4);
+    if (kr == 1) merge_shards_kernel<1><<<grid, 128, 0, s>>>(dist, ids, nshards, nq, k, out_dist, out_ids);
+    else if (kr == 4) merge_shards_kernel<4><<<grid, 128, 0, s>>>(dist, ids, nshards, nq, k, out_dist, out_ids);
+    else { set_error("merge: k=%d out of range (1..128)", k); return NDB_B200_EINVAL; }
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
+}
+
+}  // namespace ndb
+
+using namespace ndb;
+
+extern "C" {
+
+int ndb_b200_merge_topk_dev(const float *dist_dev, const int64_t *ids_dev, int nshards, int nq, int k,
+                            float *out_dist_dev, int64_t *out_ids_dev, void *stream)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(dist_dev && ids_dev && out_dist_dev && out_ids_dev && nshards > 0 && nq > 0 && k > 0 && k <= 128,
+                NDB_B200_EINVAL, "merge_topk: bad argument");
+    return launch_merge_shards(dist_dev, ids_dev, nshards, nq, k, out_dist_dev, out_ids_dev,
+                               stream ? (cudaStream_t) stream : ctx().stream);
+}
+
+int ndb_b200_merge_topk(const float *dist, const int64_t *ids, int nshards, int nq, int k, float *out_dist,
+                        int64_t *out_ids)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(dist && ids && out_dist && out_ids && nshards > 0 && nq > 0 && k > 0 && k <= 128, NDB_B200_EINVAL,
+                "merge_topk: bad argument");
+    const size_t n = (size_t) nshards * nq * k, m = (size_t) nq * k;
+    DevBuf dd, di, od, oi;
+    NDB_CHECK(dd.reserve(n * 4)); NDB_CHECK(di.reserve(n * 8)); NDB_CHECK(od.reserve(m * 4)); NDB_CHECK(oi.reserve(m * 8));
+    cudaStream_t s = ctx().stream;
+    NDB_CUDA(cudaMemcpyAsync(dd.p, dist, n * 4, cudaMemcpyHostToDevice, s));
+    NDB_CUDA(cudaMemcpyAsync(di.p, ids, n * 8, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(launch_merge_shards(dd.as<float>(), di.as<int64_t>(), nshards, nq, k, od.as<float>(), oi.as<int64_t>(), s));
+    NDB_CUDA(cudaMemcpyAsync(out_dist, od.p, m * 4, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaMemcpyAsync(out_ids, oi.p, m * 8, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    return NDB_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def ndb():
+    """The product library, initialised on cuda:0.  Fails loudly if the .so is missing."""
+    import neurondb_b200 as n
+    n.init(0)
+    yield n
+
+
+@pytest.fixture(scope="session")
+def orc():
+    import oracle_lib
+    oracle_lib.lib()
+    return oracle_lib

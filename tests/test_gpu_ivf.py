@@ -1,0 +1,111 @@
+"""GPU parity for the IVF path (ivfbuild / ivfinsert / ivfgettuple) against the oracle."""
+import numpy as np
+import pytest
+
+import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+BITS = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def build_pair(ndb, orc, X, lists, metric=1, ids=None):
+    ix = ndb.IvfIndex(X.shape[1], lists, metric)
+    ix.ivfbuild(X)
+    ns = orc.lib().orc_ivf_train_samples(X.shape[0], lists)
+    oC, _, _, _, _ = orc.kmeans_train(X[:ns], lists)
+    assert np.array_equal(BITS(ix.centroids()), BITS(oC)), "k-means centroids differ from the oracle"
+    got_lists = ix.ivfinsert(X, ids)
+    want_lists = orc.ivf_assign(X, oC)
+    assert np.array_equal(got_lists, want_lists), "ivfinsert list assignment differs"
+    off, rows = orc.lists_from_assignment(want_lists, lists)
+    assert np.array_equal(ix.list_sizes(), np.diff(off))
+    return ix, oC, off, rows
+
+
+@pytest.mark.parametrize("n,dim,lists,nprobe,k", [(20000, 32, 64, 8, 10), (30000, 128, 100, 10, 10),
+                                                   (5000, 17, 16, 16, 5), (8000, 96, 50, 3, 32)])
+@pytest.mark.parametrize("metric", [1, 2, 3])
+def test_ivf_full_scan_parity(ndb, orc, n, dim, lists, nprobe, k, metric):
+    X = W.mixture(n, dim, lists, 2024 + n)
+    Q = W.mixture(300, dim, lists, 2025 + n, centers_seed=2024 + n)
+    ix, oC, off, rows = build_pair(ndb, orc, X, lists, metric)
+    probes = ix.select_clusters(Q, nprobe)
+    want_probes = np.stack([orc.select_clusters(q, oC, nprobe) for q in Q[:50]])
+    assert np.array_equal(probes[:50, :want_probes.shape[1]], want_probes)
+    d, i = ix.search(Q, nprobe, k, ndb.IVF_FULL)
+    od, oi, _ = orc.ivf_search(X, oC, off, rows, Q, nprobe, k, strategy=metric, literal=False)
+    assert np.array_equal(i, oi)
+    assert np.array_equal(BITS(d), BITS(od))
+
+
+def test_ivf_literal_mode_parity(ndb, orc):
+    """ivfCollectCandidates as written: k*10 candidate cap in probe order."""
+    X = W.mixture(20000, 64, 40, 7)
+    Q = W.mixture(200, 64, 40, 8, centers_seed=7)
+    ix, oC, off, rows = build_pair(ndb, orc, X, 40)
+    d, i = ix.search(Q, 10, 10, ndb.IVF_LITERAL)
+    od, oi, _ = orc.ivf_search(X, oC, off, rows, Q, 10, 10, literal=True)
+    assert np.array_equal(i, oi) and np.array_equal(BITS(d), BITS(od))
+
+
+def test_ivf_ids_and_unsorted_insert(ndb, orc):
+    """heap ids that are not the row index, inserted in two batches in shuffled id order."""
+    X = W.mixture(6000, 24, 20, 31)
+    ids = np.random.default_rng(1).permutation(100000)[:6000].astype(np.int64)
+    Q = W.mixture(100, 24, 20, 32, centers_seed=31)
+    ix = ndb.IvfIndex(24, 20)
+    ix.ivfbuild(X)
+    ix.ivfinsert(X[:2500], ids[:2500])
+    ix.ivfinsert(X[2500:], ids[2500:])
+    assert len(ix) == 6000
+    oC = ix.centroids()
+    assign = orc.ivf_assign(X, oC)
+    off, rows = orc.lists_from_assignment(assign, 20)
+    d, i = ix.search(Q, 5, 10)
+    od, oi, _ = orc.ivf_search(X, oC, off, rows, Q, 5, 10, ids=ids)
+    assert np.array_equal(i, oi) and np.array_equal(BITS(d), BITS(od))
+    # literal mode depends on insertion order, not id order
+    d, i = ix.search(Q, 5, 10, ndb.IVF_LITERAL)
+    od, oi, _ = orc.ivf_search(X, oC, off, rows, Q, 5, 10, ids=ids, literal=True)
+    assert np.array_equal(i, oi) and np.array_equal(BITS(d), BITS(od))
+
+
+def test_ivf_edge_cases(ndb, orc):
+    X = W.gaussian(400, 8, 3)
+    ix = ndb.IvfIndex(8, 4)
+    with pytest.raises(ndb.NdbError):          # search before build: no centroids
+        ix.search(X[:2], 2, 5)
+    with pytest.raises(ndb.NdbError):          # "ivf: not enough sample vectors" (ivf_am.c:596-603)
+        ndb.IvfIndex(8, 500).ivfbuild(X)
+    ix.ivfbuild(X)
+    d, i = ix.search(X[:3], 2, 5)              # trained but empty: no rows
+    assert np.all(i == -1) and np.all(np.isinf(d))
+    ix.ivfinsert(X[:3])                        # fewer rows than k
+    d, i = ix.search(X[:3], 4, 5)
+    assert np.all(i[:, 0] == np.arange(3)) and np.all(d[:, 0] == 0.0)
+    assert np.all(i[:, 3:] == -1)
+    d, i = ix.search(X[:3], 99, 5)             # nprobe > nlists is clamped (ivf_am.c:1622-1623)
+    assert np.all(i[:, 3:] == -1)
+
+
+def test_ivf_config2_shape_recall(ndb, orc):
+    """BASELINE config 2 shape scaled to 200k rows: recall@10 vs exact ground truth, id parity
+    with the oracle on a query slice."""
+    n, dim, lists, nprobe = 200_000, 128, 256, 16
+    X = W.mixture(n, dim, lists, 2024)
+    Q = W.mixture(2000, dim, lists, 2025, centers_seed=2024)
+    ix = ndb.IvfIndex(dim, lists)
+    ix.ivfbuild(X)
+    ix.ivfinsert(X)
+    d, i = ix.search(Q, nprobe, 10)
+    gt = W.exact_ground_truth(X, Q, 10)
+    recall = orc.recall_at_k(i, gt)
+    oC = ix.centroids()
+    off, rows = orc.lists_from_assignment(orc.ivf_assign(X, oC), lists)
+    od, oi, _ = orc.ivf_search(X, oC, off, rows, Q[:200], nprobe, 10)
+    assert np.array_equal(i[:200], oi) and np.array_equal(BITS(d[:200]), BITS(od))
+    assert recall >= 0.95, recall
+    df, i_f = ix.search(Q, nprobe, 10, arith=ndb.ARITH_FAST)
+    assert orc.recall_at_k(i_f, gt) >= recall - 0.002
+    assert np.max(np.abs(df - d) / np.maximum(d, 1e-6)) < 1e-5
