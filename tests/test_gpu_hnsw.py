@@ -1,0 +1,98 @@
+"""GPU parity for the HNSW path (hnswSearch / hnswInsertNode) against the oracle."""
+import numpy as np
+import pytest
+
+import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+BITS = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def oracle_graph(orc, X, m, efc, levels, mode):
+    g = orc.Hnsw(X.shape[1], m, efc, 40, capacity=X.shape[0])
+    g.build(X, levels, mode)
+    return g
+
+
+@pytest.mark.parametrize("n,dim,m,efc", [(3000, 32, 8, 32), (2000, 768, 16, 64), (1500, 19, 4, 16)])
+@pytest.mark.parametrize("build_mode", [0, 1])
+def test_search_same_graph_is_id_exact(ndb, orc, n, dim, m, efc, build_mode):
+    """Upload the oracle's graph; both search modes must return the oracle's ids and distances."""
+    X = W.normalised(n, dim, 768 + n)
+    Q = W.normalised(200, dim, 769 + n)
+    levels = orc.hnsw_levels(n, seed=n)
+    og = oracle_graph(orc, X, m, efc, levels, build_mode)
+    h = ndb.HnswIndex(dim, m, efc, 40)
+    h.load_graph(X, og.export())
+    assert len(h) == n
+    for strategy in (1, 2, 3):
+        for mode, ef, k in ((ndb.HNSW_LITERAL, 40, 10), (ndb.HNSW_BESTFIRST, 40, 10), (ndb.HNSW_BESTFIRST, 100, 32),
+                            (ndb.HNSW_LITERAL, 16, 16)):
+            d, i = h.search(Q, ef, k, strategy, mode)
+            od, on, cnt = og.search(Q, ef, k, strategy, 0 if mode == ndb.HNSW_LITERAL else 1)
+            oi = np.where(on == 0xFFFFFFFF, -1, on.astype(np.int64))
+            assert np.array_equal(i, oi), (strategy, mode, ef, k)
+            assert np.array_equal(BITS(d), BITS(od)), (strategy, mode, ef, k)
+            assert h.last_evals() == og.distance_evals()
+
+
+def test_build_batch1_equals_sequential_oracle(ndb, orc):
+    """batch = 1 is hnswInsertNode one node at a time: the exported graph equals the oracle's."""
+    n, dim, m, efc = 800, 24, 6, 20
+    X = W.gaussian(n, dim, 5)
+    levels = orc.hnsw_levels(n, seed=7)
+    og = oracle_graph(orc, X, m, efc, levels, 1).export()
+    h = ndb.HnswIndex(dim, m, efc, 40)
+    h.hnswbuild(X, levels=levels, batch=1)
+    g = h.export_graph()
+    assert g["entry_point"] == og["entry_point"] and g["entry_level"] == og["entry_level"]
+    assert np.array_equal(g["levels"], og["levels"])
+    assert np.array_equal(g["cnt"], og["cnt"])
+    assert np.array_equal(g["nbr0"], og["nbr0"])
+    assert np.array_equal(g["upper_off"], og["upper_off"])
+    assert np.array_equal(g["upper"][: int(g["upper_off"][-1])], og["upper"][: int(og["upper_off"][-1])])
+
+
+def test_build_batched_recall_vs_reference_graph(ndb, orc):
+    """Recall contract: the GPU-built graph must reach recall@10 >= the reference-literal
+    index at the same ef_search, and match the sequential build within a small margin."""
+    n, dim, m, efc, efs = 20000, 64, 16, 64, 40
+    X = W.normalised(n, dim, 11)
+    Q = W.normalised(500, dim, 12)
+    gt = W.exact_ground_truth(X, Q, 10)
+    levels = orc.hnsw_levels(n, seed=3)
+    h = ndb.HnswIndex(dim, m, efc, efs)
+    h.hnswbuild(X, levels=levels)            # default batching
+    d, i = h.search(Q, efs, 10, 1, ndb.HNSW_BESTFIRST)
+    r_gpu = orc.recall_at_k(i, gt)
+    lit = oracle_graph(orc, X, m, efc, levels, 0)
+    _, on, _ = lit.search(Q, efs, 10, 1, 0)
+    r_ref_literal = orc.recall_at_k(on.astype(np.int64), gt)
+    _, on, _ = lit.search(Q, efs, 10, 1, 1)
+    r_ref_graph_bestfirst = orc.recall_at_k(on.astype(np.int64), gt)
+    seq = oracle_graph(orc, X, m, efc, levels, 1)
+    _, on, _ = seq.search(Q, efs, 10, 1, 1)
+    r_seq = orc.recall_at_k(on.astype(np.int64), gt)
+    print("recall gpu %.4f | reference literal %.4f | reference graph best-first %.4f | sequential %.4f"
+          % (r_gpu, r_ref_literal, r_ref_graph_bestfirst, r_seq))
+    assert r_gpu >= r_ref_literal
+    assert r_gpu >= r_ref_graph_bestfirst - 0.01
+    assert r_gpu >= r_seq - 0.02
+    # distances returned are exact hnswComputeDistance values of the returned ids
+    chk = orc.distance_pairs(np.repeat(Q, 10, 0), X[i.reshape(-1)], 1, orc.ARITH_HNSW).reshape(i.shape)
+    assert np.array_equal(BITS(d), BITS(chk))
+
+
+def test_hnsw_edge_cases(ndb, orc):
+    with pytest.raises(ndb.NdbError):
+        ndb.HnswIndex(8, m=1)                  # "hnsw: m must be between 2 and 128"
+    with pytest.raises(ndb.NdbError):
+        ndb.HnswIndex(8, m=16, ef_construction=8)   # ef_construction >= m
+    X = W.gaussian(5, 8, 1)
+    h = ndb.HnswIndex(8, 4, 8, 8)
+    h.hnswbuild(X, levels=np.zeros(5, np.int32), batch=1)
+    d, i = h.search(X, 8, 10, 1, ndb.HNSW_BESTFIRST)     # fewer nodes than k
+    assert np.all(i[:, 0] == np.arange(5)) and np.all(d[:, 0] == 0)
+    assert np.all(i[:, 5:] == -1) and np.all(np.isinf(d[:, 5:]))
+    assert all(sorted(r[:5]) == [0, 1, 2, 3, 4] for r in i)
