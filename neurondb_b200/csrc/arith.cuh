@@ -196,6 +196,10 @@ template <class KeyT> __device__ __forceinline__ KeyT shfl_up_key(KeyT v);
 template <> __device__ __forceinline__ uint32_t shfl_up_key<uint32_t>(uint32_t v) { return __shfl_up_sync(FULL, v, 1); }
 template <> __device__ __forceinline__ int64_t shfl_up_key<int64_t>(int64_t v) { return __shfl_up_sync(FULL, v, 1); }
 
+template <class KeyT> __device__ __forceinline__ KeyT shfl_xor_key(KeyT v, int m);
+template <> __device__ __forceinline__ uint32_t shfl_xor_key<uint32_t>(uint32_t v, int m) { return __shfl_xor_sync(FULL, v, m); }
+template <> __device__ __forceinline__ int64_t shfl_xor_key<int64_t>(int64_t v, int m) { return __shfl_xor_sync(FULL, v, m); }
+
 template <class KeyT> struct KeyMax;
 template <> struct KeyMax<uint32_t> { static constexpr uint32_t v = 0xffffffffu; };
 template <> struct KeyMax<int64_t> { static constexpr int64_t v = 0x7fffffffffffffffll; };
@@ -244,10 +248,47 @@ template <int KR, class KeyT> struct WarpTopK {
         }
         refresh_threshold(k);
     }
+    // KR == 1 only: merge up to 32 candidates (one per lane) in one go.  Bitonic-sort the
+    // candidates across the lanes, take the element-wise minimum with the reversed current list
+    // (which leaves the 32 smallest of the union as a bitonic sequence) and finish with one
+    // bitonic merge: 21 shuffle stages regardless of how many lanes carry a candidate.
+    __device__ __forceinline__ void merge32(float cd, KeyT ck, bool pass, int lane, int k)
+    {
+        float nd = pass ? cd : INFINITY;
+        KeyT nk = pass ? ck : KeyMax<KeyT>::v;
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                const float pd = __shfl_xor_sync(FULL, nd, j);
+                const KeyT pk = shfl_xor_key<KeyT>(nk, j);
+                const bool want_min = ((lane & j) == 0) == ((lane & kk) == 0);
+                const bool take = want_min ? pair_less<KeyT>(pd, pk, nd, nk) : pair_less<KeyT>(nd, nk, pd, pk);
+                if (take) { nd = pd; nk = pk; }
+            }
+        }
+        const float rd = __shfl_sync(FULL, nd, 31 - lane);
+        const KeyT rk = shfl_key<KeyT>(nk, 31 - lane);
+        if (pair_less<KeyT>(rd, rk, d[0], key[0])) { d[0] = rd; key[0] = rk; }
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            const float pd = __shfl_xor_sync(FULL, d[0], j);
+            const KeyT pk = shfl_xor_key<KeyT>(key[0], j);
+            const bool want_min = (lane & j) == 0;
+            const bool take = want_min ? pair_less<KeyT>(pd, pk, d[0], key[0]) : pair_less<KeyT>(d[0], key[0], pd, pk);
+            if (take) { d[0] = pd; key[0] = pk; }
+        }
+        refresh_threshold(k);
+    }
     // every lane offers (cd, ck) if valid; all 32 lanes must call
     __device__ __forceinline__ void offer(float cd, KeyT ck, bool valid, int lane, int k)
     {
-        unsigned m = __ballot_sync(FULL, valid && pair_less<KeyT>(cd, ck, td, tk));
+        const bool pass = valid && pair_less<KeyT>(cd, ck, td, tk);
+        unsigned m = __ballot_sync(FULL, pass);
+        if (KR == 1 && __popc(m) >= 8) {       // serial insertion costs ~20 instr per candidate
+            merge32(cd, ck, pass, lane, k);
+            return;
+        }
         while (m) {
             const int src = __ffs(m) - 1;
             m &= m - 1;

@@ -36,17 +36,32 @@ struct ndb_b200_ivf {
     // laid-out lists
     bool dirty = true;
     VecStore store;
-    DevBuf ids, vnorm_ivf, vnorm_fast, lit_order, d_list_len, d_list_blk;
+    DevBuf ids, vnorm_ivf, vnorm_fast, lit_order, d_list_len, d_list_blk, d_list_order;
     bool vnorm_ivf_ok = false, vnorm_fast_ok = false;
     std::vector<uint32_t> list_len, list_blk;
     // scratch
     ScanScratch cscr, scr;
-    DevBuf probe, cnt, fill, qoff, item_off, qmap, items, nitems, stats, tmp_rows, tmp_assign, tmp_keep;
+    DevBuf probe, cnt, fill, qoff, item_off, qmap, pairpos, items, nitems, stats, tmp_rows, tmp_assign, tmp_keep;
     DevBuf qbuf, outd, outi, cdist;
     int64_t last_scanned = 0;
 };
 
 namespace ndb {
+
+// Long lists are cut into runs of `segb` 32-vector blocks so that one work item is bounded, and
+// the items are emitted longest-list-first (`order` = lists by descending length, fixed at
+// layout time): the persistent CTAs pick the heavy items up first and the short ones fill the
+// tail, whatever the list-length skew.
+__host__ __device__ inline uint32_t ivf_nseg(uint32_t len, uint32_t segb)
+{
+    const uint32_t blocks = (len + 31) / 32;
+    return (blocks + segb - 1) / segb;
+}
+static uint32_t ivf_seg_blocks()
+{
+    static const uint32_t v = [] { const char *e = getenv("NDB_IVF_SEG_BLOCKS"); int x = e ? atoi(e) : 32; return (uint32_t) (x >= 1 ? x : 32); }();
+    return v;
+}
 
 // ---- work-item construction -----------------------------------------------------------------
 __global__ void ivf_hist_kernel(const uint32_t *__restrict__ probe, int64_t npairs, const uint32_t *__restrict__ list_len,
@@ -58,11 +73,11 @@ __global__ void ivf_hist_kernel(const uint32_t *__restrict__ probe, int64_t npai
     if (l < (uint32_t) nlists && list_len[l] > 0) atomicAdd(&cnt[l], 1u);
 }
 
-// single CTA: exclusive scans of cnt (-> qoff) and of ceil(cnt/QT) (-> item_off); totals
+// single CTA: exclusive scans, in `order`, of cnt (-> qoff) and of tiles * segments (-> item_off)
 __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ list_len,
-                                                           int nlists, int qt, uint32_t *__restrict__ qoff,
-                                                           uint32_t *__restrict__ item_off, uint32_t *__restrict__ nitems,
-                                                           unsigned long long *__restrict__ scanned)
+                                                           const uint32_t *__restrict__ order, int nlists, int qt, uint32_t segb,
+                                                           uint32_t *__restrict__ qoff, uint32_t *__restrict__ item_off,
+                                                           uint32_t *__restrict__ nitems, unsigned long long *__restrict__ scanned)
 {
     typedef cub::BlockScan<uint32_t, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
@@ -72,22 +87,26 @@ __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__res
     if (threadIdx.x == 0) s_scanned = 0;
     uint32_t sq = 0, st = 0;
     unsigned long long sc = 0;
-    for (int l = b; l < e; l++) {
-        sq += cnt[l];
-        st += (cnt[l] + qt - 1) / qt;
-        sc += (unsigned long long) cnt[l] * list_len[l];
+    for (int i = b; i < e; i++) {
+        const uint32_t l = order[i], c = cnt[l];
+        sq += c;
+        st += ((c + qt - 1) / qt) * ivf_nseg(list_len[l], segb);
+        sc += (unsigned long long) c * list_len[l];
     }
     uint32_t oq, ot;
     Scan(tmp).ExclusiveSum(sq, oq);
     __syncthreads();
     Scan(tmp).ExclusiveSum(st, ot);
     __syncthreads();
-    atomicAdd(&s_scanned, sc);
-    for (int l = b; l < e; l++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(FULL, sc, o);
+    if ((threadIdx.x & 31) == 0 && sc) atomicAdd(&s_scanned, sc);
+    for (int i = b; i < e; i++) {
+        const uint32_t l = order[i], c = cnt[l];
         qoff[l] = oq;
         item_off[l] = ot;
-        oq += cnt[l];
-        ot += (cnt[l] + qt - 1) / qt;
+        oq += c;
+        ot += ((c + qt - 1) / qt) * ivf_nseg(list_len[l], segb);
     }
     if (threadIdx.x == 1023) *nitems = ot;   // last thread's running total == grand total
     __syncthreads();
@@ -96,30 +115,88 @@ __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__res
 
 __global__ void ivf_scatter_kernel(const uint32_t *__restrict__ probe, int64_t npairs, const uint32_t *__restrict__ list_len,
                                    int nlists, const uint32_t *__restrict__ qoff, uint32_t *__restrict__ fill,
-                                   uint32_t *__restrict__ qmap)
+                                   uint32_t *__restrict__ qmap, uint32_t *__restrict__ pairpos)
 {
     const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     const uint32_t l = probe[p];
-    if (l < (uint32_t) nlists && list_len[l] > 0) qmap[qoff[l] + atomicAdd(&fill[l], 1u)] = (uint32_t) p;
+    if (l < (uint32_t) nlists && list_len[l] > 0) {
+        const uint32_t pos = atomicAdd(&fill[l], 1u);      // position of this query among the list's queries
+        qmap[qoff[l] + pos] = (uint32_t) p;
+        pairpos[p] = pos;
+    }
 }
 
 __global__ void ivf_items_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ qoff,
                                  const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len,
-                                 const uint32_t *__restrict__ list_blk, int nlists, int qt, WorkItem *__restrict__ items)
+                                 const uint32_t *__restrict__ list_blk, int nlists, int qt, uint32_t segb,
+                                 WorkItem *__restrict__ items)
 {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per list, lanes over its (tile, segment) items
+    const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (l >= nlists) return;
     const uint32_t c = cnt[l];
     const uint32_t tiles = (c + qt - 1) / qt;
-    for (uint32_t t = 0; t < tiles; t++) {
+    const uint32_t len = list_len[l], nseg = ivf_nseg(len, segb);
+    // item (tile t, segment sg) sits at item_off[l] + t * nseg + sg
+    for (uint32_t i = threadIdx.x & 31; i < tiles * nseg; i += 32) {
+        const uint32_t t = i / nseg, sg = i - t * nseg;
         WorkItem it;
-        it.blk_begin = list_blk[l];
-        it.nvec = list_len[l];
+        it.blk_begin = list_blk[l] + sg * segb;
+        it.nvec = min(segb * 32, len - sg * segb * 32);
         it.qoff = qoff[l] + t * qt;
         it.nq = min((uint32_t) qt, c - t * qt);
-        it.part = 0;
-        items[item_off[l] + t] = it;
+        it.part = sg;
+        items[item_off[l] + i] = it;
+    }
+}
+
+// merge, per query, the partial top-k lists written by the list-mode scan: for each probed list
+// the query sits at position pairpos[p] among that list's queries, i.e. in tile pos / tile and
+// slot pos % tile of the items item_off[l] + (pos / tile) * nseg + sg.  (dist, id) order.
+template <int KR>
+__global__ void ivf_merge_kernel(const float *__restrict__ pdist, const uint32_t *__restrict__ pslot,
+                                 const int64_t *__restrict__ ids, const uint32_t *__restrict__ probe,
+                                 const uint32_t *__restrict__ pairpos, const uint32_t *__restrict__ item_off,
+                                 const uint32_t *__restrict__ list_len, int nq, int nprobe, int nlists, int tile, uint32_t segb, int k,
+                                 float *__restrict__ out_dist, int64_t *__restrict__ out_ids)
+{
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    WarpTopK<KR, int64_t> top;
+    top.init();
+    for (int r = 0; r < nprobe; r++) {
+        const size_t p = (size_t) q * nprobe + r;
+        const uint32_t l = probe[p];
+        if (l >= (uint32_t) nlists) continue;
+        const uint32_t len = list_len[l];
+        if (len == 0) continue;
+        const uint32_t pos = pairpos[p], nseg = ivf_nseg(len, segb);
+        const uint32_t item0 = item_off[l] + (pos / tile) * nseg;
+        const uint32_t it = pos % tile;
+        for (uint32_t sg = 0; sg < nseg; sg++) {
+            const size_t base = ((size_t) (item0 + sg) * tile + it) * k;
+            for (int i = lane; i < round_up(k, 32); i += 32) {
+                float cd = INFINITY;
+                int64_t id = -1;
+                bool valid = false;
+                if (i < k) {
+                    const uint32_t s = pslot[base + i];
+                    if (s != INVALID_SLOT) { cd = pdist[base + i]; id = ids[s]; valid = true; }
+                }
+                top.offer(cd, id, valid, lane, k);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KR; r++) {
+        const int e = r * 32 + lane;
+        if (e < k) {
+            const bool have = top.key[r] != KeyMax<int64_t>::v;
+            out_dist[(size_t) q * k + e] = have ? top.d[r] : INFINITY;
+            out_ids[(size_t) q * k + e] = have ? top.key[r] : -1;
+        }
     }
 }
 
@@ -266,6 +343,11 @@ static int ivf_layout(ndb_b200_ivf *ix, cudaStream_t s)
         NDB_CHECK(ix->tmp_assign.reserve((size_t) (n ? n : 1) * 4));
         NDB_CHECK(ix->d_list_len.reserve((size_t) L * 4));
         NDB_CHECK(ix->d_list_blk.reserve((size_t) L * 4));
+        NDB_CHECK(ix->d_list_order.reserve((size_t) L * 4));
+        std::vector<uint32_t> lorder(L);
+        std::iota(lorder.begin(), lorder.end(), 0u);
+        std::stable_sort(lorder.begin(), lorder.end(), [&](uint32_t a, uint32_t b) { return ix->list_len[a] > ix->list_len[b]; });
+        NDB_CUDA(cudaMemcpyAsync(ix->d_list_order.p, lorder.data(), (size_t) L * 4, cudaMemcpyHostToDevice, s));
         if (bytes) NDB_CUDA(cudaMemsetAsync(ix->store.data.p, 0, bytes, s));
         NDB_CUDA(cudaMemcpyAsync(ix->ids.p, ids_by_slot.data(), (size_t) (nslots ? nslots : 1) * 8, cudaMemcpyHostToDevice, s));
         NDB_CUDA(cudaMemcpyAsync(ix->lit_order.p, lit.data(), (size_t) (nslots ? nslots : 1) * 4, cudaMemcpyHostToDevice, s));
@@ -544,31 +626,41 @@ int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np
     // 2. bucket pairs by list
     const int qt = scan_pick_qt(arith, ix->dim, k);
     NDB_REQUIRE(qt > 0, NDB_B200_EINVAL, "ivf_search: unsupported shape dim=%d k=%d", ix->dim, k);
-    const size_t max_items = (size_t) npairs / qt + L + 1;
     NDB_CHECK(ix->cnt.reserve((size_t) L * 4 * 2));
     NDB_CHECK(ix->qoff.reserve((size_t) L * 4));
     NDB_CHECK(ix->item_off.reserve((size_t) L * 4));
     NDB_CHECK(ix->qmap.reserve((size_t) npairs * 4));
-    NDB_CHECK(ix->items.reserve(max_items * sizeof(WorkItem)));
+    NDB_CHECK(ix->pairpos.reserve((size_t) npairs * 4));
     NDB_CHECK(ix->nitems.reserve(64));
     NDB_CHECK(ix->stats.reserve(64));
     uint32_t *cnt = ix->cnt.as<uint32_t>(), *fill = cnt + L;
     NDB_CUDA(cudaMemsetAsync(cnt, 0, (size_t) L * 4 * 2, s));
     ivf_hist_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L, cnt);
-    ivf_offsets_kernel<<<1, 1024, 0, s>>>(cnt, ix->d_list_len.as<uint32_t>(), L, qt, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
-                                          ix->nitems.as<uint32_t>(), ix->stats.as<unsigned long long>());
+    const uint32_t segb = ivf_seg_blocks();
+    ivf_offsets_kernel<<<1, 1024, 0, s>>>(cnt, ix->d_list_len.as<uint32_t>(), ix->d_list_order.as<uint32_t>(), L, qt, segb,
+                                          ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->nitems.as<uint32_t>(),
+                                          ix->stats.as<unsigned long long>());
+    // the number of work items depends on how the batch's probes fall on long and short lists:
+    // one 4-byte read-back sizes the item and partial-result buffers exactly
+    uint32_t *h_nitems = reinterpret_cast<uint32_t *>(ctx().pinned);
+    NDB_CUDA(cudaMemcpyAsync(h_nitems, ix->nitems.p, 4, cudaMemcpyDeviceToHost, s));
     ivf_scatter_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L,
-                                                                        ix->qoff.as<uint32_t>(), fill, ix->qmap.as<uint32_t>());
-    ivf_items_kernel<<<(unsigned) ((L + 127) / 128), 128, 0, s>>>(cnt, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
-                                                                 ix->d_list_len.as<uint32_t>(), ix->d_list_blk.as<uint32_t>(), L, qt,
-                                                                 ix->items.as<WorkItem>());
-    count_launch(4);
+                                                                        ix->qoff.as<uint32_t>(), fill, ix->qmap.as<uint32_t>(),
+                                                                        ix->pairpos.as<uint32_t>());
+    count_launch(3);
+    NDB_CUDA(cudaGetLastError());
+    NDB_CUDA(cudaStreamSynchronize(s));
+    const size_t n_items = *h_nitems;
+    NDB_CHECK(ix->items.reserve((n_items + 1) * sizeof(WorkItem)));
+    ivf_items_kernel<<<(unsigned) ((L + 3) / 4), 128, 0, s>>>(cnt, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
+                                                             ix->d_list_len.as<uint32_t>(), ix->d_list_blk.as<uint32_t>(), L, qt, segb,
+                                                             ix->items.as<WorkItem>());
+    count_launch();
     NDB_CUDA(cudaGetLastError());
 
     // 3. list scan with fused top-k
-    NDB_CHECK(ix->scr.ensure((size_t) npairs, k, nq, ix->metric == NDB_COSINE ? 4 : 0));
+    NDB_CHECK(ix->scr.ensure((n_items + 1) * qt, k, nq, ix->metric == NDB_COSINE ? 4 : 0));
     if (ix->metric == NDB_COSINE) NDB_CHECK(row_norms(arith, Q_dev, nq, ix->dim, ix->scr.qnorm.p, s));
-    NDB_CUDA(cudaMemsetAsync(ix->scr.pslot.p, 0xff, (size_t) npairs * k * 4, s));
     ScanParams p;
     memset(&p, 0, sizeof(p));
     p.vecs = reinterpret_cast<const float4 *>(ix->store.ptr());
@@ -585,7 +677,7 @@ int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np
     p.pslot = ix->scr.pslot.as<uint32_t>();
     Context &c = ctx();
     if (c.timing) NDB_CUDA(cudaEventRecord(c.ev0, s));
-    NDB_CHECK(launch_scan(ix->metric, arith, qt, p, (uint32_t) max_items, s));
+    NDB_CHECK(launch_scan(ix->metric, arith, qt, p, (uint32_t) n_items, s));
     if (c.timing) {
         NDB_CUDA(cudaEventRecord(c.ev1, s));
         c.last_ms = -1.0;
@@ -596,8 +688,18 @@ int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np
     }
 
     // 4. merge the probed lists' partial results by (dist, id)
-    return launch_merge_parts(ix->scr.pdist.as<float>(), ix->scr.pslot.as<uint32_t>(), ix->ids.as<int64_t>(), nq, np, k,
-                              dist_dev, ids_dev, nullptr, s);
+    const unsigned mgrid = (unsigned) ((nq + 3) / 4);
+    if (k <= 32)
+        ivf_merge_kernel<1><<<mgrid, 128, 0, s>>>(ix->scr.pdist.as<float>(), ix->scr.pslot.as<uint32_t>(), ix->ids.as<int64_t>(),
+                                                  ix->probe.as<uint32_t>(), ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(),
+                                                  ix->d_list_len.as<uint32_t>(), nq, np, L, qt, segb, k, dist_dev, ids_dev);
+    else
+        ivf_merge_kernel<4><<<mgrid, 128, 0, s>>>(ix->scr.pdist.as<float>(), ix->scr.pslot.as<uint32_t>(), ix->ids.as<int64_t>(),
+                                                  ix->probe.as<uint32_t>(), ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(),
+                                                  ix->d_list_len.as<uint32_t>(), nq, np, L, qt, segb, k, dist_dev, ids_dev);
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
 }
 
 int ndb_b200_ivf_search(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, int k, int mode, int arith, float *dist,

@@ -91,7 +91,7 @@ int dense_scan(const float *store, const void *vnorm, int64_t nvec, int dim, int
     int64_t nseg = (target_items + ntiles - 1) / ntiles;
     if (nseg < 1) nseg = 1;
     int64_t seg_blocks = (B + nseg - 1) / nseg;
-    if (seg_blocks < 32) seg_blocks = 32;          // >= 4 blocks per warp
+    if (seg_blocks < 8) seg_blocks = 8;            // short runs defeat the k-th-best filter
     if (seg_blocks > B) seg_blocks = B > 0 ? B : 1;
     nseg = B > 0 ? (B + seg_blocks - 1) / seg_blocks : 1;
     const size_t norm_bytes = (metric == NDB_COSINE) ? norm_elem_size(arith) : 0;

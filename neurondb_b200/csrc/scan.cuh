@@ -6,16 +6,20 @@
 //   * ivfinsert / kmeans_assign: rows x centroids, k = 1 (:906-935, :2164-2177)    dense mode
 //   * ivfCollectCandidates: (query, probed list) pairs grouped by list (:1722-1909)  list mode
 //
-// Work item = (a run of 32-vector blocks, a tile of QT queries).  A CTA of NW warps takes an
-// item; warp w streams blocks w, w+NW, ... with one 128-bit load per lane per 4 dimensions
-// (IL32 layout, 512 contiguous bytes per warp-load).  Lane l owns vector l of the block and
-// walks its dimensions in order with QT accumulators -- the query tile sits in shared memory
-// and is read with broadcast LDS.128 -- so every distance is produced by exactly the
-// reference's sequential loop (see arith.cuh) while each stored vector is fetched once per QT
-// queries.  No distance matrix is written: each warp keeps a sorted top-k per query in
-// registers (WarpTopK), filters new distances against the k-th best with one ballot, merges
-// the NW per-warp lists through shared memory and writes k (dist, slot) pairs per
-// (query, item-part).  A second small kernel merges the parts per query by (dist, id).
+// Work item = (a run of 32-vector blocks, a tile of NW*QT queries).  A persistent CTA of NW
+// warps takes an item from an atomic counter.  The blocks of the run are staged into shared
+// memory by TMA bulk copies (cp.async.bulk + mbarrier, SCAN_STAGES-deep ring of 16 KB stages:
+// an IL32 block is one contiguous run of bytes, so a stage is a single bulk copy) issued by one
+// elected thread; every warp consumes every stage.  Warp w owns queries [w*QT, (w+1)*QT) of the
+// tile: lane l owns vector l of the staged block and walks its dimensions in order with QT
+// accumulators -- the query tile sits in shared memory and is read with broadcast LDS.128 -- so
+// every distance is produced by exactly the reference's sequential loop (see arith.cuh) while
+// each stored vector is fetched from HBM/L2 once per NW*QT queries.  No distance matrix is
+// written: each warp keeps a sorted top-k per query in registers (WarpTopK), filters new
+// distances against the k-th best with one ballot, and falls back to a shuffle bitonic merge
+// when many lanes pass.  Because a warp sees the whole run for its queries there is no
+// cross-warp merge; the warp writes k (dist, slot) pairs per (query, item-part).  A second small
+// kernel merges the parts per query by (dist, id).
 #pragma once
 #include "arith.cuh"
 
@@ -25,7 +29,7 @@ struct WorkItem {
     uint32_t blk_begin;   // first 32-vector block
     uint32_t nvec;        // valid vectors from blk_begin*32 on
     uint32_t qoff;        // first entry of the query tile (index into qmap, or query index)
-    uint32_t nq;          // queries in this tile (<= QT)
+    uint32_t nq;          // queries in this tile (<= NW*QT)
     uint32_t part;        // dense mode: which partial slot of the query this item fills
 };
 
@@ -38,8 +42,8 @@ struct ScanParams {
     // list mode
     const WorkItem *items;     // nullptr => dense mode
     const uint32_t *n_items_ptr;
-    const uint32_t *qmap;      // entry -> pair index p ; query = p / nprobe ; partial = p
-    uint32_t nprobe;
+    const uint32_t *qmap;      // entry -> pair index p ; query = p / nprobe
+    uint32_t nprobe;           // partial index (list mode) = item index * tile + position in tile
     // dense mode: item i -> seg = i / ntiles, tile = i % ntiles
     uint32_t dense_items, dense_ntiles, dense_seg_blocks, dense_nq, dense_nparts;
     uint64_t dense_nvec;
@@ -48,7 +52,16 @@ struct ScanParams {
     uint32_t *pslot;
 };
 
-constexpr int SCAN_NW = 8;     // warps per CTA
+constexpr int SCAN_STAGES = 3;        // TMA ring depth
+constexpr int SCAN_CH = 32;           // float4 chunks (of 32 lanes) per stage: 32 * 512 B = 16 KB
+constexpr int SCAN_STAGE_BYTES = SCAN_CH * 512;
+constexpr int SCAN_MAX_TILE = 64;     // NW * QT upper bound
+
+struct ScanShape {
+    int qt, nw, kr;
+    size_t smem;
+    int tile() const { return qt * nw; }
+};
 
 template <class QE> __device__ __forceinline__ void load_q4(const QE *q, QE &q0, QE &q1, QE &q2, QE &q3);
 template <> __device__ __forceinline__ void load_q4<float>(const float *q, float &q0, float &q1, float &q2, float &q3)
@@ -63,25 +76,112 @@ template <> __device__ __forceinline__ void load_q4<double>(const double *q, dou
     q0 = t0.x; q1 = t0.y; q2 = t1.x; q3 = t1.y;
 }
 
+// ---- mbarrier / TMA bulk-copy primitives (PTX ISA: mbarrier, cp.async.bulk) -------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");      // suspend-time hint: sleep, do not spin
+}
+// global -> shared bulk copy completing on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// the chunks of one staged block-part for the NQ live queries of a warp: lane l walks vector l;
+// the queries of the warp sit `qstride` elements apart in shared memory
+template <class P, int QT, int NQ>
+__device__ __forceinline__ void consume_stage(typename P::Acc (&acc)[QT], const float4 *sb, const typename P::Q *myq,
+                                              size_t qstride, int c0, int nf, int nch, int rem)
+{
+    using QE = typename P::Q;
+#pragma unroll 4
+    for (int c = 0; c < nf; c++) {
+        const float4 x = sb[c * 32];
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) {
+            QE q0, q1, q2, q3;
+            load_q4<QE>(myq + (size_t) qi * qstride + 4 * (c0 + c), q0, q1, q2, q3);
+            P::step(acc[qi], x.x, q0);
+            P::step(acc[qi], x.y, q1);
+            P::step(acc[qi], x.z, q2);
+            P::step(acc[qi], x.w, q3);
+        }
+    }
+    if (rem && nf < nch) {
+        // dim % 4 trailing elements: the pad is never fed to the accumulators (a zero element is
+        // not a no-op for the Kahan recurrence)
+        const float4 x = sb[nf * 32];
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) {
+            QE q0, q1, q2, q3;
+            load_q4<QE>(myq + (size_t) qi * qstride + 4 * (c0 + nf), q0, q1, q2, q3);
+            P::step(acc[qi], x.x, q0);
+            if (rem > 1) P::step(acc[qi], x.y, q1);
+            if (rem > 2) P::step(acc[qi], x.z, q2);
+        }
+    }
+}
+
 template <class P, int QT, int KR>
-__global__ void __launch_bounds__(SCAN_NW * 32) scan_topk_kernel(const ScanParams prm)
+__global__ void __launch_bounds__(256, 2) scan_topk_kernel(const ScanParams prm)
 {
     using QE = typename P::Q;
     using NT = typename P::N;
     using Acc = typename P::Acc;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    QE *qs = reinterpret_cast<QE *>(smem_raw);                       // [QT][dimp]
-    // cross-warp merge area after the query tile: [NW][QT][KR*32] (dist, slot)
-    float *md = reinterpret_cast<float *>(smem_raw + sizeof(QE) * (size_t) QT * prm.dimp);
-    uint32_t *ms = reinterpret_cast<uint32_t *>(md + SCAN_NW * QT * KR * 32);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [stage ring][query tile]
+    float4 *ring = reinterpret_cast<float4 *>(smem_raw);
+    QE *qs = reinterpret_cast<QE *>(smem_raw + SCAN_STAGES * SCAN_STAGE_BYTES);       // [NW*QT][dimp]
+    __shared__ __align__(8) uint64_t full_bar[SCAN_STAGES];    // TMA bytes of the stage have landed
+    __shared__ __align__(8) uint64_t empty_bar[SCAN_STAGES];   // all consumer warps are done with the stage
     __shared__ WorkItem s_item;
-    __shared__ uint32_t s_qidx[QT];     // global query index per tile entry
-    __shared__ uint32_t s_pidx[QT];     // partial-result index per tile entry
-    __shared__ NT s_qnorm[QT];
+    __shared__ uint32_t s_item_idx;
+    __shared__ uint32_t s_qidx[SCAN_MAX_TILE];     // global query index per tile entry
+    __shared__ uint32_t s_pidx[SCAN_MAX_TILE];     // partial-result index per tile entry
+    __shared__ NT s_qnorm[SCAN_MAX_TILE];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warps 0..NW-1 consume, warp NW is the TMA producer
+    const int nthreads = blockDim.x, NW = (nthreads >> 5) - 1, TQ = NW * QT;
     const int dimp = prm.dimp, dim = prm.dim, k = prm.k;
-    const int nfull = dim >> 2, rem = dim & 3;
+    const int nfull = dim >> 2, rem = dim & 3, nchunk = dimp >> 2;
+    const int spb = (nchunk + SCAN_CH - 1) / SCAN_CH;          // stages per 32-vector block
+
+    if (tid == 0) {
+        for (int s = 0; s < SCAN_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t git = 0;       // stages consumed so far by this CTA (ring position and phase)
 
     for (;;) {
         // ---- fetch the next work item ---------------------------------------------------
@@ -99,27 +199,30 @@ __global__ void __launch_bounds__(SCAN_NW * 32) scan_topk_kernel(const ScanParam
                 uint64_t cap = (uint64_t) prm.dense_seg_blocks * 32;
                 it.blk_begin = seg * prm.dense_seg_blocks;
                 it.nvec = (uint32_t) (left < cap ? left : cap);
-                it.qoff = tile * QT;
+                it.qoff = tile * TQ;
                 uint32_t ql = prm.dense_nq - it.qoff;
-                it.nq = ql < (uint32_t) QT ? ql : (uint32_t) QT;
+                it.nq = ql < (uint32_t) TQ ? ql : (uint32_t) TQ;
                 it.part = seg;
             } else {
                 it.nq = 0;
             }
             s_item = it;
+            s_item_idx = idx;
         }
         __syncthreads();
         const WorkItem item = s_item;
         if (item.nq == 0) break;
+        const uint32_t nblk = (item.nvec + 31) >> 5;
+        const uint32_t total = nblk * spb;
 
         // ---- stage the query tile ---------------------------------------------------------
-        if (tid < QT) {
+        if (tid < TQ) {
             uint32_t qi = 0, pi = 0;
             if (tid < (int) item.nq) {
                 if (prm.qmap) {
                     uint32_t p = prm.qmap[item.qoff + tid];
                     qi = p / prm.nprobe;
-                    pi = p;
+                    pi = s_item_idx * (uint32_t) TQ + (uint32_t) tid;
                 } else {
                     qi = item.qoff + tid;
                     pi = qi * prm.dense_nparts + item.part;
@@ -130,7 +233,7 @@ __global__ void __launch_bounds__(SCAN_NW * 32) scan_topk_kernel(const ScanParam
             if (P::NORMS) s_qnorm[tid] = tid < (int) item.nq ? reinterpret_cast<const NT *>(prm.qnorm)[qi] : NT(0);
         }
         __syncthreads();
-        for (int i = tid; i < QT * dimp; i += SCAN_NW * 32) {
+        for (int i = tid; i < TQ * dimp; i += nthreads) {
             int qi = i / dimp, dd = i - qi * dimp;
             float v = 0.0f;
             if (qi < (int) item.nq && dd < dim) v = prm.Q[(size_t) s_qidx[qi] * dim + dd];
@@ -138,88 +241,99 @@ __global__ void __launch_bounds__(SCAN_NW * 32) scan_topk_kernel(const ScanParam
         }
         __syncthreads();
 
+        // the live queries of the tile are dealt round-robin to the consumer warps (warp w owns tile
+        // positions w, w+NW, ...), so a partial tile keeps every warp busy with fewer queries each
+        const int myn = warp < NW && warp < (int) item.nq ? ((int) item.nq - warp + NW - 1) / NW : 0;
+        const bool active = myn > 0;
+        const QE *myq = qs + (size_t) warp * dimp;
+        const size_t qstride = (size_t) NW * dimp;
         WarpTopK<KR, uint32_t> top[QT];
 #pragma unroll
         for (int qi = 0; qi < QT; qi++) top[qi].init();
+        Acc acc[QT];
 
-        // ---- stream the blocks ------------------------------------------------------------
-        const uint32_t nblk = (item.nvec + 31) >> 5;
-        for (uint32_t b = warp; b < nblk; b += SCAN_NW) {
-            const uint32_t slot = (item.blk_begin + b) * 32 + lane;
-            const bool valid = b * 32 + lane < item.nvec;
-            const float4 *vp = prm.vecs + (size_t) (item.blk_begin + b) * (8 * (size_t) dimp) + lane;
-            Acc acc[QT];
-#pragma unroll
-            for (int qi = 0; qi < QT; qi++) P::init(acc[qi]);
-#pragma unroll 2
-            for (int c = 0; c < nfull; c++) {
-                const float4 x = __ldg(vp + (size_t) c * 32);
-#pragma unroll
-                for (int qi = 0; qi < QT; qi++) {
-                    QE q0, q1, q2, q3;
-                    load_q4<QE>(qs + (size_t) qi * dimp + 4 * c, q0, q1, q2, q3);
-                    P::step(acc[qi], x.x, q0);
-                    P::step(acc[qi], x.y, q1);
-                    P::step(acc[qi], x.z, q2);
-                    P::step(acc[qi], x.w, q3);
+        // ---- consume the stages ------------------------------------------------------------
+        if (warp == NW) {
+            // producer warp: one elected lane refills a ring slot as soon as every consumer warp
+            // has released it; stage st = (block st / spb, chunk range st % spb)
+            if (lane == 0) {
+                for (uint32_t st = 0; st < total; st++) {
+                    const uint32_t g = git + st, buf = g % SCAN_STAGES;
+                    mbar_wait(&empty_bar[buf], ((g / SCAN_STAGES) & 1u) ^ 1u);
+                    const uint32_t b = st / spb, r = st - b * spb;
+                    const uint32_t c0 = r * SCAN_CH;
+                    const uint32_t nch = min((uint32_t) SCAN_CH, (uint32_t) nchunk - c0);
+                    const float4 *src = prm.vecs + (size_t) (item.blk_begin + b) * (8 * (size_t) dimp) + (size_t) c0 * 32;
+                    mbar_arrive_expect_tx(&full_bar[buf], nch * 512u);
+                    tma_bulk_g2s(ring + (size_t) buf * (SCAN_STAGE_BYTES / 16), src, nch * 512u, &full_bar[buf]);
                 }
             }
-            if (rem) {
-                // dim % 4 trailing elements: the pad is never fed to the accumulators (a zero
-                // element is not a no-op for the Kahan recurrence)
-                const float4 x = __ldg(vp + (size_t) nfull * 32);
+        } else
+        for (uint32_t st = 0; st < total; st++) {
+            const uint32_t buf = (git + st) % SCAN_STAGES;
+            // warps without a live query still follow the ring so that the phases stay in step
+            mbar_wait(&full_bar[buf], ((git + st) / SCAN_STAGES) & 1u);
+            if (active) {
+                const uint32_t b = st / spb, r = st - b * spb;
+                const int c0 = (int) r * SCAN_CH;
+                const int nch = min(SCAN_CH, nchunk - c0);
+                const int nf = max(0, min(nch, nfull - c0));          // chunks with 4 live elements
+                const float4 *sb = ring + (size_t) buf * (SCAN_STAGE_BYTES / 16) + lane;
+                if (r == 0) {
 #pragma unroll
-                for (int qi = 0; qi < QT; qi++) {
-                    QE q0, q1, q2, q3;
-                    load_q4<QE>(qs + (size_t) qi * dimp + 4 * nfull, q0, q1, q2, q3);
-                    P::step(acc[qi], x.x, q0);
-                    if (rem > 1) P::step(acc[qi], x.y, q1);
-                    if (rem > 2) P::step(acc[qi], x.z, q2);
+                    for (int qi = 0; qi < QT; qi++) P::init(acc[qi]);
+                }
+                if (QT == 1) {
+                    consume_stage<P, QT, 1>(acc, sb, myq, qstride, c0, nf, nch, rem);
+                } else {
+                    switch (myn) {
+                    case 1: consume_stage<P, QT, 1>(acc, sb, myq, qstride, c0, nf, nch, rem); break;
+                    case 2: consume_stage<P, QT, (QT >= 2 ? 2 : 1)>(acc, sb, myq, qstride, c0, nf, nch, rem); break;
+                    case 3: consume_stage<P, QT, (QT >= 3 ? 3 : 1)>(acc, sb, myq, qstride, c0, nf, nch, rem); break;
+                    case 4: consume_stage<P, QT, (QT >= 4 ? 4 : 1)>(acc, sb, myq, qstride, c0, nf, nch, rem); break;
+                    case 5: consume_stage<P, QT, (QT >= 5 ? 5 : 1)>(acc, sb, myq, qstride, c0, nf, nch, rem); break;
+                    case 6: consume_stage<P, QT, (QT >= 6 ? 6 : 1)>(acc, sb, myq, qstride, c0, nf, nch, rem); break;
+                    case 7: consume_stage<P, QT, (QT >= 7 ? 7 : 1)>(acc, sb, myq, qstride, c0, nf, nch, rem); break;
+                    default: consume_stage<P, QT, QT>(acc, sb, myq, qstride, c0, nf, nch, rem); break;
+                    }
+                }
+                if (r == (uint32_t) spb - 1) {
+                    const uint32_t slot = (item.blk_begin + b) * 32 + lane;
+                    const bool valid = b * 32 + lane < item.nvec;
+                    NT xn = NT(0);
+                    if (P::NORMS) xn = valid ? reinterpret_cast<const NT *>(prm.vnorm)[slot] : NT(0);
+#pragma unroll
+                    for (int qi = 0; qi < QT; qi++) {
+                        if (qi < myn) {
+                            const float dist = P::finish(acc[qi], xn, P::NORMS ? s_qnorm[warp + qi * NW] : NT(0));
+                            top[qi].offer(dist, slot, valid, lane, k);
+                        }
+                    }
                 }
             }
-            NT xn = NT(0);
-            if (P::NORMS) xn = valid ? reinterpret_cast<const NT *>(prm.vnorm)[slot] : NT(0);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[buf]);       // this warp is done with the stage
+        }
+        git += total;
+
+        // ---- each warp writes the k best of its own queries --------------------------------
+        if (active) {
 #pragma unroll
             for (int qi = 0; qi < QT; qi++) {
-                const float dist = P::finish(acc[qi], xn, P::NORMS ? s_qnorm[qi] : NT(0));
-                top[qi].offer(dist, slot, valid && qi < (int) item.nq, lane, k);
-            }
-        }
-
-        // ---- merge the NW per-warp lists per query, write k results -----------------------
+                if (qi < myn) {
+                    const size_t base = (size_t) s_pidx[warp + qi * NW] * k;
 #pragma unroll
-        for (int qi = 0; qi < QT; qi++) {
-#pragma unroll
-            for (int r = 0; r < KR; r++) {
-                const int o = ((warp * QT + qi) * KR + r) * 32 + lane;
-                md[o] = top[qi].d[r];
-                ms[o] = top[qi].key[r];
-            }
-        }
-        __syncthreads();
-        for (int qi = warp; qi < (int) item.nq; qi += SCAN_NW) {
-            WarpTopK<KR, uint32_t> fin;
-            fin.init();
-            for (int w = 0; w < SCAN_NW; w++) {
-#pragma unroll
-                for (int r = 0; r < KR; r++) {
-                    const int o = ((w * QT + qi) * KR + r) * 32 + lane;
-                    const float cd = md[o];
-                    const uint32_t cs = ms[o];
-                    fin.offer(cd, cs, cs != INVALID_SLOT && r * 32 + lane < k, lane, k);
-                }
-            }
-            const size_t base = (size_t) s_pidx[qi] * k;
-#pragma unroll
-            for (int r = 0; r < KR; r++) {
-                const int e = r * 32 + lane;
-                if (e < k) {
-                    prm.pdist[base + e] = fin.d[r];
-                    prm.pslot[base + e] = fin.key[r];
+                    for (int r = 0; r < KR; r++) {
+                        const int e = r * 32 + lane;
+                        if (e < k) {
+                            prm.pdist[base + e] = top[qi].d[r];
+                            prm.pslot[base + e] = top[qi].key[r];
+                        }
+                    }
                 }
             }
         }
-        __syncthreads();   // smem is reused by the next item
+        __syncthreads();   // the query tile and s_* are rewritten by the next item
     }
 }
 

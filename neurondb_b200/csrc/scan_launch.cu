@@ -4,64 +4,91 @@
 
 namespace ndb {
 
-static size_t scan_smem_bytes(size_t qelem, int qt, int kr, int dimp)
-{
-    return qelem * (size_t) qt * dimp + (size_t) SCAN_NW * qt * kr * 32 * 8;
-}
-
 static size_t qelem_size(int arith) { return arith == NDB_ARITH_OP_F64 ? 8 : 4; }
 
 static int kr_for(int k) { return k <= 32 ? 1 : (k <= 128 ? 4 : 0); }
 
-int scan_pick_qt(int arith, int dim, int k)
+static size_t scan_smem_bytes(size_t qelem, int tile, int dimp)
+{
+    return (size_t) SCAN_STAGES * SCAN_STAGE_BYTES + qelem * (size_t) tile * dimp;
+}
+
+// tile shape for (arith, dim, k): QT queries per warp, NW warps per CTA.  Prefer 8 x 8 with two
+// CTAs per SM; shrink the CTA, then the per-warp tile, until the query tile fits in shared memory.
+static bool scan_shape(int arith, int dim, int k, ScanShape *out)
 {
     const int kr = kr_for(k);
-    if (kr == 0 || dim <= 0) return 0;
+    if (kr == 0 || dim <= 0) return false;
     const int dimp = round_up(dim, 4);
-    const size_t limit = ctx().smem_optin ? ctx().smem_optin - 1024 : 200 * 1024;
-    if (scan_smem_bytes(qelem_size(arith), 8, kr, dimp) <= limit) return 8;
-    if (scan_smem_bytes(qelem_size(arith), 1, kr, dimp) <= limit) return 1;
-    return 0;
+    const size_t limit = (ctx().smem_optin ? ctx().smem_optin : 227 * 1024) - 2048;
+    const size_t qe = qelem_size(arith);
+    // consumer warps per CTA: 7, 3 or 1 (+1 producer warp = 256, 128 or 64 threads).
+    // NDB_SCAN_NW is a tuning knob for experiments (profiles/), not a user setting.
+    static const int nw_max = [] { const char *e = getenv("NDB_SCAN_NW"); int v = e ? atoi(e) : 7; return (v == 1 || v == 3 || v == 7) ? v : 7; }();
+    for (int pass = 0; pass < 2; pass++) {
+        const size_t budget = pass == 0 ? limit / 2 : limit;
+        for (int qt = 8; qt >= 1; qt = (qt == 8 ? 1 : 0)) {
+            for (int nw = nw_max; nw >= 1; nw >>= 1) {
+                if (pass == 0 && nw < 3 && nw_max >= 3) continue;
+                const size_t smem = scan_smem_bytes(qe, qt * nw, dimp);
+                if (smem <= budget) {
+                    out->qt = qt; out->nw = nw; out->kr = kr; out->smem = smem;
+                    return true;
+                }
+            }
+            if (qt == 1) break;
+        }
+    }
+    return false;
+}
+
+int scan_pick_qt(int arith, int dim, int k)
+{
+    ScanShape sh;
+    return scan_shape(arith, dim, k, &sh) ? sh.tile() : 0;
 }
 
 template <class P, int QT, int KR>
-static int launch_one(const ScanParams &prm, uint32_t items_upper, cudaStream_t s)
+static int launch_one(const ScanParams &prm, const ScanShape &sh, uint32_t items_upper, cudaStream_t s)
 {
     auto kern = scan_topk_kernel<P, QT, KR>;
-    const size_t smem = scan_smem_bytes(sizeof(typename P::Q), QT, KR, prm.dimp);
     static thread_local size_t configured = 0;
-    if (smem > configured) {
-        NDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        configured = smem;
+    if (sh.smem > configured) {
+        NDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sh.smem));
+        configured = sh.smem;
     }
     int per_sm = 0;
-    NDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SCAN_NW * 32, smem));
+    NDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (sh.nw + 1) * 32, sh.smem));
     if (per_sm < 1) per_sm = 1;
     uint32_t grid = (uint32_t) ctx().sm_count * (uint32_t) per_sm;
     if (items_upper < grid) grid = items_upper;
     if (grid == 0) return NDB_B200_OK;
     NDB_CUDA(cudaMemsetAsync(prm.counter, 0, sizeof(uint32_t), s));
-    kern<<<grid, SCAN_NW * 32, smem, s>>>(prm);
+    kern<<<grid, (sh.nw + 1) * 32, sh.smem, s>>>(prm);      // nw consumer warps + 1 TMA producer warp
     count_launch();
     NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
 }
 
-template <class P> static int launch_policy(int qt, const ScanParams &prm, uint32_t items_upper, cudaStream_t s)
+template <class P> static int launch_policy(const ScanShape &sh, const ScanParams &prm, uint32_t items_upper, cudaStream_t s)
 {
-    const int kr = kr_for(prm.k);
-    if (qt == 8 && kr == 1) return launch_one<P, 8, 1>(prm, items_upper, s);
-    if (qt == 8 && kr == 4) return launch_one<P, 8, 4>(prm, items_upper, s);
-    if (qt == 1 && kr == 1) return launch_one<P, 1, 1>(prm, items_upper, s);
-    if (qt == 1 && kr == 4) return launch_one<P, 1, 4>(prm, items_upper, s);
-    set_error("scan: unsupported tile/k combination qt=%d k=%d", qt, prm.k);
+    if (sh.qt == 8 && sh.kr == 1) return launch_one<P, 8, 1>(prm, sh, items_upper, s);
+    if (sh.qt == 8 && sh.kr == 4) return launch_one<P, 8, 4>(prm, sh, items_upper, s);
+    if (sh.qt == 1 && sh.kr == 1) return launch_one<P, 1, 1>(prm, sh, items_upper, s);
+    if (sh.qt == 1 && sh.kr == 4) return launch_one<P, 1, 4>(prm, sh, items_upper, s);
+    set_error("scan: unsupported tile/k combination qt=%d k=%d", sh.qt, prm.k);
     return NDB_B200_EINVAL;
 }
 
-int launch_scan(int metric, int arith, int qt, const ScanParams &prm, uint32_t items_upper, cudaStream_t s)
+int launch_scan(int metric, int arith, int tile, const ScanParams &prm, uint32_t items_upper, cudaStream_t s)
 {
+    ScanShape sh;
+    if (!scan_shape(arith, prm.dim, prm.k, &sh) || sh.tile() != tile) {
+        set_error("scan: tile %d does not match the shape for dim=%d k=%d", tile, prm.dim, prm.k);
+        return NDB_B200_EINVAL;
+    }
 #define NDB_SCAN_CASE(M, A) \
-    if (metric == M && arith == A) return launch_policy<Arith<M, A>>(qt, prm, items_upper, s);
+    if (metric == M && arith == A) return launch_policy<Arith<M, A>>(sh, prm, items_upper, s);
     NDB_SCAN_CASE(NDB_L2, NDB_ARITH_IVF_F32)
     NDB_SCAN_CASE(METRIC_L2SQ, NDB_ARITH_IVF_F32)
     NDB_SCAN_CASE(NDB_COSINE, NDB_ARITH_IVF_F32)
