@@ -123,9 +123,14 @@ __device__ __forceinline__ void consume_stage(typename P::Acc (&acc)[QT], const 
                                               size_t qstride, int c0, int nf, int nch, int rem)
 {
     using QE = typename P::Q;
-#pragma unroll 4
+    // One chunk per iteration: NQ * 12 FP instructions is already NQ independent chains, and a
+    // body of ~100 instructions stays inside the 6 KB L0 instruction cache (an unroll of 4 does
+    // not: ncu showed no_instruction as the top stall).  The next x is fetched one chunk ahead.
+    float4 xn = nf > 0 ? sb[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
     for (int c = 0; c < nf; c++) {
-        const float4 x = sb[c * 32];
+        const float4 x = xn;
+        if (c + 1 < nf) xn = sb[(c + 1) * 32];
 #pragma unroll
         for (int qi = 0; qi < NQ; qi++) {
             QE q0, q1, q2, q3;

@@ -1,0 +1,76 @@
+"""Generate the golden vectors under tests/golden/ (run in the build container, where
+/root/reference exists and oracle/_ref/*.so have been built by `make -C oracle`).
+
+operator_distances.npz : outputs of the REFERENCE's own vector_l2_distance / vector_cosine_distance /
+    vector_inner_product (NeuronDB/src/vector/vector_distance.c + vector_distance_simd.c compiled
+    unmodified under oracle/pgshim), default scalar build and -mavx2 -mfma build, on seeded inputs.
+index_paths.npz : outputs of the oracle restatement for the IVF / HNSW / k-means paths (the reference's
+    tests pin nothing there -- SURVEY.md 8c -- so these are regression vectors, not reference outputs).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import oracle_lib as O  # noqa: E402
+import workloads as W  # noqa: E402
+
+DIMS = [1, 2, 3, 4, 7, 8, 9, 15, 16, 17, 31, 33, 96, 128, 768]
+
+
+def operator_inputs(dim):
+    rng = np.random.default_rng(1000 + dim)
+    A = rng.standard_normal((48, dim)).astype(np.float32)
+    B = rng.standard_normal((48, dim)).astype(np.float32)
+    A[0] = 0.0                                   # zero vector (cosine -> 1.0)
+    B[1] = A[1]                                  # identical
+    A[2] *= 1e18; B[2] *= 1e-18                  # wide dynamic range
+    B[3] = -A[3]                                 # opposite (cosine -> 2)
+    return A, B
+
+
+def main():
+    assert O.ref_lib() is not None, "build oracle/_ref first (make -C oracle)"
+    out = {}
+    for dim in DIMS:
+        A, B = operator_inputs(dim)
+        for metric in (1, 2, 3):
+            out["scalar_m%d_d%d" % (metric, dim)] = O.ref_distance_pairs(metric, A, B)
+            out["avx2_m%d_d%d" % (metric, dim)] = O.ref_distance_pairs(metric, A, B, avx2=True)
+    np.savez_compressed(os.path.join(HERE, "operator_distances.npz"), **out)
+
+    idx = {}
+    X = W.mixture(3000, 16, 12, 5)
+    Q = W.mixture(40, 16, 12, 6, centers_seed=5)
+    C, assign, counts, iters, cost = O.kmeans_train(X[:1200], 12)
+    idx.update(km_C=C, km_assign=assign, km_counts=counts, km_iters=np.int32(iters), km_cost=np.float32(cost))
+    lists = O.ivf_assign(X, C)
+    off, rows = O.lists_from_assignment(lists, 12)
+    for lit in (0, 1):
+        for metric in (1, 2, 3):
+            d, i, cnt = O.ivf_search(X, C, off, rows, Q, 4, 10, strategy=metric, literal=bool(lit))
+            idx["ivf_d_l%d_m%d" % (lit, metric)] = d
+            idx["ivf_i_l%d_m%d" % (lit, metric)] = i
+    idx["ivf_lists"] = lists
+    levels = O.hnsw_levels(1500, seed=9)
+    idx["hnsw_levels"] = levels
+    for mode in (0, 1):
+        g = O.Hnsw(16, 6, 24, 24, capacity=1500)
+        g.build(X[:1500], levels, mode)
+        e = g.export()
+        idx["hnsw_nbr0_b%d" % mode] = e["nbr0"]
+        idx["hnsw_cnt_b%d" % mode] = e["cnt"]
+        for smode in (0, 1):
+            d, n, c = g.search(Q, 24, 10, 1, smode)
+            idx["hnsw_d_b%d_s%d" % (mode, smode)] = d
+            idx["hnsw_n_b%d_s%d" % (mode, smode)] = n
+    d, i = O.knn_exact(X, Q, 10, 1, O.ARITH_OP_F64)
+    idx.update(knn_d=d, knn_i=i)
+    np.savez_compressed(os.path.join(HERE, "index_paths.npz"), **idx)
+    print("wrote", sorted(os.listdir(HERE)))
+
+
+if __name__ == "__main__":
+    main()

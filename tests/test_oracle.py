@@ -1,0 +1,191 @@
+"""CPU: the oracle against the reference's known answers, the reference's own compiled operator
+sources (when present) and the committed golden vectors."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import workloads as W
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BITS = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _golden_mod():
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def d1(fn, a, b, *extra):
+    a, b = O.f32(a), O.f32(b)
+    return fn(a, b, a.size, *extra)
+
+
+def test_known_answers_t005():
+    """NeuronDB/t/005_distances_comprehensive.t:40-56,140-158,248-255."""
+    l = O.lib()
+    assert d1(l.orc_l2_distance, [0, 0], [3, 4]) == 5.0
+    assert d1(l.orc_l2_distance, [1, 2, 3], [1, 2, 3]) == 0.0
+    assert d1(l.orc_l2_distance, [0, 0], [0, 0]) == 0.0
+    assert d1(l.orc_cosine_distance, [1, 0], [0, 1]) == 1.0
+    assert d1(l.orc_cosine_distance, [1, 0], [1, 0]) == 0.0
+    assert d1(l.orc_cosine_distance, [1, 0], [-1, 0]) == 2.0
+    assert d1(l.orc_inner_product_op, [1, 2, 3], [4, 5, 6]) == 32.0          # <#> yields +dot
+    assert d1(l.orc_inner_product_distance, [1, 2, 3], [4, 5, 6]) == -32.0
+    assert d1(l.orc_inner_product_op, [1, 0], [0, 1]) == 0.0
+    assert d1(l.orc_cosine_distance, [0, 0], [1, 0]) == 1.0                  # vector_distance.c:201-202
+    assert d1(l.orc_hnsw_distance, [0, 0], [1, 0], 2) == 2.0                 # hnsw_am.c:1329-1330 (Q15)
+    assert d1(l.orc_ivf_distance, [0, 0], [1, 0], 2) == 1.0
+    assert l.orc_check_vector(O.f32([1, np.nan, 2]), 3) == 1
+    assert l.orc_check_vector(O.f32([1, 2, np.inf]), 3) == 2
+    assert l.orc_check_vector(O.f32([1, 2, 3]), 3) == -1
+
+
+def test_golden_operator_distances():
+    """Outputs of the reference's own fmgr functions, committed as fixtures."""
+    g = np.load(os.path.join(HERE, "golden", "operator_distances.npz"))
+    mg = _golden_mod()
+    for dim in mg.DIMS:
+        A, B = mg.operator_inputs(dim)
+        for metric in (1, 2, 3):
+            got = O.distance_pairs(A, B, metric, O.ARITH_OP_F64)
+            assert np.array_equal(BITS(got), BITS(g["scalar_m%d_d%d" % (metric, dim)])), (dim, metric)
+            got = O.distance_pairs(A, B, metric, O.ARITH_AVX2)
+            assert np.array_equal(BITS(got), BITS(g["avx2_m%d_d%d" % (metric, dim)])), (dim, metric, "avx2")
+
+
+@pytest.mark.skipif(O.ref_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_oracle_equals_reference_build_bit_for_bit():
+    rng = np.random.default_rng(42)
+    for dim in [1, 5, 8, 13, 16, 29, 64, 128, 200, 768, 1536]:
+        A = (rng.standard_normal((300, dim)) * rng.choice([1e-3, 1.0, 1e3])).astype(np.float32)
+        B = rng.standard_normal((300, dim)).astype(np.float32)
+        for metric in (1, 2, 3):
+            assert np.array_equal(BITS(O.ref_distance_pairs(metric, A, B)),
+                                  BITS(O.distance_pairs(A, B, metric, O.ARITH_OP_F64))), (dim, metric)
+            assert np.array_equal(BITS(O.ref_distance_pairs(metric, A, B, avx2=True)),
+                                  BITS(O.distance_pairs(A, B, metric, O.ARITH_AVX2))), (dim, metric, "avx2")
+
+
+@pytest.mark.skipif(O.ref_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_reference_error_behaviour():
+    """dimension mismatch / NaN / Inf are rejected (t/005:106-132,285-300; vector_distance.c:34-74)."""
+    rc, _, msg = O.ref_distance(1, [1, 2], [1, 2, 3])
+    assert rc != 0 and "dimension" in msg
+    rc, _, msg = O.ref_distance(1, [np.nan, 1], [1, 2])
+    assert rc != 0 and "NaN" in msg
+    rc, _, msg = O.ref_distance(2, [np.inf, 1], [1, 2])
+    assert rc != 0
+    rc, v, _ = O.ref_distance(1, [0, 0], [3, 4])
+    assert rc == 0 and v == 5.0
+
+
+def test_golden_index_paths():
+    g = np.load(os.path.join(HERE, "golden", "index_paths.npz"))
+    X = W.mixture(3000, 16, 12, 5)
+    Q = W.mixture(40, 16, 12, 6, centers_seed=5)
+    C, assign, counts, iters, cost = O.kmeans_train(X[:1200], 12)
+    assert np.array_equal(BITS(C), BITS(g["km_C"])) and np.array_equal(assign, g["km_assign"])
+    assert iters == int(g["km_iters"]) and np.float32(cost) == g["km_cost"]
+    lists = O.ivf_assign(X, C)
+    assert np.array_equal(lists, g["ivf_lists"])
+    off, rows = O.lists_from_assignment(lists, 12)
+    for lit in (0, 1):
+        for metric in (1, 2, 3):
+            d, i, _ = O.ivf_search(X, C, off, rows, Q, 4, 10, strategy=metric, literal=bool(lit))
+            assert np.array_equal(i, g["ivf_i_l%d_m%d" % (lit, metric)])
+            assert np.array_equal(BITS(d), BITS(g["ivf_d_l%d_m%d" % (lit, metric)]))
+    levels = O.hnsw_levels(1500, seed=9)
+    assert np.array_equal(levels, g["hnsw_levels"])
+    for mode in (0, 1):
+        h = O.Hnsw(16, 6, 24, 24, capacity=1500)
+        h.build(X[:1500], levels, mode)
+        e = h.export()
+        assert np.array_equal(e["nbr0"], g["hnsw_nbr0_b%d" % mode])
+        for smode in (0, 1):
+            d, n, _ = h.search(Q, 24, 10, 1, smode)
+            assert np.array_equal(n, g["hnsw_n_b%d_s%d" % (mode, smode)])
+    d, i = O.knn_exact(X, Q, 10, 1, O.ARITH_OP_F64)
+    assert np.array_equal(i, g["knn_i"]) and np.array_equal(BITS(d), BITS(g["knn_d"]))
+
+
+def test_kmeans_literal_semantics():
+    """centroids := first k samples (Q8); empty clusters stay at zero; strict < keeps the lowest index."""
+    X = np.zeros((40, 3), np.float32)
+    X[:, 0] = np.arange(40) % 4                     # four distinct points, many duplicates
+    C, assign, counts, iters, cost = O.kmeans_train(X, 6, max_iter=50, threshold=0.001)
+    # samples 4,5 duplicate samples 0,1: centroids 4,5 start equal to 0,1 and lose every tie
+    assert counts[4] == 0 and counts[5] == 0
+    assert np.all(C[4] == 0) and np.all(C[5] == 0)
+    assert sorted(np.unique(assign).tolist()) == [0, 1, 2, 3]
+    assert cost == 0.0 and iters == 2               # second pass: |prev - cost| = 0 < 0.001
+    assert O.lib().orc_ivf_train_samples(1_000_000, 1024) == 10000
+    assert O.lib().orc_ivf_train_samples(1_000_000, 50) == 5000
+    assert O.lib().orc_ivf_train_samples(300, 50) == 300
+
+
+def test_ivf_literal_cap_and_ties():
+    """k*10 candidate cap in probe order (Q9); select_clusters ties go to the lowest list id."""
+    X = W.gaussian(2000, 8, 3)
+    C = X[:4].copy()
+    C[1] = C[0]                                      # two identical centroids
+    probes = O.select_clusters(X[0], C, 4)
+    assert probes[0] == 0 and probes[1] == 1         # equal distance: lower index first
+    lists = O.ivf_assign(X, C)
+    assert not np.any(lists == 1)                    # strict <: the duplicate never wins
+    off, rows = O.lists_from_assignment(lists, 4)
+    d_lit, i_lit, c_lit = O.ivf_search(X, C, off, rows, X[:20], 4, 10, literal=True)
+    d_full, i_full, _ = O.ivf_search(X, C, off, rows, X[:20], 4, 10, literal=False)
+    assert np.all(c_lit == 10)
+    # the capped scan only ever sees the first 100 entries in probe order
+    for q in range(20):
+        first = []
+        for l in O.select_clusters(X[q], C, 4):
+            first += rows[off[l]:off[l + 1]].tolist()
+        assert set(i_lit[q]) <= set(first[:100])
+    assert np.all(d_full[:, 0] == 0.0) and np.all(i_full[:, 0] == np.arange(20))
+    assert np.all(d_full <= d_lit + 1e-30)
+
+
+def test_knn_ties_by_id_and_recall():
+    X = np.tile(np.arange(8, dtype=np.float32)[:, None], (3, 4))        # rows 0..7 three times
+    ids = np.arange(24)[::-1].copy()                                     # descending ids
+    d, i = O.knn_exact(X, X[:2], 6, 1, O.ARITH_OP_F64, ids=ids)
+    assert np.all(d[0, :3] == 0) and i[0, :3].tolist() == sorted(i[0, :3].tolist())
+    assert O.recall_at_k(np.array([[1, 2, 3, 4]]), np.array([[4, 3, 9, 8]])) == 0.5
+
+
+def test_merge_topk_matches_lexsort():
+    rng = np.random.default_rng(0)
+    d = rng.integers(0, 9, size=(3, 20, 5)).astype(np.float32)
+    ids = rng.permutation(300).reshape(3, 20, 5).astype(np.int64)
+    md, mi = O.merge_topk(d, ids)
+    for q in range(20):
+        dd = d[:, q, :].reshape(-1); ii = ids[:, q, :].reshape(-1)
+        order = np.lexsort((ii, dd))[:5]
+        assert np.array_equal(mi[q], ii[order]) and np.array_equal(md[q], dd[order])
+
+
+def test_hnsw_oracle_properties():
+    X = W.gaussian(1200, 12, 21)
+    Q = W.gaussian(50, 12, 22)
+    levels = O.hnsw_levels(1200, seed=4)
+    assert levels.min() == 0 and levels.max() < 16 and 0.02 < (levels > 0).mean() < 0.12   # P(level>=1)=e^(-1/0.36)
+    gt = W.exact_ground_truth(X, Q, 10)
+    g = O.Hnsw(12, 8, 40, 40, capacity=1200)
+    g.build(X, levels, 1)
+    d, n, cnt = g.search(Q, 64, 10, 1, 1)
+    assert np.all(cnt == 10) and np.all(np.diff(d, axis=1) >= 0)
+    assert O.recall_at_k(n.astype(np.int64), gt) > 0.9
+    # the literal BFS stops at ef candidates: never more than ef + 2m evaluations at level 0
+    g.search(Q, 16, 10, 1, 0)
+    lit_evals = g.distance_evals()
+    g.search(Q, 16, 10, 1, 1)
+    assert lit_evals < g.distance_evals()
+    e = g.export()
+    assert np.all(e["cnt"] <= 16) and e["nbr0"].shape == (1200, 16)
+    assert np.all((e["nbr0"] == 0xFFFFFFFF) | (e["nbr0"] < 1200))
