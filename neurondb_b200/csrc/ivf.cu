@@ -59,7 +59,7 @@ __host__ __device__ inline uint32_t ivf_nseg(uint32_t len, uint32_t segb)
 }
 static uint32_t ivf_seg_blocks()
 {
-    static const uint32_t v = [] { const char *e = getenv("NDB_IVF_SEG_BLOCKS"); int x = e ? atoi(e) : 32; return (uint32_t) (x >= 1 ? x : 32); }();
+    static const uint32_t v = [] { const char *e = getenv("NDB_IVF_SEG_BLOCKS"); int x = e ? atoi(e) : 64; return (uint32_t) (x >= 1 ? x : 64); }();
     return v;
 }
 

@@ -156,8 +156,201 @@ __device__ __forceinline__ void consume_stage(typename P::Acc (&acc)[QT], const 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// direct variant: no shared-memory ring.  Every warp streams the item's blocks itself with
+// coalesced 128-bit loads (one 512-byte warp-load per 4 dimensions, PF chunks in flight in
+// registers); the NW warps of a CTA read the same blocks at about the same time, so all but
+// the first reader hit L1.  Warps never wait for each other inside an item.
+// ---------------------------------------------------------------------------------------
+template <class P, int QT, int NQ>
+__device__ __forceinline__ void consume_block_direct(typename P::Acc (&acc)[QT], const float4 *vp, const typename P::Q *myq,
+                                                     size_t qstride, int nfull, int rem)
+{
+    using QE = typename P::Q;
+    constexpr int PF = 4;
+    const int ntot = nfull + (rem ? 1 : 0);
+    float4 xb[PF];
+#pragma unroll
+    for (int i = 0; i < PF; i++) xb[i] = i < ntot ? __ldg(vp + (size_t) i * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int c = 0;
+    for (; c + PF <= nfull; c += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) {
+            const float4 x = xb[u];
+            if (c + u + PF < ntot) xb[u] = __ldg(vp + (size_t) (c + u + PF) * 32);
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) {
+                QE q0, q1, q2, q3;
+                load_q4<QE>(myq + (size_t) qi * qstride + 4 * (c + u), q0, q1, q2, q3);
+                P::step(acc[qi], x.x, q0);
+                P::step(acc[qi], x.y, q1);
+                P::step(acc[qi], x.z, q2);
+                P::step(acc[qi], x.w, q3);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+        const float4 x = xb[u];
+        if (c + u < nfull) {
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) {
+                QE q0, q1, q2, q3;
+                load_q4<QE>(myq + (size_t) qi * qstride + 4 * (c + u), q0, q1, q2, q3);
+                P::step(acc[qi], x.x, q0);
+                P::step(acc[qi], x.y, q1);
+                P::step(acc[qi], x.z, q2);
+                P::step(acc[qi], x.w, q3);
+            }
+        } else if (c + u == nfull && rem) {
+            // dim % 4 trailing elements (the pad is never fed to the accumulators)
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) {
+                QE q0, q1, q2, q3;
+                load_q4<QE>(myq + (size_t) qi * qstride + 4 * (c + u), q0, q1, q2, q3);
+                P::step(acc[qi], x.x, q0);
+                if (rem > 1) P::step(acc[qi], x.y, q1);
+                if (rem > 2) P::step(acc[qi], x.z, q2);
+            }
+        }
+    }
+}
+
 template <class P, int QT, int KR>
-__global__ void __launch_bounds__(256, 2) scan_topk_kernel(const ScanParams prm)
+__global__ void __launch_bounds__(256, 2) scan_topk_direct_kernel(const ScanParams prm)
+{
+    using QE = typename P::Q;
+    using NT = typename P::N;
+    using Acc = typename P::Acc;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    QE *qs = reinterpret_cast<QE *>(smem_raw);       // [NW*QT][dimp]
+    __shared__ WorkItem s_item;
+    __shared__ uint32_t s_item_idx;
+    __shared__ uint32_t s_qidx[SCAN_MAX_TILE];
+    __shared__ uint32_t s_pidx[SCAN_MAX_TILE];
+    __shared__ NT s_qnorm[SCAN_MAX_TILE];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x, NW = nthreads >> 5, TQ = NW * QT;
+    const int dimp = prm.dimp, dim = prm.dim, k = prm.k;
+    const int nfull = dim >> 2, rem = dim & 3;
+
+    for (;;) {
+        if (tid == 0) {
+            uint32_t idx = atomicAdd(prm.counter, 1u);
+            WorkItem it;
+            if (prm.items) {
+                uint32_t n = *prm.n_items_ptr;
+                if (idx < n) it = prm.items[idx];
+                else it.nq = 0;
+            } else if (idx < prm.dense_items) {
+                uint32_t seg = idx / prm.dense_ntiles, tile = idx % prm.dense_ntiles;
+                uint64_t v0 = (uint64_t) seg * prm.dense_seg_blocks * 32;
+                uint64_t left = prm.dense_nvec - v0;
+                uint64_t cap = (uint64_t) prm.dense_seg_blocks * 32;
+                it.blk_begin = seg * prm.dense_seg_blocks;
+                it.nvec = (uint32_t) (left < cap ? left : cap);
+                it.qoff = tile * TQ;
+                uint32_t ql = prm.dense_nq - it.qoff;
+                it.nq = ql < (uint32_t) TQ ? ql : (uint32_t) TQ;
+                it.part = seg;
+            } else {
+                it.nq = 0;
+            }
+            s_item = it;
+            s_item_idx = idx;
+        }
+        __syncthreads();
+        const WorkItem item = s_item;
+        if (item.nq == 0) break;
+        const uint32_t nblk = (item.nvec + 31) >> 5;
+
+        if (tid < TQ) {
+            uint32_t qi = 0, pi = 0;
+            if (tid < (int) item.nq) {
+                if (prm.qmap) {
+                    uint32_t p = prm.qmap[item.qoff + tid];
+                    qi = p / prm.nprobe;
+                    pi = s_item_idx * (uint32_t) TQ + (uint32_t) tid;
+                } else {
+                    qi = item.qoff + tid;
+                    pi = qi * prm.dense_nparts + item.part;
+                }
+            }
+            s_qidx[tid] = qi;
+            s_pidx[tid] = pi;
+            if (P::NORMS) s_qnorm[tid] = tid < (int) item.nq ? reinterpret_cast<const NT *>(prm.qnorm)[qi] : NT(0);
+        }
+        __syncthreads();
+        for (int i = tid; i < TQ * dimp; i += nthreads) {
+            int qi = i / dimp, dd = i - qi * dimp;
+            float v = 0.0f;
+            if (qi < (int) item.nq && dd < dim) v = prm.Q[(size_t) s_qidx[qi] * dim + dd];
+            qs[i] = (QE) v;
+        }
+        __syncthreads();
+
+        // live queries dealt round-robin: warp w owns tile positions w, w+NW, ...
+        const int myn = warp < (int) item.nq ? ((int) item.nq - warp + NW - 1) / NW : 0;
+        const QE *myq = qs + (size_t) warp * dimp;
+        const size_t qstride = (size_t) NW * dimp;
+        WarpTopK<KR, uint32_t> top[QT];
+#pragma unroll
+        for (int qi = 0; qi < QT; qi++) top[qi].init();
+
+        if (myn > 0) {
+            for (uint32_t b = 0; b < nblk; b++) {
+                const float4 *vp = prm.vecs + (size_t) (item.blk_begin + b) * (8 * (size_t) dimp) + lane;
+                Acc acc[QT];
+#pragma unroll
+                for (int qi = 0; qi < QT; qi++) P::init(acc[qi]);
+                if (QT == 1) {
+                    consume_block_direct<P, QT, 1>(acc, vp, myq, qstride, nfull, rem);
+                } else {
+                    switch (myn) {
+                    case 1: consume_block_direct<P, QT, 1>(acc, vp, myq, qstride, nfull, rem); break;
+                    case 2: consume_block_direct<P, QT, (QT >= 2 ? 2 : 1)>(acc, vp, myq, qstride, nfull, rem); break;
+                    case 3: consume_block_direct<P, QT, (QT >= 3 ? 3 : 1)>(acc, vp, myq, qstride, nfull, rem); break;
+                    case 4: consume_block_direct<P, QT, (QT >= 4 ? 4 : 1)>(acc, vp, myq, qstride, nfull, rem); break;
+                    case 5: consume_block_direct<P, QT, (QT >= 5 ? 5 : 1)>(acc, vp, myq, qstride, nfull, rem); break;
+                    case 6: consume_block_direct<P, QT, (QT >= 6 ? 6 : 1)>(acc, vp, myq, qstride, nfull, rem); break;
+                    case 7: consume_block_direct<P, QT, (QT >= 7 ? 7 : 1)>(acc, vp, myq, qstride, nfull, rem); break;
+                    default: consume_block_direct<P, QT, QT>(acc, vp, myq, qstride, nfull, rem); break;
+                    }
+                }
+                const uint32_t slot = (item.blk_begin + b) * 32 + lane;
+                const bool valid = b * 32 + lane < item.nvec;
+                NT xn = NT(0);
+                if (P::NORMS) xn = valid ? reinterpret_cast<const NT *>(prm.vnorm)[slot] : NT(0);
+#pragma unroll
+                for (int qi = 0; qi < QT; qi++) {
+                    if (qi < myn) {
+                        const float dist = P::finish(acc[qi], xn, P::NORMS ? s_qnorm[warp + qi * NW] : NT(0));
+                        top[qi].offer(dist, slot, valid, lane, k);
+                    }
+                }
+            }
+#pragma unroll
+            for (int qi = 0; qi < QT; qi++) {
+                if (qi < myn) {
+                    const size_t base = (size_t) s_pidx[warp + qi * NW] * k;
+#pragma unroll
+                    for (int r = 0; r < KR; r++) {
+                        const int e = r * 32 + lane;
+                        if (e < k) {
+                            prm.pdist[base + e] = top[qi].d[r];
+                            prm.pslot[base + e] = top[qi].key[r];
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // the query tile and s_* are rewritten by the next item
+    }
+}
+
+template <class P, int QT, int KR>
+__global__ void __maxnreg__(112) scan_topk_kernel(const ScanParams prm)
 {
     using QE = typename P::Q;
     using NT = typename P::N;

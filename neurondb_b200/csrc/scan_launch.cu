@@ -22,14 +22,15 @@ static bool scan_shape(int arith, int dim, int k, ScanShape *out)
     const int dimp = round_up(dim, 4);
     const size_t limit = (ctx().smem_optin ? ctx().smem_optin : 227 * 1024) - 2048;
     const size_t qe = qelem_size(arith);
-    // consumer warps per CTA: 7, 3 or 1 (+1 producer warp = 256, 128 or 64 threads).
-    // NDB_SCAN_NW is a tuning knob for experiments (profiles/), not a user setting.
-    static const int nw_max = [] { const char *e = getenv("NDB_SCAN_NW"); int v = e ? atoi(e) : 7; return (v == 1 || v == 3 || v == 7) ? v : 7; }();
+    // consumer warps per CTA: 4 by default (measured on B200, profiles/r01_scan_variants.txt: CTAs
+    // of 4 + 1 warps with three CTAs per SM beat 8 + 1 with two -- smaller groups of warps
+    // moving in step through the ring).  NDB_SCAN_NW is a tuning knob for experiments only.
+    static const int nw_max = [] { const char *e = getenv("NDB_SCAN_NW"); int v = e ? atoi(e) : 4; return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4; }();
     for (int pass = 0; pass < 2; pass++) {
         const size_t budget = pass == 0 ? limit / 2 : limit;
-        for (int qt = 8; qt >= 1; qt = (qt == 8 ? 1 : 0)) {
+        for (int qt = 8; qt >= 1; qt = (qt > 1 ? 1 : 0)) {
             for (int nw = nw_max; nw >= 1; nw >>= 1) {
-                if (pass == 0 && nw < 3 && nw_max >= 3) continue;
+                if (pass == 0 && nw < 4 && nw_max >= 4) continue;
                 const size_t smem = scan_smem_bytes(qe, qt * nw, dimp);
                 if (smem <= budget) {
                     out->qt = qt; out->nw = nw; out->kr = kr; out->smem = smem;
@@ -48,9 +49,42 @@ int scan_pick_qt(int arith, int dim, int k)
     return scan_shape(arith, dim, k, &sh) ? sh.tile() : 0;
 }
 
+// Streaming variant.  Default: the TMA ring for list mode (short runs re-read from L2 by many
+// tiles: staging once per CTA wins) and direct per-warp 128-bit loads for dense mode (long runs,
+// warps never wait for each other).  NDB_SCAN_MODE=direct|tma forces one (A/B knob for profiles/).
+static bool scan_direct(bool list_mode)
+{
+    static const int v = [] { const char *e = getenv("NDB_SCAN_MODE"); return !e ? 0 : (strcmp(e, "tma") == 0 ? 2 : (strcmp(e, "direct") == 0 ? 1 : 0)); }();
+    return v == 0 ? !list_mode : v == 1;
+}
+
+template <class P, int QT, int KR>
+static int launch_one_direct(const ScanParams &prm, const ScanShape &sh, uint32_t items_upper, cudaStream_t s)
+{
+    auto kern = scan_topk_direct_kernel<P, QT, KR>;
+    const size_t smem = sh.smem - (size_t) SCAN_STAGES * SCAN_STAGE_BYTES;      // query tile only
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        NDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        configured = smem;
+    }
+    int per_sm = 0;
+    NDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, sh.nw * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (uint32_t) ctx().sm_count * (uint32_t) per_sm;
+    if (items_upper < grid) grid = items_upper;
+    if (grid == 0) return NDB_B200_OK;
+    NDB_CUDA(cudaMemsetAsync(prm.counter, 0, sizeof(uint32_t), s));
+    kern<<<grid, sh.nw * 32, smem, s>>>(prm);
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
+}
+
 template <class P, int QT, int KR>
 static int launch_one(const ScanParams &prm, const ScanShape &sh, uint32_t items_upper, cudaStream_t s)
 {
+    if (scan_direct(prm.items != nullptr)) return launch_one_direct<P, QT, KR>(prm, sh, items_upper, s);
     auto kern = scan_topk_kernel<P, QT, KR>;
     static thread_local size_t configured = 0;
     if (sh.smem > configured) {
