@@ -18,6 +18,7 @@
 //                      memory and the nearest unexpanded entry is expanded until none is left.
 #include "layout.cuh"
 #include "arith.cuh"
+#include "pages.cuh"
 
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
@@ -867,6 +868,61 @@ int ndb_b200_hnsw_search(ndb_b200_hnsw *h, const float *Q, int nq, int strategy,
     NDB_CUDA(cudaMemcpyAsync(ids, h->outi.p, m * 8, cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaStreamSynchronize(s));
     return NDB_B200_OK;
+}
+
+// ---- relation loader: meta page + one HnswNodeData item per 8 KB page (hnsw_am.c:108-181) -----
+// node id = block - 1; neighbour slots hold block numbers and are rebased the same way.
+int ndb_b200_hnsw_load_relation(ndb_b200_hnsw *h, const void *blocks, uint32_t nblocks)
+{
+    using namespace ndb::pg;
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(h && blocks && nblocks >= 2, NDB_B200_EINVAL, "hnsw_load_relation: need the meta block and at least one node");
+    HnswMeta meta;
+    memcpy(&meta, page_at(blocks, 0) + PAGE_HEADER, sizeof(meta));
+    NDB_REQUIRE(meta.magic == HNSW_MAGIC, NDB_B200_EINVAL, "hnsw_load_relation: bad magic 0x%08x in the meta page", meta.magic);
+    NDB_REQUIRE(meta.m == h->m, NDB_B200_EINVAL, "hnsw_load_relation: relation m=%d, handle m=%d", (int) meta.m, h->m);
+    const int64_t n = (int64_t) nblocks - 1;
+    const int dim = h->dim, m2 = 2 * h->m;
+    std::vector<float> rows((size_t) n * dim);
+    std::vector<int64_t> ids(n);
+    std::vector<int> levels(n);
+    std::vector<uint32_t> nbr0((size_t) n * m2, INVALID_SLOT);
+    std::vector<int16_t> cnt((size_t) n * HNSW_MAX_LEVEL, 0);
+    std::vector<int64_t> uoff(n + 1, 0);
+    std::vector<uint32_t> upper;
+    auto rebase = [&](uint32_t blk) { return (blk == INVALID_BLOCK || blk == 0 || blk >= nblocks) ? INVALID_SLOT : blk - 1; };
+    for (int64_t i = 0; i < n; i++) {
+        const uint8_t *page = page_at(blocks, (uint32_t) (i + 1));
+        NDB_REQUIRE(max_offset(page) >= 1, NDB_B200_EINVAL, "hnsw_load_relation: block %lld holds no node", (long long) (i + 1));
+        uint32_t lo, fl, len;
+        item_id(page, 1, &lo, &fl, &len);                         // always FirstOffsetNumber (:70-80)
+        const uint8_t *node = page + lo;
+        int32_t level;
+        int16_t ndim;
+        memcpy(&level, node + 8, 4);
+        memcpy(&ndim, node + 12, 2);
+        NDB_REQUIRE(level >= 0 && level < HNSW_MAX_LEVEL, NDB_B200_EINVAL, "hnsw_load_relation: invalid node level %d at block %lld", level, (long long) (i + 1));
+        NDB_REQUIRE(ndim == dim, NDB_B200_EDIM, "hnsw_load_relation: node dim %d, handle dim %d", (int) ndim, dim);
+        NDB_REQUIRE(len >= HNSW_NODE_HDR + (uint32_t) dim * 4 + (uint32_t) (level + 1) * m2 * 4, NDB_B200_EINVAL,
+                    "hnsw_load_relation: node item at block %lld is truncated", (long long) (i + 1));
+        ids[i] = tid_unpack(node);
+        levels[i] = level;
+        memcpy(&cnt[(size_t) i * HNSW_MAX_LEVEL], node + 14, 2 * HNSW_MAX_LEVEL);
+        memcpy(&rows[(size_t) i * dim], node + HNSW_NODE_HDR, (size_t) dim * 4);
+        const uint8_t *nb = node + HNSW_NODE_HDR + (size_t) dim * 4;
+        uoff[i + 1] = uoff[i] + (int64_t) level * m2;
+        for (int l = 0; l <= level; l++)
+            for (int j = 0; j < m2; j++) {
+                uint32_t v;
+                memcpy(&v, nb + ((size_t) l * m2 + j) * 4, 4);
+                if (l == 0) nbr0[(size_t) i * m2 + j] = rebase(v);
+                else upper.push_back(rebase(v));
+            }
+    }
+    if (upper.empty()) upper.push_back(INVALID_SLOT);
+    const uint32_t entry = rebase(meta.entryPoint);
+    return ndb_b200_hnsw_load_graph(h, rows.data(), ids.data(), n, levels.data(), nbr0.data(), cnt.data(), uoff.data(),
+                                    upper.data(), entry, meta.entryLevel);
 }
 
 }  // extern "C"

@@ -15,6 +15,7 @@
 //   4. merge the nprobe partial top-k lists per query by (dist, id)
 #include "kmeans.cuh"
 #include "scan.cuh"
+#include "pages.cuh"
 
 #include <algorithm>
 #include <numeric>
@@ -267,6 +268,17 @@ __global__ void __launch_bounds__(128) ivf_literal_kernel(const float4 *__restri
         out_dist[(size_t) q * k + i] = have ? cd[idx[i]] : INFINITY;
         out_ids[(size_t) q * k + i] = have ? ids[cs[idx[i]]] : -1;
     }
+}
+
+// relation loader: pull the float4[dim] payload of entry i out of the staged 8 KB pages
+__global__ void extract_payload_kernel(const unsigned char *__restrict__ pages, const unsigned long long *__restrict__ src,
+                                       int64_t n, int dim, float *__restrict__ arena)
+{
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * dim) return;
+    const int64_t i = t / dim;
+    const int j = (int) (t - i * dim);
+    arena[t] = reinterpret_cast<const float *>(pages + src[i])[j];
 }
 
 __global__ void copy_kept_rows_kernel(const float *__restrict__ rows, const uint32_t *__restrict__ keep, int64_t nkeep,
@@ -719,6 +731,94 @@ int ndb_b200_ivf_search(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, in
     NDB_CUDA(cudaMemcpyAsync(dist, ix->outd.p, m * 4, cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaMemcpyAsync(ids, ix->outi.p, m * 8, cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaStreamSynchronize(s));
+    return NDB_B200_OK;
+}
+
+// ---- relation loader: meta page + centroid page(s) + inverted-list page chains ----------------
+// The host walks headers, line pointers and chain links (a few bytes per page); the vector
+// payloads -- the bulk -- are pulled out of the staged pages on the device.
+int ndb_b200_ivf_load_relation(ndb_b200_ivf *ix, const void *blocks, uint32_t nblocks)
+{
+    using namespace ndb::pg;
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix && blocks && nblocks >= 2, NDB_B200_EINVAL, "ivf_load_relation: need at least the meta and centroid blocks");
+    NDB_REQUIRE(ix->nrows == 0, NDB_B200_ESTATE, "ivf_load_relation: index already holds rows");
+    IvfMeta meta;
+    memcpy(&meta, page_at(blocks, 0) + PAGE_HEADER, sizeof(meta));
+    NDB_REQUIRE(meta.magic == IVF_MAGIC, NDB_B200_EINVAL, "ivf_load_relation: bad magic 0x%08x in the meta page", meta.magic);
+    NDB_REQUIRE(meta.nlists == ix->nlists, NDB_B200_EINVAL, "ivf_load_relation: relation has %d lists, handle has %d", meta.nlists, ix->nlists);
+    NDB_REQUIRE(meta.dim == ix->dim || meta.insertedVectors == 0, NDB_B200_EDIM, "ivf_load_relation: relation dim %d, handle dim %d", meta.dim, ix->dim);
+    NDB_REQUIRE(meta.centroidsBlock != INVALID_BLOCK && meta.centroidsBlock < nblocks, NDB_B200_ESTATE, "ivf_load_relation: no centroids block");
+
+    // centroid items: IvfCentroidData + float4[dim]; one page in the reference (Q7), consecutive
+    // pages accepted here
+    const int L = ix->nlists, dim = ix->dim;
+    std::vector<float> C((size_t) L * dim, 0.0f);
+    std::vector<uint32_t> first(L, INVALID_BLOCK);
+    int got = 0;
+    for (uint32_t b = meta.centroidsBlock; b < nblocks && got < L; b++) {
+        const uint8_t *page = page_at(blocks, b);
+        if (special_offset(page) != BLCKSZ - 24) break;            // not a centroid page
+        const int maxoff = max_offset(page);
+        for (int off = 1; off <= maxoff && got < L; off++) {
+            uint32_t lo, fl, len;
+            item_id(page, off, &lo, &fl, &len);
+            if (fl != LP_NORMAL) continue;
+            IvfCentroidHdr h;
+            memcpy(&h, page + lo, sizeof(h));
+            NDB_REQUIRE(h.listId >= 0 && h.listId < L && h.dim == dim, NDB_B200_EINVAL,
+                        "ivf_load_relation: centroid item %d/%d is inconsistent (list %d dim %d)", (int) b, off, h.listId, h.dim);
+            memcpy(&C[(size_t) h.listId * dim], page + lo + 24, (size_t) dim * 4);
+            first[h.listId] = h.firstBlock;
+            got++;
+        }
+    }
+    NDB_REQUIRE(got == L, NDB_B200_EINVAL, "ivf_load_relation: found %d of %d centroids", got, L);
+    NDB_CHECK(ndb_b200_ivf_set_centroids(ix, C.data()));
+
+    // walk every chain: page order = insertion order inside a list (ivf_am.c:1793-1840)
+    std::vector<uint64_t> src;           // byte offset of each live entry's vector payload
+    std::vector<uint8_t> seen(nblocks, 0);
+    for (int l = 0; l < L; l++) {
+        if (l % ix->world != ix->rank) continue;
+        for (uint32_t b = first[l]; b != INVALID_BLOCK;) {
+            NDB_REQUIRE(b < nblocks && !seen[b], NDB_B200_EINVAL, "ivf_load_relation: list %d chain is corrupt at block %u", l, b);
+            seen[b] = 1;
+            const uint8_t *page = page_at(blocks, b);
+            NDB_REQUIRE(special_offset(page) == BLCKSZ - 8, NDB_B200_EINVAL, "ivf_load_relation: block %u is not a list page", b);
+            const int maxoff = max_offset(page);
+            for (int off = 1; off <= maxoff; off++) {
+                uint32_t lo, fl, len;
+                item_id(page, off, &lo, &fl, &len);
+                if (fl != LP_NORMAL) continue;                       // unused or LP_DEAD (:1816)
+                int16_t edim;
+                memcpy(&edim, page + lo + 6, 2);
+                if (edim != dim) continue;                           // :1821-1822
+                ix->row_id.push_back(tid_unpack(page + lo));
+                ix->row_list.push_back(l);
+                src.push_back((uint64_t) b * BLCKSZ + lo + IVF_ENTRY_HDR);
+            }
+            IvfListSpecial sp;
+            memcpy(&sp, page + BLCKSZ - 8, sizeof(sp));
+            b = sp.nextBlock;
+        }
+    }
+    const int64_t n = (int64_t) src.size();
+    if (n == 0) { ix->dirty = true; return NDB_B200_OK; }
+    cudaStream_t s = ctx().stream;
+    DevBuf d_pages, d_src;
+    NDB_CHECK(d_pages.reserve((size_t) nblocks * BLCKSZ));
+    NDB_CHECK(d_src.reserve((size_t) n * 8));
+    NDB_CHECK(ix->arena.reserve((size_t) n * dim * 4));
+    NDB_CUDA(cudaMemcpyAsync(d_pages.p, blocks, (size_t) nblocks * BLCKSZ, cudaMemcpyHostToDevice, s));
+    NDB_CUDA(cudaMemcpyAsync(d_src.p, src.data(), (size_t) n * 8, cudaMemcpyHostToDevice, s));
+    extract_payload_kernel<<<(unsigned) ((n * dim + 255) / 256), 256, 0, s>>>(d_pages.as<unsigned char>(), d_src.as<unsigned long long>(), n, dim,
+                                                                             ix->arena.as<float>());
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    NDB_CUDA(cudaStreamSynchronize(s));
+    ix->nrows = n;
+    ix->dirty = true;
     return NDB_B200_OK;
 }
 

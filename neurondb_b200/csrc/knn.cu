@@ -87,11 +87,14 @@ int dense_scan(const float *store, const void *vnorm, int64_t nvec, int dim, int
     NDB_REQUIRE(qt > 0, NDB_B200_EINVAL, "unsupported scan shape: dim=%d k=%d (k must be 1..128)", dim, k);
     const int64_t B = (nvec + 31) / 32;
     const int ntiles = (nq + qt - 1) / qt;
-    const int64_t target_items = (int64_t) ctx().sm_count * 8;
+    // cut the store into runs so that there are ~4 work items per resident CTA slot, but never
+    // below 32 blocks (1024 vectors) per run: every run restarts the k-th-best filter from scratch,
+    // and short runs turn most candidates into insertions (profiles/r01_scan_variants.txt)
+    const int64_t target_items = (int64_t) ctx().sm_count * 12;
     int64_t nseg = (target_items + ntiles - 1) / ntiles;
     if (nseg < 1) nseg = 1;
     int64_t seg_blocks = (B + nseg - 1) / nseg;
-    if (seg_blocks < 8) seg_blocks = 8;            // short runs defeat the k-th-best filter
+    if (seg_blocks < 32) seg_blocks = 32;
     if (seg_blocks > B) seg_blocks = B > 0 ? B : 1;
     nseg = B > 0 ? (B + seg_blocks - 1) / seg_blocks : 1;
     const size_t norm_bytes = (metric == NDB_COSINE) ? norm_elem_size(arith) : 0;

@@ -117,6 +117,14 @@ void     orc_hnsw_export(const OrcHnsw *g, int *levels /*n*/, uint32_t *nbr0 /*n
 int64_t  orc_hnsw_upper_slots(const OrcHnsw *g);    /* sum over nodes of level * 2m */
 int64_t  orc_hnsw_distance_evals(void);             /* counter of the last search batch */
 
+/* ---- relation images in the reference's on-disk page layout (ndb_oracle_pages.c) ------- */
+int64_t orc_ivf_encode_relation(const float *X, const int64_t *tids, int64_t n, int dim,
+                                const float *C, int nlists, int nprobe, const int *assign,
+                                uint8_t *blocks, int64_t cap_blocks, int multi_page_centroids);
+void    orc_page_mark_dead(uint8_t *blocks, int64_t block, int offnum);
+int64_t orc_hnsw_encode_relation(const OrcHnsw *g, const float *X, const int64_t *tids, int dim, int m, int efc,
+                                 int efs, uint8_t *blocks, int64_t cap_blocks);
+
 /* ---- recall@k (ml_recall_metrics.c:65-126) ------------------------------ */
 double orc_recall_at_k(const int64_t *found, const int64_t *truth, int nq, int k);
 

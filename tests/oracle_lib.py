@@ -282,3 +282,51 @@ def ref_distance_pairs(metric, A, B, avx2=False):
     rc = l.ndb_ref_distance_pairs(metric, A, B, out, A.shape[0], A.shape[1])
     assert rc == 0, l.ndb_ref_last_error()
     return out
+
+
+# ---- relation images in the reference's page layout (oracle/ndb_oracle_pages.c) ------------
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def _pages_lib():
+    l = lib()
+    if not getattr(l, "_pages_bound", False):
+        l.orc_ivf_encode_relation.restype = C.c_int64
+        l.orc_ivf_encode_relation.argtypes = [_f32p, C.c_void_p, C.c_int64, C.c_int, _f32p, C.c_int, C.c_int, _i32p, _u8p,
+                                              C.c_int64, C.c_int]
+        l.orc_page_mark_dead.restype = None
+        l.orc_page_mark_dead.argtypes = [_u8p, C.c_int64, C.c_int]
+        l.orc_hnsw_encode_relation.restype = C.c_int64
+        l.orc_hnsw_encode_relation.argtypes = [C.c_void_p, _f32p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p,
+                                               C.c_int64]
+        l._pages_bound = True
+    return l
+
+
+def ivf_encode_relation(X, Cn, assign, tids=None, nprobe=10, multi_page_centroids=True):
+    """Blocks (uint8 [nblocks, 8192]) as ivfbuild + ivfinsert-per-row would leave them."""
+    X, Cn = f32(X), f32(Cn)
+    n, dim = X.shape
+    per_page = max(1, (8192 - 24 - 8) // (8 + 4 * dim + 4))
+    cap = 2 + Cn.shape[0] + n // per_page + 2 * Cn.shape[0] + 8
+    blocks = np.zeros((cap, 8192), np.uint8)
+    tp = None if tids is None else np.ascontiguousarray(tids, np.int64).ctypes.data
+    nb = _pages_lib().orc_ivf_encode_relation(X, tp, n, dim, Cn, Cn.shape[0], nprobe,
+                                              np.ascontiguousarray(assign, np.int32), blocks.reshape(-1), cap,
+                                              1 if multi_page_centroids else 0)
+    if nb < 0:
+        return nb, None
+    return nb, blocks[:nb]
+
+
+def page_mark_dead(blocks, block, offnum):
+    _pages_lib().orc_page_mark_dead(blocks.reshape(-1), block, offnum)
+
+
+def hnsw_encode_relation(g, X, tids=None, efc=64, efs=40):
+    X = f32(X)
+    n = X.shape[0]
+    blocks = np.zeros((n + 1, 8192), np.uint8)
+    tp = None if tids is None else np.ascontiguousarray(tids, np.int64).ctypes.data
+    nb = _pages_lib().orc_hnsw_encode_relation(g.h, X, tp, g.dim, g.m, efc, efs, blocks.reshape(-1), n + 1)
+    return nb, blocks
