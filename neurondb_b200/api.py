@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from ._lib import (ARITH_FAST, ARITH_HNSW, ARITH_IVF_F32, ARITH_OP_F64, COSINE, HNSW_BESTFIRST, HNSW_LITERAL, IP,
+from ._lib import (ARITH_FAST, ARITH_HNSW, ARITH_IVF_F32, ARITH_OP_F64, ARITH_TENSOR, COSINE, HNSW_BESTFIRST, HNSW_LITERAL, IP,
                    IVF_FULL, IVF_LITERAL, L2, NdbError, check, f32, ptr)
 
 _initialised = {"device": None}

@@ -2,6 +2,7 @@
 // fused scan, evaluated with the arithmetic the `<->`/`<=>`/`<#>` operators really execute).
 #include "layout.cuh"
 #include "scan.cuh"
+#include "tc.cuh"
 
 namespace ndb {
 
@@ -22,6 +23,8 @@ struct ndb_b200_dataset {
     NormCache norm_f32_ivf, norm_f32_fast, norm_f64;
     ScanScratch scratch;
     DevBuf tmp_rows, tmp_ids, qbuf, outd, outi;
+    TcStore tc;                 // bf16 blocked copy for NDB_ARITH_TENSOR, built on first use
+    TcScratch tcs;
 };
 
 namespace ndb {
@@ -198,9 +201,14 @@ int ndb_b200_knn_exact_dev(ndb_b200_dataset *ds, int metric, int arith, const fl
     NDB_REQUIRE(ds && Q_dev && dist_dev && ids_dev && nq > 0, NDB_B200_EINVAL, "knn_exact: NULL or empty input");
     NDB_REQUIRE(k >= 1 && k <= 128, NDB_B200_EINVAL, "knn_exact: k=%d out of range 1..128", k);
     NDB_REQUIRE(metric >= NDB_L2 && metric <= NDB_IP, NDB_B200_EINVAL, "knn_exact: unknown metric %d", metric);
-    NDB_REQUIRE(arith == NDB_ARITH_OP_F64 || arith == NDB_ARITH_IVF_F32 || arith == NDB_ARITH_FAST, NDB_B200_EINVAL,
-                "knn_exact: arith %d not available for the scan", arith);
+    NDB_REQUIRE(arith == NDB_ARITH_OP_F64 || arith == NDB_ARITH_IVF_F32 || arith == NDB_ARITH_FAST || arith == NDB_ARITH_TENSOR,
+                NDB_B200_EINVAL, "knn_exact: arith %d not available for the scan", arith);
     cudaStream_t s = stream ? (cudaStream_t) stream : ctx().stream;
+    if (arith == NDB_ARITH_TENSOR) {
+        // bf16 tcgen05 GEMM-form path (tolerance 1e-3): ||x||^2 - 2 x.q + ||q||^2 with fused top-k
+        if (ds->tc.valid_for != ds->n) NDB_CHECK(tc_build_store(ds->tc, ds->store.ptr(), ds->n, ds->dim, ds->dimp, s));
+        return tc_knn(ds->tc, ds->tcs, ds->dim, metric, Q_dev, nq, k, ds->ids.as<int64_t>(), dist_dev, ids_dev, nullptr, s);
+    }
     const void *vnorm = nullptr;
     if (metric == NDB_COSINE) NDB_CHECK(dataset_norms(ds, arith, &vnorm, s));
     int nparts = 1;

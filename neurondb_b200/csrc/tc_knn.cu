@@ -1,0 +1,498 @@
+// tc_knn.cu -- GEMM-form distances on the 5th-generation tensor cores (tcgen05 + TMEM) with a
+// fused per-query top-k, for the genuinely dense contractions of the path: brute-force kNN and
+// (k = 1) nearest-centroid assignment over bf16 data (BASELINE config 5; tolerance path,
+// |rel err| <= 1e-3, north_star).
+//
+//   ||x - q||^2 = ||x||^2 - 2 x.q + ||q||^2            (L2; ranked squared, sqrt on output)
+//   -x.q                                                (inner product, HNSW sign convention)
+//
+// Layout.  Stored rows and queries are kept as bf16 in the UMMA *canonical K-major no-swizzle*
+// layout, blocked so that every operand tile is one contiguous run of bytes:
+//   X: [tile of 256 rows][K-chunk of 128 dims][16 k-groups][32 row-groups][8 rows][8 elems]  = 64 KB per (tile, chunk)
+//   Q: [tile of 128 queries][K-chunk][16 k-groups][16 row-groups][8][8]                     = 32 KB per (tile, chunk)
+// i.e. 8x8 "core matrices" of 128 contiguous bytes; consecutive core matrices along the
+// row direction are 128 B apart (SBO), along K they are 32*128 B (X) / 16*128 B (Q) apart (LBO).
+// A (tile, chunk) is fetched with ONE cp.async.bulk (no tensor map, no swizzle) and is directly
+// consumable by tcgen05.mma through a shared-memory matrix descriptor.
+//
+// Kernel (persistent, 256 threads):
+//   warp 0    TMA producer: Q tile once per work item, then X (tile, chunk) stages into a 2-deep ring
+//   warp 1    MMA issuer: one elected thread issues 8 x tcgen05.mma.kind::f16 (M=128, N=256, K=16) per
+//             stage into one of two 256-column TMEM accumulators; tcgen05.commit frees the smem
+//             stage and, after the last chunk, publishes the accumulator
+//   warp 2    TMEM allocator (512 columns)
+//   warps 4-7 epilogue: thread = query (TMEM lane); tcgen05.ld 32 columns at a time; candidate =
+//             fma(-2, dot, ||x||^2) compared against the thread's k-th best; the top-k is a
+//             thread-local sorted array in registers -- no cross-lane traffic at all
+// Work item = (query tile, range of X tiles); per-item top-k lists are merged by (dist, id) by
+// merge_parts_kernel (scan.cuh).
+#include "layout.cuh"
+#include "scan.cuh"
+#include "tc.cuh"
+
+#include <cuda_bf16.h>
+
+namespace ndb {
+
+constexpr int TC_M = 128;          // queries per tile  (TMEM lanes)
+constexpr int TC_N = 256;          // stored rows per tile (TMEM columns per accumulator)
+constexpr int TC_KC = 128;         // dims per K-chunk (one smem stage)
+constexpr int TC_STAGES = 2;
+constexpr int TC_XSTAGE_BYTES = TC_N * TC_KC * 2;      // 64 KB
+constexpr int TC_QCHUNK_BYTES = TC_M * TC_KC * 2;      // 32 KB
+constexpr int TC_MAX_CHUNKS = 2;                       // dim <= 256 in this round
+constexpr int TC_NORM_RING = 8;
+constexpr int TC_KMAX = 16;                            // k <= 16 (thread-local register list)
+
+// ---- layout conversion -------------------------------------------------------------------
+// IL32 fp32 store -> blocked bf16 + per-row squared norm of the rounded values (fp32)
+__global__ void tc_block_rows_kernel(const float4 *__restrict__ store, int64_t n, int64_t npad, int dim, int dimp,
+                                     int nkc, __nv_bfloat16 *__restrict__ xb, float *__restrict__ xnorm)
+{
+    const int groups = nkc * (TC_KC / 8);                      // 8-element groups per row (padded dims)
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npad * groups) return;
+    const int64_t row = t / groups;
+    const int g = (int) (t - row * groups);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = 0.0f;
+    if (row < n) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int c = 2 * g + h;                           // float4 chunk of the row
+            if (4 * c < dimp) {
+                const float4 x = store[(size_t) (row >> 5) * (8 * (size_t) dimp) + (size_t) c * 32 + (row & 31)];
+                v[4 * h + 0] = 4 * c + 0 < dim ? x.x : 0.0f;
+                v[4 * h + 1] = 4 * c + 1 < dim ? x.y : 0.0f;
+                v[4 * h + 2] = 4 * c + 2 < dim ? x.z : 0.0f;
+                v[4 * h + 3] = 4 * c + 3 < dim ? x.w : 0.0f;
+            }
+        }
+    }
+    const int64_t tile = row / TC_N;
+    const int rr = (int) (row - tile * TC_N);
+    const int chunk = g / (TC_KC / 8), kc = g % (TC_KC / 8);
+    const size_t off = ((((size_t) (tile * nkc + chunk) * (TC_KC / 8) + kc) * (TC_N / 8) + (rr >> 3)) * 8 + (rr & 7)) * 8;
+    __nv_bfloat16 o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = __float2bfloat16_rn(v[i]);
+    *reinterpret_cast<uint4 *>(xb + off) = *reinterpret_cast<const uint4 *>(o);
+    (void) xnorm;
+}
+
+// one thread per row: squared norm of the bf16-rounded row; +inf for pad rows so they never rank
+__global__ void tc_row_norms_kernel(const float4 *__restrict__ store, int64_t n, int64_t npad, int dim, int dimp,
+                                    float *__restrict__ xnorm)
+{
+    const int64_t row = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= npad) return;
+    if (row >= n) { xnorm[row] = INFINITY; return; }
+    float acc = 0.0f;
+    const float4 *vp = store + (size_t) (row >> 5) * (8 * (size_t) dimp) + (row & 31);
+    for (int c = 0; 4 * c < dimp; c++) {
+        const float4 x = vp[(size_t) c * 32];
+        const float a = __bfloat162float(__float2bfloat16_rn(4 * c + 0 < dim ? x.x : 0.0f));
+        const float b = __bfloat162float(__float2bfloat16_rn(4 * c + 1 < dim ? x.y : 0.0f));
+        const float cc = __bfloat162float(__float2bfloat16_rn(4 * c + 2 < dim ? x.z : 0.0f));
+        const float d = __bfloat162float(__float2bfloat16_rn(4 * c + 3 < dim ? x.w : 0.0f));
+        acc = fmaf(a, a, acc); acc = fmaf(b, b, acc); acc = fmaf(cc, cc, acc); acc = fmaf(d, d, acc);
+    }
+    xnorm[row] = acc;
+}
+
+// row-major fp32 queries -> blocked bf16 query tiles + squared norms
+__global__ void tc_block_queries_kernel(const float *__restrict__ Q, int nq, int nqpad, int dim, int nkc,
+                                        __nv_bfloat16 *__restrict__ qb, float *__restrict__ qnorm)
+{
+    const int groups = nkc * (TC_KC / 8);
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t) nqpad * groups) return;
+    const int q = (int) (t / groups);
+    const int g = (int) (t - (int64_t) q * groups);
+    __nv_bfloat16 o[8];
+    float part = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int d = g * 8 + i;
+        const float v = (q < nq && d < dim) ? Q[(size_t) q * dim + d] : 0.0f;
+        o[i] = __float2bfloat16_rn(v);
+        const float r = __bfloat162float(o[i]);
+        part = fmaf(r, r, part);
+    }
+    const int tile = q / TC_M, rr = q % TC_M;
+    const int chunk = g / (TC_KC / 8), kc = g % (TC_KC / 8);
+    const size_t off = ((((size_t) (tile * nkc + chunk) * (TC_KC / 8) + kc) * (TC_M / 8) + (rr >> 3)) * 8 + (rr & 7)) * 8;
+    *reinterpret_cast<uint4 *>(qb + off) = *reinterpret_cast<const uint4 *>(o);
+    (void) part;
+    (void) qnorm;
+}
+
+// squared norm of the bf16-rounded query, one thread per query (fixed order: deterministic)
+__global__ void tc_query_norms_kernel(const float *__restrict__ Q, int nq, int nqpad, int dim, float *__restrict__ qnorm)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nqpad) return;
+    float acc = 0.0f;
+    if (q < nq)
+        for (int d = 0; d < dim; d++) {
+            const float r = __bfloat162float(__float2bfloat16_rn(Q[(size_t) q * dim + d]));
+            acc = fmaf(r, r, acc);
+        }
+    qnorm[q] = acc;
+}
+
+// ---- tcgen05 / TMEM primitives -------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *holder_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 in, fp32 accumulate, issued by one thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (K-direction core-matrix stride) |
+//   [32,46) SBO >> 4 (row-direction 8-row-group stride) | [46,48) version = 1 | [61,64) layout = 0
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t) ((smem_addr >> 4) & 0x3fffu) | ((uint64_t) ((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t) ((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = BF16
+// (bits 7-9, 10-12 = 1), both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (m >> 4) << 24);
+}
+
+struct TcParams {
+    const __nv_bfloat16 *xb;       // blocked stored rows
+    const float *xnorm;            // [ntiles * 256]
+    const __nv_bfloat16 *qb;       // blocked query tiles
+    const float *qnorm;            // [nqpad]
+    int nkc;                       // K-chunks (dimp / 128)
+    int nq, k, metric;
+    uint32_t nqt;                  // query tiles
+    uint32_t ntiles;               // X tiles
+    uint32_t nranges;              // X ranges (parts per query)
+    uint32_t tiles_per_range;
+    float *pdist;                  // [nq][nranges][k]
+    uint32_t *pslot;
+    float *debug_d;                // optional: raw accumulator of the first tile [128][256]
+};
+
+// thread-local sorted top-k in registers (k <= TC_KMAX): insert (d, id) known to beat entry k-1
+__device__ __forceinline__ void tk_insert(float (&bd)[TC_KMAX], uint32_t (&bi)[TC_KMAX], float d, uint32_t id, int k)
+{
+    bool placed = false;
+#pragma unroll
+    for (int j = TC_KMAX - 1; j >= 0; j--) {
+        if (j < k && !placed) {
+            const bool prev_greater = j > 0 && (bd[j - 1] > d || (bd[j - 1] == d && bi[j - 1] > id));
+            if (prev_greater) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; }
+            else { bd[j] = d; bi[j] = id; placed = true; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) tc_knn_kernel(const TcParams p)
+{
+    extern __shared__ __align__(1024) unsigned char tsm[];
+    // [Q tile: nkc * 32 KB][X ring: 2 * 64 KB][norm ring: 8 * 1 KB]
+    unsigned char *q_smem = tsm;
+    unsigned char *x_smem = tsm + (size_t) TC_MAX_CHUNKS * TC_QCHUNK_BYTES;
+    float *n_smem = reinterpret_cast<float *>(x_smem + (size_t) TC_STAGES * TC_XSTAGE_BYTES);
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], q_full, q_empty, acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_holder;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nitems = p.nqt * p.nranges;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&q_full, 1);
+        mbar_init(&q_empty, 1);
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        mbar_fence_init();
+    }
+    if (warp == 2) { tmem_alloc(&tmem_holder, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_holder;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage_it = 0, tile_it = 0, item_it = 0;
+            for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x, item_it++) {
+                const uint32_t qt = item % p.nqt, xr = item / p.nqt;
+                mbar_wait(&q_empty, (item_it & 1u) ^ 1u);              // MMA finished with the previous Q tile
+                mbar_arrive_expect_tx(&q_full, (uint32_t) p.nkc * TC_QCHUNK_BYTES);
+                for (int c = 0; c < p.nkc; c++)
+                    tma_bulk_g2s(q_smem + (size_t) c * TC_QCHUNK_BYTES,
+                                 reinterpret_cast<const unsigned char *>(p.qb) + ((size_t) qt * p.nkc + c) * TC_QCHUNK_BYTES,
+                                 TC_QCHUNK_BYTES, &q_full);
+                const uint32_t t0 = xr * p.tiles_per_range;
+                const uint32_t t1 = min(p.ntiles, t0 + p.tiles_per_range);
+                for (uint32_t t = t0; t < t1; t++, tile_it++) {
+                    for (int c = 0; c < p.nkc; c++, stage_it++) {
+                        const uint32_t s = stage_it % TC_STAGES;
+                        mbar_wait(&empty_bar[s], ((stage_it / TC_STAGES) & 1u) ^ 1u);
+                        const uint32_t bytes = TC_XSTAGE_BYTES + (c == 0 ? TC_N * 4 : 0);
+                        mbar_arrive_expect_tx(&full_bar[s], bytes);
+                        tma_bulk_g2s(x_smem + (size_t) s * TC_XSTAGE_BYTES,
+                                     reinterpret_cast<const unsigned char *>(p.xb) + ((size_t) t * p.nkc + c) * TC_XSTAGE_BYTES,
+                                     TC_XSTAGE_BYTES, &full_bar[s]);
+                        if (c == 0)
+                            tma_bulk_g2s(n_smem + (size_t) (tile_it % TC_NORM_RING) * TC_N, p.xnorm + (size_t) t * TC_N, TC_N * 4,
+                                         &full_bar[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
+            uint32_t stage_it = 0, tile_it = 0, item_it = 0;
+            for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x, item_it++) {
+                const uint32_t xr = item / p.nqt;
+                const uint32_t t0 = xr * p.tiles_per_range;
+                const uint32_t t1 = min(p.ntiles, t0 + p.tiles_per_range);
+                mbar_wait(&q_full, item_it & 1u);
+                tc_fence_after();
+                for (uint32_t t = t0; t < t1; t++, tile_it++) {
+                    const uint32_t a = tile_it & 1u;
+                    mbar_wait(&acc_empty[a], ((tile_it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + a * TC_N;
+                    for (int c = 0; c < p.nkc; c++, stage_it++) {
+                        const uint32_t s = stage_it % TC_STAGES;
+                        mbar_wait(&full_bar[s], (stage_it / TC_STAGES) & 1u);
+                        tc_fence_after();
+                        const uint32_t qa = smem_u32(q_smem + (size_t) c * TC_QCHUNK_BYTES);
+                        const uint32_t xa = smem_u32(x_smem + (size_t) s * TC_XSTAGE_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < TC_KC / 16; ks++) {
+                            // one MMA consumes K = 16 = two 8-element core matrices along K
+                            const uint64_t da = umma_desc(qa + ks * 2 * (TC_M / 8) * 128, (TC_M / 8) * 128, 128);
+                            const uint64_t db = umma_desc(xa + ks * 2 * (TC_N / 8) * 128, (TC_N / 8) * 128, 128);
+                            umma_bf16(tmem_d, da, db, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&empty_bar[s]);                     // smem stage reusable once these MMAs retire
+                    }
+                    umma_commit(&acc_full[a]);                          // accumulator complete
+                }
+                umma_commit(&q_empty);                                  // Q tile reusable
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread = query =====
+        const int ql = tid - 128;                                       // TMEM lane
+        const uint32_t lane_addr = (uint32_t) (ql & ~31) << 16;         // this warp's lane quarter
+        uint32_t tile_it = 0;
+        for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const uint32_t qt = item % p.nqt, xr = item / p.nqt;
+            const uint32_t t0 = xr * p.tiles_per_range;
+            const uint32_t t1 = min(p.ntiles, t0 + p.tiles_per_range);
+            const uint32_t q = qt * TC_M + ql;
+            const float qn = p.qnorm[q];
+            float bd[TC_KMAX];
+            uint32_t bi[TC_KMAX];
+#pragma unroll
+            for (int j = 0; j < TC_KMAX; j++) { bd[j] = INFINITY; bi[j] = INVALID_SLOT; }
+            float thr = INFINITY;                                       // k-th best, in "candidate" units
+            for (uint32_t t = t0; t < t1; t++, tile_it++) {
+                const uint32_t a = tile_it & 1u;
+                mbar_wait(&acc_full[a], (tile_it >> 1) & 1u);
+                tc_fence_after();
+                const float *xn = n_smem + (size_t) (tile_it % TC_NORM_RING) * TC_N;
+#pragma unroll 1
+                for (int j = 0; j < TC_N / 32; j++) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_addr + a * TC_N + j * 32, v);
+                    tmem_ld_wait();
+                    if (p.debug_d && item == 0 && t == t0) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) p.debug_d[(size_t) ql * TC_N + j * 32 + i] = __uint_as_float(v[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const float dot = __uint_as_float(v[i]);
+                        // L2: ||x||^2 - 2 x.q (+ ||q||^2 added on output); IP: -x.q; pad rows carry +inf norms
+                        const float cand = p.metric == NDB_L2 ? fmaf(-2.0f, dot, xn[j * 32 + i]) : (xn[j * 32 + i] == INFINITY ? INFINITY : -dot);
+                        if (cand < thr) {
+                            tk_insert(bd, bi, cand, t * TC_N + j * 32 + i, p.k);
+#pragma unroll
+                            for (int jj = 0; jj < TC_KMAX; jj++) if (jj == p.k - 1) thr = bd[jj];
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty[a]);                             // 128 arrivals release the accumulator
+            }
+            if (q < (uint32_t) p.nq) {
+                const size_t base = ((size_t) q * p.nranges + xr) * p.k;
+#pragma unroll
+                for (int j = 0; j < TC_KMAX; j++) {
+                    if (j < p.k) {
+                        float d = bd[j];
+                        if (p.metric == NDB_L2 && bi[j] != INVALID_SLOT) d = sqrtf(fmaxf(d + qn, 0.0f));
+                        p.pdist[base + j] = d;
+                        p.pslot[base + j] = bi[j];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static size_t tc_smem_bytes() { return (size_t) TC_MAX_CHUNKS * TC_QCHUNK_BYTES + (size_t) TC_STAGES * TC_XSTAGE_BYTES + (size_t) TC_NORM_RING * TC_N * 4; }
+
+int tc_build_store(TcStore &st, const float *il32_store, int64_t n, int dim, int dimp, cudaStream_t s)
+{
+    NDB_REQUIRE(dim <= TC_MAX_CHUNKS * TC_KC, NDB_B200_EINVAL, "tensor path: dim %d > %d is not supported yet", dim, TC_MAX_CHUNKS * TC_KC);
+    const int nkc = (dim + TC_KC - 1) / TC_KC;
+    const int64_t ntiles = (n + TC_N - 1) / TC_N, npad = ntiles * TC_N;
+    NDB_CHECK(st.xb.reserve((size_t) npad * nkc * TC_KC * 2));
+    NDB_CHECK(st.xnorm.reserve((size_t) npad * 4));
+    const int groups = nkc * (TC_KC / 8);
+    tc_block_rows_kernel<<<(unsigned) ((npad * groups + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(il32_store), n, npad, dim,
+                                                                                 dimp, nkc, st.xb.as<__nv_bfloat16>(), st.xnorm.as<float>());
+    tc_row_norms_kernel<<<(unsigned) ((npad + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(il32_store), n, npad, dim, dimp,
+                                                                        st.xnorm.as<float>());
+    count_launch(2);
+    NDB_CUDA(cudaGetLastError());
+    st.valid_for = n;
+    st.ntiles = ntiles;
+    st.nkc = nkc;
+    return NDB_B200_OK;
+}
+
+// top-k of nq row-major fp32 queries against a TcStore; writes (dist, id) like the scan path
+int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q_dev, int nq, int k, const int64_t *ids,
+           float *dist_dev, int64_t *ids_dev, float *debug_d_dev, cudaStream_t s)
+{
+    NDB_REQUIRE(k >= 1 && k <= TC_KMAX, NDB_B200_EINVAL, "tensor path: k must be 1..%d", TC_KMAX);
+    NDB_REQUIRE(metric == NDB_L2 || metric == NDB_IP, NDB_B200_EINVAL, "tensor path: metric %d not supported (L2, IP)", metric);
+    NDB_REQUIRE(st.ntiles > 0, NDB_B200_ESTATE, "tensor path: empty store");
+    const int nkc = st.nkc;
+    const uint32_t nqt = (uint32_t) ((nq + TC_M - 1) / TC_M);
+    const int nqpad = (int) nqt * TC_M;
+    NDB_CHECK(sc.qb.reserve((size_t) nqpad * nkc * TC_KC * 2));
+    NDB_CHECK(sc.qnorm.reserve((size_t) nqpad * 4));
+    const int groups = nkc * (TC_KC / 8);
+    tc_block_queries_kernel<<<(unsigned) (((int64_t) nqpad * groups + 255) / 256), 256, 0, s>>>(Q_dev, nq, nqpad, dim, nkc,
+                                                                                                sc.qb.as<__nv_bfloat16>(), sc.qnorm.as<float>());
+    tc_query_norms_kernel<<<(unsigned) ((nqpad + 127) / 128), 128, 0, s>>>(Q_dev, nq, nqpad, dim, sc.qnorm.as<float>());
+    count_launch(2);
+    // split the stored tiles into ranges so that there are ~2 work items per SM
+    const uint32_t sms = (uint32_t) ctx().sm_count;
+    uint32_t nranges = (2 * sms + nqt - 1) / nqt;
+    if (nranges < 1) nranges = 1;
+    if (nranges > (uint32_t) st.ntiles) nranges = (uint32_t) st.ntiles;
+    const uint32_t tpr = (uint32_t) ((st.ntiles + nranges - 1) / nranges);
+    nranges = (uint32_t) ((st.ntiles + tpr - 1) / tpr);
+    NDB_CHECK(sc.pdist.reserve((size_t) nq * nranges * k * 4));
+    NDB_CHECK(sc.pslot.reserve((size_t) nq * nranges * k * 4));
+    TcParams p;
+    p.xb = st.xb.as<__nv_bfloat16>();
+    p.xnorm = st.xnorm.as<float>();
+    p.qb = sc.qb.as<__nv_bfloat16>();
+    p.qnorm = sc.qnorm.as<float>();
+    p.nkc = nkc; p.nq = nq; p.k = k; p.metric = metric;
+    p.nqt = nqt; p.ntiles = (uint32_t) st.ntiles; p.nranges = nranges; p.tiles_per_range = tpr;
+    p.pdist = sc.pdist.as<float>();
+    p.pslot = sc.pslot.as<uint32_t>();
+    p.debug_d = debug_d_dev;
+    const size_t smem = tc_smem_bytes();
+    static bool configured = false;
+    if (!configured) {
+        NDB_CUDA(cudaFuncSetAttribute(tc_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        configured = true;
+    }
+    const uint32_t nitems = nqt * nranges;
+    const uint32_t grid = nitems < sms ? nitems : sms;
+    Context &c = ctx();
+    if (c.timing) NDB_CUDA(cudaEventRecord(c.ev0, s));
+    tc_knn_kernel<<<grid, 256, smem, s>>>(p);
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    if (c.timing) {
+        NDB_CUDA(cudaEventRecord(c.ev1, s));
+        c.last_ms = -1.0;
+        c.last_bytes = (double) st.ntiles * TC_N * nkc * TC_KC * 2.0;          // stored bf16 bytes, read once per launch
+        c.last_evals = (int64_t) st.valid_for * nq;
+        c.stats_src = nullptr;
+    }
+    return launch_merge_parts(sc.pdist.as<float>(), sc.pslot.as<uint32_t>(), ids, nq, (int) nranges, k, dist_dev, ids_dev, nullptr, s);
+}
+
+}  // namespace ndb
+
+// development hook (not part of the ABI in include/ndb_b200.h): raw accumulator tile D = Q X^T of the
+// first (query tile, row tile) -- used by tests/test_gpu_tensor.py to validate the UMMA descriptors
+extern "C" int ndbdbg_tc_gemm(const float *Q, int nq, const float *X, int n, int dim, float *D /* [128][256] */)
+{
+    using namespace ndb;
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(Q && X && D && nq >= 1 && nq <= TC_M && n >= 1 && n <= TC_N && dim >= 1, NDB_B200_EINVAL, "dbg_tc_gemm: bad shape");
+    cudaStream_t s = ctx().stream;
+    const int dimp = round_up(dim, 4);
+    DevBuf dq, dx, store, dd, od, oi;
+    TcStore st;
+    TcScratch sc;
+    NDB_CHECK(dq.reserve((size_t) nq * dim * 4)); NDB_CHECK(dx.reserve((size_t) n * dim * 4));
+    const int64_t blocks = (n + 31) / 32;
+    NDB_CHECK(store.reserve((size_t) blocks * 32 * dimp * 4));
+    NDB_CHECK(dd.reserve((size_t) TC_M * TC_N * 4)); NDB_CHECK(od.reserve((size_t) nq * 4)); NDB_CHECK(oi.reserve((size_t) nq * 8));
+    NDB_CUDA(cudaMemcpyAsync(dq.p, Q, (size_t) nq * dim * 4, cudaMemcpyHostToDevice, s));
+    NDB_CUDA(cudaMemcpyAsync(dx.p, X, (size_t) n * dim * 4, cudaMemcpyHostToDevice, s));
+    NDB_CUDA(cudaMemsetAsync(store.p, 0, (size_t) blocks * 32 * dimp * 4, s));
+    NDB_CUDA(cudaMemsetAsync(dd.p, 0, (size_t) TC_M * TC_N * 4, s));
+    NDB_CHECK(il32_scatter(dx.as<float>(), n, dim, dimp, nullptr, 0, store.as<float>(), s));
+    NDB_CHECK(tc_build_store(st, store.as<float>(), n, dim, dimp, s));
+    NDB_CHECK(tc_knn(st, sc, dim, NDB_L2, dq.as<float>(), nq, 1, nullptr, od.as<float>(), oi.as<int64_t>(), dd.as<float>(), s));
+    NDB_CUDA(cudaMemcpyAsync(D, dd.p, (size_t) TC_M * TC_N * 4, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    return NDB_B200_OK;
+}

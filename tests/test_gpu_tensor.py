@@ -1,0 +1,57 @@
+"""GPU: the tcgen05 (bf16 tensor-core) GEMM-form distance path, tolerance 1e-3 (north_star)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def bf16_round(a):
+    """Round fp32 to the nearest bf16-representable value (round to nearest even)."""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("dim", [128, 64, 96, 200, 256])
+def test_umma_tile_matches_numpy(ndb, dim):
+    """Raw accumulator D = Q X^T of one 128 x 256 tile: validates the smem/instruction descriptors."""
+    rng = np.random.default_rng(dim)
+    Q = bf16_round(rng.standard_normal((128, dim)).astype(np.float32))
+    X = bf16_round(rng.standard_normal((256, dim)).astype(np.float32))
+    D = np.zeros((128, 256), np.float32)
+    lib = ndb._lib.load()
+    lib.ndbdbg_tc_gemm.restype = C.c_int
+    lib.ndbdbg_tc_gemm.argtypes = [C.c_void_p] * 1 + [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    rc = lib.ndbdbg_tc_gemm(Q.ctypes.data, 128, X.ctypes.data, 256, dim, D.ctypes.data)
+    assert rc == 0, lib.ndb_b200_last_error()
+    want = Q.astype(np.float64) @ X.astype(np.float64).T
+    assert np.max(np.abs(D - want)) < 1e-3 * np.max(np.abs(want)), np.max(np.abs(D - want))
+
+
+@pytest.mark.parametrize("n,dim,nq,k", [(5000, 128, 300, 10), (1000, 96, 130, 1), (70000, 128, 1000, 10), (300, 256, 7, 16)])
+@pytest.mark.parametrize("metric", [1, 3])
+def test_tensor_knn_within_tolerance(ndb, orc, n, dim, nq, k, metric):
+    X = bf16_round(W.gaussian(n, dim, 50 + n))          # config 5 data is bf16: inputs are representable
+    Q = bf16_round(W.gaussian(nq, dim, 51 + n))
+    ds = ndb.Dataset(dim)
+    ds.append(X)
+    d, i = ds.knn(Q, k, metric, ndb.ARITH_TENSOR)
+    if metric == 1:
+        od, oi = orc.knn_exact(X, Q, k, 1, orc.ARITH_OP_F64)
+    else:
+        # tensor IP = -dot (ranking by largest inner product, hnsw_am.c:1334-1337 sign convention)
+        dots = Q.astype(np.float64) @ X.astype(np.float64).T
+        oi = np.argsort(-dots, axis=1, kind="stable")[:, :k]
+        od = np.take_along_axis(-dots, oi, 1).astype(np.float32)
+    # distances within 1e-3 relative (bf16 tensor-core contract)
+    assert np.max(np.abs(d - od) / np.maximum(np.abs(od), 1e-3)) < 1e-3
+    # ids identical wherever the gap to the neighbouring rank exceeds the tolerance
+    same = (i == oi)
+    assert same.mean() > 0.995
+    for q, j in zip(*np.nonzero(~same)):
+        assert abs(od[q, j] - d[q, j]) <= 1e-3 * max(abs(od[q, j]), 1e-3)
+    assert np.all(np.diff(d, axis=1) >= 0)

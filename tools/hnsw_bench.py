@@ -1,0 +1,48 @@
+"""HNSW (BASELINE config 3 shape, scaled): build seconds, search QPS, evaluations per query and
+recall@10 on the GPU; the reference-literal CPU build/search (oracle) timed next to it."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np
+import neurondb_b200 as ndb
+import oracle_lib as O
+import workloads as W
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
+dim = int(sys.argv[2]) if len(sys.argv) > 2 else 768
+n_cpu = int(sys.argv[3]) if len(sys.argv) > 3 else 20_000
+m, efc, efs, nq = 16, 64, 40, 10_000
+ndb.init(0)
+ndb.set_timing(True)
+X = W.normalised(n, dim, 768)
+Q = W.normalised(nq, dim, 769)
+levels = O.hnsw_levels(n, seed=768)
+h = ndb.HnswIndex(dim, m, efc, efs, ndb.COSINE)
+t = time.time(); h.hnswbuild(X, levels=levels); tb = time.time() - t
+print(f"GPU build n={n} dim={dim} M={m} efC={efc}: {tb:.2f} s ({n/tb:.0f} inserts/s), {h.last_evals()/n:.0f} evals/insert")
+gt = W.exact_ground_truth(X, Q[:500], 10)
+for mode, nm in ((ndb.HNSW_BESTFIRST, "best-first"), (ndb.HNSW_LITERAL, "literal")):
+    for strategy, sn in ((1, "L2"), (2, "cosine")):
+        for _ in range(3):
+            t = time.time(); d, i = h.search(Q, efs, 10, strategy, mode); e2e = time.time() - t
+        ms, _, _ = ndb.last_kernel_stats()
+        ev = h.last_evals() / nq
+        rec = O.recall_at_k(i[:500], gt)
+        bytes_q = ev * (dim * 4 + 2 * m * 4)
+        print(f"GPU search {nm:10s} {sn:6s} ef={efs}: kernel {ms:.3f} ms -> {nq/ms*1e3:.0f} QPS ({nq/e2e:.0f} e2e), {ev:.0f} evals/query, "
+              f"{bytes_q*nq/ms/1e6:.0f} GB/s gathered, recall@10 {rec:.4f}")
+if n_cpu:
+    Xc, lc = X[:n_cpu], levels[:n_cpu]
+    gtc = W.exact_ground_truth(Xc, Q[:500], 10)
+    for bmode, bn in ((0, "reference-literal"), (1, "per-level")):
+        g = O.Hnsw(dim, m, efc, efs, capacity=n_cpu, native=True)
+        t = time.time(); g.build(Xc, lc, bmode); tcb = time.time() - t
+        for smode, sn in ((0, "literal"), (1, "best-first")):
+            t = time.time(); d, nn, _ = g.search(Q[:2000], efs, 10, 1, smode, nthreads=os.cpu_count()); ts = time.time() - t
+            rec = O.recall_at_k(nn[:500].astype(np.int64), gtc)
+            print(f"CPU oracle n={n_cpu} build {bn} {tcb:.1f} s ({n_cpu/tcb:.0f} inserts/s, 1 thread); search {sn}: {2000/ts:.0f} QPS "
+                  f"({os.cpu_count()} threads), recall@10 {rec:.4f}")
+    hg = ndb.HnswIndex(dim, m, efc, efs)
+    t = time.time(); hg.hnswbuild(Xc, levels=lc); tg = time.time() - t
+    d, i = hg.search(Q[:2000], efs, 10, 1, ndb.HNSW_BESTFIRST)
+    print(f"GPU n={n_cpu}: build {tg:.2f} s; best-first recall@10 {O.recall_at_k(i[:500], gtc):.4f}")
