@@ -15,15 +15,16 @@
 // A (tile, chunk) is fetched with ONE cp.async.bulk (no tensor map, no swizzle) and is directly
 // consumable by tcgen05.mma through a shared-memory matrix descriptor.
 //
-// Kernel (persistent, 256 threads):
+// Kernel (persistent, 384 threads):
 //   warp 0    TMA producer: Q tile once per work item, then X (tile, chunk) stages into a 2-deep ring
 //   warp 1    MMA issuer: one elected thread issues 8 x tcgen05.mma.kind::f16 (M=128, N=256, K=16) per
 //             stage into one of two 256-column TMEM accumulators; tcgen05.commit frees the smem
 //             stage and, after the last chunk, publishes the accumulator
 //   warp 2    TMEM allocator (512 columns)
-//   warps 4-7 epilogue: thread = query (TMEM lane); tcgen05.ld 32 columns at a time; candidate =
-//             fma(-2, dot, ||x||^2) compared against the thread's k-th best; the top-k is a
-//             thread-local sorted array in registers -- no cross-lane traffic at all
+//   warps 4-11 epilogue: thread = (query = TMEM lane, half of the 256 columns); tcgen05.ld 32 columns
+//             at a time; candidates fma(-2, dot, ||x||^2) are min-reduced and compared against the
+//             thread's k-th best once per 32; the top-k is a thread-local sorted list -- no
+//             cross-lane traffic at all
 // Work item = (query tile, range of X tiles); per-item top-k lists are merged by (dist, id) by
 // merge_parts_kernel (scan.cuh).
 #include "layout.cuh"
@@ -213,23 +214,65 @@ struct TcParams {
     float *pdist;                  // [nq][nranges][k]
     uint32_t *pslot;
     float *debug_d;                // optional: raw accumulator of the first tile [128][256]
+    int debug_mode;                // NDB_TC_DEBUG: 1 = no epilogue math, 2 = no MMA issue, 4 = no X bulk copies (bisection aid)
 };
 
-// thread-local sorted top-k in registers (k <= TC_KMAX): insert (d, id) known to beat entry k-1
-__device__ __forceinline__ void tk_insert(float (&bd)[TC_KMAX], uint32_t (&bi)[TC_KMAX], float d, uint32_t id, int k)
+// thread-local sorted top-KT list in registers: branch-free insertion of (d, id).
+//   L'[j] = L[j]            if L[j] precedes the new pair
+//         = new             if L[j-1] precedes it (or j == 0) but L[j] does not
+//         = L[j-1]          otherwise (shifted down; the last entry falls off)
+// One copy of this code sits in a loop over the (rare) passing candidates of a 32-column chunk:
+// inlining it per candidate blows the instruction cache (ncu: no_instruction 17.8 cycles/issue),
+// and a called version with the list in local memory serialises on LDL/STL latency.
+template <int KT>
+__device__ __forceinline__ void tk_insert(float (&bd)[KT], uint32_t (&bi)[KT], float d, uint32_t id)
 {
-    bool placed = false;
+    bool lt[KT];
 #pragma unroll
-    for (int j = TC_KMAX - 1; j >= 0; j--) {
-        if (j < k && !placed) {
-            const bool prev_greater = j > 0 && (bd[j - 1] > d || (bd[j - 1] == d && bi[j - 1] > id));
-            if (prev_greater) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; }
-            else { bd[j] = d; bi[j] = id; placed = true; }
-        }
+    for (int j = 0; j < KT; j++) lt[j] = bd[j] < d || (bd[j] == d && bi[j] < id);
+#pragma unroll
+    for (int j = KT - 1; j >= 0; j--) {
+        const bool take_new = j == 0 ? !lt[0] : (lt[j - 1] && !lt[j]);
+        const bool take_prev = j > 0 && !lt[j - 1];
+        const float pd = j > 0 ? bd[j - 1] : d;
+        const uint32_t pi = j > 0 ? bi[j - 1] : id;
+        bd[j] = take_new ? d : (take_prev ? pd : bd[j]);
+        bi[j] = take_new ? id : (take_prev ? pi : bi[j]);
     }
 }
 
-__global__ void __launch_bounds__(256, 1) tc_knn_kernel(const TcParams p)
+// c[i] for a run-time i with c held in registers: 5-level select tree on the bits of i
+__device__ __forceinline__ float pick32(const float (&c)[32], int i)
+{
+    float t16[16], t8[8], t4[4], t2[2];
+#pragma unroll
+    for (int j = 0; j < 16; j++) t16[j] = (i & 1) ? c[2 * j + 1] : c[2 * j];
+#pragma unroll
+    for (int j = 0; j < 8; j++) t8[j] = (i & 2) ? t16[2 * j + 1] : t16[2 * j];
+#pragma unroll
+    for (int j = 0; j < 4; j++) t4[j] = (i & 4) ? t8[2 * j + 1] : t8[2 * j];
+#pragma unroll
+    for (int j = 0; j < 2; j++) t2[j] = (i & 8) ? t4[2 * j + 1] : t4[2 * j];
+    return (i & 16) ? t2[1] : t2[0];
+}
+
+// spin (no suspend-time hint): every tile hand-off between producer, MMA issuer and epilogue sits on
+// the critical path, and a suspended waiter wakes up late
+__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "SPIN_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra OUT_%=;\n\t"
+        "bra SPIN_%=;\n\t"
+        "OUT_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int KT, int METRIC>
+__global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
 {
     extern __shared__ __align__(1024) unsigned char tsm[];
     // [Q tile: nkc * 32 KB][X ring: 2 * 64 KB][norm ring: 8 * 1 KB]
@@ -246,7 +289,7 @@ __global__ void __launch_bounds__(256, 1) tc_knn_kernel(const TcParams p)
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&q_full, 1);
         mbar_init(&q_empty, 1);
-        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 256); }
         mbar_fence_init();
     }
     if (warp == 2) { tmem_alloc(&tmem_holder, 512); tmem_relinquish(); }
@@ -261,7 +304,7 @@ __global__ void __launch_bounds__(256, 1) tc_knn_kernel(const TcParams p)
             uint32_t stage_it = 0, tile_it = 0, item_it = 0;
             for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x, item_it++) {
                 const uint32_t qt = item % p.nqt, xr = item / p.nqt;
-                mbar_wait(&q_empty, (item_it & 1u) ^ 1u);              // MMA finished with the previous Q tile
+                mbar_spin(&q_empty, (item_it & 1u) ^ 1u);              // MMA finished with the previous Q tile
                 mbar_arrive_expect_tx(&q_full, (uint32_t) p.nkc * TC_QCHUNK_BYTES);
                 for (int c = 0; c < p.nkc; c++)
                     tma_bulk_g2s(q_smem + (size_t) c * TC_QCHUNK_BYTES,
@@ -272,10 +315,11 @@ __global__ void __launch_bounds__(256, 1) tc_knn_kernel(const TcParams p)
                 for (uint32_t t = t0; t < t1; t++, tile_it++) {
                     for (int c = 0; c < p.nkc; c++, stage_it++) {
                         const uint32_t s = stage_it % TC_STAGES;
-                        mbar_wait(&empty_bar[s], ((stage_it / TC_STAGES) & 1u) ^ 1u);
-                        const uint32_t bytes = TC_XSTAGE_BYTES + (c == 0 ? TC_N * 4 : 0);
+                        mbar_spin(&empty_bar[s], ((stage_it / TC_STAGES) & 1u) ^ 1u);
+                        const bool skip_x = (p.debug_mode & 4) != 0;
+                        const uint32_t bytes = (skip_x ? 0 : TC_XSTAGE_BYTES) + (c == 0 ? TC_N * 4 : 0);
                         mbar_arrive_expect_tx(&full_bar[s], bytes);
-                        tma_bulk_g2s(x_smem + (size_t) s * TC_XSTAGE_BYTES,
+                        if (!skip_x) tma_bulk_g2s(x_smem + (size_t) s * TC_XSTAGE_BYTES,
                                      reinterpret_cast<const unsigned char *>(p.xb) + ((size_t) t * p.nkc + c) * TC_XSTAGE_BYTES,
                                      TC_XSTAGE_BYTES, &full_bar[s]);
                         if (c == 0)
@@ -294,16 +338,16 @@ __global__ void __launch_bounds__(256, 1) tc_knn_kernel(const TcParams p)
                 const uint32_t xr = item / p.nqt;
                 const uint32_t t0 = xr * p.tiles_per_range;
                 const uint32_t t1 = min(p.ntiles, t0 + p.tiles_per_range);
-                mbar_wait(&q_full, item_it & 1u);
+                mbar_spin(&q_full, item_it & 1u);
                 tc_fence_after();
                 for (uint32_t t = t0; t < t1; t++, tile_it++) {
                     const uint32_t a = tile_it & 1u;
-                    mbar_wait(&acc_empty[a], ((tile_it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
+                    mbar_spin(&acc_empty[a], ((tile_it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + a * TC_N;
                     for (int c = 0; c < p.nkc; c++, stage_it++) {
                         const uint32_t s = stage_it % TC_STAGES;
-                        mbar_wait(&full_bar[s], (stage_it / TC_STAGES) & 1u);
+                        mbar_spin(&full_bar[s], (stage_it / TC_STAGES) & 1u);
                         tc_fence_after();
                         const uint32_t qa = smem_u32(q_smem + (size_t) c * TC_QCHUNK_BYTES);
                         const uint32_t xa = smem_u32(x_smem + (size_t) s * TC_XSTAGE_BYTES);
@@ -312,7 +356,7 @@ __global__ void __launch_bounds__(256, 1) tc_knn_kernel(const TcParams p)
                             // one MMA consumes K = 16 = two 8-element core matrices along K
                             const uint64_t da = umma_desc(qa + ks * 2 * (TC_M / 8) * 128, (TC_M / 8) * 128, 128);
                             const uint64_t db = umma_desc(xa + ks * 2 * (TC_N / 8) * 128, (TC_N / 8) * 128, 128);
-                            umma_bf16(tmem_d, da, db, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                            if (!(p.debug_mode & 2)) umma_bf16(tmem_d, da, db, idesc, (c > 0 || ks > 0) ? 1u : 0u);
                         }
                         umma_commit(&empty_bar[s]);                     // smem stage reusable once these MMAs retire
                     }
@@ -322,9 +366,13 @@ __global__ void __launch_bounds__(256, 1) tc_knn_kernel(const TcParams p)
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread = query =====
-        const int ql = tid - 128;                                       // TMEM lane
-        const uint32_t lane_addr = (uint32_t) (ql & ~31) << 16;         // this warp's lane quarter
+        // ===== epilogue: 8 warps; thread = (query lane, column half) =====
+        // warps 4-7 read accumulator columns [0,128), warps 8-11 columns [128,256) of the same 128
+        // TMEM lanes (a warp may only touch the lane quarter 32*(warp%4)); each thread keeps its own
+        // top-KT list and the two halves are merged with the other parts afterwards.
+        const int ql = (warp & 3) * 32 + lane;                          // TMEM lane = query within the tile
+        const int half = (warp - 4) >> 2;
+        const uint32_t lane_addr = (uint32_t) ((warp & 3) * 32) << 16;
         uint32_t tile_it = 0;
         for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
             const uint32_t qt = item % p.nqt, xr = item / p.nqt;
@@ -332,47 +380,77 @@ __global__ void __launch_bounds__(256, 1) tc_knn_kernel(const TcParams p)
             const uint32_t t1 = min(p.ntiles, t0 + p.tiles_per_range);
             const uint32_t q = qt * TC_M + ql;
             const float qn = p.qnorm[q];
-            float bd[TC_KMAX];
-            uint32_t bi[TC_KMAX];
+            float bd[KT];
+            uint32_t bi[KT];
 #pragma unroll
-            for (int j = 0; j < TC_KMAX; j++) { bd[j] = INFINITY; bi[j] = INVALID_SLOT; }
-            float thr = INFINITY;                                       // k-th best, in "candidate" units
+            for (int j = 0; j < KT; j++) { bd[j] = INFINITY; bi[j] = INVALID_SLOT; }
+            float thr = INFINITY;                                       // KT-th best, in "candidate" units
             for (uint32_t t = t0; t < t1; t++, tile_it++) {
                 const uint32_t a = tile_it & 1u;
-                mbar_wait(&acc_full[a], (tile_it >> 1) & 1u);
+                mbar_spin(&acc_full[a], (tile_it >> 1) & 1u);
                 tc_fence_after();
                 const float *xn = n_smem + (size_t) (tile_it % TC_NORM_RING) * TC_N;
 #pragma unroll 1
-                for (int j = 0; j < TC_N / 32; j++) {
+                for (int j = 0; j < ((p.debug_mode & 1) ? 0 : TC_N / 64); j++) {
+                    const int col0 = half * (TC_N / 2) + j * 32;
                     uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_addr + a * TC_N + j * 32, v);
+                    tmem_ld32(tmem_base + lane_addr + a * TC_N + col0, v);
                     tmem_ld_wait();
                     if (p.debug_d && item == 0 && t == t0) {
 #pragma unroll
-                        for (int i = 0; i < 32; i++) p.debug_d[(size_t) ql * TC_N + j * 32 + i] = __uint_as_float(v[i]);
+                        for (int i = 0; i < 32; i++) p.debug_d[(size_t) ql * TC_N + col0 + i] = __uint_as_float(v[i]);
                     }
+                    // candidates: L2 -> ||x||^2 - 2 x.q (||q||^2 is added on output); IP -> -x.q; pad rows
+                    // carry +inf norms and never rank.  32 independent FFMAs, then one min tree: the
+                    // common case (nothing beats the threshold) is branch-free.
+                    float c[32];
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        const float dot = __uint_as_float(v[i]);
-                        // L2: ||x||^2 - 2 x.q (+ ||q||^2 added on output); IP: -x.q; pad rows carry +inf norms
-                        const float cand = p.metric == NDB_L2 ? fmaf(-2.0f, dot, xn[j * 32 + i]) : (xn[j * 32 + i] == INFINITY ? INFINITY : -dot);
-                        if (cand < thr) {
-                            tk_insert(bd, bi, cand, t * TC_N + j * 32 + i, p.k);
+                    for (int i4 = 0; i4 < 8; i4++) {
+                        const float4 n4 = *reinterpret_cast<const float4 *>(xn + col0 + 4 * i4);
+                        if (METRIC == NDB_L2) {
+                            c[4 * i4 + 0] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 0]), n4.x);
+                            c[4 * i4 + 1] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 1]), n4.y);
+                            c[4 * i4 + 2] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 2]), n4.z);
+                            c[4 * i4 + 3] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 3]), n4.w);
+                        } else {
+                            c[4 * i4 + 0] = n4.x == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 0]);
+                            c[4 * i4 + 1] = n4.y == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 1]);
+                            c[4 * i4 + 2] = n4.z == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 2]);
+                            c[4 * i4 + 3] = n4.w == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 3]);
+                        }
+                    }
+                    float m[16];
 #pragma unroll
-                            for (int jj = 0; jj < TC_KMAX; jj++) if (jj == p.k - 1) thr = bd[jj];
+                    for (int i = 0; i < 16; i++) m[i] = fminf(c[i], c[i + 16]);
+#pragma unroll
+                    for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+                        for (int i = 0; i < w; i++) m[i] = fminf(m[i], m[i + w]);
+                    if (m[0] < thr) {
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) mask |= (c[i] < thr ? 1u : 0u) << i;
+                        while (mask) {
+                            const int i = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const float cand = pick32(c, i);
+                            if (cand < thr) {
+                                tk_insert<KT>(bd, bi, cand, t * TC_N + col0 + i);
+                                thr = bd[KT - 1];
+                            }
                         }
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&acc_empty[a]);                             // 128 arrivals release the accumulator
+                mbar_arrive(&acc_empty[a]);                             // 256 arrivals release the accumulator
             }
             if (q < (uint32_t) p.nq) {
-                const size_t base = ((size_t) q * p.nranges + xr) * p.k;
+                const size_t base = ((size_t) q * (p.nranges * 2) + xr * 2 + half) * p.k;
 #pragma unroll
-                for (int j = 0; j < TC_KMAX; j++) {
+                for (int j = 0; j < KT; j++) {
                     if (j < p.k) {
                         float d = bd[j];
-                        if (p.metric == NDB_L2 && bi[j] != INVALID_SLOT) d = sqrtf(fmaxf(d + qn, 0.0f));
+                        if (METRIC == NDB_L2 && bi[j] != INVALID_SLOT) d = sqrtf(fmaxf(d + qn, 0.0f));
                         p.pdist[base + j] = d;
                         p.pslot[base + j] = bi[j];
                     }
@@ -432,8 +510,8 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     if (nranges > (uint32_t) st.ntiles) nranges = (uint32_t) st.ntiles;
     const uint32_t tpr = (uint32_t) ((st.ntiles + nranges - 1) / nranges);
     nranges = (uint32_t) ((st.ntiles + tpr - 1) / tpr);
-    NDB_CHECK(sc.pdist.reserve((size_t) nq * nranges * k * 4));
-    NDB_CHECK(sc.pslot.reserve((size_t) nq * nranges * k * 4));
+    NDB_CHECK(sc.pdist.reserve((size_t) nq * nranges * 2 * k * 4));
+    NDB_CHECK(sc.pslot.reserve((size_t) nq * nranges * 2 * k * 4));
     TcParams p;
     p.xb = st.xb.as<__nv_bfloat16>();
     p.xnorm = st.xnorm.as<float>();
@@ -444,17 +522,32 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     p.pdist = sc.pdist.as<float>();
     p.pslot = sc.pslot.as<uint32_t>();
     p.debug_d = debug_d_dev;
+    p.debug_mode = getenv("NDB_TC_DEBUG") ? atoi(getenv("NDB_TC_DEBUG")) : 0;
     const size_t smem = tc_smem_bytes();
-    static bool configured = false;
-    if (!configured) {
-        NDB_CUDA(cudaFuncSetAttribute(tc_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        configured = true;
-    }
     const uint32_t nitems = nqt * nranges;
     const uint32_t grid = nitems < sms ? nitems : sms;
     Context &c = ctx();
     if (c.timing) NDB_CUDA(cudaEventRecord(c.ev0, s));
-    tc_knn_kernel<<<grid, 256, smem, s>>>(p);
+    // list length: the smallest of {1, 10, 16} that holds k (a shorter list = a tighter threshold)
+#define NDB_TC_LAUNCH(KT, M)                                                                                  \
+    do {                                                                                                      \
+        static bool cfg = false;                                                                              \
+        if (!cfg) {                                                                                           \
+            NDB_CUDA(cudaFuncSetAttribute(tc_knn_kernel<KT, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+            cfg = true;                                                                                       \
+        }                                                                                                     \
+        tc_knn_kernel<KT, M><<<grid, 384, smem, s>>>(p);                                                      \
+    } while (0)
+    if (metric == NDB_L2) {
+        if (k == 1) NDB_TC_LAUNCH(1, NDB_L2);
+        else if (k <= 10) NDB_TC_LAUNCH(10, NDB_L2);
+        else NDB_TC_LAUNCH(TC_KMAX, NDB_L2);
+    } else {
+        if (k == 1) NDB_TC_LAUNCH(1, NDB_IP);
+        else if (k <= 10) NDB_TC_LAUNCH(10, NDB_IP);
+        else NDB_TC_LAUNCH(TC_KMAX, NDB_IP);
+    }
+#undef NDB_TC_LAUNCH
     count_launch();
     NDB_CUDA(cudaGetLastError());
     if (c.timing) {
@@ -464,7 +557,7 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
         c.last_evals = (int64_t) st.valid_for * nq;
         c.stats_src = nullptr;
     }
-    return launch_merge_parts(sc.pdist.as<float>(), sc.pslot.as<uint32_t>(), ids, nq, (int) nranges, k, dist_dev, ids_dev, nullptr, s);
+    return launch_merge_parts(sc.pdist.as<float>(), sc.pslot.as<uint32_t>(), ids, nq, (int) nranges * 2, k, dist_dev, ids_dev, nullptr, s);
 }
 
 }  // namespace ndb
