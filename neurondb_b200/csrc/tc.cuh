@@ -12,9 +12,19 @@ struct TcStore {
     int nkc = 0;
 };
 
-struct TcScratch {
-    DevBuf qb, qnorm, pdist, pslot, debug;
+// one unit of work of tc_knn_kernel: query tile `qtile` (128 queries) against stored tiles [t0, t1)
+// (256 rows each); lane ql / column-half h writes its k results at partial slot
+// out_base + ql * out_stride + h, for ql < nq
+struct TcItem {
+    uint32_t qtile, t0, t1, nq, out_base, out_stride;
 };
+
+struct TcScratch {
+    DevBuf qb, qnorm, pdist, pslot, debug, items;
+};
+
+struct TcParams;
+int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s);
 
 int tc_build_store(TcStore &st, const float *il32_store, int64_t n, int dim, int dimp, cudaStream_t s);
 int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q_dev, int nq, int k, const int64_t *ids,

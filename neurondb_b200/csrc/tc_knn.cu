@@ -32,6 +32,7 @@
 #include "tc.cuh"
 
 #include <cuda_bf16.h>
+#include <algorithm>
 
 namespace ndb {
 
@@ -204,14 +205,12 @@ struct TcParams {
     const __nv_bfloat16 *xb;       // blocked stored rows
     const float *xnorm;            // [ntiles * 256]
     const __nv_bfloat16 *qb;       // blocked query tiles
-    const float *qnorm;            // [nqpad]
+    const float *qnorm;            // [query tiles * 128]
     int nkc;                       // K-chunks (dimp / 128)
-    int nq, k, metric;
-    uint32_t nqt;                  // query tiles
-    uint32_t ntiles;               // X tiles
-    uint32_t nranges;              // X ranges (parts per query)
-    uint32_t tiles_per_range;
-    float *pdist;                  // [nq][nranges][k]
+    int k;
+    const TcItem *items;           // work items
+    uint32_t nitems;
+    float *pdist;                  // partial results, indexed through TcItem::out_base / out_stride
     uint32_t *pslot;
     float *debug_d;                // optional: raw accumulator of the first tile [128][256]
     int debug_mode;                // NDB_TC_DEBUG: 1 = no epilogue math, 2 = no MMA issue, 4 = no X bulk copies (bisection aid)
@@ -283,7 +282,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
     __shared__ uint32_t tmem_holder;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t nitems = p.nqt * p.nranges;
+    const uint32_t nitems = p.nitems;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -303,15 +302,15 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
         if (lane == 0) {
             uint32_t stage_it = 0, tile_it = 0, item_it = 0;
             for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x, item_it++) {
-                const uint32_t qt = item % p.nqt, xr = item / p.nqt;
+                const TcItem it = p.items[item];
+                const uint32_t qt = it.qtile;
                 mbar_spin(&q_empty, (item_it & 1u) ^ 1u);              // MMA finished with the previous Q tile
                 mbar_arrive_expect_tx(&q_full, (uint32_t) p.nkc * TC_QCHUNK_BYTES);
                 for (int c = 0; c < p.nkc; c++)
                     tma_bulk_g2s(q_smem + (size_t) c * TC_QCHUNK_BYTES,
                                  reinterpret_cast<const unsigned char *>(p.qb) + ((size_t) qt * p.nkc + c) * TC_QCHUNK_BYTES,
                                  TC_QCHUNK_BYTES, &q_full);
-                const uint32_t t0 = xr * p.tiles_per_range;
-                const uint32_t t1 = min(p.ntiles, t0 + p.tiles_per_range);
+                const uint32_t t0 = it.t0, t1 = it.t1;
                 for (uint32_t t = t0; t < t1; t++, tile_it++) {
                     for (int c = 0; c < p.nkc; c++, stage_it++) {
                         const uint32_t s = stage_it % TC_STAGES;
@@ -335,9 +334,8 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
             const uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
             uint32_t stage_it = 0, tile_it = 0, item_it = 0;
             for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x, item_it++) {
-                const uint32_t xr = item / p.nqt;
-                const uint32_t t0 = xr * p.tiles_per_range;
-                const uint32_t t1 = min(p.ntiles, t0 + p.tiles_per_range);
+                const TcItem it = p.items[item];
+                const uint32_t t0 = it.t0, t1 = it.t1;
                 mbar_spin(&q_full, item_it & 1u);
                 tc_fence_after();
                 for (uint32_t t = t0; t < t1; t++, tile_it++) {
@@ -375,11 +373,9 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
         const uint32_t lane_addr = (uint32_t) ((warp & 3) * 32) << 16;
         uint32_t tile_it = 0;
         for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const uint32_t qt = item % p.nqt, xr = item / p.nqt;
-            const uint32_t t0 = xr * p.tiles_per_range;
-            const uint32_t t1 = min(p.ntiles, t0 + p.tiles_per_range);
-            const uint32_t q = qt * TC_M + ql;
-            const float qn = p.qnorm[q];
+            const TcItem it = p.items[item];
+            const uint32_t t0 = it.t0, t1 = it.t1;
+            const float qn = p.qnorm[(size_t) it.qtile * TC_M + ql];
             float bd[KT];
             uint32_t bi[KT];
 #pragma unroll
@@ -396,7 +392,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     uint32_t v[32];
                     tmem_ld32(tmem_base + lane_addr + a * TC_N + col0, v);
                     tmem_ld_wait();
-                    if (p.debug_d && item == 0 && t == t0) {
+                    if (p.debug_d && item == 0 && t == t0) {   // first item's first tile
 #pragma unroll
                         for (int i = 0; i < 32; i++) p.debug_d[(size_t) ql * TC_N + col0 + i] = __uint_as_float(v[i]);
                     }
@@ -444,8 +440,8 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                 tc_fence_before();
                 mbar_arrive(&acc_empty[a]);                             // 256 arrivals release the accumulator
             }
-            if (q < (uint32_t) p.nq) {
-                const size_t base = ((size_t) q * (p.nranges * 2) + xr * 2 + half) * p.k;
+            if ((uint32_t) ql < it.nq) {
+                const size_t base = ((size_t) it.out_base + (size_t) ql * it.out_stride + half) * p.k;
 #pragma unroll
                 for (int j = 0; j < KT; j++) {
                     if (j < p.k) {
@@ -486,46 +482,15 @@ int tc_build_store(TcStore &st, const float *il32_store, int64_t n, int dim, int
     return NDB_B200_OK;
 }
 
-// top-k of nq row-major fp32 queries against a TcStore; writes (dist, id) like the scan path
-int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q_dev, int nq, int k, const int64_t *ids,
-           float *dist_dev, int64_t *ids_dev, float *debug_d_dev, cudaStream_t s)
+// launch the persistent kernel over p.items (grid = min(items, SMs)); records timing events
+int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s)
 {
     NDB_REQUIRE(k >= 1 && k <= TC_KMAX, NDB_B200_EINVAL, "tensor path: k must be 1..%d", TC_KMAX);
     NDB_REQUIRE(metric == NDB_L2 || metric == NDB_IP, NDB_B200_EINVAL, "tensor path: metric %d not supported (L2, IP)", metric);
-    NDB_REQUIRE(st.ntiles > 0, NDB_B200_ESTATE, "tensor path: empty store");
-    const int nkc = st.nkc;
-    const uint32_t nqt = (uint32_t) ((nq + TC_M - 1) / TC_M);
-    const int nqpad = (int) nqt * TC_M;
-    NDB_CHECK(sc.qb.reserve((size_t) nqpad * nkc * TC_KC * 2));
-    NDB_CHECK(sc.qnorm.reserve((size_t) nqpad * 4));
-    const int groups = nkc * (TC_KC / 8);
-    tc_block_queries_kernel<<<(unsigned) (((int64_t) nqpad * groups + 255) / 256), 256, 0, s>>>(Q_dev, nq, nqpad, dim, nkc,
-                                                                                                sc.qb.as<__nv_bfloat16>(), sc.qnorm.as<float>());
-    tc_query_norms_kernel<<<(unsigned) ((nqpad + 127) / 128), 128, 0, s>>>(Q_dev, nq, nqpad, dim, sc.qnorm.as<float>());
-    count_launch(2);
-    // split the stored tiles into ranges so that there are ~2 work items per SM
-    const uint32_t sms = (uint32_t) ctx().sm_count;
-    uint32_t nranges = (2 * sms + nqt - 1) / nqt;
-    if (nranges < 1) nranges = 1;
-    if (nranges > (uint32_t) st.ntiles) nranges = (uint32_t) st.ntiles;
-    const uint32_t tpr = (uint32_t) ((st.ntiles + nranges - 1) / nranges);
-    nranges = (uint32_t) ((st.ntiles + tpr - 1) / tpr);
-    NDB_CHECK(sc.pdist.reserve((size_t) nq * nranges * 2 * k * 4));
-    NDB_CHECK(sc.pslot.reserve((size_t) nq * nranges * 2 * k * 4));
-    TcParams p;
-    p.xb = st.xb.as<__nv_bfloat16>();
-    p.xnorm = st.xnorm.as<float>();
-    p.qb = sc.qb.as<__nv_bfloat16>();
-    p.qnorm = sc.qnorm.as<float>();
-    p.nkc = nkc; p.nq = nq; p.k = k; p.metric = metric;
-    p.nqt = nqt; p.ntiles = (uint32_t) st.ntiles; p.nranges = nranges; p.tiles_per_range = tpr;
-    p.pdist = sc.pdist.as<float>();
-    p.pslot = sc.pslot.as<uint32_t>();
-    p.debug_d = debug_d_dev;
-    p.debug_mode = getenv("NDB_TC_DEBUG") ? atoi(getenv("NDB_TC_DEBUG")) : 0;
+    if (p.nitems == 0) return NDB_B200_OK;
     const size_t smem = tc_smem_bytes();
-    const uint32_t nitems = nqt * nranges;
-    const uint32_t grid = nitems < sms ? nitems : sms;
+    const uint32_t sms = (uint32_t) ctx().sm_count;
+    const uint32_t grid = p.nitems < sms ? p.nitems : sms;
     Context &c = ctx();
     if (c.timing) NDB_CUDA(cudaEventRecord(c.ev0, s));
     // list length: the smallest of {1, 10, 16} that holds k (a shorter list = a tighter threshold)
@@ -553,9 +518,73 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     if (c.timing) {
         NDB_CUDA(cudaEventRecord(c.ev1, s));
         c.last_ms = -1.0;
-        c.last_bytes = (double) st.ntiles * TC_N * nkc * TC_KC * 2.0;          // stored bf16 bytes, read once per launch
-        c.last_evals = (int64_t) st.valid_for * nq;
+        c.last_bytes = 0.0;
+        c.last_evals = 0;
         c.stats_src = nullptr;
+    }
+    return NDB_B200_OK;
+}
+
+// top-k of nq row-major fp32 queries against a TcStore; writes (dist, id) like the scan path
+int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q_dev, int nq, int k, const int64_t *ids,
+           float *dist_dev, int64_t *ids_dev, float *debug_d_dev, cudaStream_t s)
+{
+    NDB_REQUIRE(k >= 1 && k <= TC_KMAX, NDB_B200_EINVAL, "tensor path: k must be 1..%d", TC_KMAX);
+    NDB_REQUIRE(metric == NDB_L2 || metric == NDB_IP, NDB_B200_EINVAL, "tensor path: metric %d not supported (L2, IP)", metric);
+    NDB_REQUIRE(st.ntiles > 0, NDB_B200_ESTATE, "tensor path: empty store");
+    const int nkc = st.nkc;
+    const uint32_t nqt = (uint32_t) ((nq + TC_M - 1) / TC_M);
+    const int nqpad = (int) nqt * TC_M;
+    NDB_CHECK(sc.qb.reserve((size_t) nqpad * nkc * TC_KC * 2));
+    NDB_CHECK(sc.qnorm.reserve((size_t) nqpad * 4));
+    const int groups = nkc * (TC_KC / 8);
+    tc_block_queries_kernel<<<(unsigned) (((int64_t) nqpad * groups + 255) / 256), 256, 0, s>>>(Q_dev, nq, nqpad, dim, nkc,
+                                                                                                sc.qb.as<__nv_bfloat16>(), sc.qnorm.as<float>());
+    tc_query_norms_kernel<<<(unsigned) ((nqpad + 127) / 128), 128, 0, s>>>(Q_dev, nq, nqpad, dim, sc.qnorm.as<float>());
+    count_launch(2);
+    // split the stored tiles into ranges so that there are ~2 work items per SM
+    const uint32_t sms = (uint32_t) ctx().sm_count;
+    uint32_t nranges = (2 * sms + nqt - 1) / nqt;
+    if (nranges < 1) nranges = 1;
+    if (nranges > (uint32_t) st.ntiles) nranges = (uint32_t) st.ntiles;
+    const uint32_t tpr = (uint32_t) ((st.ntiles + nranges - 1) / nranges);
+    nranges = (uint32_t) ((st.ntiles + tpr - 1) / tpr);
+    NDB_CHECK(sc.pdist.reserve((size_t) nq * nranges * 2 * k * 4));
+    NDB_CHECK(sc.pslot.reserve((size_t) nq * nranges * 2 * k * 4));
+    // dense work items: (query tile, range of stored tiles); partial slot of (query q, part) is
+    // q * nparts + part with nparts = 2 * nranges (two column halves per range)
+    const uint32_t nitems = nqt * nranges;
+    std::vector<TcItem> items(nitems);
+    for (uint32_t i = 0; i < nitems; i++) {
+        const uint32_t qt = i % nqt, xr = i / nqt;
+        TcItem &it = items[i];
+        it.qtile = qt;
+        it.t0 = xr * tpr;
+        it.t1 = std::min<uint32_t>((uint32_t) st.ntiles, it.t0 + tpr);
+        it.nq = (uint32_t) std::min<int>(TC_M, nq - (int) qt * TC_M);
+        it.out_base = qt * TC_M * nranges * 2 + xr * 2;
+        it.out_stride = nranges * 2;
+    }
+    NDB_CHECK(sc.items.reserve((size_t) nitems * sizeof(TcItem)));
+    NDB_CUDA(cudaMemcpyAsync(sc.items.p, items.data(), (size_t) nitems * sizeof(TcItem), cudaMemcpyHostToDevice, s));
+    NDB_CUDA(cudaStreamSynchronize(s));        // `items` is a host temporary
+    TcParams p;
+    p.xb = st.xb.as<__nv_bfloat16>();
+    p.xnorm = st.xnorm.as<float>();
+    p.qb = sc.qb.as<__nv_bfloat16>();
+    p.qnorm = sc.qnorm.as<float>();
+    p.nkc = nkc; p.k = k;
+    p.items = sc.items.as<TcItem>();
+    p.nitems = nitems;
+    p.pdist = sc.pdist.as<float>();
+    p.pslot = sc.pslot.as<uint32_t>();
+    p.debug_d = debug_d_dev;
+    p.debug_mode = getenv("NDB_TC_DEBUG") ? atoi(getenv("NDB_TC_DEBUG")) : 0;
+    const size_t smem = tc_smem_bytes();
+    NDB_CHECK(tc_launch(p, metric, k, s));
+    if (ctx().timing) {
+        ctx().last_bytes = (double) st.ntiles * TC_N * nkc * TC_KC * 2.0;          // stored bf16 bytes, read once per launch
+        ctx().last_evals = (int64_t) st.valid_for * nq;
     }
     return launch_merge_parts(sc.pdist.as<float>(), sc.pslot.as<uint32_t>(), ids, nq, (int) nranges * 2, k, dist_dev, ids_dev, nullptr, s);
 }
