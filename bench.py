@@ -150,7 +150,7 @@ def run_reference(args, w):
     line = {
         "impl": "reference", "metric": "QPS@recall@10>=0.95", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16 select + f32 re-rank" if args.arith == "tensor" else "f32", "data": "synthetic",
         "config": {"workload": w["label"], "rows": w["n"], "dim": w["dim"], "lists": w["lists"], "nprobe": w["nprobe"],
                    "k": w["k"], "queries_per_step": sample},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
@@ -170,7 +170,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--arith", default="ivf_f32", choices=["ivf_f32", "fast"])
+    ap.add_argument("--arith", default="ivf_f32", choices=["ivf_f32", "fast", "tensor"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -192,7 +192,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ndb.init(local)
-    arith = ndb.ARITH_IVF_F32 if args.arith == "ivf_f32" else ndb.ARITH_FAST
+    arith = {"ivf_f32": ndb.ARITH_IVF_F32, "fast": ndb.ARITH_FAST, "tensor": ndb.ARITH_TENSOR}[args.arith]
 
     X, Q = make_data(w)
     nq, k, dim = w["nq"], w["k"], w["dim"]
@@ -348,6 +348,18 @@ def main():
                          "frac": fp32_ops / (kernel_ms * 1e-3) / fp32_peak, "unit": "T fp32 instr/s (non-fused)",
                          "sm_mhz": sm_mhz}}
 
+    if args.arith == "tensor":
+        # tc_knn_kernel (list mode): GEMM-form distances on tcgen05; algorithmic flops = 2 * dim per
+        # (query, scanned vector) pair; the kernel runs inside a longer step -> sustained peak
+        flops = 2.0 * evals * dim
+        tpeak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                    "traffic": None, "peak_source": peak_kind, "kernel": "tc_knn_kernel (list mode)",
+                    "kernel_ms": kernel_ms, "distance_evals_per_launch": evals,
+                    "note": "algorithmic flops only: the kernel also multiplies tile padding (lists padded to 256 rows, "
+                            "query groups padded to 128), which is not counted"}
+
     cpu = None
     if not args.no_cpu_baseline:
         import oracle_lib as O
@@ -366,7 +378,7 @@ def main():
     line = {
         "metric": "QPS@recall@10>=0.95", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16 select + f32 re-rank" if args.arith == "tensor" else "f32", "data": "synthetic",
         "config": {"workload": w["label"], "rows": w["n"], "dim": dim, "lists": w["lists"], "nprobe": w["nprobe"], "k": k,
                    "queries_per_step": nq, "arith": args.arith,
                    "l2": "inputs (%.2f GB of lists) larger than the 126 MB L2; 4 query batches rotate" % (w["n"] * dim * 4 / 1e9),

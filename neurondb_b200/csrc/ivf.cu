@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <numeric>
 #include <cub/block/block_scan.cuh>
+#include "tc.cuh"
 
 using namespace ndb;
 
@@ -45,6 +46,11 @@ struct ndb_b200_ivf {
     DevBuf probe, cnt, fill, qoff, item_off, qmap, pairpos, items, nitems, stats, tmp_rows, tmp_assign, tmp_keep;
     DevBuf qbuf, outd, outi, cdist;
     int64_t last_scanned = 0;
+    // tensor-core copy (NDB_ARITH_TENSOR): every list padded to whole 256-row tiles of blocked bf16
+    bool tc_ok = false, ctc_ok = false;
+    TcStore tc, ctc;                     // lists, centroids
+    TcScratch tcs, ctcs;
+    DevBuf tc_src, d_ltile8;             // tensor row -> IL32 slot; first tile of each list (* 8, in 32-row blocks)
 };
 
 namespace ndb {
@@ -77,7 +83,7 @@ __global__ void ivf_hist_kernel(const uint32_t *__restrict__ probe, int64_t npai
 // single CTA: exclusive scans, in `order`, of cnt (-> qoff) and of tiles * segments (-> item_off)
 __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ list_len,
                                                            const uint32_t *__restrict__ order, int nlists, int qt, uint32_t segb,
-                                                           uint32_t *__restrict__ qoff, uint32_t *__restrict__ item_off,
+                                                           uint32_t qalign, uint32_t *__restrict__ qoff, uint32_t *__restrict__ item_off,
                                                            uint32_t *__restrict__ nitems, unsigned long long *__restrict__ scanned)
 {
     typedef cub::BlockScan<uint32_t, 1024> Scan;
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__res
     unsigned long long sc = 0;
     for (int i = b; i < e; i++) {
         const uint32_t l = order[i], c = cnt[l];
-        sq += c;
+        sq += (c + qalign - 1) / qalign * qalign;
         st += ((c + qt - 1) / qt) * ivf_nseg(list_len[l], segb);
         sc += (unsigned long long) c * list_len[l];
     }
@@ -106,10 +112,10 @@ __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__res
         const uint32_t l = order[i], c = cnt[l];
         qoff[l] = oq;
         item_off[l] = ot;
-        oq += c;
+        oq += (c + qalign - 1) / qalign * qalign;
         ot += ((c + qt - 1) / qt) * ivf_nseg(list_len[l], segb);
     }
-    if (threadIdx.x == 1023) *nitems = ot;   // last thread's running total == grand total
+    if (threadIdx.x == 1023) { nitems[0] = ot; nitems[1] = oq; }   // last thread's running totals == grand totals
     __syncthreads();
     if (threadIdx.x == 0) *scanned = s_scanned;
 }
@@ -198,6 +204,102 @@ __global__ void ivf_merge_kernel(const float *__restrict__ pdist, const uint32_t
             out_dist[(size_t) q * k + e] = have ? top.d[r] : INFINITY;
             out_ids[(size_t) q * k + e] = have ? top.key[r] : -1;
         }
+    }
+}
+
+// ---- tensor-core list scan (NDB_ARITH_TENSOR) ---------------------------------------------------
+// Work items for tc_knn_kernel: (tile of 128 queries probing list l) x (segment of the list's
+// 256-row tiles).  list_blk here is the list's first tile * 8, segb the segment length in 32-row
+// blocks, so the bucketing kernels above are shared with the fp32 path.
+__global__ void ivf_tc_items_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ qoff,
+                                    const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len,
+                                    const uint32_t *__restrict__ ltile8, int nlists, uint32_t segb, TcItem *__restrict__ items)
+{
+    const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (l >= nlists) return;
+    const uint32_t c = cnt[l];
+    const uint32_t tiles = (c + TC_M - 1) / TC_M;
+    const uint32_t len = list_len[l], nseg = ivf_nseg(len, segb);
+    for (uint32_t i = threadIdx.x & 31; i < tiles * nseg; i += 32) {
+        const uint32_t t = i / nseg, sg = i - t * nseg;
+        const uint32_t nvec = min(segb * 32, len - sg * segb * 32);
+        TcItem it;
+        it.qtile = qoff[l] / TC_M + t;
+        it.t0 = (ltile8[l] + sg * segb) / 8;
+        it.t1 = it.t0 + (nvec + TC_N - 1) / TC_N;
+        it.nq = min((uint32_t) TC_M, c - t * TC_M);
+        it.out_base = (item_off[l] + i) * (2 * TC_M);
+        it.out_stride = 2;
+        items[item_off[l] + i] = it;
+    }
+}
+
+// Warp per query: merge the query's bf16 candidates over the probed lists (kc best by approximate
+// distance), then re-evaluate those candidates with the reference's fp32 arithmetic (policy P) and
+// return the k best by (dist, id).  The returned distances are therefore bit-identical to what the
+// fp32 path returns for the same ids; only the candidate SELECTION used bf16 products.
+template <class P>
+__global__ void __launch_bounds__(128) ivf_tc_finish_kernel(const float *__restrict__ pdist, const uint32_t *__restrict__ pslot,
+                                                            const uint32_t *__restrict__ tc_src, const float4 *__restrict__ vecs,
+                                                            const int64_t *__restrict__ ids, const float *__restrict__ Q,
+                                                            const uint32_t *__restrict__ probe, const uint32_t *__restrict__ pairpos,
+                                                            const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len,
+                                                            int nq, int nprobe, int nlists, uint32_t segb, int dim, int dimp, int kc,
+                                                            int k, float *__restrict__ out_dist, int64_t *__restrict__ out_ids)
+{
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    WarpTopK<1, uint32_t> cand;
+    cand.init();
+    for (int r = 0; r < nprobe; r++) {
+        const size_t p = (size_t) q * nprobe + r;
+        const uint32_t l = probe[p];
+        if (l >= (uint32_t) nlists) continue;
+        const uint32_t len = list_len[l];
+        if (len == 0) continue;
+        const uint32_t pos = pairpos[p], nseg = ivf_nseg(len, segb);
+        const uint32_t item0 = item_off[l] + (pos / TC_M) * nseg;
+        const uint32_t it = pos % TC_M;
+        // the 2 * nseg partial lists of kc entries are contiguous per (item, lane-in-tile)
+        for (uint32_t sg = 0; sg < nseg; sg++) {
+            const size_t base = ((size_t) (item0 + sg) * (2 * TC_M) + it * 2) * kc;
+            for (int i = lane; i < round_up(2 * kc, 32); i += 32) {
+                float cd = INFINITY;
+                uint32_t slot = INVALID_SLOT;
+                if (i < 2 * kc) { slot = pslot[base + i]; cd = pdist[base + i]; }
+                cand.offer(cd, slot, slot != INVALID_SLOT, lane, kc);
+            }
+        }
+    }
+    // lane e < kc holds candidate e
+    const uint32_t ts = lane < kc ? cand.key[0] : INVALID_SLOT;
+    float ed = INFINITY;
+    int64_t id = -1;
+    const bool have = ts != INVALID_SLOT;
+    if (have) {
+        const uint32_t slot = tc_src[ts];
+        const float *qv = Q + (size_t) q * dim;
+        const float4 *vp = vecs + (size_t) (slot >> 5) * (8 * (size_t) dimp) + (slot & 31);
+        typename P::Acc acc;
+        P::init(acc);
+        for (int j = 0; j < dim; j += 4) {
+            const float4 x = vp[(size_t) (j >> 2) * 32];
+            P::step(acc, x.x, qv[j]);
+            if (j + 1 < dim) P::step(acc, x.y, qv[j + 1]);
+            if (j + 2 < dim) P::step(acc, x.z, qv[j + 2]);
+            if (j + 3 < dim) P::step(acc, x.w, qv[j + 3]);
+        }
+        ed = P::finish(acc, 0, 0);
+        id = ids[slot];
+    }
+    WarpTopK<1, int64_t> top;
+    top.init();
+    top.offer(ed, id, have, lane, k);
+    if (lane < k) {
+        const bool got = top.key[0] != KeyMax<int64_t>::v;
+        out_dist[(size_t) q * k + lane] = got ? top.d[0] : INFINITY;
+        out_ids[(size_t) q * k + lane] = got ? top.key[0] : -1;
     }
 }
 
@@ -371,7 +473,166 @@ static int ivf_layout(ndb_b200_ivf *ix, cudaStream_t s)
         NDB_CUDA(cudaStreamSynchronize(s));     // host vectors above go out of scope
     }
     ix->vnorm_ivf_ok = ix->vnorm_fast_ok = false;
+    ix->tc_ok = false;
     ix->dirty = false;
+    return NDB_B200_OK;
+}
+
+static int ivf_coarse(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np, int arith, cudaStream_t s);
+
+// blocked bf16 copies for the tensor path: lists (each padded to whole 256-row tiles) and centroids
+static int ivf_tensor_ready(ndb_b200_ivf *ix, cudaStream_t s)
+{
+    const int L = ix->nlists;
+    if (!ix->ctc_ok) {
+        NDB_CHECK(tc_build_store(ix->ctc, ix->kw.cstore.as<float>(), L, ix->dim, ix->dimp, s));
+        ix->ctc_ok = true;
+    }
+    if (ix->tc_ok) return NDB_B200_OK;
+    std::vector<uint32_t> ltile8(L);
+    uint64_t nt = 0;
+    for (int l = 0; l < L; l++) {
+        ltile8[l] = (uint32_t) (nt * 8);
+        nt += (ix->list_len[l] + TC_N - 1) / TC_N;
+    }
+    NDB_REQUIRE(nt * TC_N < 0xfffffff0ull, NDB_B200_EINVAL, "ivf: too many rows for the tensor copy");
+    std::vector<uint32_t> src((size_t) (nt ? nt : 1) * TC_N, INVALID_SLOT);
+    for (int l = 0; l < L; l++) {
+        uint32_t *d = src.data() + (size_t) ltile8[l] * 32;
+        const uint32_t base = ix->list_blk[l] * 32;
+        for (uint32_t j = 0; j < ix->list_len[l]; j++) d[j] = base + j;
+    }
+    NDB_CHECK(ix->tc_src.reserve(src.size() * 4));
+    NDB_CHECK(ix->d_ltile8.reserve((size_t) L * 4));
+    NDB_CUDA(cudaMemcpyAsync(ix->tc_src.p, src.data(), src.size() * 4, cudaMemcpyHostToDevice, s));
+    NDB_CUDA(cudaMemcpyAsync(ix->d_ltile8.p, ltile8.data(), (size_t) L * 4, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(tc_build_store_mapped(ix->tc, ix->store.ptr(), ix->tc_src.as<uint32_t>(), (int64_t) (nt ? nt : 1) * TC_N, ix->dim,
+                                    ix->dimp, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    ix->tc_ok = true;
+    return NDB_B200_OK;
+}
+
+static uint32_t ivf_tc_seg_tiles()
+{
+    static const uint32_t v = [] { const char *e = getenv("NDB_IVF_TC_SEG_TILES"); int x = e ? atoi(e) : 16; return (uint32_t) (x >= 1 && x <= TC_PACKED_MAX_TILES ? x : 16); }();
+    return v;
+}
+static int ivf_tc_margin()
+{
+    static const int v = [] { const char *e = getenv("NDB_IVF_TC_MARGIN"); int x = e ? atoi(e) : 6; return x >= 0 ? x : 6; }();
+    return v;
+}
+
+// NDB_ARITH_TENSOR search: coarse quantizer and list scans on the tensor cores (bf16 products, fp32
+// accumulation) select k + margin candidates per query, which are then re-ranked in fp32.
+static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np, int k, float *dist_dev, int64_t *ids_dev,
+                             cudaStream_t s)
+{
+    NDB_REQUIRE(ix->metric == NDB_L2 || ix->metric == NDB_IP, NDB_B200_EINVAL, "ivf tensor path: metric %d not supported (L2, IP)", ix->metric);
+    NDB_REQUIRE(k <= TC_KMAX, NDB_B200_EINVAL, "ivf tensor path: k=%d > %d", k, TC_KMAX);
+    NDB_REQUIRE(ix->dim <= TC_MAX_CHUNKS * TC_KC, NDB_B200_EINVAL, "ivf tensor path: dim %d > %d", ix->dim, TC_MAX_CHUNKS * TC_KC);
+    NDB_CHECK(ivf_tensor_ready(ix, s));
+    const int L = ix->nlists;
+    const int64_t npairs = (int64_t) nq * np;
+    const int kc = std::min(TC_KMAX, k + ivf_tc_margin());
+
+    // 1. coarse quantizer: k = nprobe nearest centroids (always L2, ivfSelectClusters)
+    NDB_CHECK(ix->probe.reserve((size_t) npairs * 4));
+    NDB_CHECK(ix->cdist.reserve((size_t) npairs * 4));
+    if (np <= TC_KMAX) {
+        NDB_CHECK(tc_knn(ix->ctc, ix->ctcs, ix->dim, NDB_L2, Q_dev, nq, np, nullptr, ix->cdist.as<float>(), nullptr,
+                         ix->probe.as<uint32_t>(), nullptr, true, s));
+    } else {
+        NDB_CHECK(ivf_coarse(ix, Q_dev, nq, np, NDB_ARITH_FAST, s));
+    }
+
+    // 2. bucket (query, list) pairs by list; query positions padded to whole 128-query tiles per list
+    NDB_CHECK(ix->cnt.reserve((size_t) L * 4 * 2));
+    NDB_CHECK(ix->qoff.reserve((size_t) L * 4));
+    NDB_CHECK(ix->item_off.reserve((size_t) L * 4));
+    NDB_CHECK(ix->pairpos.reserve((size_t) npairs * 4));
+    NDB_CHECK(ix->nitems.reserve(64));
+    NDB_CHECK(ix->stats.reserve(64));
+    uint32_t *cnt = ix->cnt.as<uint32_t>(), *fill = cnt + L;
+    const uint32_t segb = ivf_tc_seg_tiles() * 8;
+    NDB_CUDA(cudaMemsetAsync(cnt, 0, (size_t) L * 4 * 2, s));
+    ivf_hist_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L, cnt);
+    ivf_offsets_kernel<<<1, 1024, 0, s>>>(cnt, ix->d_list_len.as<uint32_t>(), ix->d_list_order.as<uint32_t>(), L, TC_M, segb,
+                                          (uint32_t) TC_M, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
+                                          ix->nitems.as<uint32_t>(), ix->stats.as<unsigned long long>());
+    uint32_t *h_tot = reinterpret_cast<uint32_t *>(ctx().pinned);
+    NDB_CUDA(cudaMemcpyAsync(h_tot, ix->nitems.p, 8, cudaMemcpyDeviceToHost, s));
+    count_launch(2);
+    NDB_CUDA(cudaGetLastError());
+    NDB_CUDA(cudaStreamSynchronize(s));
+    const size_t n_items = h_tot[0], npos = h_tot[1];
+    if (getenv("NDB_IVF_DEBUG")) fprintf(stderr, "ivf tensor: %zu items, %zu query positions for %lld pairs\n", n_items, npos, (long long) npairs);
+    if (n_items == 0) {
+        // nothing to scan (all probed lists empty)
+        std::vector<float> hd((size_t) nq * k, INFINITY);
+        std::vector<int64_t> hi((size_t) nq * k, -1);
+        NDB_CUDA(cudaMemcpyAsync(dist_dev, hd.data(), hd.size() * 4, cudaMemcpyHostToDevice, s));
+        NDB_CUDA(cudaMemcpyAsync(ids_dev, hi.data(), hi.size() * 8, cudaMemcpyHostToDevice, s));
+        NDB_CUDA(cudaStreamSynchronize(s));
+        return NDB_B200_OK;
+    }
+    NDB_CHECK(ix->qmap.reserve(npos * 4));
+    NDB_CUDA(cudaMemsetAsync(ix->qmap.p, 0xFF, npos * 4, s));
+    ivf_scatter_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L,
+                                                                        ix->qoff.as<uint32_t>(), fill, ix->qmap.as<uint32_t>(),
+                                                                        ix->pairpos.as<uint32_t>());
+    NDB_CHECK(ix->tcs.items.reserve(n_items * sizeof(TcItem)));
+    ivf_tc_items_kernel<<<(unsigned) ((L + 3) / 4), 128, 0, s>>>(cnt, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
+                                                                ix->d_list_len.as<uint32_t>(), ix->d_ltile8.as<uint32_t>(), L, segb,
+                                                                ix->tcs.items.as<TcItem>());
+    count_launch(2);
+    NDB_CUDA(cudaGetLastError());
+
+    // 3. gather the query tiles (blocked bf16) and run the tensor kernel over the items
+    const int nkc = ix->tc.nkc;
+    NDB_CHECK(ix->tcs.qb.reserve(npos * nkc * TC_KC * 2));
+    NDB_CHECK(ix->tcs.qnorm.reserve(npos * 4));
+    NDB_CHECK(tc_block_queries(Q_dev, ix->qmap.as<uint32_t>(), (uint32_t) np, nq, (int) npos, ix->dim, nkc,
+                               ix->tcs.qb.as<__nv_bfloat16>(), ix->tcs.qnorm.as<float>(), s));
+    const size_t nparts = n_items * 2 * TC_M;
+    NDB_CHECK(ix->tcs.pdist.reserve(nparts * kc * 4));
+    NDB_CHECK(ix->tcs.pslot.reserve(nparts * kc * 4));
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.xb = ix->tc.xb.as<__nv_bfloat16>();
+    p.xnorm = ix->tc.xnorm.as<float>();
+    p.qb = ix->tcs.qb.as<__nv_bfloat16>();
+    p.qnorm = ix->tcs.qnorm.as<float>();
+    p.nkc = nkc;
+    p.k = kc;
+    p.items = ix->tcs.items.as<TcItem>();
+    p.nitems = (uint32_t) n_items;
+    p.pdist = ix->tcs.pdist.as<float>();
+    p.pslot = ix->tcs.pslot.as<uint32_t>();
+    NDB_CHECK(ix->tcs.gthr.reserve((size_t) nq * 4));
+    NDB_CUDA(cudaMemsetAsync(ix->tcs.gthr.p, 0x7f, (size_t) nq * 4, s));      // 3.4e38: "no bound yet"
+    p.qmap = ix->qmap.as<uint32_t>();
+    p.nprobe = (uint32_t) np;
+    p.gthr = getenv("NDB_IVF_TC_NOSHARE") ? nullptr : ix->tcs.gthr.as<float>();
+    p.packed = getenv("NDB_IVF_TC_UNPACKED") ? 0 : 1;
+    NDB_CHECK(tc_launch(p, ix->metric, kc, s));
+    if (ctx().timing) {                 // evals resolved from ix->stats in last_kernel_stats
+        Context &c = ctx();
+        c.last_bytes = -1.0;
+        c.last_evals = -1;
+        c.stats_src = ix->stats.p;
+        c.stats_dim = ix->dim;
+    }
+
+    // 4. merge + fp32 re-rank
+    const unsigned mgrid = (unsigned) ((nq + 3) / 4);
+#define NDB_FIN(M) ivf_tc_finish_kernel<Arith<M, NDB_ARITH_IVF_F32>><<<mgrid, 128, 0, s>>>(         ix->tcs.pdist.as<float>(), ix->tcs.pslot.as<uint32_t>(), ix->tc_src.as<uint32_t>(),         reinterpret_cast<const float4 *>(ix->store.ptr()), ix->ids.as<int64_t>(), Q_dev, ix->probe.as<uint32_t>(),         ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), nq, np, L, segb, ix->dim,         ix->dimp, kc, k, dist_dev, ids_dev)
+    if (ix->metric == NDB_L2) NDB_FIN(NDB_L2);
+    else NDB_FIN(NDB_IP);
+#undef NDB_FIN
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
 }
 
@@ -459,6 +720,7 @@ static int ivf_install_centroids(ndb_b200_ivf *ix, cudaStream_t s)
     NDB_CUDA(cudaMemsetAsync(ix->kw.cstore.p, 0, bytes, s));
     NDB_CHECK(il32_scatter(ix->kw.C.as<float>(), ix->nlists, ix->dim, ix->dimp, nullptr, 0, ix->kw.cstore.as<float>(), s));
     ix->trained = true;
+    ix->ctc_ok = false;
     return NDB_B200_OK;
 }
 
@@ -605,11 +867,16 @@ int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np
     NDB_CHECK(require_init());
     NDB_REQUIRE(ix && Q_dev && dist_dev && ids_dev && nq > 0 && nprobe > 0, NDB_B200_EINVAL, "ivf_search: bad argument");
     NDB_REQUIRE(k >= 1 && k <= 128, NDB_B200_EINVAL, "ivf_search: k=%d out of range 1..128", k);
-    NDB_REQUIRE(arith == NDB_ARITH_IVF_F32 || arith == NDB_ARITH_FAST, NDB_B200_EINVAL, "ivf_search: arith %d unsupported", arith);
+    NDB_REQUIRE(arith == NDB_ARITH_IVF_F32 || arith == NDB_ARITH_FAST || arith == NDB_ARITH_TENSOR, NDB_B200_EINVAL,
+                "ivf_search: arith %d unsupported", arith);
     cudaStream_t s = stream ? (cudaStream_t) stream : ctx().stream;
     NDB_CHECK(ivf_ready(ix, s));
     const int np = nprobe < ix->nlists ? nprobe : ix->nlists;
     NDB_REQUIRE(np <= 128, NDB_B200_EINVAL, "ivf: nprobe > 128 is not supported");
+    if (arith == NDB_ARITH_TENSOR) {
+        NDB_REQUIRE(mode != NDB_IVF_LITERAL, NDB_B200_EINVAL, "ivf_search: the literal mode has no tensor variant");
+        return ivf_search_tensor(ix, Q_dev, nq, np, k, dist_dev, ids_dev, s);
+    }
     const int L = ix->nlists;
     const int64_t npairs = (int64_t) nq * np;
 
@@ -649,7 +916,7 @@ int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np
     NDB_CUDA(cudaMemsetAsync(cnt, 0, (size_t) L * 4 * 2, s));
     ivf_hist_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L, cnt);
     const uint32_t segb = ivf_seg_blocks();
-    ivf_offsets_kernel<<<1, 1024, 0, s>>>(cnt, ix->d_list_len.as<uint32_t>(), ix->d_list_order.as<uint32_t>(), L, qt, segb,
+    ivf_offsets_kernel<<<1, 1024, 0, s>>>(cnt, ix->d_list_len.as<uint32_t>(), ix->d_list_order.as<uint32_t>(), L, qt, segb, 1u,
                                           ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->nitems.as<uint32_t>(),
                                           ix->stats.as<unsigned long long>());
     // the number of work items depends on how the batch's probes fall on long and short lists:

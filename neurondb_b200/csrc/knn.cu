@@ -207,7 +207,7 @@ int ndb_b200_knn_exact_dev(ndb_b200_dataset *ds, int metric, int arith, const fl
     if (arith == NDB_ARITH_TENSOR) {
         // bf16 tcgen05 GEMM-form path (tolerance 1e-3): ||x||^2 - 2 x.q + ||q||^2 with fused top-k
         if (ds->tc.valid_for != ds->n) NDB_CHECK(tc_build_store(ds->tc, ds->store.ptr(), ds->n, ds->dim, ds->dimp, s));
-        return tc_knn(ds->tc, ds->tcs, ds->dim, metric, Q_dev, nq, k, ds->ids.as<int64_t>(), dist_dev, ids_dev, nullptr, s);
+        return tc_knn(ds->tc, ds->tcs, ds->dim, metric, Q_dev, nq, k, ds->ids.as<int64_t>(), dist_dev, ids_dev, nullptr, nullptr, false, s);
     }
     const void *vnorm = nullptr;
     if (metric == NDB_COSINE) NDB_CHECK(dataset_norms(ds, arith, &vnorm, s));

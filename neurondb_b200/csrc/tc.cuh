@@ -1,8 +1,16 @@
 // tc.cuh -- host-side handles of the tensor-core (tcgen05) distance path (tc_knn.cu).
 #pragma once
 #include "layout.cuh"
+#include <cuda_bf16.h>
 
 namespace ndb {
+
+constexpr int TC_M = 128;          // queries per tile  (TMEM lanes)
+constexpr int TC_N = 256;          // stored rows per tile (TMEM columns per accumulator)
+constexpr int TC_KC = 128;         // dims per K-chunk (one smem stage)
+constexpr int TC_MAX_CHUNKS = 2;   // dim <= 256 in this round
+constexpr int TC_KMAX = 16;        // k <= 16 (thread-local register list)
+constexpr int TC_PACKED_MAX_TILES = 16;   // packed-key epilogue: 11 index bits = 16 tiles x 128 columns per half
 
 // stored rows in the blocked bf16 layout + squared norms of the rounded rows
 struct TcStore {
@@ -20,14 +28,37 @@ struct TcItem {
 };
 
 struct TcScratch {
-    DevBuf qb, qnorm, pdist, pslot, debug, items;
+    DevBuf qb, qnorm, pdist, pslot, debug, items, gthr;
 };
 
-struct TcParams;
+struct TcParams {
+    const __nv_bfloat16 *xb;       // blocked stored rows
+    const float *xnorm;            // [ntiles * 256]
+    const __nv_bfloat16 *qb;       // blocked query tiles
+    const float *qnorm;            // [query tiles * 128]
+    int nkc;                       // K-chunks (dimp / 128)
+    int k;
+    const TcItem *items;           // work items
+    uint32_t nitems;
+    float *pdist;                  // partial results, indexed through TcItem::out_base / out_stride
+    uint32_t *pslot;
+    const uint32_t *qmap;          // optional (list mode): tile position -> (query * nprobe + rank), INVALID_SLOT = empty
+    uint32_t nprobe;
+    float *gthr;                   // optional (list mode): per query, an upper bound of its k-th best candidate, shared
+                                   // between the items of the query (atomic min; initialised to a huge finite value)
+    int packed;                    // 1: items span <= TC_PACKED_MAX_TILES tiles; (distance | index) keys, sorting-network epilogue
+    float *debug_d;                // optional: raw accumulator of the first tile [128][256]
+    int debug_mode;                // NDB_TC_DEBUG: 1 = no epilogue math, 2 = no MMA issue, 4 = no X bulk copies (bisection aid)
+};
+
 int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s);
+int tc_build_store_mapped(TcStore &st, const float *il32_store, const uint32_t *src_slot_dev, int64_t n, int dim, int dimp,
+                          cudaStream_t s);
+int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t nprobe, int nq, int nqpad, int dim, int nkc,
+                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s);
 
 int tc_build_store(TcStore &st, const float *il32_store, int64_t n, int dim, int dimp, cudaStream_t s);
 int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q_dev, int nq, int k, const int64_t *ids,
-           float *dist_dev, int64_t *ids_dev, float *debug_d_dev, cudaStream_t s);
+           float *dist_dev, int64_t *ids_dev, uint32_t *slots_dev, float *debug_d_dev, bool packed, cudaStream_t s);
 
 }  // namespace ndb

@@ -33,23 +33,21 @@
 
 #include <cuda_bf16.h>
 #include <algorithm>
+#include <cfloat>
 
 namespace ndb {
 
-constexpr int TC_M = 128;          // queries per tile  (TMEM lanes)
-constexpr int TC_N = 256;          // stored rows per tile (TMEM columns per accumulator)
-constexpr int TC_KC = 128;         // dims per K-chunk (one smem stage)
 constexpr int TC_STAGES = 2;
 constexpr int TC_XSTAGE_BYTES = TC_N * TC_KC * 2;      // 64 KB
 constexpr int TC_QCHUNK_BYTES = TC_M * TC_KC * 2;      // 32 KB
-constexpr int TC_MAX_CHUNKS = 2;                       // dim <= 256 in this round
 constexpr int TC_NORM_RING = 8;
-constexpr int TC_KMAX = 16;                            // k <= 16 (thread-local register list)
 
 // ---- layout conversion -------------------------------------------------------------------
 // IL32 fp32 store -> blocked bf16 + per-row squared norm of the rounded values (fp32)
-__global__ void tc_block_rows_kernel(const float4 *__restrict__ store, int64_t n, int64_t npad, int dim, int dimp,
-                                     int nkc, __nv_bfloat16 *__restrict__ xb, float *__restrict__ xnorm)
+// src_slot (optional): tensor row r is IL32 slot src_slot[r] (INVALID_SLOT = pad row); identity if null
+__global__ void tc_block_rows_kernel(const float4 *__restrict__ store, const uint32_t *__restrict__ src_slot, int64_t n,
+                                     int64_t npad, int dim, int dimp, int nkc, __nv_bfloat16 *__restrict__ xb,
+                                     float *__restrict__ xnorm)
 {
     const int groups = nkc * (TC_KC / 8);                      // 8-element groups per row (padded dims)
     const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,12 +57,13 @@ __global__ void tc_block_rows_kernel(const float4 *__restrict__ store, int64_t n
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = 0.0f;
-    if (row < n) {
+    const int64_t srow = src_slot ? (row < npad && src_slot[row] != INVALID_SLOT ? (int64_t) src_slot[row] : -1) : (row < n ? row : -1);
+    if (srow >= 0) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int c = 2 * g + h;                           // float4 chunk of the row
             if (4 * c < dimp) {
-                const float4 x = store[(size_t) (row >> 5) * (8 * (size_t) dimp) + (size_t) c * 32 + (row & 31)];
+                const float4 x = store[(size_t) (srow >> 5) * (8 * (size_t) dimp) + (size_t) c * 32 + (srow & 31)];
                 v[4 * h + 0] = 4 * c + 0 < dim ? x.x : 0.0f;
                 v[4 * h + 1] = 4 * c + 1 < dim ? x.y : 0.0f;
                 v[4 * h + 2] = 4 * c + 2 < dim ? x.z : 0.0f;
@@ -84,14 +83,15 @@ __global__ void tc_block_rows_kernel(const float4 *__restrict__ store, int64_t n
 }
 
 // one thread per row: squared norm of the bf16-rounded row; +inf for pad rows so they never rank
-__global__ void tc_row_norms_kernel(const float4 *__restrict__ store, int64_t n, int64_t npad, int dim, int dimp,
-                                    float *__restrict__ xnorm)
+__global__ void tc_row_norms_kernel(const float4 *__restrict__ store, const uint32_t *__restrict__ src_slot, int64_t n,
+                                    int64_t npad, int dim, int dimp, float *__restrict__ xnorm)
 {
     const int64_t row = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= npad) return;
-    if (row >= n) { xnorm[row] = INFINITY; return; }
+    const int64_t srow = src_slot ? (src_slot[row] != INVALID_SLOT ? (int64_t) src_slot[row] : -1) : (row < n ? row : -1);
+    if (srow < 0) { xnorm[row] = INFINITY; return; }
     float acc = 0.0f;
-    const float4 *vp = store + (size_t) (row >> 5) * (8 * (size_t) dimp) + (row & 31);
+    const float4 *vp = store + (size_t) (srow >> 5) * (8 * (size_t) dimp) + (srow & 31);
     for (int c = 0; 4 * c < dimp; c++) {
         const float4 x = vp[(size_t) c * 32];
         const float a = __bfloat162float(__float2bfloat16_rn(4 * c + 0 < dim ? x.x : 0.0f));
@@ -104,20 +104,23 @@ __global__ void tc_row_norms_kernel(const float4 *__restrict__ store, int64_t n,
 }
 
 // row-major fp32 queries -> blocked bf16 query tiles + squared norms
-__global__ void tc_block_queries_kernel(const float *__restrict__ Q, int nq, int nqpad, int dim, int nkc,
-                                        __nv_bfloat16 *__restrict__ qb, float *__restrict__ qnorm)
+// qmap (optional): tile position q holds query qmap[q] / nprobe (INVALID_SLOT = empty position)
+__global__ void tc_block_queries_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap, uint32_t nprobe,
+                                        int nq, int nqpad, int dim, int nkc, __nv_bfloat16 *__restrict__ qb,
+                                        float *__restrict__ qnorm)
 {
     const int groups = nkc * (TC_KC / 8);
     const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t) nqpad * groups) return;
     const int q = (int) (t / groups);
     const int g = (int) (t - (int64_t) q * groups);
+    const int64_t src = qmap ? (qmap[q] != INVALID_SLOT ? (int64_t) (qmap[q] / nprobe) : -1) : (q < nq ? q : -1);
     __nv_bfloat16 o[8];
     float part = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int d = g * 8 + i;
-        const float v = (q < nq && d < dim) ? Q[(size_t) q * dim + d] : 0.0f;
+        const float v = (src >= 0 && d < dim) ? Q[(size_t) src * dim + d] : 0.0f;
         o[i] = __float2bfloat16_rn(v);
         const float r = __bfloat162float(o[i]);
         part = fmaf(r, r, part);
@@ -131,14 +134,16 @@ __global__ void tc_block_queries_kernel(const float *__restrict__ Q, int nq, int
 }
 
 // squared norm of the bf16-rounded query, one thread per query (fixed order: deterministic)
-__global__ void tc_query_norms_kernel(const float *__restrict__ Q, int nq, int nqpad, int dim, float *__restrict__ qnorm)
+__global__ void tc_query_norms_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap, uint32_t nprobe, int nq,
+                                      int nqpad, int dim, float *__restrict__ qnorm)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nqpad) return;
+    const int64_t src = qmap ? (qmap[q] != INVALID_SLOT ? (int64_t) (qmap[q] / nprobe) : -1) : (q < nq ? q : -1);
     float acc = 0.0f;
-    if (q < nq)
+    if (src >= 0)
         for (int d = 0; d < dim; d++) {
-            const float r = __bfloat162float(__float2bfloat16_rn(Q[(size_t) q * dim + d]));
+            const float r = __bfloat162float(__float2bfloat16_rn(Q[(size_t) src * dim + d]));
             acc = fmaf(r, r, acc);
         }
     qnorm[q] = acc;
@@ -201,21 +206,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (m >> 4) << 24);
 }
 
-struct TcParams {
-    const __nv_bfloat16 *xb;       // blocked stored rows
-    const float *xnorm;            // [ntiles * 256]
-    const __nv_bfloat16 *qb;       // blocked query tiles
-    const float *qnorm;            // [query tiles * 128]
-    int nkc;                       // K-chunks (dimp / 128)
-    int k;
-    const TcItem *items;           // work items
-    uint32_t nitems;
-    float *pdist;                  // partial results, indexed through TcItem::out_base / out_stride
-    uint32_t *pslot;
-    float *debug_d;                // optional: raw accumulator of the first tile [128][256]
-    int debug_mode;                // NDB_TC_DEBUG: 1 = no epilogue math, 2 = no MMA issue, 4 = no X bulk copies (bisection aid)
-};
-
 // thread-local sorted top-KT list in registers: branch-free insertion of (d, id).
 //   L'[j] = L[j]            if L[j] precedes the new pair
 //         = new             if L[j-1] precedes it (or j == 0) but L[j] does not
@@ -270,7 +260,76 @@ __device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity)
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-template <int KT, int METRIC>
+// ---- packed keys (short items: IVF lists, coarse quantizer) --------------------------------------
+// Where an item holds only a few hundred candidates per query, most of the epilogue's time would go
+// into list insertions (a thread's k-th best tightens slowly, and a warp pays for its slowest
+// lane).  For such items the candidate distance and its index within the item are packed into ONE
+// float: the low TC_IDX_BITS mantissa bits carry the index, so that a compare-exchange is two
+// FMNMX and whole groups of 16 candidates can go through a sorting network instead of being
+// inserted one by one.  The 12 remaining mantissa bits (2.4e-4) are finer than the bf16 products
+// that produced the value.
+constexpr int TC_IDX_BITS = 11;                                  // 16 tiles x 128 columns per half
+constexpr uint32_t TC_IDX_MASK = (1u << TC_IDX_BITS) - 1;
+static_assert(TC_PACKED_MAX_TILES == 1 << (TC_IDX_BITS - 7), "index bits");
+constexpr float TC_KEY_BIG = 1.7e38f;                            // keys at or above: pad rows / empty slots
+constexpr int TC_HEAVY = 6;                                      // passes per 32 columns above which the warp sorts
+
+template <int N> __device__ __forceinline__ void oem_sort(float (&a)[N])     // Batcher odd-even merge sort, ascending
+{
+#pragma unroll
+    for (int p = 1; p < N; p <<= 1)
+#pragma unroll
+        for (int k = p; k >= 1; k >>= 1)
+#pragma unroll
+            for (int j = k % p; j <= N - 1 - k; j += 2 * k)
+#pragma unroll
+                for (int i = 0; i <= (k - 1 < N - j - k - 1 ? k - 1 : N - j - k - 1); i++)
+                    if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+                        const float lo = fminf(a[i + j], a[i + j + k]), hi = fmaxf(a[i + j], a[i + j + k]);
+                        a[i + j] = lo;
+                        a[i + j + k] = hi;
+                    }
+}
+template <int N> __device__ __forceinline__ void bitonic_merge(float (&m)[N])   // bitonic -> ascending
+{
+#pragma unroll
+    for (int s = N / 2; s >= 1; s >>= 1)
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            if (!(i & s)) {
+                const float lo = fminf(m[i], m[i + s]), hi = fmaxf(m[i], m[i + s]);
+                m[i] = lo;
+                m[i + s] = hi;
+            }
+}
+__device__ __forceinline__ float tc_pack(float c, uint32_t idx)
+{
+    return __uint_as_float((__float_as_uint(fminf(c, TC_KEY_BIG)) & ~TC_IDX_MASK) | idx);
+}
+// L (ascending, 16) <- the 16 smallest of L and the 16 keys g
+__device__ __forceinline__ void tc_sort_merge16(float (&L)[16], float (&g)[16])
+{
+    oem_sort<16>(g);
+#pragma unroll
+    for (int i = 0; i < 16; i++) L[i] = fminf(L[i], g[15 - i]);
+    bitonic_merge<16>(L);
+}
+// branch-free insertion of key x into the ascending list L[0..KT)
+template <int KT> __device__ __forceinline__ void tc_key_insert(float (&L)[16], float x)
+{
+#pragma unroll
+    for (int j = KT - 1; j >= 1; j--) L[j] = fmaxf(L[j - 1], fminf(L[j], x));
+    L[0] = fminf(L[0], x);
+}
+
+// float atomic min for values of either sign (the cell starts at a positive value)
+__device__ __forceinline__ void atomic_min_f32(float *a, float v)
+{
+    if (v >= 0.0f) atomicMin(reinterpret_cast<int *>(a), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned *>(a), __float_as_uint(v));
+}
+
+template <int KT, int METRIC, bool PACKED>
 __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
 {
     extern __shared__ __align__(1024) unsigned char tsm[];
@@ -376,13 +435,35 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
             const TcItem it = p.items[item];
             const uint32_t t0 = it.t0, t1 = it.t1;
             const float qn = p.qnorm[(size_t) it.qtile * TC_M + ql];
-            float bd[KT];
-            uint32_t bi[KT];
+            const bool live = (uint32_t) ql < it.nq;
+            float bd[PACKED ? 16 : KT];                                 // PACKED: keys (distance | index), ascending
+            uint32_t bi[PACKED ? 1 : KT];
 #pragma unroll
-            for (int j = 0; j < KT; j++) { bd[j] = INFINITY; bi[j] = INVALID_SLOT; }
-            float thr = INFINITY;                                       // KT-th best, in "candidate" units
+            for (int j = 0; j < (PACKED ? 16 : KT); j++) bd[j] = PACKED ? FLT_MAX : INFINITY;
+#pragma unroll
+            for (int j = 0; j < (PACKED ? 1 : KT); j++) bi[j] = INVALID_SLOT;
+            // list mode: the items of one query (its probed lists, their segments, the two column
+            // halves) share an upper bound of the query's KT-th best candidate.  Whatever order the
+            // items run in, the bound only ever filters candidates that cannot be in the merged
+            // top-KT, so the merged result does not depend on the schedule.  Lanes without a query
+            // (ql >= nq) never take a candidate.
+            float *gcell = nullptr;
+            float gcap = live ? INFINITY : -INFINITY, published = INFINITY;
+            if (p.gthr && live) {
+                const uint32_t pr = p.qmap[(size_t) it.qtile * TC_M + ql];
+                if (pr != INVALID_SLOT) gcell = p.gthr + pr / p.nprobe;
+            }
+            float thr = gcap;                                           // KT-th best so far, in "candidate" units
+            // candidate units: L2 -> ||x||^2 - 2 x.q (PACKED: + ||q||^2, i.e. the squared distance);
+            // IP -> -x.q.  Pad rows carry +inf norms and never rank.
+            const float cadd = (PACKED && METRIC == NDB_L2) ? qn : 0.0f;
             for (uint32_t t = t0; t < t1; t++, tile_it++) {
                 const uint32_t a = tile_it & 1u;
+                if (gcell) {
+                    // strictly above the shared bound: ties with the bound itself must survive
+                    gcap = fminf(gcap, nextafterf(*reinterpret_cast<volatile float *>(gcell), INFINITY));
+                    thr = fminf(thr, gcap);
+                }
                 mbar_spin(&acc_full[a], (tile_it >> 1) & 1u);
                 tc_fence_after();
                 const float *xn = n_smem + (size_t) (tile_it % TC_NORM_RING) * TC_N;
@@ -396,18 +477,17 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
 #pragma unroll
                         for (int i = 0; i < 32; i++) p.debug_d[(size_t) ql * TC_N + col0 + i] = __uint_as_float(v[i]);
                     }
-                    // candidates: L2 -> ||x||^2 - 2 x.q (||q||^2 is added on output); IP -> -x.q; pad rows
-                    // carry +inf norms and never rank.  32 independent FFMAs, then one min tree: the
-                    // common case (nothing beats the threshold) is branch-free.
+                    // 32 independent FFMAs, then one min tree: the common case (nothing beats the
+                    // threshold) is branch-free.
                     float c[32];
 #pragma unroll
                     for (int i4 = 0; i4 < 8; i4++) {
                         const float4 n4 = *reinterpret_cast<const float4 *>(xn + col0 + 4 * i4);
                         if (METRIC == NDB_L2) {
-                            c[4 * i4 + 0] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 0]), n4.x);
-                            c[4 * i4 + 1] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 1]), n4.y);
-                            c[4 * i4 + 2] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 2]), n4.z);
-                            c[4 * i4 + 3] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 3]), n4.w);
+                            c[4 * i4 + 0] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 0]), n4.x + cadd);
+                            c[4 * i4 + 1] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 1]), n4.y + cadd);
+                            c[4 * i4 + 2] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 2]), n4.z + cadd);
+                            c[4 * i4 + 3] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 3]), n4.w + cadd);
                         } else {
                             c[4 * i4 + 0] = n4.x == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 0]);
                             c[4 * i4 + 1] = n4.y == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 1]);
@@ -422,33 +502,85 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     for (int w = 8; w > 0; w >>= 1)
 #pragma unroll
                         for (int i = 0; i < w; i++) m[i] = fminf(m[i], m[i + w]);
-                    if (m[0] < thr) {
+                    if constexpr (PACKED) {
                         uint32_t mask = 0;
+                        if (m[0] < thr) {
 #pragma unroll
-                        for (int i = 0; i < 32; i++) mask |= (c[i] < thr ? 1u : 0u) << i;
-                        while (mask) {
-                            const int i = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            const float cand = pick32(c, i);
-                            if (cand < thr) {
-                                tk_insert<KT>(bd, bi, cand, t * TC_N + col0 + i);
-                                thr = bd[KT - 1];
+                            for (int i = 0; i < 32; i++) mask |= (c[i] < thr ? 1u : 0u) << i;
+                        }
+                        const uint32_t ibase = (t - t0) * (TC_N / 2) + j * 32;
+                        if (__any_sync(FULL, __popc(mask) > TC_HEAVY)) {
+                            // some lane has many takers (its list is still filling): every lane sorts
+                            // its 32 keys through the network -- a fixed cost, no lane-by-lane tail
+                            if (!live) {
+#pragma unroll
+                                for (int i = 0; i < 32; i++) c[i] = INFINITY;
+                            }
+                            float g[16];
+#pragma unroll
+                            for (int i = 0; i < 16; i++) g[i] = tc_pack(c[i], ibase + i);
+                            tc_sort_merge16(bd, g);
+#pragma unroll
+                            for (int i = 0; i < 16; i++) g[i] = tc_pack(c[16 + i], ibase + 16 + i);
+                            tc_sort_merge16(bd, g);
+                            thr = fminf(bd[KT - 1], gcap);
+                        } else {
+                            while (mask) {
+                                const int i = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const float cand = pick32(c, i);
+                                if (cand < thr) {
+                                    tc_key_insert<KT>(bd, tc_pack(cand, ibase + i));
+                                    thr = fminf(bd[KT - 1], gcap);
+                                }
+                            }
+                        }
+                    } else {
+                        if (m[0] < thr) {
+                            uint32_t mask = 0;
+#pragma unroll
+                            for (int i = 0; i < 32; i++) mask |= (c[i] < thr ? 1u : 0u) << i;
+                            while (mask) {
+                                const int i = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const float cand = pick32(c, i);
+                                if (cand < thr) {
+                                    tk_insert<KT>(bd, bi, cand, t * TC_N + col0 + i);
+                                    thr = fminf(bd[KT - 1], gcap);
+                                }
                             }
                         }
                     }
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[a]);                             // 256 arrivals release the accumulator
+                if (gcell && bd[KT - 1] < published) {                  // own list full and improved
+                    published = bd[KT - 1];
+                    float pub = published;
+                    if (PACKED)     // an upper bound of the value the key stands for
+                        pub = __uint_as_float(pub >= 0.0f ? (__float_as_uint(pub) | TC_IDX_MASK) : (__float_as_uint(pub) & ~TC_IDX_MASK));
+                    if (!PACKED || pub < TC_KEY_BIG) atomic_min_f32(gcell, pub);
+                }
             }
-            if ((uint32_t) ql < it.nq) {
+            if (live) {
                 const size_t base = ((size_t) it.out_base + (size_t) ql * it.out_stride + half) * p.k;
 #pragma unroll
                 for (int j = 0; j < KT; j++) {
                     if (j < p.k) {
                         float d = bd[j];
-                        if (METRIC == NDB_L2 && bi[j] != INVALID_SLOT) d = sqrtf(fmaxf(d + qn, 0.0f));
+                        uint32_t slot;
+                        if (PACKED) {
+                            const uint32_t bits = __float_as_uint(d), idx = bits & TC_IDX_MASK;
+                            const bool have = d < TC_KEY_BIG;
+                            slot = have ? (t0 + (idx >> 7)) * TC_N + half * (TC_N / 2) + (idx & 127u) : INVALID_SLOT;
+                            d = have ? __uint_as_float(bits & ~TC_IDX_MASK) : INFINITY;
+                            if (METRIC == NDB_L2 && have) d = sqrtf(fmaxf(d, 0.0f));
+                        } else {
+                            slot = bi[j];
+                            if (METRIC == NDB_L2 && slot != INVALID_SLOT) d = sqrtf(fmaxf(d + qn, 0.0f));
+                        }
                         p.pdist[base + j] = d;
-                        p.pslot[base + j] = bi[j];
+                        p.pslot[base + j] = slot;
                     }
                 }
             }
@@ -464,21 +596,41 @@ static size_t tc_smem_bytes() { return (size_t) TC_MAX_CHUNKS * TC_QCHUNK_BYTES 
 
 int tc_build_store(TcStore &st, const float *il32_store, int64_t n, int dim, int dimp, cudaStream_t s)
 {
+    return tc_build_store_mapped(st, il32_store, nullptr, n, dim, dimp, s);
+}
+
+// src_slot_dev (optional, length n rounded up to 256): tensor row -> IL32 slot, INVALID_SLOT = pad
+int tc_build_store_mapped(TcStore &st, const float *il32_store, const uint32_t *src_slot_dev, int64_t n, int dim, int dimp,
+                          cudaStream_t s)
+{
     NDB_REQUIRE(dim <= TC_MAX_CHUNKS * TC_KC, NDB_B200_EINVAL, "tensor path: dim %d > %d is not supported yet", dim, TC_MAX_CHUNKS * TC_KC);
     const int nkc = (dim + TC_KC - 1) / TC_KC;
     const int64_t ntiles = (n + TC_N - 1) / TC_N, npad = ntiles * TC_N;
     NDB_CHECK(st.xb.reserve((size_t) npad * nkc * TC_KC * 2));
     NDB_CHECK(st.xnorm.reserve((size_t) npad * 4));
     const int groups = nkc * (TC_KC / 8);
-    tc_block_rows_kernel<<<(unsigned) ((npad * groups + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(il32_store), n, npad, dim,
+    tc_block_rows_kernel<<<(unsigned) ((npad * groups + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(il32_store), src_slot_dev, n, npad, dim,
                                                                                  dimp, nkc, st.xb.as<__nv_bfloat16>(), st.xnorm.as<float>());
-    tc_row_norms_kernel<<<(unsigned) ((npad + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(il32_store), n, npad, dim, dimp,
+    tc_row_norms_kernel<<<(unsigned) ((npad + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(il32_store), src_slot_dev, n, npad, dim, dimp,
                                                                         st.xnorm.as<float>());
     count_launch(2);
     NDB_CUDA(cudaGetLastError());
     st.valid_for = n;
     st.ntiles = ntiles;
     st.nkc = nkc;
+    return NDB_B200_OK;
+}
+
+// blocked bf16 query tiles + squared norms; qmap_dev (optional) gathers the tile positions
+int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t nprobe, int nq, int nqpad, int dim, int nkc,
+                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s)
+{
+    const int groups = nkc * (TC_KC / 8);
+    tc_block_queries_kernel<<<(unsigned) (((int64_t) nqpad * groups + 255) / 256), 256, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, dim,
+                                                                                                nkc, qb, qnorm);
+    tc_query_norms_kernel<<<(unsigned) ((nqpad + 127) / 128), 128, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, dim, qnorm);
+    count_launch(2);
+    NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
 }
 
@@ -494,24 +646,30 @@ int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s)
     Context &c = ctx();
     if (c.timing) NDB_CUDA(cudaEventRecord(c.ev0, s));
     // list length: the smallest of {1, 10, 16} that holds k (a shorter list = a tighter threshold)
-#define NDB_TC_LAUNCH(KT, M)                                                                                  \
+#define NDB_TC_LAUNCH(KT, M, PK)                                                                              \
     do {                                                                                                      \
         static bool cfg = false;                                                                              \
         if (!cfg) {                                                                                           \
-            NDB_CUDA(cudaFuncSetAttribute(tc_knn_kernel<KT, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+            NDB_CUDA(cudaFuncSetAttribute(tc_knn_kernel<KT, M, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
             cfg = true;                                                                                       \
         }                                                                                                     \
-        tc_knn_kernel<KT, M><<<grid, 384, smem, s>>>(p);                                                      \
+        tc_knn_kernel<KT, M, PK><<<grid, 384, smem, s>>>(p);                                                  \
     } while (0)
+#define NDB_TC_PICK(M, PK)                                                                                    \
+    do {                                                                                                      \
+        if (k == 1) NDB_TC_LAUNCH(1, M, PK);                                                                  \
+        else if (k <= 10) NDB_TC_LAUNCH(10, M, PK);                                                           \
+        else NDB_TC_LAUNCH(TC_KMAX, M, PK);                                                                   \
+    } while (0)
+    // packed: every item spans at most TC_PACKED_MAX_TILES tiles (the caller's contract)
     if (metric == NDB_L2) {
-        if (k == 1) NDB_TC_LAUNCH(1, NDB_L2);
-        else if (k <= 10) NDB_TC_LAUNCH(10, NDB_L2);
-        else NDB_TC_LAUNCH(TC_KMAX, NDB_L2);
+        if (p.packed) NDB_TC_PICK(NDB_L2, true);
+        else NDB_TC_PICK(NDB_L2, false);
     } else {
-        if (k == 1) NDB_TC_LAUNCH(1, NDB_IP);
-        else if (k <= 10) NDB_TC_LAUNCH(10, NDB_IP);
-        else NDB_TC_LAUNCH(TC_KMAX, NDB_IP);
+        if (p.packed) NDB_TC_PICK(NDB_IP, true);
+        else NDB_TC_PICK(NDB_IP, false);
     }
+#undef NDB_TC_PICK
 #undef NDB_TC_LAUNCH
     count_launch();
     NDB_CUDA(cudaGetLastError());
@@ -527,7 +685,7 @@ int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s)
 
 // top-k of nq row-major fp32 queries against a TcStore; writes (dist, id) like the scan path
 int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q_dev, int nq, int k, const int64_t *ids,
-           float *dist_dev, int64_t *ids_dev, float *debug_d_dev, cudaStream_t s)
+           float *dist_dev, int64_t *ids_dev, uint32_t *slots_dev, float *debug_d_dev, bool packed, cudaStream_t s)
 {
     NDB_REQUIRE(k >= 1 && k <= TC_KMAX, NDB_B200_EINVAL, "tensor path: k must be 1..%d", TC_KMAX);
     NDB_REQUIRE(metric == NDB_L2 || metric == NDB_IP, NDB_B200_EINVAL, "tensor path: metric %d not supported (L2, IP)", metric);
@@ -537,17 +695,14 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     const int nqpad = (int) nqt * TC_M;
     NDB_CHECK(sc.qb.reserve((size_t) nqpad * nkc * TC_KC * 2));
     NDB_CHECK(sc.qnorm.reserve((size_t) nqpad * 4));
-    const int groups = nkc * (TC_KC / 8);
-    tc_block_queries_kernel<<<(unsigned) (((int64_t) nqpad * groups + 255) / 256), 256, 0, s>>>(Q_dev, nq, nqpad, dim, nkc,
-                                                                                                sc.qb.as<__nv_bfloat16>(), sc.qnorm.as<float>());
-    tc_query_norms_kernel<<<(unsigned) ((nqpad + 127) / 128), 128, 0, s>>>(Q_dev, nq, nqpad, dim, sc.qnorm.as<float>());
-    count_launch(2);
+    NDB_CHECK(tc_block_queries(Q_dev, nullptr, 0, nq, nqpad, dim, nkc, sc.qb.as<__nv_bfloat16>(), sc.qnorm.as<float>(), s));
     // split the stored tiles into ranges so that there are ~2 work items per SM
     const uint32_t sms = (uint32_t) ctx().sm_count;
     uint32_t nranges = (2 * sms + nqt - 1) / nqt;
     if (nranges < 1) nranges = 1;
     if (nranges > (uint32_t) st.ntiles) nranges = (uint32_t) st.ntiles;
-    const uint32_t tpr = (uint32_t) ((st.ntiles + nranges - 1) / nranges);
+    uint32_t tpr = (uint32_t) ((st.ntiles + nranges - 1) / nranges);
+    if (packed && tpr > (uint32_t) TC_PACKED_MAX_TILES) tpr = TC_PACKED_MAX_TILES;
     nranges = (uint32_t) ((st.ntiles + tpr - 1) / tpr);
     NDB_CHECK(sc.pdist.reserve((size_t) nq * nranges * 2 * k * 4));
     NDB_CHECK(sc.pslot.reserve((size_t) nq * nranges * 2 * k * 4));
@@ -569,6 +724,7 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     NDB_CUDA(cudaMemcpyAsync(sc.items.p, items.data(), (size_t) nitems * sizeof(TcItem), cudaMemcpyHostToDevice, s));
     NDB_CUDA(cudaStreamSynchronize(s));        // `items` is a host temporary
     TcParams p;
+    memset(&p, 0, sizeof(p));
     p.xb = st.xb.as<__nv_bfloat16>();
     p.xnorm = st.xnorm.as<float>();
     p.qb = sc.qb.as<__nv_bfloat16>();
@@ -578,6 +734,7 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     p.nitems = nitems;
     p.pdist = sc.pdist.as<float>();
     p.pslot = sc.pslot.as<uint32_t>();
+    p.packed = packed ? 1 : 0;
     p.debug_d = debug_d_dev;
     p.debug_mode = getenv("NDB_TC_DEBUG") ? atoi(getenv("NDB_TC_DEBUG")) : 0;
     const size_t smem = tc_smem_bytes();
@@ -586,7 +743,7 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
         ctx().last_bytes = (double) st.ntiles * TC_N * nkc * TC_KC * 2.0;          // stored bf16 bytes, read once per launch
         ctx().last_evals = (int64_t) st.valid_for * nq;
     }
-    return launch_merge_parts(sc.pdist.as<float>(), sc.pslot.as<uint32_t>(), ids, nq, (int) nranges * 2, k, dist_dev, ids_dev, nullptr, s);
+    return launch_merge_parts(sc.pdist.as<float>(), sc.pslot.as<uint32_t>(), ids, nq, (int) nranges * 2, k, dist_dev, ids_dev, slots_dev, s);
 }
 
 }  // namespace ndb
@@ -613,7 +770,7 @@ extern "C" int ndbdbg_tc_gemm(const float *Q, int nq, const float *X, int n, int
     NDB_CUDA(cudaMemsetAsync(dd.p, 0, (size_t) TC_M * TC_N * 4, s));
     NDB_CHECK(il32_scatter(dx.as<float>(), n, dim, dimp, nullptr, 0, store.as<float>(), s));
     NDB_CHECK(tc_build_store(st, store.as<float>(), n, dim, dimp, s));
-    NDB_CHECK(tc_knn(st, sc, dim, NDB_L2, dq.as<float>(), nq, 1, nullptr, od.as<float>(), oi.as<int64_t>(), dd.as<float>(), s));
+    NDB_CHECK(tc_knn(st, sc, dim, NDB_L2, dq.as<float>(), nq, 1, nullptr, od.as<float>(), oi.as<int64_t>(), nullptr, dd.as<float>(), false, s));
     NDB_CUDA(cudaMemcpyAsync(D, dd.p, (size_t) TC_M * TC_N * 4, cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaStreamSynchronize(s));
     return NDB_B200_OK;

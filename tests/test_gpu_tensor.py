@@ -55,3 +55,52 @@ def test_tensor_knn_within_tolerance(ndb, orc, n, dim, nq, k, metric):
     for q, j in zip(*np.nonzero(~same)):
         assert abs(od[q, j] - d[q, j]) <= 1e-3 * max(abs(od[q, j]), 1e-3)
     assert np.all(np.diff(d, axis=1) >= 0)
+
+
+@pytest.mark.parametrize("n,dim,lists,nq,nprobe,k,metric", [
+    (20000, 128, 64, 700, 8, 10, 1),      # several query tiles per list
+    (5000, 96, 40, 33, 16, 10, 3),        # ragged dims, IP
+    (3000, 128, 100, 200, 100, 5, 1),     # nprobe > 16: fp32 coarse stage, all lists probed
+    (150000, 64, 16, 300, 4, 16, 1),      # long lists -> several segments per list
+    (400, 256, 8, 5, 3, 10, 1),           # two K-chunks, tiny lists
+])
+def test_tensor_ivf_matches_fp32_path(ndb, orc, n, dim, lists, nq, nprobe, k, metric):
+    """arith=TENSOR selects candidates with bf16 products and re-ranks them in fp32: the returned
+    distances are bit-identical to the fp32 path's for the same ids, and the id sets agree except
+    where bf16 rounding moves a candidate across the probe or top-k boundary."""
+    X = bf16_round(W.mixture(n, dim, max(lists // 2, 2), 900 + n))
+    Q = bf16_round(W.mixture(nq, dim, max(lists // 2, 2), 977 + n, centers_seed=900 + n))
+    ix = ndb.IvfIndex(dim, lists, metric)
+    ix.ivfbuild(X)
+    ix.ivfinsert(X)
+    d0, i0 = ix.search(Q, nprobe, k, ndb.IVF_FULL, ndb.ARITH_IVF_F32)
+    d1, i1 = ix.search(Q, nprobe, k, ndb.IVF_FULL, ndb.ARITH_TENSOR)
+    # every returned distance is the reference fp32 distance of the returned id
+    for q in range(0, nq, max(1, nq // 40)):
+        got = i1[q] >= 0
+        assert np.all(np.isinf(d1[q][~got]))
+        want = orc.distance_pairs(X[i1[q][got]], np.repeat(Q[q:q + 1], got.sum(), 0), metric, orc.ARITH_IVF_F32)
+        assert np.array_equal(d1[q][got], want), (q, d1[q], want)
+    # sorted by (dist, id)
+    assert np.all(np.diff(d1, axis=1)[np.isfinite(d1[:, 1:]) & np.isfinite(d1[:, :-1])] >= 0)
+    overlap = np.mean([len(set(i0[q]) & set(i1[q])) / k for q in range(nq)])
+    assert overlap >= 0.98, overlap
+    if nprobe >= lists:
+        # whole index probed: the only approximation left is the candidate margin
+        assert overlap >= 0.999, overlap
+
+
+def test_tensor_ivf_rejects_what_it_cannot_do(ndb):
+    X = W.gaussian(500, 32, 1)
+    ix = ndb.IvfIndex(32, 4, ndb.COSINE)
+    ix.ivfbuild(X)
+    ix.ivfinsert(X)
+    with pytest.raises(ndb.NdbError):
+        ix.search(X[:3], 2, 10, ndb.IVF_FULL, ndb.ARITH_TENSOR)       # cosine
+    ix2 = ndb.IvfIndex(32, 4, ndb.L2)
+    ix2.ivfbuild(X)
+    ix2.ivfinsert(X)
+    with pytest.raises(ndb.NdbError):
+        ix2.search(X[:3], 2, 17, ndb.IVF_FULL, ndb.ARITH_TENSOR)      # k > 16
+    with pytest.raises(ndb.NdbError):
+        ix2.search(X[:3], 2, 10, ndb.IVF_LITERAL, ndb.ARITH_TENSOR)   # literal mode
