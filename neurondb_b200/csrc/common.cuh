@@ -60,6 +60,7 @@ struct Context {
     int stats_dim = 0;
     void *pinned = nullptr;               // staging for small D2H/H2D control traffic
     size_t pinned_bytes = 0;
+    unsigned long long *d_badidx = nullptr;   // device cell of validate_begin / validate_end
 };
 Context &ctx();
 int require_init();
@@ -145,5 +146,11 @@ struct VecStore {
 
 // host validation: NaN/Inf anywhere -> index of the first bad element, else -1
 int64_t find_nonfinite(const float *v, int64_t n);
+// The same check for input already staged on the device (the query batches of the search entry
+// points): validate_begin launches the scan, validate_end is called after the entry point's final
+// stream synchronisation and returns the first offending index or -1.  Keeps the 5 MB-per-batch
+// host scan out of the end-to-end path.
+int validate_begin(const float *v_dev, int64_t n, cudaStream_t s);
+int64_t validate_end();
 
 }  // namespace ndb

@@ -38,12 +38,51 @@ int require_init()
 
 int64_t find_nonfinite(const float *v, int64_t n)
 {
-    for (int64_t i = 0; i < n; i++) {
-        uint32_t u;
-        memcpy(&u, v + i, 4);
-        if ((u & 0x7f800000u) == 0x7f800000u) return i;
+    // blocks of 4096 without an early exit (vectorises), then locate inside the offending block
+    for (int64_t b = 0; b < n; b += 4096) {
+        const int64_t e = b + 4096 < n ? b + 4096 : n;
+        uint32_t any = 0;
+        for (int64_t i = b; i < e; i++) {
+            uint32_t u;
+            memcpy(&u, v + i, 4);
+            any |= (u & 0x7f800000u) == 0x7f800000u;
+        }
+        if (any)
+            for (int64_t i = b; i < e; i++) {
+                uint32_t u;
+                memcpy(&u, v + i, 4);
+                if ((u & 0x7f800000u) == 0x7f800000u) return i;
+            }
     }
     return -1;
+}
+
+__global__ void nonfinite_kernel(const float *__restrict__ v, int64_t n, unsigned long long *__restrict__ bad)
+{
+    unsigned long long first = ~0ull;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+        if ((__float_as_uint(v[i]) & 0x7f800000u) == 0x7f800000u && (unsigned long long) i < first) first = (unsigned long long) i;
+    if (first != ~0ull) atomicMin(bad, first);
+}
+
+int validate_begin(const float *v_dev, int64_t n, cudaStream_t s)
+{
+    Context &c = ctx();
+    unsigned long long *h = reinterpret_cast<unsigned long long *>(static_cast<char *>(c.pinned) + 256);
+    *h = ~0ull;
+    NDB_CUDA(cudaMemsetAsync(c.d_badidx, 0xFF, 8, s));
+    const int64_t blocks = (n + 255) / 256;
+    nonfinite_kernel<<<(unsigned) (blocks < 4 * c.sm_count ? blocks : 4 * c.sm_count), 256, 0, s>>>(v_dev, n, c.d_badidx);
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    NDB_CUDA(cudaMemcpyAsync(h, c.d_badidx, 8, cudaMemcpyDeviceToHost, s));
+    return NDB_B200_OK;
+}
+
+int64_t validate_end()
+{
+    const unsigned long long v = *reinterpret_cast<unsigned long long *>(static_cast<char *>(ctx().pinned) + 256);
+    return v == ~0ull ? -1 : (int64_t) v;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -228,6 +267,7 @@ int ndb_b200_init(int device)
     NDB_CUDA(cudaEventCreate(&g_ctx.ev1));
     g_ctx.pinned_bytes = 1 << 20;
     NDB_CUDA(cudaMallocHost(&g_ctx.pinned, g_ctx.pinned_bytes));
+    NDB_CUDA(cudaMalloc(&g_ctx.d_badidx, 8));
     g_ctx.initialized = true;
     g_ctx_pid = getpid();
     return NDB_B200_OK;
@@ -239,6 +279,8 @@ void ndb_b200_shutdown(void)
     cudaSetDevice(g_ctx.device);
     cudaStreamSynchronize(g_ctx.stream);
     if (g_ctx.pinned) cudaFreeHost(g_ctx.pinned);
+    if (g_ctx.d_badidx) cudaFree(g_ctx.d_badidx);
+    g_ctx.d_badidx = nullptr;
     if (g_ctx.ev0) cudaEventDestroy(g_ctx.ev0);
     if (g_ctx.ev1) cudaEventDestroy(g_ctx.ev1);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);

@@ -855,18 +855,19 @@ int ndb_b200_hnsw_search(ndb_b200_hnsw *h, const float *Q, int nq, int strategy,
 {
     NDB_CHECK(require_init());
     NDB_REQUIRE(h && Q && dist && ids && nq > 0, NDB_B200_EINVAL, "hnsw_search: NULL or empty input");
-    NDB_REQUIRE(find_nonfinite(Q, (int64_t) nq * h->dim) < 0, NDB_B200_EVECTOR, "hnsw_search: NaN/Inf in query");
     cudaStream_t s = ctx().stream;
     const size_t qb = (size_t) nq * h->dim * 4, m = (size_t) nq * k;
     NDB_CHECK(h->qbuf.reserve(qb));
     NDB_CHECK(h->outd.reserve(m * 4));
     NDB_CHECK(h->outi.reserve(m * 8));
     NDB_CUDA(cudaMemcpyAsync(h->qbuf.p, Q, qb, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(validate_begin(h->qbuf.as<float>(), (int64_t) nq * h->dim, s));
     NDB_CHECK(ndb_b200_hnsw_search_dev(h, h->qbuf.as<float>(), nq, strategy, ef, k, mode, h->outd.as<float>(),
                                        h->outi.as<int64_t>(), s));
     NDB_CUDA(cudaMemcpyAsync(dist, h->outd.p, m * 4, cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaMemcpyAsync(ids, h->outi.p, m * 8, cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaStreamSynchronize(s));
+    NDB_REQUIRE(validate_end() < 0, NDB_B200_EVECTOR, "hnsw_search: NaN/Inf in query");
     return NDB_B200_OK;
 }
 

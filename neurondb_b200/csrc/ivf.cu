@@ -986,18 +986,19 @@ int ndb_b200_ivf_search(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, in
 {
     NDB_CHECK(require_init());
     NDB_REQUIRE(ix && Q && dist && ids && nq > 0, NDB_B200_EINVAL, "ivf_search: NULL or empty input");
-    NDB_REQUIRE(find_nonfinite(Q, (int64_t) nq * ix->dim) < 0, NDB_B200_EVECTOR, "ivf_search: NaN/Inf in query");
     cudaStream_t s = ctx().stream;
     const size_t qb = (size_t) nq * ix->dim * 4, m = (size_t) nq * k;
     NDB_CHECK(ix->qbuf.reserve(qb));
     NDB_CHECK(ix->outd.reserve(m * 4));
     NDB_CHECK(ix->outi.reserve(m * 8));
     NDB_CUDA(cudaMemcpyAsync(ix->qbuf.p, Q, qb, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(validate_begin(ix->qbuf.as<float>(), (int64_t) nq * ix->dim, s));
     NDB_CHECK(ndb_b200_ivf_search_dev(ix, ix->qbuf.as<float>(), nq, nprobe, k, mode, arith, ix->outd.as<float>(),
                                       ix->outi.as<int64_t>(), s));
     NDB_CUDA(cudaMemcpyAsync(dist, ix->outd.p, m * 4, cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaMemcpyAsync(ids, ix->outi.p, m * 8, cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaStreamSynchronize(s));
+    NDB_REQUIRE(validate_end() < 0, NDB_B200_EVECTOR, "ivf_search: NaN/Inf in query");
     return NDB_B200_OK;
 }
 

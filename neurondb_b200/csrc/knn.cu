@@ -223,19 +223,20 @@ int ndb_b200_knn_exact(ndb_b200_dataset *ds, int metric, int arith, const float 
 {
     NDB_CHECK(require_init());
     NDB_REQUIRE(ds && Q && dist && ids && nq > 0, NDB_B200_EINVAL, "knn_exact: NULL or empty input");
-    const int64_t bad = find_nonfinite(Q, (int64_t) nq * ds->dim);
-    NDB_REQUIRE(bad < 0, NDB_B200_EVECTOR, "vector contains NaN or Infinity at index %lld", (long long) (bad % ds->dim));
     cudaStream_t s = ctx().stream;
     const size_t qb = (size_t) nq * ds->dim * sizeof(float), m = (size_t) nq * k;
     NDB_CHECK(ds->qbuf.reserve(qb));
     NDB_CHECK(ds->outd.reserve(m * sizeof(float)));
     NDB_CHECK(ds->outi.reserve(m * sizeof(int64_t)));
     NDB_CUDA(cudaMemcpyAsync(ds->qbuf.p, Q, qb, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(validate_begin(ds->qbuf.as<float>(), (int64_t) nq * ds->dim, s));
     NDB_CHECK(ndb_b200_knn_exact_dev(ds, metric, arith, ds->qbuf.as<float>(), nq, k, ds->outd.as<float>(),
                                      ds->outi.as<int64_t>(), s));
     NDB_CUDA(cudaMemcpyAsync(dist, ds->outd.p, m * sizeof(float), cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaMemcpyAsync(ids, ds->outi.p, m * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaStreamSynchronize(s));
+    const int64_t bad = validate_end();
+    NDB_REQUIRE(bad < 0, NDB_B200_EVECTOR, "vector contains NaN or Infinity at index %lld", (long long) (bad % ds->dim));
     return NDB_B200_OK;
 }
 
