@@ -170,7 +170,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--arith", default="ivf_f32", choices=["ivf_f32", "fast", "tensor"])
+    ap.add_argument("--arith", default="tensor", choices=["ivf_f32", "fast", "tensor"],
+                    help="tensor: tcgen05 bf16 candidate selection + fp32 re-rank (default); ivf_f32: the reference's fp32 "
+                         "arithmetic end to end, bit-exact distances and ids")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -221,8 +223,8 @@ def main():
         fin_d = torch.empty_like(out_d)
         fin_i = torch.empty_like(out_i)
 
-    def step(s):
-        q = qd[s % 4]
+    def step(s, arith=arith):
+        q = qd[0 if os.environ.get("NDB_BENCH_ONE_BATCH") else s % 4]
         ix.search_dev(q.data_ptr(), nq, out_d.data_ptr(), out_i.data_ptr(), w["nprobe"], k, ndb.IVF_FULL, arith, stream)
         if world > 1:
             dist.all_gather_into_tensor(all_d, out_d)
@@ -285,7 +287,7 @@ def main():
     hi = torch.empty((nq, k), dtype=torch.int64).pin_memory()
     lib = ndb._lib.load()
 
-    def e2e_step(s):
+    def e2e_step(s, arith=arith):
         q = qh[s % 4]
         ndb.check(lib.ndb_b200_ivf_search(ix.h, ndb.ptr(q.data_ptr()), nq, w["nprobe"], k, ndb.IVF_FULL, arith,
                                           ndb.ptr(hd.data_ptr()), ndb.ptr(hi.data_ptr())))
@@ -312,6 +314,38 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e_val = nq / e2e_s
+
+    # the same step in the reference's own fp32 arithmetic (bit-exact path), for comparison
+    alt = None
+    if args.arith == "tensor":
+        a32 = ndb.ARITH_IVF_F32
+        for s in range(3):
+            step(s, a32)
+        barrier()
+        ev0.record()
+        for s in range(args.steps):
+            step(s, a32)
+        ev1.record()
+        barrier()
+        alt_ms = ev0.elapsed_time(ev1) / args.steps
+        for s in range(2):
+            e2e_step(s, a32)
+        barrier()
+        t = time.perf_counter()
+        for s in range(args.steps):
+            e2e_step(s, a32)
+        barrier()
+        alt_e2e = (time.perf_counter() - t) / args.steps
+        if world > 1:
+            tt = torch.tensor([alt_ms, alt_e2e * 1e3], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            alt_ms, alt_e2e = float(tt[0].item()), float(tt[1].item()) * 1e-3
+        step(0, a32)
+        torch.cuda.synchronize()
+        ref_i = (fin_i if world > 1 else out_i)[:500].cpu().numpy()
+        alt = {"arith": "ivf_f32", "value": nq / (alt_ms * 1e-3), "ms_per_step": alt_ms, "e2e": nq / alt_e2e,
+               "unit": "queries/s", "ids_equal_to_tensor_path": float((ref_i == res_i).mean()),
+               "note": "the reference's fp32 arithmetic end to end (bit-exact distances and ids vs the oracle)"}
 
     if rank != 0:
         if world > 1:
@@ -384,6 +418,7 @@ def main():
                    "l2": "inputs (%.2f GB of lists) larger than the 126 MB L2; 4 query batches rotate" % (w["n"] * dim * 4 / 1e9),
                    "parallelism": "lists sharded l %% %d, NCCL all-gather + device merge" % world if world > 1 else "1 GPU"},
         "recall_at_10": recall,
+        "alt": alt,
         "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
                 "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches),

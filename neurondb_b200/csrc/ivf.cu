@@ -50,7 +50,8 @@ struct ndb_b200_ivf {
     bool tc_ok = false, ctc_ok = false;
     TcStore tc, ctc;                     // lists, centroids
     TcScratch tcs, ctcs;
-    DevBuf tc_src, d_ltile8;             // tensor row -> IL32 slot; first tile of each list (* 8, in 32-row blocks)
+    DevBuf tc_src, tc_row, d_ltile8;     // tensor row -> IL32 slot / arena row; first tile of each list (* 8, in 32-row blocks)
+    std::vector<uint32_t> row_of_slot;   // IL32 slot -> arena row (host copy, kept for the tensor layout)
 };
 
 namespace ndb {
@@ -240,35 +241,51 @@ __global__ void ivf_tc_items_kernel(const uint32_t *__restrict__ cnt, const uint
 // fp32 path returns for the same ids; only the candidate SELECTION used bf16 products.
 template <class P>
 __global__ void __launch_bounds__(128) ivf_tc_finish_kernel(const float *__restrict__ pdist, const uint32_t *__restrict__ pslot,
-                                                            const uint32_t *__restrict__ tc_src, const float4 *__restrict__ vecs,
-                                                            const int64_t *__restrict__ ids, const float *__restrict__ Q,
+                                                            const uint32_t *__restrict__ tc_src, const uint32_t *__restrict__ tc_row,
+                                                            const float *__restrict__ arena, const int64_t *__restrict__ ids,
+                                                            const float *__restrict__ Q,
                                                             const uint32_t *__restrict__ probe, const uint32_t *__restrict__ pairpos,
                                                             const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len,
-                                                            int nq, int nprobe, int nlists, uint32_t segb, int dim, int dimp, int kc,
-                                                            int k, float *__restrict__ out_dist, int64_t *__restrict__ out_ids)
+                                                            const float *__restrict__ gthr, int nq, int nprobe, int nlists,
+                                                            uint32_t segb, int dim, int dimp, int kc, int k,
+                                                            float *__restrict__ out_dist, int64_t *__restrict__ out_ids)
 {
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
     WarpTopK<1, uint32_t> cand;
     cand.init();
-    for (int r = 0; r < nprobe; r++) {
-        const size_t p = (size_t) q * nprobe + r;
-        const uint32_t l = probe[p];
-        if (l >= (uint32_t) nlists) continue;
-        const uint32_t len = list_len[l];
-        if (len == 0) continue;
-        const uint32_t pos = pairpos[p], nseg = ivf_nseg(len, segb);
-        const uint32_t item0 = item_off[l] + (pos / TC_M) * nseg;
-        const uint32_t it = pos % TC_M;
-        // the 2 * nseg partial lists of kc entries are contiguous per (item, lane-in-tile)
-        for (uint32_t sg = 0; sg < nseg; sg++) {
-            const size_t base = ((size_t) (item0 + sg) * (2 * TC_M) + it * 2) * kc;
-            for (int i = lane; i < round_up(2 * kc, 32); i += 32) {
-                float cd = INFINITY;
-                uint32_t slot = INVALID_SLOT;
-                if (i < 2 * kc) { slot = pslot[base + i]; cd = pdist[base + i]; }
-                cand.offer(cd, slot, slot != INVALID_SLOT, lane, kc);
+    // the scan kernel left, per query, an upper bound of its kc-th best key (packed keys only):
+    // partial entries above it cannot be among the kc best
+    const float bound = gthr ? gthr[q] : INFINITY;
+    for (int r0 = 0; r0 < nprobe; r0 += 32) {
+        // lane r: where the partial lists of probe r0 + r start, and how many segments there are
+        uint32_t my_first = 0, my_nseg = 0;
+        if (r0 + lane < nprobe) {
+            const size_t p = (size_t) q * nprobe + r0 + lane;
+            const uint32_t l = probe[p];
+            if (l < (uint32_t) nlists) {
+                const uint32_t len = list_len[l];
+                if (len) {
+                    const uint32_t pos = pairpos[p];
+                    my_nseg = ivf_nseg(len, segb);
+                    my_first = (item_off[l] + (pos / TC_M) * my_nseg) * (2 * TC_M) + (pos % TC_M) * 2;
+                }
+            }
+        }
+        const int nr = min(32, nprobe - r0);
+        for (int r = 0; r < nr; r++) {
+            const uint32_t nseg = __shfl_sync(FULL, my_nseg, r), first = __shfl_sync(FULL, my_first, r);
+            // the two halves' kc entries are contiguous per (item, lane-in-tile)
+            for (uint32_t sg = 0; sg < nseg; sg++) {
+                const size_t base = ((size_t) first + (size_t) sg * (2 * TC_M)) * kc;
+                for (int i = lane; i < round_up(2 * kc, 32); i += 32) {
+                    float cd = INFINITY;
+                    uint32_t slot = INVALID_SLOT;
+                    if (i < 2 * kc) { slot = pslot[base + i]; cd = pdist[base + i]; }
+                    const bool ok = slot != INVALID_SLOT && cd <= bound;
+                    if (__any_sync(FULL, ok)) cand.offer(cd, slot, ok, lane, kc);
+                }
             }
         }
     }
@@ -278,20 +295,25 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_kernel(const float *__restr
     int64_t id = -1;
     const bool have = ts != INVALID_SLOT;
     if (have) {
-        const uint32_t slot = tc_src[ts];
+        // the candidate's fp32 row from the row-major arena: 4 * dim contiguous bytes (the IL32 list
+        // store would hand out one 16-byte piece per 512 bytes)
         const float *qv = Q + (size_t) q * dim;
-        const float4 *vp = vecs + (size_t) (slot >> 5) * (8 * (size_t) dimp) + (slot & 31);
+        const float *xv = arena + (size_t) tc_row[ts] * dim;
         typename P::Acc acc;
         P::init(acc);
-        for (int j = 0; j < dim; j += 4) {
-            const float4 x = vp[(size_t) (j >> 2) * 32];
-            P::step(acc, x.x, qv[j]);
-            if (j + 1 < dim) P::step(acc, x.y, qv[j + 1]);
-            if (j + 2 < dim) P::step(acc, x.z, qv[j + 2]);
-            if (j + 3 < dim) P::step(acc, x.w, qv[j + 3]);
+        if ((dim & 3) == 0) {
+            for (int j = 0; j < dim; j += 4) {
+                const float4 x = *reinterpret_cast<const float4 *>(xv + j);
+                P::step(acc, x.x, qv[j]);
+                P::step(acc, x.y, qv[j + 1]);
+                P::step(acc, x.z, qv[j + 2]);
+                P::step(acc, x.w, qv[j + 3]);
+            }
+        } else {
+            for (int j = 0; j < dim; j++) P::step(acc, xv[j], qv[j]);
         }
         ed = P::finish(acc, 0, 0);
-        id = ids[slot];
+        id = ids[tc_src[ts]];
     }
     WarpTopK<1, int64_t> top;
     top.init();
@@ -428,6 +450,7 @@ static int ivf_layout(ndb_b200_ivf *ix, cudaStream_t s)
             by_list[start[l] + pos[l]++] = (uint32_t) r;
         }
         std::vector<uint32_t> slot_of_row(n);
+        ix->row_of_slot.assign(nslots > 0 ? nslots : 1, INVALID_SLOT);
         std::vector<int64_t> ids_by_slot(nslots > 0 ? nslots : 1, -1);
         std::vector<uint32_t> lit(nslots > 0 ? nslots : 1, INVALID_SLOT);
         std::vector<uint32_t> order;
@@ -444,6 +467,7 @@ static int ivf_layout(ndb_b200_ivf *ix, cudaStream_t s)
             for (uint32_t j = 0; j < len; j++) {
                 slot_of_row[order[j]] = base + j;
                 ids_by_slot[base + j] = ix->row_id[order[j]];
+                ix->row_of_slot[base + j] = order[j];
             }
             for (uint32_t j = 0; j < len; j++) lit[base + j] = slot_of_row[rows[j]];
         }
@@ -496,13 +520,15 @@ static int ivf_tensor_ready(ndb_b200_ivf *ix, cudaStream_t s)
         nt += (ix->list_len[l] + TC_N - 1) / TC_N;
     }
     NDB_REQUIRE(nt * TC_N < 0xfffffff0ull, NDB_B200_EINVAL, "ivf: too many rows for the tensor copy");
-    std::vector<uint32_t> src((size_t) (nt ? nt : 1) * TC_N, INVALID_SLOT);
+    std::vector<uint32_t> src((size_t) (nt ? nt : 1) * TC_N, INVALID_SLOT), row(src.size(), INVALID_SLOT);
     for (int l = 0; l < L; l++) {
-        uint32_t *d = src.data() + (size_t) ltile8[l] * 32;
+        uint32_t *d = src.data() + (size_t) ltile8[l] * 32, *r = row.data() + (size_t) ltile8[l] * 32;
         const uint32_t base = ix->list_blk[l] * 32;
-        for (uint32_t j = 0; j < ix->list_len[l]; j++) d[j] = base + j;
+        for (uint32_t j = 0; j < ix->list_len[l]; j++) { d[j] = base + j; r[j] = ix->row_of_slot[base + j]; }
     }
     NDB_CHECK(ix->tc_src.reserve(src.size() * 4));
+    NDB_CHECK(ix->tc_row.reserve(row.size() * 4));
+    NDB_CUDA(cudaMemcpyAsync(ix->tc_row.p, row.data(), row.size() * 4, cudaMemcpyHostToDevice, s));
     NDB_CHECK(ix->d_ltile8.reserve((size_t) L * 4));
     NDB_CUDA(cudaMemcpyAsync(ix->tc_src.p, src.data(), src.size() * 4, cudaMemcpyHostToDevice, s));
     NDB_CUDA(cudaMemcpyAsync(ix->d_ltile8.p, ltile8.data(), (size_t) L * 4, cudaMemcpyHostToDevice, s));
@@ -611,7 +637,9 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     p.pdist = ix->tcs.pdist.as<float>();
     p.pslot = ix->tcs.pslot.as<uint32_t>();
     NDB_CHECK(ix->tcs.gthr.reserve((size_t) nq * 4));
-    NDB_CUDA(cudaMemsetAsync(ix->tcs.gthr.p, 0x7f, (size_t) nq * 4, s));      // 3.4e38: "no bound yet"
+    static int calls = 0;
+    if (!getenv("NDB_IVF_TC_EXPERIMENT_KEEP_BOUNDS") || calls++ == 0)      // experiment only: start from the previous call's final bounds
+        NDB_CUDA(cudaMemsetAsync(ix->tcs.gthr.p, 0x7f, (size_t) nq * 4, s));      // 3.4e38: "no bound yet"
     p.qmap = ix->qmap.as<uint32_t>();
     p.nprobe = (uint32_t) np;
     p.gthr = getenv("NDB_IVF_TC_NOSHARE") ? nullptr : ix->tcs.gthr.as<float>();
@@ -627,7 +655,12 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
 
     // 4. merge + fp32 re-rank
     const unsigned mgrid = (unsigned) ((nq + 3) / 4);
-#define NDB_FIN(M) ivf_tc_finish_kernel<Arith<M, NDB_ARITH_IVF_F32>><<<mgrid, 128, 0, s>>>(         ix->tcs.pdist.as<float>(), ix->tcs.pslot.as<uint32_t>(), ix->tc_src.as<uint32_t>(),         reinterpret_cast<const float4 *>(ix->store.ptr()), ix->ids.as<int64_t>(), Q_dev, ix->probe.as<uint32_t>(),         ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), nq, np, L, segb, ix->dim,         ix->dimp, kc, k, dist_dev, ids_dev)
+#define NDB_FIN(M)                                                                                                   \
+    ivf_tc_finish_kernel<Arith<M, NDB_ARITH_IVF_F32>><<<mgrid, 128, 0, s>>>(                                          \
+        ix->tcs.pdist.as<float>(), ix->tcs.pslot.as<uint32_t>(), ix->tc_src.as<uint32_t>(), ix->tc_row.as<uint32_t>(),  \
+        ix->arena.as<float>(), ix->ids.as<int64_t>(), Q_dev, ix->probe.as<uint32_t>(),                                  \
+        ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), p.packed ? p.gthr : nullptr, \
+        nq, np, L, segb, ix->dim, ix->dimp, kc, k, dist_dev, ids_dev)
     if (ix->metric == NDB_L2) NDB_FIN(NDB_L2);
     else NDB_FIN(NDB_IP);
 #undef NDB_FIN

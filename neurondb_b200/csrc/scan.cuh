@@ -578,6 +578,43 @@ __global__ void merge_parts_kernel(const float *pdist, const uint32_t *pslot, co
     }
 }
 
+// the same merge when a query's partial lists hold at most 32 entries in all (the tensor path's two
+// column halves): one entry per lane and a single 15-stage bitonic sort by (dist, key)
+template <class KeyT>
+__global__ void merge_parts32_kernel(const float *pdist, const uint32_t *pslot, const int64_t *ids, int nq, int total, int k,
+                                     float *out_dist, int64_t *out_ids, uint32_t *out_slot)
+{
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    float d = INFINITY;
+    KeyT key = KeyMax<KeyT>::v;
+    if (lane < total) {
+        const uint32_t s = pslot[(size_t) q * total + lane];
+        if (s != INVALID_SLOT) {
+            d = pdist[(size_t) q * total + lane];
+            key = ids ? (KeyT) ids[s] : (KeyT) s;
+        }
+    }
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            const float pd = __shfl_xor_sync(FULL, d, j);
+            const KeyT pk = shfl_xor_key<KeyT>(key, j);
+            const bool want_min = ((lane & j) == 0) == ((lane & kk) == 0 || kk == 32);
+            const bool take = want_min ? pair_less<KeyT>(pd, pk, d, key) : pair_less<KeyT>(d, key, pd, pk);
+            if (take) { d = pd; key = pk; }
+        }
+    }
+    if (lane < k) {
+        const bool have = key != KeyMax<KeyT>::v;
+        out_dist[(size_t) q * k + lane] = have ? d : INFINITY;
+        if (out_ids) out_ids[(size_t) q * k + lane] = have ? (int64_t) key : -1;
+        if (out_slot) out_slot[(size_t) q * k + lane] = have ? (uint32_t) key : INVALID_SLOT;
+    }
+}
+
 // merge of [nshards][nq][k] (dist, id) lists from other ranks (distributed.c:425-438 order)
 template <int KR>
 __global__ void merge_shards_kernel(const float *dist, const int64_t *ids, int nshards, int nq, int k,

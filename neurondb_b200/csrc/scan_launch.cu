@@ -145,7 +145,10 @@ int launch_merge_parts(const float *pdist, const uint32_t *pslot, const int64_t 
     if (nq <= 0) return NDB_B200_OK;
     const int kr = kr_for(k);
     const unsigned grid = (unsigned) ((nq + 3) / 4);
-    if (kr == 1) merge_parts_kernel<1><<<grid, 128, 0, s>>>(pdist, pslot, ids, nq, nparts, k, out_dist, out_ids, out_slot);
+    if (nparts * k <= 32) {
+        if (ids) merge_parts32_kernel<int64_t><<<grid, 128, 0, s>>>(pdist, pslot, ids, nq, nparts * k, k, out_dist, out_ids, out_slot);
+        else merge_parts32_kernel<uint32_t><<<grid, 128, 0, s>>>(pdist, pslot, ids, nq, nparts * k, k, out_dist, out_ids, out_slot);
+    } else if (kr == 1) merge_parts_kernel<1><<<grid, 128, 0, s>>>(pdist, pslot, ids, nq, nparts, k, out_dist, out_ids, out_slot);
     else if (kr == 4) merge_parts_kernel<4><<<grid, 128, 0, s>>>(pdist, pslot, ids, nq, nparts, k, out_dist, out_ids, out_slot);
     else { set_error("merge: k=%d out of range (1..128)", k); return NDB_B200_EINVAL; }
     count_launch();

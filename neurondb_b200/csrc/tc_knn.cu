@@ -129,24 +129,10 @@ __global__ void tc_block_queries_kernel(const float *__restrict__ Q, const uint3
     const int chunk = g / (TC_KC / 8), kc = g % (TC_KC / 8);
     const size_t off = ((((size_t) (tile * nkc + chunk) * (TC_KC / 8) + kc) * (TC_M / 8) + (rr >> 3)) * 8 + (rr & 7)) * 8;
     *reinterpret_cast<uint4 *>(qb + off) = *reinterpret_cast<const uint4 *>(o);
-    (void) part;
-    (void) qnorm;
-}
-
-// squared norm of the bf16-rounded query, one thread per query (fixed order: deterministic)
-__global__ void tc_query_norms_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap, uint32_t nprobe, int nq,
-                                      int nqpad, int dim, float *__restrict__ qnorm)
-{
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nqpad) return;
-    const int64_t src = qmap ? (qmap[q] != INVALID_SLOT ? (int64_t) (qmap[q] / nprobe) : -1) : (q < nq ? q : -1);
-    float acc = 0.0f;
-    if (src >= 0)
-        for (int d = 0; d < dim; d++) {
-            const float r = __bfloat162float(__float2bfloat16_rn(Q[(size_t) src * dim + d]));
-            acc = fmaf(r, r, acc);
-        }
-    qnorm[q] = acc;
+    // squared norm of the rounded query: the row's 16 or 32 threads are adjacent lanes of one warp;
+    // a fixed xor tree, so a query gets the same norm at whatever tile position it sits
+    for (int o2 = groups >> 1; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(FULL, part, o2);
+    if (g == 0) qnorm[q] = part;
 }
 
 // ---- tcgen05 / TMEM primitives -------------------------------------------------------------
@@ -322,6 +308,13 @@ template <int KT> __device__ __forceinline__ void tc_key_insert(float (&L)[16], 
     L[0] = fminf(L[0], x);
 }
 
+// next representable float above a finite g
+__device__ __forceinline__ float float_next_up(float g)
+{
+    const uint32_t b = __float_as_uint(g + 0.0f);              // -0 -> +0
+    return __uint_as_float(g >= 0.0f ? b + 1u : b - 1u);
+}
+
 // float atomic min for values of either sign (the cell starts at a positive value)
 __device__ __forceinline__ void atomic_min_f32(float *a, float v)
 {
@@ -337,7 +330,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
     unsigned char *q_smem = tsm;
     unsigned char *x_smem = tsm + (size_t) TC_MAX_CHUNKS * TC_QCHUNK_BYTES;
     float *n_smem = reinterpret_cast<float *>(x_smem + (size_t) TC_STAGES * TC_XSTAGE_BYTES);
-    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], q_full, q_empty, acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], q_full[2], q_empty[2], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_holder;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -345,8 +338,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&q_full, 1);
-        mbar_init(&q_empty, 1);
+        for (int b = 0; b < 2; b++) { mbar_init(&q_full[b], 1); mbar_init(&q_empty[b], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 256); }
         mbar_fence_init();
     }
@@ -355,6 +347,9 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_holder;
+    // the Q region holds TC_MAX_CHUNKS 32 KB chunks: with one K-chunk (dim <= 128) it is used as two
+    // buffers, so that the next item's query tile loads while this item's MMAs run
+    const uint32_t nqbuf = p.nkc == 1 ? 2u : 1u;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -363,12 +358,13 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
             for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x, item_it++) {
                 const TcItem it = p.items[item];
                 const uint32_t qt = it.qtile;
-                mbar_spin(&q_empty, (item_it & 1u) ^ 1u);              // MMA finished with the previous Q tile
-                mbar_arrive_expect_tx(&q_full, (uint32_t) p.nkc * TC_QCHUNK_BYTES);
+                const uint32_t qb_i = item_it % nqbuf, qn_i = item_it / nqbuf;
+                mbar_spin(&q_empty[qb_i], (qn_i & 1u) ^ 1u);           // MMA finished with this buffer's previous tile
+                mbar_arrive_expect_tx(&q_full[qb_i], (uint32_t) p.nkc * TC_QCHUNK_BYTES);
                 for (int c = 0; c < p.nkc; c++)
-                    tma_bulk_g2s(q_smem + (size_t) c * TC_QCHUNK_BYTES,
+                    tma_bulk_g2s(q_smem + (size_t) (qb_i * p.nkc + c) * TC_QCHUNK_BYTES,
                                  reinterpret_cast<const unsigned char *>(p.qb) + ((size_t) qt * p.nkc + c) * TC_QCHUNK_BYTES,
-                                 TC_QCHUNK_BYTES, &q_full);
+                                 TC_QCHUNK_BYTES, &q_full[qb_i]);
                 const uint32_t t0 = it.t0, t1 = it.t1;
                 for (uint32_t t = t0; t < t1; t++, tile_it++) {
                     for (int c = 0; c < p.nkc; c++, stage_it++) {
@@ -395,7 +391,8 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
             for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x, item_it++) {
                 const TcItem it = p.items[item];
                 const uint32_t t0 = it.t0, t1 = it.t1;
-                mbar_spin(&q_full, item_it & 1u);
+                const uint32_t qb_i = item_it % nqbuf, qn_i = item_it / nqbuf;
+                mbar_spin(&q_full[qb_i], qn_i & 1u);
                 tc_fence_after();
                 for (uint32_t t = t0; t < t1; t++, tile_it++) {
                     const uint32_t a = tile_it & 1u;
@@ -406,7 +403,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                         const uint32_t s = stage_it % TC_STAGES;
                         mbar_spin(&full_bar[s], (stage_it / TC_STAGES) & 1u);
                         tc_fence_after();
-                        const uint32_t qa = smem_u32(q_smem + (size_t) c * TC_QCHUNK_BYTES);
+                        const uint32_t qa = smem_u32(q_smem + (size_t) (qb_i * p.nkc + c) * TC_QCHUNK_BYTES);
                         const uint32_t xa = smem_u32(x_smem + (size_t) s * TC_XSTAGE_BYTES);
 #pragma unroll
                         for (int ks = 0; ks < TC_KC / 16; ks++) {
@@ -419,7 +416,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     }
                     umma_commit(&acc_full[a]);                          // accumulator complete
                 }
-                umma_commit(&q_empty);                                  // Q tile reusable
+                umma_commit(&q_empty[qb_i]);                            // Q buffer reusable
             }
         }
     } else if (warp >= 4) {
@@ -456,16 +453,23 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
             float thr = gcap;                                           // KT-th best so far, in "candidate" units
             // candidate units: L2 -> ||x||^2 - 2 x.q (PACKED: + ||q||^2, i.e. the squared distance);
             // IP -> -x.q.  Pad rows carry +inf norms and never rank.
+            // PACKED keys and the shared bound are in units of (candidate + cadd); the tile loop compares raw
+            // candidates against thr - cadd
             const float cadd = (PACKED && METRIC == NDB_L2) ? qn : 0.0f;
+            // the bound is read one tile ahead (the load's latency hides behind the wait for the
+            // accumulator or the previous tile's work); a slightly stale bound is still a bound
+            float gnext = FLT_MAX;
+            if (gcell) gnext = *reinterpret_cast<volatile float *>(gcell);
             for (uint32_t t = t0; t < t1; t++, tile_it++) {
                 const uint32_t a = tile_it & 1u;
-                if (gcell) {
-                    // strictly above the shared bound: ties with the bound itself must survive
-                    gcap = fminf(gcap, nextafterf(*reinterpret_cast<volatile float *>(gcell), INFINITY));
-                    thr = fminf(thr, gcap);
-                }
                 mbar_spin(&acc_full[a], (tile_it >> 1) & 1u);
                 tc_fence_after();
+                if (gcell) {
+                    // strictly above the shared bound: ties with the bound itself must survive
+                    gcap = fminf(gcap, float_next_up(gnext));
+                    thr = fminf(thr, gcap);
+                    if (t + 1 < t1) gnext = *reinterpret_cast<volatile float *>(gcell);
+                }
                 const float *xn = n_smem + (size_t) (tile_it % TC_NORM_RING) * TC_N;
 #pragma unroll 1
                 for (int j = 0; j < ((p.debug_mode & 1) ? 0 : TC_N / 64); j++) {
@@ -484,10 +488,10 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     for (int i4 = 0; i4 < 8; i4++) {
                         const float4 n4 = *reinterpret_cast<const float4 *>(xn + col0 + 4 * i4);
                         if (METRIC == NDB_L2) {
-                            c[4 * i4 + 0] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 0]), n4.x + cadd);
-                            c[4 * i4 + 1] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 1]), n4.y + cadd);
-                            c[4 * i4 + 2] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 2]), n4.z + cadd);
-                            c[4 * i4 + 3] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 3]), n4.w + cadd);
+                            c[4 * i4 + 0] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 0]), n4.x);
+                            c[4 * i4 + 1] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 1]), n4.y);
+                            c[4 * i4 + 2] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 2]), n4.z);
+                            c[4 * i4 + 3] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 3]), n4.w);
                         } else {
                             c[4 * i4 + 0] = n4.x == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 0]);
                             c[4 * i4 + 1] = n4.y == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 1]);
@@ -504,9 +508,10 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                         for (int i = 0; i < w; i++) m[i] = fminf(m[i], m[i + w]);
                     if constexpr (PACKED) {
                         uint32_t mask = 0;
-                        if (m[0] < thr) {
+                        float thc = thr - cadd;                         // threshold in raw candidate units
+                        if (m[0] < thc) {
 #pragma unroll
-                            for (int i = 0; i < 32; i++) mask |= (c[i] < thr ? 1u : 0u) << i;
+                            for (int i = 0; i < 32; i++) mask |= (c[i] < thc ? 1u : 0u) << i;
                         }
                         const uint32_t ibase = (t - t0) * (TC_N / 2) + j * 32;
                         if (__any_sync(FULL, __popc(mask) > TC_HEAVY)) {
@@ -518,10 +523,10 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             }
                             float g[16];
 #pragma unroll
-                            for (int i = 0; i < 16; i++) g[i] = tc_pack(c[i], ibase + i);
+                            for (int i = 0; i < 16; i++) g[i] = tc_pack(c[i] + cadd, ibase + i);
                             tc_sort_merge16(bd, g);
 #pragma unroll
-                            for (int i = 0; i < 16; i++) g[i] = tc_pack(c[16 + i], ibase + 16 + i);
+                            for (int i = 0; i < 16; i++) g[i] = tc_pack(c[16 + i] + cadd, ibase + 16 + i);
                             tc_sort_merge16(bd, g);
                             thr = fminf(bd[KT - 1], gcap);
                         } else {
@@ -529,9 +534,10 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                                 const int i = __ffs(mask) - 1;
                                 mask &= mask - 1;
                                 const float cand = pick32(c, i);
-                                if (cand < thr) {
-                                    tc_key_insert<KT>(bd, tc_pack(cand, ibase + i));
+                                if (cand < thc) {
+                                    tc_key_insert<KT>(bd, tc_pack(cand + cadd, ibase + i));
                                     thr = fminf(bd[KT - 1], gcap);
+                                    thc = thr - cadd;
                                 }
                             }
                         }
@@ -573,8 +579,8 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             const uint32_t bits = __float_as_uint(d), idx = bits & TC_IDX_MASK;
                             const bool have = d < TC_KEY_BIG;
                             slot = have ? (t0 + (idx >> 7)) * TC_N + half * (TC_N / 2) + (idx & 127u) : INVALID_SLOT;
+                            // the key's value: squared distance (L2) / -dot (IP), comparable with p.gthr
                             d = have ? __uint_as_float(bits & ~TC_IDX_MASK) : INFINITY;
-                            if (METRIC == NDB_L2 && have) d = sqrtf(fmaxf(d, 0.0f));
                         } else {
                             slot = bi[j];
                             if (METRIC == NDB_L2 && slot != INVALID_SLOT) d = sqrtf(fmaxf(d + qn, 0.0f));
@@ -628,8 +634,7 @@ int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t npro
     const int groups = nkc * (TC_KC / 8);
     tc_block_queries_kernel<<<(unsigned) (((int64_t) nqpad * groups + 255) / 256), 256, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, dim,
                                                                                                 nkc, qb, qnorm);
-    tc_query_norms_kernel<<<(unsigned) ((nqpad + 127) / 128), 128, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, dim, qnorm);
-    count_launch(2);
+    count_launch();
     NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
 }
@@ -702,7 +707,12 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     if (nranges < 1) nranges = 1;
     if (nranges > (uint32_t) st.ntiles) nranges = (uint32_t) st.ntiles;
     uint32_t tpr = (uint32_t) ((st.ntiles + nranges - 1) / nranges);
-    if (packed && tpr > (uint32_t) TC_PACKED_MAX_TILES) tpr = TC_PACKED_MAX_TILES;
+    if (packed) {
+        // short stores (the IVF centroids): an item's first tile pays for filling the top-k lists, so
+        // prefer one item per query tile over many one-tile items as soon as half the SMs have work
+        if (tpr > (uint32_t) TC_PACKED_MAX_TILES) tpr = TC_PACKED_MAX_TILES;
+        else if (2 * nqt >= sms && st.ntiles <= TC_PACKED_MAX_TILES) tpr = (uint32_t) st.ntiles;
+    }
     nranges = (uint32_t) ((st.ntiles + tpr - 1) / tpr);
     NDB_CHECK(sc.pdist.reserve((size_t) nq * nranges * 2 * k * 4));
     NDB_CHECK(sc.pslot.reserve((size_t) nq * nranges * 2 * k * 4));
