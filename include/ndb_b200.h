@@ -211,6 +211,25 @@ int ndb_b200_merge_topk_dev(const float *dist_dev, const int64_t *ids_dev, int n
 int ndb_b200_merge_topk(const float *dist, const int64_t *ids, int nshards, int nq, int k,
                         float *out_dist, int64_t *out_ids);
 
+/* ---- index key extraction: ivfExtractVectorData (ivf_am.c:117-218), hnswExtractVectorData -----
+ * (hnsw_am.c:1402-1519).  The access methods accept vector, halfvec, sparsevec and bit columns and
+ * turn every key into float4[dim] first; these do it for a batch of n keys, writing n rows of dim
+ * floats (row-major) that dataset_append / ivf_insert / hnsw_build take as they are.
+ *   halfvec   : n*dim IEEE binary16 values (VectorF16.data, neurondb.h:44-49) through
+ *               fp16_to_float (src/types/quantization.c:171-215): IEEE for zeros, normals, Inf and
+ *               NaN; subnormal halves come out 2^-10 times their IEEE value, as in the reference
+ *   bit       : n rows of ceil(nbits/8) bytes (VARBITS), bit i = MSB-first -> 1.0f, else -1.0f
+ *   sparsevec : CSR batch of VectorMap entries (neurondb_types.h:47-53,106-107): row r holds
+ *               indices/values [indptr[r], indptr[r+1]); zero fill, entries applied in order (a
+ *               repeated index keeps the last value), indices outside [0,total_dim) ignored
+ * dim / nbits / total_dim must be 1..32767 (the reference's check), else NDB_B200_EINVAL. */
+int ndb_b200_keys_from_halfvec(const uint16_t *h, int64_t n, int dim, float *rows);
+int ndb_b200_keys_from_halfvec_dev(const uint16_t *h_dev, int64_t n, int dim, float *rows_dev, void *stream);
+int ndb_b200_keys_from_bits(const uint8_t *bits, int64_t n, int nbits, float *rows);
+int ndb_b200_keys_from_bits_dev(const uint8_t *bits_dev, int64_t n, int nbits, float *rows_dev, void *stream);
+int ndb_b200_keys_from_sparse(const int64_t *indptr, const int32_t *indices, const float *values, int64_t n,
+                              int total_dim, float *rows);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 /* kernels launched by this library since init (bench.py's gpu_launches) */
 int64_t ndb_b200_launch_count(void);

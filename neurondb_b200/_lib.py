@@ -93,6 +93,11 @@ SIGNATURES = {
     "ndb_b200_hnsw_last_evals": (_i64, [_p]),
     "ndb_b200_merge_topk_dev": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "ndb_b200_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "ndb_b200_keys_from_halfvec": (_i, [_p, _i64, _i, _p]),
+    "ndb_b200_keys_from_halfvec_dev": (_i, [_p, _i64, _i, _p, _p]),
+    "ndb_b200_keys_from_bits": (_i, [_p, _i64, _i, _p]),
+    "ndb_b200_keys_from_bits_dev": (_i, [_p, _i64, _i, _p, _p]),
+    "ndb_b200_keys_from_sparse": (_i, [_p, _p, _p, _i64, _i, _p]),
     "ndb_b200_launch_count": (_i64, []),
     "ndb_b200_set_timing": (_i, [_i]),
     "ndb_b200_last_kernel_stats": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),

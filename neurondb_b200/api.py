@@ -127,6 +127,37 @@ def merge_topk(dist, ids):
     return od, oi
 
 
+def keys_from_halfvec(h):
+    """halfvec keys (uint16 IEEE binary16 bit patterns, [n, dim]) -> float32 rows (hnsw_am.c:1435-1450)."""
+    h = np.ascontiguousarray(h, np.uint16)
+    n, dim = h.shape
+    out = np.empty((n, dim), np.float32)
+    check(L.load().ndb_b200_keys_from_halfvec(ptr(h), n, dim, ptr(out)))
+    return out
+
+
+def keys_from_bits(bits, nbits):
+    """bit keys ([n, ceil(nbits/8)] bytes, MSB first) -> rows of +1/-1 (hnsw_am.c:1480-1507)."""
+    bits = np.ascontiguousarray(bits, np.uint8)
+    n = bits.shape[0]
+    if bits.shape[1] != (nbits + 7) // 8:
+        raise ValueError("bits must have ceil(nbits/8) bytes per row")
+    out = np.empty((n, nbits), np.float32)
+    check(L.load().ndb_b200_keys_from_bits(ptr(bits), n, nbits, ptr(out)))
+    return out
+
+
+def keys_from_sparse(indptr, indices, values, total_dim):
+    """sparsevec keys as a CSR batch -> dense float32 rows (hnsw_am.c:1451-1479)."""
+    indptr = np.ascontiguousarray(indptr, np.int64)
+    indices = np.ascontiguousarray(indices, np.int32)
+    values = f32(values)
+    n = indptr.shape[0] - 1
+    out = np.empty((n, total_dim), np.float32)
+    check(L.load().ndb_b200_keys_from_sparse(ptr(indptr), ptr(indices), ptr(values), n, total_dim, ptr(out)))
+    return out
+
+
 class _Handle:
     _free = None
 

@@ -605,3 +605,64 @@ void orc_merge_topk(const float *dist, const int64_t *ids, int nshards, int nq, 
     }
     free(best);
 }
+
+/* ---- index key extraction -------------------------------------------------------------- */
+/* fp16_to_float, src/types/quantization.c:171-215: sign / 5-bit exponent / 10-bit mantissa;
+ * exponent 31 -> Inf/NaN with the mantissa moved up; normal numbers re-biased by 127 - 15 (exact,
+ * = IEEE).  QUIRK (kept, the reference's own result is the contract): a binary16 SUBNORMAL is
+ * renormalised with the float exponent 127 - 15 - (10 - e), e = 1 - shifts, i.e. 103 - shifts,
+ * where IEEE needs 113 - shifts: subnormal halves come out 2^-10 times their IEEE value. */
+float orc_fp16_to_float(uint16_t h)
+{
+    uint32_t sign = ((uint32_t) h & 0x8000u) << 16;
+    uint32_t e = ((uint32_t) h & 0x7c00u) >> 10;
+    uint32_t man = (uint32_t) h & 0x03ffu;
+    uint32_t f;
+    if (e == 0) {
+        if (man == 0) f = sign;
+        else {
+            /* shift the leading one up to bit 10, counting the shifts (:188-196) */
+            int shifts = 0;
+            while ((man & 0x0400u) == 0) { man <<= 1; shifts++; }
+            man &= 0x03ffu;
+            f = sign | ((uint32_t) (127 - 15 - (10 - (1 - shifts))) << 23) | (man << 13);
+        }
+    } else if (e == 0x1f) {
+        f = sign | 0x7f800000u | (man << 13);
+    } else {
+        f = sign | ((e + 127 - 15) << 23) | (man << 13);
+    }
+    float r;
+    memcpy(&r, &f, 4);
+    return r;
+}
+
+/* halfvec branch of hnswExtractVectorData (hnsw_am.c:1435-1450) / ivfExtractVectorData (ivf_am.c:165-173) */
+void orc_keys_from_halfvec(const uint16_t *h, int64_t n, int dim, float *rows)
+{
+    for (int64_t i = 0; i < n * dim; i++) rows[i] = orc_fp16_to_float(h[i]);
+}
+
+/* bit branch (hnsw_am.c:1480-1507, ivf_am.c:190-206): MSB-first inside each byte, 1 -> +1, 0 -> -1 */
+void orc_keys_from_bits(const uint8_t *bits, int64_t n, int nbits, float *rows)
+{
+    const int row_bytes = (nbits + 7) / 8;
+    for (int64_t r = 0; r < n; r++)
+        for (int i = 0; i < nbits; i++) {
+            int byte_idx = i / 8, bit_idx = i % 8;
+            int v = (bits[r * row_bytes + byte_idx] >> (8 - 1 - bit_idx)) & 1;
+            rows[r * nbits + i] = v ? 1.0f : -1.0f;
+        }
+}
+
+/* sparsevec branch (hnsw_am.c:1451-1479, ivf_am.c:174-189): memset 0, then entries in order */
+void orc_keys_from_sparse(const int64_t *indptr, const int32_t *indices, const float *values,
+                          int64_t n, int total_dim, float *rows)
+{
+    for (int64_t r = 0; r < n; r++) {
+        float *row = rows + r * total_dim;
+        memset(row, 0, sizeof(float) * (size_t) total_dim);
+        for (int64_t e = indptr[r]; e < indptr[r + 1]; e++)
+            if (indices[e] >= 0 && indices[e] < total_dim) row[indices[e]] = values[e];
+    }
+}

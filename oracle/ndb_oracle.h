@@ -132,6 +132,13 @@ double orc_recall_at_k(const int64_t *found, const int64_t *truth, int nq, int k
 void orc_merge_topk(const float *dist, const int64_t *ids, int nshards, int nq, int k,
                     float *out_dist, int64_t *out_ids);
 
+/* ---- index key extraction (ivf_am.c:117-218, hnsw_am.c:1402-1519) -------- */
+float orc_fp16_to_float(uint16_t h);                 /* src/types/quantization.c:171-215 */
+void orc_keys_from_halfvec(const uint16_t *h, int64_t n, int dim, float *rows);
+void orc_keys_from_bits(const uint8_t *bits, int64_t n, int nbits, float *rows);
+void orc_keys_from_sparse(const int64_t *indptr, const int32_t *indices, const float *values,
+                          int64_t n, int total_dim, float *rows);
+
 #ifdef __cplusplus
 }
 #endif

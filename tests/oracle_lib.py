@@ -78,6 +78,13 @@ def _load(name="libndb_oracle.so"):
     f = lib.orc_recall_at_k; f.restype = C.c_double; f.argtypes = [_i64p, _i64p, C.c_int, C.c_int]
     f = lib.orc_merge_topk; f.restype = None
     f.argtypes = [_f32p, _i64p, C.c_int, C.c_int, C.c_int, _f32p, _i64p]
+    f = lib.orc_fp16_to_float; f.restype = C.c_float; f.argtypes = [C.c_uint16]
+    f = lib.orc_keys_from_halfvec; f.restype = None
+    f.argtypes = [np.ctypeslib.ndpointer(np.uint16, flags="C"), C.c_int64, C.c_int, _f32p]
+    f = lib.orc_keys_from_bits; f.restype = None
+    f.argtypes = [np.ctypeslib.ndpointer(np.uint8, flags="C"), C.c_int64, C.c_int, _f32p]
+    f = lib.orc_keys_from_sparse; f.restype = None
+    f.argtypes = [_i64p, _i32p, _f32p, C.c_int64, C.c_int, _f32p]
     return lib
 
 
@@ -233,6 +240,29 @@ def recall_at_k(found, truth):
     return lib().orc_recall_at_k(found, truth, found.shape[0], found.shape[1])
 
 
+def keys_from_halfvec(h):
+    h = np.ascontiguousarray(h, np.uint16)
+    out = np.empty(h.shape, np.float32)
+    lib().orc_keys_from_halfvec(h, h.shape[0], h.shape[1], out)
+    return out
+
+
+def keys_from_bits(bits, nbits):
+    bits = np.ascontiguousarray(bits, np.uint8)
+    out = np.empty((bits.shape[0], nbits), np.float32)
+    lib().orc_keys_from_bits(bits, bits.shape[0], nbits, out)
+    return out
+
+
+def keys_from_sparse(indptr, indices, values, total_dim):
+    indptr = np.ascontiguousarray(indptr, np.int64)
+    indices = np.ascontiguousarray(indices, np.int32)
+    values = f32(values)
+    out = np.empty((indptr.shape[0] - 1, total_dim), np.float32)
+    lib().orc_keys_from_sparse(indptr, indices, values, indptr.shape[0] - 1, total_dim, out)
+    return out
+
+
 def merge_topk(dist, ids):
     dist = f32(dist); ids = np.ascontiguousarray(ids, np.int64)
     s, nq, k = dist.shape
@@ -330,3 +360,14 @@ def hnsw_encode_relation(g, X, tids=None, efc=64, efs=40):
     tp = None if tids is None else np.ascontiguousarray(tids, np.int64).ctypes.data
     nb = _pages_lib().orc_hnsw_encode_relation(g.h, X, tp, g.dim, g.m, efc, efs, blocks.reshape(-1), n + 1)
     return nb, blocks
+
+
+def ref_fp16_lib():
+    """fp16_to_float cut out of the reference's quantization.c (oracle/Makefile ref_build), or None."""
+    path = os.path.join(ORACLE_DIR, "_ref", "libndb_ref_fp16.so")
+    if not os.path.exists(path):
+        return None
+    lib_ = C.CDLL(path)
+    lib_.fp16_to_float.restype = C.c_float
+    lib_.fp16_to_float.argtypes = [C.c_uint16]
+    return lib_

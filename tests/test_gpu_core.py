@@ -166,3 +166,42 @@ def test_merge_topk(ndb, orc):
     gd, gi = ndb.merge_topk(d, ids)
     od, oi = orc.merge_topk(d, ids)
     assert np.array_equal(gi, oi) and same_bits(gd, od)
+
+
+# ---- key extraction ------------------------------------------------------
+def test_keys_from_halfvec_every_half_bit_exact(ndb, orc):
+    h = np.arange(65536, dtype=np.uint16).reshape(64, 1024)
+    got = ndb.keys_from_halfvec(h)
+    want = orc.keys_from_halfvec(h)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,nbits", [(1, 1), (33, 19), (500, 128), (3, 32767)])
+def test_keys_from_bits(ndb, orc, n, nbits):
+    bits = np.random.default_rng(nbits).integers(0, 256, size=(n, (nbits + 7) // 8), dtype=np.uint8)
+    assert np.array_equal(ndb.keys_from_bits(bits, nbits), orc.keys_from_bits(bits, nbits))
+
+
+def test_keys_from_sparse(ndb, orc):
+    rng = np.random.default_rng(77)
+    n, dim = 300, 257
+    nnz = rng.integers(0, 40, size=n)
+    nnz[5] = 0
+    indptr = np.concatenate([[0], np.cumsum(nnz)]).astype(np.int64)
+    indices = rng.integers(-3, dim + 3, size=int(indptr[-1])).astype(np.int32)     # some out of range, some repeated
+    values = rng.standard_normal(int(indptr[-1])).astype(np.float32)
+    got = ndb.keys_from_sparse(indptr, indices, values, dim)
+    assert np.array_equal(got, orc.keys_from_sparse(indptr, indices, values, dim))
+    # the extracted rows feed the index like any other
+    ix = ndb.IvfIndex(dim, 4)
+    ix.ivfbuild(got)
+    ix.ivfinsert(got)
+    d, i = ix.search(got[:5], 4, 1)
+    assert np.array_equal(i[:, 0], np.arange(5)) and np.all(d[:, 0] == 0)
+
+
+def test_keys_reject_bad_dimensions(ndb):
+    with pytest.raises(ndb.NdbError):
+        ndb.keys_from_bits(np.zeros((1, 4097), np.uint8), 32768)
+    with pytest.raises(ndb.NdbError):
+        ndb.keys_from_sparse(np.array([0, 0], np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32), 0)

@@ -189,3 +189,44 @@ def test_hnsw_oracle_properties():
     e = g.export()
     assert np.all(e["cnt"] <= 16) and e["nbr0"].shape == (1200, 16)
     assert np.all((e["nbr0"] == 0xFFFFFFFF) | (e["nbr0"] < 1200))
+
+
+# ---- key extraction ------------------------------------------------------
+@pytest.mark.skipif(O.ref_fp16_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_fp16_restatement_equals_reference_for_every_half():
+    ref = O.ref_fp16_lib()
+    h = np.arange(65536, dtype=np.uint16)
+    want = np.array([ref.fp16_to_float(int(x)) for x in h], np.float32)
+    got = O.keys_from_halfvec(h.reshape(1, -1))[0]
+    # (a float returned through ctypes passes through a Python double, which quiets signalling NaNs:
+    # compare NaNs as NaNs, everything else bit for bit)
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(got), nan)
+    assert np.array_equal(got[~nan].view(np.uint32), want[~nan].view(np.uint32))
+
+
+def test_fp16_is_ieee_except_for_the_subnormal_quirk():
+    """Pins the restatement without the reference tree: IEEE binary16 -> binary32 everywhere except
+    subnormal halves, which the reference scales by a further 2^-10 (quantization.c:186-197)."""
+    h = np.arange(65536, dtype=np.uint16)
+    got = O.keys_from_halfvec(h.reshape(256, 256)).reshape(-1)
+    ieee = h.view(np.float16).astype(np.float32)
+    sub = ((h & 0x7C00) == 0) & ((h & 0x03FF) != 0)
+    nan = np.isnan(ieee)
+    assert np.array_equal(got[~sub & ~nan].view(np.uint32), ieee[~sub & ~nan].view(np.uint32))
+    assert np.all(np.isnan(got[nan]))
+    assert np.array_equal(got[sub], ieee[sub] * np.float32(2.0 ** -10))
+
+
+def test_bit_and_sparse_keys():
+    rng = np.random.default_rng(5)
+    bits = rng.integers(0, 256, size=(7, 3), dtype=np.uint8)
+    rows = O.keys_from_bits(bits, 19)                       # 19 bits: the last byte is partly used
+    want = np.where(np.unpackbits(bits, axis=1)[:, :19] == 1, 1.0, -1.0).astype(np.float32)
+    assert np.array_equal(rows, want)
+    # sparsevec: out-of-range indices ignored, a repeated index keeps the last value, empty row = zeros
+    indptr = np.array([0, 3, 3, 6], np.int64)
+    indices = np.array([1, 4, 1, -1, 5, 2], np.int32)
+    values = np.array([1.5, 2.5, 3.5, 9.0, 9.0, -4.0], np.float32)
+    rows = O.keys_from_sparse(indptr, indices, values, 5)
+    assert np.array_equal(rows, np.array([[0, 3.5, 0, 0, 2.5], [0, 0, 0, 0, 0], [0, 0, -4.0, 0, 0]], np.float32))
