@@ -142,6 +142,18 @@ int ndb_b200_knn_exact_dev(ndb_b200_dataset *ds, int metric, int arith, const fl
 int ndb_b200_kmeans_train(const float *X, int n, int d, int k, int max_iter, float tol,
                           float *C, int *assign, int *counts, int *iters, float *cost);
 
+/* Row-sharded training (one process per GPU, rows split, centroids replicated): the local half of
+ * one Lloyd iteration.  shard_step assigns the n local rows to the k centroids C_dev
+ * (find_nearest_centroid, ivf_am.c:2274-2294) and writes the per-cluster f32 sums [k*d] and counts [k]
+ * of the local members (kmeans_update_centroids :2182-2213 without the division); the caller
+ * all-reduces sums and counts over the ranks, divides (empty cluster -> zeros), and calls shard_cost
+ * with the new centroids for its share of kmeans_compute_cost (:2218-2233), all-reducing that too.
+ * All pointers are device pointers.  With a single rank the sequence is bit-identical to kmeans_train. */
+int ndb_b200_kmeans_shard_step_dev(const float *X_dev, int64_t n, int d, int k, const float *C_dev, int *assign_dev,
+                                   float *sums_dev, int *counts_dev, void *stream);
+int ndb_b200_kmeans_shard_cost_dev(const float *X_dev, int64_t n, int d, const float *C_dev, const int *assign_dev,
+                                   float *cost_dev, void *stream);
+
 /* ---- IVF index: ivfbuild / ivfinsert / ivfrescan+ivfgettuple (src/index/ivf_am.c) -------- */
 int ndb_b200_ivf_create(int dim, int nlists, int metric, ndb_b200_ivf **out);
 void ndb_b200_ivf_free(ndb_b200_ivf *ix);

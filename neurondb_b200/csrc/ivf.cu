@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_kernel(const float *__restr
     const uint32_t ts = lane < kc ? cand.key[0] : INVALID_SLOT;
     float ed = INFINITY;
     int64_t id = -1;
-    const bool have = ts != INVALID_SLOT;
+    const bool have = ts != INVALID_SLOT && tc_row[ts] != INVALID_SLOT;      // (never a pad row of the tile layout)
     if (have) {
         // the candidate's fp32 row from the row-major arena: 4 * dim contiguous bytes (the IL32 list
         // store would hand out one 16-byte piece per 512 bytes)

@@ -42,7 +42,7 @@ __global__ void segment_starts_kernel(const int *sorted_keys, int64_t n, int k, 
 // ascending sample order, then sum / (float) count  (ivf_am.c:2189-2212)
 __global__ void kmeans_update_kernel(const float *__restrict__ X, const uint32_t *__restrict__ members,
                                      const int *__restrict__ start, int dim, int k, float *__restrict__ C,
-                                     int *__restrict__ counts)
+                                     int *__restrict__ counts, bool sums_only)
 {
     const int c = blockIdx.x;
     const int b = start[c], e = start[c + 1];
@@ -51,7 +51,7 @@ __global__ void kmeans_update_kernel(const float *__restrict__ X, const uint32_t
     if (j >= dim) return;
     float sum = 0.0f;
     for (int t = b; t < e; t++) sum = __fadd_rn(sum, X[(size_t) members[t] * dim + j]);
-    if (e > b) sum = __fdiv_rn(sum, (float) (e - b));
+    if (e > b && !sums_only) sum = __fdiv_rn(sum, (float) (e - b));
     C[(size_t) c * dim + j] = sum;
 }
 
@@ -144,7 +144,7 @@ int kmeans_assign_dev(KMeansWork &w, const float *dX, int64_t n, int dim, int k,
 }
 
 int kmeans_update_dev(KMeansWork &w, const float *dX, const int *d_assign, int64_t n, int dim, int k, float *dC,
-                      int *d_counts, cudaStream_t s)
+                      int *d_counts, cudaStream_t s, bool sums_only)
 {
     NDB_REQUIRE(n < (int64_t) 0x7fffffff, NDB_B200_EINVAL, "kmeans_update: n too large");
     NDB_CHECK(w.keys_sorted.reserve((size_t) n * 4));
@@ -166,7 +166,7 @@ int kmeans_update_dev(KMeansWork &w, const float *dX, const int *d_assign, int64
     segment_starts_kernel<<<(unsigned) ((n + 1 + 255) / 256), 256, 0, s>>>(w.keys_sorted.as<int>(), n, k, w.start.as<int>());
     count_launch();
     dim3 grid((unsigned) k, (unsigned) ((dim + 127) / 128));
-    kmeans_update_kernel<<<grid, 128, 0, s>>>(dX, w.vals_sorted.as<uint32_t>(), w.start.as<int>(), dim, k, dC, d_counts);
+    kmeans_update_kernel<<<grid, 128, 0, s>>>(dX, w.vals_sorted.as<uint32_t>(), w.start.as<int>(), dim, k, dC, d_counts, sums_only);
     count_launch();
     NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
@@ -264,6 +264,41 @@ int ndb_b200_launch_kmeans_update(const float *X, const int *idx, float *C, int 
     NDB_CHECK(kmeans_update_dev(w, w.X.as<float>(), w.assign.as<int>(), n, d, k, w.C.as<float>(), nullptr, s));
     NDB_CUDA(cudaMemcpyAsync(C, w.C.p, (size_t) k * d * 4, cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaStreamSynchronize(s));
+    return NDB_B200_OK;
+}
+
+// ---- row-sharded training: one Lloyd iteration's local half -----------------------
+// Every rank holds a slice of the rows and all k centroids.  shard_step assigns the local rows
+// (kmeans_assign, :2274-2294) and leaves the per-cluster f32 SUMS (not means) and counts of the
+// local members; the caller all-reduces both (NCCL), divides, and calls shard_cost with the new
+// centroids for its part of kmeans_compute_cost (:2218-2233).  With one rank the sequence is
+// bit-identical to kmeans_train.
+int ndb_b200_kmeans_shard_step_dev(const float *X_dev, int64_t n, int d, int k, const float *C_dev, int *assign_dev,
+                                   float *sums_dev, int *counts_dev, void *stream)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(X_dev && C_dev && assign_dev && sums_dev && counts_dev && n > 0 && d > 0 && k > 0, NDB_B200_EINVAL,
+                "kmeans_shard_step: bad argument");
+    cudaStream_t s = stream ? (cudaStream_t) stream : ctx().stream;
+    static KMeansWork w;                 // scratch kept across iterations
+    NDB_CHECK(w.C.reserve((size_t) k * d * 4));
+    NDB_CUDA(cudaMemcpyAsync(w.C.p, C_dev, (size_t) k * d * 4, cudaMemcpyDeviceToDevice, s));
+    NDB_CHECK(kmeans_assign_dev(w, X_dev, n, d, k, METRIC_L2SQ, assign_dev, s));
+    return kmeans_update_dev(w, X_dev, assign_dev, n, d, k, sums_dev, counts_dev, s, true);
+}
+
+int ndb_b200_kmeans_shard_cost_dev(const float *X_dev, int64_t n, int d, const float *C_dev, const int *assign_dev,
+                                   float *cost_dev, void *stream)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(X_dev && C_dev && assign_dev && cost_dev && n > 0 && d > 0, NDB_B200_EINVAL, "kmeans_shard_cost: bad argument");
+    cudaStream_t s = stream ? (cudaStream_t) stream : ctx().stream;
+    static DevBuf dcost;
+    NDB_CHECK(dcost.reserve((size_t) n * 4));
+    kmeans_sample_cost_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(X_dev, C_dev, assign_dev, n, d, dcost.as<float>());
+    sequential_sum_kernel<<<1, 1024, 0, s>>>(dcost.as<float>(), n, cost_dev);
+    count_launch(2);
+    NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
 }
 

@@ -257,7 +257,8 @@ __device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity)
 constexpr int TC_IDX_BITS = 11;                                  // 16 tiles x 128 columns per half
 constexpr uint32_t TC_IDX_MASK = (1u << TC_IDX_BITS) - 1;
 static_assert(TC_PACKED_MAX_TILES == 1 << (TC_IDX_BITS - 7), "index bits");
-constexpr float TC_KEY_BIG = 1.7e38f;                            // keys at or above: pad rows / empty slots
+constexpr float TC_KEY_BIG = 1.7014118346046923e38f;             // 2^127 (index bits all zero): keys at or above are pad
+                                                                 // rows / empty slots, also once an index is packed in
 constexpr int TC_HEAVY = 6;                                      // passes per 32 columns above which the warp sorts
 
 template <int N> __device__ __forceinline__ void oem_sort(float (&a)[N])     // Batcher odd-even merge sort, ascending

@@ -202,6 +202,6 @@ def test_keys_from_sparse(ndb, orc):
 
 def test_keys_reject_bad_dimensions(ndb):
     with pytest.raises(ndb.NdbError):
-        ndb.keys_from_bits(np.zeros((1, 4097), np.uint8), 32768)
+        ndb.keys_from_bits(np.zeros((1, 4096), np.uint8), 32768)
     with pytest.raises(ndb.NdbError):
         ndb.keys_from_sparse(np.array([0, 0], np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32), 0)

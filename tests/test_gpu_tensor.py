@@ -63,6 +63,7 @@ def test_tensor_knn_within_tolerance(ndb, orc, n, dim, nq, k, metric):
     (3000, 128, 100, 200, 100, 5, 1),     # nprobe > 16: fp32 coarse stage, all lists probed
     (150000, 64, 16, 300, 4, 16, 1),      # long lists -> several segments per list
     (400, 256, 8, 5, 3, 10, 1),           # two K-chunks, tiny lists
+    (300, 64, 32, 50, 16, 10, 1),         # lists shorter than the candidate count: pad rows must never rank
 ])
 def test_tensor_ivf_matches_fp32_path(ndb, orc, n, dim, lists, nq, nprobe, k, metric):
     """arith=TENSOR selects candidates with bf16 products and re-ranks them in fp32: the returned
@@ -104,3 +105,21 @@ def test_tensor_ivf_rejects_what_it_cannot_do(ndb):
         ix2.search(X[:3], 2, 17, ndb.IVF_FULL, ndb.ARITH_TENSOR)      # k > 16
     with pytest.raises(ndb.NdbError):
         ix2.search(X[:3], 2, 10, ndb.IVF_LITERAL, ndb.ARITH_TENSOR)   # literal mode
+
+
+def test_tensor_ivf_on_a_list_shard(ndb, orc):
+    """One rank of a two-rank job (lists l % 2 == 1 only): most probed lists are empty here, the rest
+    short -- the tile padding must stay invisible."""
+    X = bf16_round(W.mixture(30000, 128, 128, 4242))
+    Q = bf16_round(W.mixture(500, 128, 128, 4243, centers_seed=4242))
+    ix = ndb.IvfIndex(128, 256)
+    ix.set_shard(1, 2)
+    ix.ivfbuild(X)
+    ix.ivfinsert(X)
+    # nprobe > 16: both paths take the fp32 coarse stage, hence probe the same lists
+    d0, i0 = ix.search(Q, 20, 10, ndb.IVF_FULL, ndb.ARITH_IVF_F32)
+    d1, i1 = ix.search(Q, 20, 10, ndb.IVF_FULL, ndb.ARITH_TENSOR)
+    assert np.array_equal(i1 < 0, i0 < 0)                   # the same number of results per query
+    same = i0 == i1
+    assert same.mean() >= 0.98
+    assert np.array_equal(d1[same].view(np.uint32), d0[same].view(np.uint32))
