@@ -43,10 +43,12 @@ WORKLOADS = {
 }
 
 
-def make_data(w):
+def make_data(w, qstream=0):
+    """Rows, and 4 batches of queries from the same mixture; qstream picks a different query stream
+    (the replicas of a multi-GPU job each answer their own)."""
     import workloads as W
     X = W.mixture(w["n"], w["dim"], w["comps"], w["seed"])
-    Q = W.mixture(w["nq"] * 4, w["dim"], w["comps"], w["seed"] + 1, centers_seed=w["seed"])
+    Q = W.mixture(w["nq"] * 4, w["dim"], w["comps"], w["seed"] + 1 + 7919 * qstream, centers_seed=w["seed"])
     return X, Q
 
 
@@ -150,7 +152,7 @@ def run_reference(args, w):
     line = {
         "impl": "reference", "metric": "QPS@recall@10>=0.95", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "bf16 select + f32 re-rank" if args.arith == "tensor" else "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["label"], "rows": w["n"], "dim": w["dim"], "lists": w["lists"], "nprobe": w["nprobe"],
                    "k": w["k"], "queries_per_step": sample},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
@@ -173,6 +175,10 @@ def main():
     ap.add_argument("--arith", default="tensor", choices=["ivf_f32", "fast", "tensor"],
                     help="tensor: tcgen05 bf16 candidate selection + fp32 re-rank (default); ivf_f32: the reference's fp32 "
                          "arithmetic end to end, bit-exact distances and ids")
+    ap.add_argument("--shard", default="queries", choices=["queries", "lists"],
+                    help="N > 1: 'queries' = index replicated, every GPU answers its own query batches, no data-path "
+                         "collective (weak scaling); 'lists' = inverted lists split between the GPUs, queries replicated, "
+                         "NCCL all-gather of the per-rank top-k + device merge (strong scaling; the capacity mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -196,10 +202,12 @@ def main():
     ndb.init(local)
     arith = {"ivf_f32": ndb.ARITH_IVF_F32, "fast": ndb.ARITH_FAST, "tensor": ndb.ARITH_TENSOR}[args.arith]
 
-    X, Q = make_data(w)
+    gather = world > 1 and args.shard == "lists"        # lists split between the ranks -> results merged
+    replicas = world if (world > 1 and not gather) else 1
+    X, Q = make_data(w, rank if replicas > 1 else 0)
     nq, k, dim = w["nq"], w["k"], w["dim"]
     ix = ndb.IvfIndex(dim, w["lists"], w["metric"])
-    if world > 1:
+    if gather:
         ix.set_shard(rank, world)
     t0 = time.perf_counter()
     ix.ivfbuild(X)                     # k-means on the first min(10000, lists*100) rows (ivf_am.c:580)
@@ -217,7 +225,8 @@ def main():
     qd = [torch.from_numpy(Q[i * nq:(i + 1) * nq]).cuda() for i in range(4)]
     out_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
     out_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
-    if world > 1:
+    fin_d = fin_i = None
+    if gather:
         all_d = torch.empty((world, nq, k), dtype=torch.float32, device="cuda")
         all_i = torch.empty((world, nq, k), dtype=torch.int64, device="cuda")
         fin_d = torch.empty_like(out_d)
@@ -226,7 +235,7 @@ def main():
     def step(s, arith=arith):
         q = qd[0 if os.environ.get("NDB_BENCH_ONE_BATCH") else s % 4]
         ix.search_dev(q.data_ptr(), nq, out_d.data_ptr(), out_i.data_ptr(), w["nprobe"], k, ndb.IVF_FULL, arith, stream)
-        if world > 1:
+        if gather:
             dist.all_gather_into_tensor(all_d, out_d)
             dist.all_gather_into_tensor(all_i, out_i)
             ndb.check(ndb._lib.load().ndb_b200_merge_topk_dev(ndb.ptr(all_d.data_ptr()), ndb.ptr(all_i.data_ptr()), world,
@@ -261,12 +270,12 @@ def main():
         elapsed_ms = float(t.item())
     clocks = sampler.stop()
     ms_per_step = elapsed_ms / args.steps
-    value = nq / (ms_per_step * 1e-3)
+    value = nq * replicas / (ms_per_step * 1e-3)
 
     # recall@10 of the timed configuration against exact ground truth (first 500 queries of batch 0)
     step(0)
     torch.cuda.synchronize()
-    res_i = (fin_i if world > 1 else out_i)[:500].cpu().numpy()
+    res_i = (fin_i if gather else out_i)[:500].cpu().numpy()
 
     # dominant kernel (scan_topk_kernel): device time from CUDA events recorded by the library on the
     # launching stream, algorithmic bytes = sum over (query, probed list) of len*(dim*4+8)  
@@ -291,7 +300,7 @@ def main():
         q = qh[s % 4]
         ndb.check(lib.ndb_b200_ivf_search(ix.h, ndb.ptr(q.data_ptr()), nq, w["nprobe"], k, ndb.IVF_FULL, arith,
                                           ndb.ptr(hd.data_ptr()), ndb.ptr(hi.data_ptr())))
-        if world > 1:
+        if gather:
             # ranks exchange their host results through the same NCCL path (device staging of 1.2 MB)
             out_d.copy_(hd, non_blocking=True); out_i.copy_(hi, non_blocking=True)
             dist.all_gather_into_tensor(all_d, out_d)
@@ -313,7 +322,7 @@ def main():
         tt = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-    e2e_val = nq / e2e_s
+    e2e_val = nq * replicas / e2e_s
 
     # the same step in the reference's own fp32 arithmetic (bit-exact path), for comparison
     alt = None
@@ -342,8 +351,8 @@ def main():
             alt_ms, alt_e2e = float(tt[0].item()), float(tt[1].item()) * 1e-3
         step(0, a32)
         torch.cuda.synchronize()
-        ref_i = (fin_i if world > 1 else out_i)[:500].cpu().numpy()
-        alt = {"arith": "ivf_f32", "value": nq / (alt_ms * 1e-3), "ms_per_step": alt_ms, "e2e": nq / alt_e2e,
+        ref_i = (fin_i if gather else out_i)[:500].cpu().numpy()
+        alt = {"arith": "ivf_f32", "value": nq * replicas / (alt_ms * 1e-3), "ms_per_step": alt_ms, "e2e": nq * replicas / alt_e2e,
                "unit": "queries/s", "ids_equal_to_tensor_path": float((ref_i == res_i).mean()),
                "note": "the reference's fp32 arithmetic end to end (bit-exact distances and ids vs the oracle)"}
 
@@ -411,16 +420,18 @@ def main():
 
     line = {
         "metric": "QPS@recall@10>=0.95", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if gather else "weak",
         "vs_baseline": None, "dtype": "bf16 select + f32 re-rank" if args.arith == "tensor" else "f32", "data": "synthetic",
         "config": {"workload": w["label"], "rows": w["n"], "dim": dim, "lists": w["lists"], "nprobe": w["nprobe"], "k": k,
-                   "queries_per_step": nq, "arith": args.arith,
+                   "queries_per_step": nq * replicas, "arith": args.arith,
                    "l2": "inputs (%.2f GB of lists) larger than the 126 MB L2; 4 query batches rotate" % (w["n"] * dim * 4 / 1e9),
-                   "parallelism": "lists sharded l %% %d, NCCL all-gather + device merge" % world if world > 1 else "1 GPU"},
+                   "parallelism": ("lists sharded l %% %d, queries replicated, NCCL all-gather + device merge" % world) if gather
+                   else ("index replicated on %d GPUs, each answers its own %d-query batches (no data-path collective)"
+                         % (world, nq)) if world > 1 else "1 GPU"},
         "recall_at_10": recall,
         "alt": alt,
-        "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
-                "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_s * 1e3},
+        "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": nq * replicas * dim * 4,
+                "d2h_bytes_per_step": nq * replicas * k * 12, "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

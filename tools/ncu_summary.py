@@ -2,6 +2,7 @@
 """Summarise ncu output into small text files for profiles/ (the .ncu-rep files are scratch).
 
   ncu_summary.py launches <launches.csv>           -> per-kernel launch count / total time / share
+  ncu_summary.py steps    <launches.csv> <kernel>  -> per-step sequence, a step ending with <kernel>
   ncu_summary.py kernel   <file.ncu-rep> [index]   -> key metrics, stall reasons, SASS opcode mix
 """
 import collections
@@ -19,6 +20,32 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
+
+
+def steps(path, last_kernel):
+    """Per-step view of a launch list: a step is the run of launches that ends with `last_kernel`
+    (e.g. ivf_tc_finish_kernel); prints the mean duration of each position over the steps found."""
+    lines = [l for l in open(path) if not l.startswith("==")]
+    rows = [(re.sub(r"\(.*", "", r["Kernel Name"])[:80], float(r["Metric Value"].replace(",", "")) / 1000.0)
+            for r in csv.DictReader(lines)]
+    ends = [i for i, (n, _) in enumerate(rows) if last_kernel in n]
+    seqs = []
+    for a, b in zip(ends, ends[1:]):
+        seq = rows[a + 1:b + 1]
+        if len(seq) <= 16:
+            seqs.append(seq)
+    if not seqs:
+        print("no steps found")
+        return
+    shape = collections.Counter(tuple(n for n, _ in q) for q in seqs).most_common(1)[0][0]
+    seqs = [q for q in seqs if tuple(n for n, _ in q) == shape]
+    print("# one step = %d launches, mean over %d steps (ncu gpu__time_duration.sum: cold-cache, serialised)" % (len(shape), len(seqs)))
+    tot = 0.0
+    for i, name in enumerate(shape):
+        us = sum(q[i][1] for q in seqs) / len(seqs)
+        tot += us
+        print("%9.1f us  %s" % (us, name))
+    print("%9.1f us  total" % tot)
 
 
 def launches(path):
@@ -76,5 +103,7 @@ def kernel(path, index=0):
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "steps":
+        steps(sys.argv[2], sys.argv[3])
     else:
         kernel(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
