@@ -50,6 +50,8 @@ struct ndb_b200_ivf {
     bool tc_ok = false, ctc_ok = false;
     TcStore tc, ctc;                     // lists, centroids
     TcScratch tcs, ctcs;
+    uint32_t tc_max_nseg = 1;            // longest list, in segments of the tensor scan
+    uint64_t tc_sum_nseg = 0, tc_nonempty = 0;   // over the non-empty lists
     DevBuf tc_src, tc_row, d_ltile8;     // tensor row -> IL32 slot / arena row; first tile of each list (* 8, in 32-row blocks)
     std::vector<uint32_t> row_of_slot;   // IL32 slot -> arena row (host copy, kept for the tensor layout)
 };
@@ -504,6 +506,12 @@ static int ivf_layout(ndb_b200_ivf *ix, cudaStream_t s)
 
 static int ivf_coarse(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np, int arith, cudaStream_t s);
 
+static uint32_t ivf_tc_seg_tiles()
+{
+    static const uint32_t v = [] { const char *e = getenv("NDB_IVF_TC_SEG_TILES"); int x = e ? atoi(e) : 16; return (uint32_t) (x >= 1 && x <= TC_PACKED_MAX_TILES ? x : 16); }();
+    return v;
+}
+
 // blocked bf16 copies for the tensor path: lists (each padded to whole 256-row tiles) and centroids
 static int ivf_tensor_ready(ndb_b200_ivf *ix, cudaStream_t s)
 {
@@ -535,15 +543,20 @@ static int ivf_tensor_ready(ndb_b200_ivf *ix, cudaStream_t s)
     NDB_CHECK(tc_build_store_mapped(ix->tc, ix->store.ptr(), ix->tc_src.as<uint32_t>(), (int64_t) (nt ? nt : 1) * TC_N, ix->dim,
                                     ix->dimp, s));
     NDB_CUDA(cudaStreamSynchronize(s));
+    const uint32_t segb = ivf_tc_seg_tiles() * 8;
+    ix->tc_max_nseg = 1;
+    ix->tc_sum_nseg = ix->tc_nonempty = 0;
+    for (int l = 0; l < L; l++) {
+        if (!ix->list_len[l]) continue;
+        const uint32_t ns = ivf_nseg(ix->list_len[l], segb);
+        ix->tc_max_nseg = std::max(ix->tc_max_nseg, ns);
+        ix->tc_sum_nseg += ns;
+        ix->tc_nonempty++;
+    }
     ix->tc_ok = true;
     return NDB_B200_OK;
 }
 
-static uint32_t ivf_tc_seg_tiles()
-{
-    static const uint32_t v = [] { const char *e = getenv("NDB_IVF_TC_SEG_TILES"); int x = e ? atoi(e) : 16; return (uint32_t) (x >= 1 && x <= TC_PACKED_MAX_TILES ? x : 16); }();
-    return v;
-}
 static int ivf_tc_margin()
 {
     static const int v = [] { const char *e = getenv("NDB_IVF_TC_MARGIN"); int x = e ? atoi(e) : 6; return x >= 0 ? x : 6; }();
@@ -587,22 +600,28 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     ivf_offsets_kernel<<<1, 1024, 0, s>>>(cnt, ix->d_list_len.as<uint32_t>(), ix->d_list_order.as<uint32_t>(), L, TC_M, segb,
                                           (uint32_t) TC_M, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
                                           ix->nitems.as<uint32_t>(), ix->stats.as<unsigned long long>());
-    uint32_t *h_tot = reinterpret_cast<uint32_t *>(ctx().pinned);
-    NDB_CUDA(cudaMemcpyAsync(h_tot, ix->nitems.p, 8, cudaMemcpyDeviceToHost, s));
     count_launch(2);
     NDB_CUDA(cudaGetLastError());
-    NDB_CUDA(cudaStreamSynchronize(s));
-    const size_t n_items = h_tot[0], npos = h_tot[1];
-    if (getenv("NDB_IVF_DEBUG")) fprintf(stderr, "ivf tensor: %zu items, %zu query positions for %lld pairs\n", n_items, npos, (long long) npairs);
-    if (n_items == 0) {
-        // nothing to scan (all probed lists empty)
-        std::vector<float> hd((size_t) nq * k, INFINITY);
-        std::vector<int64_t> hi((size_t) nq * k, -1);
-        NDB_CUDA(cudaMemcpyAsync(dist_dev, hd.data(), hd.size() * 4, cudaMemcpyHostToDevice, s));
-        NDB_CUDA(cudaMemcpyAsync(ids_dev, hi.data(), hi.size() * 8, cudaMemcpyHostToDevice, s));
+    // How many work items and query-tile positions this batch needs depends on how its probes fall on
+    // the lists.  Both have host-side upper bounds (every list with queries wastes < 128 positions;
+    // items <= max_nseg * pairs / 128 + one per segment of a non-empty list); when the buffers those
+    // bounds ask for are affordable the kernels read the exact counts from device memory and the
+    // search needs no host round trip at all.  Otherwise one 8-byte read-back sizes them exactly.
+    size_t n_items = (size_t) ix->tc_max_nseg * (size_t) ((npairs + TC_M - 1) / TC_M) + ix->tc_sum_nseg;
+    size_t npos = (size_t) npairs + (size_t) (TC_M - 1) * std::min<uint64_t>(ix->tc_nonempty, (uint64_t) npairs);
+    npos = (npos + TC_M - 1) / TC_M * TC_M;
+    const bool exact_counts = getenv("NDB_IVF_TC_SYNC") != nullptr ||
+                              n_items * 2 * TC_M * kc * 8 + npos * ix->tc.nkc * TC_KC * 2 > ((size_t) 1 << 30);
+    if (exact_counts) {
+        uint32_t *h_tot = reinterpret_cast<uint32_t *>(ctx().pinned);
+        NDB_CUDA(cudaMemcpyAsync(h_tot, ix->nitems.p, 8, cudaMemcpyDeviceToHost, s));
         NDB_CUDA(cudaStreamSynchronize(s));
-        return NDB_B200_OK;
+        n_items = h_tot[0];
+        npos = h_tot[1];
     }
+    if (getenv("NDB_IVF_DEBUG")) fprintf(stderr, "ivf tensor: %zu items, %zu query positions for %lld pairs (%s)\n", n_items, npos, (long long) npairs, exact_counts ? "exact" : "bounds");
+    if (n_items == 0) n_items = 1;          // (nothing to scan: the kernels see the zero count on the device)
+    if (npos == 0) npos = TC_M;
     NDB_CHECK(ix->qmap.reserve(npos * 4));
     NDB_CUDA(cudaMemsetAsync(ix->qmap.p, 0xFF, npos * 4, s));
     ivf_scatter_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L,
@@ -620,7 +639,7 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     NDB_CHECK(ix->tcs.qb.reserve(npos * nkc * TC_KC * 2));
     NDB_CHECK(ix->tcs.qnorm.reserve(npos * 4));
     NDB_CHECK(tc_block_queries(Q_dev, ix->qmap.as<uint32_t>(), (uint32_t) np, nq, (int) npos, ix->dim, nkc,
-                               ix->tcs.qb.as<__nv_bfloat16>(), ix->tcs.qnorm.as<float>(), s));
+                               ix->tcs.qb.as<__nv_bfloat16>(), ix->tcs.qnorm.as<float>(), s, ix->nitems.as<uint32_t>() + 1));
     const size_t nparts = n_items * 2 * TC_M;
     NDB_CHECK(ix->tcs.pdist.reserve(nparts * kc * 4));
     NDB_CHECK(ix->tcs.pslot.reserve(nparts * kc * 4));
@@ -634,6 +653,7 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     p.k = kc;
     p.items = ix->tcs.items.as<TcItem>();
     p.nitems = (uint32_t) n_items;
+    p.nitems_ptr = ix->nitems.as<uint32_t>();
     p.pdist = ix->tcs.pdist.as<float>();
     p.pslot = ix->tcs.pslot.as<uint32_t>();
     NDB_CHECK(ix->tcs.gthr.reserve((size_t) nq * 4));

@@ -40,6 +40,7 @@ struct TcParams {
     int k;
     const TcItem *items;           // work items
     uint32_t nitems;
+    const uint32_t *nitems_ptr;    // optional: the item count lives on the device (nitems is then only an upper bound)
     float *pdist;                  // partial results, indexed through TcItem::out_base / out_stride
     uint32_t *pslot;
     const uint32_t *qmap;          // optional (list mode): tile position -> (query * nprobe + rank), INVALID_SLOT = empty
@@ -54,8 +55,9 @@ struct TcParams {
 int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s);
 int tc_build_store_mapped(TcStore &st, const float *il32_store, const uint32_t *src_slot_dev, int64_t n, int dim, int dimp,
                           cudaStream_t s);
+// npos_dev (optional): device count of tile positions actually in use (nqpad is then an upper bound)
 int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t nprobe, int nq, int nqpad, int dim, int nkc,
-                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s);
+                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s, const uint32_t *npos_dev = nullptr);
 
 int tc_build_store(TcStore &st, const float *il32_store, int64_t n, int dim, int dimp, cudaStream_t s);
 int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q_dev, int nq, int k, const int64_t *ids,

@@ -106,11 +106,12 @@ __global__ void tc_row_norms_kernel(const float4 *__restrict__ store, const uint
 // row-major fp32 queries -> blocked bf16 query tiles + squared norms
 // qmap (optional): tile position q holds query qmap[q] / nprobe (INVALID_SLOT = empty position)
 __global__ void tc_block_queries_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap, uint32_t nprobe,
-                                        int nq, int nqpad, int dim, int nkc, __nv_bfloat16 *__restrict__ qb,
-                                        float *__restrict__ qnorm)
+                                        int nq, int nqpad, const uint32_t *__restrict__ npos, int dim, int nkc,
+                                        __nv_bfloat16 *__restrict__ qb, float *__restrict__ qnorm)
 {
     const int groups = nkc * (TC_KC / 8);
     const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (npos) nqpad = min(nqpad, (int) *npos);          // whole warps either way: both are multiples of 128
     if (t >= (int64_t) nqpad * groups) return;
     const int q = (int) (t / groups);
     const int g = (int) (t - (int64_t) q * groups);
@@ -323,6 +324,14 @@ __device__ __forceinline__ void atomic_min_f32(float *a, float v)
     else atomicMax(reinterpret_cast<unsigned *>(a), __float_as_uint(v));
 }
 
+// Items are dealt to the persistent CTAs in boustrophedon order: round r goes 0..G-1 when r is even and
+// G-1..0 when odd.  The callers emit items longest first, and a plain round-robin would hand CTA 0 the
+// longest item of every round.
+__device__ __forceinline__ uint32_t tc_item_of(uint32_t round, uint32_t cta, uint32_t ncta)
+{
+    return round * ncta + ((round & 1u) ? ncta - 1u - cta : cta);
+}
+
 template <int KT, int METRIC, bool PACKED>
 __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
 {
@@ -335,7 +344,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
     __shared__ uint32_t tmem_holder;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t nitems = p.nitems;
+    const uint32_t nitems = p.nitems_ptr ? *p.nitems_ptr : p.nitems;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -356,7 +365,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage_it = 0, tile_it = 0, item_it = 0;
-            for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x, item_it++) {
+            for (uint32_t item = tc_item_of(0, blockIdx.x, gridDim.x); item < nitems; item = tc_item_of(++item_it, blockIdx.x, gridDim.x)) {
                 const TcItem it = p.items[item];
                 const uint32_t qt = it.qtile;
                 const uint32_t qb_i = item_it % nqbuf, qn_i = item_it / nqbuf;
@@ -389,7 +398,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
             uint32_t stage_it = 0, tile_it = 0, item_it = 0;
-            for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x, item_it++) {
+            for (uint32_t item = tc_item_of(0, blockIdx.x, gridDim.x); item < nitems; item = tc_item_of(++item_it, blockIdx.x, gridDim.x)) {
                 const TcItem it = p.items[item];
                 const uint32_t t0 = it.t0, t1 = it.t1;
                 const uint32_t qb_i = item_it % nqbuf, qn_i = item_it / nqbuf;
@@ -429,7 +438,8 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
         const int half = (warp - 4) >> 2;
         const uint32_t lane_addr = (uint32_t) ((warp & 3) * 32) << 16;
         uint32_t tile_it = 0;
-        for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+        uint32_t item_it = 0;
+        for (uint32_t item = tc_item_of(0, blockIdx.x, gridDim.x); item < nitems; item = tc_item_of(++item_it, blockIdx.x, gridDim.x)) {
             const TcItem it = p.items[item];
             const uint32_t t0 = it.t0, t1 = it.t1;
             const float qn = p.qnorm[(size_t) it.qtile * TC_M + ql];
@@ -472,12 +482,28 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     if (t + 1 < t1) gnext = *reinterpret_cast<volatile float *>(gcell);
                 }
                 const float *xn = n_smem + (size_t) (tile_it % TC_NORM_RING) * TC_N;
+                // PACKED (short items, latency-bound epilogue): the TMEM read of chunk j + 1 is in flight
+                // while chunk j is processed.  The dense kernel is ALU-bound and keeps the plain order.
+                const int nchunk = (p.debug_mode & 1) ? 0 : TC_N / 64;
+                uint32_t vn[PACKED ? 32 : 1];
+                if (PACKED && nchunk) tmem_ld32(tmem_base + lane_addr + a * TC_N + half * (TC_N / 2), (uint32_t (&)[32]) vn);
 #pragma unroll 1
-                for (int j = 0; j < ((p.debug_mode & 1) ? 0 : TC_N / 64); j++) {
+                for (int j = 0; j < nchunk; j++) {
                     const int col0 = half * (TC_N / 2) + j * 32;
+                    // this chunk's row norms first: their shared-memory latency overlaps the TMEM wait
+                    float4 n4s[8];
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; i4++) n4s[i4] = *reinterpret_cast<const float4 *>(xn + col0 + 4 * i4);
                     uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_addr + a * TC_N + col0, v);
-                    tmem_ld_wait();
+                    if (PACKED) {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; i++) v[i] = vn[PACKED ? i : 0];
+                        if (j + 1 < nchunk) tmem_ld32(tmem_base + lane_addr + a * TC_N + col0 + 32, (uint32_t (&)[32]) vn);
+                    } else {
+                        tmem_ld32(tmem_base + lane_addr + a * TC_N + col0, v);
+                        tmem_ld_wait();
+                    }
                     if (p.debug_d && item == 0 && t == t0) {   // first item's first tile
 #pragma unroll
                         for (int i = 0; i < 32; i++) p.debug_d[(size_t) ql * TC_N + col0 + i] = __uint_as_float(v[i]);
@@ -487,7 +513,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     float c[32];
 #pragma unroll
                     for (int i4 = 0; i4 < 8; i4++) {
-                        const float4 n4 = *reinterpret_cast<const float4 *>(xn + col0 + 4 * i4);
+                        const float4 n4 = n4s[i4];
                         if (METRIC == NDB_L2) {
                             c[4 * i4 + 0] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 0]), n4.x);
                             c[4 * i4 + 1] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 1]), n4.y);
@@ -630,11 +656,11 @@ int tc_build_store_mapped(TcStore &st, const float *il32_store, const uint32_t *
 
 // blocked bf16 query tiles + squared norms; qmap_dev (optional) gathers the tile positions
 int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t nprobe, int nq, int nqpad, int dim, int nkc,
-                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s)
+                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s, const uint32_t *npos_dev)
 {
     const int groups = nkc * (TC_KC / 8);
-    tc_block_queries_kernel<<<(unsigned) (((int64_t) nqpad * groups + 255) / 256), 256, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, dim,
-                                                                                                nkc, qb, qnorm);
+    tc_block_queries_kernel<<<(unsigned) (((int64_t) nqpad * groups + 255) / 256), 256, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev,
+                                                                                                dim, nkc, qb, qnorm);
     count_launch();
     NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
@@ -648,7 +674,7 @@ int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s)
     if (p.nitems == 0) return NDB_B200_OK;
     const size_t smem = tc_smem_bytes();
     const uint32_t sms = (uint32_t) ctx().sm_count;
-    const uint32_t grid = p.nitems < sms ? p.nitems : sms;
+    const uint32_t grid = (p.nitems < sms && !p.nitems_ptr) ? p.nitems : sms;
     Context &c = ctx();
     if (c.timing) NDB_CUDA(cudaEventRecord(c.ev0, s));
     // list length: the smallest of {1, 10, 16} that holds k (a shorter list = a tighter threshold)
