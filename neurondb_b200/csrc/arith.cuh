@@ -204,6 +204,22 @@ template <class KeyT> struct KeyMax;
 template <> struct KeyMax<uint32_t> { static constexpr uint32_t v = 0xffffffffu; };
 template <> struct KeyMax<int64_t> { static constexpr int64_t v = 0x7fffffffffffffffll; };
 
+// full 32-lane bitonic sort, ascending by (d, key): 15 shuffle stages
+template <class KeyT> __device__ __forceinline__ void warp_sort32(float &d, KeyT &key, int lane)
+{
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            const float pd = __shfl_xor_sync(FULL, d, j);
+            const KeyT pk = shfl_xor_key<KeyT>(key, j);
+            const bool want_min = ((lane & j) == 0) == ((lane & kk) == 0);
+            const bool take = want_min ? pair_less<KeyT>(pd, pk, d, key) : pair_less<KeyT>(d, key, pd, pk);
+            if (take) { d = pd; key = pk; }
+        }
+    }
+}
+
 template <int KR, class KeyT> struct WarpTopK {
     float d[KR];
     KeyT key[KR];

@@ -596,17 +596,7 @@ __global__ void merge_parts32_kernel(const float *pdist, const uint32_t *pslot, 
             key = ids ? (KeyT) ids[s] : (KeyT) s;
         }
     }
-#pragma unroll
-    for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            const float pd = __shfl_xor_sync(FULL, d, j);
-            const KeyT pk = shfl_xor_key<KeyT>(key, j);
-            const bool want_min = ((lane & j) == 0) == ((lane & kk) == 0 || kk == 32);
-            const bool take = want_min ? pair_less<KeyT>(pd, pk, d, key) : pair_less<KeyT>(d, key, pd, pk);
-            if (take) { d = pd; key = pk; }
-        }
-    }
+    warp_sort32<KeyT>(d, key, lane);
     if (lane < k) {
         const bool have = key != KeyMax<KeyT>::v;
         out_dist[(size_t) q * k + lane] = have ? d : INFINITY;
