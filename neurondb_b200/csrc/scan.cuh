@@ -6,20 +6,23 @@
 //   * ivfinsert / kmeans_assign: rows x centroids, k = 1 (:906-935, :2164-2177)    dense mode
 //   * ivfCollectCandidates: (query, probed list) pairs grouped by list (:1722-1909)  list mode
 //
-// Work item = (a run of 32-vector blocks, a tile of NW*QT queries).  A persistent CTA of NW
-// warps takes an item from an atomic counter.  The blocks of the run are staged into shared
-// memory by TMA bulk copies (cp.async.bulk + mbarrier, SCAN_STAGES-deep ring of 16 KB stages:
-// an IL32 block is one contiguous run of bytes, so a stage is a single bulk copy) issued by one
-// elected thread; every warp consumes every stage.  Warp w owns queries [w*QT, (w+1)*QT) of the
-// tile: lane l owns vector l of the staged block and walks its dimensions in order with QT
-// accumulators -- the query tile sits in shared memory and is read with broadcast LDS.128 -- so
-// every distance is produced by exactly the reference's sequential loop (see arith.cuh) while
-// each stored vector is fetched from HBM/L2 once per NW*QT queries.  No distance matrix is
-// written: each warp keeps a sorted top-k per query in registers (WarpTopK), filters new
-// distances against the k-th best with one ballot, and falls back to a shuffle bitonic merge
-// when many lanes pass.  Because a warp sees the whole run for its queries there is no
-// cross-warp merge; the warp writes k (dist, slot) pairs per (query, item-part).  A second small
-// kernel merges the parts per query by (dist, id).
+// Work item = (a run of 32-vector blocks, a tile of NW*QT queries).  A persistent CTA takes items
+// from an atomic counter.  Lane l owns vector l of a block and walks its dimensions in order with
+// QT accumulators -- the query tile sits in shared memory and is read with broadcast LDS.128 -- so
+// every distance is produced by exactly the reference's sequential loop (see arith.cuh) while each
+// stored vector is fetched from HBM/L2 once per NW*QT queries.  The queries of a tile are dealt to
+// the warps round-robin and every warp sees the whole run for its queries, so there is no
+// cross-warp merge.  No distance matrix is written: a warp keeps a sorted top-k per query in
+// registers (WarpTopK), filters new distances against the k-th best with one ballot, and falls
+// back to a shuffle bitonic merge when many lanes pass; it writes k (dist, slot) pairs per
+// (query, item-part), and a second small kernel merges the parts per query by (dist, id).
+//
+// Two ways of bringing the blocks in (profiles/r01_scan_variants.txt):
+//   * scan_topk_kernel (list mode): a dedicated producer warp issues TMA bulk copies
+//     (cp.async.bulk + mbarrier; an IL32 block is one contiguous run of bytes, so a 16 KB stage is
+//     a single copy) into a SCAN_STAGES-deep ring with full/empty barriers; NW consumer warps.
+//   * scan_topk_direct_kernel (dense mode): every warp streams the run itself with coalesced
+//     LDG.128 (512-byte warp loads); the warps never wait for each other.
 #pragma once
 #include "arith.cuh"
 

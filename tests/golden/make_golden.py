@@ -69,6 +69,16 @@ def main():
     d, i = O.knn_exact(X, Q, 10, 1, O.ARITH_OP_F64)
     idx.update(knn_d=d, knn_i=i)
     np.savez_compressed(os.path.join(HERE, "index_paths.npz"), **idx)
+
+    # key extraction: the reference's own fp16_to_float (oracle/_ref/libndb_ref_fp16.so, cut out of
+    # src/types/quantization.c by oracle/Makefile) on every binary16 pattern, as float32 bit patterns
+    ref16 = O.ref_fp16_lib()
+    assert ref16 is not None, "build oracle/_ref first (make -C oracle)"
+    import ctypes as C
+    ref16.fp16_to_float.restype = C.c_uint32          # read the float's bits back untouched (keeps NaN payloads)
+    table = np.array([ref16.fp16_to_float(h) for h in range(65536)], np.uint32)
+    ref16.fp16_to_float.restype = C.c_float
+    np.savez_compressed(os.path.join(HERE, "fp16_table.npz"), bits=table)
     print("wrote", sorted(os.listdir(HERE)))
 
 

@@ -1,4 +1,6 @@
 """GPU parity: operator distances, exact kNN, k-means, through the C ABI, against the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -174,6 +176,8 @@ def test_keys_from_halfvec_every_half_bit_exact(ndb, orc):
     got = ndb.keys_from_halfvec(h)
     want = orc.keys_from_halfvec(h)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "fp16_table.npz"))["bits"]
+    assert np.array_equal(got.view(np.uint32).reshape(-1), golden)          # the reference's own table
 
 
 @pytest.mark.parametrize("n,nbits", [(1, 1), (33, 19), (500, 128), (3, 32767)])
