@@ -235,6 +235,6 @@ def test_bit_and_sparse_keys():
 def test_fp16_restatement_equals_golden_table():
     """tests/golden/fp16_table.npz holds the reference's fp16_to_float on all 65 536 halves (float32 bit
     patterns, NaN payloads included), generated by tests/golden/make_golden.py."""
-    want = np.load(os.path.join(GOLDEN, "fp16_table.npz"))["bits"]
+    want = np.load(os.path.join(HERE, "golden", "fp16_table.npz"))["bits"]
     got = O.keys_from_halfvec(np.arange(65536, dtype=np.uint16).reshape(1, -1))[0].view(np.uint32)
     assert np.array_equal(got, want)
