@@ -184,6 +184,15 @@ int ndb_b200_ivf_search(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, in
                         int arith, float *dist, int64_t *ids);
 int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int nprobe, int k, int mode,
                             int arith, float *dist_dev, int64_t *ids_dev, void *stream);
+/* Pipelined form of ndb_b200_ivf_search for a stream of batches (a scan feeding executor batches):
+ * begin queues one batch and returns a ticket, end(ticket) blocks until that batch's dist / ids are
+ * filled.  Up to two batches per index may be in flight; the copies of neighbouring batches run on
+ * their own streams and overlap the kernels, which still run one batch at a time.  Q, dist and ids
+ * must stay valid until end (pinned memory makes the copies true DMA).  A third begin without an end
+ * -> NDB_B200_ESTATE; a NaN/Inf query is reported by end (NDB_B200_EVECTOR). */
+int ndb_b200_ivf_search_begin(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, int k, int mode,
+                              int arith, float *dist, int64_t *ids, int *ticket);
+int ndb_b200_ivf_search_end(ndb_b200_ivf *ix, int ticket);
 /* ivfSelectClusters alone: probe lists per query, nq*nprobe ints, -1 = none (:1597-1717) */
 int ndb_b200_ivf_select_clusters(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, int *probes);
 /* multi-GPU: keep only the lists l with l % world == rank (lists partition across ranks,
@@ -232,6 +241,9 @@ int ndb_b200_merge_topk(const float *dist, const int64_t *ids, int nshards, int 
  * (hnsw_am.c:1402-1519).  The access methods accept vector, halfvec, sparsevec and bit columns and
  * turn every key into float4[dim] first; these do it for a batch of n keys, writing n rows of dim
  * floats (row-major) that dataset_append / ivf_insert / hnsw_build take as they are.
+ *   vector    : n detoasted Vector datums laid end to end (struct Vector, neurondb.h:35-41: int32
+ *               vl_len_, int16 dim, int16 unused, float4 data[dim] = 8 + 4*dim bytes each); a datum
+ *               of another dimension -> NDB_B200_EDIM (check_dimensions, vector_distance.c:55-73)
  *   halfvec   : n*dim IEEE binary16 values (VectorF16.data, neurondb.h:44-49) through
  *               fp16_to_float (src/types/quantization.c:171-215): IEEE for zeros, normals, Inf and
  *               NaN; subnormal halves come out 2^-10 times their IEEE value, as in the reference
@@ -240,6 +252,7 @@ int ndb_b200_merge_topk(const float *dist, const int64_t *ids, int nshards, int 
  *               indices/values [indptr[r], indptr[r+1]); zero fill, entries applied in order (a
  *               repeated index keeps the last value), indices outside [0,total_dim) ignored
  * dim / nbits / total_dim must be 1..32767 (the reference's check), else NDB_B200_EINVAL. */
+int ndb_b200_keys_from_vector(const void *datums, int64_t n, int dim, float *rows);
 int ndb_b200_keys_from_halfvec(const uint16_t *h, int64_t n, int dim, float *rows);
 int ndb_b200_keys_from_halfvec_dev(const uint16_t *h_dev, int64_t n, int dim, float *rows_dev, void *stream);
 int ndb_b200_keys_from_bits(const uint8_t *bits, int64_t n, int nbits, float *rows);

@@ -95,6 +95,9 @@ SIGNATURES = {
     "ndb_b200_merge_topk": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "ndb_b200_kmeans_shard_step_dev": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p]),
     "ndb_b200_kmeans_shard_cost_dev": (_i, [_p, _i64, _i, _p, _p, _p, _p]),
+    "ndb_b200_ivf_search_begin": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "ndb_b200_ivf_search_end": (_i, [_p, _i]),
+    "ndb_b200_keys_from_vector": (_i, [_p, _i64, _i, _p]),
     "ndb_b200_keys_from_halfvec": (_i, [_p, _i64, _i, _p]),
     "ndb_b200_keys_from_halfvec_dev": (_i, [_p, _i64, _i, _p, _p]),
     "ndb_b200_keys_from_bits": (_i, [_p, _i64, _i, _p]),

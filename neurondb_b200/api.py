@@ -127,6 +127,18 @@ def merge_topk(dist, ids):
     return od, oi
 
 
+def keys_from_vector(datums, dim):
+    """Detoasted `vector` datums (bytes: n x (8-byte varlena header + 4*dim)) -> float32 rows."""
+    buf = np.frombuffer(datums, np.uint8) if not isinstance(datums, np.ndarray) else np.ascontiguousarray(datums, np.uint8).reshape(-1)
+    stride = 8 + 4 * dim
+    if buf.size % stride:
+        raise ValueError("datums must be a whole number of %d-byte Vector values" % stride)
+    n = buf.size // stride
+    out = np.empty((n, dim), np.float32)
+    check(L.load().ndb_b200_keys_from_vector(ptr(buf), n, dim, ptr(out)))
+    return out
+
+
 def keys_from_halfvec(h):
     """halfvec keys (uint16 IEEE binary16 bit patterns, [n, dim]) -> float32 rows (hnsw_am.c:1435-1450)."""
     h = np.ascontiguousarray(h, np.uint16)
@@ -274,6 +286,17 @@ class IvfIndex(_Handle):
         i = np.empty((Q.shape[0], k), np.int64)
         check(L.load().ndb_b200_ivf_search(self.h, ptr(Q), Q.shape[0], nprobe, k, mode, arith, ptr(d), ptr(i)))
         return d, i
+
+    def search_begin(self, Q, dist, ids, nprobe=10, k=10, mode=IVF_FULL, arith=ARITH_IVF_F32):
+        """Queue one batch (Q [nq, dim] float32, dist [nq, k] float32, ids [nq, k] int64: numpy arrays the
+        caller keeps alive, ideally pinned); returns a ticket for search_end.  Two batches may be in flight."""
+        t = C.c_int(-1)
+        check(L.load().ndb_b200_ivf_search_begin(self.h, ptr(Q), Q.shape[0], nprobe, k, mode, arith, ptr(dist), ptr(ids),
+                                                 C.byref(t)))
+        return t.value
+
+    def search_end(self, ticket):
+        check(L.load().ndb_b200_ivf_search_end(self.h, ticket))
 
     def search_dev(self, q_ptr, nq, dist_ptr, ids_ptr, nprobe=10, k=10, mode=IVF_FULL, arith=ARITH_IVF_F32,
                    stream=None):

@@ -51,6 +51,7 @@ struct Context {
     int sm_count = 148;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;        // library stream for host-pointer entry points
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy streams of the pipelined (begin/end) entry points
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false;
     double last_ms = 0.0, last_bytes = 0.0;
@@ -151,6 +152,8 @@ int64_t find_nonfinite(const float *v, int64_t n);
 // stream synchronisation and returns the first offending index or -1.  Keeps the 5 MB-per-batch
 // host scan out of the end-to-end path.
 int validate_begin(const float *v_dev, int64_t n, cudaStream_t s);
+// the same scan into a caller-owned device cell (pre-set to all ones): first offending index
+int validate_into(const float *v_dev, int64_t n, unsigned long long *cell_dev, cudaStream_t s);
 int64_t validate_end();
 
 }  // namespace ndb

@@ -79,6 +79,17 @@ int validate_begin(const float *v_dev, int64_t n, cudaStream_t s)
     return NDB_B200_OK;
 }
 
+int validate_into(const float *v_dev, int64_t n, unsigned long long *cell_dev, cudaStream_t s)
+{
+    Context &c = ctx();
+    NDB_CUDA(cudaMemsetAsync(cell_dev, 0xFF, 8, s));
+    const int64_t blocks = (n + 255) / 256;
+    nonfinite_kernel<<<(unsigned) (blocks < 4 * c.sm_count ? blocks : 4 * c.sm_count), 256, 0, s>>>(v_dev, n, cell_dev);
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
+}
+
 int64_t validate_end()
 {
     const unsigned long long v = *reinterpret_cast<unsigned long long *>(static_cast<char *>(ctx().pinned) + 256);
@@ -263,6 +274,8 @@ int ndb_b200_init(int device)
     g_ctx.sm_count = prop.multiProcessorCount;
     g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
     NDB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    NDB_CUDA(cudaStreamCreateWithFlags(&g_ctx.h2d_stream, cudaStreamNonBlocking));
+    NDB_CUDA(cudaStreamCreateWithFlags(&g_ctx.d2h_stream, cudaStreamNonBlocking));
     NDB_CUDA(cudaEventCreate(&g_ctx.ev0));
     NDB_CUDA(cudaEventCreate(&g_ctx.ev1));
     g_ctx.pinned_bytes = 1 << 20;
@@ -284,6 +297,8 @@ void ndb_b200_shutdown(void)
     if (g_ctx.ev0) cudaEventDestroy(g_ctx.ev0);
     if (g_ctx.ev1) cudaEventDestroy(g_ctx.ev1);
     if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    if (g_ctx.h2d_stream) cudaStreamDestroy(g_ctx.h2d_stream);
+    if (g_ctx.d2h_stream) cudaStreamDestroy(g_ctx.d2h_stream);
     g_ctx = Context();
 }
 

@@ -46,6 +46,22 @@ struct ndb_b200_ivf {
     DevBuf probe, cnt, fill, qoff, item_off, qmap, pairpos, items, nitems, stats, tmp_rows, tmp_assign, tmp_keep;
     DevBuf qbuf, outd, outi, cdist;
     int64_t last_scanned = 0;
+    // pipelined searches (search_begin / search_end): two batches in flight, each with its own staging
+    struct Slot {
+        DevBuf q, d, i, bad;
+        cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
+        unsigned long long *h_bad = nullptr;      // pinned
+        bool busy = false;
+    } slot[2];
+    ~ndb_b200_ivf()
+    {
+        for (Slot &sl : slot) {
+            if (sl.h2d) cudaEventDestroy(sl.h2d);
+            if (sl.done) cudaEventDestroy(sl.done);
+            if (sl.d2h) cudaEventDestroy(sl.d2h);
+            if (sl.h_bad) cudaFreeHost(sl.h_bad);
+        }
+    }
     // tensor-core copy (NDB_ARITH_TENSOR): every list padded to whole 256-row tiles of blocked bf16
     bool tc_ok = false, ctc_ok = false;
     TcStore tc, ctc;                     // lists, centroids
@@ -828,7 +844,11 @@ int ndb_b200_ivf_create(int dim, int nlists, int metric, ndb_b200_ivf **out)
 void ndb_b200_ivf_free(ndb_b200_ivf *ix)
 {
     if (!ix) return;
-    if (ctx().initialized) { cudaSetDevice(ctx().device); cudaStreamSynchronize(ctx().stream); }
+    if (ctx().initialized) {
+        cudaSetDevice(ctx().device);
+        cudaStreamSynchronize(ctx().stream);
+        cudaStreamSynchronize(ctx().d2h_stream);
+    }
     delete ix;
 }
 
@@ -1129,6 +1149,61 @@ int ndb_b200_ivf_search(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, in
     NDB_CUDA(cudaMemcpyAsync(ids, ix->outi.p, m * 8, cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaStreamSynchronize(s));
     NDB_REQUIRE(validate_end() < 0, NDB_B200_EVECTOR, "ivf_search: NaN/Inf in query");
+    return NDB_B200_OK;
+}
+
+// ---- pipelined form ----------------------------------------------------------------------------
+// search_begin queues one batch and returns; search_end blocks until that batch's results are in the
+// caller's buffers.  Up to two batches per index may be in flight: the H2D copy of batch i+1 (its own
+// stream) and the D2H copy of batch i-1 (another) overlap the kernels of batch i, which still run one
+// batch at a time on the library stream (the index's scratch belongs to one search at a time).
+// Q, dist and ids must stay valid until search_end; pinned buffers make the copies true DMA.
+int ndb_b200_ivf_search_begin(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, int k, int mode, int arith, float *dist,
+                              int64_t *ids, int *ticket)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix && Q && dist && ids && ticket && nq > 0, NDB_B200_EINVAL, "ivf_search_begin: NULL or empty input");
+    int t = -1;
+    for (int i = 0; i < 2; i++) if (!ix->slot[i].busy) { t = i; break; }
+    NDB_REQUIRE(t >= 0, NDB_B200_ESTATE, "ivf_search_begin: two batches already in flight (call ivf_search_end first)");
+    ndb_b200_ivf::Slot &sl = ix->slot[t];
+    Context &c = ctx();
+    if (!sl.h2d) {
+        NDB_CUDA(cudaEventCreateWithFlags(&sl.h2d, cudaEventDisableTiming));
+        NDB_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        NDB_CUDA(cudaEventCreateWithFlags(&sl.d2h, cudaEventDisableTiming));
+        NDB_CUDA(cudaMallocHost(&sl.h_bad, 8));
+        NDB_CHECK(sl.bad.reserve(8));
+    }
+    const size_t qb = (size_t) nq * ix->dim * 4, m = (size_t) nq * k;
+    NDB_CHECK(sl.q.reserve(qb));
+    NDB_CHECK(sl.d.reserve(m * 4));
+    NDB_CHECK(sl.i.reserve(m * 8));
+    *sl.h_bad = ~0ull;
+    NDB_CUDA(cudaMemcpyAsync(sl.q.p, Q, qb, cudaMemcpyHostToDevice, c.h2d_stream));
+    NDB_CUDA(cudaEventRecord(sl.h2d, c.h2d_stream));
+    NDB_CUDA(cudaStreamWaitEvent(c.stream, sl.h2d, 0));
+    NDB_CHECK(validate_into(sl.q.as<float>(), (int64_t) nq * ix->dim, sl.bad.as<unsigned long long>(), c.stream));
+    NDB_CHECK(ndb_b200_ivf_search_dev(ix, sl.q.as<float>(), nq, nprobe, k, mode, arith, sl.d.as<float>(), sl.i.as<int64_t>(), c.stream));
+    NDB_CUDA(cudaEventRecord(sl.done, c.stream));
+    NDB_CUDA(cudaStreamWaitEvent(c.d2h_stream, sl.done, 0));
+    NDB_CUDA(cudaMemcpyAsync(dist, sl.d.p, m * 4, cudaMemcpyDeviceToHost, c.d2h_stream));
+    NDB_CUDA(cudaMemcpyAsync(ids, sl.i.p, m * 8, cudaMemcpyDeviceToHost, c.d2h_stream));
+    NDB_CUDA(cudaMemcpyAsync(sl.h_bad, sl.bad.p, 8, cudaMemcpyDeviceToHost, c.d2h_stream));
+    NDB_CUDA(cudaEventRecord(sl.d2h, c.d2h_stream));
+    sl.busy = true;
+    *ticket = t;
+    return NDB_B200_OK;
+}
+
+int ndb_b200_ivf_search_end(ndb_b200_ivf *ix, int ticket)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix && ticket >= 0 && ticket < 2 && ix->slot[ticket].busy, NDB_B200_EINVAL, "ivf_search_end: no such batch in flight");
+    ndb_b200_ivf::Slot &sl = ix->slot[ticket];
+    sl.busy = false;
+    NDB_CUDA(cudaEventSynchronize(sl.d2h));
+    NDB_REQUIRE(*sl.h_bad == ~0ull, NDB_B200_EVECTOR, "ivf_search: NaN/Inf in query");
     return NDB_B200_OK;
 }
 

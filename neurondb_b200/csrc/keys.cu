@@ -1,7 +1,8 @@
 // keys.cu -- index key extraction: the access methods turn whatever the indexed
 // column holds into float4[dim] before anything else happens (ivfExtractVectorData, ivf_am.c:117-218;
 // hnswExtractVectorData, hnsw_am.c:1402-1519):
-//   vector     -> copied
+//   vector     -> copied out of the varlena (struct Vector, neurondb.h:35-41: int32 vl_len_, int16 dim,
+//                 int16 unused, float4 data[dim]); a datum whose dim differs is an error
 //   halfvec    -> fp16_to_float per element (src/types/quantization.c:171-215; IEEE except that
 //                 subnormal halves come out 2^-10 too small -- the reference's result is kept)
 //   sparsevec  -> zero-filled row, result[indices[i]] = values[i] in entry order, out-of-range
@@ -61,6 +62,22 @@ __global__ void keys_sparse_kernel(const int64_t *__restrict__ indptr, const int
     }
 }
 
+// detoasted Vector datums laid end to end, each 8 + 4 * dim bytes; bad[0] = first datum whose header
+// disagrees with dim (or ~0)
+__global__ void keys_vector_kernel(const unsigned char *__restrict__ datums, int64_t n, int dim, float *__restrict__ out,
+                                   unsigned long long *__restrict__ bad)
+{
+    const int64_t total = n * dim;
+    const size_t stride = 8 + (size_t) dim * 4;
+    for (int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t) gridDim.x * blockDim.x) {
+        const int64_t r = t / dim;
+        const int j = (int) (t - r * dim);
+        const unsigned char *d = datums + (size_t) r * stride;
+        if (j == 0 && *reinterpret_cast<const int16_t *>(d + 4) != (int16_t) dim) atomicMin(bad, (unsigned long long) r);
+        out[t] = *reinterpret_cast<const float *>(d + 8 + (size_t) j * 4);
+    }
+}
+
 static unsigned grid_for(int64_t total)
 {
     const int64_t b = (total + 255) / 256, cap = (int64_t) ctx().sm_count * 16;
@@ -91,6 +108,27 @@ template <class F> static int staged(const void *in, size_t in_bytes, float *row
 using namespace ndb;
 
 extern "C" {
+
+int ndb_b200_keys_from_vector(const void *datums, int64_t n, int dim, float *rows)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(datums && rows && n >= 0, NDB_B200_EINVAL, "keys_from_vector: bad argument");
+    NDB_REQUIRE(dim > 0 && dim <= 32767, NDB_B200_EINVAL, "invalid vector dimension %d", dim);
+    if (n == 0) return NDB_B200_OK;
+    unsigned long long first_bad = ~0ull;
+    int rc = staged(datums, (size_t) n * (8 + (size_t) dim * 4), rows, (size_t) n * dim, [&](void *din, float *dout, cudaStream_t s) {
+        Context &c = ctx();
+        NDB_CUDA(cudaMemsetAsync(c.d_badidx, 0xFF, 8, s));
+        keys_vector_kernel<<<grid_for(n * dim), 256, 0, s>>>(static_cast<const unsigned char *>(din), n, dim, dout, c.d_badidx);
+        count_launch();
+        NDB_CUDA(cudaGetLastError());
+        NDB_CUDA(cudaMemcpyAsync(&first_bad, c.d_badidx, 8, cudaMemcpyDeviceToHost, s));
+        return (int) NDB_B200_OK;
+    });
+    NDB_CHECK(rc);
+    NDB_REQUIRE(first_bad == ~0ull, NDB_B200_EDIM, "vector dimensions must match: datum %llu is not of dimension %d", first_bad, dim);
+    return NDB_B200_OK;
+}
 
 int ndb_b200_keys_from_halfvec_dev(const uint16_t *h_dev, int64_t n, int dim, float *rows_dev, void *stream)
 {

@@ -209,3 +209,19 @@ def test_keys_reject_bad_dimensions(ndb):
         ndb.keys_from_bits(np.zeros((1, 4096), np.uint8), 32768)
     with pytest.raises(ndb.NdbError):
         ndb.keys_from_sparse(np.array([0, 0], np.int64), np.zeros(0, np.int32), np.zeros(0, np.float32), 0)
+
+
+def test_keys_from_vector_datums(ndb):
+    """struct Vector (neurondb.h:35-41): int32 vl_len_ (4-byte varlena header: size << 2), int16 dim, int16 unused, data."""
+    rng = np.random.default_rng(8)
+    n, dim = 37, 20
+    X = rng.standard_normal((n, dim)).astype(np.float32)
+    hdr = np.zeros((n, 2), np.int32)
+    hdr[:, 0] = (8 + 4 * dim) << 2
+    hdr[:, 1] = dim                                   # int16 dim | int16 unused (little endian)
+    datums = np.concatenate([hdr.view(np.uint8).reshape(n, 8), X.view(np.uint8).reshape(n, 4 * dim)], axis=1)
+    assert np.array_equal(ndb.keys_from_vector(datums, dim), X)
+    datums[5, 4] = dim + 1                            # a datum of another dimension
+    with pytest.raises(ndb.NdbError) as e:
+        ndb.keys_from_vector(datums, dim)
+    assert "datum 5" in str(e.value)

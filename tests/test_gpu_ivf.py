@@ -109,3 +109,38 @@ def test_ivf_config2_shape_recall(ndb, orc):
     df, i_f = ix.search(Q, nprobe, 10, arith=ndb.ARITH_FAST)
     assert orc.recall_at_k(i_f, gt) >= recall - 0.002
     assert np.max(np.abs(df - d) / np.maximum(d, 1e-6)) < 1e-5
+
+
+def test_pipelined_search_equals_synchronous(ndb):
+    """ndb_b200_ivf_search_begin / _end: two batches in flight return what the synchronous call returns."""
+    X = W.mixture(20000, 32, 64, 91)
+    ix = ndb.IvfIndex(32, 64)
+    ix.ivfbuild(X)
+    ix.ivfinsert(X)
+    batches = [np.ascontiguousarray(W.mixture(300, 32, 64, 92 + b, centers_seed=91)) for b in range(5)]
+    want = [ix.search(Q, 8, 10) for Q in batches]
+    for arith in (ndb.ARITH_IVF_F32, ndb.ARITH_TENSOR):
+        ref = want if arith == ndb.ARITH_IVF_F32 else [ix.search(Q, 8, 10, ndb.IVF_FULL, arith) for Q in batches]
+        outs = [(np.empty((300, 10), np.float32), np.empty((300, 10), np.int64)) for _ in batches]
+        prev = None
+        for b, Q in enumerate(batches):
+            t = ix.search_begin(Q, outs[b][0], outs[b][1], 8, 10, ndb.IVF_FULL, arith)
+            if prev is not None:
+                ix.search_end(prev)
+            prev = t
+        ix.search_end(prev)
+        for (d, i), (wd, wi) in zip(outs, ref):
+            assert np.array_equal(i, wi) and np.array_equal(d.view(np.uint32), wd.view(np.uint32))
+    # a third batch without an end is refused; a NaN query is reported by end
+    o = [(np.empty((300, 10), np.float32), np.empty((300, 10), np.int64)) for _ in range(3)]
+    t0 = ix.search_begin(batches[0], o[0][0], o[0][1], 8, 10)
+    t1 = ix.search_begin(batches[1], o[1][0], o[1][1], 8, 10)
+    with pytest.raises(ndb.NdbError):
+        ix.search_begin(batches[2], o[2][0], o[2][1], 8, 10)
+    ix.search_end(t0)
+    ix.search_end(t1)
+    bad = batches[0].copy()
+    bad[7, 3] = np.nan
+    t = ix.search_begin(bad, o[0][0], o[0][1], 8, 10)
+    with pytest.raises(ndb.NdbError):
+        ix.search_end(t)
