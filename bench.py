@@ -388,8 +388,9 @@ def main():
 
     peaks, peak_kind = measured_peaks()
     import workloads as W
-    gt = W.exact_ground_truth(X, Q[:500], k)
-    recall = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(res_i, gt)]))
+    ngt = 500 if w["n"] <= 2_000_000 else 100
+    gt = W.exact_ground_truth(X, Q[:ngt], k, w["metric"])
+    recall = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(res_i[:ngt], gt)]))
 
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")

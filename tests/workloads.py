@@ -22,16 +22,25 @@ def normalised(n, dim, seed):
     return np.ascontiguousarray(X, dtype=np.float32)
 
 
-def exact_ground_truth(X, Q, k):
-    """fp64 exact kNN ids by L2 with (dist, id) ties -- numpy, for recall only."""
-    X64 = X.astype(np.float64)
-    out = np.empty((Q.shape[0], k), np.int64)
-    xn = (X64 * X64).sum(1)
-    for s in range(0, Q.shape[0], 256):
-        q = Q[s:s + 256].astype(np.float64)
-        d = xn[None, :] - 2.0 * q @ X64.T + (q * q).sum(1)[:, None]
-        idx = np.argpartition(d, k, axis=1)[:, :k]
-        dd = np.take_along_axis(d, idx, 1)
-        order = np.lexsort((idx, dd), axis=1)
-        out[s:s + 256] = np.take_along_axis(idx, order, 1)
-    return out
+def exact_ground_truth(X, Q, k, metric=1):
+    """fp64 exact kNN ids (metric 1 = L2, 3 = inner product: largest dot first) with (dist, id) ties --
+    numpy, for recall only.  Rows are processed in chunks so that 10 M-row workloads fit in memory."""
+    nq = Q.shape[0]
+    q = Q.astype(np.float64)
+    best_d = np.full((nq, k), np.inf)
+    best_i = np.full((nq, k), -1, np.int64)
+    chunk = 1_000_000
+    for r0 in range(0, X.shape[0], chunk):
+        X64 = X[r0:r0 + chunk].astype(np.float64)
+        if metric == 3:
+            d = -(q @ X64.T)
+        else:
+            d = (X64 * X64).sum(1)[None, :] - 2.0 * (q @ X64.T) + (q * q).sum(1)[:, None]
+        kk = min(k, d.shape[1])
+        idx = np.argpartition(d, kk - 1, axis=1)[:, :kk]
+        cd = np.concatenate([best_d, np.take_along_axis(d, idx, 1)], axis=1)
+        ci = np.concatenate([best_i, idx + r0], axis=1)
+        order = np.lexsort((ci, cd), axis=1)[:, :k]
+        best_d = np.take_along_axis(cd, order, 1)
+        best_i = np.take_along_axis(ci, order, 1)
+    return best_i
