@@ -271,145 +271,76 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_kernel(const float *__restr
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
-    // the scan kernel left, per query, an upper bound of its kc-th best key (packed keys only):
-    // partial entries above it cannot be among the kc best.  The survivors (about kc of them) are
-    // collected in shared memory and sorted in one go; only if more than 32 survive (no bound, or a
-    // mass of ties) the entries go through the incremental top-k instead.
-    __shared__ float sdist[4][32];
-    __shared__ uint32_t sslot[4][32];
-    const int w = threadIdx.x >> 5;
-    const float bound = gthr ? gthr[q] : INFINITY;
     WarpTopK<1, uint32_t> cand;
     cand.init();
-    int cnt = 0;
-    for (int pass = 0; pass < 2; pass++) {          // pass 0: collect; pass 1 (only on overflow): incremental
-        for (int r0 = 0; r0 < nprobe; r0 += 32) {
-            // lane r: where the partial lists of probe r0 + r start, and how many segments there are
-            uint32_t my_first = 0, my_nseg = 0;
-            if (r0 + lane < nprobe) {
-                const size_t p = (size_t) q * nprobe + r0 + lane;
-                const uint32_t l = probe[p];
-                if (l < (uint32_t) nlists) {
-                    const uint32_t len = list_len[l];
-                    if (len) {
-                        const uint32_t pos = pairpos[p];
-                        my_nseg = ivf_nseg(len, segb);
-                        my_first = (item_off[l] + (pos / TC_M) * my_nseg) * (2 * TC_M) + (pos % TC_M) * 2;
-                    }
-                }
-            }
-            const int nr = min(32, nprobe - r0);
-            // (segment sg of probe r) for sg < nseg(r), eight of them at a time: the loads of a group are
-            // issued together, so a query pays for two or three L2 round trips instead of one per probe
-            const int maxseg = (int) __reduce_max_sync(FULL, my_nseg);
-            for (int sg = 0; sg < maxseg; sg++) {
-                for (int rb = 0; rb < nr; rb += 8) {
-                    float cdv[8];
-                    uint32_t slv[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const int r = rb + u;
-                        const uint32_t nseg = __shfl_sync(FULL, my_nseg, r & 31), first = __shfl_sync(FULL, my_first, r & 31);
-                        cdv[u] = INFINITY;
-                        slv[u] = INVALID_SLOT;
-                        // the two halves' kc entries are contiguous per (item, lane-in-tile): 2 * kc <= 32 entries
-                        if (r < nr && (uint32_t) sg < nseg && lane < 2 * kc) {
-                            const size_t at = ((size_t) first + (size_t) sg * (2 * TC_M)) * kc + lane;
-                            slv[u] = pslot[at];
-                            cdv[u] = pdist[at];
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const float cd = cdv[u];
-                        const uint32_t slot = slv[u];
-                        const bool ok = slot != INVALID_SLOT && cd <= bound;
-                        const unsigned m = __ballot_sync(FULL, ok);
-                        if (!m) continue;
-                        if (pass == 0) {
-                            const int at = cnt + __popc(m & ((1u << lane) - 1u));
-                            if (ok && at < 32) { sdist[w][at] = cd; sslot[w][at] = slot; }
-                            cnt += __popc(m);
-                        } else {
-                            cand.offer(cd, slot, ok, lane, kc);
-                        }
-                    }
+    // the scan kernel left, per query, an upper bound of its kc-th best key (packed keys only):
+    // partial entries above it cannot be among the kc best
+    const float bound = gthr ? gthr[q] : INFINITY;
+    for (int r0 = 0; r0 < nprobe; r0 += 32) {
+        // lane r: where the partial lists of probe r0 + r start, and how many segments there are
+        uint32_t my_first = 0, my_nseg = 0;
+        if (r0 + lane < nprobe) {
+            const size_t p = (size_t) q * nprobe + r0 + lane;
+            const uint32_t l = probe[p];
+            if (l < (uint32_t) nlists) {
+                const uint32_t len = list_len[l];
+                if (len) {
+                    const uint32_t pos = pairpos[p];
+                    my_nseg = ivf_nseg(len, segb);
+                    my_first = (item_off[l] + (pos / TC_M) * my_nseg) * (2 * TC_M) + (pos % TC_M) * 2;
                 }
             }
         }
-        if (pass == 0) {
-            if (cnt > 32) continue;                  // overflow: second pass
-            __syncwarp();
-            cand.d[0] = lane < cnt ? sdist[w][lane] : INFINITY;
-            cand.key[0] = lane < cnt ? sslot[w][lane] : KeyMax<uint32_t>::v;
-            warp_sort32<uint32_t>(cand.d[0], cand.key[0], lane);
-            break;
+        const int nr = min(32, nprobe - r0);
+        for (int r = 0; r < nr; r++) {
+            const uint32_t nseg = __shfl_sync(FULL, my_nseg, r), first = __shfl_sync(FULL, my_first, r);
+            // the two halves' kc entries are contiguous per (item, lane-in-tile)
+            for (uint32_t sg = 0; sg < nseg; sg++) {
+                const size_t base = ((size_t) first + (size_t) sg * (2 * TC_M)) * kc;
+                for (int i = lane; i < round_up(2 * kc, 32); i += 32) {
+                    float cd = INFINITY;
+                    uint32_t slot = INVALID_SLOT;
+                    if (i < 2 * kc) { slot = pslot[base + i]; cd = pdist[base + i]; }
+                    const bool ok = slot != INVALID_SLOT && cd <= bound;
+                    if (__any_sync(FULL, ok)) cand.offer(cd, slot, ok, lane, kc);
+                }
+            }
         }
     }
     // lane e < kc holds candidate e
     const uint32_t ts = lane < kc ? cand.key[0] : INVALID_SLOT;
-    uint32_t myrow = ts != INVALID_SLOT ? tc_row[ts] : INVALID_SLOT;         // (INVALID: a pad row of the tile layout)
-    const bool have = myrow != INVALID_SLOT;
-    // Stage the candidates' fp32 rows in shared memory: the whole warp fetches one row (4 * dim
-    // contiguous bytes of the row-major arena) per request, kc independent requests in flight.  A
-    // lane walking its own row straight from global memory would serialise dim / 4 DRAM round trips.
-    extern __shared__ float fin_rows[];
-    const int rstride = dim + 1;                                              // odd stride: lanes hit distinct banks
-    float *wr = fin_rows + (size_t) w * (kc + 1) * rstride;                   // kc candidate rows + the query
-    const float *qrow = Q + (size_t) q * dim;
-    if ((dim & 3) == 0) {
-        // rows 0..kc-1 = candidates, row kc = the query; 8 row requests in flight per lane
-        for (int c0 = 0; c0 <= kc; c0 += 8) {
-            const float *srcs[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {                                     // (shuffles: all lanes, outside the j loop)
-                const int c = c0 + u;
-                const uint32_t row = __shfl_sync(FULL, myrow, c & 31);
-                srcs[u] = c == kc ? qrow : (c < kc && row != INVALID_SLOT ? arena + (size_t) row * dim : nullptr);
-            }
-            for (int j = lane * 4; j < dim; j += 128) {
-                float4 x[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-                    x[u] = srcs[u] ? *reinterpret_cast<const float4 *>(srcs[u] + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int c = c0 + u;
-                    if (c <= kc) {
-                        float *dst = wr + (size_t) c * rstride + j;
-                        dst[0] = x[u].x; dst[1] = x[u].y; dst[2] = x[u].z; dst[3] = x[u].w;
-                    }
-                }
-            }
-        }
-    } else {
-        for (int c = 0; c <= kc; c++) {
-            const uint32_t row = __shfl_sync(FULL, myrow, c & 31);
-            const float *src = c == kc ? qrow : (row != INVALID_SLOT ? arena + (size_t) row * dim : nullptr);
-            if (src)
-                for (int j = lane; j < dim; j += 32) wr[(size_t) c * rstride + j] = src[j];
-        }
-    }
-    __syncwarp();
     float ed = INFINITY;
     int64_t id = -1;
+    const bool have = ts != INVALID_SLOT && tc_row[ts] != INVALID_SLOT;      // (never a pad row of the tile layout)
     if (have) {
-        const float *qv = wr + (size_t) kc * rstride;                        // broadcast reads
-        const float *xv = wr + (size_t) lane * rstride;
+        // the candidate's fp32 row from the row-major arena: 4 * dim contiguous bytes (the IL32 list
+        // store would hand out one 16-byte piece per 512 bytes)
+        const float *qv = Q + (size_t) q * dim;
+        const float *xv = arena + (size_t) tc_row[ts] * dim;
         typename P::Acc acc;
         P::init(acc);
+        if ((dim & 3) == 0) {
 #pragma unroll 8
-        for (int j = 0; j < dim; j++) P::step(acc, xv[j], qv[j]);
+            for (int j = 0; j < dim; j += 4) {                        // (unrolled: several row loads in flight)
+                const float4 x = *reinterpret_cast<const float4 *>(xv + j);
+                P::step(acc, x.x, qv[j]);
+                P::step(acc, x.y, qv[j + 1]);
+                P::step(acc, x.z, qv[j + 2]);
+                P::step(acc, x.w, qv[j + 3]);
+            }
+        } else {
+            for (int j = 0; j < dim; j++) P::step(acc, xv[j], qv[j]);
+        }
         ed = P::finish(acc, 0, 0);
         id = ids[tc_src[ts]];
     }
-    int64_t key = have ? id : KeyMax<int64_t>::v;
-    if (!have) ed = INFINITY;
-    warp_sort32<int64_t>(ed, key, lane);
+    WarpTopK<1, int64_t> top;
+    top.init();
+    top.offer(ed, id, have, lane, k);
     if (lane < k) {
-        const bool got = key != KeyMax<int64_t>::v;
-        out_dist[(size_t) q * k + lane] = got ? ed : INFINITY;
-        out_ids[(size_t) q * k + lane] = got ? key : -1;
+        const bool got = top.key[0] != KeyMax<int64_t>::v;
+        out_dist[(size_t) q * k + lane] = got ? top.d[0] : INFINITY;
+        out_ids[(size_t) q * k + lane] = got ? top.key[0] : -1;
     }
 }
 
@@ -761,15 +692,8 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
 
     // 4. merge + fp32 re-rank
     const unsigned mgrid = (unsigned) ((nq + 3) / 4);
-    const size_t fin_smem = (size_t) 4 * (kc + 1) * (ix->dim + 1) * sizeof(float);
-    static size_t fin_smem_cfg = 48 * 1024;
-    if (fin_smem > fin_smem_cfg) {
-        NDB_CUDA(cudaFuncSetAttribute(ivf_tc_finish_kernel<Arith<NDB_L2, NDB_ARITH_IVF_F32>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fin_smem));
-        NDB_CUDA(cudaFuncSetAttribute(ivf_tc_finish_kernel<Arith<NDB_IP, NDB_ARITH_IVF_F32>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fin_smem));
-        fin_smem_cfg = fin_smem;
-    }
 #define NDB_FIN(M)                                                                                                   \
-    ivf_tc_finish_kernel<Arith<M, NDB_ARITH_IVF_F32>><<<mgrid, 128, fin_smem, s>>>(                                   \
+    ivf_tc_finish_kernel<Arith<M, NDB_ARITH_IVF_F32>><<<mgrid, 128, 0, s>>>(                                   \
         ix->tcs.pdist.as<float>(), ix->tcs.pslot.as<uint32_t>(), ix->tc_src.as<uint32_t>(), ix->tc_row.as<uint32_t>(),  \
         ix->arena.as<float>(), ix->ids.as<int64_t>(), Q_dev, ix->probe.as<uint32_t>(),                                  \
         ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), p.packed ? p.gthr : nullptr, \
