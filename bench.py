@@ -392,14 +392,15 @@ def main():
     gt = W.exact_ground_truth(X, Q[:ngt], k, w["metric"])
     recall = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(res_i[:ngt], gt)]))
 
-    traffic = None
+    traffic = tensor_traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
+                tj = json.load(f).get(args.workload, {})
+            traffic, tensor_traffic = tj.get("dram_bytes_per_launch"), tj.get("tensor_dram_bytes_per_launch")
         except Exception:
-            traffic = None
+            traffic = tensor_traffic = None
 
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
@@ -424,10 +425,11 @@ def main():
         tpeak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         ach = flops / (kernel_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
-                    "traffic": None, "peak_source": peak_kind, "kernel": "tc_knn_kernel (list mode)",
+                    "traffic": tensor_traffic, "peak_source": peak_kind, "kernel": "tc_knn_kernel (list mode)",
                     "kernel_ms": kernel_ms, "distance_evals_per_launch": evals,
                     "note": "algorithmic flops only: the kernel also multiplies tile padding (lists padded to 256 rows, "
-                            "query groups padded to 128), which is not counted"}
+                            "query groups padded to 128; about 7x the algorithmic flops on C2), which is not counted; the "
+                            "kernel is bound by its top-k epilogue, see DESIGN.md 4.2b"}
 
     cpu = None
     if not args.no_cpu_baseline:

@@ -14,8 +14,13 @@ n_cpu = int(sys.argv[3]) if len(sys.argv) > 3 else 20_000
 m, efc, efs, nq = 16, 64, 40, 10_000
 ndb.init(0)
 ndb.set_timing(True)
-X = W.normalised(n, dim, 768)
-Q = W.normalised(nq, dim, 769)
+if os.environ.get("HNSW_DATA") == "mixture":        # clustered data (the C2 mixture): a regime where graph search can reach high recall
+    X = W.mixture(n, dim, 1024, 2024)
+    Q = W.mixture(nq, dim, 1024, 2025, centers_seed=2024)
+else:                                               # structureless unit vectors
+    X = W.normalised(n, dim, 768)
+    Q = W.normalised(nq, dim, 769)
+efs = int(os.environ.get("HNSW_EF", efs))
 levels = O.hnsw_levels(n, seed=768)
 h = ndb.HnswIndex(dim, m, efc, efs, ndb.COSINE)
 t = time.time(); h.hnswbuild(X, levels=levels); tb = time.time() - t
