@@ -218,6 +218,17 @@ int ndb_b200_hnsw_export_graph(const ndb_b200_hnsw *h, int *levels, uint32_t *nb
                                int64_t *upper_off, uint32_t *upper, int64_t upper_cap,
                                uint32_t *entry_point, int *entry_level);
 int64_t ndb_b200_hnsw_size(const ndb_b200_hnsw *h);
+/* Neighbour selection of ndb_b200_hnsw_build.  NDB_HNSW_SELECT_CLOSEST (default) is the reference:
+ * the closest m candidates become the forward links, and a back-link is written only while the
+ * neighbour has a free slot among its 2m (hnsw_am.c:2386-2424,2493-2513; the prune block after it,
+ * :2515-2612, can never run).  On a million rows that leaves late nodes nearly without in-links and
+ * recall@10 below 0.9 at any ef.  NDB_HNSW_SELECT_HEURISTIC is an extension for the recall target of
+ * the benchmark: forward links chosen by the diversity heuristic of Malkov & Yashunin (Alg. 4), and
+ * a full neighbour re-selects its 2m links among the current ones and the new node.  m <= 16.
+ * Search and the stored layout are unchanged. */
+#define NDB_HNSW_SELECT_CLOSEST    0
+#define NDB_HNSW_SELECT_HEURISTIC  1
+int ndb_b200_hnsw_set_select(ndb_b200_hnsw *h, int select_mode);
 /* load node pages (one HnswNodeData per 8 KB page, hnsw_am.c:124-181) + the meta page */
 int ndb_b200_hnsw_load_relation(ndb_b200_hnsw *h, const void *blocks, uint32_t nblocks);
 /* hnswSearch for a batch: strategy = metric (the AMs always pass 1, Q4), ef, k;

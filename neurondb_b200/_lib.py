@@ -16,6 +16,7 @@ L2, COSINE, IP = 1, 2, 3
 ARITH_OP_F64, ARITH_IVF_F32, ARITH_HNSW, ARITH_FAST, ARITH_TENSOR = 0, 3, 4, 5, 6
 IVF_FULL, IVF_LITERAL = 0, 1
 HNSW_LITERAL, HNSW_BESTFIRST = 0, 1
+HNSW_SELECT_CLOSEST, HNSW_SELECT_HEURISTIC = 0, 1
 
 ERRORS = {-1: "EINVAL", -2: "ECUDA", -3: "ENOTINIT", -4: "EVECTOR", -5: "EDIM", -6: "ENOMEM", -7: "ESTATE",
           -8: "ERANGE"}
@@ -97,6 +98,7 @@ SIGNATURES = {
     "ndb_b200_kmeans_shard_cost_dev": (_i, [_p, _i64, _i, _p, _p, _p, _p]),
     "ndb_b200_ivf_search_begin": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "ndb_b200_ivf_search_end": (_i, [_p, _i]),
+    "ndb_b200_hnsw_set_select": (_i, [_p, _i]),
     "ndb_b200_keys_from_vector": (_i, [_p, _i64, _i, _p]),
     "ndb_b200_keys_from_halfvec": (_i, [_p, _i64, _i, _p]),
     "ndb_b200_keys_from_halfvec_dev": (_i, [_p, _i64, _i, _p, _p]),

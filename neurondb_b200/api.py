@@ -9,7 +9,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from ._lib import (ARITH_FAST, ARITH_HNSW, ARITH_IVF_F32, ARITH_OP_F64, ARITH_TENSOR, COSINE, HNSW_BESTFIRST, HNSW_LITERAL, IP,
+from ._lib import (ARITH_FAST, ARITH_HNSW, ARITH_IVF_F32, ARITH_OP_F64, ARITH_TENSOR, COSINE, HNSW_BESTFIRST, HNSW_LITERAL,
+                   HNSW_SELECT_CLOSEST, HNSW_SELECT_HEURISTIC, IP,
                    IVF_FULL, IVF_LITERAL, L2, NdbError, check, f32, ptr)
 
 _initialised = {"device": None}
@@ -313,7 +314,10 @@ class HnswIndex(_Handle):
         self.dim, self.m, self.efc, self.efs, self.metric = dim, m, ef_construction, ef_search, metric
         check(L.load().ndb_b200_hnsw_create(dim, m, ef_construction, ef_search, metric, C.byref(self.h)))
 
-    def hnswbuild(self, rows, ids=None, levels=None, seed=0, batch=0):
+    def hnswbuild(self, rows, ids=None, levels=None, seed=0, batch=0, select=HNSW_SELECT_CLOSEST):
+        """hnswbuild (:343-415).  select=HNSW_SELECT_HEURISTIC swaps the reference's closest-m / capped
+        back-link rule for the diversity heuristic with re-selection of full neighbours (an extension)."""
+        check(L.load().ndb_b200_hnsw_set_select(self.h, select))
         rows = f32(rows)
         idp = None if ids is None else np.ascontiguousarray(ids, np.int64)
         lv = None if levels is None else np.ascontiguousarray(levels, np.int32)

@@ -388,7 +388,42 @@ struct HnswBuildArgs {
     unsigned long long *req;     // back-link requests: ((u*16+lev) << 32) | v
     unsigned int *nreq;
     unsigned long long *evals;
+    int heuristic;               // NDB_HNSW_SELECT_HEURISTIC: diversity selection instead of closest-m
 };
+
+// Neighbour selection by the diversity heuristic (Malkov & Yashunin, Alg. 4; hnswlib's
+// getNeighborsByHeuristic2), an EXTENSION over the reference's closest-m rule: candidates are taken in
+// ascending (distance to the base, id) order and one is kept if it is closer to the base than to every
+// neighbour kept so far.  cand(i, &id, &d) yields the i-th candidate (warp-uniform).  The kept
+// neighbours live one per lane (lane j < kept holds the j-th), so a candidate is checked against all
+// of them at once: lane j walks the dimensions of (candidate, kept_j) in order -- the same sequential
+// arithmetic as everywhere else, hence the same graph as the CPU oracle when built one node at a time.
+// cs: [dimp] shared-memory staging of the candidate's vector.  Returns the number kept (<= want <= 32).
+template <class P, class CandFn>
+__device__ int select_heuristic_warp(const HnswGraph &g, WarpCtx &w, float *cs, int ncand, int want, int lane, CandFn cand,
+                                     uint32_t &my_id, float &my_d)
+{
+    int kept = 0;
+    my_id = INVALID_SLOT;
+    my_d = INFINITY;
+    for (int i = 0; i < ncand && kept < want; i++) {
+        uint32_t c;
+        float dc;
+        cand(i, c, dc);
+        __syncwarp();
+        for (int t = lane; t < g.dimp; t += 32) cs[t] = g.vec[(size_t) c * g.dimp + t];
+        __syncwarp();
+        bool closer_to_kept = false;
+        if (lane < kept) closer_to_kept = node_distance<P>(g, cs, 0.0, my_id) < dc;
+        w.evals += kept;
+        if (!__any_sync(FULL, closer_to_kept)) {
+            if (lane == kept) { my_id = c; my_d = dc; }
+            kept++;
+        }
+    }
+    __syncwarp();
+    return kept;
+}
 
 // per new node: search the graph as it stood before this batch, keep the closest m per level
 // (hnsw_am.c:2365-2424), write the forward links (:2452-2458), queue the back-links
@@ -397,13 +432,14 @@ __global__ void hnsw_build_search_kernel(const HnswBuildArgs a)
     using P = Arith<NDB_L2, NDB_ARITH_HNSW>;          // hnswInsertNode always searches with L2 (:2375-2384)
     extern __shared__ __align__(16) unsigned char hs[];
     const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-    const size_t per_warp = (size_t) a.g.dimp * 4 + (size_t) a.efc * 12;
+    const size_t per_warp = (size_t) a.g.dimp * 4 * (a.heuristic ? 2 : 1) + (size_t) a.efc * 12;
     unsigned char *base = hs + per_warp * wl;
     WarpCtx w;
     w.qs = reinterpret_cast<float *>(base);
     w.wd = reinterpret_cast<float *>(base + (size_t) a.g.dimp * 4);
     w.wid = reinterpret_cast<uint32_t *>(w.wd + a.efc);
     w.widx = reinterpret_cast<int *>(w.wid + a.efc);
+    float *cs = reinterpret_cast<float *>(w.widx + a.efc);          // heuristic only: candidate staging
     const int gw = blockIdx.x * wpb + wl, total = gridDim.x * wpb;
     w.bits = a.bits + (size_t) gw * a.words;
     w.vlist = a.vlist + (size_t) gw * a.vcap;
@@ -423,14 +459,19 @@ __global__ void hnsw_build_search_kernel(const HnswBuildArgs a)
         for (int lev = maxLevel; lev >= 0; lev--) {
             const int wn = search_layer<P>(g, w, 0.0, ep, lev, a.efc, lane);
             clear_visited(w, g.n, lane);
-            const int sel = min(a.m, wn);
+            int sel = min(a.m, wn);
             uint32_t *mine = lev == 0 ? a.g.nbr0 + (size_t) v * g.m2
                                       : a.g.upper + a.g.upper_off[v] + (size_t) (lev - 1) * g.m2;
+            uint32_t hid = INVALID_SLOT;
+            float hd = INFINITY;
+            if (a.heuristic)
+                sel = select_heuristic_warp<P>(g, w, cs, wn, a.m, lane,
+                                               [&](int i, uint32_t &c, float &dc) { c = w.wid[i] & ~EXPANDED; dc = w.wd[i]; }, hid, hd);
             unsigned int rbase = 0;
             if (lane == 0 && sel > 0) rbase = atomicAdd(a.nreq, (unsigned int) sel);
             rbase = __shfl_sync(FULL, rbase, 0);
             for (int i = lane; i < sel; i += 32) {
-                const uint32_t u = w.wid[i] & ~EXPANDED;
+                const uint32_t u = a.heuristic ? hid : (w.wid[i] & ~EXPANDED);
                 mine[i] = u;
                 a.req[rbase + i] = ((unsigned long long) ((unsigned long long) u * 16 + lev) << 32) | v;
             }
@@ -458,6 +499,70 @@ __global__ void hnsw_backlink_write_kernel(const unsigned long long *req, unsign
     if (!slots) return;
     const int pos = nbr_count(g, u, lev) + rank;
     if (pos < g.m2) slots[pos] = v;
+}
+
+// Heuristic mode: one warp per (node u, level) segment of the sorted requests.  The new nodes v of the
+// segment are taken in ascending order: appended while u has a free slot, otherwise u's neighbours are
+// re-selected among the current ones and v (hnswlib's mutuallyConnectNewElement).
+__global__ void hnsw_backlink_select_kernel(const unsigned long long *req, unsigned int nreq, HnswGraph g,
+                                            unsigned long long *evals)
+{
+    using P = Arith<NDB_L2, NDB_ARITH_HNSW>;
+    extern __shared__ __align__(16) unsigned char hs[];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const unsigned int i0 = blockIdx.x * (blockDim.x >> 5) + wl;
+    if (i0 >= nreq) return;
+    const unsigned long long key = req[i0] >> 32;
+    if (i0 > 0 && (req[i0 - 1] >> 32) == key) return;               // not the first request of its segment
+    float *us = reinterpret_cast<float *>(hs) + (size_t) wl * 2 * g.dimp;     // u's vector
+    float *cs = us + g.dimp;                                        // candidate staging
+    const uint32_t u = (uint32_t) (key >> 4);
+    const int lev = (int) (key & 15);
+    uint32_t *slots = nbr_slots(g, u, lev);
+    if (!slots) return;
+    WarpCtx w;
+    w.qs = us;
+    w.evals = 0;
+    for (int t = lane; t < g.dimp; t += 32) us[t] = g.vec[(size_t) u * g.dimp + t];
+    __syncwarp();
+    int nc = nbr_count(g, u, lev);
+    for (unsigned int i = i0; i < nreq && (req[i] >> 32) == key; i++) {
+        const uint32_t v = (uint32_t) (req[i] & 0xffffffffu);
+        if (nc < g.m2) {
+            if (lane == 0) slots[nc] = v;
+            nc++;
+            continue;
+        }
+        // full: (distance to u, id) of the current neighbours, one per lane, and of v
+        const uint32_t e = lane < nc ? slots[lane] : INVALID_SLOT;
+        float d = INFINITY;
+        uint32_t id = 0xffffffffu;
+        if (e != INVALID_SLOT) { d = node_distance<P>(g, us, 0.0, e); id = e; }
+        float dv = 0.0f;
+        if (lane == 0) dv = node_distance<P>(g, us, 0.0, v);
+        dv = __shfl_sync(FULL, dv, 0);
+        w.evals += nc + 1;
+        warp_sort32<uint32_t>(d, id, lane);                         // ascending; empty lanes (INF, ~0) last
+        const int rank = __popc(__ballot_sync(FULL, id != 0xffffffffu && pair_less<uint32_t>(d, id, dv, v)));
+        uint32_t kid;
+        float kd;
+        const int kept = select_heuristic_warp<P>(g, w, cs, nc + 1, g.m2, lane,
+                                                  [&](int j, uint32_t &c, float &dc) {
+                                                      const int src = j < rank ? j : j - 1;
+                                                      const uint32_t sc = __shfl_sync(FULL, id, src & 31);
+                                                      const float sd = __shfl_sync(FULL, d, src & 31);
+                                                      c = j == rank ? v : sc;
+                                                      dc = j == rank ? dv : sd;
+                                                  }, kid, kd);
+        __syncwarp();
+        if (lane < g.m2) slots[lane] = lane < kept ? kid : INVALID_SLOT;
+        __syncwarp();
+        nc = kept;
+    }
+    if (lane == 0) {
+        g.cnt[(size_t) u * HNSW_MAX_LEVEL + lev] = (int16_t) nc;
+        if (w.evals) atomicAdd(evals, (unsigned long long) w.evals);
+    }
 }
 
 __global__ void hnsw_backlink_count_kernel(const unsigned long long *req, unsigned int nreq, HnswGraph g)
@@ -515,6 +620,7 @@ struct ndb_b200_hnsw {
     int64_t last_evals = 0;
     int64_t bits_words = 0;
     int bits_warps = 0;
+    int select_mode = NDB_HNSW_SELECT_CLOSEST;
 };
 
 namespace ndb {
@@ -538,9 +644,9 @@ static HnswGraph graph_of(const ndb_b200_hnsw *h)
 }
 
 // shared-memory budget -> warps per CTA and grid for the warp-per-query kernels
-static int hnsw_launch_shape(const ndb_b200_hnsw *h, int ef, int *wpb, int *grid, size_t *smem)
+static int hnsw_launch_shape(const ndb_b200_hnsw *h, int ef, int *wpb, int *grid, size_t *smem, bool staging = false)
 {
-    const size_t per_warp = (size_t) h->dimp * 4 + (size_t) ef * 12;
+    const size_t per_warp = (size_t) h->dimp * 4 * (staging ? 2 : 1) + (size_t) ef * 12;
     const size_t limit = ctx().smem_optin ? ctx().smem_optin - 2048 : 200 * 1024;
     NDB_REQUIRE(per_warp <= limit, NDB_B200_EINVAL, "hnsw: dim=%d with ef=%d does not fit in shared memory", h->dim, ef);
     int w = (int) std::min<size_t>(8, (limit / 2) / per_warp);     // aim for >= 2 CTAs per SM
@@ -671,6 +777,14 @@ int64_t ndb_b200_hnsw_last_evals(const ndb_b200_hnsw *ch)
     return (int64_t) v;
 }
 
+int ndb_b200_hnsw_set_select(ndb_b200_hnsw *h, int select_mode)
+{
+    NDB_REQUIRE(h && (select_mode == NDB_HNSW_SELECT_CLOSEST || select_mode == NDB_HNSW_SELECT_HEURISTIC), NDB_B200_EINVAL,
+                "hnsw_set_select: bad argument");
+    h->select_mode = select_mode;
+    return NDB_B200_OK;
+}
+
 int ndb_b200_hnsw_load_graph(ndb_b200_hnsw *h, const float *rows, const int64_t *ids, int64_t n, const int *levels,
                              const uint32_t *nbr0, const int16_t *cnt, const int64_t *upper_off, const uint32_t *upper,
                              uint32_t entry_point, int entry_level)
@@ -737,9 +851,14 @@ int ndb_b200_hnsw_build(ndb_b200_hnsw *h, const float *rows, const int64_t *ids,
     NDB_CHECK(hnsw_alloc_nodes(h, rows, ids, n, levels, s));
     int wpb, grid;
     size_t smem;
-    NDB_CHECK(hnsw_launch_shape(h, h->efc, &wpb, &grid, &smem));
+    const bool heuristic = h->select_mode == NDB_HNSW_SELECT_HEURISTIC;
+    NDB_REQUIRE(!heuristic || 2 * h->m <= 32, NDB_B200_EINVAL, "hnsw_build: heuristic selection supports m <= 16 (m = %d)", h->m);
+    NDB_CHECK(hnsw_launch_shape(h, h->efc, &wpb, &grid, &smem, heuristic));
     NDB_CHECK(hnsw_scratch(h, grid * wpb, s));
     NDB_CUDA(cudaFuncSetAttribute(hnsw_build_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    const size_t sel_smem = (size_t) 4 * 2 * h->dimp * 4;             // hnsw_backlink_select_kernel: 4 warps per CTA
+    if (heuristic)
+        NDB_CUDA(cudaFuncSetAttribute(hnsw_backlink_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sel_smem));
     const int64_t max_batch = batch > 0 ? batch : 4096;
     const size_t req_cap = (size_t) max_batch * HNSW_MAX_LEVEL * h->m;
     NDB_CHECK(h->req.reserve(req_cap * 8));
@@ -774,6 +893,7 @@ int ndb_b200_hnsw_build(ndb_b200_hnsw *h, const float *rows, const int64_t *ids,
         a.req = h->req.as<unsigned long long>();
         a.nreq = h->nreq.as<unsigned int>();
         a.evals = h->evals.as<unsigned long long>();
+        a.heuristic = heuristic ? 1 : 0;
         unsigned int nreq = 0;
         if (entry != INVALID_SLOT) {
             NDB_CUDA(cudaMemsetAsync(h->nreq.p, 0, 4, s));
@@ -789,8 +909,13 @@ int ndb_b200_hnsw_build(ndb_b200_hnsw *h, const float *rows, const int64_t *ids,
             NDB_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_tmp.p, tb, h->req.as<unsigned long long>(),
                                                     h->req_sorted.as<unsigned long long>(), (int) nreq, 0, 64, s));
             const unsigned gb = (nreq + 255) / 256;
-            hnsw_backlink_write_kernel<<<gb, 256, 0, s>>>(h->req_sorted.as<unsigned long long>(), nreq, a.g);
-            hnsw_backlink_count_kernel<<<gb, 256, 0, s>>>(h->req_sorted.as<unsigned long long>(), nreq, a.g);
+            if (heuristic) {
+                hnsw_backlink_select_kernel<<<(nreq + 3) / 4, 128, sel_smem, s>>>(h->req_sorted.as<unsigned long long>(), nreq, a.g,
+                                                                                  h->evals.as<unsigned long long>());
+            } else {
+                hnsw_backlink_write_kernel<<<gb, 256, 0, s>>>(h->req_sorted.as<unsigned long long>(), nreq, a.g);
+                hnsw_backlink_count_kernel<<<gb, 256, 0, s>>>(h->req_sorted.as<unsigned long long>(), nreq, a.g);
+            }
             count_launch(5);
             NDB_CUDA(cudaGetLastError());
         }

@@ -32,6 +32,7 @@ extern "C" {
 
 #define ORC_INVALID 0xFFFFFFFFu        /* InvalidBlockNumber */
 #define ORC_HNSW_MAX_LEVEL 16          /* hnsw_am.c:84 */
+#define ORC_HNSW_MAX_M2 256            /* 2 * m upper bound of the scratch arrays (m <= 128, hnsw_am.c:79) */
 
 /* metrics / strategies (sk_strategy numbering of the AMs: 1=L2, 2=cosine, 3=-IP) */
 enum { ORC_L2 = 1, ORC_COSINE = 2, ORC_IP = 3 };

@@ -17,6 +17,12 @@
  *   insert mode 1 -- per-level search at that level and no self hits; what the GPU build
  *                    implements (the literal mode cannot complete in the reference
  *                    itself: SURVEY Q22).
+ *   insert mode 2 -- EXTENSION, experiment only: mode 1 + a full neighbour swaps its farthest
+ *                    link for a closer new node (the intent of the reference's unreachable
+ *                    prune block, :2515-2612).  Measured worse than mode 3; no GPU twin.
+ *   insert mode 3 -- EXTENSION: mode 1 with the diversity heuristic of Malkov & Yashunin
+ *                    (Alg. 4) for the forward links and re-selection of a full neighbour's
+ *                    links; the GPU build's NDB_HNSW_SELECT_HEURISTIC, link for link.
  * Out-of-bounds behaviour of the reference (back-links written at a level the
  * neighbour node does not have, :2493-2513 via HnswGetNeighborsSafe) is undefined
  * there and skipped here.
@@ -289,7 +295,38 @@ void orc_hnsw_search(const OrcHnsw *g, const float *Q, int nq, int strategy, int
 /* back-link append, hnsw_am.c:2493-2513: first InvalidBlockNumber hole below the count,
  * else the count itself; written only if < 2m.  (The prune block after it, :2515-2612,
  * is unreachable: count can never exceed 2m.) */
-static void backlink(OrcHnsw *g, uint32_t nb, int lev, uint32_t newnode)
+/* EXTENSION (insert mode 3): neighbour selection by the diversity heuristic of Malkov & Yashunin
+ * (Alg. 4, as in hnswlib's getNeighborsByHeuristic2).  cand/cd: candidates sorted ascending by
+ * (distance to the base vector, id); a candidate is kept if it is closer to the base than to every
+ * neighbour kept so far; at most `want` are kept.  Returns the number kept (in place, order kept). */
+static int select_heuristic(OrcHnsw *g, uint32_t *cand, float *cd, int cc, int want)
+{
+    int kept = 0;
+    for (int i = 0; i < cc && kept < want; i++) {
+        const float *cv = g->vec + (size_t) cand[i] * g->dim;
+        int good = 1;
+        for (int j = 0; j < kept; j++) {
+            float d = orc_hnsw_distance(cv, g->vec + (size_t) cand[j] * g->dim, g->dim, 1);
+            g_evals++;
+            if (d < cd[i]) { good = 0; break; }
+        }
+        if (good) { cand[kept] = cand[i]; cd[kept] = cd[i]; kept++; }
+    }
+    return kept;
+}
+
+/* ascending by (distance, id): insertion sort, the lists are short */
+static void sort_by_dist_id(uint32_t *cand, float *cd, int cc)
+{
+    for (int i = 1; i < cc; i++) {
+        uint32_t c = cand[i]; float d = cd[i];
+        int j = i - 1;
+        while (j >= 0 && (cd[j] > d || (cd[j] == d && cand[j] > c))) { cand[j + 1] = cand[j]; cd[j + 1] = cd[j]; j--; }
+        cand[j + 1] = c; cd[j + 1] = d;
+    }
+}
+
+static void backlink(OrcHnsw *g, uint32_t nb, int lev, uint32_t newnode, int mode, float d_new)
 {
     uint32_t *s = slots(g, nb, lev);
     if (!s) return;     /* reference writes out of the node's bounds here: skipped */
@@ -301,6 +338,39 @@ static void backlink(OrcHnsw *g, uint32_t nb, int lev, uint32_t newnode)
         s[insertPos] = newnode;
         if (insertPos >= nc)
             g->cnt[(size_t) nb * ORC_HNSW_MAX_LEVEL + lev] = (int16_t) (insertPos + 1);
+    } else if (mode == 3) {
+        /* full: re-select nb's neighbours among the current ones and the new node (hnswlib's
+         * mutuallyConnectNewElement) */
+        const int m2 = g->m * 2;
+        uint32_t tc[ORC_HNSW_MAX_M2 + 1];
+        float td[ORC_HNSW_MAX_M2 + 1];
+        const float *nv = g->vec + (size_t) nb * g->dim;
+        int cc = 0;
+        for (int j = 0; j < nc; j++) {
+            tc[cc] = s[j];
+            td[cc] = orc_hnsw_distance(nv, g->vec + (size_t) s[j] * g->dim, g->dim, 1);
+            g_evals++;
+            cc++;
+        }
+        tc[cc] = newnode; td[cc] = d_new; cc++;
+        sort_by_dist_id(tc, td, cc);
+        int kept = select_heuristic(g, tc, td, cc, m2);
+        for (int j = 0; j < m2; j++) s[j] = j < kept ? tc[j] : ORC_INVALID;
+        g->cnt[(size_t) nb * ORC_HNSW_MAX_LEVEL + lev] = (int16_t) kept;
+    } else if (mode == 2) {
+        /* EXTENSION (insert mode 2): what the reference's unreachable prune block (:2515-2612,
+         * "prune to at most m*2 nearest neighbors") is after, restated as a replacement: the new
+         * node takes the slot of the farthest current neighbour (hnswComputeDistance, strategy 1;
+         * ties -> the later slot) if it is strictly closer to nb than that neighbour. */
+        const float *nv = g->vec + (size_t) nb * g->dim;
+        int far = -1;
+        float fd = 0.0f;
+        for (int j = 0; j < nc; j++) {
+            float d = orc_hnsw_distance(nv, g->vec + (size_t) s[j] * g->dim, g->dim, 1);
+            g_evals++;
+            if (far < 0 || d >= fd) { far = j; fd = d; }
+        }
+        if (far >= 0 && d_new < fd) s[far] = newnode;
     }
 }
 
@@ -333,7 +403,7 @@ void orc_hnsw_insert(OrcHnsw *g, const float *vec, int level, int mode)
         float *cd = (float *) malloc(sizeof(float) * (size_t) efc);
         uint8_t *visited = (uint8_t *) malloc((size_t) g->n);
         uint32_t ep = g->entry;
-        if (mode == 1)  /* ADDITION: descend once to maxLevel+1, then carry ep level to level */
+        if (mode >= 1)  /* ADDITION: descend once to maxLevel+1, then carry ep level to level */
             ep = greedy_descent(g, vec, 1, g->entry, g->entry_level, maxLevel);
 
         for (int lev = maxLevel; lev >= 0; lev--) {
@@ -351,8 +421,12 @@ void orc_hnsw_insert(OrcHnsw *g, const float *vec, int level, int mode)
                 if (cc > 0) ep = cand[0];
             }
             int selectedCount = m < cc ? m : cc;
+            if (mode == 3) {
+                sort_by_dist_id(cand, cd, cc);
+                selectedCount = select_heuristic(g, cand, cd, cc, m);
+            }
             /* "closest m" selection sort with swaps, :2386-2424 */
-            for (int idx = 0; idx < selectedCount; idx++) {
+            for (int idx = 0; idx < selectedCount && mode != 3; idx++) {
                 int bestIdx = idx;
                 float bestDist = cd[idx];
                 for (int j = idx + 1; j < cc; j++)
@@ -370,7 +444,7 @@ void orc_hnsw_insert(OrcHnsw *g, const float *vec, int level, int mode)
                     mine[idx] = cand[idx];
                     g->cnt[(size_t) blkno * ORC_HNSW_MAX_LEVEL + lev] = (int16_t) (idx + 1);
                 }
-                backlink(g, cand[idx], lev, blkno);
+                backlink(g, cand[idx], lev, blkno, mode, cd[idx]);
             }
         }
         free(cand); free(cd); free(visited);

@@ -96,3 +96,38 @@ def test_hnsw_edge_cases(ndb, orc):
     assert np.all(i[:, 0] == np.arange(5)) and np.all(d[:, 0] == 0)
     assert np.all(i[:, 5:] == -1) and np.all(np.isinf(d[:, 5:]))
     assert all(sorted(r[:5]) == [0, 1, 2, 3, 4] for r in i)
+
+
+def test_heuristic_build_sequential_equals_oracle(ndb, orc):
+    """NDB_HNSW_SELECT_HEURISTIC, one node at a time == the oracle's insert mode 3, link for link."""
+    n, dim, m, efc = 700, 24, 6, 24
+    X = W.mixture(n, dim, 8, 123)
+    levels = orc.hnsw_levels(n, seed=5)
+    h = ndb.HnswIndex(dim, m, efc, 24)
+    h.hnswbuild(X, levels=levels, batch=1, select=ndb.HNSW_SELECT_HEURISTIC)
+    og = orc.Hnsw(dim, m, efc, 24, capacity=n)
+    og.build(X, levels, 3)
+    want, got = og.export(), h.export_graph()
+    assert np.array_equal(got["cnt"], want["cnt"])
+    assert np.array_equal(got["nbr0"], want["nbr0"])
+    assert np.array_equal(got["upper"][: int(got["upper_off"][-1])], want["upper"][: int(want["upper_off"][-1])])
+    Q = W.mixture(40, dim, 8, 124, centers_seed=123)
+    d, i = h.search(Q, 24, 10, 1, ndb.HNSW_BESTFIRST)
+    od, on, _ = og.search(Q, 24, 10, 1, 1)
+    assert np.array_equal(i, on.astype(np.int64)) and np.array_equal(d.view(np.uint32), od.view(np.uint32))
+
+
+def test_heuristic_build_raises_recall(ndb, orc):
+    """Batched build on clustered data: the heuristic graph answers better than the reference rule's."""
+    n, dim = 60000, 32
+    X = W.mixture(n, dim, 64, 321)
+    Q = W.mixture(300, dim, 64, 322, centers_seed=321)
+    gt = W.exact_ground_truth(X, Q, 10)
+    rec = {}
+    for sel in (ndb.HNSW_SELECT_CLOSEST, ndb.HNSW_SELECT_HEURISTIC):
+        h = ndb.HnswIndex(dim, 16, 64, 40)
+        h.hnswbuild(X, seed=3, select=sel)
+        d, i = h.search(Q, 64, 10, 1, ndb.HNSW_BESTFIRST)
+        rec[sel] = orc.recall_at_k(i, gt)
+    assert rec[ndb.HNSW_SELECT_HEURISTIC] >= 0.95, rec
+    assert rec[ndb.HNSW_SELECT_HEURISTIC] > rec[ndb.HNSW_SELECT_CLOSEST], rec

@@ -238,3 +238,26 @@ def test_fp16_restatement_equals_golden_table():
     want = np.load(os.path.join(HERE, "golden", "fp16_table.npz"))["bits"]
     got = O.keys_from_halfvec(np.arange(65536, dtype=np.uint16).reshape(1, -1))[0].view(np.uint32)
     assert np.array_equal(got, want)
+
+
+def test_hnsw_heuristic_insert_mode():
+    """Insert mode 3 (diversity heuristic + re-selection of full neighbours, an extension): a valid graph
+    (no self links, no duplicates, counts within 2m) that answers at least as well as the reference rule."""
+    n, dim, m = 6000, 16, 8
+    X = W.mixture(n, dim, 16, 77)
+    Q = W.mixture(200, dim, 16, 78, centers_seed=77)
+    gt = W.exact_ground_truth(X, Q, 10)
+    levels = O.hnsw_levels(n, seed=4)
+    rec = {}
+    for mode in (1, 3):
+        g = O.Hnsw(dim, m, 32, 32, capacity=n)
+        g.build(X, levels, mode)
+        e = g.export()
+        cnt0 = e["cnt"][:, 0]
+        assert cnt0.max() <= 2 * m
+        for v in range(0, n, 97):
+            nb = e["nbr0"][v, :cnt0[v]]
+            assert v not in nb and len(set(nb.tolist())) == len(nb) and np.all(nb < n)
+        d, nn, _ = g.search(Q, 32, 10, 1, 1)
+        rec[mode] = O.recall_at_k(nn.astype(np.int64), gt)
+    assert rec[3] >= rec[1] - 0.005 and rec[3] >= 0.9, rec

@@ -11,7 +11,7 @@ import workloads as W
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
 dim = int(sys.argv[2]) if len(sys.argv) > 2 else 768
 n_cpu = int(sys.argv[3]) if len(sys.argv) > 3 else 20_000
-m, efc, efs, nq = 16, 64, 40, 10_000
+m, efc, efs, nq = 16, int(os.environ.get("HNSW_EFC", "64")), 40, 10_000
 ndb.init(0)
 ndb.set_timing(True)
 if os.environ.get("HNSW_DATA") == "mixture":        # clustered data (the C2 mixture): a regime where graph search can reach high recall
@@ -23,9 +23,17 @@ else:                                               # structurele
 efs = int(os.environ.get("HNSW_EF", efs))
 levels = O.hnsw_levels(n, seed=768)
 h = ndb.HnswIndex(dim, m, efc, efs, ndb.COSINE)
-t = time.time(); h.hnswbuild(X, levels=levels); tb = time.time() - t
-print(f"GPU build n={n} dim={dim} M={m} efC={efc}: {tb:.2f} s ({n/tb:.0f} inserts/s), {h.last_evals()/n:.0f} evals/insert")
+select = ndb.HNSW_SELECT_HEURISTIC if os.environ.get("HNSW_SELECT") == "heuristic" else ndb.HNSW_SELECT_CLOSEST
+t = time.time(); h.hnswbuild(X, levels=levels, select=select, batch=int(os.environ.get("HNSW_BATCH", "0"))); tb = time.time() - t
+print(f"GPU build n={n} dim={dim} M={m} efC={efc} select={'heuristic' if select else 'closest (reference)'}: {tb:.2f} s "
+      f"({n/tb:.0f} inserts/s), {h.last_evals()/n:.0f} evals/insert")
 gt = W.exact_ground_truth(X, Q[:500], 10)
+for extra_ef in [int(e) for e in os.environ.get("HNSW_EFS", "").split(",") if e]:
+    for _ in range(2):
+        t = time.time(); d, i = h.search(Q, extra_ef, 10, 1, ndb.HNSW_BESTFIRST); e2e = time.time() - t
+    ms, _, _ = ndb.last_kernel_stats()
+    print(f"GPU search best-first L2 ef={extra_ef}: kernel {ms:.3f} ms -> {nq/ms*1e3:.0f} QPS ({nq/e2e:.0f} e2e), "
+          f"{h.last_evals()/nq:.0f} evals/query, recall@10 {O.recall_at_k(i[:500], gt):.4f}")
 for mode, nm in ((ndb.HNSW_BESTFIRST, "best-first"), (ndb.HNSW_LITERAL, "literal")):
     for strategy, sn in ((1, "L2"), (2, "cosine")):
         for _ in range(3):
