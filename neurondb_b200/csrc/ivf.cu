@@ -587,7 +587,7 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
 {
     NDB_REQUIRE(ix->metric == NDB_L2 || ix->metric == NDB_IP, NDB_B200_EINVAL, "ivf tensor path: metric %d not supported (L2, IP)", ix->metric);
     NDB_REQUIRE(k <= TC_KMAX, NDB_B200_EINVAL, "ivf tensor path: k=%d > %d", k, TC_KMAX);
-    NDB_REQUIRE(ix->dim <= TC_MAX_CHUNKS * TC_KC, NDB_B200_EINVAL, "ivf tensor path: dim %d > %d", ix->dim, TC_MAX_CHUNKS * TC_KC);
+    NDB_REQUIRE(ix->dim <= TC_MAX_DIM, NDB_B200_EINVAL, "ivf tensor path: dim %d > %d", ix->dim, TC_MAX_DIM);
     NDB_CHECK(ivf_tensor_ready(ix, s));
     const int L = ix->nlists;
     const int64_t npairs = (int64_t) nq * np;

@@ -8,7 +8,8 @@ namespace ndb {
 constexpr int TC_M = 128;          // queries per tile  (TMEM lanes)
 constexpr int TC_N = 256;          // stored rows per tile (TMEM columns per accumulator)
 constexpr int TC_KC = 128;         // dims per K-chunk (one smem stage)
-constexpr int TC_MAX_CHUNKS = 2;   // dim <= 256 in this round
+constexpr int TC_MAX_CHUNKS = 2;   // K-chunks of a query tile that stay resident in shared memory (dim <= 256)
+constexpr int TC_MAX_DIM = 2048;   // beyond TC_MAX_CHUNKS chunks the query tile is streamed with the stored tiles
 constexpr int TC_KMAX = 16;        // k <= 16 (thread-local register list)
 constexpr int TC_PACKED_MAX_TILES = 16;   // packed-key epilogue: 11 index bits = 16 tiles x 128 columns per half
 

@@ -132,8 +132,28 @@ __global__ void tc_block_queries_kernel(const float *__restrict__ Q, const uint3
     *reinterpret_cast<uint4 *>(qb + off) = *reinterpret_cast<const uint4 *>(o);
     // squared norm of the rounded query: the row's 16 or 32 threads are adjacent lanes of one warp;
     // a fixed xor tree, so a query gets the same norm at whatever tile position it sits
-    for (int o2 = groups >> 1; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(FULL, part, o2);
-    if (g == 0) qnorm[q] = part;
+    // (more than 32 groups per row, dim > 256: tc_query_norms_kernel does it instead)
+    if (groups <= 32) {
+        for (int o2 = groups >> 1; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(FULL, part, o2);
+        if (g == 0) qnorm[q] = part;
+    }
+}
+
+// squared norm of the bf16-rounded query, one thread per tile position (rows of more than 256 dims)
+__global__ void tc_query_norms_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap, uint32_t nprobe, int nq,
+                                      int nqpad, const uint32_t *__restrict__ npos, int dim, float *__restrict__ qnorm)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (npos) nqpad = min(nqpad, (int) *npos);
+    if (q >= nqpad) return;
+    const int64_t src = qmap ? (qmap[q] != INVALID_SLOT ? (int64_t) (qmap[q] / nprobe) : -1) : (q < nq ? q : -1);
+    float acc = 0.0f;
+    if (src >= 0)
+        for (int d = 0; d < dim; d++) {
+            const float r = __bfloat162float(__float2bfloat16_rn(Q[(size_t) src * dim + d]));
+            acc = fmaf(r, r, acc);
+        }
+    qnorm[q] = acc;
 }
 
 // ---- tcgen05 / TMEM primitives -------------------------------------------------------------
@@ -360,6 +380,11 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
     // the Q region holds TC_MAX_CHUNKS 32 KB chunks: with one K-chunk (dim <= 128) it is used as two
     // buffers, so that the next item's query tile loads while this item's MMAs run
     const uint32_t nqbuf = p.nkc == 1 ? 2u : 1u;
+    // More than TC_MAX_CHUNKS K-chunks (dim > 256): the query tile no longer fits next to the X ring, so
+    // its chunks are streamed with the X chunks instead -- stage s holds X chunk c in the ring and Q chunk
+    // c in slot s of the Q region, both under full_bar[s] / empty_bar[s].  The Q chunk is re-read (from
+    // L2) for every stored tile: +50 % shared-memory fill traffic, same HBM traffic.
+    const bool q_streamed = p.nkc > TC_MAX_CHUNKS;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -369,20 +394,26 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                 const TcItem it = p.items[item];
                 const uint32_t qt = it.qtile;
                 const uint32_t qb_i = item_it % nqbuf, qn_i = item_it / nqbuf;
-                mbar_spin(&q_empty[qb_i], (qn_i & 1u) ^ 1u);           // MMA finished with this buffer's previous tile
-                mbar_arrive_expect_tx(&q_full[qb_i], (uint32_t) p.nkc * TC_QCHUNK_BYTES);
-                for (int c = 0; c < p.nkc; c++)
-                    tma_bulk_g2s(q_smem + (size_t) (qb_i * p.nkc + c) * TC_QCHUNK_BYTES,
-                                 reinterpret_cast<const unsigned char *>(p.qb) + ((size_t) qt * p.nkc + c) * TC_QCHUNK_BYTES,
-                                 TC_QCHUNK_BYTES, &q_full[qb_i]);
+                if (!q_streamed) {
+                    mbar_spin(&q_empty[qb_i], (qn_i & 1u) ^ 1u);       // MMA finished with this buffer's previous tile
+                    mbar_arrive_expect_tx(&q_full[qb_i], (uint32_t) p.nkc * TC_QCHUNK_BYTES);
+                    for (int c = 0; c < p.nkc; c++)
+                        tma_bulk_g2s(q_smem + (size_t) (qb_i * p.nkc + c) * TC_QCHUNK_BYTES,
+                                     reinterpret_cast<const unsigned char *>(p.qb) + ((size_t) qt * p.nkc + c) * TC_QCHUNK_BYTES,
+                                     TC_QCHUNK_BYTES, &q_full[qb_i]);
+                }
                 const uint32_t t0 = it.t0, t1 = it.t1;
                 for (uint32_t t = t0; t < t1; t++, tile_it++) {
                     for (int c = 0; c < p.nkc; c++, stage_it++) {
                         const uint32_t s = stage_it % TC_STAGES;
                         mbar_spin(&empty_bar[s], ((stage_it / TC_STAGES) & 1u) ^ 1u);
                         const bool skip_x = (p.debug_mode & 4) != 0;
-                        const uint32_t bytes = (skip_x ? 0 : TC_XSTAGE_BYTES) + (c == 0 ? TC_N * 4 : 0);
+                        const uint32_t bytes = (skip_x ? 0 : TC_XSTAGE_BYTES) + (c == 0 ? TC_N * 4 : 0) + (q_streamed ? TC_QCHUNK_BYTES : 0);
                         mbar_arrive_expect_tx(&full_bar[s], bytes);
+                        if (q_streamed)
+                            tma_bulk_g2s(q_smem + (size_t) s * TC_QCHUNK_BYTES,
+                                         reinterpret_cast<const unsigned char *>(p.qb) + ((size_t) qt * p.nkc + c) * TC_QCHUNK_BYTES,
+                                         TC_QCHUNK_BYTES, &full_bar[s]);
                         if (!skip_x) tma_bulk_g2s(x_smem + (size_t) s * TC_XSTAGE_BYTES,
                                      reinterpret_cast<const unsigned char *>(p.xb) + ((size_t) t * p.nkc + c) * TC_XSTAGE_BYTES,
                                      TC_XSTAGE_BYTES, &full_bar[s]);
@@ -402,8 +433,10 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                 const TcItem it = p.items[item];
                 const uint32_t t0 = it.t0, t1 = it.t1;
                 const uint32_t qb_i = item_it % nqbuf, qn_i = item_it / nqbuf;
-                mbar_spin(&q_full[qb_i], qn_i & 1u);
-                tc_fence_after();
+                if (!q_streamed) {
+                    mbar_spin(&q_full[qb_i], qn_i & 1u);
+                    tc_fence_after();
+                }
                 for (uint32_t t = t0; t < t1; t++, tile_it++) {
                     const uint32_t a = tile_it & 1u;
                     mbar_spin(&acc_empty[a], ((tile_it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
@@ -413,7 +446,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                         const uint32_t s = stage_it % TC_STAGES;
                         mbar_spin(&full_bar[s], (stage_it / TC_STAGES) & 1u);
                         tc_fence_after();
-                        const uint32_t qa = smem_u32(q_smem + (size_t) (qb_i * p.nkc + c) * TC_QCHUNK_BYTES);
+                        const uint32_t qa = smem_u32(q_smem + (size_t) (q_streamed ? s : qb_i * p.nkc + c) * TC_QCHUNK_BYTES);
                         const uint32_t xa = smem_u32(x_smem + (size_t) s * TC_XSTAGE_BYTES);
 #pragma unroll
                         for (int ks = 0; ks < TC_KC / 16; ks++) {
@@ -426,7 +459,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     }
                     umma_commit(&acc_full[a]);                          // accumulator complete
                 }
-                umma_commit(&q_empty[qb_i]);                            // Q buffer reusable
+                if (!q_streamed) umma_commit(&q_empty[qb_i]);           // Q buffer reusable
             }
         }
     } else if (warp >= 4) {
@@ -636,7 +669,7 @@ int tc_build_store(TcStore &st, const float *il32_store, int64_t n, int dim, int
 int tc_build_store_mapped(TcStore &st, const float *il32_store, const uint32_t *src_slot_dev, int64_t n, int dim, int dimp,
                           cudaStream_t s)
 {
-    NDB_REQUIRE(dim <= TC_MAX_CHUNKS * TC_KC, NDB_B200_EINVAL, "tensor path: dim %d > %d is not supported yet", dim, TC_MAX_CHUNKS * TC_KC);
+    NDB_REQUIRE(dim <= TC_MAX_DIM, NDB_B200_EINVAL, "tensor path: dim %d > %d is not supported", dim, TC_MAX_DIM);
     const int nkc = (dim + TC_KC - 1) / TC_KC;
     const int64_t ntiles = (n + TC_N - 1) / TC_N, npad = ntiles * TC_N;
     NDB_CHECK(st.xb.reserve((size_t) npad * nkc * TC_KC * 2));
@@ -662,6 +695,10 @@ int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t npro
     tc_block_queries_kernel<<<(unsigned) (((int64_t) nqpad * groups + 255) / 256), 256, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev,
                                                                                                 dim, nkc, qb, qnorm);
     count_launch();
+    if (groups > 32) {
+        tc_query_norms_kernel<<<(unsigned) ((nqpad + 127) / 128), 128, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev, dim, qnorm);
+        count_launch();
+    }
     NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
 }

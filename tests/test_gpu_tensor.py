@@ -16,7 +16,7 @@ def bf16_round(a):
     return u.astype(np.uint32).view(np.float32)
 
 
-@pytest.mark.parametrize("dim", [128, 64, 96, 200, 256])
+@pytest.mark.parametrize("dim", [128, 64, 96, 200, 256, 384, 768, 1000])      # > 256: query tile streamed
 def test_umma_tile_matches_numpy(ndb, dim):
     """Raw accumulator D = Q X^T of one 128 x 256 tile: validates the smem/instruction descriptors."""
     rng = np.random.default_rng(dim)
@@ -32,7 +32,8 @@ def test_umma_tile_matches_numpy(ndb, dim):
     assert np.max(np.abs(D - want)) < 1e-3 * np.max(np.abs(want)), np.max(np.abs(D - want))
 
 
-@pytest.mark.parametrize("n,dim,nq,k", [(5000, 128, 300, 10), (1000, 96, 130, 1), (70000, 128, 1000, 10), (300, 256, 7, 16)])
+@pytest.mark.parametrize("n,dim,nq,k", [(5000, 128, 300, 10), (1000, 96, 130, 1), (70000, 128, 1000, 10), (300, 256, 7, 16),
+                                         (6000, 768, 300, 10), (3000, 1536, 40, 10)])
 @pytest.mark.parametrize("metric", [1, 3])
 def test_tensor_knn_within_tolerance(ndb, orc, n, dim, nq, k, metric):
     X = bf16_round(W.gaussian(n, dim, 50 + n))          # config 5 data is bf16: inputs are representable
@@ -63,6 +64,7 @@ def test_tensor_knn_within_tolerance(ndb, orc, n, dim, nq, k, metric):
     (3000, 128, 100, 200, 100, 5, 1),     # nprobe > 16: fp32 coarse stage, all lists probed
     (150000, 64, 16, 300, 4, 16, 1),      # long lists -> several segments per list
     (400, 256, 8, 5, 3, 10, 1),           # two K-chunks, tiny lists
+    (8000, 384, 32, 300, 8, 10, 1),       # three K-chunks: the query tile is streamed with the stored tiles
     (300, 64, 32, 50, 16, 10, 1),         # lists shorter than the candidate count: pad rows must never rank
 ])
 def test_tensor_ivf_matches_fp32_path(ndb, orc, n, dim, lists, nq, nprobe, k, metric):

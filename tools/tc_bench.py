@@ -7,7 +7,7 @@ import neurondb_b200 as ndb
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 6_250_000
 nq = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000
-dim, k = 128, 10
+dim, k = (int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 128), 10
 ndb.init(0)
 ndb.set_timing(True)
 rng = np.random.default_rng(5)
