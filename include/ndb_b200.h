@@ -61,7 +61,7 @@ extern "C" {
 #define NDB_ARITH_HNSW     4  /* hnswComputeDistance: f32 op, f64 accumulate
                                  (hnsw_am.c:1301-1345)                                        */
 #define NDB_ARITH_FAST     5  /* fp32 FFMA, several accumulators: <= 1e-5 relative          */
-#define NDB_ARITH_TENSOR   6  /* bf16 tcgen05 tiles, fp32 accumulate; NDB_L2 / NDB_IP, dim <= 2048,
+#define NDB_ARITH_TENSOR   6  /* bf16 tcgen05 tiles, fp32 accumulate; all three metrics, dim <= 2048,
                                  k <= 16, anything else -> NDB_B200_EINVAL (no fallback).
                                  ndb_b200_knn_exact: distances <= 1e-3 relative.
                                  ndb_b200_ivf_search: the tensor cores only SELECT k + 6 candidates

@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_kernel(const float *__restr
         const float *qv = Q + (size_t) q * dim;
         const float *xv = arena + (size_t) tc_row[ts] * dim;
         typename P::Acc acc;
+        typename P::N vn = 0, qn = 0;                                 // cosine: the norms, in the same sequential order
         P::init(acc);
         if ((dim & 3) == 0) {
 #pragma unroll 8
@@ -327,11 +328,18 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_kernel(const float *__restr
                 P::step(acc, x.y, qv[j + 1]);
                 P::step(acc, x.z, qv[j + 2]);
                 P::step(acc, x.w, qv[j + 3]);
+                if (P::NORMS) {
+                    P::nstep(vn, x.x); P::nstep(vn, x.y); P::nstep(vn, x.z); P::nstep(vn, x.w);
+                    P::nstep(qn, qv[j]); P::nstep(qn, qv[j + 1]); P::nstep(qn, qv[j + 2]); P::nstep(qn, qv[j + 3]);
+                }
             }
         } else {
-            for (int j = 0; j < dim; j++) P::step(acc, xv[j], qv[j]);
+            for (int j = 0; j < dim; j++) {
+                P::step(acc, xv[j], qv[j]);
+                if (P::NORMS) { P::nstep(vn, xv[j]); P::nstep(qn, qv[j]); }
+            }
         }
-        ed = P::finish(acc, 0, 0);
+        ed = P::finish(acc, vn, qn);
         id = ids[tc_src[ts]];
     }
     WarpTopK<1, int64_t> top;
@@ -585,7 +593,6 @@ static int ivf_tc_margin()
 static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np, int k, float *dist_dev, int64_t *ids_dev,
                              cudaStream_t s)
 {
-    NDB_REQUIRE(ix->metric == NDB_L2 || ix->metric == NDB_IP, NDB_B200_EINVAL, "ivf tensor path: metric %d not supported (L2, IP)", ix->metric);
     NDB_REQUIRE(k <= TC_KMAX, NDB_B200_EINVAL, "ivf tensor path: k=%d > %d", k, TC_KMAX);
     NDB_REQUIRE(ix->dim <= TC_MAX_DIM, NDB_B200_EINVAL, "ivf tensor path: dim %d > %d", ix->dim, TC_MAX_DIM);
     NDB_CHECK(ivf_tensor_ready(ix, s));
@@ -664,6 +671,7 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     memset(&p, 0, sizeof(p));
     p.xb = ix->tc.xb.as<__nv_bfloat16>();
     p.xnorm = ix->tc.xnorm.as<float>();
+    if (ix->metric == NDB_COSINE) NDB_CHECK(tc_store_rinv(ix->tc, &p.xnorm, s));
     p.qb = ix->tcs.qb.as<__nv_bfloat16>();
     p.qnorm = ix->tcs.qnorm.as<float>();
     p.nkc = nkc;
@@ -699,6 +707,7 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
         ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), p.packed ? p.gthr : nullptr, \
         nq, np, L, segb, ix->dim, ix->dimp, kc, k, dist_dev, ids_dev)
     if (ix->metric == NDB_L2) NDB_FIN(NDB_L2);
+    else if (ix->metric == NDB_COSINE) NDB_FIN(NDB_COSINE);
     else NDB_FIN(NDB_IP);
 #undef NDB_FIN
     count_launch();

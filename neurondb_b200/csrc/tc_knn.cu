@@ -552,6 +552,13 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             c[4 * i4 + 1] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 1]), n4.y);
                             c[4 * i4 + 2] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 2]), n4.z);
                             c[4 * i4 + 3] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 3]), n4.w);
+                        } else if (METRIC == NDB_COSINE) {
+                            // p.xnorm holds 1 / ||x|| here (0 for a zero row, +inf for a pad row): -x.q / ||x||
+                            // orders the rows like the cosine distance, whose 1 / ||q|| is applied on output
+                            c[4 * i4 + 0] = n4.x == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 0]) * n4.x;
+                            c[4 * i4 + 1] = n4.y == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 1]) * n4.y;
+                            c[4 * i4 + 2] = n4.z == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 2]) * n4.z;
+                            c[4 * i4 + 3] = n4.w == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 3]) * n4.w;
                         } else {
                             c[4 * i4 + 0] = n4.x == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 0]);
                             c[4 * i4 + 1] = n4.y == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 1]);
@@ -644,6 +651,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                         } else {
                             slot = bi[j];
                             if (METRIC == NDB_L2 && slot != INVALID_SLOT) d = sqrtf(fmaxf(d + qn, 0.0f));
+                            if (METRIC == NDB_COSINE && slot != INVALID_SLOT) d = qn > 0.0f ? fmaf(d, 1.0f / sqrtf(qn), 1.0f) : 1.0f;
                         }
                         p.pdist[base + j] = d;
                         p.pslot[base + j] = slot;
@@ -682,8 +690,32 @@ int tc_build_store_mapped(TcStore &st, const float *il32_store, const uint32_t *
     count_launch(2);
     NDB_CUDA(cudaGetLastError());
     st.valid_for = n;
+    st.rinv_for = -2;
     st.ntiles = ntiles;
     st.nkc = nkc;
+    return NDB_B200_OK;
+}
+
+__global__ void tc_rinv_kernel(const float *__restrict__ xnorm, int64_t n, float *__restrict__ out)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = xnorm[i];
+    out[i] = v == INFINITY ? INFINITY : (v > 0.0f ? 1.0f / sqrtf(v) : 0.0f);
+}
+
+// per-row 1 / ||x|| for the cosine metric (built on first use, kept with the store)
+int tc_store_rinv(TcStore &st, const float **out, cudaStream_t s)
+{
+    const int64_t n = st.ntiles * TC_N;
+    if (st.rinv_for != st.valid_for || st.xrinv.cap < (size_t) n * 4) {
+        NDB_CHECK(st.xrinv.reserve((size_t) n * 4));
+        tc_rinv_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(st.xnorm.as<float>(), n, st.xrinv.as<float>());
+        count_launch();
+        NDB_CUDA(cudaGetLastError());
+        st.rinv_for = st.valid_for;
+    }
+    *out = st.xrinv.as<float>();
     return NDB_B200_OK;
 }
 
@@ -707,7 +739,7 @@ int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t npro
 int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s)
 {
     NDB_REQUIRE(k >= 1 && k <= TC_KMAX, NDB_B200_EINVAL, "tensor path: k must be 1..%d", TC_KMAX);
-    NDB_REQUIRE(metric == NDB_L2 || metric == NDB_IP, NDB_B200_EINVAL, "tensor path: metric %d not supported (L2, IP)", metric);
+    NDB_REQUIRE(metric == NDB_L2 || metric == NDB_IP || metric == NDB_COSINE, NDB_B200_EINVAL, "tensor path: metric %d not supported", metric);
     if (p.nitems == 0) return NDB_B200_OK;
     const size_t smem = tc_smem_bytes();
     const uint32_t sms = (uint32_t) ctx().sm_count;
@@ -734,6 +766,9 @@ int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s)
     if (metric == NDB_L2) {
         if (p.packed) NDB_TC_PICK(NDB_L2, true);
         else NDB_TC_PICK(NDB_L2, false);
+    } else if (metric == NDB_COSINE) {
+        if (p.packed) NDB_TC_PICK(NDB_COSINE, true);
+        else NDB_TC_PICK(NDB_COSINE, false);
     } else {
         if (p.packed) NDB_TC_PICK(NDB_IP, true);
         else NDB_TC_PICK(NDB_IP, false);
@@ -757,7 +792,7 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
            float *dist_dev, int64_t *ids_dev, uint32_t *slots_dev, float *debug_d_dev, bool packed, cudaStream_t s)
 {
     NDB_REQUIRE(k >= 1 && k <= TC_KMAX, NDB_B200_EINVAL, "tensor path: k must be 1..%d", TC_KMAX);
-    NDB_REQUIRE(metric == NDB_L2 || metric == NDB_IP, NDB_B200_EINVAL, "tensor path: metric %d not supported (L2, IP)", metric);
+    NDB_REQUIRE(metric == NDB_L2 || metric == NDB_IP || metric == NDB_COSINE, NDB_B200_EINVAL, "tensor path: metric %d not supported", metric);
     NDB_REQUIRE(st.ntiles > 0, NDB_B200_ESTATE, "tensor path: empty store");
     const int nkc = st.nkc;
     const uint32_t nqt = (uint32_t) ((nq + TC_M - 1) / TC_M);
@@ -801,6 +836,7 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     memset(&p, 0, sizeof(p));
     p.xb = st.xb.as<__nv_bfloat16>();
     p.xnorm = st.xnorm.as<float>();
+    if (metric == NDB_COSINE) NDB_CHECK(tc_store_rinv(const_cast<TcStore &>(st), &p.xnorm, s));
     p.qb = sc.qb.as<__nv_bfloat16>();
     p.qnorm = sc.qnorm.as<float>();
     p.nkc = nkc; p.k = k;

@@ -34,15 +34,15 @@ def test_umma_tile_matches_numpy(ndb, dim):
 
 @pytest.mark.parametrize("n,dim,nq,k", [(5000, 128, 300, 10), (1000, 96, 130, 1), (70000, 128, 1000, 10), (300, 256, 7, 16),
                                          (6000, 768, 300, 10), (3000, 1536, 40, 10)])
-@pytest.mark.parametrize("metric", [1, 3])
+@pytest.mark.parametrize("metric", [1, 2, 3])
 def test_tensor_knn_within_tolerance(ndb, orc, n, dim, nq, k, metric):
     X = bf16_round(W.gaussian(n, dim, 50 + n))          # config 5 data is bf16: inputs are representable
     Q = bf16_round(W.gaussian(nq, dim, 51 + n))
     ds = ndb.Dataset(dim)
     ds.append(X)
     d, i = ds.knn(Q, k, metric, ndb.ARITH_TENSOR)
-    if metric == 1:
-        od, oi = orc.knn_exact(X, Q, k, 1, orc.ARITH_OP_F64)
+    if metric in (1, 2):
+        od, oi = orc.knn_exact(X, Q, k, metric, orc.ARITH_OP_F64)
     else:
         # tensor IP = -dot (ranking by largest inner product, hnsw_am.c:1334-1337 sign convention)
         dots = Q.astype(np.float64) @ X.astype(np.float64).T
@@ -65,6 +65,8 @@ def test_tensor_knn_within_tolerance(ndb, orc, n, dim, nq, k, metric):
     (150000, 64, 16, 300, 4, 16, 1),      # long lists -> several segments per list
     (400, 256, 8, 5, 3, 10, 1),           # two K-chunks, tiny lists
     (8000, 384, 32, 300, 8, 10, 1),       # three K-chunks: the query tile is streamed with the stored tiles
+    (12000, 64, 48, 400, 8, 10, 2),       # vector_cosine_ops: lists scanned by cosine distance (coarse stage stays L2)
+    (2000, 128, 16, 50, 20, 10, 2),       # cosine, fp32 coarse stage, short lists
     (300, 64, 32, 50, 16, 10, 1),         # lists shorter than the candidate count: pad rows must never rank
 ])
 def test_tensor_ivf_matches_fp32_path(ndb, orc, n, dim, lists, nq, nprobe, k, metric):
@@ -95,11 +97,6 @@ def test_tensor_ivf_matches_fp32_path(ndb, orc, n, dim, lists, nq, nprobe, k, me
 
 def test_tensor_ivf_rejects_what_it_cannot_do(ndb):
     X = W.gaussian(500, 32, 1)
-    ix = ndb.IvfIndex(32, 4, ndb.COSINE)
-    ix.ivfbuild(X)
-    ix.ivfinsert(X)
-    with pytest.raises(ndb.NdbError):
-        ix.search(X[:3], 2, 10, ndb.IVF_FULL, ndb.ARITH_TENSOR)       # cosine
     ix2 = ndb.IvfIndex(32, 4, ndb.L2)
     ix2.ivfbuild(X)
     ix2.ivfinsert(X)
