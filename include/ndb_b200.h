@@ -56,6 +56,11 @@ extern "C" {
 #define NDB_ARITH_OP_F64   0  /* <->,<=>,<#> default build: fp64, Kahan for L2
                                  (src/vector/vector_distance.c:93-122,145-157,180-213);
                                  <#> yields +dot (vector_distance_simd.c:557)                  */
+#define NDB_ARITH_AVX2     1  /* the operators as an AVX2 build of the reference computes them
+                                 (vector_distance_simd.c:159-185,233-258,300-345): 8 f32 lane
+                                 accumulators, fixed reduction tree (:85-101), scalar tail;
+                                 ndb_b200_distance_pairs / _rows only                           */
+#define NDB_ARITH_AVX512   2  /* the same with 16 lanes (:188-217,261-291,348-392,120-137)      */
 #define NDB_ARITH_IVF_F32  3  /* ivfComputeDistance: f32 sequential (ivf_am.c:1550-1592);
                                  NDB_IP = -dot f32 sequential (not in the reference, Q5)     */
 #define NDB_ARITH_HNSW     4  /* hnswComputeDistance: f32 op, f64 accumulate

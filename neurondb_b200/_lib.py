@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libndb_b200.so")
 OK = 0
 L2, COSINE, IP = 1, 2, 3
 ARITH_OP_F64, ARITH_IVF_F32, ARITH_HNSW, ARITH_FAST, ARITH_TENSOR = 0, 3, 4, 5, 6
+ARITH_AVX2, ARITH_AVX512 = 1, 2
 IVF_FULL, IVF_LITERAL = 0, 1
 HNSW_LITERAL, HNSW_BESTFIRST = 0, 1
 HNSW_SELECT_CLOSEST, HNSW_SELECT_HEURISTIC = 0, 1

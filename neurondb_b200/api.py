@@ -9,7 +9,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from ._lib import (ARITH_FAST, ARITH_HNSW, ARITH_IVF_F32, ARITH_OP_F64, ARITH_TENSOR, COSINE, HNSW_BESTFIRST, HNSW_LITERAL,
+from ._lib import (ARITH_AVX2, ARITH_AVX512, ARITH_FAST, ARITH_HNSW, ARITH_IVF_F32, ARITH_OP_F64, ARITH_TENSOR, COSINE,
+                   HNSW_BESTFIRST, HNSW_LITERAL,
                    HNSW_SELECT_CLOSEST, HNSW_SELECT_HEURISTIC, IP,
                    IVF_FULL, IVF_LITERAL, L2, NdbError, check, f32, ptr)
 

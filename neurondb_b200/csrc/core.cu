@@ -140,6 +140,95 @@ __global__ void __launch_bounds__(128) pairs_kernel(const float *__restrict__ A,
     if (lane < np) out[p0 + lane] = P::finish(acc, na, nb);
 }
 
+// ---------------------------------------------------------------------------------------
+// The operators as an AVX build of the reference computes them (SURVEY 8a row a5;
+// vector_distance_simd.c:159-392 with the horizontal sums of :85-137): LANES (8 = AVX2, 16 =
+// AVX-512) f32 lane accumulators over the first dim / LANES * LANES elements, a fixed reduction
+// tree, then a scalar tail.  L2 and inner product multiply and add separately, cosine uses fmadd
+// (and, built with -mfma as the AVX2 build must be, gcc contracts its scalar tail too).  Element
+// i goes to lane accumulator i % LANES, which is static here because a tile column block starts
+// at a multiple of 32.
+// ---------------------------------------------------------------------------------------
+template <int LANES> __device__ __forceinline__ float avx_hsum(const float (&v)[LANES])
+{
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = LANES == 16 ? __fadd_rn(v[i], v[(i + 8) % LANES]) : v[i];
+    const float s0 = __fadd_rn(t[0], t[4]), s1 = __fadd_rn(t[1], t[5]), s2 = __fadd_rn(t[2], t[6]), s3 = __fadd_rn(t[3], t[7]);
+    return __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+}
+
+template <int METRIC, int LANES>
+__global__ void __launch_bounds__(128) pairs_avx_kernel(const float *__restrict__ A, const float *__restrict__ B,
+                                                         float *__restrict__ out, int64_t n, int dim, int64_t b_stride)
+{
+    __shared__ float ta[4][32][33];
+    __shared__ float tb[4][32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t p0 = ((int64_t) blockIdx.x * 4 + w) * 32;
+    if (p0 >= n) return;
+    const int np = (int) (n - p0 < 32 ? n - p0 : 32);
+    const int simd_end = dim / LANES * LANES;
+    float d[LANES], na[LANES], nb[LANES];
+#pragma unroll
+    for (int l = 0; l < LANES; l++) { d[l] = 0.0f; na[l] = 0.0f; nb[l] = 0.0f; }
+    float sum = 0.0f, suma = 0.0f, sumb = 0.0f;          // after the reduction tree: the scalar tail runs on these
+    for (int c0 = 0; c0 < dim; c0 += 32) {
+        const int cw = dim - c0 < 32 ? dim - c0 : 32;
+        for (int r = 0; r < np; r++) {
+            if (lane < cw) {
+                ta[w][r][lane] = A[(size_t) (p0 + r) * dim + c0 + lane];
+                tb[w][r][lane] = B[(size_t) (p0 + r) * b_stride + c0 + lane];
+            }
+        }
+        __syncwarp();
+        if (lane < np) {
+            const int vec_cw = min(cw, simd_end - c0);               // elements of this block inside the vector body
+            for (int j0 = 0; j0 + LANES <= vec_cw; j0 += LANES) {
+#pragma unroll
+                for (int l = 0; l < LANES; l++) {
+                    const float x = ta[w][lane][j0 + l], q = tb[w][lane][j0 + l];
+                    if (METRIC == NDB_L2) {
+                        const float df = __fsub_rn(x, q);
+                        d[l] = __fadd_rn(d[l], __fmul_rn(df, df));
+                    } else if (METRIC == NDB_IP) {
+                        d[l] = __fadd_rn(d[l], __fmul_rn(x, q));
+                    } else {
+                        d[l] = __fmaf_rn(x, q, d[l]);
+                        na[l] = __fmaf_rn(x, x, na[l]);
+                        nb[l] = __fmaf_rn(q, q, nb[l]);
+                    }
+                }
+            }
+            if (c0 + cw == dim) {                                    // last block: reduce, then the scalar tail
+                sum = avx_hsum<LANES>(d);
+                if (METRIC == NDB_COSINE) { suma = avx_hsum<LANES>(na); sumb = avx_hsum<LANES>(nb); }
+                for (int j = max(simd_end - c0, 0); j < cw; j++) {
+                    const float x = ta[w][lane][j], q = tb[w][lane][j];
+                    if (METRIC == NDB_L2) {
+                        const float df = __fsub_rn(x, q);
+                        sum = __fadd_rn(sum, __fmul_rn(df, df));
+                    } else if (METRIC == NDB_IP) {
+                        sum = __fadd_rn(sum, __fmul_rn(x, q));
+                    } else {
+                        sum = __fmaf_rn(x, q, sum);
+                        suma = __fmaf_rn(x, x, suma);
+                        sumb = __fmaf_rn(q, q, sumb);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < np) {
+        float r;
+        if (METRIC == NDB_L2) r = __fsqrt_rn(sum);
+        else if (METRIC == NDB_IP) r = sum;                           // inner_product_simd's +dot (Q3)
+        else r = (suma == 0.0f || sumb == 0.0f) ? 1.0f : __fsub_rn(1.0f, __fdiv_rn(sum, __fmul_rn(__fsqrt_rn(suma), __fsqrt_rn(sumb))));
+        out[p0 + lane] = r;
+    }
+}
+
 // the CUDA backend's cosine (gpu_backend_cuda.c:459-537): Sdot / (Snrm2 * Snrm2), clamped to
 // [-1,1], 1.0 when a norm is <= 0.  cuBLAS level-1 summation order is unspecified, so this is
 // the fp32 tolerance path.
@@ -173,6 +262,9 @@ static int run_pairs(const float *dA, const float *dB, float *dOut, int64_t n, i
 int launch_pairs(int metric, int arith, const float *dA, const float *dB, float *dOut, int64_t n, int dim,
                  int64_t b_stride, cudaStream_t s)
 {
+    // the *_simd dispatchers (vector_distance_simd.c:467-509,516-558,571-613) take the SIMD body only when
+    // dim >= lanes (and an AVX-512 build skips its AVX2 branch): shorter vectors go to the scalar functions
+    if ((arith == NDB_ARITH_AVX2 && dim < 8) || (arith == NDB_ARITH_AVX512 && dim < 16)) arith = NDB_ARITH_OP_F64;
 #define NDB_PAIRS_CASE(M, A) \
     if (metric == M && arith == A) return run_pairs<Arith<M, A>>(dA, dB, dOut, n, dim, b_stride, s);
     NDB_PAIRS_CASE(NDB_L2, NDB_ARITH_OP_F64)
@@ -188,6 +280,21 @@ int launch_pairs(int metric, int arith, const float *dA, const float *dB, float 
     NDB_PAIRS_CASE(NDB_COSINE, NDB_ARITH_FAST)
     NDB_PAIRS_CASE(NDB_IP, NDB_ARITH_FAST)
 #undef NDB_PAIRS_CASE
+    if (arith == NDB_ARITH_AVX2 || arith == NDB_ARITH_AVX512) {
+        const unsigned blocks = (unsigned) ((n + 127) / 128);
+#define NDB_AVX_CASE(M)                                                                                              \
+        if (metric == M) {                                                                                           \
+            if (arith == NDB_ARITH_AVX2) pairs_avx_kernel<M, 8><<<blocks, 128, 0, s>>>(dA, dB, dOut, n, dim, b_stride); \
+            else pairs_avx_kernel<M, 16><<<blocks, 128, 0, s>>>(dA, dB, dOut, n, dim, b_stride);                     \
+            count_launch();                                                                                          \
+            NDB_CUDA(cudaGetLastError());                                                                            \
+            return NDB_B200_OK;                                                                                      \
+        }
+        NDB_AVX_CASE(NDB_L2)
+        NDB_AVX_CASE(NDB_COSINE)
+        NDB_AVX_CASE(NDB_IP)
+#undef NDB_AVX_CASE
+    }
     set_error("unsupported metric/arith combination %d/%d", metric, arith);
     return NDB_B200_EINVAL;
 }

@@ -225,3 +225,29 @@ def test_keys_from_vector_datums(ndb):
     with pytest.raises(ndb.NdbError) as e:
         ndb.keys_from_vector(datums, dim)
     assert "datum 5" in str(e.value)
+
+
+@pytest.mark.parametrize("metric", [1, 2, 3])
+def test_operator_distances_as_an_avx_build_computes_them(ndb, orc, metric):
+    """8 / 16 f32 lane accumulators, fixed reduction tree, scalar tail -- bit for bit
+    against the oracle's lane-by-lane restatement and, for AVX2, the reference's own sources built
+    with -mavx2 -mfma under the shim."""
+    rng = np.random.default_rng(metric)
+    for dim in list(range(1, 41)) + [63, 64, 65, 127, 128, 129, 768, 1000]:
+        A = rng.standard_normal((67, dim)).astype(np.float32)
+        B = rng.standard_normal((67, dim)).astype(np.float32)
+        if dim > 3:
+            A[5] = 0.0                                        # zero norm: cosine returns 1.0
+        for arith, oarith in ((ndb.ARITH_AVX2, orc.ARITH_AVX2), (ndb.ARITH_AVX512, orc.ARITH_AVX512)):
+            got = ndb.distance_pairs(A, B, metric, arith)
+            want = orc.distance_pairs(A, B, metric, oarith)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (dim, arith)
+        if orc.ref_lib(avx2=True) is not None:
+            ref = orc.ref_distance_pairs(metric, A, B, avx2=True)
+            assert np.array_equal(ndb.distance_pairs(A, B, metric, ndb.ARITH_AVX2).view(np.uint32), ref.view(np.uint32)), dim
+    # one query against rows (vector_*_distance_batch)
+    X = rng.standard_normal((100, 24)).astype(np.float32)
+    q = rng.standard_normal(24).astype(np.float32)
+    got = ndb.distance_rows(X, q, metric, ndb.ARITH_AVX2)
+    want = orc.distance_pairs(X, np.repeat(q[None], 100, 0), metric, orc.ARITH_AVX2)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
