@@ -657,6 +657,23 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
                                                                 ix->tcs.items.as<TcItem>());
     count_launch(2);
     NDB_CUDA(cudaGetLastError());
+    if (getenv("NDB_IVF_DEBUG")) {
+        // tile-steps by live queries per item: how full are the 128-query tiles the tensor cores work on
+        uint32_t cnt_h[2];
+        NDB_CUDA(cudaMemcpyAsync(cnt_h, ix->nitems.p, 8, cudaMemcpyDeviceToHost, s));
+        NDB_CUDA(cudaStreamSynchronize(s));
+        std::vector<TcItem> hi(cnt_h[0]);
+        NDB_CUDA(cudaMemcpy(hi.data(), ix->tcs.items.p, hi.size() * sizeof(TcItem), cudaMemcpyDeviceToHost));
+        unsigned long long steps[5] = {0, 0, 0, 0, 0}, tot = 0, live = 0;
+        for (const TcItem &t : hi) {
+            const unsigned ts = t.t1 - t.t0;
+            steps[t.nq <= 16 ? 0 : t.nq <= 32 ? 1 : t.nq <= 64 ? 2 : t.nq <= 96 ? 3 : 4] += ts;
+            tot += ts;
+            live += (unsigned long long) ts * t.nq;
+        }
+        fprintf(stderr, "ivf tensor: %u items, %llu tile-steps; by live queries <=16:%llu <=32:%llu <=64:%llu <=96:%llu <=128:%llu; mean live %.1f\n",
+                cnt_h[0], tot, steps[0], steps[1], steps[2], steps[3], steps[4], tot ? (double) live / tot : 0.0);
+    }
 
     // 3. gather the query tiles (blocked bf16) and run the tensor kernel over the items
     const int nkc = ix->tc.nkc;

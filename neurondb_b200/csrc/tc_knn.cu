@@ -126,7 +126,11 @@ __global__ void tc_block_queries_kernel(const float *__restrict__ Q, const uint3
         const float r = __bfloat162float(o[i]);
         part = fmaf(r, r, part);
     }
-    const int tile = q / TC_M, rr = q % TC_M;
+    // Query i of a tile sits on TMEM lane (i % 4) * 32 + i / 4: the tile's queries are dealt round-robin
+    // to the four lane quarters, each of which only one pair of epilogue warps can read.  A tile with 16
+    // live queries (most tile-steps of an IVF batch: long lists probed by a few queries) then keeps all
+    // eight epilogue warps busy with 4 queries each instead of two warps with 16.
+    const int tile = q / TC_M, qi_ = q % TC_M, rr = (qi_ & 3) * 32 + (qi_ >> 2);
     const int chunk = g / (TC_KC / 8), kc = g % (TC_KC / 8);
     const size_t off = ((((size_t) (tile * nkc + chunk) * (TC_KC / 8) + kc) * (TC_M / 8) + (rr >> 3)) * 8 + (rr & 7)) * 8;
     *reinterpret_cast<uint4 *>(qb + off) = *reinterpret_cast<const uint4 *>(o);
@@ -467,7 +471,8 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
         // warps 4-7 read accumulator columns [0,128), warps 8-11 columns [128,256) of the same 128
         // TMEM lanes (a warp may only touch the lane quarter 32*(warp%4)); each thread keeps its own
         // top-KT list and the two halves are merged with the other parts afterwards.
-        const int ql = (warp & 3) * 32 + lane;                          // TMEM lane = query within the tile
+        const int ql = lane * 4 + (warp & 3);                           // query within the tile; it sits on TMEM lane
+                                                                        // (warp & 3) * 32 + lane (tc_block_queries_kernel)
         const int half = (warp - 4) >> 2;
         const uint32_t lane_addr = (uint32_t) ((warp & 3) * 32) << 16;
         uint32_t tile_it = 0;
@@ -517,7 +522,11 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                 const float *xn = n_smem + (size_t) (tile_it % TC_NORM_RING) * TC_N;
                 // PACKED (short items, latency-bound epilogue): the TMEM read of chunk j + 1 is in flight
                 // while chunk j is processed.  The dense kernel is ALU-bound and keeps the plain order.
-                const int nchunk = (p.debug_mode & 1) ? 0 : TC_N / 64;
+                // a warp whose 32 query lanes are all beyond the item's query count has nothing to read: it
+                // only keeps the accumulator hand-shake in step (most tile-steps of an IVF batch belong to
+                // long lists probed by a handful of queries)
+                const bool warp_dead = (uint32_t) (warp & 3) >= it.nq;          // (its first lane's query is the lowest)
+                const int nchunk = ((p.debug_mode & 1) || warp_dead) ? 0 : TC_N / 64;
                 uint32_t vn[PACKED ? 32 : 1];
                 if (PACKED && nchunk) tmem_ld32(tmem_base + lane_addr + a * TC_N + half * (TC_N / 2), (uint32_t (&)[32]) vn);
 #pragma unroll 1
