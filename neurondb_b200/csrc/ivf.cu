@@ -89,6 +89,13 @@ static uint32_t ivf_seg_blocks()
     return v;
 }
 
+// Tensor path: a list probed by at most rep_max queries of the batch gets every query FOUR times, on
+// consecutive tile positions (= the same lane of the four TMEM lane quarters, see
+// tc_block_queries_kernel), and each replica's epilogue thread scans a quarter of its column half.
+// Most tile-steps of a batch belong to long lists probed by a handful of queries; this cuts the
+// serial epilogue work per tile of exactly those from 128 columns per thread to 32.
+__host__ __device__ inline uint32_t ivf_rep(uint32_t c, uint32_t rep_max) { return c <= rep_max ? 4u : 1u; }
+
 // ---- work-item construction -----------------------------------------------------------------
 __global__ void ivf_hist_kernel(const uint32_t *__restrict__ probe, int64_t npairs, const uint32_t *__restrict__ list_len,
                                 int nlists, uint32_t *__restrict__ cnt)
@@ -102,8 +109,9 @@ __global__ void ivf_hist_kernel(const uint32_t *__restrict__ probe, int64_t npai
 // single CTA: exclusive scans, in `order`, of cnt (-> qoff) and of tiles * segments (-> item_off)
 __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ list_len,
                                                            const uint32_t *__restrict__ order, int nlists, int qt, uint32_t segb,
-                                                           uint32_t qalign, uint32_t *__restrict__ qoff, uint32_t *__restrict__ item_off,
-                                                           uint32_t *__restrict__ nitems, unsigned long long *__restrict__ scanned)
+                                                           uint32_t qalign, uint32_t rep_max, uint32_t *__restrict__ qoff,
+                                                           uint32_t *__restrict__ item_off, uint32_t *__restrict__ nitems,
+                                                           unsigned long long *__restrict__ scanned)
 {
     typedef cub::BlockScan<uint32_t, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
@@ -114,9 +122,9 @@ __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__res
     uint32_t sq = 0, st = 0;
     unsigned long long sc = 0;
     for (int i = b; i < e; i++) {
-        const uint32_t l = order[i], c = cnt[l];
-        sq += (c + qalign - 1) / qalign * qalign;
-        st += ((c + qt - 1) / qt) * ivf_nseg(list_len[l], segb);
+        const uint32_t l = order[i], c = cnt[l], cr = c * ivf_rep(c, rep_max);
+        sq += (cr + qalign - 1) / qalign * qalign;
+        st += ((cr + qt - 1) / qt) * ivf_nseg(list_len[l], segb);
         sc += (unsigned long long) c * list_len[l];
     }
     uint32_t oq, ot;
@@ -128,11 +136,11 @@ __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__res
     for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(FULL, sc, o);
     if ((threadIdx.x & 31) == 0 && sc) atomicAdd(&s_scanned, sc);
     for (int i = b; i < e; i++) {
-        const uint32_t l = order[i], c = cnt[l];
+        const uint32_t l = order[i], c = cnt[l], cr = c * ivf_rep(c, rep_max);
         qoff[l] = oq;
         item_off[l] = ot;
-        oq += (c + qalign - 1) / qalign * qalign;
-        ot += ((c + qt - 1) / qt) * ivf_nseg(list_len[l], segb);
+        oq += (cr + qalign - 1) / qalign * qalign;
+        ot += ((cr + qt - 1) / qt) * ivf_nseg(list_len[l], segb);
     }
     if (threadIdx.x == 1023) { nitems[0] = ot; nitems[1] = oq; }   // last thread's running totals == grand totals
     __syncthreads();
@@ -141,14 +149,16 @@ __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__res
 
 __global__ void ivf_scatter_kernel(const uint32_t *__restrict__ probe, int64_t npairs, const uint32_t *__restrict__ list_len,
                                    int nlists, const uint32_t *__restrict__ qoff, uint32_t *__restrict__ fill,
-                                   uint32_t *__restrict__ qmap, uint32_t *__restrict__ pairpos)
+                                   uint32_t *__restrict__ qmap, uint32_t *__restrict__ pairpos,
+                                   const uint32_t *__restrict__ cnt, uint32_t rep_max)
 {
     const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     const uint32_t l = probe[p];
     if (l < (uint32_t) nlists && list_len[l] > 0) {
         const uint32_t pos = atomicAdd(&fill[l], 1u);      // position of this query among the list's queries
-        qmap[qoff[l] + pos] = (uint32_t) p;
+        const uint32_t r = cnt ? ivf_rep(cnt[l], rep_max) : 1u;
+        for (uint32_t j = 0; j < r; j++) qmap[qoff[l] + pos * r + j] = (uint32_t) p;
         pairpos[p] = pos;
     }
 }
@@ -232,11 +242,13 @@ __global__ void ivf_merge_kernel(const float *__restrict__ pdist, const uint32_t
 // blocks, so the bucketing kernels above are shared with the fp32 path.
 __global__ void ivf_tc_items_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ qoff,
                                     const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len,
-                                    const uint32_t *__restrict__ ltile8, int nlists, uint32_t segb, TcItem *__restrict__ items)
+                                    const uint32_t *__restrict__ ltile8, int nlists, uint32_t segb, uint32_t rep_max,
+                                    TcItem *__restrict__ items)
 {
     const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (l >= nlists) return;
-    const uint32_t c = cnt[l];
+    const uint32_t rp = ivf_rep(cnt[l], rep_max);
+    const uint32_t c = cnt[l] * rp;                            // tile positions in use
     const uint32_t tiles = (c + TC_M - 1) / TC_M;
     const uint32_t len = list_len[l], nseg = ivf_nseg(len, segb);
     for (uint32_t i = threadIdx.x & 31; i < tiles * nseg; i += 32) {
@@ -249,6 +261,7 @@ __global__ void ivf_tc_items_kernel(const uint32_t *__restrict__ cnt, const uint
         it.nq = min((uint32_t) TC_M, c - t * TC_M);
         it.out_base = (item_off[l] + i) * (2 * TC_M);
         it.out_stride = 2;
+        it.rep = rp;
         items[item_off[l] + i] = it;
     }
 }
@@ -264,7 +277,8 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_kernel(const float *__restr
                                                             const float *__restrict__ Q,
                                                             const uint32_t *__restrict__ probe, const uint32_t *__restrict__ pairpos,
                                                             const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len,
-                                                            const float *__restrict__ gthr, int nq, int nprobe, int nlists,
+                                                            const float *__restrict__ gthr, const uint32_t *__restrict__ cnt,
+                                                            uint32_t rep_max, int nq, int nprobe, int nlists,
                                                             uint32_t segb, int dim, int dimp, int kc, int k,
                                                             float *__restrict__ out_dist, int64_t *__restrict__ out_ids)
 {
@@ -278,14 +292,15 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_kernel(const float *__restr
     const float bound = gthr ? gthr[q] : INFINITY;
     for (int r0 = 0; r0 < nprobe; r0 += 32) {
         // lane r: where the partial lists of probe r0 + r start, and how many segments there are
-        uint32_t my_first = 0, my_nseg = 0;
+        uint32_t my_first = 0, my_nseg = 0, my_rep = 1;
         if (r0 + lane < nprobe) {
             const size_t p = (size_t) q * nprobe + r0 + lane;
             const uint32_t l = probe[p];
             if (l < (uint32_t) nlists) {
                 const uint32_t len = list_len[l];
                 if (len) {
-                    const uint32_t pos = pairpos[p];
+                    my_rep = ivf_rep(cnt[l], rep_max);
+                    const uint32_t pos = pairpos[p] * my_rep;        // first of the query's (replicated) tile positions
                     my_nseg = ivf_nseg(len, segb);
                     my_first = (item_off[l] + (pos / TC_M) * my_nseg) * (2 * TC_M) + (pos % TC_M) * 2;
                 }
@@ -294,13 +309,14 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_kernel(const float *__restr
         const int nr = min(32, nprobe - r0);
         for (int r = 0; r < nr; r++) {
             const uint32_t nseg = __shfl_sync(FULL, my_nseg, r), first = __shfl_sync(FULL, my_first, r);
-            // the two halves' kc entries are contiguous per (item, lane-in-tile)
+            const int nent = (int) __shfl_sync(FULL, my_rep, r) * 2 * kc;
+            // the kc entries of the query's replicas and column halves are contiguous per item
             for (uint32_t sg = 0; sg < nseg; sg++) {
                 const size_t base = ((size_t) first + (size_t) sg * (2 * TC_M)) * kc;
-                for (int i = lane; i < round_up(2 * kc, 32); i += 32) {
+                for (int i = lane; i < round_up(nent, 32); i += 32) {
                     float cd = INFINITY;
                     uint32_t slot = INVALID_SLOT;
-                    if (i < 2 * kc) { slot = pslot[base + i]; cd = pdist[base + i]; }
+                    if (i < nent) { slot = pslot[base + i]; cd = pdist[base + i]; }
                     const bool ok = slot != INVALID_SLOT && cd <= bound;
                     if (__any_sync(FULL, ok)) cand.offer(cd, slot, ok, lane, kc);
                 }
@@ -621,8 +637,9 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     const uint32_t segb = ivf_tc_seg_tiles() * 8;
     NDB_CUDA(cudaMemsetAsync(cnt, 0, (size_t) L * 4 * 2, s));
     ivf_hist_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L, cnt);
+    static const uint32_t rep_max = [] { const char *e = getenv("NDB_IVF_TC_REP_MAX"); int x = e ? atoi(e) : 32; return (uint32_t) (x >= 0 && x <= 32 ? x : 32); }();
     ivf_offsets_kernel<<<1, 1024, 0, s>>>(cnt, ix->d_list_len.as<uint32_t>(), ix->d_list_order.as<uint32_t>(), L, TC_M, segb,
-                                          (uint32_t) TC_M, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
+                                          (uint32_t) TC_M, rep_max, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
                                           ix->nitems.as<uint32_t>(), ix->stats.as<unsigned long long>());
     count_launch(2);
     NDB_CUDA(cudaGetLastError());
@@ -650,11 +667,11 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     NDB_CUDA(cudaMemsetAsync(ix->qmap.p, 0xFF, npos * 4, s));
     ivf_scatter_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L,
                                                                         ix->qoff.as<uint32_t>(), fill, ix->qmap.as<uint32_t>(),
-                                                                        ix->pairpos.as<uint32_t>());
+                                                                        ix->pairpos.as<uint32_t>(), cnt, rep_max);
     NDB_CHECK(ix->tcs.items.reserve(n_items * sizeof(TcItem)));
     ivf_tc_items_kernel<<<(unsigned) ((L + 3) / 4), 128, 0, s>>>(cnt, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
                                                                 ix->d_list_len.as<uint32_t>(), ix->d_ltile8.as<uint32_t>(), L, segb,
-                                                                ix->tcs.items.as<TcItem>());
+                                                                rep_max, ix->tcs.items.as<TcItem>());
     count_launch(2);
     NDB_CUDA(cudaGetLastError());
     if (getenv("NDB_IVF_DEBUG")) {
@@ -721,7 +738,7 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     ivf_tc_finish_kernel<Arith<M, NDB_ARITH_IVF_F32>><<<mgrid, 128, 0, s>>>(                                   \
         ix->tcs.pdist.as<float>(), ix->tcs.pslot.as<uint32_t>(), ix->tc_src.as<uint32_t>(), ix->tc_row.as<uint32_t>(),  \
         ix->arena.as<float>(), ix->ids.as<int64_t>(), Q_dev, ix->probe.as<uint32_t>(),                                  \
-        ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), p.packed ? p.gthr : nullptr, \
+        ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), p.packed ? p.gthr : nullptr, cnt, rep_max, \
         nq, np, L, segb, ix->dim, ix->dimp, kc, k, dist_dev, ids_dev)
     if (ix->metric == NDB_L2) NDB_FIN(NDB_L2);
     else if (ix->metric == NDB_COSINE) NDB_FIN(NDB_COSINE);
@@ -1016,7 +1033,7 @@ int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np
     NDB_CUDA(cudaMemsetAsync(cnt, 0, (size_t) L * 4 * 2, s));
     ivf_hist_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L, cnt);
     const uint32_t segb = ivf_seg_blocks();
-    ivf_offsets_kernel<<<1, 1024, 0, s>>>(cnt, ix->d_list_len.as<uint32_t>(), ix->d_list_order.as<uint32_t>(), L, qt, segb, 1u,
+    ivf_offsets_kernel<<<1, 1024, 0, s>>>(cnt, ix->d_list_len.as<uint32_t>(), ix->d_list_order.as<uint32_t>(), L, qt, segb, 1u, 0u,
                                           ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->nitems.as<uint32_t>(),
                                           ix->stats.as<unsigned long long>());
     // the number of work items depends on how the batch's probes fall on long and short lists:
@@ -1025,7 +1042,7 @@ int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np
     NDB_CUDA(cudaMemcpyAsync(h_nitems, ix->nitems.p, 4, cudaMemcpyDeviceToHost, s));
     ivf_scatter_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L,
                                                                         ix->qoff.as<uint32_t>(), fill, ix->qmap.as<uint32_t>(),
-                                                                        ix->pairpos.as<uint32_t>());
+                                                                        ix->pairpos.as<uint32_t>(), nullptr, 0u);
     count_launch(3);
     NDB_CUDA(cudaGetLastError());
     NDB_CUDA(cudaStreamSynchronize(s));

@@ -26,6 +26,9 @@ struct TcStore {
 // out_base + ql * out_stride + h, for ql < nq
 struct TcItem {
     uint32_t qtile, t0, t1, nq, out_base, out_stride;
+    uint32_t rep;       // 4: every query sits on four consecutive tile positions and replica r scans only the r-th
+                        // 32-column chunk of its column half (sparsely probed IVF lists); else 1
+    uint32_t pad_;
 };
 
 struct TcScratch {

@@ -526,11 +526,13 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                 // only keeps the accumulator hand-shake in step (most tile-steps of an IVF batch belong to
                 // long lists probed by a handful of queries)
                 const bool warp_dead = (uint32_t) (warp & 3) >= it.nq;          // (its first lane's query is the lowest)
-                const int nchunk = ((p.debug_mode & 1) || warp_dead) ? 0 : TC_N / 64;
+                // replicated queries (it.rep == 4): this warp's lanes are replica (warp & 3) and scan chunk (warp & 3) only
+                const int jlo = it.rep == 4 ? (warp & 3) : 0;
+                const int nchunk = ((p.debug_mode & 1) || warp_dead) ? 0 : (it.rep == 4 ? jlo + 1 : TC_N / 64);
                 uint32_t vn[PACKED ? 32 : 1];
-                if (PACKED && nchunk) tmem_ld32(tmem_base + lane_addr + a * TC_N + half * (TC_N / 2), (uint32_t (&)[32]) vn);
+                if (PACKED && nchunk) tmem_ld32(tmem_base + lane_addr + a * TC_N + half * (TC_N / 2) + jlo * 32, (uint32_t (&)[32]) vn);
 #pragma unroll 1
-                for (int j = 0; j < nchunk; j++) {
+                for (int j = jlo; j < nchunk; j++) {
                     const int col0 = half * (TC_N / 2) + j * 32;
                     // this chunk's row norms first: their shared-memory latency overlaps the TMEM wait
                     float4 n4s[8];
@@ -837,6 +839,8 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
         it.nq = (uint32_t) std::min<int>(TC_M, nq - (int) qt * TC_M);
         it.out_base = qt * TC_M * nranges * 2 + xr * 2;
         it.out_stride = nranges * 2;
+        it.rep = 1;
+        it.pad_ = 0;
     }
     NDB_CHECK(sc.items.reserve((size_t) nitems * sizeof(TcItem)));
     NDB_CUDA(cudaMemcpyAsync(sc.items.p, items.data(), (size_t) nitems * sizeof(TcItem), cudaMemcpyHostToDevice, s));
