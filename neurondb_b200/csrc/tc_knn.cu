@@ -103,69 +103,61 @@ __global__ void tc_row_norms_kernel(const float4 *__restrict__ store, const uint
     xnorm[row] = acc;
 }
 
-// row-major fp32 queries -> blocked bf16 query tiles + squared norms of the rounded queries.
-// One CTA per 128-query tile.  A tile's K-chunk in the blocked layout is one contiguous 32 KB run, so the
-// CTA assembles it in shared memory (a warp reads one query row per step, 512 coalesced bytes) and then
-// copies the 32 KB out with fully coalesced 16-byte stores; writing the layout's 16-byte units straight
-// from the row order would touch a different 128-byte line with every lane.
-// qmap (optional): tile position q holds query qmap[q] / nprobe (INVALID_SLOT = empty position).
-// Query i of a tile sits on TMEM lane (i % 4) * 32 + i / 4: the tile's queries are dealt round-robin
-// to the four lane quarters, each of which only one pair of epilogue warps can read.  A tile with 16
-// live queries (most tile-steps of an IVF batch: long lists probed by a few queries) then keeps all
-// eight epilogue warps busy with 4 queries each instead of two warps with 16.
-// The norm of a row is a fixed reduction (4 elements per lane in order, xor tree, chunks in order), so
-// a query gets the same norm at whatever tile position it sits.
-__global__ void __launch_bounds__(256) tc_block_queries_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap,
-                                                                uint32_t nprobe, int nq, int nqpad,
-                                                                const uint32_t *__restrict__ npos, int dim, int nkc,
-                                                                __nv_bfloat16 *__restrict__ qb, float *__restrict__ qnorm)
+// row-major fp32 queries -> blocked bf16 query tiles + squared norms
+// qmap (optional): tile position q holds query qmap[q] / nprobe (INVALID_SLOT = empty position)
+__global__ void tc_block_queries_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap, uint32_t nprobe,
+                                        int nq, int nqpad, const uint32_t *__restrict__ npos, int dim, int nkc,
+                                        __nv_bfloat16 *__restrict__ qb, float *__restrict__ qnorm)
 {
-    __shared__ __align__(16) __nv_bfloat16 tile_s[TC_M * TC_KC];      // one K-chunk of the tile, blocked layout
-    __shared__ float norm_s[TC_M];
-    const int tile = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (npos) nqpad = min(nqpad, (int) *npos);
-    if (tile * TC_M >= nqpad) return;
-    for (int r = threadIdx.x; r < TC_M; r += blockDim.x) norm_s[r] = 0.0f;
-    __syncthreads();
-    for (int c = 0; c < nkc; c++) {
-        for (int r = w; r < TC_M; r += 8) {                            // logical position r of the tile
-            const int q = tile * TC_M + r;
-            const int64_t src = qmap ? (qmap[q] != INVALID_SLOT ? (int64_t) (qmap[q] / nprobe) : -1) : (q < nq ? q : -1);
-            const int d0 = c * TC_KC + 4 * lane;
-            float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (src >= 0) {
-                const float *row = Q + (size_t) src * dim;
-                if ((dim & 3) == 0 && d0 + 3 < dim) {
-                    const float4 x = *reinterpret_cast<const float4 *>(row + d0);
-                    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-                } else {
+    const int groups = nkc * (TC_KC / 8);
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (npos) nqpad = min(nqpad, (int) *npos);          // whole warps either way: both are multiples of 128
+    if (t >= (int64_t) nqpad * groups) return;
+    const int q = (int) (t / groups);
+    const int g = (int) (t - (int64_t) q * groups);
+    const int64_t src = qmap ? (qmap[q] != INVALID_SLOT ? (int64_t) (qmap[q] / nprobe) : -1) : (q < nq ? q : -1);
+    __nv_bfloat16 o[8];
+    float part = 0.0f;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) if (d0 + i < dim) v[i] = row[d0 + i];
-                }
-            }
-            __nv_bfloat16 o[4];
-            float part = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                o[i] = __float2bfloat16_rn(v[i]);
-                const float rr = __bfloat162float(o[i]);
-                part = fmaf(rr, rr, part);
-            }
-#pragma unroll
-            for (int o2 = 16; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(FULL, part, o2);
-            if (lane == 0) norm_s[r] += part;                          // (this warp owns row r for every chunk)
-            const int pr = (r & 3) * 32 + (r >> 2);                    // TMEM lane of position r
-            const int kc = lane >> 1, hf = lane & 1;                   // 8-element group, half of it
-            const int off = ((kc * (TC_M / 8) + (pr >> 3)) * 8 + (pr & 7)) * 8 + hf * 4;
-            *reinterpret_cast<uint2 *>(tile_s + off) = *reinterpret_cast<const uint2 *>(o);
-        }
-        __syncthreads();
-        uint4 *dst = reinterpret_cast<uint4 *>(qb + ((size_t) tile * nkc + c) * (TC_M * TC_KC));
-        const uint4 *srcs = reinterpret_cast<const uint4 *>(tile_s);
-        for (int i = threadIdx.x; i < TC_M * TC_KC * 2 / 16; i += blockDim.x) dst[i] = srcs[i];
-        __syncthreads();
+    for (int i = 0; i < 8; i++) {
+        const int d = g * 8 + i;
+        const float v = (src >= 0 && d < dim) ? Q[(size_t) src * dim + d] : 0.0f;
+        o[i] = __float2bfloat16_rn(v);
+        const float r = __bfloat162float(o[i]);
+        part = fmaf(r, r, part);
     }
-    for (int r = threadIdx.x; r < TC_M; r += blockDim.x) qnorm[(size_t) tile * TC_M + r] = norm_s[r];
+    // Query i of a tile sits on TMEM lane (i % 4) * 32 + i / 4: the tile's queries are dealt round-robin
+    // to the four lane quarters, each of which only one pair of epilogue warps can read.  A tile with 16
+    // live queries (most tile-steps of an IVF batch: long lists probed by a few queries) then keeps all
+    // eight epilogue warps busy with 4 queries each instead of two warps with 16.
+    const int tile = q / TC_M, qi_ = q % TC_M, rr = (qi_ & 3) * 32 + (qi_ >> 2);
+    const int chunk = g / (TC_KC / 8), kc = g % (TC_KC / 8);
+    const size_t off = ((((size_t) (tile * nkc + chunk) * (TC_KC / 8) + kc) * (TC_M / 8) + (rr >> 3)) * 8 + (rr & 7)) * 8;
+    *reinterpret_cast<uint4 *>(qb + off) = *reinterpret_cast<const uint4 *>(o);
+    // squared norm of the rounded query: the row's 16 or 32 threads are adjacent lanes of one warp;
+    // a fixed xor tree, so a query gets the same norm at whatever tile position it sits
+    // (more than 32 groups per row, dim > 256: tc_query_norms_kernel does it instead)
+    if (groups <= 32) {
+        for (int o2 = groups >> 1; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(FULL, part, o2);
+        if (g == 0) qnorm[q] = part;
+    }
+}
+
+// squared norm of the bf16-rounded query, one thread per tile position (rows of more than 256 dims)
+__global__ void tc_query_norms_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap, uint32_t nprobe, int nq,
+                                      int nqpad, const uint32_t *__restrict__ npos, int dim, float *__restrict__ qnorm)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (npos) nqpad = min(nqpad, (int) *npos);
+    if (q >= nqpad) return;
+    const int64_t src = qmap ? (qmap[q] != INVALID_SLOT ? (int64_t) (qmap[q] / nprobe) : -1) : (q < nq ? q : -1);
+    float acc = 0.0f;
+    if (src >= 0)
+        for (int d = 0; d < dim; d++) {
+            const float r = __bfloat162float(__float2bfloat16_rn(Q[(size_t) src * dim + d]));
+            acc = fmaf(r, r, acc);
+        }
+    qnorm[q] = acc;
 }
 
 // ---- tcgen05 / TMEM primitives -------------------------------------------------------------
@@ -742,8 +734,14 @@ int tc_store_rinv(TcStore &st, const float **out, cudaStream_t s)
 int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t nprobe, int nq, int nqpad, int dim, int nkc,
                      __nv_bfloat16 *qb, float *qnorm, cudaStream_t s, const uint32_t *npos_dev)
 {
-    tc_block_queries_kernel<<<(unsigned) (nqpad / TC_M), 256, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev, dim, nkc, qb, qnorm);
+    const int groups = nkc * (TC_KC / 8);
+    tc_block_queries_kernel<<<(unsigned) (((int64_t) nqpad * groups + 255) / 256), 256, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev,
+                                                                                                dim, nkc, qb, qnorm);
     count_launch();
+    if (groups > 32) {
+        tc_query_norms_kernel<<<(unsigned) ((nqpad + 127) / 128), 128, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev, dim, qnorm);
+        count_launch();
+    }
     NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
 }
