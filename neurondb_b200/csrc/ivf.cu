@@ -307,19 +307,36 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_kernel(const float *__restr
             }
         }
         const int nr = min(32, nprobe - r0);
+        // One unit = the partial lists of (probe, segment): the kc entries of the query's replicas and column
+        // halves, contiguous, at most 4 * 2 * 16 = 128 of them.  A unit's four 32-entry groups are loaded
+        // before the first is looked at, so a unit costs one L2 round trip, not four.  (Keeping two probes'
+        // units in flight as well was measured slower: the extra registers cost more occupancy than the
+        // overlap gains.)
+        auto load4 = [&](size_t base, int nent, float (&cdv)[4], uint32_t (&slv)[4]) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = u * 32 + lane;
+                cdv[u] = INFINITY;
+                slv[u] = INVALID_SLOT;
+                if (i < nent) { slv[u] = pslot[base + i]; cdv[u] = pdist[base + i]; }
+            }
+        };
+        auto take4 = [&](int nent, const float (&cdv)[4], const uint32_t (&slv)[4]) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (u * 32 >= nent) break;
+                const bool ok = slv[u] != INVALID_SLOT && cdv[u] <= bound;
+                if (__any_sync(FULL, ok)) cand.offer(cdv[u], slv[u], ok, lane, kc);
+            }
+        };
         for (int r = 0; r < nr; r++) {
             const uint32_t nseg = __shfl_sync(FULL, my_nseg, r), first = __shfl_sync(FULL, my_first, r);
             const int nent = (int) __shfl_sync(FULL, my_rep, r) * 2 * kc;
-            // the kc entries of the query's replicas and column halves are contiguous per item
             for (uint32_t sg = 0; sg < nseg; sg++) {
-                const size_t base = ((size_t) first + (size_t) sg * (2 * TC_M)) * kc;
-                for (int i = lane; i < round_up(nent, 32); i += 32) {
-                    float cd = INFINITY;
-                    uint32_t slot = INVALID_SLOT;
-                    if (i < nent) { slot = pslot[base + i]; cd = pdist[base + i]; }
-                    const bool ok = slot != INVALID_SLOT && cd <= bound;
-                    if (__any_sync(FULL, ok)) cand.offer(cd, slot, ok, lane, kc);
-                }
+                float cdv[4];
+                uint32_t slv[4];
+                load4(((size_t) first + (size_t) sg * (2 * TC_M)) * kc, nent, cdv, slv);
+                take4(nent, cdv, slv);
             }
         }
     }
