@@ -56,7 +56,7 @@ def main():
     idx["ivf_lists"] = lists
     levels = O.hnsw_levels(1500, seed=9)
     idx["hnsw_levels"] = levels
-    for mode in (0, 1):
+    for mode in (0, 1, 3):            # 3 = the diversity-heuristic extension (NDB_HNSW_SELECT_HEURISTIC)
         g = O.Hnsw(16, 6, 24, 24, capacity=1500)
         g.build(X[:1500], levels, mode)
         e = g.export()

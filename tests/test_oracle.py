@@ -101,7 +101,7 @@ def test_golden_index_paths():
             assert np.array_equal(BITS(d), BITS(g["ivf_d_l%d_m%d" % (lit, metric)]))
     levels = O.hnsw_levels(1500, seed=9)
     assert np.array_equal(levels, g["hnsw_levels"])
-    for mode in (0, 1):
+    for mode in (0, 1, 3):
         h = O.Hnsw(16, 6, 24, 24, capacity=1500)
         h.build(X[:1500], levels, mode)
         e = h.export()
