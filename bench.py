@@ -440,11 +440,13 @@ def main():
         sample = min(nq, 4000)
         qps_all, dt_all, _ = cpu_reference_qps(w, X, Q, Cn, sample, cores, native=True)
         qps_1, dt_1, _ = cpu_reference_qps(w, X, Q, Cn, min(500, sample), 1, native=True)
+        # the reference's own build flags (-O2, no -march: NeuronDB/build.sh:712), all cores, smaller sample
+        qps_o2, _, _ = cpu_reference_qps(w, X, Q, Cn, min(1000, sample), cores, native=False)
         cpu = {"value": qps_all, "unit": "queries/s", "cores": cores, "kind": "port",
                "sample": "%d queries of the 10k batch (%.1f s), oracle/ndb_oracle.c -O3 -march=native, OpenMP over "
                          "queries; 1 thread = %.0f QPS on %d queries; excludes PostgreSQL executor/bufmgr overhead"
                          % (sample, dt_all, qps_1, min(500, sample)),
-               "value_1thread": qps_1}
+               "value_1thread": qps_1, "value_reference_flags_O2": qps_o2}
 
     line = {
         "metric": "QPS@recall@10>=0.95", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
