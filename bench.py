@@ -251,10 +251,22 @@ def main():
     for s in range(args.warmup):
         step(s)
     barrier()
-    launches0 = ndb.launch_count()
+
+    def burn(seconds):
+        """Untimed steps of the same work: a step takes a fraction of a millisecond, so the K timed steps are over
+        before nvidia-smi (100 ms period) samples once.  The timed region sits inside ~1 s of continuous identical
+        load, and the clocks and throttle reasons reported are those of that second."""
+        t_end, s = time.perf_counter() + seconds, 0
+        while time.perf_counter() < t_end:
+            for _ in range(16):
+                step(s)
+                s += 1
+            torch.cuda.synchronize()
+
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.25)
+    burn(0.5)
+    launches0 = ndb.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -264,11 +276,13 @@ def main():
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = ndb.launch_count() - launches0
+    burn(0.5)
     if world > 1:
         t = torch.tensor([elapsed_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     clocks = sampler.stop()
+    clocks["window"] = "0.5 s of untimed identical steps before and after the timed region"
     ms_per_step = elapsed_ms / args.steps
     value = nq * replicas / (ms_per_step * 1e-3)
 
