@@ -14,9 +14,17 @@
  *     NeuronDB/t/005_distances_comprehensive.t and against the reference's own
  *     vector_distance.c / vector_distance_simd.c compiled under oracle/pgshim
  *     (oracle/_ref/libndb_ref_distance*.so) on seeded random inputs, bit for bit.
- *   - IVF k-means / assignment / scan, HNSW insert / search: the reference's
- *     tests pin no results for these ("parity unpinned" by reference tests);
- *     they are restated line by line from the cited source ranges.
+ *   - index arithmetic (orc_ivf_distance, orc_hnsw_distance, orc_hnsw_random_level,
+ *     orc_kmeans_train / _assign / _update): PINNED against the reference's own
+ *     ivfComputeDistance, hnswComputeDistance, hnswGetRandomLevel and k-means
+ *     block, cut out of ivf_am.c / hnsw_am.c by oracle/extract_ref_leafs.py and
+ *     compiled with the reference's flags (oracle/_ref/libndb_ref_leafs.so), and
+ *     against tests/golden/index_leafs.npz generated from it.
+ *   - key extraction (orc_fp16_to_float): PINNED the same way (libndb_ref_fp16.so).
+ *   - the control flow around them (ivfSelectClusters, ivfCollectCandidates, the
+ *     ivfinsert assignment loop, hnswSearch, hnswInsertNode): welded to the buffer
+ *     manager, no results asserted by the reference's tests -- "parity unpinned";
+ *     restated line by line from the cited source ranges.
  *
  * Compile with -O2 -ffp-contract=off (the reference's default build has no
  * -march flag, so no FMA contraction can occur: NeuronDB/build.sh:712).

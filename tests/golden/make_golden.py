@@ -79,6 +79,21 @@ def main():
     table = np.array([ref16.fp16_to_float(h) for h in range(65536)], np.uint32)
     ref16.fp16_to_float.restype = C.c_float
     np.savez_compressed(os.path.join(HERE, "fp16_table.npz"), bits=table)
+    # the index access methods' leaf functions, from the reference's own code (oracle/extract_ref_leafs.py)
+    leafs = O.ref_leafs_lib()
+    assert leafs is not None, "build oracle/_ref first (make -C oracle)"
+    import test_oracle as T
+    ivf, hn = [], []
+    for a, b in T._leaf_inputs():
+        dim = a.shape[1]
+        for s_ in (1, 2):
+            ivf.append(np.array([leafs.ref_ivf_distance(a[i], b[i], dim, s_) for i in range(a.shape[0])], np.float32))
+        for s_ in (1, 2, 3):
+            hn.append(np.array([leafs.ref_hnsw_distance(a[i], b[i], dim, s_) for i in range(a.shape[0])], np.float32))
+    Xk = W.mixture(1500, 16, 10, 31)
+    kC, ka, kc = O.ref_kmeans_train(Xk, 24)
+    np.savez_compressed(os.path.join(HERE, "index_leafs.npz"), ivf_bits=np.concatenate(ivf).view(np.uint32),
+                        hnsw_bits=np.concatenate(hn).view(np.uint32), km_C_bits=kC.view(np.uint32), km_assign=ka, km_counts=kc)
     print("wrote", sorted(os.listdir(HERE)))
 
 

@@ -371,3 +371,29 @@ def ref_fp16_lib():
     lib_.fp16_to_float.restype = C.c_float
     lib_.fp16_to_float.argtypes = [C.c_uint16]
     return lib_
+
+
+def ref_leafs_lib():
+    """The reference's own ivfComputeDistance, hnswComputeDistance, hnswGetRandomLevel and k-means block
+    (kmeans_init ... find_nearest_centroid), cut out of ivf_am.c / hnsw_am.c by oracle/extract_ref_leafs.py
+    and compiled with the reference's flags; None when oracle/_ref has not been built."""
+    path = os.path.join(ORACLE_DIR, "_ref", "libndb_ref_leafs.so")
+    if not os.path.exists(path):
+        return None
+    l = C.CDLL(path)
+    l.ref_ivf_distance.restype = C.c_float; l.ref_ivf_distance.argtypes = [_f32p, _f32p, C.c_int, C.c_int]
+    l.ref_hnsw_distance.restype = C.c_float; l.ref_hnsw_distance.argtypes = [_f32p, _f32p, C.c_int, C.c_int]
+    l.ref_hnsw_random_level.restype = C.c_int; l.ref_hnsw_random_level.argtypes = [C.c_float]
+    l.ref_kmeans_train.restype = None
+    l.ref_kmeans_train.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _i32p, _i32p]
+    return l
+
+
+def ref_kmeans_train(X, k):
+    X = f32(X)
+    n, d = X.shape
+    Cn = np.zeros((k, d), np.float32)
+    assign = np.zeros(n, np.int32)
+    counts = np.zeros(k, np.int32)
+    ref_leafs_lib().ref_kmeans_train(X, n, d, k, Cn, assign, counts)
+    return Cn, assign, counts

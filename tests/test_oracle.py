@@ -261,3 +261,74 @@ def test_hnsw_heuristic_insert_mode():
         d, nn, _ = g.search(Q, 32, 10, 1, 1)
         rec[mode] = O.recall_at_k(nn.astype(np.int64), gt)
     assert rec[3] >= rec[1] - 0.005 and rec[3] >= 0.9, rec
+
+
+# ---- the index access methods' own leaf functions (oracle/extract_ref_leafs.py) ------------------------
+def _leaf_inputs():
+    rng = np.random.default_rng(2718)
+    out = []
+    for dim in list(range(1, 40)) + [64, 128, 300, 768]:
+        a = rng.standard_normal((3, dim)).astype(np.float32)
+        b = rng.standard_normal((3, dim)).astype(np.float32)
+        a[2] = 0.0                                   # zero norm: IVF cosine -> 1.0, HNSW cosine -> 2.0
+        out.append((a, b))
+    return out
+
+
+@pytest.mark.skipif(O.ref_leafs_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_index_distances_equal_the_reference_functions():
+    """orc_ivf_distance / orc_hnsw_distance against ivfComputeDistance (ivf_am.c:1550-1592) and
+    hnswComputeDistance (hnsw_am.c:1301-1345) themselves, compiled from the reference source."""
+    ref = O.ref_leafs_lib()
+    for a, b in _leaf_inputs():
+        dim = a.shape[1]
+        for i in range(a.shape[0]):
+            for s in (1, 2):
+                want = np.float32(ref.ref_ivf_distance(a[i], b[i], dim, s))
+                got = O.distance_pairs(a[i:i + 1], b[i:i + 1], s, O.ARITH_IVF_F32)[0]
+                assert BITS(np.array([got]))[0] == BITS(np.array([want]))[0], ("ivf", dim, s)
+            for s in (1, 2, 3):
+                want = np.float32(ref.ref_hnsw_distance(a[i], b[i], dim, s))
+                got = O.distance_pairs(a[i:i + 1], b[i:i + 1], s, O.ARITH_HNSW)[0]
+                assert BITS(np.array([got]))[0] == BITS(np.array([want]))[0], ("hnsw", dim, s)
+
+
+@pytest.mark.skipif(O.ref_leafs_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_kmeans_equals_the_reference_functions():
+    """orc_kmeans_train against the reference's kmeans_init + kmeans_run (ivf_am.c:2070-2294), compiled
+    from its source: centroids bit for bit, assignments, counts -- including k > n and empty clusters."""
+    for n, dim, k in [(1200, 16, 12), (3000, 24, 40), (500, 7, 64), (30, 5, 50), (2000, 128, 100)]:
+        X = W.mixture(n, dim, max(2, k // 3), n)
+        rC, ra, rc = O.ref_kmeans_train(X, k)
+        C, a, c, iters, cost = O.kmeans_train(X, k)
+        assert np.array_equal(BITS(C), BITS(rC)) and np.array_equal(a, ra) and np.array_equal(c, rc), (n, dim, k)
+
+
+@pytest.mark.skipif(O.ref_leafs_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_level_draw_equals_the_reference_function():
+    import ctypes
+    libc = ctypes.CDLL(None)
+    ref = O.ref_leafs_lib()
+    libc.srandom(42)
+    want = [ref.ref_hnsw_random_level(0.36) for _ in range(3000)]
+    libc.srandom(42)
+    got = [O.lib().orc_hnsw_random_level(0.36) for _ in range(3000)]
+    assert got == want and max(want) >= 1
+
+
+def test_index_leaf_golden_vectors():
+    """The same comparisons against committed outputs of the reference's functions (tests/golden/
+    index_leafs.npz, written by make_golden.py from oracle/_ref/libndb_ref_leafs.so), so that they also
+    run where the reference tree is absent."""
+    g = np.load(os.path.join(HERE, "golden", "index_leafs.npz"))
+    ivf, hn = [], []
+    for a, b in _leaf_inputs():
+        for s in (1, 2):
+            ivf.append(O.distance_pairs(a, b, s, O.ARITH_IVF_F32))
+        for s in (1, 2, 3):
+            hn.append(O.distance_pairs(a, b, s, O.ARITH_HNSW))
+    assert np.array_equal(BITS(np.concatenate(ivf)), g["ivf_bits"])
+    assert np.array_equal(BITS(np.concatenate(hn)), g["hnsw_bits"])
+    X = W.mixture(1500, 16, 10, 31)
+    C, a, c, _, _ = O.kmeans_train(X, 24)
+    assert np.array_equal(BITS(C), g["km_C_bits"]) and np.array_equal(a, g["km_assign"]) and np.array_equal(c, g["km_counts"])
