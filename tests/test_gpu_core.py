@@ -251,3 +251,23 @@ def test_operator_distances_as_an_avx_build_computes_them(ndb, orc, metric):
     got = ndb.distance_rows(X, q, metric, ndb.ARITH_AVX2)
     want = orc.distance_pairs(X, np.repeat(q[None], 100, 0), metric, orc.ARITH_AVX2)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_index_arithmetic_equals_the_reference_golden_vectors(ndb):
+    """tests/golden/index_leafs.npz holds outputs of the reference's OWN ivfComputeDistance,
+    hnswComputeDistance and k-means block (cut out of ivf_am.c / hnsw_am.c and compiled,
+    oracle/extract_ref_leafs.py): the kernels must reproduce them bit for bit, no oracle in between."""
+    import test_oracle as T
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "index_leafs.npz"))
+    ivf, hn = [], []
+    for a, b in T._leaf_inputs():
+        for s in (1, 2):
+            ivf.append(ndb.distance_pairs(a, b, s, ndb.ARITH_IVF_F32))
+        for s in (1, 2, 3):
+            hn.append(ndb.distance_pairs(a, b, s, ndb.ARITH_HNSW))
+    assert np.array_equal(np.concatenate(ivf).view(np.uint32), g["ivf_bits"])
+    assert np.array_equal(np.concatenate(hn).view(np.uint32), g["hnsw_bits"])
+    X = W.mixture(1500, 16, 10, 31)
+    C, assign, counts, iters, cost = ndb.kmeans_train(X, 24)
+    assert np.array_equal(C.view(np.uint32), g["km_C_bits"])
+    assert np.array_equal(assign, g["km_assign"]) and np.array_equal(counts, g["km_counts"])
