@@ -271,3 +271,24 @@ def test_index_arithmetic_equals_the_reference_golden_vectors(ndb):
     C, assign, counts, iters, cost = ndb.kmeans_train(X, 24)
     assert np.array_equal(C.view(np.uint32), g["km_C_bits"])
     assert np.array_equal(assign, g["km_assign"]) and np.array_equal(counts, g["km_counts"])
+
+
+def test_reference_index_fixture_t010(ndb):
+    """t/010_indexes_comprehensive.t:32-48 -- 8 rows [1+i, 2+i, 3+i, 4+i], query [1,2,3,4]: row i at distance 2 i,
+    through the exact scan, an IVF index (vector_l2_ops) and an HNSW index with the default options."""
+    import test_oracle as T
+    X, q = T.FIXTURE_T010, T.FIXTURE_T010[:1]
+    want_d = np.arange(8, dtype=np.float32) * 2
+    ds = ndb.Dataset(4)
+    ds.append(X)
+    d, i = ds.knn(q, 8, ndb.L2, ndb.ARITH_OP_F64)
+    assert np.array_equal(i[0], np.arange(8)) and np.array_equal(d[0], want_d)
+    ix = ndb.IvfIndex(4, 4)
+    ix.ivfbuild(X)
+    ix.ivfinsert(X)
+    d, i = ix.search(q, 4, 8)
+    assert np.array_equal(i[0], np.arange(8)) and np.array_equal(d[0], want_d)
+    h = ndb.HnswIndex(4, 16, 200, 64)
+    h.hnswbuild(X, levels=np.zeros(8, np.int32))
+    d, i = h.search(q, 64, 8)
+    assert np.array_equal(i[0], np.arange(8)) and np.array_equal(d[0], want_d)

@@ -332,3 +332,25 @@ def test_index_leaf_golden_vectors():
     X = W.mixture(1500, 16, 10, 31)
     C, a, c, _, _ = O.kmeans_train(X, 24)
     assert np.array_equal(BITS(C), g["km_C_bits"]) and np.array_equal(a, g["km_assign"]) and np.array_equal(c, g["km_counts"])
+
+
+# ---- the reference's index fixture (t/010_indexes_comprehensive.t:32-48) ------------------------------
+FIXTURE_T010 = np.array([[1 + i, 2 + i, 3 + i, 4 + i] for i in range(8)], np.float32)
+
+
+def test_reference_index_fixture_t010():
+    """The 8-row table of the reference's index test, query '[1,2,3,4]' ORDER BY vec <-> q: the reference
+    asserts no output, but the answer is forced -- row i is at distance exactly 2 i."""
+    X, q = FIXTURE_T010, FIXTURE_T010[:1]
+    want_d = np.arange(8, dtype=np.float32) * 2
+    d, i = O.knn_exact(X, q, 8, 1, O.ARITH_OP_F64)
+    assert np.array_equal(i[0], np.arange(8)) and np.array_equal(d[0], want_d)
+    C, assign, counts, _, _ = O.kmeans_train(X, 4)
+    lists = O.ivf_assign(X, C)
+    off, rows = O.lists_from_assignment(lists, 4)
+    d, i, _ = O.ivf_search(X, C, off, rows, q, 4, 8)
+    assert np.array_equal(i[0], np.arange(8)) and np.array_equal(d[0], want_d)
+    g = O.Hnsw(4, 16, 200, 64, capacity=8)
+    g.build(X, np.zeros(8, np.int32), 1)
+    d, n, _ = g.search(q, 64, 8, 1, 1)
+    assert np.array_equal(n[0], np.arange(8)) and np.array_equal(d[0], want_d)
