@@ -256,6 +256,12 @@ def main():
         """Untimed steps of the same work: a step takes a fraction of a millisecond, so the K timed steps are over
         before nvidia-smi (100 ms period) samples once.  The timed region sits inside ~1 s of continuous identical
         load, and the clocks and throttle reasons reported are those of that second."""
+        if gather:
+            # the step contains collectives here: every rank must run the same number of them
+            for s in range(int(seconds * 2048)):
+                step(s)
+            torch.cuda.synchronize()
+            return
         t_end, s = time.perf_counter() + seconds, 0
         while time.perf_counter() < t_end:
             for _ in range(16):
