@@ -452,7 +452,7 @@ def main():
                             "kernel is bound by its top-k epilogue, see DESIGN.md 4.2b"}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # (rank 0 at N = 1 only: the host cores are shared by the ranks)
         import oracle_lib as O
         O.build_oracle()
         cores = os.cpu_count() or 1
