@@ -148,6 +148,10 @@ void orc_keys_from_bits(const uint8_t *bits, int64_t n, int nbits, float *rows);
 void orc_keys_from_sparse(const int64_t *indptr, const int32_t *indices, const float *values,
                           int64_t n, int total_dim, float *rows);
 
+/* sizes / field offsets used by the relation encoders (ndb_oracle_pages.c), in the order of the
+ * reference-side ref_layout() built by oracle/extract_ref_leafs.py; returns the count */
+int orc_page_layout(int64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

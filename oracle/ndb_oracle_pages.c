@@ -14,6 +14,7 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <stddef.h>
 
 #define BLCKSZ 8192
 #define PAGE_HEADER 24
@@ -78,6 +79,18 @@ static void tid_pack(int64_t tid, uint8_t *out6)
     uint16_t v[3] = { (uint16_t) (blk >> 16), (uint16_t) (blk & 0xffff), (uint16_t) (tid & 0xffff) };
     memcpy(out6, v, 6);
 }
+
+/* item layouts the encoders below write; orc_page_layout() reports them (and the struct sizes / offsets)
+ * in the order of the reference-side ref_layout() of oracle/extract_ref_leafs.py, so that the test can hold
+ * them against the reference's own struct definitions */
+#define IVF_ENTRY_TID_OFF 0      /* IvfListEntryData.heapPtr (ivf_am.c:251-256) */
+#define IVF_ENTRY_DIM_OFF 6      /* IvfListEntryData.dim */
+#define IVF_ENTRY_HDR 8          /* sizeof(IvfListEntryData); the vector follows at MAXALIGN of it */
+#define HNSW_NODE_TID_OFF 0      /* HnswNodeData.heapPtr (hnsw_am.c:124-136) */
+#define HNSW_NODE_LEVEL_OFF 8
+#define HNSW_NODE_DIM_OFF 12
+#define HNSW_NODE_CNT_OFF 14     /* int16 neighborCount[16] */
+#define HNSW_NODE_HDR 48         /* sizeof(HnswNodeData) = MAXALIGN of it; vector, then neighbours[level+1][2m] */
 
 /* ---- IVF ------------------------------------------------------------------------------- */
 typedef struct { uint32_t magic, version; int32_t nlists, nprobe, dim; uint32_t centroidsBlock; int64_t insertedVectors; } IvfMeta;           /* ivf_am.c:75-84 */
@@ -164,10 +177,10 @@ int64_t orc_ivf_encode_relation(const float *X, const int64_t *tids, int64_t n, 
             }
         }
         memset(entry, 0, entrySize);
-        tid_pack(tids ? tids[r] : r, entry);
+        tid_pack(tids ? tids[r] : r, entry + IVF_ENTRY_TID_OFF);
         int16_t d16 = (int16_t) dim;
-        memcpy(entry + 6, &d16, 2);
-        memcpy(entry + MAXALIGN8(8), X + (size_t) r * dim, (size_t) dim * 4);
+        memcpy(entry + IVF_ENTRY_DIM_OFF, &d16, 2);
+        memcpy(entry + MAXALIGN8(IVF_ENTRY_HDR), X + (size_t) r * dim, (size_t) dim * 4);
         if (!page_add_item(lpage, entry, entrySize)) { nblocks = -2; break; }
         ((IvfListSpecial *) (lpage + BLCKSZ - 8))->entryCount++;
         cen->memberCount++;
@@ -220,7 +233,7 @@ int64_t orc_hnsw_encode_relation(const OrcHnsw *g, const float *X, const int64_t
     meta->ml = 0.36f;
     meta->insertedVectors = n;
 
-    const size_t hdr = 48;
+    const size_t hdr = HNSW_NODE_HDR;
     uint8_t *item = (uint8_t *) malloc(BLCKSZ);
     int64_t rc = n + 1;
     for (int64_t i = 0; i < n; i++) {
@@ -228,12 +241,12 @@ int64_t orc_hnsw_encode_relation(const OrcHnsw *g, const float *X, const int64_t
         const size_t size = MAXALIGN8(hdr + (size_t) dim * 4 + (size_t) (level + 1) * m2 * 4);
         if (size > BLCKSZ - PAGE_HEADER - 4) { rc = -1; break; }
         memset(item, 0, size);
-        tid_pack(tids ? tids[i] : i, item);
+        tid_pack(tids ? tids[i] : i, item + HNSW_NODE_TID_OFF);
         int32_t lv = level;
         int16_t d16 = (int16_t) dim;
-        memcpy(item + 8, &lv, 4);
-        memcpy(item + 12, &d16, 2);
-        memcpy(item + 14, cnt + (size_t) i * ORC_HNSW_MAX_LEVEL, 2 * ORC_HNSW_MAX_LEVEL);
+        memcpy(item + HNSW_NODE_LEVEL_OFF, &lv, 4);
+        memcpy(item + HNSW_NODE_DIM_OFF, &d16, 2);
+        memcpy(item + HNSW_NODE_CNT_OFF, cnt + (size_t) i * ORC_HNSW_MAX_LEVEL, 2 * ORC_HNSW_MAX_LEVEL);
         memcpy(item + hdr, X + (size_t) i * dim, (size_t) dim * 4);
         uint32_t *nb = (uint32_t *) (item + hdr + (size_t) dim * 4);
         for (int l = 0; l <= level; l++)
@@ -247,4 +260,35 @@ int64_t orc_hnsw_encode_relation(const OrcHnsw *g, const float *X, const int64_t
     }
     free(item); free(nbr0); free(cnt); free(upper); free(uoff); free(levels);
     return rc;
+}
+
+
+/* sizes and offsets the encoders above use, in the order of ref_layout() (oracle/extract_ref_leafs.py) */
+int orc_page_layout(int64_t *o)
+{
+    int n = 0;
+    o[n++] = sizeof(IvfMeta);
+    o[n++] = offsetof(IvfMeta, magic); o[n++] = offsetof(IvfMeta, version);
+    o[n++] = offsetof(IvfMeta, nlists); o[n++] = offsetof(IvfMeta, nprobe); o[n++] = offsetof(IvfMeta, dim);
+    o[n++] = offsetof(IvfMeta, centroidsBlock); o[n++] = offsetof(IvfMeta, insertedVectors);
+    o[n++] = 0x49564646;
+    o[n++] = sizeof(IvfCentroidHdr); o[n++] = MAXALIGN8(sizeof(IvfCentroidHdr));
+    o[n++] = offsetof(IvfCentroidHdr, listId); o[n++] = offsetof(IvfCentroidHdr, dim);
+    o[n++] = offsetof(IvfCentroidHdr, memberCount); o[n++] = offsetof(IvfCentroidHdr, firstBlock);
+    o[n++] = sizeof(IvfListSpecial); o[n++] = offsetof(IvfListSpecial, nextBlock); o[n++] = offsetof(IvfListSpecial, entryCount);
+    o[n++] = IVF_ENTRY_HDR; o[n++] = MAXALIGN8(IVF_ENTRY_HDR);
+    o[n++] = IVF_ENTRY_TID_OFF; o[n++] = IVF_ENTRY_DIM_OFF;
+    o[n++] = sizeof(HnswMeta);
+    o[n++] = offsetof(HnswMeta, magic); o[n++] = offsetof(HnswMeta, version); o[n++] = offsetof(HnswMeta, entryPoint);
+    o[n++] = offsetof(HnswMeta, entryLevel); o[n++] = offsetof(HnswMeta, maxLevel); o[n++] = offsetof(HnswMeta, m);
+    o[n++] = offsetof(HnswMeta, efConstruction); o[n++] = offsetof(HnswMeta, efSearch); o[n++] = offsetof(HnswMeta, ml);
+    o[n++] = offsetof(HnswMeta, insertedVectors);
+    o[n++] = 0x48534E57;
+    o[n++] = HNSW_NODE_HDR; o[n++] = MAXALIGN8(HNSW_NODE_HDR);
+    o[n++] = HNSW_NODE_TID_OFF; o[n++] = HNSW_NODE_LEVEL_OFF; o[n++] = HNSW_NODE_DIM_OFF; o[n++] = HNSW_NODE_CNT_OFF;
+    o[n++] = (int64_t) MAXALIGN8(HNSW_NODE_HDR + (size_t) 768 * 4 + (size_t) (0 + 1) * 32 * 4);
+    o[n++] = (int64_t) MAXALIGN8(HNSW_NODE_HDR + (size_t) 128 * 4 + (size_t) (2 + 1) * 16 * 4);
+    o[n++] = (int64_t) (HNSW_NODE_HDR + (size_t) 768 * 4 + (size_t) 1 * 32 * 4);       /* level-1 neighbours, 768-d, m = 16 */
+    o[n++] = (int64_t) (HNSW_NODE_HDR + (size_t) 768 * 4);
+    return n;
 }

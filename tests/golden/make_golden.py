@@ -93,7 +93,8 @@ def main():
     Xk = W.mixture(1500, 16, 10, 31)
     kC, ka, kc = O.ref_kmeans_train(Xk, 24)
     np.savez_compressed(os.path.join(HERE, "index_leafs.npz"), ivf_bits=np.concatenate(ivf).view(np.uint32),
-                        hnsw_bits=np.concatenate(hn).view(np.uint32), km_C_bits=kC.view(np.uint32), km_assign=ka, km_counts=kc)
+                        hnsw_bits=np.concatenate(hn).view(np.uint32), km_C_bits=kC.view(np.uint32), km_assign=ka, km_counts=kc,
+                        page_layout=O.ref_page_layout())
     print("wrote", sorted(os.listdir(HERE)))
 
 

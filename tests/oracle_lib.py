@@ -386,7 +386,26 @@ def ref_leafs_lib():
     l.ref_hnsw_random_level.restype = C.c_int; l.ref_hnsw_random_level.argtypes = [C.c_float]
     l.ref_kmeans_train.restype = None
     l.ref_kmeans_train.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _i32p, _i32p]
+    l.ref_layout.restype = C.c_int
+    l.ref_layout.argtypes = [_i64p]
     return l
+
+
+def ref_page_layout():
+    """Sizes / field offsets of the reference's own on-page structs (IvfMetaPageData ... HnswNodeData)."""
+    o = np.zeros(64, np.int64)
+    n = ref_leafs_lib().ref_layout(o)
+    return o[:n].copy()
+
+
+def page_layout():
+    """The same list as the oracle's relation encoders use it (ndb_oracle_pages.c)."""
+    o = np.zeros(64, np.int64)
+    f = lib().orc_page_layout
+    f.restype = C.c_int
+    f.argtypes = [_i64p]
+    n = f(o)
+    return o[:n].copy()
 
 
 def ref_kmeans_train(X, k):

@@ -1,7 +1,9 @@
 """CPU: the oracle's relation images follow the reference's page layout (ivf_am.c / hnsw_am.c)."""
+import os
 import struct
 
 import numpy as np
+import pytest
 
 import oracle_lib as O
 import workloads as W
@@ -66,3 +68,20 @@ def test_hnsw_relation_layout():
         nb0 = np.frombuffer(page, np.uint32, 16, off + 48 + 96)
         want = np.where(e["nbr0"][i] == 0xFFFFFFFF, 0xFFFFFFFF, e["nbr0"][i] + 1)
         assert np.array_equal(nb0, want)
+
+
+# ---- the page layouts themselves, against the reference's struct definitions ----------------------------
+@pytest.mark.skipif(O.ref_leafs_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_page_layout_equals_the_reference_structs():
+    """Sizes and field offsets of IvfMetaPageData, IvfCentroidData, IvfListPageHeader, IvfListEntryData,
+    HnswMetaPageData, HnswNodeData, HnswNodeSizeWithM and HnswGetNeighborsSafe, read back from the reference's
+    own definitions (oracle/extract_ref_leafs.py), equal what the oracle's relation encoders write -- and the
+    GPU loaders are tested against those relations (tests/test_gpu_pages.py)."""
+    want, got = O.ref_page_layout(), O.page_layout()
+    assert np.array_equal(got, want), (got, want)
+    assert want[0] == 32 and want[9] == 24 and want[22] == 40 and want[34] == 48 and want[40] == 3248   # SURVEY 8a
+
+
+def test_page_layout_golden():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "index_leafs.npz"))
+    assert np.array_equal(O.page_layout(), g["page_layout"])
