@@ -19,7 +19,7 @@ $(OBJDIR)/%.o: $(SRCDIR)/%.cu $(HDRS)
 
 $(LIBDIR)/libndb_b200.so: $(OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $@ $(OBJS)
+	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $@ $(OBJS) -ldl
 
 oracle:
 	$(MAKE) -s -C oracle

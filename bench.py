@@ -1,22 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200-native NeuronDB vector-search hot path.
+"""bench.py -- benchmark of the B200-native NeuronDB vector-search hot path.
 
-Workload (BASELINE.json configs[1], "C2"): IVFFlat L2, 1M x 128 synthetic vectors (1024-component
-Gaussian mixture), lists=1024, nprobe=16, k=10, one 10k-query batch per step.
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c2|c3|c4|c5|smoke]
+
+Default workload (every N): BASELINE.json configs[3], "C4" -- IVFFlat inner product, 10 M x 96 synthetic
+vectors (4096-component Gaussian mixture), lists = 4096, nprobe = 32, k = 10, one 10 k-query
+batch per step.  It is the configuration BASELINE.json's metric quotes for 1/2/4/8 B200 ("lists sharded
+across 2/4/8 B200 with NCCL top-k merge"), it fits one GPU, and the driver computes scaling efficiency as
+v_N / (N * v_1) -- which only means something when every N runs the same workload.  At N = 1 the same run
+also measures C2 (configs[1], IVFFlat L2 1 M x 128) and reports it under "also".
+
 A step = ivfSelectClusters + ivfCollectCandidates for the whole batch (NeuronDB/src/index/ivf_am.c
-:1597-1909) through the C ABI of libndb_b200.so.
+:1597-1909) through the C ABI of libndb_b200.so.  `value` = QPS with the query batch already resident in HBM
+(device-pointer entry point, CUDA events on the launching stream, max over ranks); `e2e` = the same metric
+through the host-pointer entry point with pinned host buffers, H2D and D2H inside the timed region.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c4]
+N > 1 (torchrun, one process per GPU): the index is sharded -- every inverted list is striped over the
+ranks (row i of the insertion order lives on rank i % N; `--shard lists` keeps whole lists, l % N, instead)
+-- the queries are replicated, every rank answers the batch against its shard, the per-rank top-k travel in
+ONE ncclAllGather of packed 12-byte (dist, id) records issued by the library's own communicator
+(ndb_b200_comm_*), and every rank merges them on the device by (dist, id): strong scaling of one workload.
+`--shard queries` is the replica mode (index copied to every GPU, no data-path collective).
 
-Prints ONE JSON line (see the keys below).  `value` = QPS with the query batch already resident in
-HBM (device-pointer entry point, CUDA events, max over ranks); `e2e` = the same metric through the
-host-pointer entry point with pinned host buffers, H2D and D2H inside the timed region.
-N > 1 (torchrun): inverted lists are sharded l % N across ranks, every rank answers the whole batch
-against its shard, per-rank top-k are exchanged with an NCCL all-gather and merged on the device by
-(dist, id) -- strong scaling of the same workload.
-
---impl reference times the reference's CPU algorithm for the same step (the oracle restatement
-compiled -O3 -march=native, OpenMP over queries, all host cores) on a bounded sample of queries.
+--impl reference times the reference's CPU algorithm for the same step (the oracle restatement compiled
+-O3 -march=native, OpenMP over queries, all host cores) on a bounded sample of queries.
 """
 import argparse
 import json
@@ -32,15 +39,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+METRIC = "QPS@recall@10>=0.95"
+
 WORKLOADS = {
-    # name: (rows, dim, lists, nprobe, k, nq, metric, mixture components, seed)
-    "c2": dict(n=1_000_000, dim=128, lists=1024, nprobe=16, k=10, nq=10_000, metric=1, comps=1024, seed=2024,
+    # IVF: rows, dim, lists, nprobe, k, queries per batch, metric (1 L2 / 2 cosine / 3 inner product), mixture components, seed
+    "c2": dict(kind="ivf", n=1_000_000, dim=128, lists=1024, nprobe=16, k=10, nq=10_000, metric=1, comps=1024, seed=2024,
                label="C2: IVFFlat L2 1Mx128 lists=1024 nprobe=16 k=10, 10k-query batch"),
-    "c4": dict(n=10_000_000, dim=96, lists=4096, nprobe=32, k=10, nq=10_000, metric=3, comps=4096, seed=96,
+    "c4": dict(kind="ivf", n=10_000_000, dim=96, lists=4096, nprobe=32, k=10, nq=10_000, metric=3, comps=4096, seed=96,
                label="C4: IVFFlat inner-product 10Mx96 lists=4096 nprobe=32 k=10, 10k-query batch"),
-    "smoke": dict(n=50_000, dim=64, lists=64, nprobe=8, k=10, nq=1000, metric=1, comps=64, seed=7,
+    "smoke": dict(kind="ivf", n=50_000, dim=64, lists=64, nprobe=8, k=10, nq=1000, metric=1, comps=64, seed=7,
                   label="smoke: IVFFlat L2 50kx64"),
+    # exact kNN through the <-> operator arithmetic (fp64 Kahan), BASELINE configs[0]
+    "c1": dict(kind="exact", n=100_000, dim=128, k=10, nq=1000, metric=1, seed=1234,
+               label="C1: exact L2 kNN k=10 over 100kx128 fp32, 1k queries, <-> operator arithmetic (fp64 Kahan)"),
+    # HNSW, BASELINE configs[2]
+    "c3": dict(kind="hnsw", n=1_000_000, dim=768, m=16, efc=64, efs=40, k=10, nq=10_000, seed=768,
+               label="C3: HNSW cosine 1Mx768 M=16 ef_construction=64 ef_search=40, 10k-query batch"),
+    # brute force + k-means on bf16-valued rows, BASELINE configs[4]: 6.25 M rows per GPU (50 M on 8)
+    "c5": dict(kind="brute", n_per_gpu=6_250_000, dim=128, k=10, nq=10_000, kmeans_k=4096, seed=5,
+               label="C5: brute-force kNN + k-means (k=4096) over 50Mx128 bf16 rows sharded 8 x 6.25M, 10k queries"),
+    "c5s": dict(kind="brute", n_per_gpu=500_000, dim=128, k=10, nq=2_000, kmeans_k=256, seed=5,
+                label="C5 (small): brute-force kNN + k-means over 500k x 128 bf16 rows per GPU"),
 }
+DEFAULT_WORKLOAD = "c4"
 
 
 def make_data(w, qstream=0):
@@ -109,60 +130,820 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def cpu_reference_qps(w, X, Q, Cn, nq_sample, threads, native=True):
+def traffic_for(workload):
+    """DRAM bytes per launch of the workload's dominant kernel, from the committed ncu --set full capture."""
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(tp) as f:
+            return json.load(f).get(workload, {})
+    except Exception:
+        return {}
+
+
+# ---------------------------------------------------------------------------------------------------
+# process context: device, torch.distributed (plumbing), the library communicator (data path)
+# ---------------------------------------------------------------------------------------------------
+class Ctx:
+    def __init__(self, need_comm):
+        import torch
+        import neurondb_b200 as ndb
+        self.torch, self.ndb = torch, ndb
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        ndb.init(self.local)
+        self.comm_nranks = 1
+        if self.world > 1 and need_comm:
+            ndb.comm_init_torch()                 # ncclCommInitRank inside libndb_b200.so
+            self.comm_nranks = ndb.comm_nranks()
+        # a real (non-NULL) stream: the C ABI treats a NULL stream as "the library's own stream", and
+        # torch.cuda.Event only sees work queued on torch's current stream
+        self.tstream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.tstream)
+        self.stream = self.tstream.cuda_stream
+        assert self.stream != 0
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        if self.world == 1:
+            return vals if len(vals) > 1 else vals[0]
+        t = self.torch.tensor(list(vals), device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        out = [float(x) for x in t.tolist()]
+        return out if len(out) > 1 else out[0]
+
+    def timed_steps(self, step, steps, warmup, collective):
+        """W warm-up steps, then exactly K steps between CUDA events on the launching stream, bracketed by a
+        barrier + synchronize on both sides, max over ranks; nvidia-smi samples a window of ~0.5 s of identical
+        untimed steps before and after (a step can be shorter than the 100 ms sampling period).
+        Returns (ms_per_step, clocks)."""
+        torch = self.torch
+        for s in range(warmup):
+            step(s)
+        self.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for s in range(2):
+            step(s)
+        ev1.record()
+        torch.cuda.synchronize()
+        est_ms = self.max_over_ranks(max(ev0.elapsed_time(ev1) / 2, 1e-3))
+        nburn = int(min(4096, max(2, 500.0 / est_ms)))      # the same count on every rank: a step may hold collectives
+
+        def burn():
+            for s in range(nburn):
+                step(s)
+                if (s & 15) == 15:
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+
+        sampler = ClockSampler(self.local)
+        sampler.start()
+        burn()
+        self.barrier()
+        ev0.record()
+        for s in range(steps):
+            step(s)
+        ev1.record()
+        self.barrier()
+        ms = ev0.elapsed_time(ev1) / steps
+        burn()
+        ms = self.max_over_ranks(ms)
+        clocks = sampler.stop()
+        clocks["window"] = "%d untimed identical steps (~0.5 s) before and after the timed region" % nburn
+        return ms, clocks
+
+    def timed_wall(self, fn, steps):
+        self.barrier()
+        t = time.perf_counter()
+        fn()
+        self.barrier()
+        return self.max_over_ranks((time.perf_counter() - t) / steps)
+
+    def finish(self):
+        if self.world > 1:
+            try:
+                self.ndb.comm_shutdown()
+            except Exception:
+                pass
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+# IVF workloads (C2, C4)
+# ---------------------------------------------------------------------------------------------------
+def cpu_ivf_qps(w, X, Q, Cn, lists, nq_sample, threads, native=True):
     """The reference's CPU algorithm for the same step on `nq_sample` queries (oracle port)."""
     import oracle_lib as O
-    assign = O.ivf_assign(X, Cn, nthreads=threads, native=native)
-    off, rows = O.lists_from_assignment(assign, w["lists"])
+    off, rows = lists
     Qs = np.ascontiguousarray(Q[:nq_sample])
     t = time.perf_counter()
     O.ivf_search(X, Cn, off, rows, Qs, w["nprobe"], w["k"], strategy=w["metric"], literal=False, nthreads=threads,
                  native=native)
     dt = time.perf_counter() - t
-    return nq_sample / dt, dt, (off, rows)
+    return nq_sample / dt, dt
 
 
-def run_reference(args, w):
-    """--impl reference: the CPU path on the host cores; rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
+def cpu_ivf_sample_size(w, X, Q, Cn, lists, cores, budget_s=12.0):
+    """Queries to time on the CPU so that the all-core run takes about `budget_s` seconds."""
+    probe = min(w["nq"], 64)
+    qps, _ = cpu_ivf_qps(w, X, Q, Cn, lists, probe, cores)
+    return int(max(probe, min(w["nq"], qps * budget_s)))
+
+
+def run_ivf(c, args, w, wname, with_cpu=True, with_alt=True):
+    torch, ndb = c.torch, c.ndb
+    rank, world = c.rank, c.world
+    arith = {"ivf_f32": ndb.ARITH_IVF_F32, "fast": ndb.ARITH_FAST, "tensor": ndb.ARITH_TENSOR}[args.arith]
+    shard = args.shard if world > 1 else "none"
+    gather = shard in ("rows", "lists")
+    replicas = world if shard == "queries" else 1
+    X, Q = make_data(w, rank if replicas > 1 else 0)
+    n, nq, k, dim = w["n"], w["nq"], w["k"], w["dim"]
+    ix = ndb.IvfIndex(dim, w["lists"], w["metric"])
+    if shard == "lists":
+        ix.set_shard(rank, world)
+    c.barrier()
+    t0 = time.perf_counter()
+    ix.ivfbuild(X)                     # k-means on the first min(10000, lists*100) rows (ivf_am.c:580)
+    t1 = time.perf_counter()
+    # list assignment + append (ivf_am.c:797-1167); striped shards insert their own rows with global ids
+    if shard == "rows":
+        got_lists = ix.ivfinsert(X[rank::world], np.arange(rank, n, world, dtype=np.int64))
+    else:
+        got_lists = ix.ivfinsert(X, np.arange(n, dtype=np.int64))
+    t2 = time.perf_counter()
+    ix.prepare(arith)                  # list layout + (tensor path) blocked bf16 copy: part of the build, not of the first search
+    c.barrier()
+    t3 = time.perf_counter()
+    build = {"train_s": t1 - t0, "insert_s": t2 - t1, "layout_s": t3 - t2, "total_s": t3 - t0,
+             "rows_this_rank": len(ix), "includes": "k-means, list assignment of every row, list layout, bf16 blocking"}
+
+    qd = [torch.from_numpy(Q[i * nq:(i + 1) * nq]).cuda() for i in range(4)]
+    out_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    search_dev = ix.search_sharded_dev if gather else ix.search_dev
+
+    def step(s, arith=arith):
+        q = qd[0 if os.environ.get("NDB_BENCH_ONE_BATCH") else s % 4]
+        search_dev(q.data_ptr(), nq, out_d.data_ptr(), out_i.data_ptr(), w["nprobe"], k, ndb.IVF_FULL, arith, c.stream)
+
+    launches0 = ndb.launch_count()
+    ms_per_step, clocks = c.timed_steps(step, args.steps, args.warmup, gather)
+    # kernels of the K timed steps: count one step's launches on a quiet stream
+    l0 = ndb.launch_count()
+    step(0)
+    torch.cuda.synchronize()
+    launches = (ndb.launch_count() - l0) * args.steps
+    value = nq * replicas / (ms_per_step * 1e-3)
+
+    # results of batch 0 for recall and for the cross-check between arithmetics
+    step(0)
+    torch.cuda.synchronize()
+    ngt = 500 if n <= 2_000_000 else 100
+    res_i = out_i[:500].cpu().numpy()
+    res_full_i, res_full_d = out_i.cpu().numpy().copy(), out_d.cpu().numpy().copy()
+
+    # dominant kernel: device time from CUDA events recorded by the library around that kernel on the
+    # launching stream; algorithmic work = distance evaluations counted on the device
+    ndb.set_timing(True)
+    kms, kevals = [], []
+    for s in range(min(args.steps, 10)):
+        step(s)
+        ms, b, ev = ndb.last_kernel_stats()
+        kms.append(ms); kevals.append(ev)
+    ndb.set_timing(False)
+    kernel_ms, evals = float(np.mean(kms)), float(np.mean(kevals))
+
+    # end to end through the host-pointer entry points with pinned host buffers
+    qh = [torch.from_numpy(Q[i * nq:(i + 1) * nq]).pin_memory() for i in range(4)]
+    hd = [torch.empty((nq, k), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+    hi = [torch.empty((nq, k), dtype=torch.int64).pin_memory().numpy() for _ in range(2)]
+    qh_np = [q.numpy() for q in qh]
+
+    def e2e_sync(nsteps, arith=arith):
+        for s in range(nsteps):
+            if gather:
+                ix.search_sharded(qh_np[s % 4], w["nprobe"], k, ndb.IVF_FULL, arith, hd[0], hi[0])
+            else:
+                ndb.check(ndb._lib.load().ndb_b200_ivf_search(ix.h, ndb.ptr(qh_np[s % 4]), nq, w["nprobe"], k, ndb.IVF_FULL, arith,
+                                                              ndb.ptr(hd[0]), ndb.ptr(hi[0])))
+
+    # pipelined form of the same call (ndb_b200_ivf_search_begin / _end, two batches in flight): the H2D copy
+    # of the next batch and the D2H copy of the previous one overlap this batch's kernels.  Every batch is
+    # still copied in from pinned host memory and its results copied back inside the timed region.
+    def e2e_pipelined(nsteps, arith=arith):
+        prev = None
+        for s in range(nsteps):
+            tk = ix.search_begin(qh_np[s % 4], hd[s % 2], hi[s % 2], w["nprobe"], k, ndb.IVF_FULL, arith)
+            if prev is not None:
+                ix.search_end(prev)
+            prev = tk
+        ix.search_end(prev)
+
+    e2e_sync(3)
+    e2e_sync_s = c.timed_wall(lambda: e2e_sync(args.steps), args.steps)
+    if gather:
+        e2e_s, e2e_mode = e2e_sync_s, "ndb_b200_ivf_search_sharded: one synchronous call per batch (H2D, search, all-gather, merge, D2H)"
+    else:
+        e2e_pipelined(4)
+        e2e_s = c.timed_wall(lambda: e2e_pipelined(args.steps), args.steps)
+        e2e_mode = "ndb_b200_ivf_search_begin/_end, 2 batches in flight"
+    e2e_val = nq * replicas / e2e_s
+
+    # the same step in the reference's own fp32 arithmetic (bit-exact path), for comparison
+    alt = None
+    if args.arith == "tensor" and with_alt:
+        a32 = ndb.ARITH_IVF_F32
+        asteps = max(2, min(args.steps, int(2000.0 / max(ms_per_step * 12, 1.0))))     # the fp32 path is ~10x slower
+        for s in range(2):
+            step(s, a32)
+        c.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for s in range(asteps):
+            step(s, a32)
+        ev1.record()
+        c.barrier()
+        alt_ms = c.max_over_ranks(ev0.elapsed_time(ev1) / asteps)
+        step(0, a32)
+        torch.cuda.synchronize()
+        ref_i, ref_d = out_i.cpu().numpy(), out_d.cpu().numpy()
+        same = ref_i == res_full_i
+        alt = {"arith": "ivf_f32", "value": nq * replicas / (alt_ms * 1e-3), "ms_per_step": alt_ms, "steps": asteps,
+               "unit": "queries/s", "ids_equal_to_tensor_path": float(same.mean()),
+               "distance_bits_equal_where_ids_agree": bool(np.array_equal(ref_d[same].view(np.uint32), res_full_d[same].view(np.uint32))),
+               "note": "the reference's fp32 arithmetic end to end (bit-exact distances and ids vs the oracle)"}
+
     if rank != 0:
-        return
+        return None
+
+    peaks, peak_kind = measured_peaks()
+    import workloads as W
+    gt = W.exact_ground_truth(X, Q[:ngt], k, w["metric"])
+    recall = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(res_i[:ngt], gt)]))
+
+    tj = traffic_for(wname)
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    if args.arith == "tensor":
+        # tc_knn_kernel (list mode): GEMM-form distances on tcgen05; algorithmic flops = 2 * dim per
+        # (query, scanned vector) pair; the kernel runs inside a longer step -> sustained peak
+        flops = 2.0 * evals * dim
+        tpeak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        traffic = tj.get("tensor_dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                    "traffic": traffic, "peak_source": peak_kind + " (sustained bf16, MEASURED_PEAKS.json)",
+                    "kernel": "tc_knn_kernel (list mode)", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
+                    "distance_evals_per_launch": evals,
+                    "hbm": None if not traffic else {"achieved": traffic / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                                     "frac": traffic / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                                     "note": "ncu dram bytes of one launch / event-timed launch duration"},
+                    "note": "algorithmic flops only (2*dim per evaluation): K padded to 128 and tile padding (lists to 256 rows, "
+                            "query groups to 128) are executed but not counted"}
+    else:
+        # fp32 list scan: every list block is re-used for a tile of queries from registers, so the binding limit
+        # is FP32 issue: 3 rounded ops (sub, mul, add) per element, 128 lanes per SM per clock
+        fp32_ops = evals * dim * 3.0
+        fp32_peak = 148 * 128 * sm_mhz * 1e6
+        algo_bytes = evals * (dim * 4.0 + 8.0)
+        roofline = {"bound": "fp32-issue", "achieved": fp32_ops / (kernel_ms * 1e-3) / 1e12, "peak": fp32_peak / 1e12,
+                    "unit": "T fp32 instr/s (non-fused)", "frac": fp32_ops / (kernel_ms * 1e-3) / fp32_peak,
+                    "traffic": tj.get("dram_bytes_per_launch"), "peak_source": "148 SM x 128 lanes x measured SM clock",
+                    "kernel": "scan_topk_kernel (list mode)", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
+                    "distance_evals_per_launch": evals,
+                    "hbm_query_major": {"achieved": algo_bytes / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                        "note": "SURVEY 8d's query-major bytes; the kernel groups queries per list, so this can exceed "
+                                                "the HBM peak and is not a roofline fraction"}}
+
+    cpu = None
+    if with_cpu and not args.no_cpu_baseline and world == 1:     # rank 0 at N = 1 only: the host cores are shared by the ranks
+        import oracle_lib as O
+        O.build_oracle()
+        cores = os.cpu_count() or 1
+        Cn = ix.centroids()
+        # the lists the GPU built (bit-identical to the oracle's assignment, tests/test_gpu_ivf.py) are the fixture;
+        # the CPU's own list assignment is timed on a bounded sample of rows
+        lists = O.lists_from_assignment(got_lists, w["lists"])
+        nrows_s = min(n, 200_000)
+        t = time.perf_counter()
+        O.ivf_assign(X[:nrows_s], Cn, nthreads=cores, native=True)
+        assign_rows_s = nrows_s / (time.perf_counter() - t)
+        sample = cpu_ivf_sample_size(w, X, Q, Cn, lists, cores)
+        qps_all, dt_all = cpu_ivf_qps(w, X, Q, Cn, lists, sample, cores, native=True)
+        s1 = max(8, min(sample, int(sample / cores) + 1))
+        qps_1, _ = cpu_ivf_qps(w, X, Q, Cn, lists, s1, 1, native=True)
+        cpu = {"value": qps_all, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": "%d queries of the 10k batch (%.1f s), oracle/ndb_oracle.c -O3 -march=native, OpenMP over "
+                         "queries; 1 thread = %.1f QPS on %d queries; excludes PostgreSQL executor/bufmgr overhead"
+                         % (sample, dt_all, qps_1, s1),
+               "value_1thread": qps_1,
+               "ivfinsert_rows_per_s": assign_rows_s,
+               "ivfinsert_full_build_s_extrapolated": n / assign_rows_s,
+               "ivfinsert_sample": "%d rows, all cores" % nrows_s}
+
+    par = {"none": "1 GPU",
+           "rows": "every inverted list striped over %d GPUs (row i on rank i %% %d), centroids and queries replicated, one "
+                   "ncclAllGather of packed 12-byte (dist,id) records per step + device merge by (dist,id)" % (world, world),
+           "lists": "whole lists split l %% %d, centroids and queries replicated, one ncclAllGather of packed (dist,id) records "
+                    "per step + device merge" % world,
+           "queries": "index replicated on %d GPUs, each answers its own %d-query batches (no data-path collective)" % (world, nq)}[shard]
+    line = {
+        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if gather or world == 1 else "weak",
+        "vs_baseline": None, "dtype": "bf16 select + f32 re-rank" if args.arith == "tensor" else "f32", "data": "synthetic",
+        "config": {"workload": w["label"], "rows": n, "dim": dim, "lists": w["lists"], "nprobe": w["nprobe"], "k": k,
+                   "queries_per_step": nq * replicas, "arith": args.arith,
+                   "l2": "inputs (%.2f GB of bf16 lists per GPU) larger than the 126 MB L2; 4 query batches rotate"
+                         % (n * dim * 2 / 1e9 / (world if gather else 1)),
+                   "parallelism": par, "comm_nranks": c.comm_nranks},
+        "recall_at_10": recall,
+        "alt": alt,
+        "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4 * world,
+                "d2h_bytes_per_step": nq * k * 12 * world, "ms_per_step": e2e_s * 1e3, "mode": e2e_mode,
+                "synchronous_call": {"value": nq * replicas / e2e_sync_s, "ms_per_step": e2e_sync_s * 1e3}},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "build": build,
+    }
+    return line
+
+
+def reference_ivf(args, w):
+    """--impl reference, IVF workloads: the CPU path on the host cores."""
     import oracle_lib as O
     O.build_oracle()
     X, Q = make_data(w)
+    cores = os.cpu_count() or 1
     ns = O.lib().orc_ivf_train_samples(X.shape[0], w["lists"])
     t0 = time.perf_counter()
     Cn, _, _, iters, _ = O.kmeans_train(X[:ns], w["lists"])
     train_s = time.perf_counter() - t0
-    cores = os.cpu_count() or 1
-    # bounded sample: sized for roughly 2-4 s of all-core work per step
-    sample = min(w["nq"], 2000)
-    assign = O.ivf_assign(X, Cn, nthreads=cores, native=True)
-    off, rows = O.lists_from_assignment(assign, w["lists"])
+    t0 = time.perf_counter()
+    assign = O.ivf_assign(X, Cn, nthreads=cores, native=True)      # ivfinsert's assignment loop for every row
+    assign_s = time.perf_counter() - t0
+    lists = O.lists_from_assignment(assign, w["lists"])
+    # bounded sample: sized for roughly 4 s of all-core work per step
+    sample = cpu_ivf_sample_size(w, X, Q, Cn, lists, cores, budget_s=4.0)
     times = []
     for s in range(args.warmup + args.steps):
         Qs = np.ascontiguousarray(Q[(s % 4) * w["nq"]:(s % 4) * w["nq"] + sample])
         t = time.perf_counter()
-        O.ivf_search(X, Cn, off, rows, Qs, w["nprobe"], w["k"], strategy=w["metric"], literal=False, nthreads=cores,
+        O.ivf_search(X, Cn, lists[0], lists[1], Qs, w["nprobe"], w["k"], strategy=w["metric"], literal=False, nthreads=cores,
                      native=True)
         if s >= args.warmup:
             times.append(time.perf_counter() - t)
     dt = float(np.mean(times))
     qps = sample / dt
-    line = {
-        "impl": "reference", "metric": "QPS@recall@10>=0.95", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+    return {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["label"], "rows": w["n"], "dim": w["dim"], "lists": w["lists"], "nprobe": w["nprobe"],
                    "k": w["k"], "queries_per_step": sample},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": "%d queries of the 10k batch per step, oracle/ndb_oracle.c -O3 -march=native, "
                                    "OpenMP over queries; excludes PostgreSQL executor/bufmgr overhead" % sample,
-                         "kmeans_train_s": train_s, "kmeans_iters": iters},
+                         "kmeans_train_s": train_s, "kmeans_iters": iters, "ivfinsert_assign_s": assign_s,
+                         "build_s": train_s + assign_s},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# C1: exact kNN in the <-> operator's arithmetic (fp64 Kahan), SURVEY 3.1
+# ---------------------------------------------------------------------------------------------------
+def c1_data(w):
+    rng = np.random.default_rng(w["seed"])
+    X = rng.standard_normal((w["n"], w["dim"]), dtype=np.float32)
+    Q = np.random.default_rng(4321).standard_normal((w["nq"] * 4, w["dim"]), dtype=np.float32)
+    return X, Q
+
+
+def run_exact(c, args, w, wname):
+    torch, ndb = c.torch, c.ndb
+    X, Q = c1_data(w)
+    n, nq, k, dim = w["n"], w["nq"], w["k"], w["dim"]
+    lo, hi = (c.rank * n) // c.world, ((c.rank + 1) * n) // c.world       # rows split, queries replicated
+    ds = ndb.Dataset(dim)
+    t0 = time.perf_counter()
+    ds.append(X[lo:hi], np.arange(lo, hi, dtype=np.int64))
+    load_s = time.perf_counter() - t0
+    qd = [torch.from_numpy(Q[i * nq:(i + 1) * nq]).cuda() for i in range(4)]
+    out_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    arith = ndb.ARITH_OP_F64
+
+    def step(s):
+        ds.knn_sharded_dev(qd[s % 4].data_ptr(), nq, k, out_d.data_ptr(), out_i.data_ptr(), ndb.L2, arith, c.stream)
+
+    ms_per_step, clocks = c.timed_steps(step, args.steps, args.warmup, c.world > 1)
+    l0 = ndb.launch_count()
+    step(0)
+    torch.cuda.synchronize()
+    launches = (ndb.launch_count() - l0) * args.steps
+    res_i = out_i.cpu().numpy()
+    res_d = out_d.cpu().numpy()
+    ndb.set_timing(True)
+    kms = []
+    for s in range(min(args.steps, 10)):
+        step(s)
+        kms.append(ndb.last_kernel_stats()[0])
+    ndb.set_timing(False)
+    kernel_ms = float(np.mean(kms))
+    qh = [torch.from_numpy(Q[i * nq:(i + 1) * nq]).pin_memory().numpy() for i in range(4)]
+    hd = torch.empty((nq, k), dtype=torch.float32).pin_memory().numpy()
+    hi_ = torch.empty((nq, k), dtype=torch.int64).pin_memory().numpy()
+    lib = ndb._lib.load()
+
+    def e2e(nsteps):
+        for s in range(nsteps):
+            ndb.check(lib.ndb_b200_knn_exact(ds.h, ndb.L2, arith, ndb.ptr(qh[s % 4]), nq, k, ndb.ptr(hd), ndb.ptr(hi_)))
+
+    e2e_s = None
+    if c.world == 1:
+        e2e(3)
+        e2e_s = c.timed_wall(lambda: e2e(args.steps), args.steps)
+    if c.rank != 0:
+        return None
+    import workloads as W
+    gt = W.exact_ground_truth(X, Q[:200], k, 1)
+    recall = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(res_i[:200], gt)]))
+    peaks, peak_kind = measured_peaks()
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    # Kahan-compensated fp64 L2 (vector_distance.c:93-122): per element 1 f32 sub (exact in fp64), 1 dmul, 4 dadd/dsub
+    # = 6 dependent fp64 instructions, none fusable without changing the rounding; 64 fp64 lanes per SM per clock
+    evals = float(nq) * (hi - lo)
+    fp64_ops = evals * dim * 6.0
+    fp64_peak = 148 * 64 * sm_mhz * 1e6
+    cpu = None
+    if not args.no_cpu_baseline and c.world == 1:
+        import oracle_lib as O
+        O.build_oracle()
+        cores = os.cpu_count() or 1
+        ns = min(nq, 200)
+        t = time.perf_counter()
+        od, oi = O.knn_exact(X, Q[:ns], k, O.L2, O.ARITH_OP_F64, nthreads=cores, native=True)
+        dt = time.perf_counter() - t
+        cpu = {"value": ns / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": "%d of the 1k queries (%.1f s), oracle fp64-Kahan operator loop, OpenMP over queries" % (ns, dt),
+               "ids_equal_gpu": bool(np.array_equal(oi, res_i[:ns])),
+               "distance_bits_equal_gpu": bool(np.array_equal(od.view(np.uint32), res_d[:ns].view(np.uint32)))}
+    return {
+        "metric": METRIC, "value": nq / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": c.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["label"], "rows": n, "dim": dim, "k": k, "queries_per_step": nq,
+                   "l2": "the 51 MB dataset fits the 126 MB L2 by construction of config 1; 4 query batches rotate",
+                   "parallelism": "1 GPU" if c.world == 1 else "rows split over %d GPUs, all-gather + merge" % c.world,
+                   "comm_nranks": c.comm_nranks},
+        "recall_at_10": recall,
+        "e2e": None if e2e_s is None else {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
+                                           "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_s * 1e3,
+                                           "mode": "ndb_b200_knn_exact, one synchronous call per batch"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp64-issue", "achieved": fp64_ops / (kernel_ms * 1e-3) / 1e12, "peak": fp64_peak / 1e12,
+                     "unit": "T fp64 instr/s (non-fused)", "frac": fp64_ops / (kernel_ms * 1e-3) / fp64_peak, "traffic": None,
+                     "peak_source": "148 SM x 64 fp64 lanes x measured SM clock", "kernel": "scan_topk_direct_kernel<L2, OP_F64>",
+                     "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
+                     "note": "6 rounded fp64 instructions per element (Kahan), the reference's arithmetic bit for bit; "
+                             "25.6 GFLOP-equivalent over 51 MB: compute-bound, not HBM-bound"},
+        "cpu_baseline": cpu, "clocks": clocks, "build": {"load_s": load_s},
+    }
+
+
+def reference_exact(args, w):
+    import oracle_lib as O
+    O.build_oracle()
+    X, Q = c1_data(w)
+    cores = os.cpu_count() or 1
+    ns = min(w["nq"], 200)
+    times = []
+    for s in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        O.knn_exact(X, Q[(s % 4) * w["nq"]:(s % 4) * w["nq"] + ns], w["k"], O.L2, O.ARITH_OP_F64, nthreads=cores, native=True)
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t)
+    dt = float(np.mean(times))
+    qps = ns / dt
+    return {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["label"], "rows": w["n"], "dim": w["dim"], "k": w["k"], "queries_per_step": ns},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                             "sample": "%d of the 1k queries per step, oracle fp64-Kahan operator loop, OpenMP over queries" % ns},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+# ---------------------------------------------------------------------------------------------------
+# C3: HNSW build + search (replicas only: the graph does not shard, SURVEY 8e)
+# ---------------------------------------------------------------------------------------------------
+def c3_data(w, n=None):
+    import workloads as W
+    n = n or w["n"]
+    return W.normalised(n, w["dim"], w["seed"]), W.normalised(w["nq"] * 2, w["dim"], w["seed"] + 1)
+
+
+def run_hnsw(c, args, w, wname):
+    torch, ndb = c.torch, c.ndb
+    import oracle_lib as O
+    import workloads as W
+    n = int(os.environ.get("NDB_BENCH_C3_ROWS", w["n"]))
+    X, Q = c3_data(w, n)
+    nq, k, dim = w["nq"], w["k"], w["dim"]
+    levels = O.hnsw_levels(n, seed=w["seed"])             # hnswGetRandomLevel draws (libc random(), seeded)
+    h = ndb.HnswIndex(dim, w["m"], w["efc"], w["efs"], ndb.COSINE)
+    select = ndb.HNSW_SELECT_HEURISTIC if args.hnsw_select == "heuristic" else ndb.HNSW_SELECT_CLOSEST
+    c.barrier()
+    t0 = time.perf_counter()
+    if c.world == 1 or c.rank == 0:
+        h.hnswbuild(X, levels=levels, select=select)
+    build_s = time.perf_counter() - t0
+    bcast_s = 0.0
+    if c.world > 1:                                      # one rank builds, the graph is broadcast to the replicas
+        t0 = time.perf_counter()
+        h.broadcast(X.shape[0], root=0)
+        c.barrier()
+        bcast_s = time.perf_counter() - t0
+    build_evals = h.last_evals()
+    # replicas: every rank answers its own slice of the batch (no data-path collective)
+    lo, hi = (c.rank * nq) // c.world, ((c.rank + 1) * nq) // c.world
+    qd = [torch.from_numpy(Q[i * nq + lo:i * nq + hi]).cuda() for i in range(2)]
+    out_d = torch.empty((hi - lo, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((hi - lo, k), dtype=torch.int64, device="cuda")
+    strategy = 1          # the AMs always pass strategy 1 to hnswSearch (Q4); on unit vectors L2 rank == cosine rank
+
+    def step(s, ef=w["efs"]):
+        h.search_dev(qd[s % 2].data_ptr(), hi - lo, out_d.data_ptr(), out_i.data_ptr(), ef, k, strategy, ndb.HNSW_BESTFIRST, c.stream)
+
+    ms_per_step, clocks = c.timed_steps(step, args.steps, args.warmup, False)
+    l0 = ndb.launch_count()
+    step(0)
+    torch.cuda.synchronize()
+    launches = (ndb.launch_count() - l0) * args.steps
+    evals_q = h.last_evals() / max(1, hi - lo)
+    res_i = out_i.cpu().numpy()
+    ndb.set_timing(True)
+    kms = []
+    for s in range(min(args.steps, 5)):
+        step(s)
+        kms.append(ndb.last_kernel_stats()[0])
+    ndb.set_timing(False)
+    kernel_ms = float(np.mean(kms))
+    qh = [torch.from_numpy(Q[i * nq + lo:i * nq + hi]).pin_memory().numpy() for i in range(2)]
+
+    def e2e(nsteps):
+        for s in range(nsteps):
+            h.search(qh[s % 2], w["efs"], k, strategy, ndb.HNSW_BESTFIRST)
+
+    e2e(2)
+    e2e_s = c.timed_wall(lambda: e2e(args.steps), args.steps)
+    if c.rank != 0:
+        return None
+    ngt = 200
+    gt = W.exact_ground_truth(X, Q[:ngt], k, 1)
+    rec = lambda ids: float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(ids[:ngt], gt)]))
+    recall = rec(res_i)
+    # recall / QPS against ef (the metric asks for recall >= 0.95; C3's isotropic data needs a far larger beam)
+    curve = []
+    qs = torch.from_numpy(Q[:1000]).cuda()
+    od = torch.empty((1000, k), dtype=torch.float32, device="cuda")
+    oi = torch.empty((1000, k), dtype=torch.int64, device="cuda")
+    for ef in [int(e) for e in args.hnsw_efs.split(",") if e]:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h.search_dev(qs.data_ptr(), 1000, od.data_ptr(), oi.data_ptr(), ef, k, strategy, ndb.HNSW_BESTFIRST, c.stream)
+        ev0.record()
+        h.search_dev(qs.data_ptr(), 1000, od.data_ptr(), oi.data_ptr(), ef, k, strategy, ndb.HNSW_BESTFIRST, c.stream)
+        ev1.record()
+        torch.cuda.synchronize()
+        curve.append({"ef": ef, "recall_at_10": rec(oi.cpu().numpy()), "qps": 1000 / (ev0.elapsed_time(ev1) * 1e-3),
+                      "evals_per_query": h.last_evals() / 1000})
+    peaks, peak_kind = measured_peaks()
+    bytes_q = evals_q * (dim * 4 + 2 * w["m"] * 4)
+    ach = bytes_q * (hi - lo) / (kernel_ms * 1e-3) / 1e9
+    tj = traffic_for(wname)
+    return {
+        "metric": METRIC, "value": nq / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": c.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if c.world > 1 else "strong",
+        "vs_baseline": None, "dtype": "f32 products, f64 accumulate (hnswComputeDistance)", "data": "synthetic",
+        "config": {"workload": w["label"], "rows": n, "dim": dim, "m": w["m"], "ef_construction": w["efc"], "ef_search": w["efs"],
+                   "k": k, "queries_per_step": nq, "select": args.hnsw_select,
+                   "l2": "%.1f GB of node vectors, far larger than the 126 MB L2; 2 query batches rotate" % (n * dim * 4 / 1e9),
+                   "parallelism": "1 GPU" if c.world == 1 else "replicas only: rank 0 builds, graph broadcast (ncclBroadcast), "
+                                  "queries split over %d GPUs" % c.world, "comm_nranks": c.comm_nranks},
+        "recall_at_10": recall, "recall_vs_ef": curve,
+        "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 12,
+                "ms_per_step": e2e_s * 1e3, "mode": "ndb_b200_hnsw_search, one synchronous call per batch"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                     "traffic": tj.get("dram_bytes_per_launch"), "peak_source": peak_kind, "kernel": "hnsw_search_kernel",
+                     "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step, "evals_per_query": evals_q,
+                     "note": "algorithmic bytes = evaluations x (dim*4 + 2m*4): every evaluation gathers one node vector and its "
+                             "neighbour list (SURVEY 8d)"},
+        "cpu_baseline": None, "clocks": clocks,
+        "build": {"build_s": build_s, "broadcast_s": bcast_s, "inserts_per_s": n / max(build_s, 1e-9),
+                  "evals_per_insert": build_evals / n},
+    }
+
+
+def reference_hnsw(args, w):
+    """CPU: the oracle's sequential hnswInsertNode + hnswSearch on a bounded prefix of the rows (the full 1 M x 768
+    sequential build takes hours on one core, which is the reference's execution model: EXCLUSIVE meta lock)."""
+    import oracle_lib as O
+    O.build_oracle()
+    n = int(os.environ.get("NDB_BENCH_C3_CPU_ROWS", "20000"))
+    X, Q = c3_data(w, n)
+    cores = os.cpu_count() or 1
+    levels = O.hnsw_levels(n, seed=w["seed"])
+    g = O.Hnsw(w["dim"], w["m"], w["efc"], w["efs"], capacity=n, native=True)
+    t0 = time.perf_counter()
+    g.build(X, levels, 1)
+    build_s = time.perf_counter() - t0
+    ns = 2000
+    times = []
+    for s in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        g.search(Q[(s % 2) * w["nq"]:(s % 2) * w["nq"] + ns], w["efs"], w["k"], 1, 1, nthreads=cores)
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t)
+    dt = float(np.mean(times))
+    qps = ns / dt
+    return {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 products, f64 accumulate", "data": "synthetic",
+            "config": {"workload": w["label"], "rows": n, "dim": w["dim"], "queries_per_step": ns,
+                       "note": "bounded sample: the first %d rows (sequential CPU build %.1f s = %.0f inserts/s on one core)"
+                               % (n, build_s, n / build_s)},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                             "sample": "%d queries per step on a %d-row graph, oracle best-first search, OpenMP over queries" % (ns, n),
+                             "build_s": build_s, "build_inserts_per_s": n / build_s},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+# ---------------------------------------------------------------------------------------------------
+# C5: brute-force kNN + k-means over bf16-valued rows, rows sharded (weak scaling: 6.25 M rows per GPU)
+# ---------------------------------------------------------------------------------------------------
+def run_brute(c, args, w, wname):
+    torch, ndb = c.torch, c.ndb
+    npg, dim, k, nq, kk = w["n_per_gpu"], w["dim"], w["k"], w["nq"], w["kmeans_k"]
+    # rows generated per shard on the device from seed + rank (SURVEY 8d), rounded to bf16-representable values
+    g = torch.Generator(device="cuda")
+    g.manual_seed(w["seed"] + c.rank)
+    ds = ndb.Dataset(dim)
+    t0 = time.perf_counter()
+    chunk = 1_250_000
+    first = None
+    for s0 in range(0, npg, chunk):
+        m = min(chunk, npg - s0)
+        x = torch.randn((m, dim), generator=g, device="cuda", dtype=torch.float32).to(torch.bfloat16).to(torch.float32)
+        ids = torch.arange(c.rank * npg + s0, c.rank * npg + s0 + m, device="cuda", dtype=torch.int64)
+        torch.cuda.synchronize()
+        ds.append_dev(x.data_ptr(), m, ids.data_ptr(), c.stream)
+        torch.cuda.synchronize()
+        if first is None:
+            first = x[:max(kk, 1)].clone()
+    load_s = time.perf_counter() - t0
+    gq = torch.Generator(device="cuda")
+    gq.manual_seed(w["seed"] + 99991)
+    qd = [torch.randn((nq, dim), generator=gq, device="cuda", dtype=torch.float32).to(torch.bfloat16).to(torch.float32) for _ in range(4)]
+    out_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+
+    def step(s):
+        ds.knn_sharded_dev(qd[s % 4].data_ptr(), nq, k, out_d.data_ptr(), out_i.data_ptr(), ndb.L2, ndb.ARITH_TENSOR, c.stream)
+
+    ms_per_step, clocks = c.timed_steps(step, args.steps, args.warmup, c.world > 1)
+    l0 = ndb.launch_count()
+    step(0)
+    torch.cuda.synchronize()
+    launches = (ndb.launch_count() - l0) * args.steps
+    ndb.set_timing(True)
+    kms = []
+    for s in range(min(args.steps, 5)):
+        step(s)
+        kms.append(ndb.last_kernel_stats()[0])
+    ndb.set_timing(False)
+    kernel_ms = float(np.mean(kms))
+    # parity inside the run: the same step in fp32 FFMA arithmetic on a slice of the queries
+    step(0)
+    chk_d = torch.empty((64, k), dtype=torch.float32, device="cuda")
+    chk_i = torch.empty((64, k), dtype=torch.int64, device="cuda")
+    ds.knn_sharded_dev(qd[0].data_ptr(), 64, k, chk_d.data_ptr(), chk_i.data_ptr(), ndb.L2, ndb.ARITH_FAST, c.stream)
+    torch.cuda.synchronize()
+    ids_same = float((chk_i == out_i[:64]).float().mean().item())
+    rel = float(((chk_d - out_d[:64]).abs() / chk_d.clamp(min=1e-9)).max().item())
+    # e2e: host queries in, merged results out
+    qh = [q.cpu().pin_memory().numpy() for q in qd]
+    hd = torch.empty((nq, k), dtype=torch.float32).pin_memory().numpy()
+    hi_ = torch.empty((nq, k), dtype=torch.int64).pin_memory().numpy()
+    lib = ndb._lib.load()
+    e2e_s = None
+    if c.world == 1:
+        def e2e(nsteps):
+            for s in range(nsteps):
+                ndb.check(lib.ndb_b200_knn_exact(ds.h, ndb.L2, ndb.ARITH_TENSOR, ndb.ptr(qh[s % 4]), nq, k, ndb.ptr(hd), ndb.ptr(hi_)))
+        e2e(2)
+        e2e_s = c.timed_wall(lambda: e2e(args.steps), args.steps)
+
+    # k-means (k = kmeans_k) over this rank's rows: Lloyd iterations with all-reduce of sums / counts / cost
+    km = None
+    if kk:
+        nkm = min(npg, int(os.environ.get("NDB_BENCH_C5_KMEANS_ROWS", npg)))
+        xk = torch.randn((nkm, dim), generator=g, device="cuda", dtype=torch.float32).to(torch.bfloat16).to(torch.float32)
+        C0 = xk[:kk].clone()
+        if c.world > 1:
+            ndb.check(lib.ndb_b200_comm_broadcast_dev(ndb.ptr(C0.data_ptr()), kk * dim * 4, 0, ndb.ptr(c.stream)))
+        assign = torch.empty(nkm, dtype=torch.int32, device="cuda")
+        counts = torch.empty(kk, dtype=torch.int32, device="cuda")
+        iters_cap = int(os.environ.get("NDB_BENCH_C5_KMEANS_ITERS", "3"))
+        c.barrier()
+        t0 = time.perf_counter()
+        its, cost = ndb.kmeans_train_sharded_dev(xk.data_ptr(), nkm, dim, kk, C0.data_ptr(), assign.data_ptr(), counts.data_ptr(),
+                                                 max_iter=iters_cap, tol=0.001, stream=c.stream)
+        torch.cuda.synchronize()
+        c.barrier()
+        km_s = c.max_over_ranks(time.perf_counter() - t0)
+        km = {"rows_per_gpu": nkm, "k": kk, "iterations": its, "s_per_iteration": km_s / max(1, its),
+              "assign_tflops_aggregate": 2.0 * nkm * c.world * kk * dim * its / km_s / 1e12,
+              "collectives_per_iteration": "allreduce(k*d f32 sums), allreduce(k i32 counts), allreduce(1 f32 cost)",
+              "counts_sum": int(counts.sum().item()), "cost": cost}
+    if c.rank != 0:
+        return None
+    peaks, peak_kind = measured_peaks()
+    rows = npg * c.world
+    flops = 2.0 * npg * nq * dim                      # per GPU per launch
+    tpeak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    ach = flops / (kernel_ms * 1e-3) / 1e12
+    tj = traffic_for(wname)
+    return {
+        "metric": METRIC, "value": nq / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": c.world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": w["label"], "rows": rows, "rows_per_gpu": npg, "dim": dim, "k": k, "queries_per_step": nq,
+                   "l2": "%.1f GB of bf16 rows per GPU, larger than the 126 MB L2; 4 query batches rotate" % (npg * dim * 2 / 1e9),
+                   "parallelism": "1 GPU" if c.world == 1 else "rows sharded over %d GPUs (6.25 M each), queries replicated, one "
+                                  "ncclAllGather of packed (dist,id) records + device merge" % c.world,
+                   "comm_nranks": c.comm_nranks,
+                   "note": "weak scaling by rows: QPS stays flat while the searched set grows with N; see tflops_aggregate"},
+        "recall_at_10": None, "exact_check": {"queries": 64, "ids_equal_fp32_path": ids_same, "max_rel_distance_error": rel,
+                                             "tolerance": 1e-3},
+        "tflops_aggregate": 2.0 * rows * nq * dim / (ms_per_step * 1e-3) / 1e12,
+        "e2e": None if e2e_s is None else {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
+                                           "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_s * 1e3,
+                                           "mode": "ndb_b200_knn_exact(NDB_ARITH_TENSOR), one synchronous call per batch"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                     "traffic": tj.get("tensor_dram_bytes_per_launch"), "peak_source": peak_kind + " (sustained bf16)",
+                     "kernel": "tc_knn_kernel (dense mode)", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step},
+        "kmeans": km, "cpu_baseline": None, "clocks": clocks, "build": {"load_s": load_s},
+    }
+
+
+def reference_brute(args, w):
+    """CPU: exact fp32 kNN (the oracle's IVF_F32 loop) over a bounded number of rows and queries, extrapolated per row."""
+    import oracle_lib as O
+    O.build_oracle()
+    cores = os.cpu_count() or 1
+    n, ns = 200_000, 256
+    X = np.random.default_rng(w["seed"]).standard_normal((n, w["dim"]), dtype=np.float32)
+    Q = np.random.default_rng(99).standard_normal((ns, w["dim"]), dtype=np.float32)
+    times = []
+    for s in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        O.knn_exact(X, Q, w["k"], O.L2, O.ARITH_IVF_F32, nthreads=cores, native=True)
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t)
+    dt = float(np.mean(times))
+    rows = w["n_per_gpu"] * max(1, args.gpus)
+    qps = ns / dt * (n / rows)                        # linear in the rows scanned
+    return {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["label"], "rows": rows, "dim": w["dim"], "k": w["k"], "queries_per_step": ns},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                             "sample": "%d queries x %d rows per step, oracle f32 sequential loop, all cores; scaled by rows to %d"
+                                       % (ns, n, rows)},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+RUNNERS = {"ivf": (run_ivf, reference_ivf), "exact": (run_exact, reference_exact), "hnsw": (run_hnsw, reference_hnsw),
+           "brute": (run_brute, reference_brute)}
 
 
 def main():
@@ -171,327 +952,37 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--arith", default="tensor", choices=["ivf_f32", "fast", "tensor"],
-                    help="tensor: tcgen05 bf16 candidate selection + fp32 re-rank (default); ivf_f32: the reference's fp32 "
-                         "arithmetic end to end, bit-exact distances and ids")
-    ap.add_argument("--shard", default="queries", choices=["queries", "lists"],
-                    help="N > 1: 'queries' = index replicated, every GPU answers its own query batches, no data-path "
-                         "collective (weak scaling); 'lists' = inverted lists split between the GPUs, queries replicated, "
-                         "NCCL all-gather of the per-rank top-k + device merge (strong scaling; the capacity mode)")
+                    help="IVF workloads. tensor: tcgen05 bf16 candidate selection + fp32 re-rank (default); ivf_f32: the "
+                         "reference's fp32 arithmetic end to end, bit-exact distances and ids")
+    ap.add_argument("--shard", default="rows", choices=["rows", "lists", "queries"],
+                    help="IVF workloads, N > 1. rows: every list striped over the GPUs (strong scaling, default); lists: whole "
+                         "lists l %% N; both exchange the per-GPU top-k with one ncclAllGather + device merge. queries: index "
+                         "replicated, every GPU answers its own batches, no data-path collective (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="N = 1 default run: skip the additional C2 measurement")
+    ap.add_argument("--hnsw-select", default="closest", choices=["closest", "heuristic"])
+    ap.add_argument("--hnsw-efs", default="40,100,400,1600")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = WORKLOADS[args.workload]
+    run, ref = RUNNERS[w["kind"]]
 
     if args.impl == "reference":
-        run_reference(args, w)
+        if int(os.environ.get("RANK", "0")) == 0:        # rank 0 only; the other ranks exit 0 without work
+            print(json.dumps(ref(args, w)))
         return
 
-    import torch
-    import neurondb_b200 as ndb
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ndb.init(local)
-    arith = {"ivf_f32": ndb.ARITH_IVF_F32, "fast": ndb.ARITH_FAST, "tensor": ndb.ARITH_TENSOR}[args.arith]
-
-    gather = world > 1 and args.shard == "lists"        # lists split between the ranks -> results merged
-    replicas = world if (world > 1 and not gather) else 1
-    X, Q = make_data(w, rank if replicas > 1 else 0)
-    nq, k, dim = w["nq"], w["k"], w["dim"]
-    ix = ndb.IvfIndex(dim, w["lists"], w["metric"])
-    if gather:
-        ix.set_shard(rank, world)
-    t0 = time.perf_counter()
-    ix.ivfbuild(X)                     # k-means on the first min(10000, lists*100) rows (ivf_am.c:580)
-    t1 = time.perf_counter()
-    ix.ivfinsert(X)                    # list assignment + append for every row (ivf_am.c:797-1167)
-    t2 = time.perf_counter()
-    build = {"train_s": t1 - t0, "insert_s": t2 - t1}
-
-    # a real (non-NULL) stream: the C ABI treats a NULL stream as "the library's own stream", and
-    # torch.cuda.Event only sees work queued on torch's current stream
-    tstream = torch.cuda.Stream()
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-    assert stream != 0
-    qd = [torch.from_numpy(Q[i * nq:(i + 1) * nq]).cuda() for i in range(4)]
-    out_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
-    out_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
-    fin_d = fin_i = None
-    if gather:
-        all_d = torch.empty((world, nq, k), dtype=torch.float32, device="cuda")
-        all_i = torch.empty((world, nq, k), dtype=torch.int64, device="cuda")
-        fin_d = torch.empty_like(out_d)
-        fin_i = torch.empty_like(out_i)
-
-    def step(s, arith=arith):
-        q = qd[0 if os.environ.get("NDB_BENCH_ONE_BATCH") else s % 4]
-        ix.search_dev(q.data_ptr(), nq, out_d.data_ptr(), out_i.data_ptr(), w["nprobe"], k, ndb.IVF_FULL, arith, stream)
-        if gather:
-            dist.all_gather_into_tensor(all_d, out_d)
-            dist.all_gather_into_tensor(all_i, out_i)
-            ndb.check(ndb._lib.load().ndb_b200_merge_topk_dev(ndb.ptr(all_d.data_ptr()), ndb.ptr(all_i.data_ptr()), world,
-                                                              nq, k, ndb.ptr(fin_d.data_ptr()), ndb.ptr(fin_i.data_ptr()),
-                                                              ndb.ptr(stream)))
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for s in range(args.warmup):
-        step(s)
-    barrier()
-
-    def burn(seconds):
-        """Untimed steps of the same work: a step takes a fraction of a millisecond, so the K timed steps are over
-        before nvidia-smi (100 ms period) samples once.  The timed region sits inside ~1 s of continuous identical
-        load, and the clocks and throttle reasons reported are those of that second."""
-        if gather:
-            # the step contains collectives here: every rank must run the same number of them
-            for s in range(int(seconds * 2048)):
-                step(s)
-            torch.cuda.synchronize()
-            return
-        t_end, s = time.perf_counter() + seconds, 0
-        while time.perf_counter() < t_end:
-            for _ in range(16):
-                step(s)
-                s += 1
-            torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    burn(0.5)
-    launches0 = ndb.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for s in range(args.steps):
-        step(s)
-    ev1.record()
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = ndb.launch_count() - launches0
-    burn(0.5)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    clocks = sampler.stop()
-    clocks["window"] = "0.5 s of untimed identical steps before and after the timed region"
-    ms_per_step = elapsed_ms / args.steps
-    value = nq * replicas / (ms_per_step * 1e-3)
-
-    # recall@10 of the timed configuration against exact ground truth (first 500 queries of batch 0)
-    step(0)
-    torch.cuda.synchronize()
-    res_i = (fin_i if gather else out_i)[:500].cpu().numpy()
-
-    # dominant kernel (scan_topk_kernel): device time from CUDA events recorded by the library on the
-    # launching stream, algorithmic bytes = sum over (query, probed list) of len*(dim*4+8)  (SURVEY 8d)
-    ndb.set_timing(True)
-    kms, kbytes, kevals = [], [], []
-    for s in range(min(args.steps, 10)):
-        step(s)
-        ms, b, ev = ndb.last_kernel_stats()
-        kms.append(ms); kbytes.append(b); kevals.append(ev)
-    ndb.set_timing(False)
-    kernel_ms = float(np.mean(kms))
-    algo_bytes = float(np.mean(kbytes))
-    evals = float(np.mean(kevals))
-
-    # end to end through the host-pointer entry point with pinned host buffers
-    qh = [torch.from_numpy(Q[i * nq:(i + 1) * nq]).pin_memory() for i in range(4)]
-    hd = torch.empty((nq, k), dtype=torch.float32).pin_memory()
-    hi = torch.empty((nq, k), dtype=torch.int64).pin_memory()
-    lib = ndb._lib.load()
-
-    def e2e_step(s, arith=arith):
-        q = qh[s % 4]
-        ndb.check(lib.ndb_b200_ivf_search(ix.h, ndb.ptr(q.data_ptr()), nq, w["nprobe"], k, ndb.IVF_FULL, arith,
-                                          ndb.ptr(hd.data_ptr()), ndb.ptr(hi.data_ptr())))
-        if gather:
-            # ranks exchange their host results through the same NCCL path (device staging of 1.2 MB)
-            out_d.copy_(hd, non_blocking=True); out_i.copy_(hi, non_blocking=True)
-            dist.all_gather_into_tensor(all_d, out_d)
-            dist.all_gather_into_tensor(all_i, out_i)
-            ndb.check(lib.ndb_b200_merge_topk_dev(ndb.ptr(all_d.data_ptr()), ndb.ptr(all_i.data_ptr()), world, nq, k,
-                                                  ndb.ptr(fin_d.data_ptr()), ndb.ptr(fin_i.data_ptr()), ndb.ptr(stream)))
-            hd.copy_(fin_d, non_blocking=True); hi.copy_(fin_i, non_blocking=True)
-            torch.cuda.synchronize()
-
-    # pipelined form of the same call (ndb_b200_ivf_search_begin / _end, two batches in flight): the H2D
-    # copy of the next batch and the D2H copy of the previous one overlap this batch's kernels.  Every
-    # batch is still copied in from pinned host memory and its results copied back inside the timed region.
-    hd2 = [hd.numpy(), torch.empty((nq, k), dtype=torch.float32).pin_memory().numpy()]
-    hi2 = [hi.numpy(), torch.empty((nq, k), dtype=torch.int64).pin_memory().numpy()]
-    qh_np = [q.numpy() for q in qh]
-
-    def e2e_pipelined(nsteps, arith=arith):
-        prev = None
-        for s in range(nsteps):
-            tk = ix.search_begin(qh_np[s % 4], hd2[s % 2], hi2[s % 2], w["nprobe"], k, ndb.IVF_FULL, arith)
-            if prev is not None:
-                ix.search_end(prev)
-            prev = tk
-        ix.search_end(prev)
-
-    def timed(fn):
-        barrier()
-        t = time.perf_counter()
-        fn()
-        barrier()
-        dt = (time.perf_counter() - t) / args.steps
-        if world > 1:
-            tt = torch.tensor([dt], device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        return dt
-
-    for s in range(3):
-        e2e_step(s)
-    e2e_sync_s = timed(lambda: [e2e_step(s) for s in range(args.steps)])
-    if gather:
-        e2e_s, e2e_mode = e2e_sync_s, "synchronous call per batch + NCCL all-gather and merge"
-    else:
-        e2e_pipelined(4)
-        e2e_s = timed(lambda: e2e_pipelined(args.steps))
-        e2e_mode = "search_begin/search_end, 2 batches in flight"
-    e2e_val = nq * replicas / e2e_s
-
-    # the same step in the reference's own fp32 arithmetic (bit-exact path), for comparison
-    alt = None
-    if args.arith == "tensor":
-        a32 = ndb.ARITH_IVF_F32
-        for s in range(3):
-            step(s, a32)
-        barrier()
-        ev0.record()
-        for s in range(args.steps):
-            step(s, a32)
-        ev1.record()
-        barrier()
-        alt_ms = ev0.elapsed_time(ev1) / args.steps
-        for s in range(2):
-            e2e_step(s, a32)
-        barrier()
-        t = time.perf_counter()
-        for s in range(args.steps):
-            e2e_step(s, a32)
-        barrier()
-        alt_e2e = (time.perf_counter() - t) / args.steps
-        if world > 1:
-            tt = torch.tensor([alt_ms, alt_e2e * 1e3], device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            alt_ms, alt_e2e = float(tt[0].item()), float(tt[1].item()) * 1e-3
-        step(0, a32)
-        torch.cuda.synchronize()
-        ref_i = (fin_i if gather else out_i)[:500].cpu().numpy()
-        alt = {"arith": "ivf_f32", "value": nq * replicas / (alt_ms * 1e-3), "ms_per_step": alt_ms, "e2e": nq * replicas / alt_e2e,
-               "unit": "queries/s", "ids_equal_to_tensor_path": float((ref_i == res_i).mean()),
-               "note": "the reference's fp32 arithmetic end to end (bit-exact distances and ids vs the oracle)"}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peaks, peak_kind = measured_peaks()
-    import workloads as W
-    ngt = 500 if w["n"] <= 2_000_000 else 100
-    gt = W.exact_ground_truth(X, Q[:ngt], k, w["metric"])
-    recall = float(np.mean([len(set(a.tolist()) & set(b.tolist())) / k for a, b in zip(res_i[:ngt], gt)]))
-
-    traffic = tensor_traffic = None
-    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
-        try:
-            with open(tp) as f:
-                tj = json.load(f).get(args.workload, {})
-            traffic, tensor_traffic = tj.get("dram_bytes_per_launch"), tj.get("tensor_dram_bytes_per_launch")
-        except Exception:
-            traffic = tensor_traffic = None
-
-    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-    # the list-major kernel re-uses each list block for 8 queries from registers/L2, so its binding
-    # limit is the FP32 pipe: 3 rounded ops (sub, mul, add) per element, 128 lanes per SM per clock
-    fp32_ops = evals * dim * 3.0
-    fp32_peak = 148 * 128 * sm_mhz * 1e6
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
-                "kernel": "scan_topk_kernel (list mode)", "kernel_ms": kernel_ms,
-                "algorithmic_bytes_per_launch": algo_bytes, "distance_evals_per_launch": evals,
-                "note": "algorithmic bytes = query-major definition of SURVEY 8d; the kernel groups queries per list "
-                        "(8 per tile), so DRAM traffic is far below it and frac can exceed 1; see fp32",
-                "fp32": {"achieved_tops": fp32_ops / (kernel_ms * 1e-3) / 1e12, "peak_tops": fp32_peak / 1e12,
-                         "frac": fp32_ops / (kernel_ms * 1e-3) / fp32_peak, "unit": "T fp32 instr/s (non-fused)",
-                         "sm_mhz": sm_mhz}}
-
-    if args.arith == "tensor":
-        # tc_knn_kernel (list mode): GEMM-form distances on tcgen05; algorithmic flops = 2 * dim per
-        # (query, scanned vector) pair; the kernel runs inside a longer step -> sustained peak
-        flops = 2.0 * evals * dim
-        tpeak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        ach = flops / (kernel_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
-                    "traffic": tensor_traffic, "peak_source": peak_kind, "kernel": "tc_knn_kernel (list mode)",
-                    "kernel_ms": kernel_ms, "distance_evals_per_launch": evals,
-                    "note": "algorithmic flops only: the kernel also multiplies tile padding (lists padded to 256 rows, "
-                            "query groups padded to 128; about 7x the algorithmic flops on C2), which is not counted; the "
-                            "kernel is bound by its top-k epilogue, see DESIGN.md 4.2b"}
-
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:          # (rank 0 at N = 1 only: the host cores are shared by the ranks)
-        import oracle_lib as O
-        O.build_oracle()
-        cores = os.cpu_count() or 1
-        Cn = ix.centroids()
-        sample = min(nq, 4000)
-        qps_all, dt_all, _ = cpu_reference_qps(w, X, Q, Cn, sample, cores, native=True)
-        qps_1, dt_1, _ = cpu_reference_qps(w, X, Q, Cn, min(500, sample), 1, native=True)
-        # the reference's own build flags (-O2, no -march: NeuronDB/build.sh:712), all cores, smaller sample
-        qps_o2, _, _ = cpu_reference_qps(w, X, Q, Cn, min(1000, sample), cores, native=False)
-        cpu = {"value": qps_all, "unit": "queries/s", "cores": cores, "kind": "port",
-               "sample": "%d queries of the 10k batch (%.1f s), oracle/ndb_oracle.c -O3 -march=native, OpenMP over "
-                         "queries; 1 thread = %.0f QPS on %d queries; excludes PostgreSQL executor/bufmgr overhead"
-                         % (sample, dt_all, qps_1, min(500, sample)),
-               "value_1thread": qps_1, "value_reference_flags_O2": qps_o2}
-
-    line = {
-        "metric": "QPS@recall@10>=0.95", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if gather else "weak",
-        "vs_baseline": None, "dtype": "bf16 select + f32 re-rank" if args.arith == "tensor" else "f32", "data": "synthetic",
-        "config": {"workload": w["label"], "rows": w["n"], "dim": dim, "lists": w["lists"], "nprobe": w["nprobe"], "k": k,
-                   "queries_per_step": nq * replicas, "arith": args.arith,
-                   "l2": "inputs (%.2f GB of lists) larger than the 126 MB L2; 4 query batches rotate" % (w["n"] * dim * 4 / 1e9),
-                   "parallelism": ("lists sharded l %% %d, queries replicated, NCCL all-gather + device merge" % world) if gather
-                   else ("index replicated on %d GPUs, each answers its own %d-query batches (no data-path collective)"
-                         % (world, nq)) if world > 1 else "1 GPU"},
-        "recall_at_10": recall,
-        "alt": alt,
-        "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": nq * replicas * dim * 4,
-                "d2h_bytes_per_step": nq * replicas * k * 12, "ms_per_step": e2e_s * 1e3, "mode": e2e_mode,
-                "synchronous_call": {"value": nq * replicas / e2e_sync_s, "ms_per_step": e2e_sync_s * 1e3}},
-        "gpu_launches": int(launches),
-        "roofline": roofline,
-        "cpu_baseline": cpu,
-        "clocks": clocks,
-        "build": build,
-    }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    args.warmup = max(args.warmup, 3)
+    c = Ctx(need_comm=True)
+    line = run(c, args, w, args.workload)
+    if c.world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_also:
+        # the same run also measures C2 (configs[1]): value, e2e, recall, roofline of its own dominant kernel
+        c2 = run_ivf(c, args, WORKLOADS["c2"], "c2", with_cpu=not args.no_cpu_baseline, with_alt=True)
+        line["also"] = {"c2": c2}
+    if c.rank == 0:
+        print(json.dumps(line))
+    c.finish()
 
 
 if __name__ == "__main__":

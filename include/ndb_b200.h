@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NDB_B200_ABI_VERSION 1
+#define NDB_B200_ABI_VERSION 2
 
 /* error codes */
 #define NDB_B200_OK        0
@@ -180,7 +180,11 @@ int ndb_b200_ivf_assign(const ndb_b200_ivf *ix, const float *rows, int64_t n, in
  * (layouts ivf_am.c:75-106,241-261; PostgreSQL page header/line pointers).  Pages are staged
  * through pinned memory and decoded on the device. */
 int ndb_b200_ivf_load_relation(ndb_b200_ivf *ix, const void *blocks, uint32_t nblocks);
+/* the tail of the build: list layout of the inserted rows and (NDB_ARITH_TENSOR) the blocked bf16 copy.
+ * Searches do it lazily on first use; call it to keep it out of the first query (and inside build timing). */
+int ndb_b200_ivf_prepare(ndb_b200_ivf *ix, int arith);
 int64_t ndb_b200_ivf_size(const ndb_b200_ivf *ix);
+int ndb_b200_ivf_dim(const ndb_b200_ivf *ix);
 int ndb_b200_ivf_list_sizes(const ndb_b200_ivf *ix, int64_t *sizes /* nlists */);
 /* ivfrescan + ivfgettuple for a batch (:1439-1545,1911-2027): ivfSelectClusters (:1597-1717,
  * always L2) then ivfCollectCandidates (:1722-1909) with the index metric.
@@ -242,6 +246,9 @@ int ndb_b200_hnsw_search(ndb_b200_hnsw *h, const float *Q, int nq, int strategy,
                          int mode, float *dist, int64_t *ids);
 int ndb_b200_hnsw_search_dev(ndb_b200_hnsw *h, const float *Q_dev, int nq, int strategy, int ef, int k,
                              int mode, float *dist_dev, int64_t *ids_dev, void *stream);
+/* replicas: the graph does not shard; the rank that built it broadcasts it (ncclBroadcast) and
+ * every rank then answers its own share of the queries.  Collective over the communicator's ranks. */
+int ndb_b200_hnsw_broadcast(ndb_b200_hnsw *h, int root);
 /* distance evaluations of the last search batch (for the bytes-per-query roofline) */
 int64_t ndb_b200_hnsw_last_evals(const ndb_b200_hnsw *h);
 
@@ -252,6 +259,50 @@ int ndb_b200_merge_topk_dev(const float *dist_dev, const int64_t *ids_dev, int n
                             float *out_dist_dev, int64_t *out_ids_dev, void *stream);
 int ndb_b200_merge_topk(const float *dist, const int64_t *ids, int nshards, int nq, int k,
                         float *out_dist, int64_t *out_ids);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ----------------------
+ * Replaces the reference's scale-out path, NeuronDB/src/util/distributed.c: a coordinator that runs the
+ * query on every shard over libpq (:56-300) and merges the per-shard (id, distance) rows on the host by
+ * (distance ASC, id ASC) (:323-487; order :425-438).  Here a shard is one GPU of the box.
+ *   comm_unique_id  rank 0 draws the 128-byte NCCL id; the host side (torchrun env, a file, a
+ *                   PostgreSQL shared-memory slot ...) hands it to the other ranks
+ *   comm_init       ncclCommInitRank on the device given to ndb_b200_init; collective over all ranks
+ *   comm_shutdown   destroys the communicator (also done by ndb_b200_shutdown)
+ * NCCL is loaded at the first comm_* call (dlopen libnccl.so.2; NDB_B200_NCCL_LIB overrides the name);
+ * a process that never calls them does not need it. */
+#define NDB_B200_COMM_ID_BYTES 128
+int ndb_b200_comm_unique_id(void *id, size_t len);
+int ndb_b200_comm_init(int rank, int world, const void *id, size_t len);
+int ndb_b200_comm_shutdown(void);
+int ndb_b200_comm_rank(void);
+int ndb_b200_comm_nranks(void);
+int ndb_b200_comm_nccl_version(void);
+/* raw collectives on device buffers, queued on `stream` (NULL = the library stream); with one rank they
+ * are a device copy / a no-op.  type: 0 = f32, 1 = i32, 2 = f64, 3 = i64. */
+int ndb_b200_comm_allgather_dev(const void *send_dev, void *recv_dev, size_t bytes_per_rank, void *stream);
+int ndb_b200_comm_allreduce_sum_dev(void *buf_dev, size_t count, int type, void *stream);
+int ndb_b200_comm_broadcast_dev(void *buf_dev, size_t bytes, int root, void *stream);
+/* Sharded search = distributed_knn_search + merge_distributed_results (distributed.c:56-487): every rank
+ * answers the (replicated) query batch against the rows its handle holds -- whole lists
+ * (ndb_b200_ivf_set_shard) or a stripe of every list (the caller inserts rows i with i % world == rank,
+ * with their global ids) -- writes its top-k as packed records (4-byte distance block + 8-byte id block
+ * = 12 bytes per result), ONE ncclAllGather moves them, and every rank merges the world's lists on the
+ * device by (dist, id).  All ranks must make the same call; every rank receives the full result.
+ * Without a communicator (or world == 1) these are the plain searches. */
+int ndb_b200_ivf_search_sharded_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int nprobe, int k, int mode, int arith,
+                                    float *dist_dev, int64_t *ids_dev, void *stream);
+int ndb_b200_ivf_search_sharded(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, int k, int mode, int arith,
+                                float *dist, int64_t *ids);
+int ndb_b200_knn_exact_sharded_dev(ndb_b200_dataset *ds, int metric, int arith, const float *Q_dev, int nq, int k,
+                                   float *dist_dev, int64_t *ids_dev, void *stream);
+/* Row-sharded kmeans_run (ivf_am.c:2117-2159): n_local rows per rank, centroids replicated.  C_dev in: the
+ * initial centroids (kmeans_init: the first k rows of the GLOBAL order, broadcast by the caller), out: the
+ * trained ones.  Per Lloyd iteration one all-reduce of the k*d f32 sums, one of the k counts, one of the
+ * cost.  One rank: bit-identical to ndb_b200_kmeans_train; several: equal to fp32 rounding (the order in
+ * which the ranks' partial sums are added is the reduction's). */
+int ndb_b200_kmeans_train_sharded_dev(const float *X_dev, int64_t n_local, int d, int k, int max_iter, float tol,
+                                      float *C_dev, int *assign_dev, int *counts_dev, int *iters, float *cost,
+                                      void *stream);
 
 /* ---- index key extraction: ivfExtractVectorData (ivf_am.c:117-218), hnswExtractVectorData -----
  * (hnsw_am.c:1402-1519).  The access methods accept vector, halfvec, sparsevec and bit columns and

@@ -106,6 +106,22 @@ SIGNATURES = {
     "ndb_b200_keys_from_bits": (_i, [_p, _i64, _i, _p]),
     "ndb_b200_keys_from_bits_dev": (_i, [_p, _i64, _i, _p, _p]),
     "ndb_b200_keys_from_sparse": (_i, [_p, _p, _p, _i64, _i, _p]),
+    "ndb_b200_ivf_dim": (_i, [_p]),
+    "ndb_b200_ivf_prepare": (_i, [_p, _i]),
+    "ndb_b200_hnsw_broadcast": (_i, [_p, _i]),
+    "ndb_b200_comm_unique_id": (_i, [_p, _sz]),
+    "ndb_b200_comm_init": (_i, [_i, _i, _p, _sz]),
+    "ndb_b200_comm_shutdown": (_i, []),
+    "ndb_b200_comm_rank": (_i, []),
+    "ndb_b200_comm_nranks": (_i, []),
+    "ndb_b200_comm_nccl_version": (_i, []),
+    "ndb_b200_comm_allgather_dev": (_i, [_p, _p, _sz, _p]),
+    "ndb_b200_comm_allreduce_sum_dev": (_i, [_p, _sz, _i, _p]),
+    "ndb_b200_comm_broadcast_dev": (_i, [_p, _sz, _i, _p]),
+    "ndb_b200_ivf_search_sharded_dev": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "ndb_b200_ivf_search_sharded": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "ndb_b200_knn_exact_sharded_dev": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p]),
+    "ndb_b200_kmeans_train_sharded_dev": (_i, [_p, _i64, _i, _i, _i, _f, _p, _p, _p, C.POINTER(_i), C.POINTER(_f), _p]),
     "ndb_b200_launch_count": (_i64, []),
     "ndb_b200_set_timing": (_i, [_i]),
     "ndb_b200_last_kernel_stats": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)]),

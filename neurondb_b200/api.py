@@ -172,6 +172,66 @@ def keys_from_sparse(indptr, indices, values, total_dim):
     return out
 
 
+def _rows(a, dim, what):
+    """float32 C-contiguous [n, dim] view of `a`; a wrong shape is the reference's dimension error (EDIM)."""
+    a = f32(a)
+    if a.ndim != 2 or a.shape[1] != dim:
+        raise NdbError(-5, "%s: expected [n, %d] float32 rows, got shape %s" % (what, dim, a.shape))
+    return a
+
+
+def _pinned_like(a, dtype, shape, what):
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags.c_contiguous or tuple(a.shape) != tuple(shape):
+        raise NdbError(-1, "%s: expected a C-contiguous %s array of shape %s" % (what, np.dtype(dtype).name, tuple(shape)))
+    return a
+
+
+# ---- multi-GPU communicator (ndb_b200_comm_*) -----------------------------------------------------
+def comm_unique_id():
+    buf = (C.c_ubyte * 128)()
+    check(L.load().ndb_b200_comm_unique_id(buf, 128))
+    return bytes(buf)
+
+
+def comm_init(rank, world, uid):
+    buf = (C.c_ubyte * 128).from_buffer_copy(uid) if world > 1 else None
+    check(L.load().ndb_b200_comm_init(rank, world, buf, 128))
+
+
+def comm_init_torch():
+    """One process per GPU under torchrun: rank 0 draws the NCCL id, torch.distributed (any backend) hands it
+    to the other ranks, every rank joins.  torch is plumbing here; the data path is the library's own
+    communicator."""
+    import torch
+    import torch.distributed as dist
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+    uid = [comm_unique_id() if rank == 0 and world > 1 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    comm_init(rank, world, uid[0])
+    return rank, world
+
+
+def comm_shutdown():
+    check(L.load().ndb_b200_comm_shutdown())
+
+
+def comm_nranks():
+    return int(L.load().ndb_b200_comm_nranks())
+
+
+def comm_rank():
+    return int(L.load().ndb_b200_comm_rank())
+
+
+def kmeans_train_sharded_dev(x_ptr, n_local, d, k, c_ptr, assign_ptr, counts_ptr=None, max_iter=50, tol=0.001, stream=None):
+    """ndb_b200_kmeans_train_sharded_dev on device pointers; returns (iters, cost)."""
+    iters, cost = C.c_int(), C.c_float()
+    check(L.load().ndb_b200_kmeans_train_sharded_dev(ptr(x_ptr), n_local, d, k, max_iter, tol, ptr(c_ptr), ptr(assign_ptr),
+                                                     ptr(counts_ptr), C.byref(iters), C.byref(cost), ptr(stream)))
+    return iters.value, cost.value
+
+
 class _Handle:
     _free = None
 
@@ -200,7 +260,7 @@ class Dataset(_Handle):
         check(L.load().ndb_b200_dataset_create(dim, C.byref(self.h)))
 
     def append(self, rows, ids=None):
-        rows = f32(rows)
+        rows = _rows(rows, self.dim, "dataset_append")
         idp = None if ids is None else np.ascontiguousarray(ids, np.int64)
         check(L.load().ndb_b200_dataset_append(self.h, ptr(rows), ptr(idp), rows.shape[0]))
 
@@ -211,7 +271,7 @@ class Dataset(_Handle):
         return int(L.load().ndb_b200_dataset_size(self.h))
 
     def knn(self, Q, k, metric=L2, arith=ARITH_OP_F64):
-        Q = f32(Q)
+        Q = _rows(Q, self.dim, "knn_exact")
         d = np.empty((Q.shape[0], k), np.float32)
         i = np.empty((Q.shape[0], k), np.int64)
         check(L.load().ndb_b200_knn_exact(self.h, metric, arith, ptr(Q), Q.shape[0], k, ptr(d), ptr(i)))
@@ -220,6 +280,12 @@ class Dataset(_Handle):
     def knn_dev(self, q_ptr, nq, k, dist_ptr, ids_ptr, metric=L2, arith=ARITH_OP_F64, stream=None):
         check(L.load().ndb_b200_knn_exact_dev(self.h, metric, arith, ptr(q_ptr), nq, k, ptr(dist_ptr), ptr(ids_ptr),
                                               ptr(stream)))
+
+    def knn_sharded_dev(self, q_ptr, nq, k, dist_ptr, ids_ptr, metric=L2, arith=ARITH_OP_F64, stream=None):
+        """Rows split between the ranks (this handle holds this rank's, with global ids), queries replicated:
+        local top-k, one all-gather, (dist, id) merge -- every rank gets the full result."""
+        check(L.load().ndb_b200_knn_exact_sharded_dev(self.h, metric, arith, ptr(q_ptr), nq, k, ptr(dist_ptr),
+                                                      ptr(ids_ptr), ptr(stream)))
 
 
 class IvfIndex(_Handle):
@@ -236,7 +302,7 @@ class IvfIndex(_Handle):
 
     def ivfbuild(self, rows):
         """ivfbuild (:501-745): k-means on the first min(10000, lists*100) rows; no list assignment (Q6)."""
-        rows = f32(rows)
+        rows = _rows(rows, self.dim, "ivfbuild")
         check(L.load().ndb_b200_ivf_train(self.h, ptr(rows), rows.shape[0]))
 
     def set_centroids(self, Cn):
@@ -251,17 +317,21 @@ class IvfIndex(_Handle):
 
     def ivfinsert(self, rows, ids=None):
         """ivfinsert (:797-1167) for each row in order; returns the list id of every row."""
-        rows = f32(rows)
+        rows = _rows(rows, self.dim, "ivfinsert")
         idp = None if ids is None else np.ascontiguousarray(ids, np.int64)
         out = np.empty(rows.shape[0], np.int32)
         check(L.load().ndb_b200_ivf_insert(self.h, ptr(rows), ptr(idp), rows.shape[0], ptr(out)))
         return out
 
     def assign(self, rows):
-        rows = f32(rows)
+        rows = _rows(rows, self.dim, "ivf_assign")
         out = np.empty(rows.shape[0], np.int32)
         check(L.load().ndb_b200_ivf_assign(self.h, ptr(rows), rows.shape[0], ptr(out)))
         return out
+
+    def prepare(self, arith=ARITH_IVF_F32):
+        """List layout (+ blocked bf16 copy for ARITH_TENSOR) now instead of inside the first search."""
+        check(L.load().ndb_b200_ivf_prepare(self.h, arith))
 
     def load_relation(self, blocks):
         blocks = np.ascontiguousarray(blocks, np.uint8)
@@ -276,14 +346,14 @@ class IvfIndex(_Handle):
         return out
 
     def select_clusters(self, Q, nprobe):
-        Q = f32(Q)
+        Q = _rows(Q, self.dim, "ivf_select_clusters")
         out = np.empty((Q.shape[0], nprobe), np.int32)
         check(L.load().ndb_b200_ivf_select_clusters(self.h, ptr(Q), Q.shape[0], nprobe, ptr(out)))
         return out
 
     def search(self, Q, nprobe=10, k=10, mode=IVF_FULL, arith=ARITH_IVF_F32):
         """ivfrescan + ivfgettuple for a batch of queries (:1439-1545, 1911-2027)."""
-        Q = f32(Q)
+        Q = _rows(Q, self.dim, "ivf_search")
         d = np.empty((Q.shape[0], k), np.float32)
         i = np.empty((Q.shape[0], k), np.int64)
         check(L.load().ndb_b200_ivf_search(self.h, ptr(Q), Q.shape[0], nprobe, k, mode, arith, ptr(d), ptr(i)))
@@ -292,6 +362,9 @@ class IvfIndex(_Handle):
     def search_begin(self, Q, dist, ids, nprobe=10, k=10, mode=IVF_FULL, arith=ARITH_IVF_F32):
         """Queue one batch (Q [nq, dim] float32, dist [nq, k] float32, ids [nq, k] int64: numpy arrays the
         caller keeps alive, ideally pinned); returns a ticket for search_end.  Two batches may be in flight."""
+        _pinned_like(Q, np.float32, (Q.shape[0] if getattr(Q, "ndim", 0) == 2 else -1, self.dim), "ivf_search_begin Q")
+        _pinned_like(dist, np.float32, (Q.shape[0], k), "ivf_search_begin dist")
+        _pinned_like(ids, np.int64, (Q.shape[0], k), "ivf_search_begin ids")
         t = C.c_int(-1)
         check(L.load().ndb_b200_ivf_search_begin(self.h, ptr(Q), Q.shape[0], nprobe, k, mode, arith, ptr(dist), ptr(ids),
                                                  C.byref(t)))
@@ -304,6 +377,20 @@ class IvfIndex(_Handle):
                    stream=None):
         check(L.load().ndb_b200_ivf_search_dev(self.h, ptr(q_ptr), nq, nprobe, k, mode, arith, ptr(dist_ptr),
                                                ptr(ids_ptr), ptr(stream)))
+
+
+    def search_sharded_dev(self, q_ptr, nq, dist_ptr, ids_ptr, nprobe=10, k=10, mode=IVF_FULL, arith=ARITH_IVF_F32,
+                           stream=None):
+        """Local search + all-gather of packed (dist, id) records + device merge (ndb_b200_ivf_search_sharded_dev)."""
+        check(L.load().ndb_b200_ivf_search_sharded_dev(self.h, ptr(q_ptr), nq, nprobe, k, mode, arith, ptr(dist_ptr),
+                                                       ptr(ids_ptr), ptr(stream)))
+
+    def search_sharded(self, Q, nprobe=10, k=10, mode=IVF_FULL, arith=ARITH_IVF_F32, dist=None, ids=None):
+        Q = _rows(Q, self.dim, "ivf_search_sharded")
+        d = np.empty((Q.shape[0], k), np.float32) if dist is None else dist
+        i = np.empty((Q.shape[0], k), np.int64) if ids is None else ids
+        check(L.load().ndb_b200_ivf_search_sharded(self.h, ptr(Q), Q.shape[0], nprobe, k, mode, arith, ptr(d), ptr(i)))
+        return d, i
 
 
 class HnswIndex(_Handle):
@@ -319,7 +406,7 @@ class HnswIndex(_Handle):
         """hnswbuild (:343-415).  select=HNSW_SELECT_HEURISTIC swaps the reference's closest-m / capped
         back-link rule for the diversity heuristic with re-selection of full neighbours (an extension)."""
         check(L.load().ndb_b200_hnsw_set_select(self.h, select))
-        rows = f32(rows)
+        rows = _rows(rows, self.dim, "hnswbuild")
         idp = None if ids is None else np.ascontiguousarray(ids, np.int64)
         lv = None if levels is None else np.ascontiguousarray(levels, np.int32)
         check(L.load().ndb_b200_hnsw_build(self.h, ptr(rows), ptr(idp), rows.shape[0], ptr(lv), seed, batch))
@@ -357,7 +444,7 @@ class HnswIndex(_Handle):
 
     def search(self, Q, ef=None, k=10, strategy=None, mode=HNSW_BESTFIRST):
         """hnswrescan + hnswgettuple for a batch (:904-1056); ef defaults to the index's ef_search."""
-        Q = f32(Q)
+        Q = _rows(Q, self.dim, "hnsw_search")
         d = np.empty((Q.shape[0], k), np.float32)
         i = np.empty((Q.shape[0], k), np.int64)
         check(L.load().ndb_b200_hnsw_search(self.h, ptr(Q), Q.shape[0], strategy or self.metric, ef or self.efs, k,
@@ -370,3 +457,7 @@ class HnswIndex(_Handle):
 
     def last_evals(self):
         return int(L.load().ndb_b200_hnsw_last_evals(self.h))
+
+    def broadcast(self, n=None, root=0):
+        """Replicas: the rank that built the graph sends it to the others (collective)."""
+        check(L.load().ndb_b200_hnsw_broadcast(self.h, root))

@@ -47,6 +47,7 @@ extern thread_local char g_last_error[512];
 // ---- global context ------------------------------------------------------------------
 struct Context {
     bool initialized = false;
+    uint64_t generation = 0;              // bumped by every ndb_b200_init: per-device caches compare against it
     int device = -1;
     int sm_count = 148;
     size_t smem_optin = 0;

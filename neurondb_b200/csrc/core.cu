@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "arith.cuh"
 #include "layout.cuh"
+#include "comm.cuh"
+#include "kmeans.cuh"
 
 #include <cstdarg>
 #include <unistd.h>
@@ -20,6 +22,7 @@ void set_error(const char *fmt, ...)
 }
 
 static Context g_ctx;
+static uint64_t g_generation = 0;
 static pid_t g_ctx_pid = 0;
 Context &ctx() { return g_ctx; }
 
@@ -369,6 +372,7 @@ int ndb_b200_init(int device)
     if (g_ctx.initialized && g_ctx_pid == getpid() && g_ctx.device == device) return NDB_B200_OK;
     if (g_ctx.initialized && g_ctx_pid == getpid()) ndb_b200_shutdown();
     g_ctx = Context();
+    g_ctx.generation = ++g_generation;
     int n = ndb_b200_device_count();
     NDB_REQUIRE(n > 0, NDB_B200_ENOTINIT, "no CUDA device visible (this library has no CPU fallback)");
     NDB_REQUIRE(device >= 0 && device < n, NDB_B200_EINVAL, "device %d out of range [0,%d)", device, n);
@@ -398,6 +402,8 @@ void ndb_b200_shutdown(void)
     if (!g_ctx.initialized || g_ctx_pid != getpid()) { g_ctx = Context(); return; }
     cudaSetDevice(g_ctx.device);
     cudaStreamSynchronize(g_ctx.stream);
+    comm_at_shutdown();
+    kmeans_at_shutdown();
     if (g_ctx.pinned) cudaFreeHost(g_ctx.pinned);
     if (g_ctx.d_badidx) cudaFree(g_ctx.d_badidx);
     g_ctx.d_badidx = nullptr;

@@ -19,6 +19,7 @@
 #include "layout.cuh"
 #include "arith.cuh"
 #include "pages.cuh"
+#include "comm.cuh"
 
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
@@ -824,6 +825,60 @@ int ndb_b200_hnsw_export_graph(const ndb_b200_hnsw *h, int *levels, uint32_t *nb
     if (upper && up) NDB_CUDA(cudaMemcpy(upper, h->upper.p, (size_t) up * 4, cudaMemcpyDeviceToHost));
     if (entry_point) *entry_point = h->entry;
     if (entry_level) *entry_level = h->entry_level;
+    return NDB_B200_OK;
+}
+
+// the graph does not shard, so one rank builds (hnswbuild is serial in the reference too,
+// hnsw_am.c:343-415) and the finished graph -- node vectors, levels, neighbour slots -- reaches the
+// replicas with ncclBroadcast over NVLink (C3: ~3.2 GB).  Collective: every rank of the communicator calls it.
+int ndb_b200_hnsw_broadcast(ndb_b200_hnsw *h, int root)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(h && root >= 0 && root < comm_nranks(), NDB_B200_EINVAL, "hnsw_broadcast: bad argument");
+    if (comm_nranks() == 1) return NDB_B200_OK;
+    cudaStream_t s = ctx().stream;
+    const bool am_root = comm_rank() == root;
+    NDB_REQUIRE(!am_root || h->n > 0, NDB_B200_ESTATE, "hnsw_broadcast: the root holds no graph");
+    struct Hdr { int64_t n, up; uint32_t entry; int entry_level, dim, m; } hdr = {0, 0, INVALID_SLOT, -1, h->dim, h->m};
+    if (am_root) { hdr.n = h->n; hdr.up = h->h_upper_off[h->n]; hdr.entry = h->entry; hdr.entry_level = h->entry_level; }
+    DevBuf dh;
+    NDB_CHECK(dh.reserve(sizeof(Hdr)));
+    NDB_CUDA(cudaMemcpyAsync(dh.p, &hdr, sizeof(Hdr), cudaMemcpyHostToDevice, s));
+    NDB_CHECK(comm_broadcast(dh.p, sizeof(Hdr), root, s));
+    Hdr got;
+    NDB_CUDA(cudaMemcpyAsync(&got, dh.p, sizeof(Hdr), cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    NDB_REQUIRE(got.dim == h->dim && got.m == h->m, NDB_B200_EDIM, "hnsw_broadcast: the root's index has dim %d m %d, this handle dim %d m %d",
+                got.dim, got.m, h->dim, h->m);
+    const int64_t n = got.n, up = got.up;
+    if (!am_root) {
+        h->n = n;
+        NDB_CHECK(h->vec.reserve((size_t) n * h->dimp * 4));
+        NDB_CHECK(h->ids.reserve((size_t) n * 8));
+        NDB_CHECK(h->level.reserve((size_t) n * 4));
+        NDB_CHECK(h->cnt.reserve((size_t) n * HNSW_MAX_LEVEL * 2));
+        NDB_CHECK(h->nbr0.reserve((size_t) n * 2 * h->m * 4));
+        NDB_CHECK(h->upper_off.reserve((size_t) (n + 1) * 8));
+        NDB_CHECK(h->upper.reserve((size_t) (up ? up : 1) * 4));
+    }
+    NDB_CHECK(comm_broadcast(h->vec.p, (size_t) n * h->dimp * 4, root, s));
+    NDB_CHECK(comm_broadcast(h->ids.p, (size_t) n * 8, root, s));
+    NDB_CHECK(comm_broadcast(h->level.p, (size_t) n * 4, root, s));
+    NDB_CHECK(comm_broadcast(h->cnt.p, (size_t) n * HNSW_MAX_LEVEL * 2, root, s));
+    NDB_CHECK(comm_broadcast(h->nbr0.p, (size_t) n * 2 * h->m * 4, root, s));
+    NDB_CHECK(comm_broadcast(h->upper_off.p, (size_t) (n + 1) * 8, root, s));
+    if (up) NDB_CHECK(comm_broadcast(h->upper.p, (size_t) up * 4, root, s));
+    if (!am_root) {
+        h->h_level.resize(n);
+        h->h_upper_off.resize(n + 1);
+        NDB_CUDA(cudaMemcpyAsync(h->h_level.data(), h->level.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
+        NDB_CUDA(cudaMemcpyAsync(h->h_upper_off.data(), h->upper_off.p, (size_t) (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+        h->entry = got.entry;
+        h->entry_level = got.entry_level;
+        h->vnorm_ok = false;
+        h->bits_words = 0;
+    }
+    NDB_CUDA(cudaStreamSynchronize(s));
     return NDB_B200_OK;
 }
 

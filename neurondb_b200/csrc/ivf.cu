@@ -723,6 +723,7 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     p.xb = ix->tc.xb.as<__nv_bfloat16>();
     p.xnorm = ix->tc.xnorm.as<float>();
     if (ix->metric == NDB_COSINE) NDB_CHECK(tc_store_rinv(ix->tc, &p.xnorm, s));
+    if (ix->metric == NDB_IP) NDB_CHECK(tc_store_pad0(ix->tc, &p.xnorm, s));
     p.qb = ix->tcs.qb.as<__nv_bfloat16>();
     p.qnorm = ix->tcs.qnorm.as<float>();
     p.nkc = nkc;
@@ -966,12 +967,27 @@ int ndb_b200_ivf_insert(ndb_b200_ivf *ix, const float *rows, const int64_t *ids,
 }
 
 int64_t ndb_b200_ivf_size(const ndb_b200_ivf *ix) { return ix ? ix->nrows : 0; }
+int ndb_b200_ivf_dim(const ndb_b200_ivf *ix) { return ix ? ix->dim : 0; }
 
 int ndb_b200_ivf_list_sizes(const ndb_b200_ivf *ix, int64_t *sizes)
 {
     NDB_REQUIRE(ix && sizes, NDB_B200_EINVAL, "ivf_list_sizes: NULL input");
     for (int l = 0; l < ix->nlists; l++) sizes[l] = 0;
     for (int64_t r = 0; r < ix->nrows; r++) sizes[ix->row_list[r]]++;
+    return NDB_B200_OK;
+}
+
+// Finish the build: lay the inserted rows out as lists and, for NDB_ARITH_TENSOR, make the blocked bf16 copy.
+// The searches do this lazily on their first call; ivfbuild-time accounting calls it explicitly so that
+// "index build seconds" contains all of it.
+int ndb_b200_ivf_prepare(ndb_b200_ivf *ix, int arith)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix, NDB_B200_EINVAL, "ivf_prepare: NULL index");
+    cudaStream_t s = ctx().stream;
+    NDB_CHECK(ivf_ready(ix, s));
+    if (arith == NDB_ARITH_TENSOR && ix->dim <= TC_MAX_DIM) NDB_CHECK(ivf_tensor_ready(ix, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
     return NDB_B200_OK;
 }
 

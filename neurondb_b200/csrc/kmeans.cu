@@ -16,6 +16,18 @@
 
 namespace ndb {
 
+// scratch of the row-sharded entry points, kept across Lloyd iterations and released by ndb_b200_shutdown
+static KMeansWork g_shard_work;
+static DevBuf g_shard_dcost;
+void kmeans_at_shutdown()
+{
+    KMeansWork &w = g_shard_work;
+    for (DevBuf *b : {&w.X, &w.C, &w.cstore, &w.assign, &w.keys_sorted, &w.vals_in, &w.vals_sorted, &w.start, &w.counts,
+                      &w.cub_tmp, &w.dcost, &w.cost, &w.scr.pdist, &w.scr.pslot, &w.scr.counter, &w.scr.qnorm})
+        b->release();
+    g_shard_dcost.release();
+}
+
 __global__ void iota_u32_kernel(uint32_t *out, int64_t n)
 {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,7 +292,7 @@ int ndb_b200_kmeans_shard_step_dev(const float *X_dev, int64_t n, int d, int k, 
     NDB_REQUIRE(X_dev && C_dev && assign_dev && sums_dev && counts_dev && n > 0 && d > 0 && k > 0, NDB_B200_EINVAL,
                 "kmeans_shard_step: bad argument");
     cudaStream_t s = stream ? (cudaStream_t) stream : ctx().stream;
-    static KMeansWork w;                 // scratch kept across iterations
+    KMeansWork &w = g_shard_work;
     NDB_CHECK(w.C.reserve((size_t) k * d * 4));
     NDB_CUDA(cudaMemcpyAsync(w.C.p, C_dev, (size_t) k * d * 4, cudaMemcpyDeviceToDevice, s));
     NDB_CHECK(kmeans_assign_dev(w, X_dev, n, d, k, METRIC_L2SQ, assign_dev, s));
@@ -293,7 +305,7 @@ int ndb_b200_kmeans_shard_cost_dev(const float *X_dev, int64_t n, int d, const f
     NDB_CHECK(require_init());
     NDB_REQUIRE(X_dev && C_dev && assign_dev && cost_dev && n > 0 && d > 0, NDB_B200_EINVAL, "kmeans_shard_cost: bad argument");
     cudaStream_t s = stream ? (cudaStream_t) stream : ctx().stream;
-    static DevBuf dcost;
+    DevBuf &dcost = g_shard_dcost;
     NDB_CHECK(dcost.reserve((size_t) n * 4));
     kmeans_sample_cost_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(X_dev, C_dev, assign_dev, n, d, dcost.as<float>());
     sequential_sum_kernel<<<1, 1024, 0, s>>>(dcost.as<float>(), n, cost_dev);

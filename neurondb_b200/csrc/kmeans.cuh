@@ -9,6 +9,8 @@ struct KMeansWork {
     ScanScratch scr;
 };
 
+void kmeans_at_shutdown();
+
 int dense_scan(const float *store, const void *vnorm, int64_t nvec, int dim, int dimp, int metric, int arith,
                const float *Q_dev, int nq, int k, ScanScratch &scr, int *out_nparts, cudaStream_t s);
 // w.C must hold the k*dim row-major centroids on the device

@@ -64,6 +64,8 @@ static int launch_one_direct(const ScanParams &prm, const ScanShape &sh, uint32_
     auto kern = scan_topk_direct_kernel<P, QT, KR>;
     const size_t smem = sh.smem - (size_t) SCAN_STAGES * SCAN_STAGE_BYTES;      // query tile only
     static thread_local size_t configured = 0;
+    static thread_local uint64_t cfg_gen = 0;
+    if (cfg_gen != ctx().generation) { configured = 0; cfg_gen = ctx().generation; }     // new device / re-init
     if (smem > configured) {
         NDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         configured = smem;
@@ -87,6 +89,8 @@ static int launch_one(const ScanParams &prm, const ScanShape &sh, uint32_t items
     if (scan_direct(prm.items != nullptr)) return launch_one_direct<P, QT, KR>(prm, sh, items_upper, s);
     auto kern = scan_topk_kernel<P, QT, KR>;
     static thread_local size_t configured = 0;
+    static thread_local uint64_t cfg_gen = 0;
+    if (cfg_gen != ctx().generation) { configured = 0; cfg_gen = ctx().generation; }
     if (sh.smem > configured) {
         NDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sh.smem));
         configured = sh.smem;

@@ -15,8 +15,8 @@ constexpr int TC_PACKED_MAX_TILES = 16;   // packed-key epilogue: 11 index bits 
 
 // stored rows in the blocked bf16 layout + squared norms of the rounded rows
 struct TcStore {
-    DevBuf xb, xnorm, xrinv;       // blocked rows, squared norms of the rounded rows, 1 / norm (cosine, on demand)
-    int64_t valid_for = -1, rinv_for = -2;
+    DevBuf xb, xnorm, xrinv, xpad0; // blocked rows, squared norms of the rounded rows, 1 / norm (cosine), 0 | +inf (inner product)
+    int64_t valid_for = -1, rinv_for = -2, pad0_for = -2;
     int64_t ntiles = 0;
     int nkc = 0;
 };
@@ -58,6 +58,7 @@ struct TcParams {
 
 int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s);
 int tc_store_rinv(TcStore &st, const float **out, cudaStream_t s);
+int tc_store_pad0(TcStore &st, const float **out, cudaStream_t s);
 int tc_build_store_mapped(TcStore &st, const float *il32_store, const uint32_t *src_slot_dev, int64_t n, int dim, int dimp,
                           cudaStream_t s);
 // npos_dev (optional): device count of tile positions actually in use (nqpad is then an upper bound)

@@ -565,16 +565,20 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             c[4 * i4 + 3] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 3]), n4.w);
                         } else if (METRIC == NDB_COSINE) {
                             // p.xnorm holds 1 / ||x|| here (0 for a zero row, +inf for a pad row): -x.q / ||x||
-                            // orders the rows like the cosine distance, whose 1 / ||q|| is applied on output
-                            c[4 * i4 + 0] = n4.x == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 0]) * n4.x;
-                            c[4 * i4 + 1] = n4.y == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 1]) * n4.y;
-                            c[4 * i4 + 2] = n4.z == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 2]) * n4.z;
-                            c[4 * i4 + 3] = n4.w == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 3]) * n4.w;
+                            // orders the rows like the cosine distance, whose 1 / ||q|| is applied on output.
+                            // A pad row is all zeros, its dot product is exactly 0 and 0 * inf = NaN, which
+                            // loses every comparison below (and packs as an empty key): one FMUL per column.
+                            c[4 * i4 + 0] = -__uint_as_float(v[4 * i4 + 0]) * n4.x;
+                            c[4 * i4 + 1] = -__uint_as_float(v[4 * i4 + 1]) * n4.y;
+                            c[4 * i4 + 2] = -__uint_as_float(v[4 * i4 + 2]) * n4.z;
+                            c[4 * i4 + 3] = -__uint_as_float(v[4 * i4 + 3]) * n4.w;
                         } else {
-                            c[4 * i4 + 0] = n4.x == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 0]);
-                            c[4 * i4 + 1] = n4.y == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 1]);
-                            c[4 * i4 + 2] = n4.z == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 2]);
-                            c[4 * i4 + 3] = n4.w == INFINITY ? INFINITY : -__uint_as_float(v[4 * i4 + 3]);
+                            // inner product: p.xnorm holds 0 for a stored row and +inf for a pad row, so the
+                            // candidate -x.q and the pad handling are one FADD per column
+                            c[4 * i4 + 0] = n4.x - __uint_as_float(v[4 * i4 + 0]);
+                            c[4 * i4 + 1] = n4.y - __uint_as_float(v[4 * i4 + 1]);
+                            c[4 * i4 + 2] = n4.z - __uint_as_float(v[4 * i4 + 2]);
+                            c[4 * i4 + 3] = n4.w - __uint_as_float(v[4 * i4 + 3]);
                         }
                     }
                     float m[16];
@@ -702,6 +706,7 @@ int tc_build_store_mapped(TcStore &st, const float *il32_store, const uint32_t *
     NDB_CUDA(cudaGetLastError());
     st.valid_for = n;
     st.rinv_for = -2;
+    st.pad0_for = -2;
     st.ntiles = ntiles;
     st.nkc = nkc;
     return NDB_B200_OK;
@@ -713,6 +718,27 @@ __global__ void tc_rinv_kernel(const float *__restrict__ xnorm, int64_t n, float
     if (i >= n) return;
     const float v = xnorm[i];
     out[i] = v == INFINITY ? INFINITY : (v > 0.0f ? 1.0f / sqrtf(v) : 0.0f);
+}
+
+__global__ void tc_pad0_kernel(const float *__restrict__ xnorm, int64_t n, float *__restrict__ out)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = xnorm[i] == INFINITY ? INFINITY : 0.0f;
+}
+
+// per-row additive term of the inner-product metric: 0 for a stored row, +inf for a pad row
+int tc_store_pad0(TcStore &st, const float **out, cudaStream_t s)
+{
+    const int64_t n = st.ntiles * TC_N;
+    if (st.pad0_for != st.valid_for || st.xpad0.cap < (size_t) n * 4) {
+        NDB_CHECK(st.xpad0.reserve((size_t) n * 4));
+        tc_pad0_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(st.xnorm.as<float>(), n, st.xpad0.as<float>());
+        count_launch();
+        NDB_CUDA(cudaGetLastError());
+        st.pad0_for = st.valid_for;
+    }
+    *out = st.xpad0.as<float>();
+    return NDB_B200_OK;
 }
 
 // per-row 1 / ||x|| for the cosine metric (built on first use, kept with the store)
@@ -760,10 +786,10 @@ int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s)
     // list length: the smallest of {1, 10, 16} that holds k (a shorter list = a tighter threshold)
 #define NDB_TC_LAUNCH(KT, M, PK)                                                                              \
     do {                                                                                                      \
-        static bool cfg = false;                                                                              \
-        if (!cfg) {                                                                                           \
+        static uint64_t cfg = 0;                                                                              \
+        if (cfg != ctx().generation) {                                                                        \
             NDB_CUDA(cudaFuncSetAttribute(tc_knn_kernel<KT, M, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-            cfg = true;                                                                                       \
+            cfg = ctx().generation;                                                                           \
         }                                                                                                     \
         tc_knn_kernel<KT, M, PK><<<grid, 384, smem, s>>>(p);                                                  \
     } while (0)
@@ -850,6 +876,7 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     p.xb = st.xb.as<__nv_bfloat16>();
     p.xnorm = st.xnorm.as<float>();
     if (metric == NDB_COSINE) NDB_CHECK(tc_store_rinv(const_cast<TcStore &>(st), &p.xnorm, s));
+    if (metric == NDB_IP) NDB_CHECK(tc_store_pad0(const_cast<TcStore &>(st), &p.xnorm, s));
     p.qb = sc.qb.as<__nv_bfloat16>();
     p.qnorm = sc.qnorm.as<float>();
     p.nkc = nkc; p.k = k;

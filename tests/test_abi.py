@@ -39,7 +39,7 @@ def test_ctypes_binding_covers_the_header():
     import neurondb_b200._lib as L
     assert sorted(L.SIGNATURES) == declared_functions()
     lib = L.load()
-    assert lib.ndb_b200_abi_version() == 1
+    assert lib.ndb_b200_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_device():
