@@ -69,10 +69,10 @@ extern "C" {
 #define NDB_ARITH_TENSOR   6  /* bf16 tcgen05 tiles, fp32 accumulate; all three metrics, dim <= 2048,
                                  k <= 16, anything else -> NDB_B200_EINVAL (no fallback).
                                  ndb_b200_knn_exact: distances <= 1e-3 relative.
-                                 ndb_b200_ivf_search: the tensor cores only SELECT k + 6 candidates
-                                 per query (coarse quantiser and list scans); the candidates are
-                                 re-ranked with NDB_ARITH_IVF_F32, so every returned distance is
-                                 ivfComputeDistance's, bit for bit, for the id it comes with      */
+                                 ndb_b200_ivf_search: the tensor cores only PROPOSE candidates (coarse
+                                 quantiser and list scans); they are re-evaluated with NDB_ARITH_IVF_F32
+                                 and the answer is certified or recomputed exactly (ndb_b200_ivf_cert_stats),
+                                 so ids and distances equal the NDB_ARITH_IVF_F32 search's, bit for bit   */
 
 /* IVF search modes */
 #define NDB_IVF_FULL     0    /* scan every probed list completely                             */
@@ -202,6 +202,15 @@ int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np
 int ndb_b200_ivf_search_begin(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, int k, int mode,
                               int arith, float *dist, int64_t *ids, int *ticket);
 int ndb_b200_ivf_search_end(ndb_b200_ivf *ix, int ticket);
+/* NDB_ARITH_TENSOR searches are certified (csrc/ivf_cert.cuh): the bf16 tensor-core scan only proposes
+ * candidates; each query's answer is accepted when a rounding-error bound proves that no row outside the
+ * re-evaluated candidates can enter the reference's top k, and recomputed exactly (every row of the probed
+ * lists, ivfComputeDistance's arithmetic) otherwise -- so ids and distance bits equal NDB_ARITH_IVF_F32's.
+ * Statistics of the last such search: out[0] queries the 32-candidate certificate rejected (list scan),
+ * out[1] exact re-evaluations of list candidates, out[2] / out[3] the same for the coarse quantiser,
+ * out[4] queries for which every row of the probed lists had to be evaluated, out[5] rows evaluated by the exact
+ * kernel's segment rescans. */
+int ndb_b200_ivf_cert_stats(ndb_b200_ivf *ix, int64_t *out /* 6 */);
 /* ivfSelectClusters alone: probe lists per query, nq*nprobe ints, -1 = none (:1597-1717) */
 int ndb_b200_ivf_select_clusters(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, int *probes);
 /* multi-GPU: keep only the lists l with l % world == rank (lists partition across ranks,

@@ -108,6 +108,7 @@ SIGNATURES = {
     "ndb_b200_keys_from_sparse": (_i, [_p, _p, _p, _i64, _i, _p]),
     "ndb_b200_ivf_dim": (_i, [_p]),
     "ndb_b200_ivf_prepare": (_i, [_p, _i]),
+    "ndb_b200_ivf_cert_stats": (_i, [_p, _p]),
     "ndb_b200_hnsw_broadcast": (_i, [_p, _i]),
     "ndb_b200_comm_unique_id": (_i, [_p, _sz]),
     "ndb_b200_comm_init": (_i, [_i, _i, _p, _sz]),

@@ -333,6 +333,15 @@ class IvfIndex(_Handle):
         """List layout (+ blocked bf16 copy for ARITH_TENSOR) now instead of inside the first search."""
         check(L.load().ndb_b200_ivf_prepare(self.h, arith))
 
+    def cert_stats(self):
+        """Certified selection of the last ARITH_TENSOR search: dict of exact-fallback queries and exact
+        re-evaluations, for the list scan and for the coarse quantiser."""
+        out = np.zeros(6, np.int64)
+        check(L.load().ndb_b200_ivf_cert_stats(self.h, ptr(out)))
+        return {"list_fallback_queries": int(out[0]), "list_exact_evals": int(out[1]),
+                "coarse_fallback_queries": int(out[2]), "coarse_exact_evals": int(out[3]),
+                "list_full_scan_queries": int(out[4]), "list_rescanned_rows": int(out[5])}
+
     def load_relation(self, blocks):
         blocks = np.ascontiguousarray(blocks, np.uint8)
         check(L.load().ndb_b200_ivf_load_relation(self.h, ptr(blocks), blocks.size // 8192))

@@ -69,6 +69,11 @@ struct ndb_b200_ivf {
     uint32_t tc_max_nseg = 1;            // longest list, in segments of the tensor scan
     uint64_t tc_sum_nseg = 0, tc_nonempty = 0;   // over the non-empty lists
     DevBuf tc_src, tc_row, d_ltile8;     // tensor row -> IL32 slot / arena row; first tile of each list (* 8, in 32-row blocks)
+    // certified selection (ivf_cert.cuh): queries sent to the exact kernels, [0] lists [1] exact evaluations (lists)
+    // [2] coarse [3] exact evaluations (coarse); items of the coarse scan, cached per batch shape
+    DevBuf cert_counters, fb_list, fb_tau, fb_clist, cert_dbg;
+    int citems_nq = -1;
+    uint32_t citems_tpr = 0, citems_nranges = 0;
     std::vector<uint32_t> row_of_slot;   // IL32 slot -> arena row (host copy, kept for the tensor layout)
 };
 
@@ -95,6 +100,10 @@ static uint32_t ivf_seg_blocks()
 // Most tile-steps of a batch belong to long lists probed by a handful of queries; this cuts the
 // serial epilogue work per tile of exactly those from 128 columns per thread to 32.
 __host__ __device__ inline uint32_t ivf_rep(uint32_t c, uint32_t rep_max) { return c <= rep_max ? 4u : 1u; }
+
+}  // namespace ndb
+#include "ivf_cert.cuh"
+namespace ndb {
 
 // ---- work-item construction -----------------------------------------------------------------
 __global__ void ivf_hist_kernel(const uint32_t *__restrict__ probe, int64_t npairs, const uint32_t *__restrict__ list_len,
@@ -263,125 +272,6 @@ __global__ void ivf_tc_items_kernel(const uint32_t *__restrict__ cnt, const uint
         it.out_stride = 2;
         it.rep = rp;
         items[item_off[l] + i] = it;
-    }
-}
-
-// Warp per query: merge the query's bf16 candidates over the probed lists (kc best by approximate
-// distance), then re-evaluate those candidates with the reference's fp32 arithmetic (policy P) and
-// return the k best by (dist, id).  The returned distances are therefore bit-identical to what the
-// fp32 path returns for the same ids; only the candidate SELECTION used bf16 products.
-template <class P>
-__global__ void __launch_bounds__(128) ivf_tc_finish_kernel(const float *__restrict__ pdist, const uint32_t *__restrict__ pslot,
-                                                            const uint32_t *__restrict__ tc_src, const uint32_t *__restrict__ tc_row,
-                                                            const float *__restrict__ arena, const int64_t *__restrict__ ids,
-                                                            const float *__restrict__ Q,
-                                                            const uint32_t *__restrict__ probe, const uint32_t *__restrict__ pairpos,
-                                                            const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len,
-                                                            const float *__restrict__ gthr, const uint32_t *__restrict__ cnt,
-                                                            uint32_t rep_max, int nq, int nprobe, int nlists,
-                                                            uint32_t segb, int dim, int dimp, int kc, int k,
-                                                            float *__restrict__ out_dist, int64_t *__restrict__ out_ids)
-{
-    const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (q >= nq) return;
-    WarpTopK<1, uint32_t> cand;
-    cand.init();
-    // the scan kernel left, per query, an upper bound of its kc-th best key (packed keys only):
-    // partial entries above it cannot be among the kc best
-    const float bound = gthr ? gthr[q] : INFINITY;
-    for (int r0 = 0; r0 < nprobe; r0 += 32) {
-        // lane r: where the partial lists of probe r0 + r start, and how many segments there are
-        uint32_t my_first = 0, my_nseg = 0, my_rep = 1;
-        if (r0 + lane < nprobe) {
-            const size_t p = (size_t) q * nprobe + r0 + lane;
-            const uint32_t l = probe[p];
-            if (l < (uint32_t) nlists) {
-                const uint32_t len = list_len[l];
-                if (len) {
-                    my_rep = ivf_rep(cnt[l], rep_max);
-                    const uint32_t pos = pairpos[p] * my_rep;        // first of the query's (replicated) tile positions
-                    my_nseg = ivf_nseg(len, segb);
-                    my_first = (item_off[l] + (pos / TC_M) * my_nseg) * (2 * TC_M) + (pos % TC_M) * 2;
-                }
-            }
-        }
-        const int nr = min(32, nprobe - r0);
-        // One unit = the partial lists of (probe, segment): the kc entries of the query's replicas and column
-        // halves, contiguous, at most 4 * 2 * 16 = 128 of them.  A unit's four 32-entry groups are loaded
-        // before the first is looked at, so a unit costs one L2 round trip, not four.  (Keeping two probes'
-        // units in flight as well was measured slower: the extra registers cost more occupancy than the
-        // overlap gains.)
-        auto load4 = [&](size_t base, int nent, float (&cdv)[4], uint32_t (&slv)[4]) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int i = u * 32 + lane;
-                cdv[u] = INFINITY;
-                slv[u] = INVALID_SLOT;
-                if (i < nent) { slv[u] = pslot[base + i]; cdv[u] = pdist[base + i]; }
-            }
-        };
-        auto take4 = [&](int nent, const float (&cdv)[4], const uint32_t (&slv)[4]) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (u * 32 >= nent) break;
-                const bool ok = slv[u] != INVALID_SLOT && cdv[u] <= bound;
-                if (__any_sync(FULL, ok)) cand.offer(cdv[u], slv[u], ok, lane, kc);
-            }
-        };
-        for (int r = 0; r < nr; r++) {
-            const uint32_t nseg = __shfl_sync(FULL, my_nseg, r), first = __shfl_sync(FULL, my_first, r);
-            const int nent = (int) __shfl_sync(FULL, my_rep, r) * 2 * kc;
-            for (uint32_t sg = 0; sg < nseg; sg++) {
-                float cdv[4];
-                uint32_t slv[4];
-                load4(((size_t) first + (size_t) sg * (2 * TC_M)) * kc, nent, cdv, slv);
-                take4(nent, cdv, slv);
-            }
-        }
-    }
-    // lane e < kc holds candidate e
-    const uint32_t ts = lane < kc ? cand.key[0] : INVALID_SLOT;
-    float ed = INFINITY;
-    int64_t id = -1;
-    const bool have = ts != INVALID_SLOT && tc_row[ts] != INVALID_SLOT;      // (never a pad row of the tile layout)
-    if (have) {
-        // the candidate's fp32 row from the row-major arena: 4 * dim contiguous bytes (the IL32 list
-        // store would hand out one 16-byte piece per 512 bytes)
-        const float *qv = Q + (size_t) q * dim;
-        const float *xv = arena + (size_t) tc_row[ts] * dim;
-        typename P::Acc acc;
-        typename P::N vn = 0, qn = 0;                                 // cosine: the norms, in the same sequential order
-        P::init(acc);
-        if ((dim & 3) == 0) {
-#pragma unroll 8
-            for (int j = 0; j < dim; j += 4) {                        // (unrolled: several row loads in flight)
-                const float4 x = *reinterpret_cast<const float4 *>(xv + j);
-                P::step(acc, x.x, qv[j]);
-                P::step(acc, x.y, qv[j + 1]);
-                P::step(acc, x.z, qv[j + 2]);
-                P::step(acc, x.w, qv[j + 3]);
-                if (P::NORMS) {
-                    P::nstep(vn, x.x); P::nstep(vn, x.y); P::nstep(vn, x.z); P::nstep(vn, x.w);
-                    P::nstep(qn, qv[j]); P::nstep(qn, qv[j + 1]); P::nstep(qn, qv[j + 2]); P::nstep(qn, qv[j + 3]);
-                }
-            }
-        } else {
-            for (int j = 0; j < dim; j++) {
-                P::step(acc, xv[j], qv[j]);
-                if (P::NORMS) { P::nstep(vn, xv[j]); P::nstep(qn, qv[j]); }
-            }
-        }
-        ed = P::finish(acc, vn, qn);
-        id = ids[tc_src[ts]];
-    }
-    WarpTopK<1, int64_t> top;
-    top.init();
-    top.offer(ed, id, have, lane, k);
-    if (lane < k) {
-        const bool got = top.key[0] != KeyMax<int64_t>::v;
-        out_dist[(size_t) q * k + lane] = got ? top.d[0] : INFINITY;
-        out_ids[(size_t) q * k + lane] = got ? top.key[0] : -1;
     }
 }
 
@@ -621,6 +511,81 @@ static int ivf_tc_margin()
     return v;
 }
 
+// ivfSelectClusters on the tensor cores, certified (ivf_cert.cuh): the centroid store is scanned in
+// `nranges` tile ranges, each (query, range, column half) leaves its kc best keys, and ivf_coarse_cert_kernel
+// re-evaluates the best of their union with the reference's arithmetic.  np <= 32.
+static int ivf_coarse_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np, cudaStream_t s)
+{
+    const TcStore &st = ix->ctc;
+    const int nkc = st.nkc, kc = TC_KMAX, L = ix->nlists;
+    const uint32_t nqt = (uint32_t) ((nq + TC_M - 1) / TC_M);
+    const int nqpad = (int) nqt * TC_M;
+    NDB_CHECK(ix->ctcs.qb.reserve((size_t) nqpad * nkc * TC_KC * 2));
+    NDB_CHECK(ix->ctcs.qnorm.reserve((size_t) nqpad * 4));
+    NDB_CHECK(tc_block_queries(Q_dev, nullptr, 0, nq, nqpad, ix->dim, nkc, ix->ctcs.qb.as<__nv_bfloat16>(), ix->ctcs.qnorm.as<float>(), s));
+    // ranges: enough partial lists that their union holds np + a margin of complete entries (np <= 16: the two
+    // column halves of one range; else four ranges), and about two items per SM when the store is long enough
+    const uint32_t sms = (uint32_t) ctx().sm_count;
+    uint32_t nranges = std::max<uint32_t>(np <= 16 ? 1u : 4u, nqt ? (2 * sms) / nqt : 1u);
+    nranges = std::max<uint32_t>(1u, std::min<uint32_t>(nranges, (uint32_t) st.ntiles));
+    uint32_t tpr = (uint32_t) ((st.ntiles + nranges - 1) / nranges);
+    if (tpr > (uint32_t) TC_PACKED_MAX_TILES) tpr = TC_PACKED_MAX_TILES;
+    nranges = (uint32_t) ((st.ntiles + tpr - 1) / tpr);
+    const uint32_t nitems = nqt * nranges;
+    if (ix->citems_nq != nq || ix->citems_tpr != tpr || ix->citems_nranges != nranges) {
+        std::vector<TcItem> items(nitems);
+        for (uint32_t i = 0; i < nitems; i++) {
+            const uint32_t qt = i % nqt, xr = i / nqt;
+            TcItem &it = items[i];
+            it.qtile = qt;
+            it.t0 = xr * tpr;
+            it.t1 = std::min<uint32_t>((uint32_t) st.ntiles, it.t0 + tpr);
+            it.nq = (uint32_t) std::min<int>(TC_M, nq - (int) qt * TC_M);
+            it.out_base = qt * TC_M * nranges * 2 + xr * 2;
+            it.out_stride = nranges * 2;
+            it.rep = 1;
+            it.pad_ = 0;
+        }
+        NDB_CHECK(ix->ctcs.items.reserve((size_t) nitems * sizeof(TcItem)));
+        NDB_CUDA(cudaMemcpyAsync(ix->ctcs.items.p, items.data(), (size_t) nitems * sizeof(TcItem), cudaMemcpyHostToDevice, s));
+        NDB_CUDA(cudaStreamSynchronize(s));        // `items` is a host temporary; once per batch shape
+        ix->citems_nq = nq; ix->citems_tpr = tpr; ix->citems_nranges = nranges;
+    }
+    const int nparts = (int) nranges * 2;
+    NDB_CHECK(ix->ctcs.pdist.reserve((size_t) nqpad * nparts * kc * 4));
+    NDB_CHECK(ix->ctcs.pslot.reserve((size_t) nqpad * nparts * kc * 4));
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.xb = st.xb.as<__nv_bfloat16>();
+    p.xnorm = st.xnorm.as<float>();
+    p.qb = ix->ctcs.qb.as<__nv_bfloat16>();
+    p.qnorm = ix->ctcs.qnorm.as<float>();
+    p.nkc = nkc;
+    p.k = kc;
+    p.items = ix->ctcs.items.as<TcItem>();
+    p.nitems = nitems;
+    p.pdist = ix->ctcs.pdist.as<float>();
+    p.pslot = ix->ctcs.pslot.as<uint32_t>();
+    p.packed = 1;
+    NDB_CHECK(tc_launch(p, NDB_L2, kc, s));
+    unsigned long long *ctr = ix->cert_counters.as<unsigned long long>() + 2;
+    const unsigned grid = (unsigned) ((nq + 3) / 4);
+    if (np <= 16)
+        ivf_coarse_cert_kernel<1><<<grid, 128, 0, s>>>(p.pdist, p.pslot, nparts, kc, ix->kw.C.as<float>(), Q_dev, nq, L, ix->dim, np,
+                                                       st.stats.as<float>(), ix->probe.as<uint32_t>(), ix->cdist.as<float>(),
+                                                       ix->fb_clist.as<uint32_t>(), ctr);
+    else
+        ivf_coarse_cert_kernel<2><<<grid, 128, 0, s>>>(p.pdist, p.pslot, nparts, kc, ix->kw.C.as<float>(), Q_dev, nq, L, ix->dim, np,
+                                                       st.stats.as<float>(), ix->probe.as<uint32_t>(), ix->cdist.as<float>(),
+                                                       ix->fb_clist.as<uint32_t>(), ctr);
+    const size_t fsm = (size_t) ix->dimp * 4 + 256 * 4 + 256 * 8;
+    ivf_coarse_fallback_kernel<<<(unsigned) std::min<int>(nq, 2 * (int) sms), 256, fsm, s>>>(ix->fb_clist.as<uint32_t>(), ctr, ix->kw.C.as<float>(), Q_dev, L,
+                                                                                      ix->dim, np, ix->probe.as<uint32_t>(), ix->cdist.as<float>());
+    count_launch(2);
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
+}
+
 // NDB_ARITH_TENSOR search: coarse quantizer and list scans on the tensor cores (bf16 products, fp32
 // accumulation) select k + margin candidates per query, which are then re-ranked in fp32.
 static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np, int k, float *dist_dev, int64_t *ids_dev,
@@ -636,11 +601,15 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     // 1. coarse quantizer: k = nprobe nearest centroids (always L2, ivfSelectClusters)
     NDB_CHECK(ix->probe.reserve((size_t) npairs * 4));
     NDB_CHECK(ix->cdist.reserve((size_t) npairs * 4));
-    if (np <= TC_KMAX) {
-        NDB_CHECK(tc_knn(ix->ctc, ix->ctcs, ix->dim, NDB_L2, Q_dev, nq, np, nullptr, ix->cdist.as<float>(), nullptr,
-                         ix->probe.as<uint32_t>(), nullptr, true, s));
+    NDB_CHECK(ix->cert_counters.reserve(64));
+    NDB_CHECK(ix->fb_list.reserve((size_t) nq * 4));
+    NDB_CHECK(ix->fb_tau.reserve((size_t) nq * 4));
+    NDB_CHECK(ix->fb_clist.reserve((size_t) nq * 4));
+    NDB_CUDA(cudaMemsetAsync(ix->cert_counters.p, 0, 64, s));
+    if (np <= 32 && ix->dim <= 4096) {
+        NDB_CHECK(ivf_coarse_tensor(ix, Q_dev, nq, np, s));
     } else {
-        NDB_CHECK(ivf_coarse(ix, Q_dev, nq, np, NDB_ARITH_FAST, s));
+        NDB_CHECK(ivf_coarse(ix, Q_dev, nq, np, NDB_ARITH_IVF_F32, s));
     }
 
     // 2. bucket (query, list) pairs by list; query positions padded to whole 128-query tiles per list
@@ -713,8 +682,10 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     const int nkc = ix->tc.nkc;
     NDB_CHECK(ix->tcs.qb.reserve(npos * nkc * TC_KC * 2));
     NDB_CHECK(ix->tcs.qnorm.reserve(npos * 4));
+    NDB_CHECK(ix->tcs.qerr.reserve(npos * 4));
     NDB_CHECK(tc_block_queries(Q_dev, ix->qmap.as<uint32_t>(), (uint32_t) np, nq, (int) npos, ix->dim, nkc,
-                               ix->tcs.qb.as<__nv_bfloat16>(), ix->tcs.qnorm.as<float>(), s, ix->nitems.as<uint32_t>() + 1));
+                               ix->tcs.qb.as<__nv_bfloat16>(), ix->tcs.qnorm.as<float>(), s, ix->nitems.as<uint32_t>() + 1,
+                               ix->tcs.qerr.as<float>()));
     const size_t nparts = n_items * 2 * TC_M;
     NDB_CHECK(ix->tcs.pdist.reserve(nparts * kc * 4));
     NDB_CHECK(ix->tcs.pslot.reserve(nparts * kc * 4));
@@ -726,6 +697,9 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     if (ix->metric == NDB_IP) NDB_CHECK(tc_store_pad0(ix->tc, &p.xnorm, s));
     p.qb = ix->tcs.qb.as<__nv_bfloat16>();
     p.qnorm = ix->tcs.qnorm.as<float>();
+    p.qerr = ix->tcs.qerr.as<float>();
+    p.cstats = ix->tc.stats.as<float>();
+    p.dim = ix->dim;
     p.nkc = nkc;
     p.k = kc;
     p.items = ix->tcs.items.as<TcItem>();
@@ -750,18 +724,39 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
         c.stats_dim = ix->dim;
     }
 
-    // 4. merge + fp32 re-rank
+    // 4. merge + certified fp32 re-rank; the queries the certificate rejects are recomputed exactly
     const unsigned mgrid = (unsigned) ((nq + 3) / 4);
+    unsigned long long *ctr = ix->cert_counters.as<unsigned long long>();
+    const size_t fsm = (size_t) ix->dimp * 4 + FB_THREADS * 4 + FB_THREADS * 8;
+    const unsigned fgrid = (unsigned) std::min<int>(nq, 2 * ctx().sm_count);
+    NDB_REQUIRE(p.packed && p.gthr, NDB_B200_EINVAL, "ivf tensor path: the certified finish needs packed keys and the shared bound");
+    float *cert_dbg = nullptr;           // NDB_CERT_DEBUG: (query, G, tau, bound(G), |S|, ||eq||, ||q||, max||ex||) of the first 16 full scans
+    if (getenv("NDB_CERT_DEBUG")) {
+        NDB_CHECK(ix->cert_dbg.reserve(16 * 8 * 4));
+        NDB_CUDA(cudaMemsetAsync(ix->cert_dbg.p, 0, 16 * 8 * 4, s));
+        cert_dbg = ix->cert_dbg.as<float>();
+    }
 #define NDB_FIN(M)                                                                                                   \
-    ivf_tc_finish_kernel<Arith<M, NDB_ARITH_IVF_F32>><<<mgrid, 128, 0, s>>>(                                   \
-        ix->tcs.pdist.as<float>(), ix->tcs.pslot.as<uint32_t>(), ix->tc_src.as<uint32_t>(), ix->tc_row.as<uint32_t>(),  \
-        ix->arena.as<float>(), ix->ids.as<int64_t>(), Q_dev, ix->probe.as<uint32_t>(),                                  \
-        ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), p.packed ? p.gthr : nullptr, cnt, rep_max, \
-        nq, np, L, segb, ix->dim, ix->dimp, kc, k, dist_dev, ids_dev)
+    do {                                                                                                             \
+        ivf_tc_finish_cert_kernel<Arith<M, NDB_ARITH_IVF_F32>, M><<<mgrid, 128, 0, s>>>(                              \
+            ix->tcs.pdist.as<float>(), ix->tcs.pslot.as<uint32_t>(), ix->tc_src.as<uint32_t>(), ix->tc_row.as<uint32_t>(), \
+            ix->arena.as<float>(), ix->ids.as<int64_t>(), Q_dev, ix->probe.as<uint32_t>(),                            \
+            ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), p.gthr, cnt, rep_max, \
+            nq, np, L, segb, ix->dim, kc, k, ix->tc.stats.as<float>(), dist_dev, ids_dev, ix->fb_list.as<uint32_t>(),  \
+            ix->fb_tau.as<float>(), ctr);                                                                             \
+        ivf_exact_fallback_kernel<Arith<M, NDB_ARITH_IVF_F32>, M><<<fgrid, FB_THREADS, fsm, s>>>(                            \
+            ix->fb_list.as<uint32_t>(), ix->fb_tau.as<float>(), ctr, ix->tcs.pdist.as<float>(), ix->tcs.pslot.as<uint32_t>(), ix->probe.as<uint32_t>(), \
+            ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(),                   \
+            ix->d_ltile8.as<uint32_t>(), p.gthr, cnt, rep_max, segb, kc, ix->tc_src.as<uint32_t>(),                    \
+            ix->tc_row.as<uint32_t>(), ix->arena.as<float>(), ix->ids.as<int64_t>(), Q_dev, ix->tc.stats.as<float>(), \
+            reinterpret_cast<const float4 *>(ix->store.ptr()), ix->d_list_blk.as<uint32_t>(), ix->dimp,                \
+            np, L, ix->dim, k, dist_dev, ids_dev, cert_dbg);                                                          \
+    } while (0)
     if (ix->metric == NDB_L2) NDB_FIN(NDB_L2);
     else if (ix->metric == NDB_COSINE) NDB_FIN(NDB_COSINE);
     else NDB_FIN(NDB_IP);
 #undef NDB_FIN
+    count_launch();
     count_launch();
     NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
@@ -988,6 +983,29 @@ int ndb_b200_ivf_prepare(ndb_b200_ivf *ix, int arith)
     NDB_CHECK(ivf_ready(ix, s));
     if (arith == NDB_ARITH_TENSOR && ix->dim <= TC_MAX_DIM) NDB_CHECK(ivf_tensor_ready(ix, s));
     NDB_CUDA(cudaStreamSynchronize(s));
+    return NDB_B200_OK;
+}
+
+// certified selection of the last NDB_ARITH_TENSOR search: out[0] = queries whose list scan went to the exact
+// kernel, out[1] = exact re-evaluations of list candidates, out[2] / out[3] = the same for the coarse quantiser,
+// out[4] = queries whose every probed row had to be evaluated, out[5] = rows evaluated by segment rescans
+int ndb_b200_ivf_cert_stats(ndb_b200_ivf *ix, int64_t *out)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix && out, NDB_B200_EINVAL, "ivf_cert_stats: NULL argument");
+    for (int i = 0; i < 6; i++) out[i] = 0;
+    if (!ix->cert_counters.p) return NDB_B200_OK;
+    unsigned long long h[6];
+    NDB_CUDA(cudaStreamSynchronize(ctx().stream));
+    NDB_CUDA(cudaMemcpy(h, ix->cert_counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 6; i++) out[i] = (int64_t) h[i];
+    if (getenv("NDB_CERT_DEBUG") && ix->cert_dbg.p) {
+        float r[16 * 8];
+        NDB_CUDA(cudaMemcpy(r, ix->cert_dbg.p, sizeof(r), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 16 && i < (int) h[4]; i++)
+            fprintf(stderr, "cert full scan: q=%d R=%g tau=%g bound(R)=%g rescanned=%d ||eq||=%g ||q||=%g tau0=%g\n", (int) r[i * 8], r[i * 8 + 1],
+                    r[i * 8 + 2], r[i * 8 + 3], (int) r[i * 8 + 4], r[i * 8 + 5], r[i * 8 + 6], r[i * 8 + 7]);
+    }
     return NDB_B200_OK;
 }
 

@@ -1,0 +1,547 @@
+// ivf_cert.cuh -- certified selection for the tensor-core IVF search (NDB_ARITH_TENSOR).
+//
+// The tensor cores rank candidates by bf16 products; the reference ranks them by ivfComputeDistance
+// (NeuronDB/src/index/ivf_am.c:1550-1592) in sequential fp32.  north_star's contract: ids identical to the
+// reference wherever the distance gap exceeds the tolerance.  These kernels give more: the ids and distance
+// bits of the fp32 path, always, because every answer is either CERTIFIED or recomputed exactly.
+//
+// What the scan leaves behind (tc_knn.cu).  Per query, partial lists of at most kc (key, row) entries, one per
+// (probed list, segment, column half, replica), and the final value G of the shared per-query bound: the
+// smallest kc-th key any full partial list ended with.  A candidate was dropped only (i) by the threshold
+// test, at a moment when the threshold was >= G, or (ii) out of the tail of a full list, whose kc-th key is
+// >= G.  Hence the entries with key <= G are the COMPLETE set of rows whose key is below G (up to the 12-bit
+// packing of the keys, which the bound below absorbs).
+//
+// Certificate.  Take the best 32 entries by key; re-evaluate them with the reference's arithmetic;
+// tau = the k-th smallest exact value so far.  Every row not re-evaluated has a key >= g, with
+// g = the key of the first entry not re-evaluated (or G when there is none).  With x~ = bf16(x), q~ = bf16(q),
+// ex = x~ - x, eq = q~ - q (the only approximation in the key; bf16 x bf16 products are exact in fp32):
+//     L2      key = ||x~ - q~||^2          ||x - q||       >= sqrt(key) - ||ex|| - ||eq||
+//     IP      key = -x~.q~                 -x.q            >= key - ||ex|| ||q~|| - ||x|| ||eq||
+//     cosine  key = -x~.q~ / ||x~||        -x.q / ||x||    >= key - rho (||q~|| + ||q||) - kappa ||eq||,
+//                                          rho = max ||ex|| / ||x~||, kappa = max ||x|| / ||x~||
+// with the maxima of ||ex||, ||x||, rho, kappa over the stored rows taken at build time (TcStore::stats),
+// ||eq||, ||q||, ||q~|| computed here, plus slack for fp32 accumulation ((dim + 8) 2^-23 of the magnitudes) and
+// for the key packing (2^-10 relative).  If that lower bound exceeds tau the answer is certified: no row
+// outside the re-evaluated set can enter the reference's top k.  Otherwise the query goes to the exact
+// kernel below, which evaluates every row of its probed lists in the reference's arithmetic.
+#pragma once
+#include "arith.cuh"
+#include "tc.cuh"
+#include "cert_bound.cuh"
+
+namespace ndb {
+
+__device__ __forceinline__ CertQ cert_query(const float *__restrict__ qv, int dim, int lane)
+{
+    float e2 = 0.0f, q2 = 0.0f, r2 = 0.0f;
+    for (int j = lane; j < dim; j += 32) {
+        const float v = qv[j], r = __bfloat162float(__float2bfloat16_rn(v));
+        e2 = fmaf(v - r, v - r, e2);
+        q2 = fmaf(v, v, q2);
+        r2 = fmaf(r, r, r2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        e2 += __shfl_xor_sync(FULL, e2, o);
+        q2 += __shfl_xor_sync(FULL, q2, o);
+        r2 += __shfl_xor_sync(FULL, r2, o);
+    }
+    CertQ c;
+    c.eq = sqrtf(e2) * 1.0002f;
+    c.qn = sqrtf(q2) * 1.0002f;
+    c.qnr = sqrtf(r2) * 1.0002f;
+    c.qn_lo = sqrtf(q2) * 0.9998f;
+    return c;
+}
+
+// the reference's distance between query qv and the row-major row xv (policy P = Arith<metric, IVF_F32>)
+template <class P>
+__device__ __forceinline__ float cert_exact(const float *__restrict__ qv, const float *__restrict__ xv, int dim)
+{
+    typename P::Acc acc;
+    typename P::N vn = 0, qn = 0;
+    P::init(acc);
+    if ((dim & 3) == 0) {
+#pragma unroll 8
+        for (int j = 0; j < dim; j += 4) {
+            const float4 x = *reinterpret_cast<const float4 *>(xv + j);
+            const float4 qq = *reinterpret_cast<const float4 *>(qv + j);       // (rows and queries are 16-byte aligned: dim % 4 == 0)
+            P::step(acc, x.x, qq.x);
+            P::step(acc, x.y, qq.y);
+            P::step(acc, x.z, qq.z);
+            P::step(acc, x.w, qq.w);
+            if (P::NORMS) {
+                P::nstep(vn, x.x); P::nstep(vn, x.y); P::nstep(vn, x.z); P::nstep(vn, x.w);
+                P::nstep(qn, qq.x); P::nstep(qn, qq.y); P::nstep(qn, qq.z); P::nstep(qn, qq.w);
+            }
+        }
+    } else {
+        for (int j = 0; j < dim; j++) {
+            P::step(acc, xv[j], qv[j]);
+            if (P::NORMS) { P::nstep(vn, xv[j]); P::nstep(qn, qv[j]); }
+        }
+    }
+    return P::finish(acc, vn, qn);
+}
+
+// the same for IL32 slot `slot` of a list store (lane-per-slot: a warp's loads are 512 contiguous bytes)
+template <class P>
+__device__ __forceinline__ float cert_exact_il32(const float *__restrict__ qv, const float4 *__restrict__ vecs, uint32_t slot, int dim,
+                                                 int dimp)
+{
+    const float4 *vp = vecs + (size_t) (slot >> 5) * (8 * (size_t) dimp) + (slot & 31);
+    typename P::Acc acc;
+    typename P::N vn = 0, qn = 0;
+    P::init(acc);
+#pragma unroll 8
+    for (int j = 0; j < dim; j += 4) {
+        const float4 x = vp[(size_t) (j >> 2) * 32];
+        P::step(acc, x.x, qv[j]);
+        if (P::NORMS) { P::nstep(vn, x.x); P::nstep(qn, qv[j]); }
+        if (j + 1 < dim) { P::step(acc, x.y, qv[j + 1]); if (P::NORMS) { P::nstep(vn, x.y); P::nstep(qn, qv[j + 1]); } }
+        if (j + 2 < dim) { P::step(acc, x.z, qv[j + 2]); if (P::NORMS) { P::nstep(vn, x.z); P::nstep(qn, qv[j + 2]); } }
+        if (j + 3 < dim) { P::step(acc, x.w, qv[j + 3]); if (P::NORMS) { P::nstep(vn, x.w); P::nstep(qn, qv[j + 3]); } }
+    }
+    return P::finish(acc, vn, qn);
+}
+
+// Re-evaluate the (up to 32 * KRC) candidates `cand` holds in ascending key order (entry e = register e / 32,
+// lane e % 32; key = row-major row index, INVALID_SLOT = none), 16 at a time, best first, and certify.  (Measured on C2:
+// 16 at a time re-evaluates 25 rows per query on average and is faster than 32 at a time, which always fetches 32.)
+// `g_rest` = the smallest key any row outside `cand` can have; `complete` = there is no such row.
+// Returns the exact top-k in `top` and whether it is certified.
+template <class P, int METRIC, int KRC, class RowOf, class KeyOf>
+__device__ __forceinline__ bool cert_rerank(const float *__restrict__ qv, const float *__restrict__ rows, int dim,
+                                            const WarpTopK<KRC, uint32_t> &cand, float g_rest, bool complete,
+                                            const float *__restrict__ st, const CertQ &cq, int k, int lane, RowOf row_of, KeyOf key_of,
+                                            WarpTopK<1, int64_t> &top, unsigned long long *__restrict__ n_exact)
+{
+    top.init();
+    bool certified = false, done = false;
+#pragma unroll
+    for (int c = 0; c < 2 * KRC; c++) {
+        if (done) break;
+        const int r = c >> 1, half = c & 1;
+        const uint32_t ck = cand.key[r];
+        const bool mine = ck != INVALID_SLOT && (lane >> 4) == half;
+        float ed = INFINITY;
+        int64_t id = -1;
+        if (mine) { ed = cert_exact<P>(qv, rows + (size_t) row_of(ck) * dim, dim); id = key_of(ck); }
+        const unsigned m = __ballot_sync(FULL, mine);
+        top.offer(ed, id, mine, lane, k);
+        if (n_exact && lane == 0 && m) atomicAdd(n_exact, (unsigned long long) __popc(m));
+        // smallest key among the rows not yet re-evaluated: entry 16 (c + 1) of cand, else g_rest
+        float g = g_rest;
+        bool more = false;
+        if (c + 1 < 2 * KRC) {
+            const int r2 = (c + 1) >> 1, l2 = ((c + 1) & 1) * 16;
+            const float kn = __shfl_sync(FULL, cand.d[r2], l2);
+            const uint32_t sn = __shfl_sync(FULL, cand.key[r2], l2);
+            more = sn != INVALID_SLOT;
+            if (more) g = fminf(kn, g_rest);
+        }
+        certified = (complete && !more) || cert_lower_bound<METRIC>(g, st, cq, dim) > top.td;
+        done = certified || !more;
+    }
+    return certified;
+}
+
+// ---- lists: merge + certified re-rank (replaces the fixed k + 6 margin) ------------------------------
+// gthr[q] = R, the RELAXED shared bound (cert_bound.cuh): every candidate the threshold test dropped had a key
+// >= R; a full partial list also dropped candidates above its own kc-th key.  Hence every row that is in no
+// partial list has a key >= min(R, smallest kc-th key of a full list) =: g_lists.
+template <class P, int METRIC>
+__global__ void __launch_bounds__(128) ivf_tc_finish_cert_kernel(
+    const float *__restrict__ pdist, const uint32_t *__restrict__ pslot, const uint32_t *__restrict__ tc_src,
+    const uint32_t *__restrict__ tc_row, const float *__restrict__ arena, const int64_t *__restrict__ ids,
+    const float *__restrict__ Q, const uint32_t *__restrict__ probe, const uint32_t *__restrict__ pairpos,
+    const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len, const float *__restrict__ gthr,
+    const uint32_t *__restrict__ cnt, uint32_t rep_max, int nq, int nprobe, int nlists, uint32_t segb, int dim, int kc, int k,
+    const float *__restrict__ stats, float *__restrict__ out_dist, int64_t *__restrict__ out_ids,
+    uint32_t *__restrict__ fb_list, float *__restrict__ fb_tau,
+    unsigned long long *__restrict__ counters /* [0] queries sent to the exact kernel, [1] exact evaluations */)
+{
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    WarpTopK<1, uint32_t> cand;
+    cand.init();
+    const float R = gthr[q];
+    const bool bounded = R < 1.0e38f;                  // "no bound": no partial list of this query ever filled
+    float own_min = INFINITY;                           // smallest kc-th key of a full partial list
+    uint32_t n_in = 0;                                  // entries met (warp-uniform)
+    for (int r0 = 0; r0 < nprobe; r0 += 32) {
+        uint32_t my_first = 0, my_nseg = 0, my_rep = 1;
+        if (r0 + lane < nprobe) {
+            const size_t p = (size_t) q * nprobe + r0 + lane;
+            const uint32_t l = probe[p];
+            if (l < (uint32_t) nlists) {
+                const uint32_t len = list_len[l];
+                if (len) {
+                    my_rep = ivf_rep(cnt[l], rep_max);
+                    const uint32_t pos = pairpos[p] * my_rep;
+                    my_nseg = ivf_nseg(len, segb);
+                    my_first = (item_off[l] + (pos / TC_M) * my_nseg) * (2 * TC_M) + (pos % TC_M) * 2;
+                }
+            }
+        }
+        const int nr = min(32, nprobe - r0);
+        for (int r = 0; r < nr; r++) {
+            const uint32_t nseg = __shfl_sync(FULL, my_nseg, r), first = __shfl_sync(FULL, my_first, r);
+            const int nent = (int) __shfl_sync(FULL, my_rep, r) * 2 * kc;
+            for (uint32_t sg = 0; sg < nseg; sg++) {
+                const size_t base = ((size_t) first + (size_t) sg * (2 * TC_M)) * kc;
+                float cdv[4];
+                uint32_t slv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = u * 32 + lane;
+                    cdv[u] = INFINITY;
+                    slv[u] = INVALID_SLOT;
+                    if (i < nent) { slv[u] = pslot[base + i]; cdv[u] = pdist[base + i]; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (u * 32 >= nent) break;
+                    const bool ok = slv[u] != INVALID_SLOT;
+                    if (ok && (u * 32 + lane) % kc == kc - 1) own_min = fminf(own_min, cdv[u]);      // last entry of a full list
+                    const unsigned m = __ballot_sync(FULL, ok);
+                    if (m) { n_in += __popc(m); cand.offer(cdv[u], slv[u], ok, lane, 32); }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) own_min = fminf(own_min, __shfl_xor_sync(FULL, own_min, o));
+    const float *qv = Q + (size_t) q * dim;
+    const CertQ cq = cert_query(qv, dim, lane);
+    // lane e holds candidate e (ascending key).  Rows outside the 32: in a partial list -> key >= the 32nd key;
+    // in none -> key >= min(R, own_min).  With no full list, no bound and no overflow the 32 are everything.
+    const float key32 = __shfl_sync(FULL, cand.d[0], 31);
+    const float g_rest = fminf(n_in > 32 ? key32 : INFINITY, fminf(R, own_min));
+    const bool complete = !bounded && own_min == INFINITY && n_in <= 32;
+    WarpTopK<1, int64_t> top;
+    const bool ok = cert_rerank<P, METRIC, 1>(qv, arena, dim, cand, g_rest, complete, stats, cq, k, lane,
+                                              [&](uint32_t ts) { return tc_row[ts]; }, [&](uint32_t ts) { return ids[tc_src[ts]]; }, top,
+                                              counters ? counters + 1 : nullptr);
+    if (!ok) {
+        if (lane == 0) {
+            const unsigned long long f = atomicAdd(counters, 1ull);
+            fb_list[f] = (uint32_t) q;
+            fb_tau[f] = top.td;           // an upper bound of the final k-th exact value (+inf: fewer than k so far)
+        }
+        return;                           // the exact kernel writes this query's result
+    }
+    if (lane < k) {
+        const bool got = top.key[0] != KeyMax<int64_t>::v;
+        out_dist[(size_t) q * k + lane] = got ? top.d[0] : INFINITY;
+        out_ids[(size_t) q * k + lane] = got ? top.key[0] : -1;
+    }
+}
+
+// ---- lists: the queries the 32-candidate certificate rejected ---------------------------------------------
+// One CTA (32 warps) per such query.  tau0 = the k-th exact value the finish kernel reached, an upper bound of the
+// final one.  Per (probed list, segment) unit:
+//   - if a full partial list of the unit ends with a key m that cannot be certified against tau0
+//     (cert_lower_bound(m) <= tau0), that list may have dropped a row of the answer: every row of the unit (at most
+//     16 tiles = 4096 rows) is evaluated in the reference's arithmetic;
+//   - otherwise the unit's entries are evaluated: whatever it dropped is certified out (full lists by their own
+//     kc-th key, the others by R, for which cert_lower_bound(R) > tau0 holds by construction of the relaxation).
+// Level 3, if cert_lower_bound(R) > tau fails after all (a zero query under cosine, fewer than k rows ...): every
+// row of the probed lists -- ivfCollectCandidates without the cut-off.  Rows are reached through the tensor
+// layout's row map (list l = tensor rows [ltile8[l] * 32, + len)).
+constexpr int FB_THREADS = 1024, FB_WARPS = FB_THREADS / 32;
+
+template <class P, int METRIC>
+__global__ void __launch_bounds__(FB_THREADS) ivf_exact_fallback_kernel(
+    const uint32_t *__restrict__ fb_list, const float *__restrict__ fb_tau, unsigned long long *__restrict__ counters,
+    const float *__restrict__ pdist, const uint32_t *__restrict__ pslot, const uint32_t *__restrict__ probe,
+    const uint32_t *__restrict__ pairpos, const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len,
+    const uint32_t *__restrict__ ltile8, const float *__restrict__ gthr, const uint32_t *__restrict__ cnt, uint32_t rep_max,
+    uint32_t segb, int kc, const uint32_t *__restrict__ tc_src, const uint32_t *__restrict__ tc_row,
+    const float *__restrict__ arena, const int64_t *__restrict__ ids, const float *__restrict__ Q,
+    const float *__restrict__ stats, const float4 *__restrict__ vecs, const uint32_t *__restrict__ list_blk, int dimp,
+    int nprobe, int nlists, int dim, int k, float *__restrict__ out_dist, int64_t *__restrict__ out_ids, float *__restrict__ dbg)
+{
+    extern __shared__ float fb_smem[];                   // [dim] query, then FB_THREADS (dist, id) pairs
+    float *qs = fb_smem;
+    float *md = fb_smem + ((dim + 3) & ~3);
+    int64_t *mi = reinterpret_cast<int64_t *>(md + FB_THREADS);
+    constexpr int MAXU = 64;
+    __shared__ unsigned s_rows, s_nu;
+    __shared__ float s_tau;
+    __shared__ uint32_t s_first[128], s_nseg[128], s_nent[128], s_l[128], s_len[128], s_ubase[129];     // nprobe <= 128
+    __shared__ uint32_t s_slot0[MAXU], s_nrow[MAXU];      // units to rescan: first IL32 slot, rows
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned nfb = (unsigned) counters[0];
+    for (unsigned f = blockIdx.x; f < nfb; f += gridDim.x) {
+        const uint32_t q = fb_list[f];
+        const float tau0 = fb_tau[f];
+        __syncthreads();
+        if (threadIdx.x == 0) { s_rows = 0; s_nu = 0; }
+        for (int j = threadIdx.x; j < dim; j += blockDim.x) qs[j] = Q[(size_t) q * dim + j];
+        __syncthreads();
+        const CertQ cq = cert_query(qs, dim, lane);
+        const float R = gthr[q];
+        WarpTopK<1, int64_t> top;
+        auto merge_and_write = [&](bool write) -> float {      // returns the k-th exact value over the whole CTA
+            md[w * 32 + lane] = top.d[0];
+            mi[w * 32 + lane] = top.key[0];
+            __syncthreads();
+            if (w == 0) {
+                WarpTopK<1, int64_t> fin;
+                fin.init();
+                for (int ww = 0; ww < FB_WARPS; ww++) {
+                    const float d = md[ww * 32 + lane];
+                    const int64_t id = mi[ww * 32 + lane];
+                    fin.offer(d, id, id != KeyMax<int64_t>::v, lane, k);
+                }
+                if (write && lane < k) {
+                    const bool got = fin.key[0] != KeyMax<int64_t>::v;
+                    out_dist[(size_t) q * k + lane] = got ? fin.d[0] : INFINITY;
+                    out_ids[(size_t) q * k + lane] = got ? fin.key[0] : -1;
+                }
+                if (lane == 0) s_tau = fin.td;
+            }
+            __syncthreads();
+            return s_tau;
+        };
+        top.init();
+        // the (probed list, segment) units of the query, dealt round-robin to the warps
+        if (threadIdx.x < 128) {
+            uint32_t first = 0, nseg = 0, nent = 0, l = 0, len = 0;
+            if ((int) threadIdx.x < nprobe) {
+                const size_t p = (size_t) q * nprobe + threadIdx.x;
+                l = probe[p];
+                if (l < (uint32_t) nlists) {
+                    len = list_len[l];
+                    if (len) {
+                        const uint32_t rep = ivf_rep(cnt[l], rep_max), pos = pairpos[p] * rep;
+                        nseg = ivf_nseg(len, segb);
+                        first = (item_off[l] + (pos / TC_M) * nseg) * (2 * TC_M) + (pos % TC_M) * 2;
+                        nent = rep * 2 * kc;
+                    }
+                }
+            }
+            s_first[threadIdx.x] = first; s_nseg[threadIdx.x] = nseg; s_nent[threadIdx.x] = nent; s_l[threadIdx.x] = l; s_len[threadIdx.x] = len;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int r = 0; r < nprobe; r++) { s_ubase[r] = acc; acc += s_nseg[r]; }
+            s_ubase[nprobe] = acc;
+        }
+        __syncthreads();
+        const uint32_t nunits = s_ubase[nprobe];
+        int r = 0;
+        for (uint32_t un = w; un < nunits; un += FB_WARPS) {
+            while (s_ubase[r + 1] <= un) r++;
+            {
+                const uint32_t sg = un - s_ubase[r], first = s_first[r], l = s_l[r], len = s_len[r];
+                const int nent = (int) s_nent[r];
+                const size_t base = ((size_t) first + (size_t) sg * (2 * TC_M)) * kc;
+                // smallest kc-th key of a full partial list of this unit
+                float m = INFINITY;
+                for (int i = lane; i < nent; i += 32)
+                    if (i % kc == kc - 1 && pslot[base + i] != INVALID_SLOT) m = fminf(m, pdist[base + i]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, o));
+                const bool rescan = m < INFINITY && !(cert_lower_bound<METRIC>(m, stats, cq, dim) > tau0);
+                bool queued = false;
+                if (rescan) {
+                    // all 8 warps rescan the unit together afterwards; its rows are IL32 slots list_blk[l] * 32 + ...
+                    unsigned u = 0;
+                    if (lane == 0) u = atomicAdd(&s_nu, 1u);
+                    u = __shfl_sync(FULL, u, 0);
+                    if (u < (unsigned) MAXU) {
+                        if (lane == 0) {
+                            s_slot0[u] = list_blk[l] * 32 + sg * segb * 32;
+                            s_nrow[u] = min(segb * 32, len - sg * segb * 32);
+                        }
+                        queued = true;
+                    }
+                }
+                if (rescan && !queued) {                  // (more than MAXU units: this warp does it alone)
+                    const uint32_t slot0 = list_blk[l] * 32 + sg * segb * 32, nrow = min(segb * 32, len - sg * segb * 32);
+                    if (lane == 0) atomicAdd(&s_rows, nrow);
+                    for (uint32_t j0 = 0; j0 < nrow; j0 += 32) {
+                        const uint32_t j = j0 + lane;
+                        const bool valid = j < nrow;
+                        float ed = INFINITY;
+                        int64_t id = -1;
+                        if (valid) { ed = cert_exact_il32<P>(qs, vecs, slot0 + j, dim, dimp); id = ids[slot0 + j]; }
+                        top.offer(ed, id, valid, lane, k);
+                    }
+                } else if (rescan) {
+                    // queued
+                } else {
+                    for (int i0 = 0; i0 < nent; i0 += 32) {
+                        const int i = i0 + lane;
+                        const uint32_t ts = i < nent ? pslot[base + i] : INVALID_SLOT;
+                        // an entry whose own key is certified out against tau0 cannot be in the answer
+                        const bool ok = ts != INVALID_SLOT && !(cert_lower_bound<METRIC>(pdist[base + i], stats, cq, dim) > tau0);
+                        if (!__any_sync(FULL, ok)) continue;
+                        float ed = INFINITY;
+                        int64_t id = -1;
+                        if (ok) { ed = cert_exact<P>(qs, arena + (size_t) tc_row[ts] * dim, dim); id = ids[tc_src[ts]]; }
+                        top.offer(ed, id, ok, lane, k);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const unsigned nu = min(s_nu, (unsigned) MAXU);
+            for (unsigned u = 0; u < nu; u++) {
+                const uint32_t slot0 = s_slot0[u], nrow = s_nrow[u];
+                if (threadIdx.x == 0) s_rows += nrow;
+                for (uint32_t j0 = w * 32; j0 < nrow; j0 += FB_THREADS) {
+                    const uint32_t j = j0 + lane;
+                    const bool valid = j < nrow;
+                    float ed = INFINITY;
+                    int64_t id = -1;
+                    if (valid) { ed = cert_exact_il32<P>(qs, vecs, slot0 + j, dim, dimp); id = ids[slot0 + j]; }
+                    top.offer(ed, id, valid, lane, k);
+                }
+            }
+        }
+        const float tau = merge_and_write(false);
+        const bool certified = (tau <= tau0 || tau0 == INFINITY) && cert_lower_bound<METRIC>(R, stats, cq, dim) > tau;
+        if (threadIdx.x == 0) {
+            atomicAdd(counters + 5, (unsigned long long) s_rows);
+            if (!certified) {
+                const unsigned long long n3 = atomicAdd(counters + 4, 1ull);
+                if (dbg && n3 < 16) {
+                    float *rr = dbg + n3 * 8;
+                    rr[0] = (float) q; rr[1] = R; rr[2] = tau; rr[3] = cert_lower_bound<METRIC>(R, stats, cq, dim); rr[4] = (float) s_rows;
+                    rr[5] = cq.eq; rr[6] = cq.qn; rr[7] = tau0;
+                }
+            }
+        }
+        if (certified) {
+            merge_and_write(true);                       // (the per-warp lists are still in `top`)
+            continue;
+        }
+        // ---- level 3: everything
+        top.init();
+        for (int r = 0; r < nprobe; r++) {
+            const uint32_t l = probe[(size_t) q * nprobe + r];
+            if (l >= (uint32_t) nlists) continue;
+            const uint32_t len = list_len[l], base = ltile8[l] * 32;
+            for (uint32_t j0 = w * 32; j0 < len; j0 += FB_THREADS) {
+                const uint32_t j = j0 + lane;
+                const bool valid = j < len;
+                float ed = INFINITY;
+                int64_t id = -1;
+                if (valid) {
+                    ed = cert_exact<P>(qs, arena + (size_t) tc_row[base + j] * dim, dim);
+                    id = ids[tc_src[base + j]];
+                }
+                top.offer(ed, id, valid, lane, k);
+            }
+        }
+        merge_and_write(true);
+    }
+}
+
+// ---- coarse quantiser: ivfSelectClusters (:1597-1717) certified the same way -----------------------------
+// pdist / pslot: per query `nparts` partial lists of kc (squared-distance key, centroid) entries from the tensor
+// scan of the centroid store (no shared bound there: G = the smallest kc-th key of a full list).  Writes the
+// nprobe nearest centroids by (sqrtf'd fp32 L2, index) -- the reference's order: repeated scan, strict <.
+template <int KRC>
+__global__ void __launch_bounds__(128) ivf_coarse_cert_kernel(
+    const float *__restrict__ pdist, const uint32_t *__restrict__ pslot, int nparts, int kc, const float *__restrict__ C,
+    const float *__restrict__ Q, int nq, int nlists, int dim, int np, const float *__restrict__ stats,
+    uint32_t *__restrict__ probe, float *__restrict__ cdist, uint32_t *__restrict__ fb_list,
+    unsigned long long *__restrict__ counters)
+{
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const size_t base = (size_t) q * nparts * kc;
+    // G = min over the full partial lists of their last key
+    float G = INFINITY;
+    for (int p = lane; p < nparts; p += 32)
+        if (pslot[base + (size_t) p * kc + kc - 1] != INVALID_SLOT) G = fminf(G, pdist[base + (size_t) p * kc + kc - 1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) G = fminf(G, __shfl_xor_sync(FULL, G, o));
+    WarpTopK<KRC, uint32_t> cand;
+    cand.init();
+    uint32_t n_in = 0;
+    const int total = nparts * kc;
+    for (int i0 = 0; i0 < total; i0 += 32) {
+        const int i = i0 + lane;
+        float d = INFINITY;
+        uint32_t sl = INVALID_SLOT;
+        if (i < total) { sl = pslot[base + i]; d = pdist[base + i]; }
+        const bool ok = sl != INVALID_SLOT && sl < (uint32_t) nlists && d <= G;
+        const unsigned m = __ballot_sync(FULL, ok);
+        if (m) { n_in += __popc(m); cand.offer(d, sl, ok, lane, 32 * KRC); }
+    }
+    const float *qv = Q + (size_t) q * dim;
+    const CertQ cq = cert_query(qv, dim, lane);
+    const float keylast = __shfl_sync(FULL, cand.d[KRC - 1], 31);
+    const float g_rest = n_in > 32 * KRC ? keylast : G;
+    const bool complete = G == INFINITY && n_in <= 32 * KRC;
+    WarpTopK<1, int64_t> top;
+    const bool ok = cert_rerank<Arith<NDB_L2, NDB_ARITH_IVF_F32>, NDB_L2, KRC>(qv, C, dim, cand, g_rest, complete, stats, cq, np, lane,
+                                                                                [&](uint32_t c) { return c; }, [&](uint32_t c) { return (int64_t) c; },
+                                                                                top, counters ? counters + 1 : nullptr);
+    if (!ok) {
+        if (lane == 0) fb_list[atomicAdd(counters, 1ull)] = (uint32_t) q;
+        return;
+    }
+    if (lane < np) {
+        const bool got = top.key[0] != KeyMax<int64_t>::v;
+        probe[(size_t) q * np + lane] = got ? (uint32_t) top.key[0] : INVALID_SLOT;
+        cdist[(size_t) q * np + lane] = got ? top.d[0] : INFINITY;
+    }
+}
+
+// exact ivfSelectClusters for the queries the certificate rejected: one CTA per query over all centroids
+__global__ void __launch_bounds__(256) ivf_coarse_fallback_kernel(
+    const uint32_t *__restrict__ fb_list, const unsigned long long *__restrict__ counters, const float *__restrict__ C,
+    const float *__restrict__ Q, int nlists, int dim, int np, uint32_t *__restrict__ probe, float *__restrict__ cdist)
+{
+    extern __shared__ float fb_smem[];
+    float *qs = fb_smem;
+    float *md = fb_smem + ((dim + 3) & ~3);
+    int64_t *mi = reinterpret_cast<int64_t *>(md + 256);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned nfb = (unsigned) counters[0];
+    using P = Arith<NDB_L2, NDB_ARITH_IVF_F32>;
+    for (unsigned f = blockIdx.x; f < nfb; f += gridDim.x) {
+        const uint32_t q = fb_list[f];
+        __syncthreads();
+        for (int j = threadIdx.x; j < dim; j += blockDim.x) qs[j] = Q[(size_t) q * dim + j];
+        __syncthreads();
+        WarpTopK<1, int64_t> top;
+        top.init();
+        for (int j0 = w * 32; j0 < nlists; j0 += 256) {
+            const int j = j0 + lane;
+            const bool valid = j < nlists;
+            const float ed = valid ? cert_exact<P>(qs, C + (size_t) j * dim, dim) : INFINITY;
+            top.offer(ed, (int64_t) j, valid, lane, np);
+        }
+        md[w * 32 + lane] = top.d[0];
+        mi[w * 32 + lane] = top.key[0];
+        __syncthreads();
+        if (w == 0) {
+            WarpTopK<1, int64_t> fin;
+            fin.init();
+            for (int ww = 0; ww < 8; ww++) {
+                const float d = md[ww * 32 + lane];
+                const int64_t id = mi[ww * 32 + lane];
+                fin.offer(d, id, id != KeyMax<int64_t>::v, lane, np);
+            }
+            if (lane < np) {
+                const bool got = fin.key[0] != KeyMax<int64_t>::v;
+                probe[(size_t) q * np + lane] = got ? (uint32_t) fin.key[0] : INVALID_SLOT;
+                cdist[(size_t) q * np + lane] = got ? fin.d[0] : INFINITY;
+            }
+        }
+    }
+}
+
+}  // namespace ndb

@@ -16,6 +16,7 @@ constexpr int TC_PACKED_MAX_TILES = 16;   // packed-key epilogue: 11 index bits 
 // stored rows in the blocked bf16 layout + squared norms of the rounded rows
 struct TcStore {
     DevBuf xb, xnorm, xrinv, xpad0; // blocked rows, squared norms of the rounded rows, 1 / norm (cosine), 0 | +inf (inner product)
+    DevBuf stats;                   // 4 floats: rounding-error maxima over the stored rows (tc_row_norms_kernel)
     int64_t valid_for = -1, rinv_for = -2, pad0_for = -2;
     int64_t ntiles = 0;
     int nkc = 0;
@@ -32,7 +33,7 @@ struct TcItem {
 };
 
 struct TcScratch {
-    DevBuf qb, qnorm, pdist, pslot, debug, items, gthr;
+    DevBuf qb, qnorm, qerr, pdist, pslot, debug, items, gthr;
 };
 
 struct TcParams {
@@ -51,6 +52,10 @@ struct TcParams {
     uint32_t nprobe;
     float *gthr;                   // optional (list mode): per query, an upper bound of its k-th best candidate, shared
                                    // between the items of the query (atomic min; initialised to a huge finite value)
+    const float *qerr;             // optional: squared norm of each tile position's bf16 rounding error (with cstats)
+    const float *cstats;           // optional: TcStore::stats of the stored rows -> the shared bound is published RELAXED
+                                   // (cert_bound.cuh), which is what makes the selection certifiable
+    int dim;                       // row dimension (for the accumulation slack)
     int packed;                    // 1: items span <= TC_PACKED_MAX_TILES tiles; (distance | index) keys, sorting-network epilogue
     float *debug_d;                // optional: raw accumulator of the first tile [128][256]
     int debug_mode;                // NDB_TC_DEBUG: 1 = no epilogue math, 2 = no MMA issue, 4 = no X bulk copies (bisection aid)
@@ -63,7 +68,7 @@ int tc_build_store_mapped(TcStore &st, const float *il32_store, const uint32_t *
                           cudaStream_t s);
 // npos_dev (optional): device count of tile positions actually in use (nqpad is then an upper bound)
 int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t nprobe, int nq, int nqpad, int dim, int nkc,
-                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s, const uint32_t *npos_dev = nullptr);
+                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s, const uint32_t *npos_dev = nullptr, float *qerr = nullptr);
 
 int tc_build_store(TcStore &st, const float *il32_store, int64_t n, int dim, int dimp, cudaStream_t s);
 int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q_dev, int nq, int k, const int64_t *ids,

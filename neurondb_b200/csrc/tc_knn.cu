@@ -30,6 +30,7 @@
 #include "layout.cuh"
 #include "scan.cuh"
 #include "tc.cuh"
+#include "cert_bound.cuh"
 
 #include <cuda_bf16.h>
 #include <algorithm>
@@ -82,32 +83,62 @@ __global__ void tc_block_rows_kernel(const float4 *__restrict__ store, const uin
     (void) xnorm;
 }
 
-// one thread per row: squared norm of the bf16-rounded row; +inf for pad rows so they never rank
+// one thread per row: squared norm of the bf16-rounded row; +inf for pad rows so they never rank.
+// stats (4 floats, zeroed by the caller) receives, over all stored rows, the maxima the certified
+// selection needs to bound what bf16 rounding can do to a distance (ivf.cu, "certified selection"):
+//   [0] max ||x - bf16(x)||^2   [1] max ||x||^2   [2] max ||x - bf16(x)||^2 / ||bf16(x)||^2   [3] max ||x||^2 / ||bf16(x)||^2
 __global__ void tc_row_norms_kernel(const float4 *__restrict__ store, const uint32_t *__restrict__ src_slot, int64_t n,
-                                    int64_t npad, int dim, int dimp, float *__restrict__ xnorm)
+                                    int64_t npad, int dim, int dimp, float *__restrict__ xnorm, float *__restrict__ stats)
 {
     const int64_t row = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= npad) return;
-    const int64_t srow = src_slot ? (src_slot[row] != INVALID_SLOT ? (int64_t) src_slot[row] : -1) : (row < n ? row : -1);
-    if (srow < 0) { xnorm[row] = INFINITY; return; }
-    float acc = 0.0f;
-    const float4 *vp = store + (size_t) (srow >> 5) * (8 * (size_t) dimp) + (srow & 31);
-    for (int c = 0; 4 * c < dimp; c++) {
-        const float4 x = vp[(size_t) c * 32];
-        const float a = __bfloat162float(__float2bfloat16_rn(4 * c + 0 < dim ? x.x : 0.0f));
-        const float b = __bfloat162float(__float2bfloat16_rn(4 * c + 1 < dim ? x.y : 0.0f));
-        const float cc = __bfloat162float(__float2bfloat16_rn(4 * c + 2 < dim ? x.z : 0.0f));
-        const float d = __bfloat162float(__float2bfloat16_rn(4 * c + 3 < dim ? x.w : 0.0f));
-        acc = fmaf(a, a, acc); acc = fmaf(b, b, acc); acc = fmaf(cc, cc, acc); acc = fmaf(d, d, acc);
+    float e2 = 0.0f, x2 = 0.0f, acc = 0.0f;
+    bool real = false;
+    if (row < npad) {
+        const int64_t srow = src_slot ? (src_slot[row] != INVALID_SLOT ? (int64_t) src_slot[row] : -1) : (row < n ? row : -1);
+        if (srow < 0) {
+            xnorm[row] = INFINITY;
+        } else {
+            real = true;
+            const float4 *vp = store + (size_t) (srow >> 5) * (8 * (size_t) dimp) + (srow & 31);
+            for (int c = 0; 4 * c < dimp; c++) {
+                const float4 x = vp[(size_t) c * 32];
+                const float xs[4] = {4 * c + 0 < dim ? x.x : 0.0f, 4 * c + 1 < dim ? x.y : 0.0f, 4 * c + 2 < dim ? x.z : 0.0f,
+                                     4 * c + 3 < dim ? x.w : 0.0f};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float r = __bfloat162float(__float2bfloat16_rn(xs[i]));
+                    acc = fmaf(r, r, acc);
+                    x2 = fmaf(xs[i], xs[i], x2);
+                    e2 = fmaf(xs[i] - r, xs[i] - r, e2);
+                }
+            }
+            xnorm[row] = acc;
+        }
     }
-    xnorm[row] = acc;
+    if (!stats) return;
+    // rounded up a little: these feed upper bounds, and the fmaf chains above round to nearest
+    float v0 = real ? e2 * 1.0001f : 0.0f, v1 = real ? x2 * 1.0001f : 0.0f;
+    float v2 = (real && acc > 0.0f) ? e2 / acc * 1.0002f : 0.0f, v3 = (real && acc > 0.0f) ? x2 / acc * 1.0002f : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v0 = fmaxf(v0, __shfl_xor_sync(FULL, v0, o));
+        v1 = fmaxf(v1, __shfl_xor_sync(FULL, v1, o));
+        v2 = fmaxf(v2, __shfl_xor_sync(FULL, v2, o));
+        v3 = fmaxf(v3, __shfl_xor_sync(FULL, v3, o));
+    }
+    if ((threadIdx.x & 31) == 0) {        // non-negative floats order like their bit patterns
+        atomicMax(reinterpret_cast<int *>(stats) + 0, __float_as_int(v0));
+        atomicMax(reinterpret_cast<int *>(stats) + 1, __float_as_int(v1));
+        atomicMax(reinterpret_cast<int *>(stats) + 2, __float_as_int(v2));
+        atomicMax(reinterpret_cast<int *>(stats) + 3, __float_as_int(v3));
+    }
 }
 
 // row-major fp32 queries -> blocked bf16 query tiles + squared norms
 // qmap (optional): tile position q holds query qmap[q] / nprobe (INVALID_SLOT = empty position)
 __global__ void tc_block_queries_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap, uint32_t nprobe,
                                         int nq, int nqpad, const uint32_t *__restrict__ npos, int dim, int nkc,
-                                        __nv_bfloat16 *__restrict__ qb, float *__restrict__ qnorm)
+                                        __nv_bfloat16 *__restrict__ qb, float *__restrict__ qnorm, float *__restrict__ qerr)
 {
     const int groups = nkc * (TC_KC / 8);
     const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,7 +148,7 @@ __global__ void tc_block_queries_kernel(const float *__restrict__ Q, const uint3
     const int g = (int) (t - (int64_t) q * groups);
     const int64_t src = qmap ? (qmap[q] != INVALID_SLOT ? (int64_t) (qmap[q] / nprobe) : -1) : (q < nq ? q : -1);
     __nv_bfloat16 o[8];
-    float part = 0.0f;
+    float part = 0.0f, perr = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int d = g * 8 + i;
@@ -125,6 +156,7 @@ __global__ void tc_block_queries_kernel(const float *__restrict__ Q, const uint3
         o[i] = __float2bfloat16_rn(v);
         const float r = __bfloat162float(o[i]);
         part = fmaf(r, r, part);
+        perr = fmaf(v - r, v - r, perr);
     }
     // Query i of a tile sits on TMEM lane (i % 4) * 32 + i / 4: the tile's queries are dealt round-robin
     // to the four lane quarters, each of which only one pair of epilogue warps can read.  A tile with 16
@@ -138,26 +170,33 @@ __global__ void tc_block_queries_kernel(const float *__restrict__ Q, const uint3
     // a fixed xor tree, so a query gets the same norm at whatever tile position it sits
     // (more than 32 groups per row, dim > 256: tc_query_norms_kernel does it instead)
     if (groups <= 32) {
-        for (int o2 = groups >> 1; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(FULL, part, o2);
-        if (g == 0) qnorm[q] = part;
+        for (int o2 = groups >> 1; o2 > 0; o2 >>= 1) {
+            part += __shfl_xor_sync(FULL, part, o2);
+            perr += __shfl_xor_sync(FULL, perr, o2);
+        }
+        if (g == 0) { qnorm[q] = part; if (qerr) qerr[q] = perr; }      // qerr: squared norm of the query's bf16 rounding error
     }
 }
 
 // squared norm of the bf16-rounded query, one thread per tile position (rows of more than 256 dims)
 __global__ void tc_query_norms_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap, uint32_t nprobe, int nq,
-                                      int nqpad, const uint32_t *__restrict__ npos, int dim, float *__restrict__ qnorm)
+                                      int nqpad, const uint32_t *__restrict__ npos, int dim, float *__restrict__ qnorm,
+                                      float *__restrict__ qerr)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (npos) nqpad = min(nqpad, (int) *npos);
     if (q >= nqpad) return;
     const int64_t src = qmap ? (qmap[q] != INVALID_SLOT ? (int64_t) (qmap[q] / nprobe) : -1) : (q < nq ? q : -1);
-    float acc = 0.0f;
+    float acc = 0.0f, err = 0.0f;
     if (src >= 0)
         for (int d = 0; d < dim; d++) {
-            const float r = __bfloat162float(__float2bfloat16_rn(Q[(size_t) src * dim + d]));
+            const float v = Q[(size_t) src * dim + d];
+            const float r = __bfloat162float(__float2bfloat16_rn(v));
             acc = fmaf(r, r, acc);
+            err = fmaf(v - r, v - r, err);
         }
     qnorm[q] = acc;
+    if (qerr) qerr[q] = err;
 }
 
 // ---- tcgen05 / TMEM primitives -------------------------------------------------------------
@@ -495,6 +534,13 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
             // (ql >= nq) never take a candidate.
             float *gcell = nullptr;
             float gcap = live ? INFINITY : -INFINITY, published = INFINITY;
+            // certified selection (cert_bound.cuh): the bound this list publishes is relaxed by what bf16 rounding can
+            // do to a distance, so that every non-full list of the query stays complete below it
+            CertQ cq;
+            if (p.cstats) {
+                const float eq = sqrtf(p.qerr[(size_t) it.qtile * TC_M + ql]) * 1.0002f, qr = sqrtf(qn);
+                cq.eq = eq; cq.qnr = qr * 1.0002f; cq.qn = (qr + eq) * 1.0002f; cq.qn_lo = fmaxf(qr - eq, 0.0f) * 0.9998f;
+            }
             if (p.gthr && live) {
                 const uint32_t pr = p.qmap[(size_t) it.qtile * TC_M + ql];
                 if (pr != INVALID_SLOT) gcell = p.gthr + pr / p.nprobe;
@@ -647,7 +693,10 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     float pub = published;
                     if (PACKED)     // an upper bound of the value the key stands for
                         pub = __uint_as_float(pub >= 0.0f ? (__float_as_uint(pub) | TC_IDX_MASK) : (__float_as_uint(pub) & ~TC_IDX_MASK));
-                    if (!PACKED || pub < TC_KEY_BIG) atomic_min_f32(gcell, pub);
+                    if (!PACKED || pub < TC_KEY_BIG) {
+                        if (p.cstats) pub = cert_relax<METRIC>(pub, p.cstats, cq, p.dim);
+                        atomic_min_f32(gcell, pub);
+                    }
                 }
             }
             if (live) {
@@ -700,8 +749,10 @@ int tc_build_store_mapped(TcStore &st, const float *il32_store, const uint32_t *
     const int groups = nkc * (TC_KC / 8);
     tc_block_rows_kernel<<<(unsigned) ((npad * groups + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(il32_store), src_slot_dev, n, npad, dim,
                                                                                  dimp, nkc, st.xb.as<__nv_bfloat16>(), st.xnorm.as<float>());
+    NDB_CHECK(st.stats.reserve(16));
+    NDB_CUDA(cudaMemsetAsync(st.stats.p, 0, 16, s));
     tc_row_norms_kernel<<<(unsigned) ((npad + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(il32_store), src_slot_dev, n, npad, dim, dimp,
-                                                                        st.xnorm.as<float>());
+                                                                        st.xnorm.as<float>(), st.stats.as<float>());
     count_launch(2);
     NDB_CUDA(cudaGetLastError());
     st.valid_for = n;
@@ -758,14 +809,14 @@ int tc_store_rinv(TcStore &st, const float **out, cudaStream_t s)
 
 // blocked bf16 query tiles + squared norms; qmap_dev (optional) gathers the tile positions
 int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t nprobe, int nq, int nqpad, int dim, int nkc,
-                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s, const uint32_t *npos_dev)
+                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s, const uint32_t *npos_dev, float *qerr)
 {
     const int groups = nkc * (TC_KC / 8);
     tc_block_queries_kernel<<<(unsigned) (((int64_t) nqpad * groups + 255) / 256), 256, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev,
-                                                                                                dim, nkc, qb, qnorm);
+                                                                                                dim, nkc, qb, qnorm, qerr);
     count_launch();
     if (groups > 32) {
-        tc_query_norms_kernel<<<(unsigned) ((nqpad + 127) / 128), 128, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev, dim, qnorm);
+        tc_query_norms_kernel<<<(unsigned) ((nqpad + 127) / 128), 128, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev, dim, qnorm, qerr);
         count_launch();
     }
     NDB_CUDA(cudaGetLastError());
