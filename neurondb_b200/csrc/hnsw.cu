@@ -1075,8 +1075,10 @@ int ndb_b200_hnsw_load_relation(ndb_b200_hnsw *h, const void *blocks, uint32_t n
     for (int64_t i = 0; i < n; i++) {
         const uint8_t *page = page_at(blocks, (uint32_t) (i + 1));
         NDB_REQUIRE(max_offset(page) >= 1, NDB_B200_EINVAL, "hnsw_load_relation: block %lld holds no node", (long long) (i + 1));
-        uint32_t lo, fl, len;
-        item_id(page, 1, &lo, &fl, &len);                         // always FirstOffsetNumber (:70-80)
+        uint32_t lo = 0, len = 0;
+        // always FirstOffsetNumber (:70-80); the header is only read once the item is known to lie inside the page
+        NDB_REQUIRE(checked_item(page, 1, HNSW_NODE_HDR + (uint32_t) dim * 4, &lo, &len) == 1, NDB_B200_EINVAL,
+                    "hnsw_load_relation: block %lld has no valid node item (line pointer outside the page or too short)", (long long) (i + 1));
         const uint8_t *node = page + lo;
         int32_t level;
         int16_t ndim;

@@ -33,6 +33,7 @@ struct ndb_b200_ivf {
     // arena: rows kept by this shard, row-major, insertion order
     DevBuf arena;
     int64_t nrows = 0;
+    int64_t inserted_total = 0;          // next default id: one past the largest id seen / handed out, over ALL rows passed in
     std::vector<int64_t> row_id;
     std::vector<int32_t> row_list;
     // laid-out lists
@@ -925,8 +926,9 @@ int ndb_b200_ivf_insert(ndb_b200_ivf *ix, const float *rows, const int64_t *ids,
     const int64_t chunk = 1 << 20;
     std::vector<int> assign;
     std::vector<uint32_t> keep;
-    int64_t next_default_id = 0;
-    for (int64_t r = 0; r < (int64_t) ix->row_id.size(); r++) next_default_id = std::max(next_default_id, ix->row_id[r] + 1);
+    // default ids number every row ever passed to this handle, kept or not: the ranks of a list-sharded index see the
+    // same rows in the same order, so they agree on the ids whatever each of them keeps
+    const int64_t next_default_id = ix->inserted_total;
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t m = n - off < chunk ? n - off : chunk;
         NDB_CHECK(ix->tmp_rows.reserve((size_t) m * ix->dim * 4));
@@ -958,6 +960,8 @@ int ndb_b200_ivf_insert(ndb_b200_ivf *ix, const float *rows, const int64_t *ids,
             ix->dirty = true;
         }
     }
+    if (ids) { for (int64_t i = 0; i < n; i++) ix->inserted_total = std::max(ix->inserted_total, ids[i] + 1); }
+    else ix->inserted_total += n;
     return NDB_B200_OK;
 }
 
@@ -1055,12 +1059,20 @@ int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np
 
     if (mode == NDB_IVF_LITERAL) {
         NDB_REQUIRE(k * 10 <= 2560, NDB_B200_EINVAL, "ivf literal mode: k too large");
-        const size_t smem = (size_t) 12 * 4 * k * 10;
+        NDB_REQUIRE(arith != NDB_ARITH_FAST, NDB_B200_EINVAL, "ivf literal mode reproduces ivfCollectCandidates: arith must be NDB_ARITH_IVF_F32");
+        const size_t smem = (size_t) 12 * 4 * k * 10;                 // k = 128: 61 440 bytes, above the 48 KB default
+        NDB_REQUIRE(smem <= ctx().smem_optin, NDB_B200_EINVAL, "ivf literal mode: k=%d needs %zu bytes of shared memory", k, smem);
         const unsigned grid = (unsigned) ((nq + 3) / 4);
-#define NDB_LIT(M) ivf_literal_kernel<Arith<M, NDB_ARITH_IVF_F32>><<<grid, 128, smem, s>>>( \
+#define NDB_LIT(M) do { \
+        static uint64_t cfg = 0; \
+        if (cfg != ctx().generation) { \
+            NDB_CUDA(cudaFuncSetAttribute(ivf_literal_kernel<Arith<M, NDB_ARITH_IVF_F32>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (12 * 4 * 1280))); \
+            cfg = ctx().generation; \
+        } \
+        ivf_literal_kernel<Arith<M, NDB_ARITH_IVF_F32>><<<grid, 128, smem, s>>>( \
         reinterpret_cast<const float4 *>(ix->store.ptr()), (const float *) vnorm, Q_dev, ix->probe.as<uint32_t>(), \
         ix->d_list_len.as<uint32_t>(), ix->d_list_blk.as<uint32_t>(), ix->lit_order.as<uint32_t>(), ix->ids.as<int64_t>(), \
-        nq, np, L, ix->dim, ix->dimp, k, dist_dev, ids_dev)
+        nq, np, L, ix->dim, ix->dimp, k, dist_dev, ids_dev); } while (0)
         if (ix->metric == NDB_L2) NDB_LIT(NDB_L2);
         else if (ix->metric == NDB_COSINE) NDB_LIT(NDB_COSINE);
         else NDB_LIT(NDB_IP);
@@ -1246,19 +1258,23 @@ int ndb_b200_ivf_load_relation(ndb_b200_ivf *ix, const void *blocks, uint32_t nb
     const int L = ix->nlists, dim = ix->dim;
     std::vector<float> C((size_t) L * dim, 0.0f);
     std::vector<uint32_t> first(L, INVALID_BLOCK);
+    std::vector<uint8_t> have_list(L, 0);
     int got = 0;
     for (uint32_t b = meta.centroidsBlock; b < nblocks && got < L; b++) {
         const uint8_t *page = page_at(blocks, b);
         if (special_offset(page) != BLCKSZ - 24) break;            // not a centroid page
         const int maxoff = max_offset(page);
         for (int off = 1; off <= maxoff && got < L; off++) {
-            uint32_t lo, fl, len;
-            item_id(page, off, &lo, &fl, &len);
-            if (fl != LP_NORMAL) continue;
+            uint32_t lo = 0, len = 0;
+            const int st = checked_item(page, off, 24 + (uint32_t) dim * 4, &lo, &len);
+            if (st == 0) continue;
+            NDB_REQUIRE(st == 1, NDB_B200_EINVAL, "ivf_load_relation: centroid item %d/%d lies outside its page or is too short", (int) b, off);
             IvfCentroidHdr h;
             memcpy(&h, page + lo, sizeof(h));
             NDB_REQUIRE(h.listId >= 0 && h.listId < L && h.dim == dim, NDB_B200_EINVAL,
                         "ivf_load_relation: centroid item %d/%d is inconsistent (list %d dim %d)", (int) b, off, h.listId, h.dim);
+            NDB_REQUIRE(!have_list[h.listId], NDB_B200_EINVAL, "ivf_load_relation: list %d has two centroid items", h.listId);
+            have_list[h.listId] = 1;
             memcpy(&C[(size_t) h.listId * dim], page + lo + 24, (size_t) dim * 4);
             first[h.listId] = h.firstBlock;
             got++;
@@ -1269,6 +1285,8 @@ int ndb_b200_ivf_load_relation(ndb_b200_ivf *ix, const void *blocks, uint32_t nb
 
     // walk every chain: page order = insertion order inside a list (ivf_am.c:1793-1840)
     std::vector<uint64_t> src;           // byte offset of each live entry's vector payload
+    std::vector<int64_t> new_id;         // committed to the index only when the whole relation has been read
+    std::vector<int32_t> new_list;
     std::vector<uint8_t> seen(nblocks, 0);
     for (int l = 0; l < L; l++) {
         if (l % ix->world != ix->rank) continue;
@@ -1279,14 +1297,16 @@ int ndb_b200_ivf_load_relation(ndb_b200_ivf *ix, const void *blocks, uint32_t nb
             NDB_REQUIRE(special_offset(page) == BLCKSZ - 8, NDB_B200_EINVAL, "ivf_load_relation: block %u is not a list page", b);
             const int maxoff = max_offset(page);
             for (int off = 1; off <= maxoff; off++) {
-                uint32_t lo, fl, len;
-                item_id(page, off, &lo, &fl, &len);
-                if (fl != LP_NORMAL) continue;                       // unused or LP_DEAD (:1816)
+                uint32_t lo = 0, len = 0;
+                const int st = checked_item(page, off, IVF_ENTRY_HDR, &lo, &len);
+                if (st == 0) continue;                               // unused or LP_DEAD (:1816)
+                NDB_REQUIRE(st == 1, NDB_B200_EINVAL, "ivf_load_relation: entry %u/%d lies outside its page", b, off);
                 int16_t edim;
                 memcpy(&edim, page + lo + 6, 2);
                 if (edim != dim) continue;                           // :1821-1822
-                ix->row_id.push_back(tid_unpack(page + lo));
-                ix->row_list.push_back(l);
+                NDB_REQUIRE(len >= IVF_ENTRY_HDR + (uint32_t) dim * 4, NDB_B200_EINVAL, "ivf_load_relation: entry %u/%d is truncated", b, off);
+                new_id.push_back(tid_unpack(page + lo));
+                new_list.push_back(l);
                 src.push_back((uint64_t) b * BLCKSZ + lo + IVF_ENTRY_HDR);
             }
             IvfListSpecial sp;
@@ -1308,6 +1328,9 @@ int ndb_b200_ivf_load_relation(ndb_b200_ivf *ix, const void *blocks, uint32_t nb
     count_launch();
     NDB_CUDA(cudaGetLastError());
     NDB_CUDA(cudaStreamSynchronize(s));
+    for (int64_t v : new_id) ix->inserted_total = std::max(ix->inserted_total, v + 1);
+    ix->row_id = std::move(new_id);
+    ix->row_list = std::move(new_list);
     ix->nrows = n;
     ix->dirty = true;
     return NDB_B200_OK;

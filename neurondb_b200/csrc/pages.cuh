@@ -46,6 +46,22 @@ inline void item_id(const uint8_t *page, int off, uint32_t *lp_off, uint32_t *fl
     *flags = (lp >> 15) & 3;
     *len = lp >> 17;
 }
+// A line pointer taken from a page image is untrusted input (a torn or corrupt page must not send the loaders
+// outside the 8 KB block): item `off` is usable iff it is LP_NORMAL, lies between pd_upper and pd_special inside
+// the block, and holds at least `min_len` bytes.  Returns 1 = usable, 0 = skip (unused / LP_DEAD), -1 = corrupt.
+inline int checked_item(const uint8_t *page, int off, uint32_t min_len, uint32_t *lp_off, uint32_t *len)
+{
+    PageHeader h;
+    memcpy(&h, page, sizeof(h));
+    uint32_t lo, fl, ln;
+    item_id(page, off, &lo, &fl, &ln);
+    if (fl != LP_NORMAL) return 0;
+    if (h.pd_special > BLCKSZ || h.pd_upper > h.pd_special || h.pd_lower > h.pd_upper) return -1;
+    if (lo < h.pd_upper || lo < PAGE_HEADER || (uint64_t) lo + ln > h.pd_special || ln < min_len) return -1;
+    *lp_off = lo;
+    *len = ln;
+    return 1;
+}
 inline uint16_t special_offset(const uint8_t *page)
 {
     PageHeader h;

@@ -144,3 +144,34 @@ def test_pipelined_search_equals_synchronous(ndb):
     t = ix.search_begin(bad, o[0][0], o[0][1], 8, 10)
     with pytest.raises(ndb.NdbError):
         ix.search_end(t)
+
+
+def test_ivf_literal_mode_at_the_largest_k(ndb, orc):
+    """k = 128: the literal kernel's candidate arrays (12 * 4 * k * 10 = 61 440 bytes) exceed the 48 KB default of
+    dynamic shared memory, so the launch needs the opt-in attribute."""
+    X = W.mixture(30000, 32, 16, 17)
+    Q = W.mixture(40, 32, 16, 18, centers_seed=17)
+    ix, oC, off, rows = build_pair(ndb, orc, X, 16)
+    d, i = ix.search(Q, 8, 128, ndb.IVF_LITERAL)
+    od, oi, _ = orc.ivf_search(X, oC, off, rows, Q, 8, 128, literal=True)
+    assert np.array_equal(i, oi) and np.array_equal(BITS(d), BITS(od))
+    with pytest.raises(ndb.NdbError):          # the literal mode is ivfCollectCandidates' own arithmetic only
+        ix.search(Q, 8, 10, ndb.IVF_LITERAL, ndb.ARITH_FAST)
+
+
+def test_wrappers_report_dimension_errors(ndb):
+    """A mismatched array is the reference's 'dimensions must match' error (EDIM), not an out-of-bounds read."""
+    X = W.gaussian(600, 8, 3)
+    ix = ndb.IvfIndex(8, 4)
+    ix.ivfbuild(X)
+    ix.ivfinsert(X)
+    for call in (lambda: ix.search(W.gaussian(3, 9, 1), 2, 5), lambda: ix.ivfinsert(W.gaussian(3, 7, 1)),
+                 lambda: ix.select_clusters(W.gaussian(3, 16, 1), 2), lambda: ix.assign(W.gaussian(3, 4, 1))):
+        with pytest.raises(ndb.NdbError) as e:
+            call()
+        assert e.value.code == -5
+    ds = ndb.Dataset(8)
+    ds.append(X)
+    with pytest.raises(ndb.NdbError) as e:
+        ds.knn(W.gaussian(2, 5, 1), 3)
+    assert e.value.code == -5

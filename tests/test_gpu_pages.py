@@ -81,3 +81,45 @@ def test_hnsw_load_relation_search_parity(ndb, orc):
         od, on, _ = g.search(Q, 32, 10, 1, smode)
         want = np.where(on == 0xFFFFFFFF, -1, tids[np.minimum(on, n - 1)])
         assert np.array_equal(i, want) and np.array_equal(BITS(d), BITS(od))
+
+
+def _set_line_pointer(blocks, block, offnum, lp_off, lp_len, flags=1):
+    b = blocks.reshape(-1, 8192)
+    lp = (lp_off & 0x7fff) | ((flags & 3) << 15) | ((lp_len & 0x7fff) << 17)
+    b[block, 24 + 4 * (offnum - 1):24 + 4 * offnum] = np.frombuffer(np.uint32(lp).tobytes(), np.uint8)
+
+
+def test_loaders_reject_line_pointers_that_leave_the_page(ndb, orc):
+    """A torn or corrupt page: lp_off / lp_len are 15-bit fields and may point past the 8 KB block.  The loaders must
+    refuse the relation, and a refused IVF relation must leave the handle empty and usable."""
+    n, dim, lists = 1500, 16, 4
+    X = W.mixture(n, dim, lists, 7)
+    C, _, _, _, _ = orc.kmeans_train(X[:400], lists)
+    assign = orc.ivf_assign(X, C)
+    nb, blocks = orc.ivf_encode_relation(X, C, assign)
+    for lp_off, lp_len in ((32000, 72), (8100, 500), (8, 72)):        # beyond the block; runs over pd_special; inside the header
+        bad = blocks.copy()
+        _set_line_pointer(bad, 2, 2, lp_off, lp_len)
+        ix = ndb.IvfIndex(dim, lists)
+        with pytest.raises(ndb.NdbError):
+            ix.load_relation(bad)
+        assert len(ix) == 0
+        ix.ivfinsert(X[:100])                    # the failed load left no stale row ids behind
+        assert len(ix) == 100 and np.array_equal(np.sort(ix.search(X[:5], lists, 1)[1][:, 0]), np.arange(5))
+    # a second centroid item for the same list
+    bad = blocks.copy().reshape(-1, 8192)
+    hdr = bad[1, 24:28].view(np.uint32)[0] & 0x7fff      # first centroid item's offset
+    second = bad[1, 28:32].view(np.uint32)[0] & 0x7fff
+    bad[1, second:second + 4] = bad[1, hdr:hdr + 4]      # duplicate listId
+    with pytest.raises(ndb.NdbError):
+        ndb.IvfIndex(dim, lists).load_relation(bad.reshape(-1))
+    # HNSW: node item pointing outside its page
+    Xh = W.gaussian(300, 12, 5)
+    levels = orc.hnsw_levels(300, seed=3)
+    g = orc.Hnsw(12, 8, 32, 32, capacity=300)
+    g.build(Xh, levels, 1)
+    nbh, hb = orc.hnsw_encode_relation(g, Xh)
+    badh = hb.copy()
+    _set_line_pointer(badh, 5, 1, 8000, 3000)
+    with pytest.raises(ndb.NdbError):
+        ndb.HnswIndex(12, 8, 32, 32).load_relation(badh)
