@@ -11,7 +11,7 @@ SRCS      := $(wildcard $(SRCDIR)/*.cu)
 OBJS      := $(patsubst $(SRCDIR)/%.cu,$(OBJDIR)/%.o,$(SRCS))
 HDRS      := $(wildcard $(SRCDIR)/*.cuh) include/ndb_b200.h
 
-all: $(LIBDIR)/libndb_b200.so oracle
+all: $(LIBDIR)/libndb_b200.so oracle glue
 
 $(OBJDIR)/%.o: $(SRCDIR)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -24,8 +24,12 @@ $(LIBDIR)/libndb_b200.so: $(OBJS)
 oracle:
 	$(MAKE) -s -C oracle
 
+# reference-side glue (integration/*.c) against the reference's own header; needs the library first
+glue: $(LIBDIR)/libndb_b200.so
+	$(MAKE) -s -C oracle glue
+
 clean:
 	rm -rf build $(LIBDIR)/*.so
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle glue clean
