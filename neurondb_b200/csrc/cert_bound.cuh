@@ -3,7 +3,8 @@
 //
 // Keys are computed from x~ = bf16(x), q~ = bf16(q); ex = x~ - x, eq = q~ - q; bf16 x bf16 products are exact in
 // fp32, so the only approximations are the roundings of the inputs, the fp32 accumulation of `dim` terms
-// (<= (dim + 8) 2^-23 of the magnitudes) and the 12-bit packing of the keys (2^-10 relative, both directions):
+// (<= (dim + 8) 2^-23 of the magnitudes) and the 12-bit packing of the keys (a key differs from the value it stands
+// for by less than 2^-12 relative; 2^-11 is charged, in both directions):
 //     L2      key = ||x~ - q~||^2          | ||x - q|| - sqrt(key) |           <= ||ex|| + ||eq||
 //     IP      key = -x~.q~                 | -x.q - key |                      <= ||ex|| ||q~|| + ||x|| ||eq||
 //     cosine  key = -x~.q~ / ||x~||        | -x.q / ||x|| - key |              <= rho (||q~|| + ||q||) + kappa ||eq||
@@ -43,7 +44,7 @@ __device__ __forceinline__ float cert_lower_bound(float key, const float *__rest
 {
     float E, D, gam;
     cert_slack<METRIC>(st, c, dim, E, D, gam);
-    const float kv = key - fabsf(key) * 9.765625e-4f - D;           // 2^-10: keys carry 12 mantissa bits
+    const float kv = key - fabsf(key) * 4.8828125e-4f - D;          // 2^-11: keys carry 12 mantissa bits
     if (METRIC == NDB_L2) {
         const float r = sqrtf(fmaxf(kv, 0.0f)) - E;
         return r - fabsf(r) * gam;
@@ -60,7 +61,7 @@ __device__ __forceinline__ float cert_upper_bound(float key, const float *__rest
 {
     float E, D, gam;
     cert_slack<METRIC>(st, c, dim, E, D, gam);
-    const float kv = key + fabsf(key) * 9.765625e-4f + D;
+    const float kv = key + fabsf(key) * 4.8828125e-4f + D;
     if (METRIC == NDB_L2) {
         const float r = sqrtf(fmaxf(kv, 0.0f)) + E;
         return r + fabsf(r) * gam;
@@ -93,7 +94,7 @@ __device__ __forceinline__ float cert_relax(float key, const float *__restrict__
         const float u = v > 0.0f ? v * c.qn : v * c.qn_lo;
         R = u + E + D;
     }
-    R += fabsf(R) * 2.9296875e-3f + 1e-30f;                          // 3 * 2^-10: packing slack, strictness
+    R += fabsf(R) * 9.765625e-4f + 1e-30f;                           // 2^-10: the lower bound's own packing slack (2^-11) + strictness
     return R;
 }
 

@@ -64,17 +64,15 @@ struct ndb_b200_ivf {
         }
     }
     // tensor-core copy (NDB_ARITH_TENSOR): every list padded to whole 256-row tiles of blocked bf16
-    bool tc_ok = false, ctc_ok = false;
-    TcStore tc, ctc;                     // lists, centroids
-    TcScratch tcs, ctcs;
+    bool tc_ok = false;
+    TcStore tc;                          // lists (the centroids' copy lives in kw.cs)
+    TcScratch tcs;
     uint32_t tc_max_nseg = 1;            // longest list, in segments of the tensor scan
     uint64_t tc_sum_nseg = 0, tc_nonempty = 0;   // over the non-empty lists
     DevBuf tc_src, tc_row, d_ltile8;     // tensor row -> IL32 slot / arena row; first tile of each list (* 8, in 32-row blocks)
     // certified selection (ivf_cert.cuh): queries sent to the exact kernels, [0] lists [1] exact evaluations (lists)
     // [2] coarse [3] exact evaluations (coarse); items of the coarse scan, cached per batch shape
-    DevBuf cert_counters, fb_list, fb_tau, fb_clist, cert_dbg;
-    int citems_nq = -1;
-    uint32_t citems_tpr = 0, citems_nranges = 0;
+    DevBuf cert_counters, fb_list, fb_tau, cert_dbg;
     std::vector<uint32_t> row_of_slot;   // IL32 slot -> arena row (host copy, kept for the tensor layout)
 };
 
@@ -465,10 +463,6 @@ static uint32_t ivf_tc_seg_tiles()
 static int ivf_tensor_ready(ndb_b200_ivf *ix, cudaStream_t s)
 {
     const int L = ix->nlists;
-    if (!ix->ctc_ok) {
-        NDB_CHECK(tc_build_store(ix->ctc, ix->kw.cstore.as<float>(), L, ix->dim, ix->dimp, s));
-        ix->ctc_ok = true;
-    }
     if (ix->tc_ok) return NDB_B200_OK;
     std::vector<uint32_t> ltile8(L);
     uint64_t nt = 0;
@@ -512,81 +506,6 @@ static int ivf_tc_margin()
     return v;
 }
 
-// ivfSelectClusters on the tensor cores, certified (ivf_cert.cuh): the centroid store is scanned in
-// `nranges` tile ranges, each (query, range, column half) leaves its kc best keys, and ivf_coarse_cert_kernel
-// re-evaluates the best of their union with the reference's arithmetic.  np <= 32.
-static int ivf_coarse_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np, cudaStream_t s)
-{
-    const TcStore &st = ix->ctc;
-    const int nkc = st.nkc, kc = TC_KMAX, L = ix->nlists;
-    const uint32_t nqt = (uint32_t) ((nq + TC_M - 1) / TC_M);
-    const int nqpad = (int) nqt * TC_M;
-    NDB_CHECK(ix->ctcs.qb.reserve((size_t) nqpad * nkc * TC_KC * 2));
-    NDB_CHECK(ix->ctcs.qnorm.reserve((size_t) nqpad * 4));
-    NDB_CHECK(tc_block_queries(Q_dev, nullptr, 0, nq, nqpad, ix->dim, nkc, ix->ctcs.qb.as<__nv_bfloat16>(), ix->ctcs.qnorm.as<float>(), s));
-    // ranges: enough partial lists that their union holds np + a margin of complete entries (np <= 16: the two
-    // column halves of one range; else four ranges), and about two items per SM when the store is long enough
-    const uint32_t sms = (uint32_t) ctx().sm_count;
-    uint32_t nranges = std::max<uint32_t>(np <= 16 ? 1u : 4u, nqt ? (2 * sms) / nqt : 1u);
-    nranges = std::max<uint32_t>(1u, std::min<uint32_t>(nranges, (uint32_t) st.ntiles));
-    uint32_t tpr = (uint32_t) ((st.ntiles + nranges - 1) / nranges);
-    if (tpr > (uint32_t) TC_PACKED_MAX_TILES) tpr = TC_PACKED_MAX_TILES;
-    nranges = (uint32_t) ((st.ntiles + tpr - 1) / tpr);
-    const uint32_t nitems = nqt * nranges;
-    if (ix->citems_nq != nq || ix->citems_tpr != tpr || ix->citems_nranges != nranges) {
-        std::vector<TcItem> items(nitems);
-        for (uint32_t i = 0; i < nitems; i++) {
-            const uint32_t qt = i % nqt, xr = i / nqt;
-            TcItem &it = items[i];
-            it.qtile = qt;
-            it.t0 = xr * tpr;
-            it.t1 = std::min<uint32_t>((uint32_t) st.ntiles, it.t0 + tpr);
-            it.nq = (uint32_t) std::min<int>(TC_M, nq - (int) qt * TC_M);
-            it.out_base = qt * TC_M * nranges * 2 + xr * 2;
-            it.out_stride = nranges * 2;
-            it.rep = 1;
-            it.pad_ = 0;
-        }
-        NDB_CHECK(ix->ctcs.items.reserve((size_t) nitems * sizeof(TcItem)));
-        NDB_CUDA(cudaMemcpyAsync(ix->ctcs.items.p, items.data(), (size_t) nitems * sizeof(TcItem), cudaMemcpyHostToDevice, s));
-        NDB_CUDA(cudaStreamSynchronize(s));        // `items` is a host temporary; once per batch shape
-        ix->citems_nq = nq; ix->citems_tpr = tpr; ix->citems_nranges = nranges;
-    }
-    const int nparts = (int) nranges * 2;
-    NDB_CHECK(ix->ctcs.pdist.reserve((size_t) nqpad * nparts * kc * 4));
-    NDB_CHECK(ix->ctcs.pslot.reserve((size_t) nqpad * nparts * kc * 4));
-    TcParams p;
-    memset(&p, 0, sizeof(p));
-    p.xb = st.xb.as<__nv_bfloat16>();
-    p.xnorm = st.xnorm.as<float>();
-    p.qb = ix->ctcs.qb.as<__nv_bfloat16>();
-    p.qnorm = ix->ctcs.qnorm.as<float>();
-    p.nkc = nkc;
-    p.k = kc;
-    p.items = ix->ctcs.items.as<TcItem>();
-    p.nitems = nitems;
-    p.pdist = ix->ctcs.pdist.as<float>();
-    p.pslot = ix->ctcs.pslot.as<uint32_t>();
-    p.packed = 1;
-    NDB_CHECK(tc_launch(p, NDB_L2, kc, s));
-    unsigned long long *ctr = ix->cert_counters.as<unsigned long long>() + 2;
-    const unsigned grid = (unsigned) ((nq + 3) / 4);
-    if (np <= 16)
-        ivf_coarse_cert_kernel<1><<<grid, 128, 0, s>>>(p.pdist, p.pslot, nparts, kc, ix->kw.C.as<float>(), Q_dev, nq, L, ix->dim, np,
-                                                       st.stats.as<float>(), ix->probe.as<uint32_t>(), ix->cdist.as<float>(),
-                                                       ix->fb_clist.as<uint32_t>(), ctr);
-    else
-        ivf_coarse_cert_kernel<2><<<grid, 128, 0, s>>>(p.pdist, p.pslot, nparts, kc, ix->kw.C.as<float>(), Q_dev, nq, L, ix->dim, np,
-                                                       st.stats.as<float>(), ix->probe.as<uint32_t>(), ix->cdist.as<float>(),
-                                                       ix->fb_clist.as<uint32_t>(), ctr);
-    const size_t fsm = (size_t) ix->dimp * 4 + 256 * 4 + 256 * 8;
-    ivf_coarse_fallback_kernel<<<(unsigned) std::min<int>(nq, 2 * (int) sms), 256, fsm, s>>>(ix->fb_clist.as<uint32_t>(), ctr, ix->kw.C.as<float>(), Q_dev, L,
-                                                                                      ix->dim, np, ix->probe.as<uint32_t>(), ix->cdist.as<float>());
-    count_launch(2);
-    NDB_CUDA(cudaGetLastError());
-    return NDB_B200_OK;
-}
-
 // NDB_ARITH_TENSOR search: coarse quantizer and list scans on the tensor cores (bf16 products, fp32
 // accumulation) select k + margin candidates per query, which are then re-ranked in fp32.
 static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np, int k, float *dist_dev, int64_t *ids_dev,
@@ -605,10 +524,11 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     NDB_CHECK(ix->cert_counters.reserve(64));
     NDB_CHECK(ix->fb_list.reserve((size_t) nq * 4));
     NDB_CHECK(ix->fb_tau.reserve((size_t) nq * 4));
-    NDB_CHECK(ix->fb_clist.reserve((size_t) nq * 4));
     NDB_CUDA(cudaMemsetAsync(ix->cert_counters.p, 0, 64, s));
-    if (np <= 32 && ix->dim <= 4096) {
-        NDB_CHECK(ivf_coarse_tensor(ix, Q_dev, nq, np, s));
+    if (np <= 32 && ix->dim <= TC_MAX_DIM) {
+        NDB_CHECK(nearest_centroids_tensor(ix->kw.cs, ix->kw.C.as<float>(), ix->kw.cstore.as<float>(), L, ix->dim, ix->dimp, Q_dev, nq, np,
+                                           false, ix->probe.as<uint32_t>(), ix->cdist.as<float>(),
+                                           ix->cert_counters.as<unsigned long long>() + 2, s));
     } else {
         NDB_CHECK(ivf_coarse(ix, Q_dev, nq, np, NDB_ARITH_IVF_F32, s));
     }
@@ -780,7 +700,7 @@ static int ivf_vnorm(ndb_b200_ivf *ix, int arith, const void **out, cudaStream_t
 // nearest centroid per row (ivfinsert :906-935): sqrtf'd L2, strict <, lowest index
 static int ivf_assign_dev(ndb_b200_ivf *ix, const float *d_rows, int64_t n, int *d_out, cudaStream_t s)
 {
-    return kmeans_assign_dev(ix->kw, d_rows, n, ix->dim, ix->nlists, NDB_L2, d_out, s);
+    return kmeans_assign_dev(ix->kw, d_rows, n, ix->dim, ix->nlists, NDB_L2, d_out, s);      // tensor cores when the centroid set is large
 }
 
 // probe lists per query into ix->probe ([nq][np] uint32, INVALID_SLOT = none)
@@ -851,7 +771,7 @@ static int ivf_install_centroids(ndb_b200_ivf *ix, cudaStream_t s)
     NDB_CUDA(cudaMemsetAsync(ix->kw.cstore.p, 0, bytes, s));
     NDB_CHECK(il32_scatter(ix->kw.C.as<float>(), ix->nlists, ix->dim, ix->dimp, nullptr, 0, ix->kw.cstore.as<float>(), s));
     ix->trained = true;
-    ix->ctc_ok = false;
+    ix->kw.cs.store_ok = false;
     return NDB_B200_OK;
 }
 

@@ -10,9 +10,11 @@
 // each (cluster, dimension) pair is one thread walking its members in ascending sample index.
 #include "kmeans.cuh"
 #include "scan.cuh"
+#include "cert_common.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cfloat>
+#include <algorithm>
 
 namespace ndb {
 
@@ -23,9 +25,14 @@ void kmeans_at_shutdown()
 {
     KMeansWork &w = g_shard_work;
     for (DevBuf *b : {&w.X, &w.C, &w.cstore, &w.assign, &w.keys_sorted, &w.vals_in, &w.vals_sorted, &w.start, &w.counts,
-                      &w.cub_tmp, &w.dcost, &w.cost, &w.scr.pdist, &w.scr.pslot, &w.scr.counter, &w.scr.qnorm})
+                      &w.cub_tmp, &w.dcost, &w.cost, &w.scr.pdist, &w.scr.pslot, &w.scr.counter, &w.scr.qnorm, &w.cs.store.xb,
+                      &w.cs.store.xnorm, &w.cs.store.xrinv, &w.cs.store.xpad0, &w.cs.store.stats, &w.cs.scr.qb, &w.cs.scr.qnorm,
+                      &w.cs.scr.qerr, &w.cs.scr.pdist, &w.cs.scr.pslot, &w.cs.scr.items, &w.cs.fb_list, &w.cs.counters, &w.cs.probe,
+                      &w.cs.cdist})
         b->release();
     g_shard_dcost.release();
+    w.cs.store_ok = false;
+    w.cs.items_nq = -1;
 }
 
 __global__ void iota_u32_kernel(uint32_t *out, int64_t n)
@@ -124,6 +131,97 @@ static int centroids_to_store(KMeansWork &w, int k, int dim, int dimp, cudaStrea
     return il32_scatter(w.C.as<float>(), k, dim, dimp, nullptr, 0, w.cstore.as<float>(), s);
 }
 
+// ---- nearest centroids on the tensor cores, certified -------------------------------------------------------
+// The centroid store is scanned in `nranges` tile ranges; each (row, range, column half) leaves its kc best bf16 keys
+// and ivf_coarse_cert_kernel re-evaluates the best of their union in the reference's arithmetic, certifying the
+// answer or sending the row to the exact kernel (cert_common.cuh).
+__global__ void probe_to_assign_kernel(const uint32_t *__restrict__ probe, int *__restrict__ assign, int64_t n)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) assign[i] = probe[i] == INVALID_SLOT ? 0 : (int) probe[i];
+}
+
+int nearest_centroids_tensor(CentroidSearch &cs, const float *C_rowmajor, const float *cstore_il32, int L, int dim, int dimp,
+                             const float *Q_dev, int nq, int np, bool squared, uint32_t *probe, float *cdist,
+                             unsigned long long *counters, cudaStream_t s)
+{
+    NDB_REQUIRE(np >= 1 && np <= 32 && dim <= TC_MAX_DIM, NDB_B200_EINVAL, "nearest_centroids_tensor: np %d / dim %d out of range", np, dim);
+    if (!cs.store_ok) {
+        NDB_CHECK(tc_build_store(cs.store, cstore_il32, L, dim, dimp, s));
+        cs.store_ok = true;
+    }
+    const TcStore &st = cs.store;
+    const int nkc = st.nkc, kc = TC_KMAX;
+    const uint32_t nqt = (uint32_t) ((nq + TC_M - 1) / TC_M);
+    const int nqpad = (int) nqt * TC_M;
+    NDB_CHECK(cs.scr.qb.reserve((size_t) nqpad * nkc * TC_KC * 2));
+    NDB_CHECK(cs.scr.qnorm.reserve((size_t) nqpad * 4));
+    NDB_CHECK(tc_block_queries(Q_dev, nullptr, 0, nq, nqpad, dim, nkc, cs.scr.qb.as<__nv_bfloat16>(), cs.scr.qnorm.as<float>(), s));
+    // ranges: enough partial lists that their union holds np + a margin of complete entries (np <= 16: the two column
+    // halves of one range; else four ranges), and about two items per SM when the store is long enough
+    const uint32_t sms = (uint32_t) ctx().sm_count;
+    uint32_t nranges = std::max<uint32_t>(np <= 16 ? 1u : 4u, nqt ? (2 * sms) / nqt : 1u);
+    nranges = std::max<uint32_t>(1u, std::min<uint32_t>(nranges, (uint32_t) st.ntiles));
+    uint32_t tpr = (uint32_t) ((st.ntiles + nranges - 1) / nranges);
+    if (tpr > (uint32_t) TC_PACKED_MAX_TILES) tpr = TC_PACKED_MAX_TILES;
+    nranges = (uint32_t) ((st.ntiles + tpr - 1) / tpr);
+    const uint32_t nitems = nqt * nranges;
+    if (cs.items_nq != nq || cs.items_tpr != tpr || cs.items_nranges != nranges || cs.items_ntiles != st.ntiles) {
+        std::vector<TcItem> items(nitems);
+        for (uint32_t i = 0; i < nitems; i++) {
+            const uint32_t qt = i % nqt, xr = i / nqt;
+            TcItem &it = items[i];
+            it.qtile = qt;
+            it.t0 = xr * tpr;
+            it.t1 = std::min<uint32_t>((uint32_t) st.ntiles, it.t0 + tpr);
+            it.nq = (uint32_t) std::min<int>(TC_M, nq - (int) qt * TC_M);
+            it.out_base = qt * TC_M * nranges * 2 + xr * 2;
+            it.out_stride = nranges * 2;
+            it.rep = 1;
+            it.pad_ = 0;
+        }
+        NDB_CHECK(cs.scr.items.reserve((size_t) nitems * sizeof(TcItem)));
+        NDB_CUDA(cudaMemcpyAsync(cs.scr.items.p, items.data(), (size_t) nitems * sizeof(TcItem), cudaMemcpyHostToDevice, s));
+        NDB_CUDA(cudaStreamSynchronize(s));        // `items` is a host temporary; once per batch shape
+        cs.items_nq = nq; cs.items_tpr = tpr; cs.items_nranges = nranges; cs.items_ntiles = st.ntiles;
+    }
+    const int nparts = (int) nranges * 2;
+    NDB_CHECK(cs.scr.pdist.reserve((size_t) nqpad * nparts * kc * 4));
+    NDB_CHECK(cs.scr.pslot.reserve((size_t) nqpad * nparts * kc * 4));
+    NDB_CHECK(cs.fb_list.reserve((size_t) nq * 4));
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.xb = st.xb.as<__nv_bfloat16>();
+    p.xnorm = st.xnorm.as<float>();
+    p.qb = cs.scr.qb.as<__nv_bfloat16>();
+    p.qnorm = cs.scr.qnorm.as<float>();
+    p.nkc = nkc;
+    p.k = kc;
+    p.items = cs.scr.items.as<TcItem>();
+    p.nitems = nitems;
+    p.pdist = cs.scr.pdist.as<float>();
+    p.pslot = cs.scr.pslot.as<uint32_t>();
+    p.packed = 1;
+    NDB_CHECK(tc_launch(p, NDB_L2, kc, s));
+    const unsigned grid = (unsigned) ((nq + 3) / 4);
+    const size_t fsm = (size_t) dimp * 4 + 256 * 4 + 256 * 8;
+    const unsigned fgrid = (unsigned) std::min<int>(nq, 2 * (int) sms);
+    using PS = Arith<NDB_L2, NDB_ARITH_IVF_F32>;
+    using PQ = Arith<METRIC_L2SQ, NDB_ARITH_IVF_F32>;
+#define NDB_CC(KRC, P)                                                                                                      \
+    do {                                                                                                                    \
+        ivf_coarse_cert_kernel<KRC, P><<<grid, 128, 0, s>>>(p.pdist, p.pslot, nparts, kc, C_rowmajor, Q_dev, nq, L, dim, np,   \
+                                                            st.stats.as<float>(), probe, cdist, cs.fb_list.as<uint32_t>(), counters); \
+        ivf_coarse_fallback_kernel<P><<<fgrid, 256, fsm, s>>>(cs.fb_list.as<uint32_t>(), counters, C_rowmajor, Q_dev, L, dim, np, probe, cdist); \
+    } while (0)
+    if (np <= 16) { if (squared) NDB_CC(1, PQ); else NDB_CC(1, PS); }
+    else { if (squared) NDB_CC(2, PQ); else NDB_CC(2, PS); }
+#undef NDB_CC
+    count_launch(2);
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
+}
+
 // assign[i] = nearest centroid of row i (dX row-major); metric selects the squared (k-means,
 // :2274-2294) or the sqrtf'd (ivfinsert, :906-935) comparison
 int kmeans_assign_dev(KMeansWork &w, const float *dX, int64_t n, int dim, int k, int metric, int *d_assign,
@@ -131,6 +229,28 @@ int kmeans_assign_dev(KMeansWork &w, const float *dX, int64_t n, int dim, int k,
 {
     const int dimp = round_up(dim, 4);
     NDB_CHECK(centroids_to_store(w, k, dim, dimp, s));
+    // Large centroid sets: GEMM-form distances on the tensor cores, certified per row (cert_common.cuh) -- the
+    // assignment is the reference loop's (strict <, lowest index), only found faster.  NDB_ASSIGN_FP32=1 keeps the
+    // fp32 scan (measurement switch).
+    static const bool force_fp32 = getenv("NDB_ASSIGN_FP32") != nullptr;
+    if (k >= 256 && dim <= TC_MAX_DIM && !force_fp32) {
+        w.cs.store_ok = false;                                  // the centroids change between calls
+        NDB_CHECK(w.cs.counters.reserve(64));
+        NDB_CUDA(cudaMemsetAsync(w.cs.counters.p, 0, 64, s));
+        const int64_t tchunk = 1 << 20;
+        for (int64_t off = 0; off < n; off += tchunk) {
+            const int m = (int) (n - off < tchunk ? n - off : tchunk);
+            NDB_CHECK(w.cs.probe.reserve((size_t) m * 4));
+            NDB_CHECK(w.cs.cdist.reserve((size_t) m * 4));
+            NDB_CHECK(nearest_centroids_tensor(w.cs, w.C.as<float>(), w.cstore.as<float>(), k, dim, dimp, dX + (size_t) off * dim, m, 1,
+                                               metric == METRIC_L2SQ, w.cs.probe.as<uint32_t>(), w.cs.cdist.as<float>(),
+                                               w.cs.counters.as<unsigned long long>(), s));
+            probe_to_assign_kernel<<<(unsigned) ((m + 255) / 256), 256, 0, s>>>(w.cs.probe.as<uint32_t>(), d_assign + off, m);
+            count_launch();
+            NDB_CUDA(cudaGetLastError());
+        }
+        return NDB_B200_OK;
+    }
     const int64_t chunk = 1 << 22;
     for (int64_t off = 0; off < n; off += chunk) {
         const int m = (int) (n - off < chunk ? n - off : chunk);

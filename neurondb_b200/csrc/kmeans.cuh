@@ -1,13 +1,35 @@
 // kmeans.cuh -- shared declarations for the k-means / assignment kernels (kmeans.cu).
 #pragma once
 #include "layout.cuh"
+#include "tc.cuh"
 
 namespace ndb {
+
+// nearest centroids on the tensor cores, certified (cert_common.cuh): blocked bf16 copy of the centroids, scratch,
+// work items cached per batch shape, the queries sent to the exact kernel and the counters [0] of them, [1] exact evaluations
+struct CentroidSearch {
+    TcStore store;
+    TcScratch scr;
+    DevBuf fb_list, counters, probe, cdist;
+    bool store_ok = false;
+    int items_nq = -1;
+    uint32_t items_tpr = 0, items_nranges = 0;
+    int64_t items_ntiles = -1;
+};
 
 struct KMeansWork {
     DevBuf X, C, cstore, assign, keys_sorted, vals_in, vals_sorted, start, counts, cub_tmp, dcost, cost;
     ScanScratch scr;
+    CentroidSearch cs;
 };
+
+// probe[nq][np] / cdist[nq][np] = the np nearest of the L centroids (C row-major, cstore its IL32 copy) of every row of
+// Q_dev, ordered by (distance, index) in the reference's fp32 arithmetic: sqrtf'd L2 (ivfSelectClusters :1597-1717,
+// ivfinsert :906-935) or, with `squared`, k-means' squared L2 (:2255-2294).  np <= 32.  The centroid store is rebuilt
+// when cs.store_ok is false.  counters (2 x u64, device) accumulate [0] exact-kernel queries, [1] exact evaluations.
+int nearest_centroids_tensor(CentroidSearch &cs, const float *C_rowmajor, const float *cstore_il32, int L, int dim, int dimp,
+                             const float *Q_dev, int nq, int np, bool squared, uint32_t *probe, float *cdist,
+                             unsigned long long *counters, cudaStream_t s);
 
 void kmeans_at_shutdown();
 

@@ -175,3 +175,29 @@ def test_wrappers_report_dimension_errors(ndb):
     with pytest.raises(ndb.NdbError) as e:
         ds.knn(W.gaussian(2, 5, 1), 3)
     assert e.value.code == -5
+
+
+@pytest.mark.parametrize("n,dim,lists", [(60000, 128, 1024), (30000, 96, 512), (20000, 40, 300), (5000, 260, 256)])
+def test_list_assignment_on_the_tensor_cores_equals_the_oracle(ndb, orc, n, dim, lists):
+    """ivfinsert's nearest-centroid loop (ivf_am.c:906-935) for centroid sets large enough to go through the tensor
+    cores (GEMM form, certified per row): the list of EVERY row equals the oracle's sequential fp32 loop -- strict <,
+    lowest index -- on ordinary (not bf16-representable) rows, including rows that coincide with a centroid."""
+    X = W.mixture(n, dim, lists // 2, 5000 + lists)
+    ix = ndb.IvfIndex(dim, lists)
+    Cn = np.ascontiguousarray(X[:lists] + 0)           # centroids = data rows: exact zero distances, duplicates of clusters
+    Cn[7] = Cn[3]                                      # two identical centroids: the lower index must win
+    ix.set_centroids(Cn)
+    got = ix.assign(X)
+    want = orc.ivf_assign(X, Cn)
+    assert np.array_equal(got, want), "%d of %d rows differ" % ((got != want).sum(), n)
+    assert not np.any(got == 7)
+
+
+def test_kmeans_on_the_tensor_cores_equals_the_oracle(ndb, orc):
+    """kmeans_run (ivf_am.c:2117-2159) with k >= 256: assignment by squared L2 on the tensor cores, certified -- centroids,
+    counts, iterations and cost stay bit-identical to the oracle (any wrong assignment would change the f32 sums)."""
+    X = W.mixture(6000, 64, 300, 77)
+    C, assign, counts, iters, cost = ndb.kmeans_train(X, 300)
+    oC, oassign, ocounts, oiters, ocost = orc.kmeans_train(X, 300)
+    assert iters == oiters and np.array_equal(assign, oassign) and np.array_equal(counts, ocounts)
+    assert np.array_equal(BITS(C), BITS(oC)) and np.float32(cost) == np.float32(ocost)
