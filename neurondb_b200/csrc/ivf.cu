@@ -841,7 +841,6 @@ int ndb_b200_ivf_insert(ndb_b200_ivf *ix, const float *rows, const int64_t *ids,
     NDB_CHECK(require_init());
     NDB_REQUIRE(ix && rows && n > 0, NDB_B200_EINVAL, "ivf_insert: NULL or empty input");
     NDB_REQUIRE(ix->trained, NDB_B200_ESTATE, "ivf_insert: index has no centroids block");
-    NDB_REQUIRE(find_nonfinite(rows, n * ix->dim) < 0, NDB_B200_EVECTOR, "ivf_insert: NaN/Inf in rows");
     cudaStream_t s = ctx().stream;
     const int64_t chunk = 1 << 20;
     std::vector<int> assign;
@@ -849,18 +848,51 @@ int ndb_b200_ivf_insert(ndb_b200_ivf *ix, const float *rows, const int64_t *ids,
     // default ids number every row ever passed to this handle, kept or not: the ranks of a list-sharded index see the
     // same rows in the same order, so they agree on the ids whatever each of them keeps
     const int64_t next_default_id = ix->inserted_total;
+    // NaN / Inf rows are rejected (vector_distance.c:55-73) for the whole batch: the check runs on the device, on the
+    // staged chunks, and a failure rolls the handle back to where it was
+    const int64_t nrows0 = ix->nrows;
+    const size_t nid0 = ix->row_id.size();
+    const bool all_mine = ix->world == 1;
+    if (all_mine) NDB_CHECK(ix->arena.grow((size_t) (ix->nrows + n) * ix->dim * 4, (size_t) ix->nrows * ix->dim * 4, s));
+    unsigned long long *h_bad = reinterpret_cast<unsigned long long *>(static_cast<char *>(ctx().pinned) + 512);
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t m = n - off < chunk ? n - off : chunk;
-        NDB_CHECK(ix->tmp_rows.reserve((size_t) m * ix->dim * 4));
         NDB_CHECK(ix->tmp_assign.reserve((size_t) m * 4));
-        NDB_CUDA(cudaMemcpyAsync(ix->tmp_rows.p, rows + (size_t) off * ix->dim, (size_t) m * ix->dim * 4, cudaMemcpyHostToDevice, s));
-        NDB_CHECK(ivf_assign_dev(ix, ix->tmp_rows.as<float>(), m, ix->tmp_assign.as<int>(), s));
+        // one rank holds every list: the chunk is staged straight into the arena
+        float *d_rows;
+        if (all_mine) {
+            d_rows = ix->arena.as<float>() + (size_t) ix->nrows * ix->dim;
+        } else {
+            NDB_CHECK(ix->tmp_rows.reserve((size_t) m * ix->dim * 4));
+            d_rows = ix->tmp_rows.as<float>();
+        }
+        NDB_CUDA(cudaMemcpyAsync(d_rows, rows + (size_t) off * ix->dim, (size_t) m * ix->dim * 4, cudaMemcpyHostToDevice, s));
+        NDB_CHECK(validate_into(d_rows, m * ix->dim, ctx().d_badidx, s));
+        NDB_CUDA(cudaMemcpyAsync(h_bad, ctx().d_badidx, 8, cudaMemcpyDeviceToHost, s));
+        NDB_CHECK(ivf_assign_dev(ix, d_rows, m, ix->tmp_assign.as<int>(), s));
         assign.resize(m);
         NDB_CUDA(cudaMemcpyAsync(assign.data(), ix->tmp_assign.p, (size_t) m * 4, cudaMemcpyDeviceToHost, s));
         NDB_CUDA(cudaStreamSynchronize(s));
+        if (*h_bad != ~0ull) {
+            ix->nrows = nrows0;
+            ix->row_id.resize(nid0);
+            ix->row_list.resize(nid0);
+            set_error("ivf_insert: NaN/Inf in row %lld", (long long) (off + (int64_t) (*h_bad / (unsigned long long) ix->dim)));
+            return NDB_B200_EVECTOR;
+        }
+        if (out_list) memcpy(out_list + off, assign.data(), (size_t) m * 4);
+        if (all_mine) {
+            ix->row_list.insert(ix->row_list.end(), assign.begin(), assign.end());
+            const size_t base = ix->row_id.size();
+            ix->row_id.resize(base + m);
+            if (ids) memcpy(ix->row_id.data() + base, ids + off, (size_t) m * 8);
+            else for (int64_t i = 0; i < m; i++) ix->row_id[base + i] = next_default_id + off + i;
+            ix->nrows += m;
+            ix->dirty = true;
+            continue;
+        }
         keep.clear();
         for (int64_t i = 0; i < m; i++) {
-            if (out_list) out_list[off + i] = assign[i];
             if (assign[i] % ix->world != ix->rank) continue;      // list owned by another rank
             keep.push_back((uint32_t) i);
             ix->row_list.push_back(assign[i]);
