@@ -131,6 +131,13 @@ int ndb_b200_distance_pairs(int metric, int arith, const float *A, const float *
 int ndb_b200_distance_rows(int metric, int arith, const float *X, int64_t n, int dim,
                            const float *q, float *out);
 
+/* vector_l2_distance_batch / vector_cosine_distance_batch / vector_inner_product_distance_batch
+ * (src/vector/vector_batch.c:37-420): rows = n x dim floats, dims[i] = the dimension of array element i (0 = a NULL
+ * element).  An element whose dimension differs from `dim` (the query's) yields nulls[i] = 1 (:123-150); the others
+ * get l2_distance / cosine_distance / -inner_product_distance (= +dot) in the operators' fp64 arithmetic. */
+int ndb_b200_vector_distance_batch(int metric, const float *rows, const int *dims, int64_t n, int dim, const float *query,
+                                   float *out, uint8_t *nulls);
+
 /* ---- dataset: the heap column a SeqScan reads ------------------------------- */
 int ndb_b200_dataset_create(int dim, ndb_b200_dataset **out);
 int ndb_b200_dataset_append(ndb_b200_dataset *ds, const float *rows, const int64_t *ids, int64_t n);
@@ -202,6 +209,10 @@ int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np
 int ndb_b200_ivf_search_begin(ndb_b200_ivf *ix, const float *Q, int nq, int nprobe, int k, int mode,
                               int arith, float *dist, int64_t *ids, int *ticket);
 int ndb_b200_ivf_search_end(ndb_b200_ivf *ix, int ticket);
+/* ivf_knn_search_gpu(index, query, k, nprobe) (src/gpu/common/gpu_sql.c:931-1456): the SQL function's argument
+ * checks and its (id, distance) rows; *nresults <= k rows are valid.  k, nprobe <= 128 here. */
+int ndb_b200_ivf_knn_search_gpu(ndb_b200_ivf *ix, const float *query, int dim, int k, int nprobe, int64_t *ids, float *dist,
+                                int *nresults);
 /* NDB_ARITH_TENSOR searches are certified (csrc/ivf_cert.cuh): the bf16 tensor-core scan only proposes
  * candidates; each query's answer is accepted when a rounding-error bound proves that no row outside the
  * re-evaluated candidates can enter the reference's top k, and recomputed exactly (every row of the probed
@@ -258,6 +269,9 @@ int ndb_b200_hnsw_search_dev(ndb_b200_hnsw *h, const float *Q_dev, int nq, int s
 /* replicas: the graph does not shard; the rank that built it broadcasts it (ncclBroadcast) and
  * every rank then answers its own share of the queries.  Collective over the communicator's ranks. */
 int ndb_b200_hnsw_broadcast(ndb_b200_hnsw *h, int root);
+/* hnsw_knn_search_gpu(index, query, k, ef_search) (src/gpu/common/gpu_sql.c:498-930): argument checks + result */
+int ndb_b200_hnsw_knn_search_gpu(ndb_b200_hnsw *h, const float *query, int dim, int k, int ef_search, int64_t *ids, float *dist,
+                                 int *nresults);
 /* distance evaluations of the last search batch (for the bytes-per-query roofline) */
 int64_t ndb_b200_hnsw_last_evals(const ndb_b200_hnsw *h);
 

@@ -106,6 +106,9 @@ SIGNATURES = {
     "ndb_b200_keys_from_bits": (_i, [_p, _i64, _i, _p]),
     "ndb_b200_keys_from_bits_dev": (_i, [_p, _i64, _i, _p, _p]),
     "ndb_b200_keys_from_sparse": (_i, [_p, _p, _p, _i64, _i, _p]),
+    "ndb_b200_vector_distance_batch": (_i, [_i, _p, _p, _i64, _i, _p, _p, _p]),
+    "ndb_b200_ivf_knn_search_gpu": (_i, [_p, _p, _i, _i, _i, _p, _p, C.POINTER(_i)]),
+    "ndb_b200_hnsw_knn_search_gpu": (_i, [_p, _p, _i, _i, _i, _p, _p, C.POINTER(_i)]),
     "ndb_b200_ivf_dim": (_i, [_p]),
     "ndb_b200_ivf_prepare": (_i, [_p, _i]),
     "ndb_b200_ivf_cert_stats": (_i, [_p, _p]),

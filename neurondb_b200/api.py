@@ -76,6 +76,27 @@ def distance_rows(X, q, metric=L2, arith=ARITH_OP_F64):
     return out
 
 
+def vector_distance_batch(vectors, query, metric=L2):
+    """vector_{l2,cosine,inner_product}_distance_batch(vector[], vector) (vector_batch.c:37-420): `vectors` is a list
+    whose elements are 1-d arrays or None; returns (distances float32[n], nulls bool[n])."""
+    q = f32(query).reshape(-1)
+    dim = q.shape[0]
+    n = len(vectors)
+    rows = np.zeros((max(n, 1), dim), np.float32)
+    dims = np.zeros(max(n, 1), np.int32)
+    for i, v in enumerate(vectors):
+        if v is None:
+            continue
+        v = f32(v).reshape(-1)
+        dims[i] = v.shape[0]
+        if v.shape[0] == dim:
+            rows[i] = v
+    out = np.zeros(max(n, 1), np.float32)
+    nulls = np.zeros(max(n, 1), np.uint8)
+    check(L.load().ndb_b200_vector_distance_batch(metric, ptr(rows), ptr(dims), n, dim, ptr(q), ptr(out), ptr(nulls)))
+    return out[:n], nulls[:n].astype(bool)
+
+
 # ---- ndb_gpu_backend launchers (neurondb_gpu_backend.h:54-79) -----------------------------------
 def launch_l2_distance(A, B):
     A, B = f32(A), f32(B)
@@ -388,6 +409,15 @@ class IvfIndex(_Handle):
                                                ptr(ids_ptr), ptr(stream)))
 
 
+    def knn_search_gpu(self, query, k, nprobe=10):
+        """ivf_knn_search_gpu(index, query, k, nprobe) (gpu_sql.c:931): (ids, distances) of the rows found."""
+        q = f32(query).reshape(-1)
+        ids = np.empty(max(k, 1), np.int64)
+        d = np.empty(max(k, 1), np.float32)
+        nres = C.c_int()
+        check(L.load().ndb_b200_ivf_knn_search_gpu(self.h, ptr(q), q.shape[0], k, nprobe, ptr(ids), ptr(d), C.byref(nres)))
+        return ids[:nres.value], d[:nres.value]
+
     def search_sharded_dev(self, q_ptr, nq, dist_ptr, ids_ptr, nprobe=10, k=10, mode=IVF_FULL, arith=ARITH_IVF_F32,
                            stream=None):
         """Local search + all-gather of packed (dist, id) records + device merge (ndb_b200_ivf_search_sharded_dev)."""
@@ -466,6 +496,15 @@ class HnswIndex(_Handle):
 
     def last_evals(self):
         return int(L.load().ndb_b200_hnsw_last_evals(self.h))
+
+    def knn_search_gpu(self, query, k, ef_search=100):
+        """hnsw_knn_search_gpu(index, query, k, ef_search) (gpu_sql.c:498): (ids, distances) of the rows found."""
+        q = f32(query).reshape(-1)
+        ids = np.empty(max(k, 1), np.int64)
+        d = np.empty(max(k, 1), np.float32)
+        nres = C.c_int()
+        check(L.load().ndb_b200_hnsw_knn_search_gpu(self.h, ptr(q), q.shape[0], k, ef_search, ptr(ids), ptr(d), C.byref(nres)))
+        return ids[:nres.value], d[:nres.value]
 
     def broadcast(self, n=None, root=0):
         """Replicas: the rank that built the graph sends it to the others (collective)."""

@@ -529,6 +529,36 @@ int ndb_b200_distance_rows(int metric, int arith, const float *X, int64_t n, int
     return pairs_host(metric, arith, false, X, q, out, n, dim, true, true);
 }
 
+// vector_l2_distance_batch / vector_cosine_distance_batch / vector_inner_product_distance_batch
+// (src/vector/vector_batch.c:37-420): an array of vectors against one query, in the operators' fp64 arithmetic
+// (the functions call l2_distance / cosine_distance / -inner_product_distance, :152,278,404).  An element that is
+// NULL, or whose dimension is invalid or differs from the query's, yields NULL (:123-150); an empty array and an
+// invalid query dimension are errors (:85-88,69-73).
+int ndb_b200_vector_distance_batch(int metric, const float *rows, const int *dims, int64_t n, int dim, const float *query,
+                                   float *out, uint8_t *nulls)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(rows && dims && query && out && nulls, NDB_B200_EINVAL, "vector array and query vector must not be NULL");
+    NDB_REQUIRE(n > 0, NDB_B200_EINVAL, "vector array must not be empty");
+    NDB_REQUIRE(dim > 0 && dim <= 16000, NDB_B200_EINVAL, "invalid query vector dimension: %d", dim);
+    NDB_REQUIRE(metric >= NDB_L2 && metric <= NDB_IP, NDB_B200_EINVAL, "distance_batch: unknown metric %d", metric);
+    // the valid elements are packed, evaluated in one launch and scattered back
+    std::vector<int64_t> valid;
+    valid.reserve((size_t) n);
+    for (int64_t i = 0; i < n; i++) {
+        nulls[i] = dims[i] == dim ? 0 : 1;
+        out[i] = 0.0f;
+        if (!nulls[i]) valid.push_back(i);
+    }
+    if (valid.empty()) return NDB_B200_OK;
+    if ((int64_t) valid.size() == n) return pairs_host(metric, NDB_ARITH_OP_F64, false, rows, query, out, n, dim, true, true);
+    std::vector<float> packed(valid.size() * (size_t) dim), res(valid.size());
+    for (size_t j = 0; j < valid.size(); j++) memcpy(&packed[j * dim], rows + (size_t) valid[j] * dim, (size_t) dim * 4);
+    NDB_CHECK(pairs_host(metric, NDB_ARITH_OP_F64, false, packed.data(), query, res.data(), (int64_t) valid.size(), dim, true, true));
+    for (size_t j = 0; j < valid.size(); j++) out[valid[j]] = res[j];
+    return NDB_B200_OK;
+}
+
 // ---- ndb_gpu_backend launchers (stream == NULL => synchronous, out valid on return) ----------
 int ndb_b200_launch_l2_distance(const float *A, const float *B, float *out, int n, int d, void *stream)
 {

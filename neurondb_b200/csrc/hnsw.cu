@@ -1053,6 +1053,26 @@ int ndb_b200_hnsw_search(ndb_b200_hnsw *h, const float *Q, int nq, int strategy,
 
 // ---- relation loader: meta page + one HnswNodeData item per 8 KB page (hnsw_am.c:108-181) -----
 // node id = block - 1; neighbour slots hold block numbers and are rebased the same way.
+// hnsw_knn_search_gpu(index_name, query, k, ef_search default 100) (src/gpu/common/gpu_sql.c:498-930): the SQL
+// function's argument checks (:556-580) and its result over the resident graph; strategy 1 as the access method.
+int ndb_b200_hnsw_knn_search_gpu(ndb_b200_hnsw *h, const float *query, int dim, int k, int ef_search, int64_t *ids, float *dist,
+                                 int *nresults)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(h, NDB_B200_EINVAL, "hnsw_knn_search_gpu: index cannot be NULL");
+    NDB_REQUIRE(query && ids && dist && nresults, NDB_B200_EINVAL, "hnsw_knn_search_gpu: query vector cannot be NULL");
+    NDB_REQUIRE(k > 0 && k <= 10000, NDB_B200_EINVAL, "hnsw_knn_search_gpu: k must be between 1 and 10000");
+    NDB_REQUIRE(ef_search > 0 && ef_search <= 10000, NDB_B200_EINVAL, "hnsw_knn_search_gpu: ef_search must be between 1 and 10000");
+    NDB_REQUIRE(dim > 0 && dim == h->dim, NDB_B200_EDIM, "hnsw_knn_search_gpu: invalid query dimension %d", dim);
+    NDB_REQUIRE(k <= 128, NDB_B200_EINVAL, "hnsw_knn_search_gpu: k > 128 is not supported by this library (k = %d)", k);
+    const int ef = ef_search < k ? k : ef_search;
+    NDB_CHECK(ndb_b200_hnsw_search(h, query, 1, 1, ef, k, NDB_HNSW_BESTFIRST, dist, ids));
+    int n = 0;
+    while (n < k && ids[n] >= 0) n++;
+    *nresults = n;
+    return NDB_B200_OK;
+}
+
 int ndb_b200_hnsw_load_relation(ndb_b200_hnsw *h, const void *blocks, uint32_t nblocks)
 {
     using namespace ndb::pg;

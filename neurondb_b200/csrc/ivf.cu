@@ -942,6 +942,28 @@ int ndb_b200_ivf_prepare(ndb_b200_ivf *ix, int arith)
     return NDB_B200_OK;
 }
 
+// ivf_knn_search_gpu(index_name, query, k, nprobe default 10) (src/gpu/common/gpu_sql.c:931-1456): the SQL function's
+// argument checks (:972-991) and its result, (heap id, distance) rows in ascending distance, over the resident index.
+// The reference's version evaluates one candidate per launch_l2_distance call (:1278-1293); here it is one search.
+int ndb_b200_ivf_knn_search_gpu(ndb_b200_ivf *ix, const float *query, int dim, int k, int nprobe, int64_t *ids, float *dist,
+                                int *nresults)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ix, NDB_B200_EINVAL, "ivf_knn_search_gpu: index cannot be NULL");
+    NDB_REQUIRE(query && ids && dist && nresults, NDB_B200_EINVAL, "ivf_knn_search_gpu: query vector cannot be NULL");
+    NDB_REQUIRE(k > 0 && k <= 10000, NDB_B200_EINVAL, "ivf_knn_search_gpu: k must be between 1 and 10000");
+    NDB_REQUIRE(nprobe > 0 && nprobe <= 1000, NDB_B200_EINVAL, "ivf_knn_search_gpu: nprobe must be between 1 and 1000");
+    NDB_REQUIRE(dim == ix->dim, NDB_B200_EDIM, "ivf_knn_search_gpu: query dimension %d does not match index dimension %d", dim, ix->dim);
+    NDB_REQUIRE(k <= 128, NDB_B200_EINVAL, "ivf_knn_search_gpu: k > 128 is not supported by this library (k = %d)", k);
+    const int np = nprobe < ix->nlists ? nprobe : ix->nlists;
+    NDB_REQUIRE(np <= 128, NDB_B200_EINVAL, "ivf_knn_search_gpu: nprobe > 128 is not supported by this library (nprobe = %d)", nprobe);
+    NDB_CHECK(ndb_b200_ivf_search(ix, query, 1, np, k, NDB_IVF_FULL, NDB_ARITH_IVF_F32, dist, ids));
+    int n = 0;
+    while (n < k && ids[n] >= 0) n++;
+    *nresults = n;
+    return NDB_B200_OK;
+}
+
 // certified selection of the last NDB_ARITH_TENSOR search: out[0] = queries whose list scan went to the exact
 // kernel, out[1] = exact re-evaluations of list candidates, out[2] / out[3] = the same for the coarse quantiser,
 // out[4] = queries whose every probed row had to be evaluated, out[5] = rows evaluated by segment rescans

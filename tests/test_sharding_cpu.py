@@ -48,6 +48,57 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_striped(rank, world, port, out):
+    """bench.py's default N > 1 layout: every inverted list striped over the ranks (row i on rank i % world), one
+    all-gather of PACKED records -- per rank a [nq*k] f32 distance block padded to 16 bytes, then a [nq*k] int64 id
+    block, exactly what ndb_b200_ivf_search_sharded_dev exchanges (csrc/comm.cu RecordLayout) -- and the (dist, id)
+    merge."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, dim, L, nq, k = 5000, 12, 16, 37, 10
+    X = W.mixture(n, dim, L, 21)
+    Q = W.mixture(nq, dim, L, 22, centers_seed=21)
+    C, _, _, _, _ = O.kmeans_train(X[:1600], L)
+    mine = np.arange(rank, n, world)
+    lists = O.ivf_assign(X[mine], C, nthreads=1)              # each rank assigns only its own rows
+    off, rows = O.lists_from_assignment(lists, L)
+    d, i, _ = O.ivf_search(X[mine], C, off, rows, Q, 5, k, strategy=3, ids=mine.astype(np.int64), nthreads=1)
+    ids_off = (nq * k * 4 + 15) // 16 * 16
+    stride = (ids_off + nq * k * 8 + 15) // 16 * 16
+    rec = np.zeros(stride, np.uint8)
+    rec[:nq * k * 4] = d.reshape(-1).view(np.uint8)
+    rec[ids_off:ids_off + nq * k * 8] = i.reshape(-1).view(np.uint8)
+    allrec = [torch.empty(stride, dtype=torch.uint8) for _ in range(world)]
+    dist.all_gather(allrec, torch.from_numpy(rec))             # ONE collective
+    gd = np.stack([r.numpy()[:nq * k * 4].view(np.float32).reshape(nq, k) for r in allrec])
+    gi = np.stack([r.numpy()[ids_off:ids_off + nq * k * 8].view(np.int64).reshape(nq, k) for r in allrec])
+    md, mi = O.merge_topk(gd, gi)
+    if rank == 0:
+        la = O.ivf_assign(X, C, nthreads=1)
+        off_all, rows_all = O.lists_from_assignment(la, L)
+        wd, wi, _ = O.ivf_search(X, C, off_all, rows_all, Q, 5, k, strategy=3, nthreads=1)
+        out.put((np.array_equal(mi, wi), np.array_equal(md.view(np.uint32), wd.view(np.uint32)),
+                 np.array_equal(la[mine], lists)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_striped_lists_packed_record_exchange_equals_unsharded():
+    O.lib()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_striped, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ids_ok, dist_ok, assign_ok = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ids_ok and dist_ok and assign_ok
+
+
 def test_sharded_ivf_merge_equals_unsharded():
     O.lib()
     ctx = mp.get_context("spawn")
