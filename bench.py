@@ -58,7 +58,8 @@ WORKLOADS = {
     # brute force + k-means on bf16-valued rows, BASELINE configs[4]: 6.25 M rows per GPU (50 M on 8)
     "c5": dict(kind="brute", n_per_gpu=6_250_000, dim=128, k=10, nq=10_000, kmeans_k=4096, seed=5,
                label="C5: brute-force kNN + k-means (k=4096) over 50Mx128 bf16 rows sharded 8 x 6.25M, 10k queries"),
-    "c5s": dict(kind="brute", n_per_gpu=500_000, dim=128, k=10, nq=2_000, kmeans_k=256, seed=5,
+    "c5s": dict(kind="brute", n_per_gpu=int(os.environ.get("NDB_BENCH_C5_KMEANS_ROWS", 500_000)), dim=128, k=10, nq=2_000,
+                kmeans_k=int(os.environ.get("NDB_BENCH_C5_KMEANS_K", 256)), seed=5,
                 label="C5 (small): brute-force kNN + k-means over 500k x 128 bf16 rows per GPU"),
 }
 DEFAULT_WORKLOAD = "c4"
@@ -872,6 +873,11 @@ def run_brute(c, args, w, wname):
         assign = torch.empty(nkm, dtype=torch.int32, device="cuda")
         counts = torch.empty(kk, dtype=torch.int32, device="cuda")
         iters_cap = int(os.environ.get("NDB_BENCH_C5_KMEANS_ITERS", "3"))
+        # one untimed iteration first: the scratch of the assignment and update kernels is allocated on first use
+        Cw = C0.clone()
+        ndb.kmeans_train_sharded_dev(xk.data_ptr(), nkm, dim, kk, Cw.data_ptr(), assign.data_ptr(), counts.data_ptr(),
+                                     max_iter=1, tol=0.001, stream=c.stream)
+        torch.cuda.synchronize()
         c.barrier()
         t0 = time.perf_counter()
         its, cost = ndb.kmeans_train_sharded_dev(xk.data_ptr(), nkm, dim, kk, C0.data_ptr(), assign.data_ptr(), counts.data_ptr(),

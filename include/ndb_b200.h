@@ -165,7 +165,9 @@ int ndb_b200_kmeans_train(const float *X, int n, int d, int k, int max_iter, flo
  * of the local members (kmeans_update_centroids :2182-2213 without the division); the caller
  * all-reduces sums and counts over the ranks, divides (empty cluster -> zeros), and calls shard_cost
  * with the new centroids for its share of kmeans_compute_cost (:2218-2233), all-reducing that too.
- * All pointers are device pointers.  With a single rank the sequence is bit-identical to kmeans_train. */
+ * All pointers are device pointers.  With a single rank the sequence is bit-identical to kmeans_train as long as
+ * n <= 2^20 rows; above that the per-cluster sums and the cost are accumulated by fixed trees (deterministic,
+ * equal to the sequential loops to fp32 rounding -- which the multi-rank result is anyway). */
 int ndb_b200_kmeans_shard_step_dev(const float *X_dev, int64_t n, int d, int k, const float *C_dev, int *assign_dev,
                                    float *sums_dev, int *counts_dev, void *stream);
 int ndb_b200_kmeans_shard_cost_dev(const float *X_dev, int64_t n, int d, const float *C_dev, const int *assign_dev,

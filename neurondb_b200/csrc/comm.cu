@@ -23,6 +23,8 @@
 
 namespace ndb {
 
+void ivf_set_coarse_by_rank(ndb_b200_ivf *ix, bool on);          // ivf.cu
+
 struct NcclApi {
     void *dl = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
@@ -294,7 +296,10 @@ int ndb_b200_ivf_search_sharded_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq
     NDB_REQUIRE(ix && Q_dev && dist_dev && ids_dev && nq > 0, NDB_B200_EINVAL, "ivf_search_sharded: bad argument");
     cudaStream_t s = stream ? (cudaStream_t) stream : ctx().stream;
     return sharded_topk(nq, k, dist_dev, ids_dev, s, [&](float *d, int64_t *i) {
-        return ndb_b200_ivf_search_dev(ix, Q_dev, nq, nprobe, k, mode, arith, d, i, s);
+        ivf_set_coarse_by_rank(ix, true);          // the coarse quantiser is split by queries, its probe lists all-gathered
+        const int rc = ndb_b200_ivf_search_dev(ix, Q_dev, nq, nprobe, k, mode, arith, d, i, s);
+        ivf_set_coarse_by_rank(ix, false);
+        return rc;
     });
 }
 

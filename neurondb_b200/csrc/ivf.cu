@@ -21,6 +21,7 @@
 #include <numeric>
 #include <cub/block/block_scan.cuh>
 #include "tc.cuh"
+#include "comm.cuh"
 
 using namespace ndb;
 
@@ -73,6 +74,8 @@ struct ndb_b200_ivf {
     // certified selection (ivf_cert.cuh): queries sent to the exact kernels, [0] lists [1] exact evaluations (lists)
     // [2] coarse [3] exact evaluations (coarse); items of the coarse scan, cached per batch shape
     DevBuf cert_counters, fb_list, fb_tau, cert_dbg;
+    bool coarse_by_rank = false;         // set by the sharded entry point for the duration of one call: the coarse quantiser is
+                                         // split by queries over the communicator's ranks and the probe lists all-gathered
     std::vector<uint32_t> row_of_slot;   // IL32 slot -> arena row (host copy, kept for the tensor layout)
 };
 
@@ -526,9 +529,26 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     NDB_CHECK(ix->fb_tau.reserve((size_t) nq * 4));
     NDB_CUDA(cudaMemsetAsync(ix->cert_counters.p, 0, 64, s));
     if (np <= 32 && ix->dim <= TC_MAX_DIM) {
-        NDB_CHECK(nearest_centroids_tensor(ix->kw.cs, ix->kw.C.as<float>(), ix->kw.cstore.as<float>(), L, ix->dim, ix->dimp, Q_dev, nq, np,
-                                           false, ix->probe.as<uint32_t>(), ix->cdist.as<float>(),
-                                           ix->cert_counters.as<unsigned long long>() + 2, s));
+        const int world = ix->coarse_by_rank ? comm_nranks() : 1;
+        if (world > 1) {
+            // Sharded search: every rank would select the same probe lists for the same queries.  Each rank does it for
+            // its slice of the batch and one all-gather hands every rank all of them (certified selection: the probe
+            // lists do not depend on who computed them).
+            const int slice = (nq + world - 1) / world, rank = comm_rank();
+            const int q0 = std::min(nq, rank * slice), q1 = std::min(nq, q0 + slice);
+            NDB_CHECK(ix->probe.reserve((size_t) world * slice * np * 4));
+            NDB_CHECK(ix->cdist.reserve((size_t) slice * np * 4));
+            uint32_t *mine = ix->probe.as<uint32_t>() + (size_t) rank * slice * np;
+            if (q1 > q0)
+                NDB_CHECK(nearest_centroids_tensor(ix->kw.cs, ix->kw.C.as<float>(), ix->kw.cstore.as<float>(), L, ix->dim, ix->dimp,
+                                                   Q_dev + (size_t) q0 * ix->dim, q1 - q0, np, false, mine, ix->cdist.as<float>(),
+                                                   ix->cert_counters.as<unsigned long long>() + 2, s));
+            NDB_CHECK(comm_allgather(mine, ix->probe.p, (size_t) slice * np * 4, s));
+        } else {
+            NDB_CHECK(nearest_centroids_tensor(ix->kw.cs, ix->kw.C.as<float>(), ix->kw.cstore.as<float>(), L, ix->dim, ix->dimp, Q_dev, nq, np,
+                                               false, ix->probe.as<uint32_t>(), ix->cdist.as<float>(),
+                                               ix->cert_counters.as<unsigned long long>() + 2, s));
+        }
     } else {
         NDB_CHECK(ivf_coarse(ix, Q_dev, nq, np, NDB_ARITH_IVF_F32, s));
     }
@@ -722,6 +742,8 @@ static int ivf_ready(ndb_b200_ivf *ix, cudaStream_t s)
     NDB_CHECK(ivf_layout(ix, s));
     return NDB_B200_OK;
 }
+
+void ivf_set_coarse_by_rank(ndb_b200_ivf *ix, bool on) { ix->coarse_by_rank = on; }
 
 }  // namespace ndb
 

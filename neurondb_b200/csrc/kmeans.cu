@@ -74,6 +74,65 @@ __global__ void kmeans_update_kernel(const float *__restrict__ X, const uint32_t
     C[(size_t) c * dim + j] = sum;
 }
 
+// The same per-cluster sums for LARGE row sets (row-sharded training over millions of rows): eight independent
+// accumulators per (cluster, dimension) instead of one dependent chain.  The additions happen in a different order
+// than kmeans_update_centroids' loop, so the result agrees with it to fp32 rounding, not bit for bit -- as the
+// row-sharded result already does through the order of the all-reduce.
+__global__ void kmeans_update_fast_kernel(const float *__restrict__ X, const uint32_t *__restrict__ members,
+                                          const int *__restrict__ start, int dim, int k, float *__restrict__ C,
+                                          int *__restrict__ counts, bool sums_only)
+{
+    const int c = blockIdx.x;
+    const int b = start[c], e = start[c + 1];
+    if (threadIdx.x == 0 && blockIdx.y == 0 && counts) counts[c] = e - b;
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
+    if (j >= dim) return;
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) acc[u] = 0.0f;
+    int t = b;
+    for (; t + 8 <= e; t += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc[u] += X[(size_t) members[t + u] * dim + j];
+    }
+    for (; t < e; t++) acc[0] += X[(size_t) members[t] * dim + j];
+    float sum = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    if (e > b && !sums_only) sum = __fdiv_rn(sum, (float) (e - b));
+    C[(size_t) c * dim + j] = sum;
+}
+
+// sum of n floats, two levels of fixed trees (deterministic, not the sequential chain)
+__global__ void __launch_bounds__(256) tree_sum_partial_kernel(const float *__restrict__ v, int64_t n, float *__restrict__ part)
+{
+    __shared__ float sh[256];
+    float acc = 0.0f;
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) acc += v[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int) threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) tree_sum_final_kernel(const float *__restrict__ part, int np, float *__restrict__ out)
+{
+    __shared__ float sh[256];
+    float acc = 0.0f;
+    for (int i = threadIdx.x; i < np; i += 256) acc += part[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int) threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
+// row sets above this size take the reordered (rounding-equivalent) sums in the row-sharded entry points
+static const int64_t KMEANS_FAST_ROWS = getenv("NDB_KMEANS_EXACT_SUMS") ? ((int64_t) 1 << 40) : ((int64_t) 1 << 20);     // (measurement switch)
+
 // squared L2 of each sample to its centroid, lane-per-sample through a transposed smem tile
 __global__ void __launch_bounds__(128) kmeans_sample_cost_kernel(const float *__restrict__ X, const float *__restrict__ C,
                                                                   const int *__restrict__ assign, int64_t n, int dim,
@@ -298,7 +357,10 @@ int kmeans_update_dev(KMeansWork &w, const float *dX, const int *d_assign, int64
     segment_starts_kernel<<<(unsigned) ((n + 1 + 255) / 256), 256, 0, s>>>(w.keys_sorted.as<int>(), n, k, w.start.as<int>());
     count_launch();
     dim3 grid((unsigned) k, (unsigned) ((dim + 127) / 128));
-    kmeans_update_kernel<<<grid, 128, 0, s>>>(dX, w.vals_sorted.as<uint32_t>(), w.start.as<int>(), dim, k, dC, d_counts, sums_only);
+    if (sums_only && n > KMEANS_FAST_ROWS)
+        kmeans_update_fast_kernel<<<grid, 128, 0, s>>>(dX, w.vals_sorted.as<uint32_t>(), w.start.as<int>(), dim, k, dC, d_counts, sums_only);
+    else
+        kmeans_update_kernel<<<grid, 128, 0, s>>>(dX, w.vals_sorted.as<uint32_t>(), w.start.as<int>(), dim, k, dC, d_counts, sums_only);
     count_launch();
     NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
@@ -428,7 +490,15 @@ int ndb_b200_kmeans_shard_cost_dev(const float *X_dev, int64_t n, int d, const f
     DevBuf &dcost = g_shard_dcost;
     NDB_CHECK(dcost.reserve((size_t) n * 4));
     kmeans_sample_cost_kernel<<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(X_dev, C_dev, assign_dev, n, d, dcost.as<float>());
-    sequential_sum_kernel<<<1, 1024, 0, s>>>(dcost.as<float>(), n, cost_dev);
+    if (n > KMEANS_FAST_ROWS) {
+        // millions of rows: the cost is a convergence test, its single f32 chain (6 M dependent adds) is replaced by trees
+        NDB_CHECK(g_shard_work.cost.reserve(1024 * 4));
+        tree_sum_partial_kernel<<<1024, 256, 0, s>>>(dcost.as<float>(), n, g_shard_work.cost.as<float>());
+        tree_sum_final_kernel<<<1, 256, 0, s>>>(g_shard_work.cost.as<float>(), 1024, cost_dev);
+        count_launch();
+    } else {
+        sequential_sum_kernel<<<1, 1024, 0, s>>>(dcost.as<float>(), n, cost_dev);
+    }
     count_launch(2);
     NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
