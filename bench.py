@@ -735,6 +735,28 @@ def run_hnsw(c, args, w, wname):
         torch.cuda.synchronize()
         curve.append({"ef": ef, "recall_at_10": rec(oi.cpu().numpy()), "qps": 1000 / (ev0.elapsed_time(ev1) * 1e-3),
                       "evals_per_query": h.last_evals() / 1000})
+    # the same rows through the exact tensor-core scan (NDB_ARITH_TENSOR, cosine): what answers this data at recall 1
+    exact_alt = None
+    try:
+        ds = ndb.Dataset(dim)
+        for s0 in range(0, n, 250_000):
+            ds.append(X[s0:s0 + 250_000], np.arange(s0, min(n, s0 + 250_000), dtype=np.int64))
+        qx = torch.from_numpy(Q[:nq]).cuda()
+        xd = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        xi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            ds.knn_dev(qx.data_ptr(), nq, k, xd.data_ptr(), xi.data_ptr(), ndb.COSINE, ndb.ARITH_TENSOR, c.stream)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        ds.knn_dev(qx.data_ptr(), nq, k, xd.data_ptr(), xi.data_ptr(), ndb.COSINE, ndb.ARITH_TENSOR, c.stream)
+        ev1.record()
+        torch.cuda.synchronize()
+        xms = ev0.elapsed_time(ev1)
+        exact_alt = {"path": "ndb_b200_knn_exact(NDB_COSINE, NDB_ARITH_TENSOR) over the same rows", "qps": nq / (xms * 1e-3),
+                     "ms_per_batch": xms, "recall_at_10": rec(xi.cpu().numpy()), "tflops": 2.0 * n * nq * dim / (xms * 1e-3) / 1e12}
+        del ds
+    except Exception as e:                       # (memory on a shared box)
+        exact_alt = {"error": str(e)[:200]}
     peaks, peak_kind = measured_peaks()
     bytes_q = evals_q * (dim * 4 + 2 * w["m"] * 4)
     ach = bytes_q * (hi - lo) / (kernel_ms * 1e-3) / 1e9
@@ -748,7 +770,7 @@ def run_hnsw(c, args, w, wname):
                    "l2": "%.1f GB of node vectors, far larger than the 126 MB L2; 2 query batches rotate" % (n * dim * 4 / 1e9),
                    "parallelism": "1 GPU" if c.world == 1 else "replicas only: rank 0 builds, graph broadcast (ncclBroadcast), "
                                   "queries split over %d GPUs" % c.world, "comm_nranks": c.comm_nranks},
-        "recall_at_10": recall, "recall_vs_ef": curve,
+        "recall_at_10": recall, "recall_vs_ef": curve, "exact_scan_same_rows": exact_alt,
         "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * k * 12,
                 "ms_per_step": e2e_s * 1e3, "mode": "ndb_b200_hnsw_search, one synchronous call per batch"},
         "gpu_launches": int(launches),
@@ -969,7 +991,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="N = 1 default run: skip the additional C2 measurement")
     ap.add_argument("--hnsw-select", default="closest", choices=["closest", "heuristic"])
-    ap.add_argument("--hnsw-efs", default="40,100,400,1600")
+    ap.add_argument("--hnsw-efs", default="40,100,400,1600,4096")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     run, ref = RUNNERS[w["kind"]]
