@@ -73,22 +73,31 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_cert_kernel(
         for (int r = 0; r < nr; r++) {
             const uint32_t nseg = __shfl_sync(FULL, my_nseg, r), first = __shfl_sync(FULL, my_first, r);
             const int nent = (int) __shfl_sync(FULL, my_rep, r) * 2 * kc;
-            for (uint32_t sg = 0; sg < nseg; sg++) {
-                const size_t base = ((size_t) first + (size_t) sg * (2 * TC_M)) * kc;
+            // A (probe, segment) unit holds nent = 32 entries (two column halves) or 128 (replicated queries).  The walk is
+            // a latency chain -- a C4 query has ~290 units, one L2 / DRAM round trip each -- so units of 32 entries are
+            // fetched four at a time (consecutive segments), units of 64 two at a time.
+            const int per = nent <= 32 ? 4 : (nent <= 64 ? 2 : 1);
+            for (uint32_t sg = 0; sg < nseg; sg += per) {
                 float cdv[4];
                 uint32_t slv[4];
+                int eidx[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const int i = u * 32 + lane;
+                    const uint32_t unit = sg + (per == 4 ? u : per == 2 ? (u >> 1) : 0);
+                    const int e = (per == 4 ? 0 : per == 2 ? (u & 1) * 32 : u * 32) + lane;
+                    eidx[u] = e;
                     cdv[u] = INFINITY;
                     slv[u] = INVALID_SLOT;
-                    if (i < nent) { slv[u] = pslot[base + i]; cdv[u] = pdist[base + i]; }
+                    if (unit < nseg && e < nent) {
+                        const size_t base = ((size_t) first + (size_t) unit * (2 * TC_M)) * kc;
+                        slv[u] = pslot[base + e];
+                        cdv[u] = pdist[base + e];
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    if (u * 32 >= nent) break;
                     const bool ok = slv[u] != INVALID_SLOT;
-                    if (ok && (u * 32 + lane) % kc == kc - 1) own_min = fminf(own_min, cdv[u]);      // last entry of a full list
+                    if (ok && eidx[u] % kc == kc - 1) own_min = fminf(own_min, cdv[u]);      // last entry of a full list
                     const unsigned m = __ballot_sync(FULL, ok);
                     if (m) { n_in += __popc(m); cand.offer(cdv[u], slv[u], ok, lane, 32); }
                 }
@@ -153,7 +162,8 @@ __global__ void __launch_bounds__(FB_THREADS) ivf_exact_fallback_kernel(
     int64_t *mi = reinterpret_cast<int64_t *>(md + FB_THREADS);
     constexpr int MAXU = 64;
     __shared__ unsigned s_rows, s_nu;
-    __shared__ float s_tau;
+    __shared__ float s_tau, s_res_d[32];
+    __shared__ int64_t s_res_i[32];
     __shared__ uint32_t s_first[128], s_nseg[128], s_nent[128], s_l[128], s_len[128], s_ubase[129];     // nprobe <= 128
     __shared__ uint32_t s_slot0[MAXU], s_nrow[MAXU];      // units to rescan: first IL32 slot, rows
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -168,7 +178,8 @@ __global__ void __launch_bounds__(FB_THREADS) ivf_exact_fallback_kernel(
         const CertQ cq = cert_query(qs, dim, lane);
         const float R = gthr[q];
         WarpTopK<1, int64_t> top;
-        auto merge_and_write = [&](bool write) -> float {      // returns the k-th exact value over the whole CTA
+        // merge of the 32 per-warp lists by warp 0: the k best of the CTA stay in s_res_*, their k-th value is returned
+        auto merge_lists = [&]() -> float {
             md[w * 32 + lane] = top.d[0];
             mi[w * 32 + lane] = top.key[0];
             __syncthreads();
@@ -180,15 +191,19 @@ __global__ void __launch_bounds__(FB_THREADS) ivf_exact_fallback_kernel(
                     const int64_t id = mi[ww * 32 + lane];
                     fin.offer(d, id, id != KeyMax<int64_t>::v, lane, k);
                 }
-                if (write && lane < k) {
-                    const bool got = fin.key[0] != KeyMax<int64_t>::v;
-                    out_dist[(size_t) q * k + lane] = got ? fin.d[0] : INFINITY;
-                    out_ids[(size_t) q * k + lane] = got ? fin.key[0] : -1;
-                }
+                s_res_d[lane] = fin.d[0];
+                s_res_i[lane] = fin.key[0];
                 if (lane == 0) s_tau = fin.td;
             }
             __syncthreads();
             return s_tau;
+        };
+        auto write_result = [&]() {
+            if (w == 0 && lane < k) {
+                const bool got = s_res_i[lane] != KeyMax<int64_t>::v;
+                out_dist[(size_t) q * k + lane] = got ? s_res_d[lane] : INFINITY;
+                out_ids[(size_t) q * k + lane] = got ? s_res_i[lane] : -1;
+            }
         };
         top.init();
         // the (probed list, segment) units of the query, dealt round-robin to the warps
@@ -289,7 +304,7 @@ __global__ void __launch_bounds__(FB_THREADS) ivf_exact_fallback_kernel(
                 }
             }
         }
-        const float tau = merge_and_write(false);
+        const float tau = merge_lists();
         const bool certified = (tau <= tau0 || tau0 == INFINITY) && cert_lower_bound<METRIC>(R, stats, cq, dim) > tau;
         if (threadIdx.x == 0) {
             atomicAdd(counters + 5, (unsigned long long) s_rows);
@@ -303,7 +318,7 @@ __global__ void __launch_bounds__(FB_THREADS) ivf_exact_fallback_kernel(
             }
         }
         if (certified) {
-            merge_and_write(true);                       // (the per-warp lists are still in `top`)
+            write_result();
             continue;
         }
         // ---- level 3: everything
@@ -324,7 +339,8 @@ __global__ void __launch_bounds__(FB_THREADS) ivf_exact_fallback_kernel(
                 top.offer(ed, id, valid, lane, k);
             }
         }
-        merge_and_write(true);
+        merge_lists();
+        write_result();
     }
 }
 

@@ -136,46 +136,69 @@ __global__ void tc_row_norms_kernel(const float4 *__restrict__ store, const uint
 
 // row-major fp32 queries -> blocked bf16 query tiles + squared norms
 // qmap (optional): tile position q holds query qmap[q] / nprobe (INVALID_SLOT = empty position)
-__global__ void tc_block_queries_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap, uint32_t nprobe,
-                                        int nq, int nqpad, const uint32_t *__restrict__ npos, int dim, int nkc,
-                                        __nv_bfloat16 *__restrict__ qb, float *__restrict__ qnorm, float *__restrict__ qerr)
+// One CTA per (query tile, K-chunk): the 32 KB blocked tile-chunk is assembled in shared memory (16 adjacent lanes = the
+// sixteen 8-element groups of one position, so the norm is a fixed xor tree whatever position a query sits on) and
+// written out as one contiguous, coalesced run -- the direct version wrote 16 bytes per thread at a 2 KB stride.
+__global__ void __launch_bounds__(256) tc_block_queries_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap, uint32_t nprobe,
+                                                               int nq, int nqpad, const uint32_t *__restrict__ npos, int dim, int nkc,
+                                                               __nv_bfloat16 *__restrict__ qb, float *__restrict__ qnorm,
+                                                               float *__restrict__ qerr)
 {
-    const int groups = nkc * (TC_KC / 8);
-    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (npos) nqpad = min(nqpad, (int) *npos);          // whole warps either way: both are multiples of 128
-    if (t >= (int64_t) nqpad * groups) return;
-    const int q = (int) (t / groups);
-    const int g = (int) (t - (int64_t) q * groups);
-    const int64_t src = qmap ? (qmap[q] != INVALID_SLOT ? (int64_t) (qmap[q] / nprobe) : -1) : (q < nq ? q : -1);
-    __nv_bfloat16 o[8];
-    float part = 0.0f, perr = 0.0f;
+    __shared__ __align__(16) __nv_bfloat16 tile_s[TC_M * TC_KC];
+    const int tile = blockIdx.x / nkc, chunk = blockIdx.x % nkc;
+    if (npos) nqpad = min(nqpad, (int) *npos);          // both are multiples of 128
+    if (tile * TC_M >= nqpad) return;
+    constexpr int G = TC_KC / 8;                        // 16 groups per position and chunk
+    for (int piece = threadIdx.x; piece < TC_M * G; piece += 256) {
+        const int qi_ = piece / G, kc = piece % G;
+        const int q = tile * TC_M + qi_;
+        const int g = chunk * G + kc;
+        const int64_t src = qmap ? (qmap[q] != INVALID_SLOT ? (int64_t) (qmap[q] / nprobe) : -1) : (q < nq ? q : -1);
+        __nv_bfloat16 o[8];
+        float part = 0.0f, perr = 0.0f;
+        if (src >= 0 && g * 8 + 8 <= dim && (dim & 3) == 0) {
+            const float4 v0 = *reinterpret_cast<const float4 *>(Q + (size_t) src * dim + g * 8);
+            const float4 v1 = *reinterpret_cast<const float4 *>(Q + (size_t) src * dim + g * 8 + 4);
+            const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int d = g * 8 + i;
-        const float v = (src >= 0 && d < dim) ? Q[(size_t) src * dim + d] : 0.0f;
-        o[i] = __float2bfloat16_rn(v);
-        const float r = __bfloat162float(o[i]);
-        part = fmaf(r, r, part);
-        perr = fmaf(v - r, v - r, perr);
-    }
-    // Query i of a tile sits on TMEM lane (i % 4) * 32 + i / 4: the tile's queries are dealt round-robin
-    // to the four lane quarters, each of which only one pair of epilogue warps can read.  A tile with 16
-    // live queries (most tile-steps of an IVF batch: long lists probed by a few queries) then keeps all
-    // eight epilogue warps busy with 4 queries each instead of two warps with 16.
-    const int tile = q / TC_M, qi_ = q % TC_M, rr = (qi_ & 3) * 32 + (qi_ >> 2);
-    const int chunk = g / (TC_KC / 8), kc = g % (TC_KC / 8);
-    const size_t off = ((((size_t) (tile * nkc + chunk) * (TC_KC / 8) + kc) * (TC_M / 8) + (rr >> 3)) * 8 + (rr & 7)) * 8;
-    *reinterpret_cast<uint4 *>(qb + off) = *reinterpret_cast<const uint4 *>(o);
-    // squared norm of the rounded query: the row's 16 or 32 threads are adjacent lanes of one warp;
-    // a fixed xor tree, so a query gets the same norm at whatever tile position it sits
-    // (more than 32 groups per row, dim > 256: tc_query_norms_kernel does it instead)
-    if (groups <= 32) {
-        for (int o2 = groups >> 1; o2 > 0; o2 >>= 1) {
-            part += __shfl_xor_sync(FULL, part, o2);
-            perr += __shfl_xor_sync(FULL, perr, o2);
+            for (int i = 0; i < 8; i++) {
+                o[i] = __float2bfloat16_rn(vv[i]);
+                const float r = __bfloat162float(o[i]);
+                part = fmaf(r, r, part);
+                perr = fmaf(vv[i] - r, vv[i] - r, perr);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int d = g * 8 + i;
+                const float v = (src >= 0 && d < dim) ? Q[(size_t) src * dim + d] : 0.0f;
+                o[i] = __float2bfloat16_rn(v);
+                const float r = __bfloat162float(o[i]);
+                part = fmaf(r, r, part);
+                perr = fmaf(v - r, v - r, perr);
+            }
         }
-        if (g == 0) { qnorm[q] = part; if (qerr) qerr[q] = perr; }      // qerr: squared norm of the query's bf16 rounding error
+        // Query i of a tile sits on TMEM lane (i % 4) * 32 + i / 4: the tile's queries are dealt round-robin
+        // to the four lane quarters, each of which only one pair of epilogue warps can read.  A tile with 16
+        // live queries (most tile-steps of an IVF batch: long lists probed by a few queries) then keeps all
+        // eight epilogue warps busy with 4 queries each instead of two warps with 16.
+        const int rr = (qi_ & 3) * 32 + (qi_ >> 2);
+        const size_t soff = (((size_t) kc * (TC_M / 8) + (rr >> 3)) * 8 + (rr & 7)) * 8;
+        *reinterpret_cast<uint4 *>(tile_s + soff) = *reinterpret_cast<const uint4 *>(o);
+        // squared norm of the rounded query (one K-chunk: dim <= 128; more chunks: tc_query_norms_kernel)
+        if (nkc == 1) {
+#pragma unroll
+            for (int o2 = G >> 1; o2 > 0; o2 >>= 1) {
+                part += __shfl_xor_sync(FULL, part, o2);
+                perr += __shfl_xor_sync(FULL, perr, o2);
+            }
+            if (kc == 0) { qnorm[q] = part; if (qerr) qerr[q] = perr; }   // qerr: squared norm of the query's bf16 rounding error
+        }
     }
+    __syncthreads();
+    uint4 *dst = reinterpret_cast<uint4 *>(qb + (size_t) (tile * nkc + chunk) * TC_M * TC_KC);
+    const uint4 *srcp = reinterpret_cast<const uint4 *>(tile_s);
+    for (int i = threadIdx.x; i < TC_M * TC_KC / 8; i += 256) dst[i] = srcp[i];
 }
 
 // squared norm of the bf16-rounded query, one thread per tile position (rows of more than 256 dims)
@@ -811,11 +834,9 @@ int tc_store_rinv(TcStore &st, const float **out, cudaStream_t s)
 int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t nprobe, int nq, int nqpad, int dim, int nkc,
                      __nv_bfloat16 *qb, float *qnorm, cudaStream_t s, const uint32_t *npos_dev, float *qerr)
 {
-    const int groups = nkc * (TC_KC / 8);
-    tc_block_queries_kernel<<<(unsigned) (((int64_t) nqpad * groups + 255) / 256), 256, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev,
-                                                                                                dim, nkc, qb, qnorm, qerr);
+    tc_block_queries_kernel<<<(unsigned) ((nqpad / TC_M) * nkc), 256, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev, dim, nkc, qb, qnorm, qerr);
     count_launch();
-    if (groups > 32) {
+    if (nkc > 1) {
         tc_query_norms_kernel<<<(unsigned) ((nqpad + 127) / 128), 128, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev, dim, qnorm, qerr);
         count_launch();
     }

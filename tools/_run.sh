@@ -1,3 +1,3 @@
-for i in 1 2; do python bench.py --workload c5 --steps 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('fast', d['kmeans']['s_per_iteration'], d['kmeans']['cost'])"; done
-NDB_KMEANS_EXACT_SUMS=1 python bench.py --workload c5 --steps 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('exact sums', d['kmeans']['s_per_iteration'], d['kmeans']['cost'])"
-NDB_ASSIGN_FP32=1 python bench.py --workload c5 --steps 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('fp32 assign', d['kmeans']['s_per_iteration'], d['kmeans']['cost'])"
+python -m pytest tests/test_gpu_tensor.py -m gpu -x -q 2>&1 | tail -2
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"tc_block_queries|ivf_tc_finish|ivf_exact_fallback" --csv --log-file gpurun_out/cert_c4_launches.csv python tools/cert_stats.py c4 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"tc_block_queries|ivf_tc_finish|ivf_exact_fallback" --csv --log-file gpurun_out/cert_c2_launches.csv python tools/cert_stats.py c2 > /dev/null 2>&1
