@@ -328,6 +328,20 @@ def run_ivf(c, args, w, wname, with_cpu=True, with_alt=True):
     ndb.set_timing(False)
     kernel_ms, evals = float(np.mean(kms)), float(np.mean(kevals))
 
+    # certified selection of the last tensor-path batch: how many queries the certificate accepted, how many went to the
+    # exact kernel, how many exact re-evaluations it all took
+    cert = None
+    if args.arith == "tensor":
+        step(0)
+        torch.cuda.synchronize()
+        cs = ix.cert_stats()
+        cert = {"queries": nq, "certified_directly": nq - cs["list_fallback_queries"], "exact_kernel_queries": cs["list_fallback_queries"],
+                "every_probed_row_queries": cs["list_full_scan_queries"], "rows_rescanned_by_exact_kernel": cs["list_rescanned_rows"],
+                "exact_evaluations_per_query": cs["list_exact_evals"] / nq,
+                "coarse_exact_kernel_queries": cs["coarse_fallback_queries"],
+                "coarse_exact_evaluations_per_query": cs["coarse_exact_evals"] / max(1, nq // (world if gather else 1)),
+                "note": "this rank's shard; ids and distance bits equal the fp32 path's either way (alt.ids_equal_to_tensor_path)"}
+
     # end to end through the host-pointer entry points with pinned host buffers
     qh = [torch.from_numpy(Q[i * nq:(i + 1) * nq]).pin_memory() for i in range(4)]
     hd = [torch.empty((nq, k), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
@@ -470,8 +484,11 @@ def run_ivf(c, args, w, wname, with_cpu=True, with_alt=True):
                    "queries_per_step": nq * replicas, "arith": args.arith,
                    "l2": "inputs (%.2f GB of bf16 lists per GPU) larger than the 126 MB L2; 4 query batches rotate"
                          % (n * dim * 2 / 1e9 / (world if gather else 1)),
-                   "parallelism": par, "comm_nranks": c.comm_nranks},
+                   "parallelism": par, "comm_nranks": c.comm_nranks,
+                   "exchange": None if not gather else ("peer-memory windows (CUDA IPC): our push kernel stores over NVLink, no collective "
+                                                        "in the step" if ndb._lib.load().ndb_b200_comm_exchange_is_p2p() else "ncclAllGather")},
         "recall_at_10": recall,
+        "certified_selection": cert,
         "alt": alt,
         "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4 * world,
                 "d2h_bytes_per_step": nq * k * 12 * world, "ms_per_step": e2e_s * 1e3, "mode": e2e_mode,

@@ -302,6 +302,8 @@ int ndb_b200_comm_shutdown(void);
 int ndb_b200_comm_rank(void);
 int ndb_b200_comm_nranks(void);
 int ndb_b200_comm_nccl_version(void);
+/* 1 once the sharded searches exchange through peer-memory windows (NVLink stores by our own kernel), 0 = ncclAllGather */
+int ndb_b200_comm_exchange_is_p2p(void);
 /* raw collectives on device buffers, queued on `stream` (NULL = the library stream); with one rank they
  * are a device copy / a no-op.  type: 0 = f32, 1 = i32, 2 = f64, 3 = i64. */
 int ndb_b200_comm_allgather_dev(const void *send_dev, void *recv_dev, size_t bytes_per_rank, void *stream);
@@ -311,8 +313,9 @@ int ndb_b200_comm_broadcast_dev(void *buf_dev, size_t bytes, int root, void *str
  * answers the (replicated) query batch against the rows its handle holds -- whole lists
  * (ndb_b200_ivf_set_shard) or a stripe of every list (the caller inserts rows i with i % world == rank,
  * with their global ids) -- writes its top-k as packed records (4-byte distance block + 8-byte id block
- * = 12 bytes per result), ONE ncclAllGather moves them, and every rank merges the world's lists on the
- * device by (dist, id).  All ranks must make the same call; every rank receives the full result.
+ * = 12 bytes per result) into an exchange window; a push kernel stores them into every peer's window over NVLink
+ * (CUDA IPC peer memory) and raises a flag -- or, where IPC is unavailable / NDB_B200_EXCHANGE=nccl, ONE
+ * ncclAllGather moves them -- and every rank merges the world's lists on the device by (dist, id).  All ranks must make the same call; every rank receives the full result.
  * Without a communicator (or world == 1) these are the plain searches. */
 int ndb_b200_ivf_search_sharded_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int nprobe, int k, int mode, int arith,
                                     float *dist_dev, int64_t *ids_dev, void *stream);

@@ -119,6 +119,7 @@ SIGNATURES = {
     "ndb_b200_comm_rank": (_i, []),
     "ndb_b200_comm_nranks": (_i, []),
     "ndb_b200_comm_nccl_version": (_i, []),
+    "ndb_b200_comm_exchange_is_p2p": (_i, []),
     "ndb_b200_comm_allgather_dev": (_i, [_p, _p, _sz, _p]),
     "ndb_b200_comm_allreduce_sum_dev": (_i, [_p, _sz, _i, _p]),
     "ndb_b200_comm_broadcast_dev": (_i, [_p, _sz, _i, _p]),

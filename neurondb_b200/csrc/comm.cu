@@ -5,9 +5,11 @@
 // coordinator opens a libpq connection per shard, runs the same kNN query on each (:56-300), collects the
 // per-shard (id, distance) rows and merges them on the host by (distance ASC, id ASC) (:323-487, order
 // :425-438).  Here the shards are the GPUs of one box: every rank answers the query batch against the rows
-// it holds, the per-rank top-k travel over NVLink in ONE ncclAllGather of packed 12-byte (dist, id) records
-// (4 bytes of distance block + 8 bytes of id block per result), and every rank merges the world's
-// lists on the device in the same (dist, id) order.  k-means training exchanges per-cluster sums and counts
+// it holds and writes its top-k as packed 12-byte (dist, id) records (4 bytes of distance block + 8 bytes of id block per
+// result) into its slot of an exchange window; one kernel stores that slot into every peer's window over NVLink
+// (CUDA IPC peer memory; no collective call in the step) and raises a flag, and every rank's merge kernel waits for the
+// world's flags and merges the lists on the device in the same (dist, id) order.  Where IPC windows cannot be had (or
+// with NDB_B200_EXCHANGE=nccl) the records travel in ONE ncclAllGather instead.  k-means training exchanges per-cluster sums and counts
 // with ncclAllReduce once per Lloyd iteration; an HNSW graph built on one rank reaches the replicas with
 // ncclBroadcast.
 //
@@ -20,6 +22,8 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <algorithm>
+#include <vector>
 
 namespace ndb {
 
@@ -43,10 +47,31 @@ struct Comm {
     int rank = 0, world = 1;
     bool ready = false;
     int device = -1;
-    DevBuf gather;                 // [world][record block] of the sharded searches
+    DevBuf gather;                 // [world][record block] of the sharded searches (NCCL exchange)
+    // Peer-memory exchange (NVLink loads / stores, no NCCL call in the step): one window per rank, opened by every
+    // other rank through CUDA IPC.  Window = [flags: world x u32, padded to 256 B][parity 0: world slots][parity 1: ...]
+    bool p2p_ok = false, p2p_tried = false;
+    void *p2p_win = nullptr;                       // this rank's window (cudaMalloc)
+    void *p2p_peer[16] = {nullptr};                // every rank's window as seen from here (own entry = p2p_win)
+    void **p2p_peer_dev = nullptr;                 // the same table on the device
+    unsigned *p2p_done = nullptr;                  // CTA counter of the push kernel
+    size_t p2p_slot = 0;                           // bytes per (rank, parity) slot
+    uint32_t p2p_step = 0;
     DevBuf qbuf, outd, outi;       // staging of the host-pointer sharded entry points
     DevBuf red, cst;               // k-means: [k*d f32 sums | k i32 counts], [1 f32 cost]
     void release_scratch() { gather.release(); qbuf.release(); outd.release(); outi.release(); red.release(); cst.release(); }
+    void release_p2p()
+    {
+        for (int r = 0; r < 16; r++) {
+            if (p2p_peer[r] && p2p_peer[r] != p2p_win) cudaIpcCloseMemHandle(p2p_peer[r]);
+            p2p_peer[r] = nullptr;
+        }
+        if (p2p_win) cudaFree(p2p_win);
+        if (p2p_peer_dev) cudaFree(p2p_peer_dev);
+        if (p2p_done) cudaFree(p2p_done);
+        p2p_win = nullptr; p2p_peer_dev = nullptr; p2p_done = nullptr;
+        p2p_ok = false; p2p_slot = 0; p2p_step = 0;
+    }
 };
 
 static Comm g_comm;
@@ -98,6 +123,8 @@ void comm_at_shutdown()
     if (g_comm.ready && g_comm.comm) g_comm.api.CommDestroy(g_comm.comm);
     g_comm.comm = nullptr;
     g_comm.release_scratch();
+    g_comm.release_p2p();
+    g_comm.p2p_tried = false;
     g_comm.ready = false;
     g_comm.rank = 0;
     g_comm.world = 1;
@@ -165,6 +192,143 @@ __global__ void merge_records_kernel(const unsigned char *__restrict__ rec, size
     }
 }
 
+// ---- peer-memory exchange ---------------------------------------------------------------------------------------
+// push: this rank's record block (already in its own window, slot `rank` of the step's parity) is stored into the same
+// slot of every peer's window over NVLink (16-byte stores), then -- once every CTA's stores are fenced -- the step number
+// is written to flag `rank` of every peer.  merge: waits until all `world` flags of the LOCAL window show the step, then
+// merges the world's lists exactly like merge_records_kernel.  Two parities: a rank can run at most one step ahead of a
+// peer that is still merging (its next push needs that peer's push of the current step).
+constexpr size_t P2P_FLAG_BYTES = 256;
+
+__global__ void __launch_bounds__(256) p2p_push_kernel(void *const *__restrict__ peer, size_t slot_off, size_t bytes, int rank, int world,
+                                                        uint32_t step, unsigned *__restrict__ done)
+{
+    const uint4 *src = reinterpret_cast<const uint4 *>(static_cast<const unsigned char *>(peer[rank]) + slot_off);
+    const size_t n16 = bytes / 16;
+    for (int r = 0; r < world; r++) {
+        if (r == rank) continue;
+        uint4 *dst = reinterpret_cast<uint4 *>(static_cast<unsigned char *>(peer[r]) + slot_off);
+        for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t) gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) *done = 0;
+        if ((int) threadIdx.x < world) {
+            volatile uint32_t *flag = reinterpret_cast<volatile uint32_t *>(peer[threadIdx.x]) + rank;
+            *flag = step;
+        }
+        __threadfence_system();
+    }
+}
+
+template <int KR>
+__global__ void p2p_merge_kernel(const unsigned char *__restrict__ win, size_t par_off, size_t stride, size_t ids_off, int nshards,
+                                 uint32_t step, int nq, int k, float *__restrict__ out_dist, int64_t *__restrict__ out_ids)
+{
+    // every rank's records of this step have arrived once its flag shows the step (flags only grow)
+    if (threadIdx.x < (unsigned) nshards) {
+        const volatile uint32_t *flag = reinterpret_cast<const volatile uint32_t *>(win) + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int32_t) (*flag - step) < 0) {
+            if (clock64() - t0 > 20000000000ll) __trap();        // ~10 s: a peer died; fail loudly rather than hang
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    const unsigned char *rec = win + par_off;
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    WarpTopK<KR, int64_t> top;
+    top.init();
+    for (int s = 0; s < nshards; s++) {
+        const float *d = reinterpret_cast<const float *>(rec + (size_t) s * stride) + (size_t) q * k;
+        const int64_t *id = reinterpret_cast<const int64_t *>(rec + (size_t) s * stride + ids_off) + (size_t) q * k;
+        for (int i = lane; i < round_up(k, 32); i += 32) {
+            float cd = INFINITY;
+            int64_t ci = -1;
+            if (i < k) { cd = __ldcv(d + i); ci = __ldcv(id + i); }      // (written by a peer: not through the read-only cache)
+            top.offer(cd, ci, i < k && ci >= 0, lane, k);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KR; r++) {
+        const int e = r * 32 + lane;
+        if (e < k) {
+            const bool have = top.key[r] != KeyMax<int64_t>::v;
+            out_dist[(size_t) q * k + e] = have ? top.d[r] : INFINITY;
+            out_ids[(size_t) q * k + e] = have ? top.key[r] : -1;
+        }
+    }
+}
+
+// (re)create the windows for slots of at least `slot` bytes: collective over the communicator
+static int p2p_setup(size_t slot, cudaStream_t s)
+{
+    Comm &c = g_comm;
+    if (c.p2p_ok && c.p2p_slot >= slot) return NDB_B200_OK;
+    static const bool disabled = getenv("NDB_B200_EXCHANGE") && !strcmp(getenv("NDB_B200_EXCHANGE"), "nccl");
+    if (disabled || c.world > 16 || (c.p2p_tried && !c.p2p_ok)) return NDB_B200_ESTATE;
+    c.p2p_tried = true;
+    NDB_CUDA(cudaStreamSynchronize(s));
+    // nobody may still be reading an old window: one all-reduce as a barrier
+    DevBuf tmp;
+    NDB_CHECK(tmp.reserve(256 + (size_t) c.world * sizeof(cudaIpcMemHandle_t)));
+    NDB_CUDA(cudaMemsetAsync(tmp.p, 0, 256, s));
+    NDB_CHECK(comm_allreduce_sum(tmp.p, 1, COMM_I32, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    c.release_p2p();
+    size_t want = ((slot + slot / 2 + 65535) / 65536) * 65536;
+    const size_t win_bytes = P2P_FLAG_BYTES + 2 * (size_t) c.world * want;
+    NDB_CUDA(cudaMalloc(&c.p2p_win, win_bytes));
+    NDB_CUDA(cudaMemset(c.p2p_win, 0, P2P_FLAG_BYTES));
+    NDB_CUDA(cudaMalloc((void **) &c.p2p_peer_dev, 16 * sizeof(void *)));
+    NDB_CUDA(cudaMalloc((void **) &c.p2p_done, 4));
+    NDB_CUDA(cudaMemset(c.p2p_done, 0, 4));
+    cudaIpcMemHandle_t mine;
+    cudaError_t e = cudaIpcGetMemHandle(&mine, c.p2p_win);
+    // exchange the handles (and whether everybody got one) through the communicator
+    std::vector<unsigned char> hbuf((size_t) c.world * (sizeof(cudaIpcMemHandle_t) + 8), 0);
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    unsigned char *d_all = tmp.as<unsigned char>();
+    std::vector<unsigned char> my(rec, 0);
+    memcpy(my.data(), &mine, sizeof(mine));
+    my[sizeof(mine)] = e == cudaSuccess ? 1 : 0;
+    NDB_CHECK(tmp.reserve((size_t) c.world * rec));
+    d_all = tmp.as<unsigned char>();
+    NDB_CUDA(cudaMemcpyAsync(d_all + (size_t) c.rank * rec, my.data(), rec, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(comm_allgather(d_all + (size_t) c.rank * rec, d_all, rec, s));
+    NDB_CUDA(cudaMemcpyAsync(hbuf.data(), d_all, hbuf.size(), cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    bool all_ok = true;
+    for (int r = 0; r < c.world; r++) all_ok = all_ok && hbuf[(size_t) r * rec + sizeof(mine)] == 1;
+    if (all_ok) {
+        for (int r = 0; r < c.world && all_ok; r++) {
+            if (r == c.rank) { c.p2p_peer[r] = c.p2p_win; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, hbuf.data() + (size_t) r * rec, sizeof(h));
+            if (cudaIpcOpenMemHandle(&c.p2p_peer[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { all_ok = false; c.p2p_peer[r] = nullptr; }
+        }
+    }
+    (void) cudaGetLastError();
+    // everybody must agree (a rank that failed to open a handle drags all to the NCCL exchange)
+    int ok_i = all_ok ? 1 : 0;
+    NDB_CUDA(cudaMemcpyAsync(tmp.p, &ok_i, 4, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(comm_allreduce_sum(tmp.p, 1, COMM_I32, s));
+    NDB_CUDA(cudaMemcpyAsync(&ok_i, tmp.p, 4, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    if (ok_i != c.world) { c.release_p2p(); return NDB_B200_ESTATE; }
+    NDB_CUDA(cudaMemcpy(c.p2p_peer_dev, c.p2p_peer, 16 * sizeof(void *), cudaMemcpyHostToDevice));
+    c.p2p_slot = want;
+    c.p2p_step = 0;
+    c.p2p_ok = true;
+    return NDB_B200_OK;
+}
+
 struct RecordLayout {
     size_t ids_off, stride;
     RecordLayout(int nq, int k)
@@ -183,12 +347,33 @@ static int sharded_topk(int nq, int k, float *dist_dev, int64_t *ids_dev, cudaSt
     const int world = comm_nranks(), rank = comm_rank();
     if (world == 1) return fill(dist_dev, ids_dev);
     const RecordLayout rl(nq, k);
+    const unsigned grid = (unsigned) ((nq + 3) / 4);
+    if (p2p_setup(rl.stride, s) == NDB_B200_OK) {
+        // exchange through peer memory: local result straight into this rank's window, one push kernel storing it into the
+        // peers' windows over NVLink, the merge kernel waits for the world's flags -- no collective call in the step
+        Comm &c = g_comm;
+        const uint32_t step = ++c.p2p_step;
+        const size_t par_off = P2P_FLAG_BYTES + (size_t) (step & 1u) * world * c.p2p_slot;
+        const size_t slot_off = par_off + (size_t) rank * c.p2p_slot;
+        unsigned char *mine = static_cast<unsigned char *>(c.p2p_win) + slot_off;
+        NDB_CHECK(fill(reinterpret_cast<float *>(mine), reinterpret_cast<int64_t *>(mine + rl.ids_off)));
+        const unsigned pgrid = (unsigned) std::min<size_t>(64, (rl.stride / 16 + 255) / 256);
+        p2p_push_kernel<<<pgrid ? pgrid : 1, 256, 0, s>>>(c.p2p_peer_dev, slot_off, rl.stride, rank, world, step, c.p2p_done);
+        if (k <= 32)
+            p2p_merge_kernel<1><<<grid, 128, 0, s>>>(static_cast<const unsigned char *>(c.p2p_win), par_off, c.p2p_slot, rl.ids_off, world, step,
+                                                     nq, k, dist_dev, ids_dev);
+        else
+            p2p_merge_kernel<4><<<grid, 128, 0, s>>>(static_cast<const unsigned char *>(c.p2p_win), par_off, c.p2p_slot, rl.ids_off, world, step,
+                                                     nq, k, dist_dev, ids_dev);
+        count_launch(2);
+        NDB_CUDA(cudaGetLastError());
+        return NDB_B200_OK;
+    }
     NDB_CHECK(g_comm.gather.reserve(rl.stride * world));
     unsigned char *rec = g_comm.gather.as<unsigned char>();
     unsigned char *mine = rec + rl.stride * rank;
     NDB_CHECK(fill(reinterpret_cast<float *>(mine), reinterpret_cast<int64_t *>(mine + rl.ids_off)));
     NDB_CHECK(comm_allgather(mine, rec, rl.stride, s));            // in place: block `rank` is already where it belongs
-    const unsigned grid = (unsigned) ((nq + 3) / 4);
     if (k <= 32) merge_records_kernel<1><<<grid, 128, 0, s>>>(rec, rl.stride, rl.ids_off, world, nq, k, dist_dev, ids_dev);
     else merge_records_kernel<4><<<grid, 128, 0, s>>>(rec, rl.stride, rl.ids_off, world, nq, k, dist_dev, ids_dev);
     count_launch();
@@ -251,6 +436,8 @@ int ndb_b200_comm_shutdown(void)
     if (g_comm.comm) g_comm.api.CommDestroy(g_comm.comm);
     g_comm.comm = nullptr;
     g_comm.release_scratch();
+    g_comm.release_p2p();
+    g_comm.p2p_tried = false;
     g_comm.ready = false;
     g_comm.rank = 0;
     g_comm.world = 1;
@@ -259,6 +446,10 @@ int ndb_b200_comm_shutdown(void)
 
 int ndb_b200_comm_rank(void) { return comm_rank(); }
 int ndb_b200_comm_nranks(void) { return comm_nranks(); }
+
+/* 1 = the sharded searches exchange their records through peer memory (CUDA IPC windows, NVLink stores);
+ * 0 = through ncclAllGather (no windows yet, IPC unavailable, or NDB_B200_EXCHANGE=nccl) */
+int ndb_b200_comm_exchange_is_p2p(void) { return g_comm.ready && g_comm.p2p_ok ? 1 : 0; }
 
 int ndb_b200_comm_nccl_version(void)
 {

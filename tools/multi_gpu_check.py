@@ -108,6 +108,7 @@ def main():
     dist.broadcast_object_list(ref, src=0)
     res["hnsw_broadcast_equal"] = bool(np.array_equal(si, ref[1]) and np.array_equal(bits(sd), bits(ref[0])) and len(h) == 5000)
 
+    res["exchange"] = "peer memory (IPC windows, NVLink stores)" if ndb._lib.load().ndb_b200_comm_exchange_is_p2p() else "ncclAllGather"
     ok = all(v for kk, v in res.items() if isinstance(v, bool)) and res["comm_nranks"] == nranks
     flags = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
