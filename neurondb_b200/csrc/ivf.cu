@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <numeric>
 #include <cub/block/block_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include "tc.cuh"
 #include "comm.cuh"
 
@@ -76,7 +77,9 @@ struct ndb_b200_ivf {
     DevBuf cert_counters, fb_list, fb_tau, cert_dbg;
     bool coarse_by_rank = false;         // set by the sharded entry point for the duration of one call: the coarse quantiser is
                                          // split by queries over the communicator's ranks and the probe lists all-gathered
-    std::vector<uint32_t> row_of_slot;   // IL32 slot -> arena row (host copy, kept for the tensor layout)
+    DevBuf d_start, d_sorted_list, d_row_of_slot;   // layout by-products kept for the tensor maps: first position of every list in
+                                                    // the (list, id) order, the lists in that order, IL32 slot -> arena row
+    uint64_t tc_tiles = 0;               // 256-row tiles of all lists
 };
 
 namespace ndb {
@@ -375,79 +378,200 @@ static int ivf_sync_centroids(ndb_b200_ivf *ix, cudaStream_t s)
     return NDB_B200_OK;
 }
 
+// ---- list layout on the device ----------------------------------------------------------------------------
+// rows (insertion order) -> IL32 slots: list l occupies the 32-vector blocks [list_blk[l], list_blk[l] + ceil(len/32)),
+// entries sorted by id inside a list (insertion order between equal ids).  Two stable radix sorts do it: by id, then
+// by list; a third (by list alone) gives the insertion order inside each list for the literal mode.
+__global__ void iota32_kernel(uint32_t *out, int64_t n)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t) i;
+}
+__global__ void gather_u32_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, int64_t n, uint32_t *__restrict__ out)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+// first position of every list in the list-sorted order: start[l] for l in [0, L], from the sorted list keys
+__global__ void list_starts_kernel(const uint32_t *__restrict__ sorted_list, int64_t n, int L, uint32_t *__restrict__ start)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const int cur = i < n ? (int) sorted_list[i] : L;
+    const int prev = i > 0 ? (int) sorted_list[i - 1] : -1;
+    for (int l = prev + 1; l <= cur && l <= L; l++) start[l] = (uint32_t) i;
+}
+// single CTA: list_len, list_blk (exclusive scan of the lists' block counts), ltile8 (of their 256-row tile counts, * 8)
+__global__ void __launch_bounds__(1024) list_extents_kernel(const uint32_t *__restrict__ start, int L, uint32_t *__restrict__ list_len,
+                                                             uint32_t *__restrict__ list_blk, uint32_t *__restrict__ ltile8,
+                                                             unsigned long long *__restrict__ totals /* blocks, tiles */)
+{
+    typedef cub::BlockScan<unsigned long long, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const int ipt = (L + 1023) / 1024;
+    const int b = threadIdx.x * ipt, e = min(L, b + ipt);
+    unsigned long long sb = 0, st = 0;
+    for (int l = b; l < e; l++) {
+        const uint32_t len = start[l + 1] - start[l];
+        sb += (len + 31) / 32;
+        st += (len + TC_N - 1) / TC_N;
+    }
+    unsigned long long ob, ot, tb, tt;
+    Scan(tmp).ExclusiveSum(sb, ob, tb);
+    __syncthreads();
+    Scan(tmp).ExclusiveSum(st, ot, tt);
+    for (int l = b; l < e; l++) {
+        const uint32_t len = start[l + 1] - start[l];
+        list_len[l] = len;
+        list_blk[l] = (uint32_t) ob;
+        ltile8[l] = (uint32_t) (ot * 8);
+        ob += (len + 31) / 32;
+        ot += (len + TC_N - 1) / TC_N;
+    }
+    if (threadIdx.x == 0) { totals[0] = tb; totals[1] = tt; }
+}
+// position p of the (list, id)-sorted order: row, list -> slot; fills slot_of_row, ids_by_slot, row_of_slot
+__global__ void place_rows_kernel(const uint32_t *__restrict__ sorted_row, const uint32_t *__restrict__ sorted_list,
+                                  const uint32_t *__restrict__ start, const uint32_t *__restrict__ list_blk,
+                                  const int64_t *__restrict__ row_id, int64_t n, uint32_t *__restrict__ slot_of_row,
+                                  int64_t *__restrict__ ids_by_slot, uint32_t *__restrict__ row_of_slot)
+{
+    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t row = sorted_row[p], l = sorted_list[p];
+    const uint32_t slot = list_blk[l] * 32 + (uint32_t) (p - start[l]);
+    slot_of_row[row] = slot;
+    ids_by_slot[slot] = row_id[row];
+    row_of_slot[slot] = row;
+}
+// position p of the list-sorted (insertion) order: the j-th inserted row of list l sits at lit[list_blk[l] * 32 + j]
+__global__ void place_literal_kernel(const uint32_t *__restrict__ ins_row, const uint32_t *__restrict__ ins_list,
+                                     const uint32_t *__restrict__ start, const uint32_t *__restrict__ list_blk,
+                                     const uint32_t *__restrict__ slot_of_row, int64_t n, uint32_t *__restrict__ lit)
+{
+    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t l = ins_list[p];
+    lit[list_blk[l] * 32 + (uint32_t) (p - start[l])] = slot_of_row[ins_row[p]];
+}
+// tensor layout maps: tensor row ltile8[l] * 32 + j  <->  IL32 slot list_blk[l] * 32 + j, arena row
+__global__ void tensor_maps_kernel(const uint32_t *__restrict__ sorted_list, const uint32_t *__restrict__ start,
+                                   const uint32_t *__restrict__ list_blk, const uint32_t *__restrict__ ltile8,
+                                   const uint32_t *__restrict__ row_of_slot, int64_t n, uint32_t *__restrict__ tc_src,
+                                   uint32_t *__restrict__ tc_row)
+{
+    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t l = sorted_list[p], j = (uint32_t) (p - start[l]);
+    const uint32_t slot = list_blk[l] * 32 + j, trow = ltile8[l] * 32 + j;
+    tc_src[trow] = slot;
+    tc_row[trow] = row_of_slot[slot];
+}
+
 // (re)build the IL32 list store from the arena
 static int ivf_layout(ndb_b200_ivf *ix, cudaStream_t s)
 {
     if (!ix->dirty) return NDB_B200_OK;
     const int64_t n = ix->nrows;
     const int L = ix->nlists;
-    ix->list_len.assign(L, 0);
-    for (int64_t r = 0; r < n; r++) ix->list_len[ix->row_list[r]]++;
-    ix->list_blk.assign(L, 0);
-    uint64_t blk = 0;
-    for (int l = 0; l < L; l++) {
-        ix->list_blk[l] = (uint32_t) blk;
-        blk += (ix->list_len[l] + 31) / 32;
+    NDB_REQUIRE(n < (int64_t) 0x7ffffff0ll, NDB_B200_EINVAL, "ivf: too many rows for 32-bit slot ids");
+    const int64_t n1 = n ? n : 1;
+    DevBuf d_list, d_id, k64a, k64b, v32a, v32b, l32a, l32b, cub_tmp, d_tot;
+    NDB_CHECK(d_list.reserve((size_t) n1 * 4)); NDB_CHECK(d_id.reserve((size_t) n1 * 8));
+    NDB_CHECK(k64b.reserve((size_t) n1 * 8));
+    NDB_CHECK(v32a.reserve((size_t) n1 * 4)); NDB_CHECK(v32b.reserve((size_t) n1 * 4));
+    NDB_CHECK(l32a.reserve((size_t) n1 * 4)); NDB_CHECK(l32b.reserve((size_t) n1 * 4));
+    NDB_CHECK(d_tot.reserve(16));
+    NDB_CHECK(ix->d_list_len.reserve((size_t) L * 4));
+    NDB_CHECK(ix->d_list_blk.reserve((size_t) L * 4));
+    NDB_CHECK(ix->d_list_order.reserve((size_t) L * 4));
+    NDB_CHECK(ix->d_ltile8.reserve((size_t) L * 4));
+    NDB_CHECK(ix->d_start.reserve((size_t) (L + 1) * 4));
+    NDB_CHECK(ix->tmp_assign.reserve((size_t) n1 * 4));
+    NDB_CHECK(ix->d_sorted_list.reserve((size_t) n1 * 4));
+    const unsigned g = (unsigned) ((n1 + 255) / 256);
+    if (n) {
+        NDB_CUDA(cudaMemcpyAsync(d_list.p, ix->row_list.data(), (size_t) n * 4, cudaMemcpyHostToDevice, s));
+        NDB_CUDA(cudaMemcpyAsync(d_id.p, ix->row_id.data(), (size_t) n * 8, cudaMemcpyHostToDevice, s));
+        int lbits = 1;
+        while ((1ll << lbits) < L) lbits++;
+        size_t t1 = 0, t2 = 0;
+        NDB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t1, d_id.as<unsigned long long>(), k64b.as<unsigned long long>(), v32a.as<uint32_t>(),
+                                                 v32b.as<uint32_t>(), (int) n, 0, 64, s));
+        NDB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t2, l32a.as<uint32_t>(), l32b.as<uint32_t>(), v32a.as<uint32_t>(), v32b.as<uint32_t>(),
+                                                 (int) n, 0, lbits, s));
+        NDB_CHECK(cub_tmp.reserve(std::max(t1, t2)));
+        // (a) insertion order inside each list: stable sort of the row indices by list
+        iota32_kernel<<<g, 256, 0, s>>>(v32a.as<uint32_t>(), n);
+        size_t tb = cub_tmp.cap;
+        NDB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tb, d_list.as<uint32_t>(), l32b.as<uint32_t>(), v32a.as<uint32_t>(), v32b.as<uint32_t>(),
+                                                 (int) n, 0, lbits, s));
+        // l32b = lists in sorted order, v32b = rows in (list, insertion) order
+        list_starts_kernel<<<(unsigned) ((n + 1 + 255) / 256), 256, 0, s>>>(l32b.as<uint32_t>(), n, L, ix->d_start.as<uint32_t>());
+        list_extents_kernel<<<1, 1024, 0, s>>>(ix->d_start.as<uint32_t>(), L, ix->d_list_len.as<uint32_t>(), ix->d_list_blk.as<uint32_t>(),
+                                               ix->d_ltile8.as<uint32_t>(), d_tot.as<unsigned long long>());
+        count_launch(6);
+        NDB_CUDA(cudaGetLastError());
+    } else {
+        NDB_CUDA(cudaMemsetAsync(ix->d_start.p, 0, (size_t) (L + 1) * 4, s));
+        list_extents_kernel<<<1, 1024, 0, s>>>(ix->d_start.as<uint32_t>(), L, ix->d_list_len.as<uint32_t>(), ix->d_list_blk.as<uint32_t>(),
+                                               ix->d_ltile8.as<uint32_t>(), d_tot.as<unsigned long long>());
+        count_launch();
     }
+    unsigned long long tot[2] = {0, 0};
+    ix->list_len.resize(L);
+    ix->list_blk.resize(L);
+    NDB_CUDA(cudaMemcpyAsync(tot, d_tot.p, 16, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaMemcpyAsync(ix->list_len.data(), ix->d_list_len.p, (size_t) L * 4, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaMemcpyAsync(ix->list_blk.data(), ix->d_list_blk.p, (size_t) L * 4, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    const uint64_t blk = tot[0];
+    ix->tc_tiles = tot[1];
     NDB_REQUIRE(blk * 32 < 0xfffffff0ull, NDB_B200_EINVAL, "ivf: too many slots for 32-bit slot ids");
-    const int64_t nslots = (int64_t) blk * 32;
-    // rows of each list in insertion order, then ranked by id inside the list
-    std::vector<uint32_t> by_list(n);
-    {
-        std::vector<uint32_t> pos(L, 0);
-        std::vector<uint64_t> start(L + 1, 0);
-        for (int l = 0; l < L; l++) start[l + 1] = start[l] + ix->list_len[l];
-        for (int64_t r = 0; r < n; r++) {
-            const int l = ix->row_list[r];
-            by_list[start[l] + pos[l]++] = (uint32_t) r;
-        }
-        std::vector<uint32_t> slot_of_row(n);
-        ix->row_of_slot.assign(nslots > 0 ? nslots : 1, INVALID_SLOT);
-        std::vector<int64_t> ids_by_slot(nslots > 0 ? nslots : 1, -1);
-        std::vector<uint32_t> lit(nslots > 0 ? nslots : 1, INVALID_SLOT);
-        std::vector<uint32_t> order;
-        for (int l = 0; l < L; l++) {
-            const uint32_t len = ix->list_len[l];
-            const uint32_t *rows = by_list.data() + start[l];
-            order.assign(rows, rows + len);
-            bool sorted = true;
-            for (uint32_t j = 1; j < len && sorted; j++) sorted = ix->row_id[order[j - 1]] <= ix->row_id[order[j]];
-            if (!sorted)
-                std::stable_sort(order.begin(), order.end(),
-                                 [&](uint32_t a, uint32_t b) { return ix->row_id[a] < ix->row_id[b]; });
-            const uint32_t base = ix->list_blk[l] * 32;
-            for (uint32_t j = 0; j < len; j++) {
-                slot_of_row[order[j]] = base + j;
-                ids_by_slot[base + j] = ix->row_id[order[j]];
-                ix->row_of_slot[base + j] = order[j];
-            }
-            for (uint32_t j = 0; j < len; j++) lit[base + j] = slot_of_row[rows[j]];
-        }
-        ix->store.dim = ix->dim;
-        ix->store.dimp = ix->dimp;
-        ix->store.nblk = (int64_t) blk;
-        const size_t bytes = ix->store.bytes_for((int64_t) blk);
-        NDB_CHECK(ix->store.data.reserve(bytes ? bytes : 16));
-        NDB_CHECK(ix->ids.reserve((size_t) (nslots ? nslots : 1) * 8));
-        NDB_CHECK(ix->lit_order.reserve((size_t) (nslots ? nslots : 1) * 4));
-        NDB_CHECK(ix->tmp_assign.reserve((size_t) (n ? n : 1) * 4));
-        NDB_CHECK(ix->d_list_len.reserve((size_t) L * 4));
-        NDB_CHECK(ix->d_list_blk.reserve((size_t) L * 4));
-        NDB_CHECK(ix->d_list_order.reserve((size_t) L * 4));
-        std::vector<uint32_t> lorder(L);
-        std::iota(lorder.begin(), lorder.end(), 0u);
-        std::stable_sort(lorder.begin(), lorder.end(), [&](uint32_t a, uint32_t b) { return ix->list_len[a] > ix->list_len[b]; });
-        NDB_CUDA(cudaMemcpyAsync(ix->d_list_order.p, lorder.data(), (size_t) L * 4, cudaMemcpyHostToDevice, s));
-        if (bytes) NDB_CUDA(cudaMemsetAsync(ix->store.data.p, 0, bytes, s));
-        NDB_CUDA(cudaMemcpyAsync(ix->ids.p, ids_by_slot.data(), (size_t) (nslots ? nslots : 1) * 8, cudaMemcpyHostToDevice, s));
-        NDB_CUDA(cudaMemcpyAsync(ix->lit_order.p, lit.data(), (size_t) (nslots ? nslots : 1) * 4, cudaMemcpyHostToDevice, s));
-        if (n) NDB_CUDA(cudaMemcpyAsync(ix->tmp_assign.p, slot_of_row.data(), (size_t) n * 4, cudaMemcpyHostToDevice, s));
-        NDB_CUDA(cudaMemcpyAsync(ix->d_list_len.p, ix->list_len.data(), (size_t) L * 4, cudaMemcpyHostToDevice, s));
-        NDB_CUDA(cudaMemcpyAsync(ix->d_list_blk.p, ix->list_blk.data(), (size_t) L * 4, cudaMemcpyHostToDevice, s));
-        NDB_CHECK(il32_scatter(ix->arena.as<float>(), n, ix->dim, ix->dimp, ix->tmp_assign.as<uint32_t>(), 0,
-                               ix->store.ptr(), s));
-        NDB_CUDA(cudaStreamSynchronize(s));     // host vectors above go out of scope
+    const int64_t nslots = (int64_t) blk * 32, ns1 = nslots ? nslots : 1;
+    ix->store.dim = ix->dim;
+    ix->store.dimp = ix->dimp;
+    ix->store.nblk = (int64_t) blk;
+    const size_t bytes = ix->store.bytes_for((int64_t) blk);
+    NDB_CHECK(ix->store.data.reserve(bytes ? bytes : 16));
+    NDB_CHECK(ix->ids.reserve((size_t) ns1 * 8));
+    NDB_CHECK(ix->lit_order.reserve((size_t) ns1 * 4));
+    NDB_CHECK(ix->d_row_of_slot.reserve((size_t) ns1 * 4));
+    if (bytes) NDB_CUDA(cudaMemsetAsync(ix->store.data.p, 0, bytes, s));
+    NDB_CUDA(cudaMemsetAsync(ix->ids.p, 0xFF, (size_t) ns1 * 8, s));              // -1
+    NDB_CUDA(cudaMemsetAsync(ix->lit_order.p, 0xFF, (size_t) ns1 * 4, s));        // INVALID_SLOT
+    NDB_CUDA(cudaMemsetAsync(ix->d_row_of_slot.p, 0xFF, (size_t) ns1 * 4, s));
+    if (n) {
+        int lbits = 1;
+        while ((1ll << lbits) < L) lbits++;
+        // (b) (list, id) order: stable sort by id, then stable sort by list
+        iota32_kernel<<<g, 256, 0, s>>>(v32a.as<uint32_t>(), n);
+        size_t tb = cub_tmp.cap;
+        NDB_CHECK(k64a.reserve((size_t) n * 8));
+        // ids are ordered as SIGNED int64 by the reference's (dist, id) rule: flip the sign bit for the unsigned radix sort
+        NDB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tb, d_id.as<long long>(), k64b.as<long long>(), v32a.as<uint32_t>(),
+                                                 l32a.as<uint32_t>(), (int) n, 0, 64, s));
+        // l32a = rows by ascending id; their lists, then the second sort
+        gather_u32_kernel<<<g, 256, 0, s>>>(d_list.as<uint32_t>(), l32a.as<uint32_t>(), n, v32a.as<uint32_t>());
+        tb = cub_tmp.cap;
+        NDB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tb, v32a.as<uint32_t>(), ix->d_sorted_list.as<uint32_t>(), l32a.as<uint32_t>(),
+                                                 k64a.as<uint32_t>(), (int) n, 0, lbits, s));
+        // d_sorted_list = lists, k64a (as u32) = rows, both in (list, id) order
+        place_rows_kernel<<<g, 256, 0, s>>>(k64a.as<uint32_t>(), ix->d_sorted_list.as<uint32_t>(), ix->d_start.as<uint32_t>(),
+                                            ix->d_list_blk.as<uint32_t>(), d_id.as<int64_t>(), n, ix->tmp_assign.as<uint32_t>(),
+                                            ix->ids.as<int64_t>(), ix->d_row_of_slot.as<uint32_t>());
+        place_literal_kernel<<<g, 256, 0, s>>>(v32b.as<uint32_t>(), l32b.as<uint32_t>(), ix->d_start.as<uint32_t>(), ix->d_list_blk.as<uint32_t>(),
+                                               ix->tmp_assign.as<uint32_t>(), n, ix->lit_order.as<uint32_t>());
+        count_launch(8);
+        NDB_CUDA(cudaGetLastError());
+        NDB_CHECK(il32_scatter(ix->arena.as<float>(), n, ix->dim, ix->dimp, ix->tmp_assign.as<uint32_t>(), 0, ix->store.ptr(), s));
     }
+    // lists by descending length (stable): the work items are emitted longest first
+    std::vector<uint32_t> lorder(L);
+    std::iota(lorder.begin(), lorder.end(), 0u);
+    std::stable_sort(lorder.begin(), lorder.end(), [&](uint32_t a, uint32_t b) { return ix->list_len[a] > ix->list_len[b]; });
+    NDB_CUDA(cudaMemcpyAsync(ix->d_list_order.p, lorder.data(), (size_t) L * 4, cudaMemcpyHostToDevice, s));
+    NDB_CUDA(cudaStreamSynchronize(s));     // host vectors / temporaries above go out of scope
     ix->vnorm_ivf_ok = ix->vnorm_fast_ok = false;
     ix->tc_ok = false;
     ix->dirty = false;
@@ -467,25 +591,21 @@ static int ivf_tensor_ready(ndb_b200_ivf *ix, cudaStream_t s)
 {
     const int L = ix->nlists;
     if (ix->tc_ok) return NDB_B200_OK;
-    std::vector<uint32_t> ltile8(L);
-    uint64_t nt = 0;
-    for (int l = 0; l < L; l++) {
-        ltile8[l] = (uint32_t) (nt * 8);
-        nt += (ix->list_len[l] + TC_N - 1) / TC_N;
-    }
+    const uint64_t nt = ix->tc_tiles;                      // 256-row tiles of all lists (ivf_layout)
     NDB_REQUIRE(nt * TC_N < 0xfffffff0ull, NDB_B200_EINVAL, "ivf: too many rows for the tensor copy");
-    std::vector<uint32_t> src((size_t) (nt ? nt : 1) * TC_N, INVALID_SLOT), row(src.size(), INVALID_SLOT);
-    for (int l = 0; l < L; l++) {
-        uint32_t *d = src.data() + (size_t) ltile8[l] * 32, *r = row.data() + (size_t) ltile8[l] * 32;
-        const uint32_t base = ix->list_blk[l] * 32;
-        for (uint32_t j = 0; j < ix->list_len[l]; j++) { d[j] = base + j; r[j] = ix->row_of_slot[base + j]; }
+    const size_t nrow_t = (size_t) (nt ? nt : 1) * TC_N;
+    NDB_CHECK(ix->tc_src.reserve(nrow_t * 4));
+    NDB_CHECK(ix->tc_row.reserve(nrow_t * 4));
+    NDB_CUDA(cudaMemsetAsync(ix->tc_src.p, 0xFF, nrow_t * 4, s));          // pad rows: INVALID_SLOT
+    NDB_CUDA(cudaMemsetAsync(ix->tc_row.p, 0xFF, nrow_t * 4, s));
+    if (ix->nrows) {
+        tensor_maps_kernel<<<(unsigned) ((ix->nrows + 255) / 256), 256, 0, s>>>(ix->d_sorted_list.as<uint32_t>(), ix->d_start.as<uint32_t>(),
+                                                                                ix->d_list_blk.as<uint32_t>(), ix->d_ltile8.as<uint32_t>(),
+                                                                                ix->d_row_of_slot.as<uint32_t>(), ix->nrows,
+                                                                                ix->tc_src.as<uint32_t>(), ix->tc_row.as<uint32_t>());
+        count_launch();
+        NDB_CUDA(cudaGetLastError());
     }
-    NDB_CHECK(ix->tc_src.reserve(src.size() * 4));
-    NDB_CHECK(ix->tc_row.reserve(row.size() * 4));
-    NDB_CUDA(cudaMemcpyAsync(ix->tc_row.p, row.data(), row.size() * 4, cudaMemcpyHostToDevice, s));
-    NDB_CHECK(ix->d_ltile8.reserve((size_t) L * 4));
-    NDB_CUDA(cudaMemcpyAsync(ix->tc_src.p, src.data(), src.size() * 4, cudaMemcpyHostToDevice, s));
-    NDB_CUDA(cudaMemcpyAsync(ix->d_ltile8.p, ltile8.data(), (size_t) L * 4, cudaMemcpyHostToDevice, s));
     NDB_CHECK(tc_build_store_mapped(ix->tc, ix->store.ptr(), ix->tc_src.as<uint32_t>(), (int64_t) (nt ? nt : 1) * TC_N, ix->dim,
                                     ix->dimp, s));
     NDB_CUDA(cudaStreamSynchronize(s));
