@@ -28,8 +28,14 @@ oracle:
 glue: $(LIBDIR)/libndb_b200.so
 	$(MAKE) -s -C oracle glue
 
+# development build with epilogue statistics in tc_knn_kernel (tools/c4_probe.py; NDB_B200_LIB_PATH selects it)
+counters: $(LIBDIR)/libndb_b200.so
+	@mkdir -p $(OBJDIR)/ctr
+	$(NVCC) $(NVFLAGS) -DNDB_TC_COUNTERS -c $(SRCDIR)/tc_knn.cu -o $(OBJDIR)/ctr/tc_knn.o
+	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $(LIBDIR)/libndb_b200_ctr.so $(filter-out $(OBJDIR)/tc_knn.o,$(OBJS)) $(OBJDIR)/ctr/tc_knn.o -ldl
+
 clean:
 	rm -rf build $(LIBDIR)/*.so
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle glue clean
+.PHONY: all oracle glue clean counters

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libndb_b200.so")
+LIB_PATH = os.environ.get("NDB_B200_LIB_PATH") or os.path.join(_HERE, "lib", "libndb_b200.so")   # (override: instrumented development builds)
 
 OK = 0
 L2, COSINE, IP = 1, 2, 3

@@ -80,6 +80,7 @@ struct ndb_b200_ivf {
     DevBuf d_start, d_sorted_list, d_row_of_slot;   // layout by-products kept for the tensor maps: first position of every list in
                                                     // the (list, id) order, the lists in that order, IL32 slot -> arena row
     uint64_t tc_tiles = 0;               // 256-row tiles of all lists
+    double tc_rows_per_pair = 0.0;       // expected rows a (query, probed list) pair scans: the size-biased mean list length
 };
 
 namespace ndb {
@@ -106,37 +107,51 @@ static uint32_t ivf_seg_blocks()
 // serial epilogue work per tile of exactly those from 128 columns per thread to 32.
 __host__ __device__ inline uint32_t ivf_rep(uint32_t c, uint32_t rep_max) { return c <= rep_max ? 4u : 1u; }
 
+// Two-phase scans (tensor path, split = nlists): the pairs (query, its NEAREST list) are bucketed apart from the others, as
+// "virtual list" l, the remaining pairs of list l as virtual list nlists + l.  The nearest lists are scanned first, their
+// partial lists give every query a bound close to its final k-th distance, and the bulk of the work -- the other
+// nprobe - 1 lists -- runs against that bound from its first tile on.  split = 0: one bucket per list.
+__host__ __device__ inline uint32_t ivf_vlist(uint32_t l, int64_t pair, uint32_t nprobe, uint32_t split)
+{
+    return (split && pair % nprobe != 0) ? l + split : l;
+}
+
+
 }  // namespace ndb
 #include "ivf_cert.cuh"
 namespace ndb {
 
 // ---- work-item construction -----------------------------------------------------------------
 __global__ void ivf_hist_kernel(const uint32_t *__restrict__ probe, int64_t npairs, const uint32_t *__restrict__ list_len,
-                                int nlists, uint32_t *__restrict__ cnt)
+                                int nlists, uint32_t *__restrict__ cnt, uint32_t nprobe, uint32_t split)
 {
     const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     const uint32_t l = probe[p];
-    if (l < (uint32_t) nlists && list_len[l] > 0) atomicAdd(&cnt[l], 1u);
+    if (l < (uint32_t) nlists && list_len[l] > 0) atomicAdd(&cnt[ivf_vlist(l, p, nprobe, split)], 1u);
 }
 
-// single CTA: exclusive scans, in `order`, of cnt (-> qoff) and of tiles * segments (-> item_off)
+// single CTA: exclusive scans, in `order`, of cnt (-> qoff) and of tiles * segments (-> item_off).
+// split != 0: 2 * nlists virtual lists, all of phase 1 (the queries' nearest lists, in `order`) before phase 2;
+// nitems[2] = the number of phase-1 items.
 __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ list_len,
                                                            const uint32_t *__restrict__ order, int nlists, int qt, uint32_t segb,
                                                            uint32_t qalign, uint32_t rep_max, uint32_t *__restrict__ qoff,
                                                            uint32_t *__restrict__ item_off, uint32_t *__restrict__ nitems,
-                                                           unsigned long long *__restrict__ scanned)
+                                                           unsigned long long *__restrict__ scanned, uint32_t split)
 {
     typedef cub::BlockScan<uint32_t, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ unsigned long long s_scanned;
-    const int ipt = (nlists + 1023) / 1024;
-    const int b = threadIdx.x * ipt, e = min(nlists, b + ipt);
-    if (threadIdx.x == 0) s_scanned = 0;
+    const int nv = split ? 2 * nlists : nlists;
+    const int ipt = (nv + 1023) / 1024;
+    const int b = threadIdx.x * ipt, e = min(nv, b + ipt);
+    if (threadIdx.x == 0) { s_scanned = 0; nitems[2] = 0; }
     uint32_t sq = 0, st = 0;
     unsigned long long sc = 0;
     for (int i = b; i < e; i++) {
-        const uint32_t l = order[i], c = cnt[l], cr = c * ivf_rep(c, rep_max);
+        const uint32_t l = order[i < nlists ? i : i - nlists], v = i < nlists ? l : l + split;
+        const uint32_t c = cnt[v], cr = c * ivf_rep(c, rep_max);
         sq += (cr + qalign - 1) / qalign * qalign;
         st += ((cr + qt - 1) / qt) * ivf_nseg(list_len[l], segb);
         sc += (unsigned long long) c * list_len[l];
@@ -150,9 +165,11 @@ __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__res
     for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(FULL, sc, o);
     if ((threadIdx.x & 31) == 0 && sc) atomicAdd(&s_scanned, sc);
     for (int i = b; i < e; i++) {
-        const uint32_t l = order[i], c = cnt[l], cr = c * ivf_rep(c, rep_max);
-        qoff[l] = oq;
-        item_off[l] = ot;
+        const uint32_t l = order[i < nlists ? i : i - nlists], v = i < nlists ? l : l + split;
+        const uint32_t c = cnt[v], cr = c * ivf_rep(c, rep_max);
+        if (split && i == nlists) nitems[2] = ot;               // everything before: phase 1
+        qoff[v] = oq;
+        item_off[v] = ot;
         oq += (cr + qalign - 1) / qalign * qalign;
         ot += ((cr + qt - 1) / qt) * ivf_nseg(list_len[l], segb);
     }
@@ -164,15 +181,16 @@ __global__ void __launch_bounds__(1024) ivf_offsets_kernel(const uint32_t *__res
 __global__ void ivf_scatter_kernel(const uint32_t *__restrict__ probe, int64_t npairs, const uint32_t *__restrict__ list_len,
                                    int nlists, const uint32_t *__restrict__ qoff, uint32_t *__restrict__ fill,
                                    uint32_t *__restrict__ qmap, uint32_t *__restrict__ pairpos,
-                                   const uint32_t *__restrict__ cnt, uint32_t rep_max)
+                                   const uint32_t *__restrict__ cnt, uint32_t rep_max, uint32_t nprobe, uint32_t split)
 {
     const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     const uint32_t l = probe[p];
     if (l < (uint32_t) nlists && list_len[l] > 0) {
-        const uint32_t pos = atomicAdd(&fill[l], 1u);      // position of this query among the list's queries
-        const uint32_t r = cnt ? ivf_rep(cnt[l], rep_max) : 1u;
-        for (uint32_t j = 0; j < r; j++) qmap[qoff[l] + pos * r + j] = (uint32_t) p;
+        const uint32_t v = ivf_vlist(l, p, nprobe, split);
+        const uint32_t pos = atomicAdd(&fill[v], 1u);      // position of this query among the (virtual) list's queries
+        const uint32_t r = cnt ? ivf_rep(cnt[v], rep_max) : 1u;
+        for (uint32_t j = 0; j < r; j++) qmap[qoff[v] + pos * r + j] = (uint32_t) p;
         pairpos[p] = pos;
     }
 }
@@ -257,26 +275,28 @@ __global__ void ivf_merge_kernel(const float *__restrict__ pdist, const uint32_t
 __global__ void ivf_tc_items_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ qoff,
                                     const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len,
                                     const uint32_t *__restrict__ ltile8, int nlists, uint32_t segb, uint32_t rep_max,
-                                    TcItem *__restrict__ items)
+                                    TcItem *__restrict__ items, uint32_t split)
 {
-    const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (l >= nlists) return;
-    const uint32_t rp = ivf_rep(cnt[l], rep_max);
-    const uint32_t c = cnt[l] * rp;                            // tile positions in use
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;           // virtual list (ivf_vlist)
+    if (v >= (split ? 2 * nlists : nlists)) return;
+    const int l = v >= nlists ? v - nlists : v;
+    const uint32_t rp = ivf_rep(cnt[v], rep_max);
+    const uint32_t c = cnt[v] * rp;                            // tile positions in use
     const uint32_t tiles = (c + TC_M - 1) / TC_M;
     const uint32_t len = list_len[l], nseg = ivf_nseg(len, segb);
     for (uint32_t i = threadIdx.x & 31; i < tiles * nseg; i += 32) {
         const uint32_t t = i / nseg, sg = i - t * nseg;
         const uint32_t nvec = min(segb * 32, len - sg * segb * 32);
         TcItem it;
-        it.qtile = qoff[l] / TC_M + t;
+        it.qtile = qoff[v] / TC_M + t;
         it.t0 = (ltile8[l] + sg * segb) / 8;
         it.t1 = it.t0 + (nvec + TC_N - 1) / TC_N;
         it.nq = min((uint32_t) TC_M, c - t * TC_M);
-        it.out_base = (item_off[l] + i) * (2 * TC_M);
+        it.out_base = (item_off[v] + i) * (2 * TC_M);
         it.out_stride = 2;
         it.rep = rp;
-        items[item_off[l] + i] = it;
+        it.nrows = nvec;
+        items[item_off[v] + i] = it;
     }
 }
 
@@ -612,6 +632,9 @@ static int ivf_tensor_ready(ndb_b200_ivf *ix, cudaStream_t s)
     const uint32_t segb = ivf_tc_seg_tiles() * 8;
     ix->tc_max_nseg = 1;
     ix->tc_sum_nseg = ix->tc_nonempty = 0;
+    double s1 = 0.0, s2 = 0.0;
+    for (int l = 0; l < L; l++) { s1 += ix->list_len[l]; s2 += (double) ix->list_len[l] * ix->list_len[l]; }
+    ix->tc_rows_per_pair = s1 > 0.0 ? s2 / s1 : 0.0;      // queries fall on lists in proportion to their length
     for (int l = 0; l < L; l++) {
         if (!ix->list_len[l]) continue;
         const uint32_t ns = ivf_nseg(ix->list_len[l], segb);
@@ -674,20 +697,28 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     }
 
     // 2. bucket (query, list) pairs by list; query positions padded to whole 128-query tiles per list
-    NDB_CHECK(ix->cnt.reserve((size_t) L * 4 * 2));
-    NDB_CHECK(ix->qoff.reserve((size_t) L * 4));
-    NDB_CHECK(ix->item_off.reserve((size_t) L * 4));
+    // Two phases when a (query, list) pair scans many rows (ivf_vlist): the bound the nearest lists establish then saves far
+    // more epilogue work in the other lists than the extra, thinly filled query tiles of phase 1 cost.
+    const char *phases_e = getenv("NDB_IVF_TC_PHASES");        // 1 / 2 force the choice (measurement switch)
+    const int phases_env = phases_e ? atoi(phases_e) : 0;
+    const bool two_phase = np > 1 && (phases_env == 2 || (phases_env != 1 && ix->tc_rows_per_pair >= 8192.0));
+    const uint32_t split = two_phase ? (uint32_t) L : 0u;
+    const int NV = two_phase ? 2 * L : L;                   // virtual lists
+    NDB_CHECK(ix->cnt.reserve((size_t) NV * 4 * 2));
+    NDB_CHECK(ix->qoff.reserve((size_t) NV * 4));
+    NDB_CHECK(ix->item_off.reserve((size_t) NV * 4));
     NDB_CHECK(ix->pairpos.reserve((size_t) npairs * 4));
     NDB_CHECK(ix->nitems.reserve(64));
     NDB_CHECK(ix->stats.reserve(64));
-    uint32_t *cnt = ix->cnt.as<uint32_t>(), *fill = cnt + L;
+    uint32_t *cnt = ix->cnt.as<uint32_t>(), *fill = cnt + NV;
     const uint32_t segb = ivf_tc_seg_tiles() * 8;
-    NDB_CUDA(cudaMemsetAsync(cnt, 0, (size_t) L * 4 * 2, s));
-    ivf_hist_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L, cnt);
+    NDB_CUDA(cudaMemsetAsync(cnt, 0, (size_t) NV * 4 * 2, s));
+    ivf_hist_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L, cnt,
+                                                                     (uint32_t) np, split);
     static const uint32_t rep_max = [] { const char *e = getenv("NDB_IVF_TC_REP_MAX"); int x = e ? atoi(e) : 32; return (uint32_t) (x >= 0 && x <= 32 ? x : 32); }();
     ivf_offsets_kernel<<<1, 1024, 0, s>>>(cnt, ix->d_list_len.as<uint32_t>(), ix->d_list_order.as<uint32_t>(), L, TC_M, segb,
                                           (uint32_t) TC_M, rep_max, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
-                                          ix->nitems.as<uint32_t>(), ix->stats.as<unsigned long long>());
+                                          ix->nitems.as<uint32_t>(), ix->stats.as<unsigned long long>(), split);
     count_launch(2);
     NDB_CUDA(cudaGetLastError());
     // How many work items and query-tile positions this batch needs depends on how its probes fall on
@@ -695,8 +726,9 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     // items <= max_nseg * pairs / 128 + one per segment of a non-empty list); when the buffers those
     // bounds ask for are affordable the kernels read the exact counts from device memory and the
     // search needs no host round trip at all.  Otherwise one 8-byte read-back sizes them exactly.
-    size_t n_items = (size_t) ix->tc_max_nseg * (size_t) ((npairs + TC_M - 1) / TC_M) + ix->tc_sum_nseg;
-    size_t npos = (size_t) npairs + (size_t) (TC_M - 1) * std::min<uint64_t>(ix->tc_nonempty, (uint64_t) npairs);
+    const uint64_t vmul = two_phase ? 2 : 1;
+    size_t n_items = (size_t) ix->tc_max_nseg * (size_t) ((npairs + TC_M - 1) / TC_M) + vmul * ix->tc_sum_nseg;
+    size_t npos = (size_t) npairs + (size_t) (TC_M - 1) * std::min<uint64_t>(vmul * ix->tc_nonempty, (uint64_t) npairs);
     npos = (npos + TC_M - 1) / TC_M * TC_M;
     const bool exact_counts = getenv("NDB_IVF_TC_SYNC") != nullptr ||
                               n_items * 2 * TC_M * kc * 8 + npos * ix->tc.nkc * TC_KC * 2 > ((size_t) 1 << 30);
@@ -707,18 +739,18 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
         n_items = h_tot[0];
         npos = h_tot[1];
     }
-    if (getenv("NDB_IVF_DEBUG")) fprintf(stderr, "ivf tensor: %zu items, %zu query positions for %lld pairs (%s)\n", n_items, npos, (long long) npairs, exact_counts ? "exact" : "bounds");
+    if (getenv("NDB_IVF_DEBUG")) fprintf(stderr, "ivf tensor: %zu items, %zu query positions for %lld pairs (%s); %.0f rows per pair expected, %d phase(s)\n", n_items, npos, (long long) npairs, exact_counts ? "exact" : "bounds", ix->tc_rows_per_pair, two_phase ? 2 : 1);
     if (n_items == 0) n_items = 1;          // (nothing to scan: the kernels see the zero count on the device)
     if (npos == 0) npos = TC_M;
     NDB_CHECK(ix->qmap.reserve(npos * 4));
     NDB_CUDA(cudaMemsetAsync(ix->qmap.p, 0xFF, npos * 4, s));
     ivf_scatter_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L,
                                                                         ix->qoff.as<uint32_t>(), fill, ix->qmap.as<uint32_t>(),
-                                                                        ix->pairpos.as<uint32_t>(), cnt, rep_max);
+                                                                        ix->pairpos.as<uint32_t>(), cnt, rep_max, (uint32_t) np, split);
     NDB_CHECK(ix->tcs.items.reserve(n_items * sizeof(TcItem)));
-    ivf_tc_items_kernel<<<(unsigned) ((L + 3) / 4), 128, 0, s>>>(cnt, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
-                                                                ix->d_list_len.as<uint32_t>(), ix->d_ltile8.as<uint32_t>(), L, segb,
-                                                                rep_max, ix->tcs.items.as<TcItem>());
+    ivf_tc_items_kernel<<<(unsigned) ((NV + 3) / 4), 128, 0, s>>>(cnt, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
+                                                                 ix->d_list_len.as<uint32_t>(), ix->d_ltile8.as<uint32_t>(), L, segb,
+                                                                 rep_max, ix->tcs.items.as<TcItem>(), split);
     count_launch(2);
     NDB_CUDA(cudaGetLastError());
     if (getenv("NDB_IVF_DEBUG")) {
@@ -746,7 +778,7 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     NDB_CHECK(ix->tcs.qerr.reserve(npos * 4));
     NDB_CHECK(tc_block_queries(Q_dev, ix->qmap.as<uint32_t>(), (uint32_t) np, nq, (int) npos, ix->dim, nkc,
                                ix->tcs.qb.as<__nv_bfloat16>(), ix->tcs.qnorm.as<float>(), s, ix->nitems.as<uint32_t>() + 1,
-                               ix->tcs.qerr.as<float>()));
+                               ix->tcs.qerr.as<float>(), ix->metric == NDB_IP));
     const size_t nparts = n_items * 2 * TC_M;
     NDB_CHECK(ix->tcs.pdist.reserve(nparts * kc * 4));
     NDB_CHECK(ix->tcs.pslot.reserve(nparts * kc * 4));
@@ -776,7 +808,35 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     p.nprobe = (uint32_t) np;
     p.gthr = getenv("NDB_IVF_TC_NOSHARE") ? nullptr : ix->tcs.gthr.as<float>();
     p.packed = getenv("NDB_IVF_TC_UNPACKED") ? 0 : 1;
-    NDB_CHECK(tc_launch(p, ix->metric, kc, s));
+    p.kpub = getenv("NDB_IVF_TC_KPUB_LAST") ? 0 : k;
+    p.debug_mode = getenv("NDB_TC_DEBUG") ? atoi(getenv("NDB_TC_DEBUG")) : 0;
+    unsigned long long *ctr = ix->cert_counters.as<unsigned long long>();
+    if (two_phase) {
+        // phase 1: the items of the queries' nearest lists; then the k-th best key of each query's partial lists becomes
+        // its bound (relaxed, so that the selection stays certifiable); phase 2: everything else
+        p.item_lo_ptr = nullptr;
+        p.item_hi_ptr = ix->nitems.as<uint32_t>() + 2;
+        NDB_CHECK(tc_launch(p, ix->metric, kc, s));
+        const unsigned bgrid = (unsigned) ((nq + 3) / 4);
+#define NDB_BND(M)                                                                                                   \
+        ivf_tc_bound_kernel<M><<<bgrid, 128, 0, s>>>(ix->tcs.pdist.as<float>(), ix->tcs.pslot.as<uint32_t>(), Q_dev,  \
+                                                     ix->probe.as<uint32_t>(), ix->pairpos.as<uint32_t>(),            \
+                                                     ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), cnt, \
+                                                     rep_max, nq, np, L, segb, ix->dim, kc, k, ix->tc.stats.as<float>(), p.gthr)
+        if (ix->metric == NDB_L2) NDB_BND(NDB_L2);
+        else if (ix->metric == NDB_COSINE) NDB_BND(NDB_COSINE);
+        else NDB_BND(NDB_IP);
+#undef NDB_BND
+        count_launch();
+        NDB_CUDA(cudaGetLastError());
+        p.item_lo_ptr = ix->nitems.as<uint32_t>() + 2;
+        p.item_hi_ptr = nullptr;
+        const bool timing = ctx().timing;           // the library's kernel timer reports the second, dominant launch
+        NDB_CHECK(tc_launch(p, ix->metric, kc, s));
+        (void) timing;
+    } else {
+        NDB_CHECK(tc_launch(p, ix->metric, kc, s));
+    }
     if (ctx().timing) {                 // evals resolved from ix->stats in last_kernel_stats
         Context &c = ctx();
         c.last_bytes = -1.0;
@@ -787,7 +847,6 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
 
     // 4. merge + certified fp32 re-rank; the queries the certificate rejects are recomputed exactly
     const unsigned mgrid = (unsigned) ((nq + 3) / 4);
-    unsigned long long *ctr = ix->cert_counters.as<unsigned long long>();
     const size_t fsm = (size_t) ix->dimp * 4 + FB_THREADS * 4 + FB_THREADS * 8;
     const unsigned fgrid = (unsigned) std::min<int>(nq, 2 * ctx().sm_count);
     NDB_REQUIRE(p.packed && p.gthr, NDB_B200_EINVAL, "ivf tensor path: the certified finish needs packed keys and the shared bound");
@@ -802,13 +861,13 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
         ivf_tc_finish_cert_kernel<Arith<M, NDB_ARITH_IVF_F32>, M><<<mgrid, 128, 0, s>>>(                              \
             ix->tcs.pdist.as<float>(), ix->tcs.pslot.as<uint32_t>(), ix->tc_src.as<uint32_t>(), ix->tc_row.as<uint32_t>(), \
             ix->arena.as<float>(), ix->ids.as<int64_t>(), Q_dev, ix->probe.as<uint32_t>(),                            \
-            ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), p.gthr, cnt, rep_max, \
+            ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), p.gthr, cnt, rep_max, split, \
             nq, np, L, segb, ix->dim, kc, k, ix->tc.stats.as<float>(), dist_dev, ids_dev, ix->fb_list.as<uint32_t>(),  \
             ix->fb_tau.as<float>(), ctr);                                                                             \
         ivf_exact_fallback_kernel<Arith<M, NDB_ARITH_IVF_F32>, M><<<fgrid, FB_THREADS, fsm, s>>>(                            \
             ix->fb_list.as<uint32_t>(), ix->fb_tau.as<float>(), ctr, ix->tcs.pdist.as<float>(), ix->tcs.pslot.as<uint32_t>(), ix->probe.as<uint32_t>(), \
             ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(),                   \
-            ix->d_ltile8.as<uint32_t>(), p.gthr, cnt, rep_max, segb, kc, ix->tc_src.as<uint32_t>(),                    \
+            ix->d_ltile8.as<uint32_t>(), p.gthr, cnt, rep_max, split, segb, kc, ix->tc_src.as<uint32_t>(),                    \
             ix->tc_row.as<uint32_t>(), ix->arena.as<float>(), ix->ids.as<int64_t>(), Q_dev, ix->tc.stats.as<float>(), \
             reinterpret_cast<const float4 *>(ix->store.ptr()), ix->d_list_blk.as<uint32_t>(), ix->dimp,                \
             np, L, ix->dim, k, dist_dev, ids_dev, cert_dbg);                                                          \
@@ -1210,18 +1269,19 @@ int ndb_b200_ivf_search_dev(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np
     NDB_CHECK(ix->stats.reserve(64));
     uint32_t *cnt = ix->cnt.as<uint32_t>(), *fill = cnt + L;
     NDB_CUDA(cudaMemsetAsync(cnt, 0, (size_t) L * 4 * 2, s));
-    ivf_hist_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L, cnt);
+    ivf_hist_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L, cnt,
+                                                                     (uint32_t) np, 0u);
     const uint32_t segb = ivf_seg_blocks();
     ivf_offsets_kernel<<<1, 1024, 0, s>>>(cnt, ix->d_list_len.as<uint32_t>(), ix->d_list_order.as<uint32_t>(), L, qt, segb, 1u, 0u,
                                           ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->nitems.as<uint32_t>(),
-                                          ix->stats.as<unsigned long long>());
+                                          ix->stats.as<unsigned long long>(), 0u);
     // the number of work items depends on how the batch's probes fall on long and short lists:
     // one 4-byte read-back sizes the item and partial-result buffers exactly
     uint32_t *h_nitems = reinterpret_cast<uint32_t *>(ctx().pinned);
     NDB_CUDA(cudaMemcpyAsync(h_nitems, ix->nitems.p, 4, cudaMemcpyDeviceToHost, s));
     ivf_scatter_kernel<<<(unsigned) ((npairs + 255) / 256), 256, 0, s>>>(ix->probe.as<uint32_t>(), npairs, ix->d_list_len.as<uint32_t>(), L,
                                                                         ix->qoff.as<uint32_t>(), fill, ix->qmap.as<uint32_t>(),
-                                                                        ix->pairpos.as<uint32_t>(), nullptr, 0u);
+                                                                        ix->pairpos.as<uint32_t>(), nullptr, 0u, (uint32_t) np, 0u);
     count_launch(3);
     NDB_CUDA(cudaGetLastError());
     NDB_CUDA(cudaStreamSynchronize(s));

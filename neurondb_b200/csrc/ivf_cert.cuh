@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_cert_kernel(
     const uint32_t *__restrict__ tc_row, const float *__restrict__ arena, const int64_t *__restrict__ ids,
     const float *__restrict__ Q, const uint32_t *__restrict__ probe, const uint32_t *__restrict__ pairpos,
     const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len, const float *__restrict__ gthr,
-    const uint32_t *__restrict__ cnt, uint32_t rep_max, int nq, int nprobe, int nlists, uint32_t segb, int dim, int kc, int k,
+    const uint32_t *__restrict__ cnt, uint32_t rep_max, uint32_t split, int nq, int nprobe, int nlists, uint32_t segb, int dim, int kc, int k,
     const float *__restrict__ stats, float *__restrict__ out_dist, int64_t *__restrict__ out_ids,
     uint32_t *__restrict__ fb_list, float *__restrict__ fb_tau,
     unsigned long long *__restrict__ counters /* [0] queries sent to the exact kernel, [1] exact evaluations */)
@@ -62,10 +62,11 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_cert_kernel(
             if (l < (uint32_t) nlists) {
                 const uint32_t len = list_len[l];
                 if (len) {
-                    my_rep = ivf_rep(cnt[l], rep_max);
+                    const uint32_t v = ivf_vlist(l, (int64_t) p, (uint32_t) nprobe, split);
+                    my_rep = ivf_rep(cnt[v], rep_max);
                     const uint32_t pos = pairpos[p] * my_rep;
                     my_nseg = ivf_nseg(len, segb);
-                    my_first = (item_off[l] + (pos / TC_M) * my_nseg) * (2 * TC_M) + (pos % TC_M) * 2;
+                    my_first = (item_off[v] + (pos / TC_M) * my_nseg) * (2 * TC_M) + (pos % TC_M) * 2;
                 }
             }
         }
@@ -132,6 +133,55 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_cert_kernel(
     }
 }
 
+// ---- two-phase scans: the bound phase 1 leaves behind ----------------------------------------------------------
+// After the scan of every query's NEAREST list (phase 1) its partial lists -- one per (segment, column half, replica) of
+// that list -- each hold at most kc keys.  The k-th smallest key K over their union is an upper bound of the query's final
+// k-th key (the union holds k rows at or below it), far tighter than the kc-th key of any single partial list; its
+// relaxation (cert_bound.cuh) goes into the shared bound gthr[q] that phase 2 filters against.  Warp per query.
+template <int METRIC>
+__global__ void __launch_bounds__(128) ivf_tc_bound_kernel(
+    const float *__restrict__ pdist, const uint32_t *__restrict__ pslot, const float *__restrict__ Q,
+    const uint32_t *__restrict__ probe, const uint32_t *__restrict__ pairpos, const uint32_t *__restrict__ item_off,
+    const uint32_t *__restrict__ list_len, const uint32_t *__restrict__ cnt, uint32_t rep_max, int nq, int nprobe, int nlists,
+    uint32_t segb, int dim, int kc, int k, const float *__restrict__ stats, float *__restrict__ gthr)
+{
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const size_t p = (size_t) q * nprobe;                    // rank 0: virtual list = the list itself
+    const uint32_t l = probe[p];
+    if (l >= (uint32_t) nlists) return;
+    const uint32_t len = list_len[l];
+    if (!len) return;
+    const uint32_t rep = ivf_rep(cnt[l], rep_max), pos = pairpos[p] * rep, nseg = ivf_nseg(len, segb);
+    const size_t first = (size_t) (item_off[l] + (pos / TC_M) * nseg) * (2 * TC_M) + (pos % TC_M) * 2;
+    const int nent = (int) rep * 2 * kc;
+    WarpTopK<1, uint32_t> best;
+    best.init();
+    uint32_t n_in = 0;
+    for (uint32_t sg = 0; sg < nseg; sg++) {
+        const size_t base = (first + (size_t) sg * (2 * TC_M)) * kc;
+        for (int e0 = 0; e0 < nent; e0 += 32) {
+            const int e = e0 + lane;
+            uint32_t sl = INVALID_SLOT;
+            float kd = INFINITY;
+            if (e < nent) { sl = pslot[base + e]; kd = pdist[base + e]; }
+            const bool ok = sl != INVALID_SLOT;
+            const unsigned m = __ballot_sync(FULL, ok);
+            if (m) { n_in += __popc(m); best.offer(kd, sl, ok, lane, k); }
+        }
+    }
+    if (n_in < (uint32_t) k) return;                          // fewer than k rows met: no bound
+    float K = best.td;                                       // the k-th smallest key (its index bits masked off)
+    // an upper bound of the value the packed key stood for (tc_knn_kernel publishes the same way)
+    K = K >= 0.0f ? __uint_as_float(__float_as_uint(K) | TC_IDX_MASK) : K;
+    const CertQ cq = cert_query(Q + (size_t) q * dim, dim, lane);
+    if (lane == 0 && K < 1.0e38f) {
+        const float R = cert_relax<METRIC>(K, stats, cq, dim);
+        if (R < gthr[q]) gthr[q] = R;                         // (nothing else writes the bounds between the two scans)
+    }
+}
+
 // ---- lists: the queries the 32-candidate certificate rejected ---------------------------------------------
 // One CTA (32 warps) per such query.  tau0 = the k-th exact value the finish kernel reached, an upper bound of the
 // final one.  Per (probed list, segment) unit:
@@ -151,7 +201,7 @@ __global__ void __launch_bounds__(FB_THREADS) ivf_exact_fallback_kernel(
     const float *__restrict__ pdist, const uint32_t *__restrict__ pslot, const uint32_t *__restrict__ probe,
     const uint32_t *__restrict__ pairpos, const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len,
     const uint32_t *__restrict__ ltile8, const float *__restrict__ gthr, const uint32_t *__restrict__ cnt, uint32_t rep_max,
-    uint32_t segb, int kc, const uint32_t *__restrict__ tc_src, const uint32_t *__restrict__ tc_row,
+    uint32_t split, uint32_t segb, int kc, const uint32_t *__restrict__ tc_src, const uint32_t *__restrict__ tc_row,
     const float *__restrict__ arena, const int64_t *__restrict__ ids, const float *__restrict__ Q,
     const float *__restrict__ stats, const float4 *__restrict__ vecs, const uint32_t *__restrict__ list_blk, int dimp,
     int nprobe, int nlists, int dim, int k, float *__restrict__ out_dist, int64_t *__restrict__ out_ids, float *__restrict__ dbg)
@@ -215,9 +265,10 @@ __global__ void __launch_bounds__(FB_THREADS) ivf_exact_fallback_kernel(
                 if (l < (uint32_t) nlists) {
                     len = list_len[l];
                     if (len) {
-                        const uint32_t rep = ivf_rep(cnt[l], rep_max), pos = pairpos[p] * rep;
+                        const uint32_t v = ivf_vlist(l, (int64_t) p, (uint32_t) nprobe, split);
+                        const uint32_t rep = ivf_rep(cnt[v], rep_max), pos = pairpos[p] * rep;
                         nseg = ivf_nseg(len, segb);
-                        first = (item_off[l] + (pos / TC_M) * nseg) * (2 * TC_M) + (pos % TC_M) * 2;
+                        first = (item_off[v] + (pos / TC_M) * nseg) * (2 * TC_M) + (pos % TC_M) * 2;
                         nent = rep * 2 * kc;
                     }
                 }

@@ -237,7 +237,7 @@ int nearest_centroids_tensor(CentroidSearch &cs, const float *C_rowmajor, const 
             it.out_base = qt * TC_M * nranges * 2 + xr * 2;
             it.out_stride = nranges * 2;
             it.rep = 1;
-            it.pad_ = 0;
+            it.nrows = (uint32_t) (std::min<int64_t>(st.valid_for, (int64_t) it.t1 * TC_N) - (int64_t) it.t0 * TC_N);
         }
         NDB_CHECK(cs.scr.items.reserve((size_t) nitems * sizeof(TcItem)));
         NDB_CUDA(cudaMemcpyAsync(cs.scr.items.p, items.data(), (size_t) nitems * sizeof(TcItem), cudaMemcpyHostToDevice, s));
@@ -255,6 +255,7 @@ int nearest_centroids_tensor(CentroidSearch &cs, const float *C_rowmajor, const 
     p.qb = cs.scr.qb.as<__nv_bfloat16>();
     p.qnorm = cs.scr.qnorm.as<float>();
     p.nkc = nkc;
+    p.dim = dim;
     p.k = kc;
     p.items = cs.scr.items.as<TcItem>();
     p.nitems = nitems;

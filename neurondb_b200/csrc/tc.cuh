@@ -12,6 +12,8 @@ constexpr int TC_MAX_CHUNKS = 2;   // K-chunks of a query tile that stay residen
 constexpr int TC_MAX_DIM = 2048;   // beyond TC_MAX_CHUNKS chunks the query tile is streamed with the stored tiles
 constexpr int TC_KMAX = 16;        // k <= 16 (thread-local register list)
 constexpr int TC_PACKED_MAX_TILES = 16;   // packed-key epilogue: 11 index bits = 16 tiles x 128 columns per half
+constexpr int TC_IDX_BITS = 11;           // low mantissa bits of a packed key that carry the candidate's index within its item
+constexpr uint32_t TC_IDX_MASK = (1u << TC_IDX_BITS) - 1;
 
 // stored rows in the blocked bf16 layout + squared norms of the rounded rows
 struct TcStore {
@@ -29,7 +31,7 @@ struct TcItem {
     uint32_t qtile, t0, t1, nq, out_base, out_stride;
     uint32_t rep;       // 4: every query sits on four consecutive tile positions and replica r scans only the r-th
                         // 32-column chunk of its column half (sparsely probed IVF lists); else 1
-    uint32_t pad_;
+    uint32_t nrows;     // stored rows in [t0, t1): the columns beyond them (the last tile's padding) never rank
 };
 
 struct TcScratch {
@@ -46,6 +48,8 @@ struct TcParams {
     const TcItem *items;           // work items
     uint32_t nitems;
     const uint32_t *nitems_ptr;    // optional: the item count lives on the device (nitems is then only an upper bound)
+    const uint32_t *item_lo_ptr;   // optional (device): this launch covers the items [*item_lo_ptr, *item_hi_ptr) only;
+    const uint32_t *item_hi_ptr;   // null = from the first / to the last (two-phase IVF scans)
     float *pdist;                  // partial results, indexed through TcItem::out_base / out_stride
     uint32_t *pslot;
     const uint32_t *qmap;          // optional (list mode): tile position -> (query * nprobe + rank), INVALID_SLOT = empty
@@ -55,9 +59,12 @@ struct TcParams {
     const float *qerr;             // optional: squared norm of each tile position's bf16 rounding error (with cstats)
     const float *cstats;           // optional: TcStore::stats of the stored rows -> the shared bound is published RELAXED
                                    // (cert_bound.cuh), which is what makes the selection certifiable
-    int dim;                       // row dimension (for the accumulation slack)
+    int dim;                       // row dimension (for the accumulation slack, and for kg_last)
+    int kg_last;                   // set by tc_launch: 8-element K groups of the last chunk that are copied and multiplied
     int packed;                    // 1: items span <= TC_PACKED_MAX_TILES tiles; (distance | index) keys, sorting-network epilogue
     float *debug_d;                // optional: raw accumulator of the first tile [128][256]
+    unsigned long long *dbg_counters; // builds with -DNDB_TC_COUNTERS only: epilogue statistics (chunks, chunks with a taker, sorted chunks, insert rounds, takers)
+    int kpub;                      // list mode: the shared bound is published from the kpub-th key of a full list (0: the last, k-th)
     int debug_mode;                // NDB_TC_DEBUG: 1 = no epilogue math, 2 = no MMA issue, 4 = no X bulk copies (bisection aid)
 };
 
@@ -67,8 +74,10 @@ int tc_store_pad0(TcStore &st, const float **out, cudaStream_t s);
 int tc_build_store_mapped(TcStore &st, const float *il32_store, const uint32_t *src_slot_dev, int64_t n, int dim, int dimp,
                           cudaStream_t s);
 // npos_dev (optional): device count of tile positions actually in use (nqpad is then an upper bound)
+// negate: the tiles hold -q (inner product: the accumulator is then the candidate -x.q itself)
 int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t nprobe, int nq, int nqpad, int dim, int nkc,
-                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s, const uint32_t *npos_dev = nullptr, float *qerr = nullptr);
+                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s, const uint32_t *npos_dev = nullptr, float *qerr = nullptr,
+                     bool negate = false);
 
 int tc_build_store(TcStore &st, const float *il32_store, int64_t n, int dim, int dimp, cudaStream_t s);
 int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q_dev, int nq, int k, const int64_t *ids,

@@ -142,7 +142,7 @@ __global__ void tc_row_norms_kernel(const float4 *__restrict__ store, const uint
 __global__ void __launch_bounds__(256) tc_block_queries_kernel(const float *__restrict__ Q, const uint32_t *__restrict__ qmap, uint32_t nprobe,
                                                                int nq, int nqpad, const uint32_t *__restrict__ npos, int dim, int nkc,
                                                                __nv_bfloat16 *__restrict__ qb, float *__restrict__ qnorm,
-                                                               float *__restrict__ qerr)
+                                                               float *__restrict__ qerr, bool negate)
 {
     __shared__ __align__(16) __nv_bfloat16 tile_s[TC_M * TC_KC];
     const int tile = blockIdx.x / nkc, chunk = blockIdx.x % nkc;
@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(256) tc_block_queries_kernel(const float *__re
                 const float r = __bfloat162float(o[i]);
                 part = fmaf(r, r, part);
                 perr = fmaf(vv[i] - r, vv[i] - r, perr);
+                if (negate) o[i] = __float2bfloat16_rn(-vv[i]);      // (rounding is symmetric: exactly -o[i])
             }
         } else {
 #pragma unroll
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(256) tc_block_queries_kernel(const float *__re
                 const float r = __bfloat162float(o[i]);
                 part = fmaf(r, r, part);
                 perr = fmaf(v - r, v - r, perr);
+                if (negate) o[i] = __float2bfloat16_rn(-v);
             }
         }
         // Query i of a tile sits on TMEM lane (i % 4) * 32 + i / 4: the tile's queries are dealt round-robin
@@ -341,8 +343,6 @@ __device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity)
 // FMNMX and whole groups of 16 candidates can go through a sorting network instead of being
 // inserted one by one.  The 12 remaining mantissa bits (2.4e-4) are finer than the bf16 products
 // that produced the value.
-constexpr int TC_IDX_BITS = 11;                                  // 16 tiles x 128 columns per half
-constexpr uint32_t TC_IDX_MASK = (1u << TC_IDX_BITS) - 1;
 static_assert(TC_PACKED_MAX_TILES == 1 << (TC_IDX_BITS - 7), "index bits");
 constexpr float TC_KEY_BIG = 1.7014118346046923e38f;             // 2^127 (index bits all zero): keys at or above are pad
                                                                  // rows / empty slots, also once an index is packed in
@@ -430,7 +430,9 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
     __shared__ uint32_t tmem_holder;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t nitems = p.nitems_ptr ? *p.nitems_ptr : p.nitems;
+    // this launch's items: [item_lo, item_lo + nitems)
+    const uint32_t item_lo = p.item_lo_ptr ? *p.item_lo_ptr : 0u;
+    const uint32_t nitems = (p.item_hi_ptr ? *p.item_hi_ptr : (p.nitems_ptr ? *p.nitems_ptr : p.nitems)) - item_lo;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -456,17 +458,20 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage_it = 0, tile_it = 0, item_it = 0;
+            // the last K-chunk of a row holds kg_last 8-element groups that are not all padding; in the blocked layout the
+            // groups of a (tile, chunk) are contiguous in K order, so only that prefix is copied (and multiplied)
+            const uint32_t x_last = (uint32_t) p.kg_last * (TC_N / 8) * 128u, q_last = (uint32_t) p.kg_last * (TC_M / 8) * 128u;
             for (uint32_t item = tc_item_of(0, blockIdx.x, gridDim.x); item < nitems; item = tc_item_of(++item_it, blockIdx.x, gridDim.x)) {
-                const TcItem it = p.items[item];
+                const TcItem it = p.items[item_lo + item];
                 const uint32_t qt = it.qtile;
                 const uint32_t qb_i = item_it % nqbuf, qn_i = item_it / nqbuf;
                 if (!q_streamed) {
                     mbar_spin(&q_empty[qb_i], (qn_i & 1u) ^ 1u);       // MMA finished with this buffer's previous tile
-                    mbar_arrive_expect_tx(&q_full[qb_i], (uint32_t) p.nkc * TC_QCHUNK_BYTES);
+                    mbar_arrive_expect_tx(&q_full[qb_i], (uint32_t) (p.nkc - 1) * TC_QCHUNK_BYTES + q_last);
                     for (int c = 0; c < p.nkc; c++)
                         tma_bulk_g2s(q_smem + (size_t) (qb_i * p.nkc + c) * TC_QCHUNK_BYTES,
                                      reinterpret_cast<const unsigned char *>(p.qb) + ((size_t) qt * p.nkc + c) * TC_QCHUNK_BYTES,
-                                     TC_QCHUNK_BYTES, &q_full[qb_i]);
+                                     c == p.nkc - 1 ? q_last : (uint32_t) TC_QCHUNK_BYTES, &q_full[qb_i]);
                 }
                 const uint32_t t0 = it.t0, t1 = it.t1;
                 for (uint32_t t = t0; t < t1; t++, tile_it++) {
@@ -474,15 +479,17 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                         const uint32_t s = stage_it % TC_STAGES;
                         mbar_spin(&empty_bar[s], ((stage_it / TC_STAGES) & 1u) ^ 1u);
                         const bool skip_x = (p.debug_mode & 4) != 0;
-                        const uint32_t bytes = (skip_x ? 0 : TC_XSTAGE_BYTES) + (c == 0 ? TC_N * 4 : 0) + (q_streamed ? TC_QCHUNK_BYTES : 0);
+                        const bool lastc = c == p.nkc - 1;
+                        const uint32_t xbytes = lastc ? x_last : (uint32_t) TC_XSTAGE_BYTES, qbytes = lastc ? q_last : (uint32_t) TC_QCHUNK_BYTES;
+                        const uint32_t bytes = (skip_x ? 0 : xbytes) + (c == 0 ? TC_N * 4 : 0) + (q_streamed ? qbytes : 0);
                         mbar_arrive_expect_tx(&full_bar[s], bytes);
                         if (q_streamed)
                             tma_bulk_g2s(q_smem + (size_t) s * TC_QCHUNK_BYTES,
                                          reinterpret_cast<const unsigned char *>(p.qb) + ((size_t) qt * p.nkc + c) * TC_QCHUNK_BYTES,
-                                         TC_QCHUNK_BYTES, &full_bar[s]);
+                                         qbytes, &full_bar[s]);
                         if (!skip_x) tma_bulk_g2s(x_smem + (size_t) s * TC_XSTAGE_BYTES,
                                      reinterpret_cast<const unsigned char *>(p.xb) + ((size_t) t * p.nkc + c) * TC_XSTAGE_BYTES,
-                                     TC_XSTAGE_BYTES, &full_bar[s]);
+                                     xbytes, &full_bar[s]);
                         if (c == 0)
                             tma_bulk_g2s(n_smem + (size_t) (tile_it % TC_NORM_RING) * TC_N, p.xnorm + (size_t) t * TC_N, TC_N * 4,
                                          &full_bar[s]);
@@ -496,7 +503,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
             const uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
             uint32_t stage_it = 0, tile_it = 0, item_it = 0;
             for (uint32_t item = tc_item_of(0, blockIdx.x, gridDim.x); item < nitems; item = tc_item_of(++item_it, blockIdx.x, gridDim.x)) {
-                const TcItem it = p.items[item];
+                const TcItem it = p.items[item_lo + item];
                 const uint32_t t0 = it.t0, t1 = it.t1;
                 const uint32_t qb_i = item_it % nqbuf, qn_i = item_it / nqbuf;
                 if (!q_streamed) {
@@ -514,12 +521,13 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                         tc_fence_after();
                         const uint32_t qa = smem_u32(q_smem + (size_t) (q_streamed ? s : qb_i * p.nkc + c) * TC_QCHUNK_BYTES);
                         const uint32_t xa = smem_u32(x_smem + (size_t) s * TC_XSTAGE_BYTES);
+                        const int nks = (c == p.nkc - 1 ? p.kg_last : TC_KC / 8) / 2;
 #pragma unroll
                         for (int ks = 0; ks < TC_KC / 16; ks++) {
                             // one MMA consumes K = 16 = two 8-element core matrices along K
                             const uint64_t da = umma_desc(qa + ks * 2 * (TC_M / 8) * 128, (TC_M / 8) * 128, 128);
                             const uint64_t db = umma_desc(xa + ks * 2 * (TC_N / 8) * 128, (TC_N / 8) * 128, 128);
-                            if (!(p.debug_mode & 2)) umma_bf16(tmem_d, da, db, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                            if (ks < nks && !(p.debug_mode & 2)) umma_bf16(tmem_d, da, db, idesc, (c > 0 || ks > 0) ? 1u : 0u);
                         }
                         umma_commit(&empty_bar[s]);                     // smem stage reusable once these MMAs retire
                     }
@@ -539,8 +547,11 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
         const uint32_t lane_addr = (uint32_t) ((warp & 3) * 32) << 16;
         uint32_t tile_it = 0;
         uint32_t item_it = 0;
+#ifdef NDB_TC_COUNTERS
+        uint32_t dc_chunks = 0, dc_any = 0, dc_heavy = 0, dc_iters = 0, dc_takers = 0;
+#endif
         for (uint32_t item = tc_item_of(0, blockIdx.x, gridDim.x); item < nitems; item = tc_item_of(++item_it, blockIdx.x, gridDim.x)) {
-            const TcItem it = p.items[item];
+            const TcItem it = p.items[item_lo + item];
             const uint32_t t0 = it.t0, t1 = it.t1;
             const float qn = p.qnorm[(size_t) it.qtile * TC_M + ql];
             const bool live = (uint32_t) ql < it.nq;
@@ -589,6 +600,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     if (t + 1 < t1) gnext = *reinterpret_cast<volatile float *>(gcell);
                 }
                 const float *xn = n_smem + (size_t) (tile_it % TC_NORM_RING) * TC_N;
+                const uint32_t tile_rows = min((uint32_t) TC_N, it.nrows - (t - t0) * TC_N);     // stored rows of this tile
                 // PACKED (short items, latency-bound epilogue): the TMEM read of chunk j + 1 is in flight
                 // while chunk j is processed.  The dense kernel is ALU-bound and keeps the plain order.
                 // a warp whose 32 query lanes are all beyond the item's query count has nothing to read: it
@@ -604,9 +616,12 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                 for (int j = jlo; j < nchunk; j++) {
                     const int col0 = half * (TC_N / 2) + j * 32;
                     // this chunk's row norms first: their shared-memory latency overlaps the TMEM wait
-                    float4 n4s[8];
+                    // (inner product: the query tile holds -q, the accumulator is the candidate itself, no norms)
+                    float4 n4s[METRIC == NDB_IP ? 1 : 8];
+                    if (METRIC != NDB_IP) {
 #pragma unroll
-                    for (int i4 = 0; i4 < 8; i4++) n4s[i4] = *reinterpret_cast<const float4 *>(xn + col0 + 4 * i4);
+                        for (int i4 = 0; i4 < 8; i4++) n4s[i4] = *reinterpret_cast<const float4 *>(xn + col0 + 4 * i4);
+                    }
                     uint32_t v[32];
                     if (PACKED) {
                         tmem_ld_wait();
@@ -624,6 +639,15 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     // 32 independent FFMAs, then one min tree: the common case (nothing beats the
                     // threshold) is branch-free.
                     float c[32];
+                    if (METRIC == NDB_IP) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) c[i] = __uint_as_float(v[i]);
+                        // the padding of a list's last tile: zero rows, whose candidate 0 must never rank
+                        if ((uint32_t) (col0 + 32) > tile_rows) {
+#pragma unroll
+                            for (int i = 0; i < 32; i++) c[i] = (uint32_t) (col0 + i) < tile_rows ? c[i] : INFINITY;
+                        }
+                    } else {
 #pragma unroll
                     for (int i4 = 0; i4 < 8; i4++) {
                         const float4 n4 = n4s[i4];
@@ -632,7 +656,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             c[4 * i4 + 1] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 1]), n4.y);
                             c[4 * i4 + 2] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 2]), n4.z);
                             c[4 * i4 + 3] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 3]), n4.w);
-                        } else if (METRIC == NDB_COSINE) {
+                        } else {
                             // p.xnorm holds 1 / ||x|| here (0 for a zero row, +inf for a pad row): -x.q / ||x||
                             // orders the rows like the cosine distance, whose 1 / ||q|| is applied on output.
                             // A pad row is all zeros, its dot product is exactly 0 and 0 * inf = NaN, which
@@ -641,22 +665,19 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             c[4 * i4 + 1] = -__uint_as_float(v[4 * i4 + 1]) * n4.y;
                             c[4 * i4 + 2] = -__uint_as_float(v[4 * i4 + 2]) * n4.z;
                             c[4 * i4 + 3] = -__uint_as_float(v[4 * i4 + 3]) * n4.w;
-                        } else {
-                            // inner product: p.xnorm holds 0 for a stored row and +inf for a pad row, so the
-                            // candidate -x.q and the pad handling are one FADD per column
-                            c[4 * i4 + 0] = n4.x - __uint_as_float(v[4 * i4 + 0]);
-                            c[4 * i4 + 1] = n4.y - __uint_as_float(v[4 * i4 + 1]);
-                            c[4 * i4 + 2] = n4.z - __uint_as_float(v[4 * i4 + 2]);
-                            c[4 * i4 + 3] = n4.w - __uint_as_float(v[4 * i4 + 3]);
                         }
                     }
-                    float m[16];
+                    }
+                    // minimum of the 32 candidates through 3-input minima (FMNMX3): 17 instructions
+                    float m[11];
 #pragma unroll
-                    for (int i = 0; i < 16; i++) m[i] = fminf(c[i], c[i + 16]);
-#pragma unroll
-                    for (int w = 8; w > 0; w >>= 1)
-#pragma unroll
-                        for (int i = 0; i < w; i++) m[i] = fminf(m[i], m[i + w]);
+                    for (int i = 0; i < 10; i++) m[i] = fminf(fminf(c[3 * i], c[3 * i + 1]), c[3 * i + 2]);
+                    m[10] = fminf(c[30], c[31]);
+                    m[0] = fminf(fminf(m[0], m[1]), m[2]);
+                    m[3] = fminf(fminf(m[3], m[4]), m[5]);
+                    m[6] = fminf(fminf(m[6], m[7]), m[8]);
+                    m[9] = fminf(m[9], m[10]);
+                    m[0] = fminf(fminf(m[0], m[3]), fminf(m[6], m[9]));
                     if constexpr (PACKED) {
                         uint32_t mask = 0;
                         float thc = thr - cadd;                         // threshold in raw candidate units
@@ -665,6 +686,13 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             for (int i = 0; i < 32; i++) mask |= (c[i] < thc ? 1u : 0u) << i;
                         }
                         const uint32_t ibase = (t - t0) * (TC_N / 2) + j * 32;
+#ifdef NDB_TC_COUNTERS
+                        dc_chunks++;
+                        dc_any += __any_sync(FULL, mask != 0) ? 1 : 0;
+                        dc_takers += __popc(mask);
+                        if (__any_sync(FULL, __popc(mask) > TC_HEAVY)) dc_heavy++;
+                        else { int mx = __popc(mask); for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o)); dc_iters += mx; }
+#endif
                         if (__any_sync(FULL, __popc(mask) > TC_HEAVY)) {
                             // some lane has many takers (its list is still filling): every lane sorts
                             // its 32 keys through the network -- a fixed cost, no lane-by-lane tail
@@ -711,8 +739,20 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[a]);                             // 256 arrivals release the accumulator
-                if (gcell && bd[KT - 1] < published) {                  // own list full and improved
-                    published = bd[KT - 1];
+                // the key the bound is taken from: any list that holds kpub entries proves that the query's kpub-th best is
+                // at most its kpub-th key (kpub = the caller's k; the list itself keeps KT >= kpub entries)
+                float kth = bd[KT - 1];
+                // (a warp-uniform switch: written as a loop of selects the compiler turns it into an indexed load and moves
+                // the list to local memory)
+#define NDB_KTH(I) case (I) + 1: kth = bd[(I) < KT ? (I) : KT - 1]; break;
+                switch (p.kpub) {
+                    NDB_KTH(0) NDB_KTH(1) NDB_KTH(2) NDB_KTH(3) NDB_KTH(4) NDB_KTH(5) NDB_KTH(6) NDB_KTH(7)
+                    NDB_KTH(8) NDB_KTH(9) NDB_KTH(10) NDB_KTH(11) NDB_KTH(12) NDB_KTH(13) NDB_KTH(14)
+                    default: break;
+                }
+#undef NDB_KTH
+                if (gcell && kth < published) {                         // own list full enough and improved
+                    published = kth;
                     float pub = published;
                     if (PACKED)     // an upper bound of the value the key stands for
                         pub = __uint_as_float(pub >= 0.0f ? (__float_as_uint(pub) | TC_IDX_MASK) : (__float_as_uint(pub) & ~TC_IDX_MASK));
@@ -746,6 +786,18 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                 }
             }
         }
+#ifdef NDB_TC_COUNTERS
+        if (p.dbg_counters) {
+            // warp-level counts from lane 0, takers from every lane
+            if (lane == 0) {
+                atomicAdd(p.dbg_counters + 0, (unsigned long long) dc_chunks);
+                atomicAdd(p.dbg_counters + 1, (unsigned long long) dc_any);
+                atomicAdd(p.dbg_counters + 2, (unsigned long long) dc_heavy);
+                atomicAdd(p.dbg_counters + 3, (unsigned long long) dc_iters);
+            }
+            atomicAdd(p.dbg_counters + 4, (unsigned long long) dc_takers);
+        }
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -832,9 +884,10 @@ int tc_store_rinv(TcStore &st, const float **out, cudaStream_t s)
 
 // blocked bf16 query tiles + squared norms; qmap_dev (optional) gathers the tile positions
 int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t nprobe, int nq, int nqpad, int dim, int nkc,
-                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s, const uint32_t *npos_dev, float *qerr)
+                     __nv_bfloat16 *qb, float *qnorm, cudaStream_t s, const uint32_t *npos_dev, float *qerr, bool negate)
 {
-    tc_block_queries_kernel<<<(unsigned) ((nqpad / TC_M) * nkc), 256, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev, dim, nkc, qb, qnorm, qerr);
+    tc_block_queries_kernel<<<(unsigned) ((nqpad / TC_M) * nkc), 256, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev, dim, nkc, qb, qnorm, qerr,
+                                                                              negate);
     count_launch();
     if (nkc > 1) {
         tc_query_norms_kernel<<<(unsigned) ((nqpad + 127) / 128), 128, 0, s>>>(Q_dev, qmap_dev, nprobe, nq, nqpad, npos_dev, dim, qnorm, qerr);
@@ -844,6 +897,9 @@ int tc_block_queries(const float *Q_dev, const uint32_t *qmap_dev, uint32_t npro
     return NDB_B200_OK;
 }
 
+#ifdef NDB_TC_COUNTERS
+static unsigned long long *g_tc_dbg_counters = nullptr;
+#endif
 // launch the persistent kernel over p.items (grid = min(items, SMs)); records timing events
 int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s)
 {
@@ -854,6 +910,17 @@ int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s)
     const uint32_t sms = (uint32_t) ctx().sm_count;
     const uint32_t grid = (p.nitems < sms && !p.nitems_ptr) ? p.nitems : sms;
     Context &c = ctx();
+    {   // 8-element K groups of the last chunk that carry data, rounded up to whole MMAs (K = 16)
+        TcParams &pm = const_cast<TcParams &>(p);
+        const int rest = p.dim - (p.nkc - 1) * TC_KC;
+        pm.kg_last = (p.dim > 0 && rest > 0 && rest <= TC_KC && !getenv("NDB_TC_FULL_K")) ? ((rest + 15) / 16) * 2 : TC_KC / 8;
+    }
+#ifdef NDB_TC_COUNTERS
+    static DevBuf dbgc;
+    if (!dbgc.p) { NDB_CHECK(dbgc.reserve(64)); NDB_CUDA(cudaMemsetAsync(dbgc.p, 0, 64, s)); }
+    const_cast<TcParams &>(p).dbg_counters = p.gthr ? dbgc.as<unsigned long long>() : nullptr;      // list mode only
+    g_tc_dbg_counters = dbgc.as<unsigned long long>();
+#endif
     if (c.timing) NDB_CUDA(cudaEventRecord(c.ev0, s));
     // list length: the smallest of {1, 10, 16} that holds k (a shorter list = a tighter threshold)
 #define NDB_TC_LAUNCH(KT, M, PK)                                                                              \
@@ -908,7 +975,8 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     const int nqpad = (int) nqt * TC_M;
     NDB_CHECK(sc.qb.reserve((size_t) nqpad * nkc * TC_KC * 2));
     NDB_CHECK(sc.qnorm.reserve((size_t) nqpad * 4));
-    NDB_CHECK(tc_block_queries(Q_dev, nullptr, 0, nq, nqpad, dim, nkc, sc.qb.as<__nv_bfloat16>(), sc.qnorm.as<float>(), s));
+    NDB_CHECK(tc_block_queries(Q_dev, nullptr, 0, nq, nqpad, dim, nkc, sc.qb.as<__nv_bfloat16>(), sc.qnorm.as<float>(), s, nullptr, nullptr,
+                               metric == NDB_IP));
     // split the stored tiles into ranges so that there are ~2 work items per SM
     const uint32_t sms = (uint32_t) ctx().sm_count;
     uint32_t nranges = (2 * sms + nqt - 1) / nqt;
@@ -938,7 +1006,7 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
         it.out_base = qt * TC_M * nranges * 2 + xr * 2;
         it.out_stride = nranges * 2;
         it.rep = 1;
-        it.pad_ = 0;
+        it.nrows = (uint32_t) (std::min<int64_t>(st.valid_for, (int64_t) it.t1 * TC_N) - (int64_t) it.t0 * TC_N);
     }
     NDB_CHECK(sc.items.reserve((size_t) nitems * sizeof(TcItem)));
     NDB_CUDA(cudaMemcpyAsync(sc.items.p, items.data(), (size_t) nitems * sizeof(TcItem), cudaMemcpyHostToDevice, s));
@@ -952,6 +1020,7 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     p.qb = sc.qb.as<__nv_bfloat16>();
     p.qnorm = sc.qnorm.as<float>();
     p.nkc = nkc; p.k = k;
+    p.dim = dim;
     p.items = sc.items.as<TcItem>();
     p.nitems = nitems;
     p.pdist = sc.pdist.as<float>();
@@ -970,6 +1039,20 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
 
 }  // namespace ndb
 
+#ifdef NDB_TC_COUNTERS
+// development hook: read and reset the epilogue statistics of the list-mode launches since the last call
+extern "C" int ndbdbg_tc_counters(unsigned long long *out /* [8] */)
+{
+    using namespace ndb;
+    NDB_CHECK(require_init());
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    if (!g_tc_dbg_counters) return NDB_B200_OK;
+    NDB_CUDA(cudaDeviceSynchronize());
+    NDB_CUDA(cudaMemcpy(out, g_tc_dbg_counters, 64, cudaMemcpyDeviceToHost));
+    NDB_CUDA(cudaMemset(g_tc_dbg_counters, 0, 64));
+    return NDB_B200_OK;
+}
+#endif
 // development hook (not part of the ABI in include/ndb_b200.h): raw accumulator tile D = Q X^T of the
 // first (query tile, row tile) -- used by tests/test_gpu_tensor.py to validate the UMMA descriptors
 extern "C" int ndbdbg_tc_gemm(const float *Q, int nq, const float *X, int n, int dim, float *D /* [128][256] */)
