@@ -275,7 +275,7 @@ __global__ void ivf_merge_kernel(const float *__restrict__ pdist, const uint32_t
 __global__ void ivf_tc_items_kernel(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ qoff,
                                     const uint32_t *__restrict__ item_off, const uint32_t *__restrict__ list_len,
                                     const uint32_t *__restrict__ ltile8, int nlists, uint32_t segb, uint32_t rep_max,
-                                    TcItem *__restrict__ items, uint32_t split)
+                                    TcItem *__restrict__ items, uint32_t split, int seg_major)
 {
     const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;           // virtual list (ivf_vlist)
     if (v >= (split ? 2 * nlists : nlists)) return;
@@ -296,7 +296,10 @@ __global__ void ivf_tc_items_kernel(const uint32_t *__restrict__ cnt, const uint
         it.out_stride = 2;
         it.rep = rp;
         it.nrows = nvec;
-        items[item_off[v] + i] = it;
+        // Execution order within the list (the output slot above is not affected): segment-major puts the query tiles of
+        // one segment on consecutive items, i.e. on different SMs at the same time, so the segment's rows come out of
+        // HBM once and out of L2 for the other tiles; tile-major streams the whole list once per query tile.
+        items[item_off[v] + (seg_major ? sg * tiles + t : i)] = it;
     }
 }
 
@@ -750,7 +753,8 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     NDB_CHECK(ix->tcs.items.reserve(n_items * sizeof(TcItem)));
     ivf_tc_items_kernel<<<(unsigned) ((NV + 3) / 4), 128, 0, s>>>(cnt, ix->qoff.as<uint32_t>(), ix->item_off.as<uint32_t>(),
                                                                  ix->d_list_len.as<uint32_t>(), ix->d_ltile8.as<uint32_t>(), L, segb,
-                                                                 rep_max, ix->tcs.items.as<TcItem>(), split);
+                                                                 rep_max, ix->tcs.items.as<TcItem>(), split,
+                                                                 getenv("NDB_IVF_TC_TILE_MAJOR") ? 0 : 1);
     count_launch(2);
     NDB_CUDA(cudaGetLastError());
     if (getenv("NDB_IVF_DEBUG")) {

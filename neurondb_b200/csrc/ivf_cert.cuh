@@ -159,16 +159,28 @@ __global__ void __launch_bounds__(128) ivf_tc_bound_kernel(
     WarpTopK<1, uint32_t> best;
     best.init();
     uint32_t n_in = 0;
-    for (uint32_t sg = 0; sg < nseg; sg++) {
-        const size_t base = (first + (size_t) sg * (2 * TC_M)) * kc;
-        for (int e0 = 0; e0 < nent; e0 += 32) {
-            const int e = e0 + lane;
-            uint32_t sl = INVALID_SLOT;
-            float kd = INFINITY;
-            if (e < nent) { sl = pslot[base + e]; kd = pdist[base + e]; }
-            const bool ok = sl != INVALID_SLOT;
+    // the nseg * nent entries as one flat range, four loads per lane in flight (the walk is a latency chain otherwise)
+    const uint32_t total = nseg * (uint32_t) nent;
+    for (uint32_t e0 = 0; e0 < total; e0 += 128) {
+        uint32_t sl[4];
+        float kd[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t e = e0 + u * 32 + lane;
+            sl[u] = INVALID_SLOT;
+            kd[u] = INFINITY;
+            if (e < total) {
+                const uint32_t sg = e / (uint32_t) nent, w = e - sg * (uint32_t) nent;
+                const size_t at = (first + (size_t) sg * (2 * TC_M)) * kc + w;
+                sl[u] = pslot[at];
+                kd[u] = pdist[at];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool ok = sl[u] != INVALID_SLOT;
             const unsigned m = __ballot_sync(FULL, ok);
-            if (m) { n_in += __popc(m); best.offer(kd, sl, ok, lane, k); }
+            if (m) { n_in += __popc(m); best.offer(kd[u], sl[u], ok, lane, k); }
         }
     }
     if (n_in < (uint32_t) k) return;                          // fewer than k rows met: no bound

@@ -118,7 +118,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-
 // the chunks of one staged block-part for the NQ live queries of a warp: lane l walks vector l;
 // the queries of the warp sit `qstride` elements apart in shared memory
 template <class P, int QT, int NQ>

@@ -60,12 +60,13 @@ struct TcParams {
     const float *cstats;           // optional: TcStore::stats of the stored rows -> the shared bound is published RELAXED
                                    // (cert_bound.cuh), which is what makes the selection certifiable
     int dim;                       // row dimension (for the accumulation slack, and for kg_last)
+    int nstages, xstride;          // set by tc_launch: depth of the stored-row ring and the byte stride of its stages
     int kg_last;                   // set by tc_launch: 8-element K groups of the last chunk that are copied and multiplied
     int packed;                    // 1: items span <= TC_PACKED_MAX_TILES tiles; (distance | index) keys, sorting-network epilogue
     float *debug_d;                // optional: raw accumulator of the first tile [128][256]
     unsigned long long *dbg_counters; // builds with -DNDB_TC_COUNTERS only: epilogue statistics (chunks, chunks with a taker, sorted chunks, insert rounds, takers)
     int kpub;                      // list mode: the shared bound is published from the kpub-th key of a full list (0: the last, k-th)
-    int debug_mode;                // NDB_TC_DEBUG: 1 = no epilogue math, 2 = no MMA issue, 4 = no X bulk copies (bisection aid)
+    int debug_mode;                // NDB_TC_DEBUG: 1 = no epilogue, 2 = no MMA issue, 4 = no X bulk copies, 8 = epilogue reads TMEM only (bisection aid)
 };
 
 int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s);

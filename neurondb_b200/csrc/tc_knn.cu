@@ -38,8 +38,13 @@
 
 namespace ndb {
 
-constexpr int TC_STAGES = 2;
-constexpr int TC_XSTAGE_BYTES = TC_N * TC_KC * 2;      // 64 KB
+constexpr int TC_XSTAGE_BYTES = TC_N * TC_KC * 2;      // 64 KB: one (tile, K-chunk) of stored rows
+// The ring of stored-row stages: 144 KB.  Rows of more than one K-chunk use it as 2 stages of 64 KB.  With one chunk
+// (dim <= 128) only the K groups that carry data are copied, a stage is kg_last * 4 KB and the ring holds
+// min(5, 144 KB / stage) of them -- dim 96: three 48 KB stages, dim 64: four of 32 KB.  The ring is latency-bound (a
+// stage is refilled ~2 us after the MMAs that read it retire), so tiles in flight are what sets the pace.
+constexpr int TC_XRING_BYTES = 144 * 1024;
+constexpr int TC_MAX_STAGES = 5;                       // < TC_NORM_RING - 2: the norms of a tile stay until its epilogue
 constexpr int TC_QCHUNK_BYTES = TC_M * TC_KC * 2;      // 32 KB
 constexpr int TC_NORM_RING = 8;
 
@@ -425,8 +430,9 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
     // [Q tile: nkc * 32 KB][X ring: 2 * 64 KB][norm ring: 8 * 1 KB]
     unsigned char *q_smem = tsm;
     unsigned char *x_smem = tsm + (size_t) TC_MAX_CHUNKS * TC_QCHUNK_BYTES;
-    float *n_smem = reinterpret_cast<float *>(x_smem + (size_t) TC_STAGES * TC_XSTAGE_BYTES);
-    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], q_full[2], q_empty[2], acc_full[2], acc_empty[2];
+    float *n_smem = reinterpret_cast<float *>(x_smem + (size_t) TC_XRING_BYTES);
+    __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], q_full[2], q_empty[2], acc_full[2], acc_empty[2];
+    const uint32_t nstages = (uint32_t) p.nstages, xstride = (uint32_t) p.xstride;
     __shared__ uint32_t tmem_holder;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -435,7 +441,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
     const uint32_t nitems = (p.item_hi_ptr ? *p.item_hi_ptr : (p.nitems_ptr ? *p.nitems_ptr : p.nitems)) - item_lo;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < TC_MAX_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&q_full[b], 1); mbar_init(&q_empty[b], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 256); }
         mbar_fence_init();
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            uint32_t stage_it = 0, tile_it = 0, item_it = 0;
+            uint32_t tile_it = 0, item_it = 0, s = 0, sph = 0;              // ring slot and its phase
             // the last K-chunk of a row holds kg_last 8-element groups that are not all padding; in the blocked layout the
             // groups of a (tile, chunk) are contiguous in K order, so only that prefix is copied (and multiplied)
             const uint32_t x_last = (uint32_t) p.kg_last * (TC_N / 8) * 128u, q_last = (uint32_t) p.kg_last * (TC_M / 8) * 128u;
@@ -475,9 +481,8 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                 }
                 const uint32_t t0 = it.t0, t1 = it.t1;
                 for (uint32_t t = t0; t < t1; t++, tile_it++) {
-                    for (int c = 0; c < p.nkc; c++, stage_it++) {
-                        const uint32_t s = stage_it % TC_STAGES;
-                        mbar_spin(&empty_bar[s], ((stage_it / TC_STAGES) & 1u) ^ 1u);
+                    for (int c = 0; c < p.nkc; c++) {
+                        mbar_spin(&empty_bar[s], sph ^ 1u);
                         const bool skip_x = (p.debug_mode & 4) != 0;
                         const bool lastc = c == p.nkc - 1;
                         const uint32_t xbytes = lastc ? x_last : (uint32_t) TC_XSTAGE_BYTES, qbytes = lastc ? q_last : (uint32_t) TC_QCHUNK_BYTES;
@@ -487,12 +492,13 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             tma_bulk_g2s(q_smem + (size_t) s * TC_QCHUNK_BYTES,
                                          reinterpret_cast<const unsigned char *>(p.qb) + ((size_t) qt * p.nkc + c) * TC_QCHUNK_BYTES,
                                          qbytes, &full_bar[s]);
-                        if (!skip_x) tma_bulk_g2s(x_smem + (size_t) s * TC_XSTAGE_BYTES,
+                        if (!skip_x) tma_bulk_g2s(x_smem + (size_t) s * xstride,
                                      reinterpret_cast<const unsigned char *>(p.xb) + ((size_t) t * p.nkc + c) * TC_XSTAGE_BYTES,
                                      xbytes, &full_bar[s]);
                         if (c == 0)
                             tma_bulk_g2s(n_smem + (size_t) (tile_it % TC_NORM_RING) * TC_N, p.xnorm + (size_t) t * TC_N, TC_N * 4,
                                          &full_bar[s]);
+                        if (++s == nstages) { s = 0; sph ^= 1u; }
                     }
                 }
             }
@@ -501,7 +507,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
-            uint32_t stage_it = 0, tile_it = 0, item_it = 0;
+            uint32_t tile_it = 0, item_it = 0, s = 0, sph = 0;
             for (uint32_t item = tc_item_of(0, blockIdx.x, gridDim.x); item < nitems; item = tc_item_of(++item_it, blockIdx.x, gridDim.x)) {
                 const TcItem it = p.items[item_lo + item];
                 const uint32_t t0 = it.t0, t1 = it.t1;
@@ -515,12 +521,11 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     mbar_spin(&acc_empty[a], ((tile_it >> 1) & 1u) ^ 1u);      // epilogue drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + a * TC_N;
-                    for (int c = 0; c < p.nkc; c++, stage_it++) {
-                        const uint32_t s = stage_it % TC_STAGES;
-                        mbar_spin(&full_bar[s], (stage_it / TC_STAGES) & 1u);
+                    for (int c = 0; c < p.nkc; c++) {
+                        mbar_spin(&full_bar[s], sph);
                         tc_fence_after();
                         const uint32_t qa = smem_u32(q_smem + (size_t) (q_streamed ? s : qb_i * p.nkc + c) * TC_QCHUNK_BYTES);
-                        const uint32_t xa = smem_u32(x_smem + (size_t) s * TC_XSTAGE_BYTES);
+                        const uint32_t xa = smem_u32(x_smem + (size_t) s * xstride);
                         const int nks = (c == p.nkc - 1 ? p.kg_last : TC_KC / 8) / 2;
 #pragma unroll
                         for (int ks = 0; ks < TC_KC / 16; ks++) {
@@ -530,6 +535,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             if (ks < nks && !(p.debug_mode & 2)) umma_bf16(tmem_d, da, db, idesc, (c > 0 || ks > 0) ? 1u : 0u);
                         }
                         umma_commit(&empty_bar[s]);                     // smem stage reusable once these MMAs retire
+                        if (++s == nstages) { s = 0; sph ^= 1u; }
                     }
                     umma_commit(&acc_full[a]);                          // accumulator complete
                 }
@@ -610,27 +616,20 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                 // replicated queries (it.rep == 4): this warp's lanes are replica (warp & 3) and scan chunk (warp & 3) only
                 const int jlo = it.rep == 4 ? (warp & 3) : 0;
                 const int nchunk = ((p.debug_mode & 1) || warp_dead) ? 0 : (it.rep == 4 ? jlo + 1 : TC_N / 64);
-                uint32_t vn[PACKED ? 32 : 1];
-                if (PACKED && nchunk) tmem_ld32(tmem_base + lane_addr + a * TC_N + half * (TC_N / 2) + jlo * 32, (uint32_t (&)[32]) vn);
-#pragma unroll 1
-                for (int j = jlo; j < nchunk; j++) {
+                const uint32_t acc_addr = tmem_base + lane_addr + a * TC_N + half * (TC_N / 2);
+                // one 32-column chunk of the accumulator, already in registers
+                auto process = [&](uint32_t (&v)[32], const int j) {
                     const int col0 = half * (TC_N / 2) + j * 32;
-                    // this chunk's row norms first: their shared-memory latency overlaps the TMEM wait
-                    // (inner product: the query tile holds -q, the accumulator is the candidate itself, no norms)
+                    // this chunk's row norms (inner product: the query tile holds -q, the accumulator is the candidate
+                    // itself, no norms)
                     float4 n4s[METRIC == NDB_IP ? 1 : 8];
                     if (METRIC != NDB_IP) {
 #pragma unroll
                         for (int i4 = 0; i4 < 8; i4++) n4s[i4] = *reinterpret_cast<const float4 *>(xn + col0 + 4 * i4);
                     }
-                    uint32_t v[32];
-                    if (PACKED) {
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; i++) v[i] = vn[PACKED ? i : 0];
-                        if (j + 1 < nchunk) tmem_ld32(tmem_base + lane_addr + a * TC_N + col0 + 32, (uint32_t (&)[32]) vn);
-                    } else {
-                        tmem_ld32(tmem_base + lane_addr + a * TC_N + col0, v);
-                        tmem_ld_wait();
+                    if (p.debug_mode & 8) {                    // bisection: TMEM reads only
+                        if (__uint_as_float(v[0]) == 1.2345e-30f) bd[0] = 0.0f;
+                        return;
                     }
                     if (p.debug_d && item == 0 && t == t0) {   // first item's first tile
 #pragma unroll
@@ -639,14 +638,13 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     // 32 independent FFMAs, then one min tree: the common case (nothing beats the
                     // threshold) is branch-free.
                     float c[32];
+                    // columns that may rank: stored rows only (inner product: the padding of a list's last tile is zero
+                    // rows with candidate 0; the other metrics give pad rows +inf / NaN candidates), live queries only
+                    const uint32_t ncol = tile_rows > (uint32_t) col0 ? tile_rows - (uint32_t) col0 : 0u;
+                    const uint32_t okmask = !live ? 0u : (ncol >= 32u ? 0xffffffffu : (1u << ncol) - 1u);
                     if (METRIC == NDB_IP) {
 #pragma unroll
                         for (int i = 0; i < 32; i++) c[i] = __uint_as_float(v[i]);
-                        // the padding of a list's last tile: zero rows, whose candidate 0 must never rank
-                        if ((uint32_t) (col0 + 32) > tile_rows) {
-#pragma unroll
-                            for (int i = 0; i < 32; i++) c[i] = (uint32_t) (col0 + i) < tile_rows ? c[i] : INFINITY;
-                        }
                     } else {
 #pragma unroll
                     for (int i4 = 0; i4 < 8; i4++) {
@@ -684,6 +682,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                         if (m[0] < thc) {
 #pragma unroll
                             for (int i = 0; i < 32; i++) mask |= (c[i] < thc ? 1u : 0u) << i;
+                            mask &= okmask;
                         }
                         const uint32_t ibase = (t - t0) * (TC_N / 2) + j * 32;
 #ifdef NDB_TC_COUNTERS
@@ -696,16 +695,12 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                         if (__any_sync(FULL, __popc(mask) > TC_HEAVY)) {
                             // some lane has many takers (its list is still filling): every lane sorts
                             // its 32 keys through the network -- a fixed cost, no lane-by-lane tail
-                            if (!live) {
-#pragma unroll
-                                for (int i = 0; i < 32; i++) c[i] = INFINITY;
-                            }
                             float g[16];
 #pragma unroll
-                            for (int i = 0; i < 16; i++) g[i] = tc_pack(c[i] + cadd, ibase + i);
+                            for (int i = 0; i < 16; i++) g[i] = (okmask >> i) & 1u ? tc_pack(c[i] + cadd, ibase + i) : FLT_MAX;
                             tc_sort_merge16(bd, g);
 #pragma unroll
-                            for (int i = 0; i < 16; i++) g[i] = tc_pack(c[16 + i] + cadd, ibase + 16 + i);
+                            for (int i = 0; i < 16; i++) g[i] = (okmask >> (16 + i)) & 1u ? tc_pack(c[16 + i] + cadd, ibase + 16 + i) : FLT_MAX;
                             tc_sort_merge16(bd, g);
                             thr = fminf(bd[KT - 1], gcap);
                         } else {
@@ -725,6 +720,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             uint32_t mask = 0;
 #pragma unroll
                             for (int i = 0; i < 32; i++) mask |= (c[i] < thr ? 1u : 0u) << i;
+                            mask &= okmask;
                             while (mask) {
                                 const int i = __ffs(mask) - 1;
                                 mask &= mask - 1;
@@ -736,6 +732,16 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             }
                         }
                     }
+                                };
+                // One TMEM read per chunk, waited for at once: its latency is a few dozen cycles, which the other epilogue
+                // warp of the scheduler covers.  (Reading a chunk ahead needs a second register set: copying it cost 32
+                // moves per chunk, alternating two sets doubled the code and thrashed the instruction cache.)
+#pragma unroll 1
+                for (int j = jlo; j < nchunk; j++) {
+                    uint32_t v[32];
+                    tmem_ld32(acc_addr + j * 32, v);
+                    tmem_ld_wait();
+                    process(v, j);
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[a]);                             // 256 arrivals release the accumulator
@@ -764,9 +770,11 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
             }
             if (live) {
                 const size_t base = ((size_t) it.out_base + (size_t) ql * it.out_stride + half) * p.k;
+                float od[KT];
+                uint32_t os[KT];
 #pragma unroll
                 for (int j = 0; j < KT; j++) {
-                    if (j < p.k) {
+                    {
                         float d = bd[j];
                         uint32_t slot;
                         if (PACKED) {
@@ -780,9 +788,22 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             if (METRIC == NDB_L2 && slot != INVALID_SLOT) d = sqrtf(fmaxf(d + qn, 0.0f));
                             if (METRIC == NDB_COSINE && slot != INVALID_SLOT) d = qn > 0.0f ? fmaf(d, 1.0f / sqrtf(qn), 1.0f) : 1.0f;
                         }
-                        p.pdist[base + j] = d;
-                        p.pslot[base + j] = slot;
+                        od[j] = d;
+                        os[j] = slot;
                     }
+                }
+                if (KT % 4 == 0 && p.k == KT) {
+                    // a full list is KT * 4 bytes, 16-byte aligned: four 128-bit stores per array (scalar stores reuse
+                    // their address registers and wait for one another)
+#pragma unroll
+                    for (int j = 0; j < KT; j += 4) {
+                        *reinterpret_cast<float4 *>(p.pdist + base + j) = make_float4(od[j], od[j + 1], od[j + 2], od[j + 3]);
+                        *reinterpret_cast<uint4 *>(p.pslot + base + j) = make_uint4(os[j], os[j + 1], os[j + 2], os[j + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < KT; j++)
+                        if (j < p.k) { p.pdist[base + j] = od[j]; p.pslot[base + j] = os[j]; }
                 }
             }
         }
@@ -805,7 +826,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-static size_t tc_smem_bytes() { return (size_t) TC_MAX_CHUNKS * TC_QCHUNK_BYTES + (size_t) TC_STAGES * TC_XSTAGE_BYTES + (size_t) TC_NORM_RING * TC_N * 4; }
+static size_t tc_smem_bytes() { return (size_t) TC_MAX_CHUNKS * TC_QCHUNK_BYTES + (size_t) TC_XRING_BYTES + (size_t) TC_NORM_RING * TC_N * 4; }
 
 int tc_build_store(TcStore &st, const float *il32_store, int64_t n, int dim, int dimp, cudaStream_t s)
 {
@@ -914,6 +935,15 @@ int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s)
         TcParams &pm = const_cast<TcParams &>(p);
         const int rest = p.dim - (p.nkc - 1) * TC_KC;
         pm.kg_last = (p.dim > 0 && rest > 0 && rest <= TC_KC && !getenv("NDB_TC_FULL_K")) ? ((rest + 15) / 16) * 2 : TC_KC / 8;
+        const char *se = getenv("NDB_TC_STAGES");                                          // measurement switch
+        if (p.nkc == 1) {
+            pm.xstride = pm.kg_last * (TC_N / 8) * 128;
+            pm.nstages = std::min(TC_MAX_STAGES, TC_XRING_BYTES / pm.xstride);
+            if (se && atoi(se) >= 1 && atoi(se) < pm.nstages) pm.nstages = atoi(se);
+        } else {
+            pm.xstride = TC_XSTAGE_BYTES;
+            pm.nstages = 2;
+        }
     }
 #ifdef NDB_TC_COUNTERS
     static DevBuf dbgc;

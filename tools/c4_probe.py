@@ -67,6 +67,11 @@ def main():
         for s in range(3):
             step(0 if one_batch else s % 4)
         torch.cuda.synchronize()
+        if os.environ.get("PROBE_PROFILE"):          # under `ncu --profile-from-start off`: capture exactly one step
+            torch.cuda.profiler.start()
+            step(0)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         if have_ctr:
             counters()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
