@@ -61,6 +61,7 @@ struct TcParams {
                                    // (cert_bound.cuh), which is what makes the selection certifiable
     int dim;                       // row dimension (for the accumulation slack, and for kg_last)
     int nstages, xstride;          // set by tc_launch: depth of the stored-row ring and the byte stride of its stages
+    int heavy;                     // set by tc_launch: takers per 32 columns above which a warp sorts instead of inserting
     int kg_last;                   // set by tc_launch: 8-element K groups of the last chunk that are copied and multiplied
     int packed;                    // 1: items span <= TC_PACKED_MAX_TILES tiles; (distance | index) keys, sorting-network epilogue
     float *debug_d;                // optional: raw accumulator of the first tile [128][256]

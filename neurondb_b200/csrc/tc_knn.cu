@@ -617,56 +617,36 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                 const int jlo = it.rep == 4 ? (warp & 3) : 0;
                 const int nchunk = ((p.debug_mode & 1) || warp_dead) ? 0 : (it.rep == 4 ? jlo + 1 : TC_N / 64);
                 const uint32_t acc_addr = tmem_base + lane_addr + a * TC_N + half * (TC_N / 2);
-                // one 32-column chunk of the accumulator, already in registers
-                auto process = [&](uint32_t (&v)[32], const int j) {
-                    const int col0 = half * (TC_N / 2) + j * 32;
-                    // this chunk's row norms (inner product: the query tile holds -q, the accumulator is the candidate
-                    // itself, no norms)
-                    float4 n4s[METRIC == NDB_IP ? 1 : 8];
-                    if (METRIC != NDB_IP) {
-#pragma unroll
-                        for (int i4 = 0; i4 < 8; i4++) n4s[i4] = *reinterpret_cast<const float4 *>(xn + col0 + 4 * i4);
-                    }
-                    if (p.debug_mode & 8) {                    // bisection: TMEM reads only
-                        if (__uint_as_float(v[0]) == 1.2345e-30f) bd[0] = 0.0f;
-                        return;
-                    }
-                    if (p.debug_d && item == 0 && t == t0) {   // first item's first tile
-#pragma unroll
-                        for (int i = 0; i < 32; i++) p.debug_d[(size_t) ql * TC_N + col0 + i] = __uint_as_float(v[i]);
-                    }
-                    // 32 independent FFMAs, then one min tree: the common case (nothing beats the
-                    // threshold) is branch-free.
-                    float c[32];
-                    // columns that may rank: stored rows only (inner product: the padding of a list's last tile is zero
-                    // rows with candidate 0; the other metrics give pad rows +inf / NaN candidates), live queries only
-                    const uint32_t ncol = tile_rows > (uint32_t) col0 ? tile_rows - (uint32_t) col0 : 0u;
-                    const uint32_t okmask = !live ? 0u : (ncol >= 32u ? 0xffffffffu : (1u << ncol) - 1u);
+                bool changed = false;                                   // did this tile put anything into the list
+                // candidates of one 32-column chunk (its accumulator values are in registers) and their minimum
+                constexpr int NN4 = METRIC == NDB_IP ? 1 : 8;
+                auto candidates = [&](const uint32_t (&v)[32], const float4 (&n4s)[NN4], float (&c)[32]) -> float {
                     if (METRIC == NDB_IP) {
+                        // the query tile holds -q: the accumulator is the candidate itself, no norms
 #pragma unroll
                         for (int i = 0; i < 32; i++) c[i] = __uint_as_float(v[i]);
                     } else {
 #pragma unroll
-                    for (int i4 = 0; i4 < 8; i4++) {
-                        const float4 n4 = n4s[i4];
-                        if (METRIC == NDB_L2) {
-                            c[4 * i4 + 0] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 0]), n4.x);
-                            c[4 * i4 + 1] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 1]), n4.y);
-                            c[4 * i4 + 2] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 2]), n4.z);
-                            c[4 * i4 + 3] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 3]), n4.w);
-                        } else {
-                            // p.xnorm holds 1 / ||x|| here (0 for a zero row, +inf for a pad row): -x.q / ||x||
-                            // orders the rows like the cosine distance, whose 1 / ||q|| is applied on output.
-                            // A pad row is all zeros, its dot product is exactly 0 and 0 * inf = NaN, which
-                            // loses every comparison below (and packs as an empty key): one FMUL per column.
-                            c[4 * i4 + 0] = -__uint_as_float(v[4 * i4 + 0]) * n4.x;
-                            c[4 * i4 + 1] = -__uint_as_float(v[4 * i4 + 1]) * n4.y;
-                            c[4 * i4 + 2] = -__uint_as_float(v[4 * i4 + 2]) * n4.z;
-                            c[4 * i4 + 3] = -__uint_as_float(v[4 * i4 + 3]) * n4.w;
+                        for (int i4 = 0; i4 < 8; i4++) {
+                            const float4 n4 = n4s[i4 < NN4 ? i4 : 0];
+                            if (METRIC == NDB_L2) {
+                                c[4 * i4 + 0] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 0]), n4.x);
+                                c[4 * i4 + 1] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 1]), n4.y);
+                                c[4 * i4 + 2] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 2]), n4.z);
+                                c[4 * i4 + 3] = fmaf(-2.0f, __uint_as_float(v[4 * i4 + 3]), n4.w);
+                            } else {
+                                // p.xnorm holds 1 / ||x|| here (0 for a zero row, +inf for a pad row): -x.q / ||x||
+                                // orders the rows like the cosine distance, whose 1 / ||q|| is applied on output.
+                                // A pad row is all zeros, its dot product is exactly 0 and 0 * inf = NaN, which
+                                // loses every comparison below (and packs as an empty key): one FMUL per column.
+                                c[4 * i4 + 0] = -__uint_as_float(v[4 * i4 + 0]) * n4.x;
+                                c[4 * i4 + 1] = -__uint_as_float(v[4 * i4 + 1]) * n4.y;
+                                c[4 * i4 + 2] = -__uint_as_float(v[4 * i4 + 2]) * n4.z;
+                                c[4 * i4 + 3] = -__uint_as_float(v[4 * i4 + 3]) * n4.w;
+                            }
                         }
                     }
-                    }
-                    // minimum of the 32 candidates through 3-input minima (FMNMX3): 17 instructions
+                    // minimum of the 32 candidates through 3-input minima (FMNMX3): 16 instructions
                     float m[11];
 #pragma unroll
                     for (int i = 0; i < 10; i++) m[i] = fminf(fminf(c[3 * i], c[3 * i + 1]), c[3 * i + 2]);
@@ -675,24 +655,32 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     m[3] = fminf(fminf(m[3], m[4]), m[5]);
                     m[6] = fminf(fminf(m[6], m[7]), m[8]);
                     m[9] = fminf(m[9], m[10]);
-                    m[0] = fminf(fminf(m[0], m[3]), fminf(m[6], m[9]));
+                    return fminf(fminf(m[0], m[3]), fminf(m[6], m[9]));
+                };
+                // the rare part: some lane of the warp holds a candidate below its threshold in chunk j
+                auto takers = [&](const float (&c)[32], const int j, const float cmin) {
+                    const int col0 = half * (TC_N / 2) + j * 32;
+                    // columns that may rank: stored rows only (inner product: the padding of a list's last tile is zero
+                    // rows with candidate 0; the other metrics give pad rows +inf / NaN candidates), live queries only
+                    const uint32_t ncol = tile_rows > (uint32_t) col0 ? tile_rows - (uint32_t) col0 : 0u;
+                    const uint32_t okmask = !live ? 0u : (ncol >= 32u ? 0xffffffffu : (1u << ncol) - 1u);
+                    changed = true;
                     if constexpr (PACKED) {
                         uint32_t mask = 0;
                         float thc = thr - cadd;                         // threshold in raw candidate units
-                        if (m[0] < thc) {
+                        if (cmin < thc) {
 #pragma unroll
                             for (int i = 0; i < 32; i++) mask |= (c[i] < thc ? 1u : 0u) << i;
                             mask &= okmask;
                         }
                         const uint32_t ibase = (t - t0) * (TC_N / 2) + j * 32;
 #ifdef NDB_TC_COUNTERS
-                        dc_chunks++;
                         dc_any += __any_sync(FULL, mask != 0) ? 1 : 0;
                         dc_takers += __popc(mask);
-                        if (__any_sync(FULL, __popc(mask) > TC_HEAVY)) dc_heavy++;
+                        if (__any_sync(FULL, __popc(mask) > p.heavy)) dc_heavy++;
                         else { int mx = __popc(mask); for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o)); dc_iters += mx; }
 #endif
-                        if (__any_sync(FULL, __popc(mask) > TC_HEAVY)) {
+                        if (__any_sync(FULL, __popc(mask) > p.heavy)) {
                             // some lane has many takers (its list is still filling): every lane sorts
                             // its 32 keys through the network -- a fixed cost, no lane-by-lane tail
                             float g[16];
@@ -716,7 +704,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             }
                         }
                     } else {
-                        if (m[0] < thr) {
+                        if (cmin < thr) {
                             uint32_t mask = 0;
 #pragma unroll
                             for (int i = 0; i < 32; i++) mask |= (c[i] < thr ? 1u : 0u) << i;
@@ -732,25 +720,72 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                             }
                         }
                     }
-                                };
-                // One TMEM read per chunk, waited for at once: its latency is a few dozen cycles, which the other epilogue
-                // warp of the scheduler covers.  (Reading a chunk ahead needs a second register set: copying it cost 32
-                // moves per chunk, alternating two sets doubled the code and thrashed the instruction cache.)
+                };
+                // Two chunks per round: both TMEM reads in flight together, two independent min trees, ONE vote that
+                // decides the common case (no lane of the warp has a taker in either chunk).  With two epilogue warps
+                // per scheduler the loop is bound by its dependent latencies, not by issue slots.
+                // (Inner product only: the other metrics keep candidates apart from the accumulator values, and two chunks of
+                // both do not fit the register file -- measured slower.)
+                constexpr int CPR = METRIC == NDB_IP ? 2 : 1;           // chunks per round
 #pragma unroll 1
-                for (int j = jlo; j < nchunk; j++) {
-                    uint32_t v[32];
-                    tmem_ld32(acc_addr + j * 32, v);
+                for (int j = jlo; j < nchunk; j += CPR) {
+                    const bool two = CPR == 2 && j + 1 < nchunk;
+                    uint32_t va[32], vb[32];
+                    tmem_ld32(acc_addr + j * 32, va);
+                    if (two) tmem_ld32(acc_addr + (j + 1) * 32, vb);
+                    // the chunk's row norms meanwhile: their shared-memory latency overlaps the TMEM wait
+                    float4 na[NN4], nb[NN4];
+                    if (METRIC != NDB_IP) {
+                        const float *xc = xn + half * (TC_N / 2) + j * 32;
+#pragma unroll
+                        for (int i4 = 0; i4 < NN4; i4++) na[i4] = *reinterpret_cast<const float4 *>(xc + 4 * i4);
+                        if (two) {
+#pragma unroll
+                            for (int i4 = 0; i4 < NN4; i4++) nb[i4] = *reinterpret_cast<const float4 *>(xc + 32 + 4 * i4);
+                        }
+                    }
                     tmem_ld_wait();
-                    process(v, j);
+                    if (p.debug_mode & 8) {                    // bisection: TMEM reads only
+                        if (__uint_as_float(va[0]) == 1.2345e-30f) bd[0] = 0.0f;
+                        continue;
+                    }
+                    if (p.debug_d && item == 0 && t == t0) {   // first item's first tile (ndbdbg_tc_gemm)
+                        const int col0 = half * (TC_N / 2) + j * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) p.debug_d[(size_t) ql * TC_N + col0 + i] = __uint_as_float(va[i]);
+                        if (two) {
+#pragma unroll
+                            for (int i = 0; i < 32; i++) p.debug_d[(size_t) ql * TC_N + col0 + 32 + i] = __uint_as_float(vb[i]);
+                        }
+                    }
+#ifdef NDB_TC_COUNTERS
+                    dc_chunks += two ? 2 : 1;
+#endif
+                    float ca[32], cb[32];
+                    const float ma = candidates(va, na, ca);
+                    float mb = INFINITY;
+                    if (two) mb = candidates(vb, nb, cb);
+                    if constexpr (PACKED) {
+                        // (the packed path sorts warp-wide: its lanes enter together)
+                        const float lim = thr - cadd;
+                        if (!__any_sync(FULL, fminf(ma, mb) < lim)) continue;
+                        if (__any_sync(FULL, ma < lim)) takers(ca, j, ma);
+                        if (two && __any_sync(FULL, mb < thr - cadd)) takers(cb, j + 1, mb);
+                    } else {
+                        if (ma < thr) takers(ca, j, ma);               // lane by lane: no vote on the dense kernel's hot path
+                        if (two && mb < thr) takers(cb, j + 1, mb);
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(&acc_empty[a]);                             // 256 arrivals release the accumulator
                 // the key the bound is taken from: any list that holds kpub entries proves that the query's kpub-th best is
                 // at most its kpub-th key (kpub = the caller's k; the list itself keeps KT >= kpub entries)
-                float kth = bd[KT - 1];
+                // (only a tile that put something into the list can improve the bound)
+                float kth = changed ? bd[KT - 1] : published;
                 // (a warp-uniform switch: written as a loop of selects the compiler turns it into an indexed load and moves
                 // the list to local memory)
 #define NDB_KTH(I) case (I) + 1: kth = bd[(I) < KT ? (I) : KT - 1]; break;
+                if (__any_sync(FULL, changed))
                 switch (p.kpub) {
                     NDB_KTH(0) NDB_KTH(1) NDB_KTH(2) NDB_KTH(3) NDB_KTH(4) NDB_KTH(5) NDB_KTH(6) NDB_KTH(7)
                     NDB_KTH(8) NDB_KTH(9) NDB_KTH(10) NDB_KTH(11) NDB_KTH(12) NDB_KTH(13) NDB_KTH(14)
@@ -810,13 +845,14 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
 #ifdef NDB_TC_COUNTERS
         if (p.dbg_counters) {
             // warp-level counts from lane 0, takers from every lane
+            unsigned long long *dc = p.dbg_counters + (p.item_lo_ptr ? 8 : 0);      // second phase of a two-phase scan: [8..13)
             if (lane == 0) {
-                atomicAdd(p.dbg_counters + 0, (unsigned long long) dc_chunks);
-                atomicAdd(p.dbg_counters + 1, (unsigned long long) dc_any);
-                atomicAdd(p.dbg_counters + 2, (unsigned long long) dc_heavy);
-                atomicAdd(p.dbg_counters + 3, (unsigned long long) dc_iters);
+                atomicAdd(dc + 0, (unsigned long long) dc_chunks);
+                atomicAdd(dc + 1, (unsigned long long) dc_any);
+                atomicAdd(dc + 2, (unsigned long long) dc_heavy);
+                atomicAdd(dc + 3, (unsigned long long) dc_iters);
             }
-            atomicAdd(p.dbg_counters + 4, (unsigned long long) dc_takers);
+            atomicAdd(dc + 4, (unsigned long long) dc_takers);
         }
 #endif
     }
@@ -935,7 +971,8 @@ int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s)
         TcParams &pm = const_cast<TcParams &>(p);
         const int rest = p.dim - (p.nkc - 1) * TC_KC;
         pm.kg_last = (p.dim > 0 && rest > 0 && rest <= TC_KC && !getenv("NDB_TC_FULL_K")) ? ((rest + 15) / 16) * 2 : TC_KC / 8;
-        const char *se = getenv("NDB_TC_STAGES");                                          // measurement switch
+        const char *se = getenv("NDB_TC_STAGES"), *he = getenv("NDB_TC_HEAVY");            // measurement switches
+        pm.heavy = he ? atoi(he) : TC_HEAVY;
         if (p.nkc == 1) {
             pm.xstride = pm.kg_last * (TC_N / 8) * 128;
             pm.nstages = std::min(TC_MAX_STAGES, TC_XRING_BYTES / pm.xstride);
@@ -947,7 +984,7 @@ int tc_launch(const TcParams &p, int metric, int k, cudaStream_t s)
     }
 #ifdef NDB_TC_COUNTERS
     static DevBuf dbgc;
-    if (!dbgc.p) { NDB_CHECK(dbgc.reserve(64)); NDB_CUDA(cudaMemsetAsync(dbgc.p, 0, 64, s)); }
+    if (!dbgc.p) { NDB_CHECK(dbgc.reserve(128)); NDB_CUDA(cudaMemsetAsync(dbgc.p, 0, 128, s)); }
     const_cast<TcParams &>(p).dbg_counters = p.gthr ? dbgc.as<unsigned long long>() : nullptr;      // list mode only
     g_tc_dbg_counters = dbgc.as<unsigned long long>();
 #endif
@@ -1071,15 +1108,15 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
 
 #ifdef NDB_TC_COUNTERS
 // development hook: read and reset the epilogue statistics of the list-mode launches since the last call
-extern "C" int ndbdbg_tc_counters(unsigned long long *out /* [8] */)
+extern "C" int ndbdbg_tc_counters(unsigned long long *out /* [16] */)
 {
     using namespace ndb;
     NDB_CHECK(require_init());
-    for (int i = 0; i < 8; i++) out[i] = 0;
+    for (int i = 0; i < 16; i++) out[i] = 0;
     if (!g_tc_dbg_counters) return NDB_B200_OK;
     NDB_CUDA(cudaDeviceSynchronize());
-    NDB_CUDA(cudaMemcpy(out, g_tc_dbg_counters, 64, cudaMemcpyDeviceToHost));
-    NDB_CUDA(cudaMemset(g_tc_dbg_counters, 0, 64));
+    NDB_CUDA(cudaMemcpy(out, g_tc_dbg_counters, 128, cudaMemcpyDeviceToHost));
+    NDB_CUDA(cudaMemset(g_tc_dbg_counters, 0, 128));
     return NDB_B200_OK;
 }
 #endif

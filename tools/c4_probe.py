@@ -50,7 +50,7 @@ def main():
         have_ctr = False
 
     def counters():
-        buf = (ctypes.c_ulonglong * 8)()
+        buf = (ctypes.c_ulonglong * 16)()
         lib.ndbdbg_tc_counters(buf)
         return list(buf)
 
@@ -98,9 +98,11 @@ def main():
         cs = ix.cert_stats()
         line = f"[{v or 'default'}] step {ms:.3f} ms  list kernel {np.mean(km):.3f} ms  same_as_default {same}  fallback_q {cs['list_fallback_queries']} exact_evals/q {cs['list_exact_evals'] / nq:.1f}"
         if ctr:
-            ch, anyc, heavy, iters, takers = [c / steps for c in ctr[:5]]
-            line += (f"  | warp-chunks {ch:.3g} any {anyc / max(ch, 1):.3f} heavy {heavy / max(ch, 1):.4f} insert-rounds/chunk {iters / max(ch, 1):.3f}"
-                     f" takers/query {takers / nq:.0f}")
+            for name, off in (("phase 1 / single", 0), ("phase 2", 8)):
+                ch, anyc, heavy, iters, takers = [c / steps for c in ctr[off:off + 5]]
+                if ch:
+                    line += (f"\n    {name}: warp-chunks {ch:.3g} any {anyc / max(ch, 1):.3f} heavy {heavy / max(ch, 1):.4f} insert-rounds/chunk "
+                             f"{iters / max(ch, 1):.3f} takers/query {takers / nq:.0f}")
         print(line, flush=True)
         for kk in sets:
             os.environ.pop(kk, None)
