@@ -421,13 +421,15 @@ def run_ivf(c, args, w, wname, with_cpu=True, with_alt=True):
         traffic = tj.get("tensor_dram_bytes_per_launch")
         roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
                     "traffic": traffic, "peak_source": peak_kind + " (sustained bf16, MEASURED_PEAKS.json)",
-                    "kernel": "tc_knn_kernel (list mode)", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
+                    "kernel": "tc_knn_kernel (list mode%s)" % ("; the second launch of the two-phase scan: every list but the queries' nearest"
+                                                               if w["n"] >= 5_000_000 else ""),
+                    "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
                     "distance_evals_per_launch": evals,
                     "hbm": None if not traffic else {"achieved": traffic / (kernel_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                                      "frac": traffic / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                                      "note": "ncu dram bytes of one launch / event-timed launch duration"},
-                    "note": "algorithmic flops only (2*dim per evaluation): K padded to 128 and tile padding (lists to 256 rows, "
-                            "query groups to 128) are executed but not counted"}
+                    "note": "algorithmic flops only (2*dim per evaluation) of this launch's evaluations: K rounded up to 16 and tile "
+                            "padding (lists to 256 rows, query groups to 128) are executed but not counted"}
     else:
         # fp32 list scan: every list block is re-used for a tile of queries from registers, so the binding limit
         # is FP32 issue: 3 rounded ops (sub, mul, add) per element, 128 lanes per SM per clock

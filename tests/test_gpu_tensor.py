@@ -102,6 +102,22 @@ def test_tensor_ivf_equals_fp32_path(ndb, orc, n, dim, lists, nq, nprobe, k, met
         assert st["coarse_fallback_queries"] <= 0.05 * nq + 2, st
 
 
+@pytest.mark.parametrize("n,dim,lists,nq,nprobe,k,metric", IVF_CASES)
+def test_tensor_ivf_two_phase_scan_equals_fp32_path(ndb, monkeypatch, n, dim, lists, nq, nprobe, k, metric):
+    """The two-phase scan (first segment of every query's nearest list, the bound it leaves, then the rest) is chosen
+    by the library for long lists only; forced here on every shape -- lists of one segment and of several, replicated
+    query tiles, every metric -- and held to the same contract: ids and distance bits of the fp32 path."""
+    monkeypatch.setenv("NDB_IVF_TC_PHASES", "2")
+    X = W.mixture(n, dim, max(lists // 2, 2), 900 + n)
+    Q = W.mixture(nq, dim, max(lists // 2, 2), 977 + n, centers_seed=900 + n)
+    ix = ndb.IvfIndex(dim, lists, metric)
+    ix.ivfbuild(X)
+    ix.ivfinsert(X)
+    _assert_equals_fp32_path(ndb, ix, Q, nprobe, k)
+    monkeypatch.setenv("NDB_IVF_TC_PHASES", "1")
+    _assert_equals_fp32_path(ndb, ix, Q, nprobe, k)
+
+
 @pytest.mark.parametrize("metric", [1, 2, 3])
 def test_tensor_ivf_exact_on_structureless_data(ndb, metric):
     """Isotropic Gaussian rows: neighbours are nearly equidistant, the rounding bound often cannot separate the k-th
