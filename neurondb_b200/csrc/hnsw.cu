@@ -87,18 +87,69 @@ struct WarpCtx {
     float *wd;            // [ef] distances (shared)
     uint32_t *wid;        // [ef] node ids, top bit = expanded (shared)
     int *widx;            // [ef] scratch index array for the literal selection sort (shared)
+    // Visited set.  Searches keep it in SHARED memory: an exact open-addressing hash set of node ids (hset, hcap slots,
+    // linear probing, EMPTY = 0xFFFFFFFF), one per warp -- a query at ef_search = 40 touches ~1 400 of a million nodes,
+    // and a bitset over all nodes (125 KB per warp at 1 M nodes, 600 MB for the grid) turns every test into a DRAM
+    // access.  When the set passes 7/8 of its slots (large ef) its content moves to the per-warp bitset in global memory
+    // and the search carries on there; the graph build (ef_construction >= 64, every level) uses the bitset throughout.
+    uint32_t *hset;       // shared; nullptr = bitset only
+    int hcap;             // power of two
+    bool hashed;          // the set currently lives in hset
     uint32_t *bits;       // per-warp visited bitset, (n+31)/32 words (global)
     uint32_t *vlist;      // nodes whose bit was set (global)
     int vcap, nvis;
     long long evals;
 };
 
+constexpr uint32_t HSET_EMPTY = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t hset_hash(uint32_t e) { return e * 2654435761u; }
+
 __device__ __forceinline__ bool test_bit(const uint32_t *bits, uint32_t e) { return (bits[e >> 5] >> (e & 31)) & 1u; }
 
-// marks `e` visited for every lane with fresh == true and records it for the later clear
+// has node e been visited (any lane, any e < n; no side effect)
+__device__ __forceinline__ bool is_visited(const WarpCtx &w, uint32_t e)
+{
+    if (!w.hashed) return test_bit(w.bits, e);
+    const uint32_t mask = (uint32_t) w.hcap - 1u;
+    for (uint32_t h = (hset_hash(e) >> 8) & mask;; h = (h + 1u) & mask) {
+        const uint32_t v = w.hset[h];
+        if (v == e) return true;
+        if (v == HSET_EMPTY) return false;
+    }
+}
+
+// marks `e` visited for every lane with fresh == true (the fresh lanes hold distinct nodes) and records it for the later
+// clear; moves the set to the global bitset when the shared one fills up
 __device__ __forceinline__ void mark_visited(WarpCtx &w, uint32_t e, bool fresh, int lane)
 {
     const unsigned fm = __ballot_sync(FULL, fresh);
+    if (w.hashed) {
+        if (fresh) {
+            const uint32_t mask = (uint32_t) w.hcap - 1u;
+            for (uint32_t h = (hset_hash(e) >> 8) & mask;; h = (h + 1u) & mask)
+                if (atomicCAS(&w.hset[h], HSET_EMPTY, e) == HSET_EMPTY) break;
+        }
+        w.nvis += __popc(fm);
+        __syncwarp();
+        if (w.nvis > w.hcap - w.hcap / 8) {
+            int cnt = 0;
+            for (int base = 0; base < w.hcap; base += 32) {
+                const uint32_t v = w.hset[base + lane];
+                const bool ok = v != HSET_EMPTY;
+                const unsigned m = __ballot_sync(FULL, ok);
+                if (ok) {
+                    atomicOr(&w.bits[v >> 5], 1u << (v & 31));
+                    const int pos = cnt + __popc(m & ((1u << lane) - 1));
+                    if (pos < w.vcap) w.vlist[pos] = v;
+                }
+                cnt += __popc(m);
+            }
+            w.nvis = cnt;
+            w.hashed = false;
+            __syncwarp();
+        }
+        return;
+    }
     if (fresh) {
         atomicOr(&w.bits[e >> 5], 1u << (e & 31));
         const int pos = w.nvis + __popc(fm & ((1u << lane) - 1));
@@ -111,6 +162,11 @@ __device__ __forceinline__ void mark_visited(WarpCtx &w, uint32_t e, bool fresh,
 __device__ __forceinline__ void clear_visited(WarpCtx &w, int64_t n, int lane)
 {
     __syncwarp();
+    if (w.hset) {
+        for (int i = lane; i < w.hcap; i += 32) w.hset[i] = HSET_EMPTY;
+        if (w.hashed) { w.nvis = 0; __syncwarp(); return; }
+        w.hashed = true;            // (the bitset is cleared below; the next query starts in shared memory again)
+    }
     if (w.nvis <= w.vcap) {
         for (int i = lane; i < w.nvis; i += 32) w.bits[w.vlist[i] >> 5] = 0u;
     } else {
@@ -177,7 +233,7 @@ __device__ uint32_t greedy_descent(const HnswGraph &g, WarpCtx &w, typename P::N
 template <class P>
 __device__ int search_layer(const HnswGraph &g, WarpCtx &w, typename P::N qn, uint32_t ep, int lev, int ef, int lane)
 {
-    mark_visited(w, ep, lane == 0 && !test_bit(w.bits, ep), lane);
+    mark_visited(w, ep, lane == 0 && !is_visited(w, ep), lane);
     const float d0 = eval_one<P>(g, w, qn, ep, lane);
     if (lane == 0) { w.wd[0] = d0; w.wid[0] = ep; }
     __syncwarp();
@@ -200,7 +256,7 @@ __device__ int search_layer(const HnswGraph &g, WarpCtx &w, typename P::N qn, ui
             const uint32_t e = j < nc ? slots[j] : INVALID_SLOT;
             const bool valid = e != INVALID_SLOT && e < (uint32_t) g.n;
             const unsigned same = __match_any_sync(FULL, e);
-            const bool fresh = valid && (__ffs(same) - 1 == lane) && !test_bit(w.bits, e);
+            const bool fresh = valid && (__ffs(same) - 1 == lane) && !is_visited(w, e);
             mark_visited(w, e, fresh, lane);
             float d = INFINITY;
             if (fresh) d = node_distance<P>(g, w.qs, qn, e);
@@ -256,7 +312,7 @@ __device__ int level0_literal(const HnswGraph &g, WarpCtx &w, typename P::N qn, 
             const uint32_t e = j < nc ? slots[j] : INVALID_SLOT;
             const bool valid = e != INVALID_SLOT && e < (uint32_t) g.n;
             const unsigned same = __match_any_sync(FULL, e);
-            const bool fresh = valid && (__ffs(same) - 1 == lane) && !test_bit(w.bits, e);
+            const bool fresh = valid && (__ffs(same) - 1 == lane) && !is_visited(w, e);
             mark_visited(w, e, fresh, lane);
             float d = INFINITY;
             if (fresh) d = node_distance<P>(g, w.qs, qn, e);
@@ -316,6 +372,7 @@ struct HnswSearchArgs {
     uint32_t *vlist;         // [total_warps][vcap]
     int64_t words;
     int vcap;
+    int hcap;                // slots of the per-warp visited hash set in shared memory (0: bitset only)
     float *out_dist;
     int64_t *out_ids;
     unsigned long long *evals;
@@ -326,13 +383,18 @@ __global__ void hnsw_search_kernel(const HnswSearchArgs a)
 {
     extern __shared__ __align__(16) unsigned char hs[];
     const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-    const size_t per_warp = (size_t) a.g.dimp * 4 + (size_t) a.ef * 12;
+    const size_t per_warp = (size_t) a.g.dimp * 4 + (size_t) a.ef * 12 + (size_t) a.hcap * 4;
     unsigned char *base = hs + per_warp * wl;
     WarpCtx w;
     w.qs = reinterpret_cast<float *>(base);
     w.wd = reinterpret_cast<float *>(base + (size_t) a.g.dimp * 4);
     w.wid = reinterpret_cast<uint32_t *>(w.wd + a.ef);
     w.widx = reinterpret_cast<int *>(w.wid + a.ef);
+    w.hset = a.hcap ? reinterpret_cast<uint32_t *>(w.widx + a.ef) : nullptr;
+    w.hcap = a.hcap;
+    w.hashed = a.hcap != 0;
+    for (int i = lane; i < a.hcap; i += 32) w.hset[i] = HSET_EMPTY;
+    __syncwarp();
     const int gw = blockIdx.x * wpb + wl, total = gridDim.x * wpb;
     w.bits = a.bits + (size_t) gw * a.words;
     w.vlist = a.vlist + (size_t) gw * a.vcap;
@@ -441,6 +503,9 @@ __global__ void hnsw_build_search_kernel(const HnswBuildArgs a)
     w.wid = reinterpret_cast<uint32_t *>(w.wd + a.efc);
     w.widx = reinterpret_cast<int *>(w.wid + a.efc);
     float *cs = reinterpret_cast<float *>(w.widx + a.efc);          // heuristic only: candidate staging
+    w.hset = nullptr;                                               // the build keeps its visited set in the global bitset
+    w.hcap = 0;
+    w.hashed = false;
     const int gw = blockIdx.x * wpb + wl, total = gridDim.x * wpb;
     w.bits = a.bits + (size_t) gw * a.words;
     w.vlist = a.vlist + (size_t) gw * a.vcap;
@@ -645,9 +710,20 @@ static HnswGraph graph_of(const ndb_b200_hnsw *h)
 }
 
 // shared-memory budget -> warps per CTA and grid for the warp-per-query kernels
-static int hnsw_launch_shape(const ndb_b200_hnsw *h, int ef, int *wpb, int *grid, size_t *smem, bool staging = false)
+// visited hash set of a search: ~34 * ef nodes are touched at M = 16 (C3: 1 364 at ef = 40); sized for a load of 7/8 at
+// most, 4096 slots (16 KB per warp) at most -- beyond that the search moves to the global bitset on the fly
+static int hnsw_hset_slots(int ef)
 {
-    const size_t per_warp = (size_t) h->dimp * 4 * (staging ? 2 : 1) + (size_t) ef * 12;
+    static const int off = [] { const char *e = getenv("NDB_HNSW_VISITED_GLOBAL"); return e && atoi(e) ? 1 : 0; }();
+    if (off) return 0;
+    int cap = 1024;
+    while (cap < 4096 && cap * 7 / 8 < ef * 36) cap <<= 1;
+    return cap;
+}
+
+static int hnsw_launch_shape(const ndb_b200_hnsw *h, int ef, int *wpb, int *grid, size_t *smem, bool staging = false, int hcap = 0)
+{
+    const size_t per_warp = (size_t) h->dimp * 4 * (staging ? 2 : 1) + (size_t) ef * 12 + (size_t) hcap * 4;
     const size_t limit = ctx().smem_optin ? ctx().smem_optin - 2048 : 200 * 1024;
     NDB_REQUIRE(per_warp <= limit, NDB_B200_EINVAL, "hnsw: dim=%d with ef=%d does not fit in shared memory", h->dim, ef);
     int w = (int) std::min<size_t>(8, (limit / 2) / per_warp);     // aim for >= 2 CTAs per SM
@@ -996,7 +1072,8 @@ int ndb_b200_hnsw_search_dev(ndb_b200_hnsw *h, const float *Q_dev, int nq, int s
     cudaStream_t s = stream ? (cudaStream_t) stream : ctx().stream;
     int wpb, grid;
     size_t smem;
-    NDB_CHECK(hnsw_launch_shape(h, ef, &wpb, &grid, &smem));
+    const int hcap = hnsw_hset_slots(ef);
+    NDB_CHECK(hnsw_launch_shape(h, ef, &wpb, &grid, &smem, false, hcap));
     if ((int64_t) grid * wpb > nq) grid = (nq + wpb - 1) / wpb;
     NDB_CHECK(hnsw_scratch(h, ctx().sm_count * 32, s));
     if (strategy == NDB_COSINE) NDB_CHECK(hnsw_norms(h, s));
@@ -1011,6 +1088,7 @@ int ndb_b200_hnsw_search_dev(ndb_b200_hnsw *h, const float *Q_dev, int nq, int s
     a.vlist = h->vlist.as<uint32_t>();
     a.words = h->bits_words;
     a.vcap = 16384;
+    a.hcap = hcap;
     a.out_dist = dist_dev;
     a.out_ids = ids_dev;
     a.evals = h->evals.as<unsigned long long>();

@@ -706,7 +706,9 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     // more epilogue work in the other lists than the extra, thinly filled query tiles of phase 1 cost.
     const char *phases_e = getenv("NDB_IVF_TC_PHASES");        // 1 / 2 force the choice (measurement switch)
     const int phases_env = phases_e ? atoi(phases_e) : 0;
-    const bool two_phase = np > 1 && (phases_env == 2 || (phases_env != 1 && ix->tc_rows_per_pair >= 8192.0));
+    // (expected evaluations of the batch on this rank: below ~1e9 the scan is too short to repay two more launches and
+    // the thinly filled query tiles of phase 1 -- C2, 0.35e9: 0.56 ms in two phases, 0.48 ms in one)
+    const bool two_phase = np > 1 && (phases_env == 2 || (phases_env != 1 && ix->tc_rows_per_pair * (double) npairs >= 1.0e9));
     const uint32_t split = two_phase ? (uint32_t) L : 0u;
     const int NV = two_phase ? 2 * L : L;                   // virtual lists
     NDB_CHECK(ix->cnt.reserve((size_t) NV * 4 * 2));

@@ -582,8 +582,12 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                 cq.eq = eq; cq.qnr = qr * 1.0002f; cq.qn = (qr + eq) * 1.0002f; cq.qn_lo = fmaxf(qr - eq, 0.0f) * 0.9998f;
             }
             if (p.gthr && live) {
-                const uint32_t pr = p.qmap[(size_t) it.qtile * TC_M + ql];
-                if (pr != INVALID_SLOT) gcell = p.gthr + pr / p.nprobe;
+                if (p.qmap) {
+                    const uint32_t pr = p.qmap[(size_t) it.qtile * TC_M + ql];
+                    if (pr != INVALID_SLOT) gcell = p.gthr + pr / p.nprobe;
+                } else {
+                    gcell = p.gthr + (size_t) it.qtile * TC_M + ql;         // dense mode: one cell per tile position
+                }
             }
             float thr = gcap;                                           // KT-th best so far, in "candidate" units
             // candidate units: L2 -> ||x||^2 - 2 x.q (PACKED: + ||q||^2, i.e. the squared distance);
@@ -1044,9 +1048,14 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     NDB_CHECK(sc.qnorm.reserve((size_t) nqpad * 4));
     NDB_CHECK(tc_block_queries(Q_dev, nullptr, 0, nq, nqpad, dim, nkc, sc.qb.as<__nv_bfloat16>(), sc.qnorm.as<float>(), s, nullptr, nullptr,
                                metric == NDB_IP));
-    // split the stored tiles into ranges so that there are ~2 work items per SM
+    // Split the stored tiles into ranges so that every SM gets ~8 work items (of at least 32 tiles): the persistent CTAs
+    // take whole items, and with ~2 per SM the last round ran a fraction of the grid (C5: 316 items on 148 SMs).  The
+    // items of a query share an upper bound of its k-th best candidate (p.gthr, as in list mode), so a range does not
+    // pay for filling its lists from nothing.
     const uint32_t sms = (uint32_t) ctx().sm_count;
-    uint32_t nranges = (2 * sms + nqt - 1) / nqt;
+    static const uint32_t per_sm = [] { const char *e = getenv("NDB_TC_ITEMS_PER_SM"); int x = e ? atoi(e) : 8; return (uint32_t) (x >= 1 ? x : 8); }();
+    uint32_t nranges = (per_sm * sms + nqt - 1) / nqt;
+    if (nranges > (uint32_t) (st.ntiles / 32)) nranges = (uint32_t) (st.ntiles / 32);
     if (nranges < 1) nranges = 1;
     if (nranges > (uint32_t) st.ntiles) nranges = (uint32_t) st.ntiles;
     uint32_t tpr = (uint32_t) ((st.ntiles + nranges - 1) / nranges);
@@ -1093,6 +1102,11 @@ int tc_knn(const TcStore &st, TcScratch &sc, int dim, int metric, const float *Q
     p.pdist = sc.pdist.as<float>();
     p.pslot = sc.pslot.as<uint32_t>();
     p.packed = packed ? 1 : 0;
+    if (!packed && !getenv("NDB_TC_DENSE_NOSHARE")) {
+        NDB_CHECK(sc.gthr.reserve((size_t) nqpad * 4));
+        NDB_CUDA(cudaMemsetAsync(sc.gthr.p, 0x7f, (size_t) nqpad * 4, s));       // 3.4e38: "no bound yet"
+        p.gthr = sc.gthr.as<float>();
+    }
     p.debug_d = debug_d_dev;
     p.debug_mode = getenv("NDB_TC_DEBUG") ? atoi(getenv("NDB_TC_DEBUG")) : 0;
     const size_t smem = tc_smem_bytes();

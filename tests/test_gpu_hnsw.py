@@ -37,6 +37,26 @@ def test_search_same_graph_is_id_exact(ndb, orc, n, dim, m, efc, build_mode):
             assert h.last_evals() == og.distance_evals()
 
 
+def test_search_visited_set_leaves_shared_memory_unnoticed(ndb, orc):
+    """The visited set of a search is a hash set in shared memory; a search that touches more nodes than it holds
+    (ef = 1000 on 8 000 nodes: nearly all of them) moves it to the global bitset half way.  Ids, distance bits and the
+    number of distance evaluations must not show it; the next query starts in shared memory again."""
+    n, dim, m, efc = 8000, 24, 16, 40
+    X = W.gaussian(n, dim, 41)
+    Q = W.gaussian(60, dim, 42)
+    levels = orc.hnsw_levels(n, seed=3)
+    og = oracle_graph(orc, X, m, efc, levels, 1)
+    h = ndb.HnswIndex(dim, m, efc, 40)
+    h.load_graph(X, og.export())
+    for ef, k in ((1000, 10), (40, 10), (1000, 50)):
+        d, i = h.search(Q, ef, k, 1, ndb.HNSW_BESTFIRST)
+        od, on, cnt = og.search(Q, ef, k, 1, 1)
+        assert np.array_equal(i, np.where(on == 0xFFFFFFFF, -1, on.astype(np.int64))), ef
+        assert np.array_equal(BITS(d), BITS(od)), ef
+        assert h.last_evals() == og.distance_evals()
+        assert h.last_evals() > (3072 * 60 if ef == 1000 else 0)       # (the large searches do overflow the shared set)
+
+
 def test_build_batch1_equals_sequential_oracle(ndb, orc):
     """batch = 1 is hnswInsertNode one node at a time: the exported graph equals the oracle's."""
     n, dim, m, efc = 800, 24, 6, 20

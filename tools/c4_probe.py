@@ -34,7 +34,11 @@ def main():
     ix = ndb.IvfIndex(w["dim"], w["lists"], w["metric"])
     t0 = time.perf_counter()
     ix.ivfbuild(X)
-    ix.ivfinsert(X, np.arange(n, dtype=np.int64))
+    stripe = int(os.environ.get("PROBE_STRIPE", "1"))      # one rank's share of a striped N-GPU index (row i on rank i % N)
+    if stripe > 1:
+        ix.ivfinsert(X[0::stripe], np.arange(0, n, stripe, dtype=np.int64))
+    else:
+        ix.ivfinsert(X, np.arange(n, dtype=np.int64))
     ix.prepare(ndb.ARITH_TENSOR)
     print(f"{wname}: build {time.perf_counter() - t0:.2f} s", flush=True)
     st = torch.cuda.Stream()
