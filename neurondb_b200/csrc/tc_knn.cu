@@ -736,7 +736,9 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     const bool two = CPR == 2 && j + 1 < nchunk;
                     uint32_t va[32], vb[32];
                     tmem_ld32(acc_addr + j * 32, va);
-                    if (two) tmem_ld32(acc_addr + (j + 1) * 32, vb);
+                    // (an odd last chunk is read twice rather than leaving vb conditionally defined: the compiler then keeps
+                    // the candidates in the registers the TMEM read delivered them to instead of copying them)
+                    if constexpr (CPR == 2) tmem_ld32(acc_addr + (two ? j + 1 : j) * 32, vb);
                     // the chunk's row norms meanwhile: their shared-memory latency overlaps the TMEM wait
                     float4 na[NN4], nb[NN4];
                     if (METRIC != NDB_IP) {
@@ -768,7 +770,10 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     float ca[32], cb[32];
                     const float ma = candidates(va, na, ca);
                     float mb = INFINITY;
-                    if (two) mb = candidates(vb, nb, cb);
+                    if constexpr (CPR == 2) {
+                        mb = candidates(vb, nb, cb);
+                        mb = two ? mb : INFINITY;
+                    }
                     if constexpr (PACKED) {
                         // (the packed path sorts warp-wide: its lanes enter together)
                         const float lim = thr - cadd;

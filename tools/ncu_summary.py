@@ -80,7 +80,10 @@ def kernel(path, index=0):
         if "issue_stalled" in h and h.endswith("per_issue_active.ratio"):
             print("  %-28s %s" % (h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), r[i]))
     src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    blocks = src.split('"Kernel Name",')[1:]
+    blocks = []
+    for b in src.split('"Kernel Name",')[1:]:       # (--import-source on: most kernels appear twice in a row, as two views)
+        if not blocks or b != blocks[-1]:
+            blocks.append(b)
     if index < len(blocks):
         lines = blocks[index].split("\n")
         srows = list(csv.reader(lines[1:]))
