@@ -1,6 +1,4 @@
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
-timeout 300 $TR tools/multi_gpu_check.py > gpurun_out/mg8.json 2> gpurun_out/mg8.err; echo "mg8 rc=$?"; tail -1 gpurun_out/mg8.json | cut -c1-600
-timeout 500 $TR bench.py --gpus 8 --steps 10 > gpurun_out/c4_n8.json 2> gpurun_out/c4_n8.err; echo "c4 n8 rc=$?"; tail -c 400 gpurun_out/c4_n8.err
-timeout 500 $TR bench.py --gpus 8 --workload c5 --steps 5 > gpurun_out/c5_n8.json 2> gpurun_out/c5_n8.err; echo "c5 n8 rc=$?"; tail -c 400 gpurun_out/c5_n8.err
-TR4="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512"
-timeout 400 $TR4 bench.py --gpus 4 --steps 10 > gpurun_out/c4_n4.json 2> gpurun_out/c4_n4.err; echo "c4 n4 rc=$?"; tail -c 300 gpurun_out/c4_n4.err
+timeout 300 $TR tools/multi_gpu_check.py > gpurun_out/mg8.json 2> gpurun_out/mg8.err; echo "mg8 rc=$?"; tail -1 gpurun_out/mg8.json | cut -c1-300
+timeout 500 $TR bench.py --gpus 8 > gpurun_out/c4_n8.json 2> gpurun_out/c4_n8.err; echo "c4 n8 rc=$?"; tail -c 300 gpurun_out/c4_n8.err
+timeout 500 $TR bench.py --gpus 8 --workload c5 --steps 5 > gpurun_out/c5_n8.json 2> gpurun_out/c5_n8.err; echo "c5 n8 rc=$?"; tail -c 300 gpurun_out/c5_n8.err
