@@ -152,6 +152,14 @@ int ndb_b200_knn_exact(ndb_b200_dataset *ds, int metric, int arith, const float 
 int ndb_b200_knn_exact_dev(ndb_b200_dataset *ds, int metric, int arith, const float *Q_dev, int nq,
                            int k, float *dist_dev, int64_t *ids_dev, void *stream);
 
+/* knn_classify / knn_regress (src/ml/ml_knn.c:112-357, 363-569; brute-force kernels src/gpu/cuda/gpu_knn_kernels.cu):
+ * euclidean_distance (:76-90: f32 difference, f64 sum) of every resident row to each query, the k nearest, then the
+ * binary majority vote (labels other than 0 / 1 are ignored, class 1 needs a strict majority) or the mean of the
+ * targets.  labels[i] / targets[i] belong to the i-th appended row.  k < 1 -> EINVAL, fewer than k rows -> ERANGE,
+ * NaN / Inf in a query -> EVECTOR, as the SQL functions raise. */
+int ndb_b200_knn_classify(ndb_b200_dataset *ds, const double *labels, const float *Q, int nq, int k, int *out_class);
+int ndb_b200_knn_regress(ndb_b200_dataset *ds, const double *targets, const float *Q, int nq, int k, double *out);
+
 /* ---- IVF k-means: kmeans_init/run/assign/update_centroids/compute_cost
  *      (src/index/ivf_am.c:2070-2294).  Literal semantics: centroids := first k rows,
  *      <= max_iter Lloyd steps, stop when |prevCost - cost| < tol, f32 sequential sums.

@@ -298,6 +298,26 @@ class Dataset(_Handle):
         check(L.load().ndb_b200_knn_exact(self.h, metric, arith, ptr(Q), Q.shape[0], k, ptr(d), ptr(i)))
         return d, i
 
+    def knn_classify(self, labels, Q, k):
+        """knn_classify (ml_knn.c:112-357) for a batch of query vectors: class 0 / 1 per query."""
+        Q = _rows(Q, self.dim, "knn_classify")
+        lab = np.ascontiguousarray(labels, np.float64)
+        if lab.shape != (len(self),):
+            raise NdbError(-1, "knn_classify: one label per row expected")
+        out = np.empty(Q.shape[0], np.int32)
+        check(L.load().ndb_b200_knn_classify(self.h, ptr(lab), ptr(Q), Q.shape[0], k, ptr(out)))
+        return out
+
+    def knn_regress(self, targets, Q, k):
+        """knn_regress (ml_knn.c:363-569): mean target of the k nearest rows per query."""
+        Q = _rows(Q, self.dim, "knn_regress")
+        t = np.ascontiguousarray(targets, np.float64)
+        if t.shape != (len(self),):
+            raise NdbError(-1, "knn_regress: one target per row expected")
+        out = np.empty(Q.shape[0], np.float64)
+        check(L.load().ndb_b200_knn_regress(self.h, ptr(t), ptr(Q), Q.shape[0], k, ptr(out)))
+        return out
+
     def knn_dev(self, q_ptr, nq, k, dist_ptr, ids_ptr, metric=L2, arith=ARITH_OP_F64, stream=None):
         check(L.load().ndb_b200_knn_exact_dev(self.h, metric, arith, ptr(q_ptr), nq, k, ptr(dist_ptr), ptr(ids_ptr),
                                               ptr(stream)))

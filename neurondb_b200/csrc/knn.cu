@@ -3,6 +3,7 @@
 #include "layout.cuh"
 #include "scan.cuh"
 #include "tc.cuh"
+#include <vector>
 
 namespace ndb {
 
@@ -201,8 +202,9 @@ int ndb_b200_knn_exact_dev(ndb_b200_dataset *ds, int metric, int arith, const fl
     NDB_REQUIRE(ds && Q_dev && dist_dev && ids_dev && nq > 0, NDB_B200_EINVAL, "knn_exact: NULL or empty input");
     NDB_REQUIRE(k >= 1 && k <= 128, NDB_B200_EINVAL, "knn_exact: k=%d out of range 1..128", k);
     NDB_REQUIRE(metric >= NDB_L2 && metric <= NDB_IP, NDB_B200_EINVAL, "knn_exact: unknown metric %d", metric);
-    NDB_REQUIRE(arith == NDB_ARITH_OP_F64 || arith == NDB_ARITH_IVF_F32 || arith == NDB_ARITH_FAST || arith == NDB_ARITH_TENSOR,
-                NDB_B200_EINVAL, "knn_exact: arith %d not available for the scan", arith);
+    NDB_REQUIRE(arith == NDB_ARITH_OP_F64 || arith == NDB_ARITH_IVF_F32 || arith == NDB_ARITH_FAST || arith == NDB_ARITH_TENSOR ||
+                    (arith == NDB_ARITH_HNSW && metric == NDB_L2),
+                NDB_B200_EINVAL, "knn_exact: arith %d not available for the scan (metric %d)", arith, metric);
     cudaStream_t s = stream ? (cudaStream_t) stream : ctx().stream;
     if (arith == NDB_ARITH_TENSOR) {
         // bf16 tcgen05 GEMM-form path (tolerance 1e-3): ||x||^2 - 2 x.q + ||q||^2 with fused top-k
@@ -237,6 +239,72 @@ int ndb_b200_knn_exact(ndb_b200_dataset *ds, int metric, int arith, const float 
     NDB_CUDA(cudaStreamSynchronize(s));
     const int64_t bad = validate_end();
     NDB_REQUIRE(bad < 0, NDB_B200_EVECTOR, "vector contains NaN or Infinity at index %lld", (long long) (bad % ds->dim));
+    return NDB_B200_OK;
+}
+
+// ---- knn_classify / knn_regress (src/ml/ml_knn.c:112-357, 363-569) ---------------------------------------------
+// The SQL functions read (feature, label) rows of a table, compute euclidean_distance (:76-90: f32 difference, f64
+// sum, sqrt) of every row to the query, qsort by distance and vote among / average the k nearest.  Here the rows are a
+// resident dataset, the distances and the top-k are the scan kernel's (NDB_ARITH_HNSW is that same arithmetic), and
+// only the vote over k labels is left to the host.  labels[i] belongs to the i-th appended row.
+static int knn_neighbours(ndb_b200_dataset *ds, const float *Q, int nq, int k, const char *who, std::vector<uint32_t> &slots)
+{
+    using namespace ndb;
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(ds && Q && nq > 0, NDB_B200_EINVAL, "%s: NULL or empty input", who);
+    NDB_REQUIRE(k >= 1, NDB_B200_EINVAL, "neurondb: %s: k must be at least 1, got %d", who, k);              // :149-154
+    NDB_REQUIRE(k <= 128, NDB_B200_EINVAL, "%s: k=%d out of range 1..128", who, k);
+    NDB_REQUIRE(ds->n >= k, NDB_B200_ERANGE, "neurondb: %s: need at least %d samples, got %lld", who, k, (long long) ds->n);  // :190-205
+    cudaStream_t s = ctx().stream;
+    const size_t qb = (size_t) nq * ds->dim * sizeof(float), m = (size_t) nq * k;
+    NDB_CHECK(ds->qbuf.reserve(qb));
+    NDB_CHECK(ds->outd.reserve(m * sizeof(float)));
+    NDB_CHECK(ds->outi.reserve(m * sizeof(int64_t)));
+    DevBuf dslots;
+    NDB_CHECK(dslots.reserve(m * sizeof(uint32_t)));
+    NDB_CUDA(cudaMemcpyAsync(ds->qbuf.p, Q, qb, cudaMemcpyHostToDevice, s));
+    NDB_CHECK(validate_begin(ds->qbuf.as<float>(), (int64_t) nq * ds->dim, s));
+    int nparts = 1;
+    NDB_CHECK(dense_scan(ds->store.ptr(), nullptr, ds->n, ds->dim, ds->dimp, NDB_L2, NDB_ARITH_HNSW, ds->qbuf.as<float>(), nq, k,
+                         ds->scratch, &nparts, s));
+    NDB_CHECK(launch_merge_parts(ds->scratch.pdist.as<float>(), ds->scratch.pslot.as<uint32_t>(), ds->ids.as<int64_t>(), nq, nparts, k,
+                                 ds->outd.as<float>(), ds->outi.as<int64_t>(), dslots.as<uint32_t>(), s));
+    slots.resize(m);
+    NDB_CUDA(cudaMemcpyAsync(slots.data(), dslots.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    const int64_t bad = validate_end();
+    NDB_REQUIRE(bad < 0, NDB_B200_EVECTOR, "vector contains NaN or Infinity at index %lld", (long long) (bad % ds->dim));   // NDB_CHECK_VECTOR_VALID
+    return NDB_B200_OK;
+}
+
+int ndb_b200_knn_classify(ndb_b200_dataset *ds, const double *labels, const float *Q, int nq, int k, int *out_class)
+{
+    using namespace ndb;
+    NDB_REQUIRE(labels && out_class, NDB_B200_EINVAL, "knn_classify: NULL labels or output");
+    std::vector<uint32_t> slots;
+    NDB_CHECK(knn_neighbours(ds, Q, nq, k, "knn_classify", slots));
+    for (int q = 0; q < nq; q++) {
+        double votes[2] = {0.0, 0.0};                               // :326-333: binary vote, other labels are ignored
+        for (int i = 0; i < k; i++) {
+            const int c = (int) labels[slots[(size_t) q * k + i]];
+            if (c >= 0 && c < 2) votes[c] += 1.0;
+        }
+        out_class[q] = votes[1] > votes[0] ? 1 : 0;
+    }
+    return NDB_B200_OK;
+}
+
+int ndb_b200_knn_regress(ndb_b200_dataset *ds, const double *targets, const float *Q, int nq, int k, double *out)
+{
+    using namespace ndb;
+    NDB_REQUIRE(targets && out, NDB_B200_EINVAL, "knn_regress: NULL targets or output");
+    std::vector<uint32_t> slots;
+    NDB_CHECK(knn_neighbours(ds, Q, nq, k, "knn_regress", slots));
+    for (int q = 0; q < nq; q++) {
+        double prediction = 0.0;                                    // :555-557: sum in neighbour order, divided by k
+        for (int i = 0; i < k; i++) prediction += targets[slots[(size_t) q * k + i]];
+        out[q] = prediction / k;
+    }
     return NDB_B200_OK;
 }
 

@@ -134,6 +134,7 @@ int launch_scan(int metric, int arith, int tile, const ScanParams &prm, uint32_t
     NDB_SCAN_CASE(NDB_L2, NDB_ARITH_OP_F64)
     NDB_SCAN_CASE(NDB_COSINE, NDB_ARITH_OP_F64)
     NDB_SCAN_CASE(NDB_IP, NDB_ARITH_OP_F64)
+    NDB_SCAN_CASE(NDB_L2, NDB_ARITH_HNSW)          // f32 difference, f64 sum: also ml_knn.c's euclidean_distance
     NDB_SCAN_CASE(NDB_L2, NDB_ARITH_FAST)
     NDB_SCAN_CASE(METRIC_L2SQ, NDB_ARITH_FAST)
     NDB_SCAN_CASE(NDB_COSINE, NDB_ARITH_FAST)
