@@ -4,7 +4,11 @@
 // |rel err| <= 1e-3, north_star).
 //
 //   ||x - q||^2 = ||x||^2 - 2 x.q + ||q||^2            (L2; ranked squared, sqrt on output)
-//   -x.q                                                (inner product, HNSW sign convention)
+//   -x.q                                                (inner product, HNSW sign convention; the query tiles hold -q,
+//                                                        so the accumulator is the candidate itself)
+// The same kernel scans the IVF lists of a query batch (list mode, packed keys: csrc/ivf.cu) and the centroid store
+// (coarse quantiser, list assignment, k-means assignment: csrc/kmeans.cu); there its candidates are only PROPOSALS that a
+// certified fp32 re-evaluation turns into the reference's exact answer (ivf_cert.cuh, cert_common.cuh).
 //
 // Layout.  Stored rows and queries are kept as bf16 in the UMMA *canonical K-major no-swizzle*
 // layout, blocked so that every operand tile is one contiguous run of bytes:
@@ -16,17 +20,19 @@
 // consumable by tcgen05.mma through a shared-memory matrix descriptor.
 //
 // Kernel (persistent, 384 threads):
-//   warp 0    TMA producer: Q tile once per work item, then X (tile, chunk) stages into a 2-deep ring
-//   warp 1    MMA issuer: one elected thread issues 8 x tcgen05.mma.kind::f16 (M=128, N=256, K=16) per
+//   warp 0    TMA producer: Q tile once per work item (double-buffered), then X (tile, chunk) stages into a ring of
+//             2-5 stages (144 KB; only the K groups that carry data are copied: 48 KB stages at dim 96)
+//   warp 1    MMA issuer: one elected thread issues up to 8 x tcgen05.mma.kind::f16 (M=128, N=256, K=16) per
 //             stage into one of two 256-column TMEM accumulators; tcgen05.commit frees the smem
 //             stage and, after the last chunk, publishes the accumulator
 //   warp 2    TMEM allocator (512 columns)
 //   warps 4-11 epilogue: thread = (query = TMEM lane, half of the 256 columns); tcgen05.ld 32 columns
-//             at a time; candidates fma(-2, dot, ||x||^2) are min-reduced and compared against the
-//             thread's k-th best once per 32; the top-k is a thread-local sorted list -- no
-//             cross-lane traffic at all
+//             at a time; candidates (L2: fma(-2, dot, ||x||^2); inner product: the accumulator) are min-reduced
+//             with 3-input minima and compared against the thread's k-th best once per 32 (inner product: per 64);
+//             the top-k is a thread-local sorted list -- no cross-lane traffic at all.  The work items of a query
+//             share an upper bound of its k-th best through a global float (p.gthr), in list and in dense mode.
 // Work item = (query tile, range of X tiles); per-item top-k lists are merged by (dist, id) by
-// merge_parts_kernel (scan.cuh).
+// merge_parts_kernel (scan.cuh) or, in list mode, by the certified finish.
 #include "layout.cuh"
 #include "scan.cuh"
 #include "tc.cuh"
