@@ -67,7 +67,8 @@ extern "C" {
                                  (hnsw_am.c:1301-1345)                                        */
 #define NDB_ARITH_FAST     5  /* fp32 FFMA, several accumulators: <= 1e-5 relative          */
 #define NDB_ARITH_TENSOR   6  /* bf16 tcgen05 tiles, fp32 accumulate; all three metrics, dim <= 2048,
-                                 k <= 16, anything else -> NDB_B200_EINVAL (no fallback).
+                                 k <= 16 (ndb_b200_knn_exact) / k <= 32 (ndb_b200_ivf_search), anything else
+                                 -> NDB_B200_EINVAL (no fallback).
                                  ndb_b200_knn_exact: distances <= 1e-3 relative.
                                  ndb_b200_ivf_search: the tensor cores only PROPOSE candidates (coarse
                                  quantiser and list scans); they are re-evaluated with NDB_ARITH_IVF_F32

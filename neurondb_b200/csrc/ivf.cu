@@ -662,7 +662,7 @@ static int ivf_tc_margin()
 static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int np, int k, float *dist_dev, int64_t *ids_dev,
                              cudaStream_t s)
 {
-    NDB_REQUIRE(k <= TC_KMAX, NDB_B200_EINVAL, "ivf tensor path: k=%d > %d", k, TC_KMAX);
+    NDB_REQUIRE(k <= TC_IVF_KMAX, NDB_B200_EINVAL, "ivf tensor path: k=%d > %d", k, TC_IVF_KMAX);
     NDB_REQUIRE(ix->dim <= TC_MAX_DIM, NDB_B200_EINVAL, "ivf tensor path: dim %d > %d", ix->dim, TC_MAX_DIM);
     NDB_CHECK(ivf_tensor_ready(ix, s));
     const int L = ix->nlists;
@@ -708,7 +708,9 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     const int phases_env = phases_e ? atoi(phases_e) : 0;
     // (expected evaluations of the batch on this rank: below ~1e9 the scan is too short to repay two more launches and
     // the thinly filled query tiles of phase 1 -- C2, 0.35e9: 0.56 ms in two phases, 0.48 ms in one)
-    const bool two_phase = np > 1 && (phases_env == 2 || (phases_env != 1 && ix->tc_rows_per_pair * (double) npairs >= 1.0e9));
+    // (k > 16: a 16-entry partial list cannot bound the k-th best by itself, so only the bound kernel of the two-phase
+    // scan gives such a search a shared bound at all)
+    const bool two_phase = np > 1 && (phases_env == 2 || (phases_env != 1 && (k > TC_KMAX || ix->tc_rows_per_pair * (double) npairs >= 1.0e9)));
     const uint32_t split = two_phase ? (uint32_t) L : 0u;
     const int NV = two_phase ? 2 * L : L;                   // virtual lists
     NDB_CHECK(ix->cnt.reserve((size_t) NV * 4 * 2));
@@ -816,7 +818,7 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     p.nprobe = (uint32_t) np;
     p.gthr = getenv("NDB_IVF_TC_NOSHARE") ? nullptr : ix->tcs.gthr.as<float>();
     p.packed = getenv("NDB_IVF_TC_UNPACKED") ? 0 : 1;
-    p.kpub = getenv("NDB_IVF_TC_KPUB_LAST") ? 0 : k;
+    p.kpub = k > kc ? -1 : (getenv("NDB_IVF_TC_KPUB_LAST") ? 0 : k);
     p.debug_mode = getenv("NDB_TC_DEBUG") ? atoi(getenv("NDB_TC_DEBUG")) : 0;
     unsigned long long *ctr = ix->cert_counters.as<unsigned long long>();
     if (two_phase) {
@@ -866,7 +868,9 @@ static int ivf_search_tensor(ndb_b200_ivf *ix, const float *Q_dev, int nq, int n
     }
 #define NDB_FIN(M)                                                                                                   \
     do {                                                                                                             \
-        ivf_tc_finish_cert_kernel<Arith<M, NDB_ARITH_IVF_F32>, M><<<mgrid, 128, 0, s>>>(                              \
+        auto fin = k <= TC_KMAX ? ivf_tc_finish_cert_kernel<Arith<M, NDB_ARITH_IVF_F32>, M, 1>                        \
+                                : ivf_tc_finish_cert_kernel<Arith<M, NDB_ARITH_IVF_F32>, M, 2>;                       \
+        fin<<<mgrid, 128, 0, s>>>(                                                                                    \
             ix->tcs.pdist.as<float>(), ix->tcs.pslot.as<uint32_t>(), ix->tc_src.as<uint32_t>(), ix->tc_row.as<uint32_t>(), \
             ix->arena.as<float>(), ix->ids.as<int64_t>(), Q_dev, ix->probe.as<uint32_t>(),                            \
             ix->pairpos.as<uint32_t>(), ix->item_off.as<uint32_t>(), ix->d_list_len.as<uint32_t>(), p.gthr, cnt, rep_max, split, \

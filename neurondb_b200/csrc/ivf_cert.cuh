@@ -34,7 +34,8 @@ namespace ndb {
 // gthr[q] = R, the RELAXED shared bound (cert_bound.cuh): every candidate the threshold test dropped had a key
 // >= R; a full partial list also dropped candidates above its own kc-th key.  Hence every row that is in no
 // partial list has a key >= min(R, smallest kc-th key of a full list) =: g_lists.
-template <class P, int METRIC>
+// KRC: candidates re-evaluated per query / 32 (1 for k <= 16; 2 for k <= 32).
+template <class P, int METRIC, int KRC>
 __global__ void __launch_bounds__(128) ivf_tc_finish_cert_kernel(
     const float *__restrict__ pdist, const uint32_t *__restrict__ pslot, const uint32_t *__restrict__ tc_src,
     const uint32_t *__restrict__ tc_row, const float *__restrict__ arena, const int64_t *__restrict__ ids,
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_cert_kernel(
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (q >= nq) return;
-    WarpTopK<1, uint32_t> cand;
+    WarpTopK<KRC, uint32_t> cand;
     cand.init();
     const float R = gthr[q];
     const bool bounded = R < 1.0e38f;                  // "no bound": no partial list of this query ever filled
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_cert_kernel(
                     const bool ok = slv[u] != INVALID_SLOT;
                     if (ok && eidx[u] % kc == kc - 1) own_min = fminf(own_min, cdv[u]);      // last entry of a full list
                     const unsigned m = __ballot_sync(FULL, ok);
-                    if (m) { n_in += __popc(m); cand.offer(cdv[u], slv[u], ok, lane, 32); }
+                    if (m) { n_in += __popc(m); cand.offer(cdv[u], slv[u], ok, lane, 32 * KRC); }
                 }
             }
         }
@@ -109,13 +110,14 @@ __global__ void __launch_bounds__(128) ivf_tc_finish_cert_kernel(
     for (int o = 16; o > 0; o >>= 1) own_min = fminf(own_min, __shfl_xor_sync(FULL, own_min, o));
     const float *qv = Q + (size_t) q * dim;
     const CertQ cq = cert_query(qv, dim, lane);
-    // lane e holds candidate e (ascending key).  Rows outside the 32: in a partial list -> key >= the 32nd key;
-    // in none -> key >= min(R, own_min).  With no full list, no bound and no overflow the 32 are everything.
-    const float key32 = __shfl_sync(FULL, cand.d[0], 31);
-    const float g_rest = fminf(n_in > 32 ? key32 : INFINITY, fminf(R, own_min));
-    const bool complete = !bounded && own_min == INFINITY && n_in <= 32;
+    // register r, lane e holds candidate 32 r + e (ascending key).  Rows outside the 32 KRC: in a partial list -> key >= the
+    // last candidate's key; in none -> key >= min(R, own_min).  With no full list, no bound and no overflow the candidates
+    // are everything.
+    const float keylast = __shfl_sync(FULL, cand.d[KRC - 1], 31);
+    const float g_rest = fminf(n_in > 32 * KRC ? keylast : INFINITY, fminf(R, own_min));
+    const bool complete = !bounded && own_min == INFINITY && n_in <= 32 * KRC;
     WarpTopK<1, int64_t> top;
-    const bool ok = cert_rerank<P, METRIC, 1>(qv, arena, dim, cand, g_rest, complete, stats, cq, k, lane,
+    const bool ok = cert_rerank<P, METRIC, KRC>(qv, arena, dim, cand, g_rest, complete, stats, cq, k, lane,
                                               [&](uint32_t ts) { return tc_row[ts]; }, [&](uint32_t ts) { return ids[tc_src[ts]]; }, top,
                                               counters ? counters + 1 : nullptr);
     if (!ok) {

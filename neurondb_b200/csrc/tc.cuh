@@ -10,7 +10,9 @@ constexpr int TC_N = 256;          // stored rows per tile (TMEM columns per acc
 constexpr int TC_KC = 128;         // dims per K-chunk (one smem stage)
 constexpr int TC_MAX_CHUNKS = 2;   // K-chunks of a query tile that stay resident in shared memory (dim <= 256)
 constexpr int TC_MAX_DIM = 2048;   // beyond TC_MAX_CHUNKS chunks the query tile is streamed with the stored tiles
-constexpr int TC_KMAX = 16;        // k <= 16 (thread-local register list)
+constexpr int TC_KMAX = 16;        // entries of a thread-local register list (dense kNN: k <= 16)
+constexpr int TC_IVF_KMAX = 32;    // the certified IVF search proposes from 16-entry partial lists and re-evaluates up to 64
+                                   // candidates per query: k <= 32
 constexpr int TC_PACKED_MAX_TILES = 16;   // packed-key epilogue: 11 index bits = 16 tiles x 128 columns per half
 constexpr int TC_IDX_BITS = 11;           // low mantissa bits of a packed key that carry the candidate's index within its item
 constexpr uint32_t TC_IDX_MASK = (1u << TC_IDX_BITS) - 1;
@@ -66,7 +68,8 @@ struct TcParams {
     int packed;                    // 1: items span <= TC_PACKED_MAX_TILES tiles; (distance | index) keys, sorting-network epilogue
     float *debug_d;                // optional: raw accumulator of the first tile [128][256]
     unsigned long long *dbg_counters; // builds with -DNDB_TC_COUNTERS only: epilogue statistics (chunks, chunks with a taker, sorted chunks, insert rounds, takers)
-    int kpub;                      // list mode: the shared bound is published from the kpub-th key of a full list (0: the last, k-th)
+    int kpub;                      // list mode: the shared bound is published from the kpub-th key of a full list (0: the last,
+                                   // k-th; < 0: never -- k exceeds the list length, only ivf_tc_bound_kernel sets the bound)
     int debug_mode;                // NDB_TC_DEBUG: 1 = no epilogue, 2 = no MMA issue, 4 = no X bulk copies, 8 = epilogue reads TMEM only (bisection aid)
 };
 

@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(384, 1) tc_knn_kernel(const TcParams p)
                     default: break;
                 }
 #undef NDB_KTH
-                if (gcell && kth < published) {                         // own list full enough and improved
+                if (gcell && p.kpub >= 0 && kth < published) {          // own list full enough and improved
                     published = kth;
                     float pub = published;
                     if (PACKED)     // an upper bound of the value the key stands for

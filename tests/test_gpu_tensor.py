@@ -70,6 +70,9 @@ IVF_CASES = [
     (300, 64, 32, 50, 16, 10, 1),         # lists shorter than the candidate count: pad rows must never rank
     (40000, 96, 512, 600, 32, 10, 3),     # C4-shaped: inner product, nprobe = 32 on the tensor coarse stage
     (30000, 128, 128, 500, 16, 1, 1),     # k = 1
+    (60000, 64, 64, 300, 8, 24, 1),       # k > 16: 16-entry partial lists, 64 candidates re-evaluated per query
+    (25000, 96, 48, 200, 12, 32, 3),      # k = 32, inner product
+    (20000, 32, 32, 150, 6, 32, 2),       # k = 32, cosine
 ]
 
 
@@ -154,7 +157,7 @@ def test_tensor_ivf_rejects_what_it_cannot_do(ndb):
     ix2.ivfbuild(X)
     ix2.ivfinsert(X)
     with pytest.raises(ndb.NdbError):
-        ix2.search(X[:3], 2, 17, ndb.IVF_FULL, ndb.ARITH_TENSOR)      # k > 16
+        ix2.search(X[:3], 2, 33, ndb.IVF_FULL, ndb.ARITH_TENSOR)      # k > 32
     with pytest.raises(ndb.NdbError):
         ix2.search(X[:3], 2, 10, ndb.IVF_LITERAL, ndb.ARITH_TENSOR)   # literal mode
 
