@@ -161,6 +161,18 @@ int ndb_b200_knn_exact_dev(ndb_b200_dataset *ds, int metric, int arith, const fl
 int ndb_b200_knn_classify(ndb_b200_dataset *ds, const double *labels, const float *Q, int nq, int k, int *out_class);
 int ndb_b200_knn_regress(ndb_b200_dataset *ds, const double *targets, const float *Q, int nq, int k, double *out);
 
+/* cluster_kmeans (src/ml/ml_kmeans.c:146-303) over n rows of X (row-major, what neurondb_fetch_vectors_from_table
+ * returns): k-means++ seeding (kmeanspp_init :45-139: float difference and square, double sums, the D^2-weighted walk
+ * in row order) and Lloyd's iterations until no assignment changes or max_iters (< 1 -> 100, :175-176); assignment by
+ * neurondb_l2_distance_squared (util/neurondb_simd_impl.c:36-104, all double; strict <, lowest index wins), update =
+ * float sums in row order / count, empty clusters end at zero.  rand_draws = the k values rand() returns, in call
+ * order (the reference draws exactly k and nothing else in between: the caller draws them, the stream stays where the
+ * reference leaves it); rand_max = RAND_MAX.  labels[n] are 1-based as the SQL function returns them (:286);
+ * centers[k*dim], iters, seeds[k] (the rows kmeanspp_init picked) are optional.  k <= 1 or n < k -> EINVAL with the
+ * reference's messages; NaN / Inf in X -> EVECTOR. */
+int ndb_b200_cluster_kmeans(const float *X, int n, int dim, int k, int max_iters, const int *rand_draws, int rand_max,
+                            int *labels, float *centers, int *iters, int *seeds);
+
 /* ---- IVF k-means: kmeans_init/run/assign/update_centroids/compute_cost
  *      (src/index/ivf_am.c:2070-2294).  Literal semantics: centroids := first k rows,
  *      <= max_iter Lloyd steps, stop when |prevCost - cost| < tol, f32 sequential sums.

@@ -70,6 +70,7 @@ SIGNATURES = {
     "ndb_b200_knn_exact_dev": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p]),
     "ndb_b200_knn_classify": (_i, [_p, _p, _p, _i, _i, _p]),
     "ndb_b200_knn_regress": (_i, [_p, _p, _p, _i, _i, _p]),
+    "ndb_b200_cluster_kmeans": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
     "ndb_b200_kmeans_train": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p, C.POINTER(_i), C.POINTER(_f)]),
     "ndb_b200_ivf_create": (_i, [_i, _i, _i, C.POINTER(_p)]),
     "ndb_b200_ivf_free": (None, [_p]),

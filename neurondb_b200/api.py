@@ -140,6 +140,25 @@ def kmeans_train(X, k, max_iter=50, tol=0.001):
     return Cn, assign, counts, iters.value, cost.value
 
 
+def cluster_kmeans(X, k, max_iters, rand_draws, rand_max=2147483647):
+    """cluster_kmeans (ml_kmeans.c:146-303): returns (labels 1-based, centers, seeds, iterations).  rand_draws = the k
+    values rand() returned, in call order."""
+    X = f32(X)
+    if X.ndim != 2:
+        raise L.NdbError(-1, "cluster_kmeans: a 2-d array of rows expected")
+    n, d = X.shape
+    draws = np.ascontiguousarray(rand_draws, np.int32)
+    if draws.shape != (max(k, 0),):
+        raise L.NdbError(-1, "cluster_kmeans: one rand() value per cluster expected")
+    labels = np.zeros(n, np.int32)
+    Cn = np.zeros((max(k, 0), d), np.float32)
+    seeds = np.zeros(max(k, 0), np.int32)
+    iters = C.c_int()
+    check(L.load().ndb_b200_cluster_kmeans(ptr(X), n, d, k, max_iters, ptr(draws), rand_max, ptr(labels), ptr(Cn),
+                                           C.byref(iters), ptr(seeds)))
+    return labels, Cn, seeds, iters.value
+
+
 def merge_topk(dist, ids):
     dist = f32(dist)
     ids = np.ascontiguousarray(ids, np.int64)

@@ -1,0 +1,224 @@
+// cluster_kmeans.cu -- the SQL function cluster_kmeans (NeuronDB/src/ml/ml_kmeans.c:146-303) on the device:
+// k-means++ seeding (kmeanspp_init, :45-139) followed by Lloyd's iterations until no assignment changes.
+//
+// Literal semantics, reproduced bit for bit (oracle: orc_cluster_kmeans, pinned to the reference's own functions):
+//   seeding : D^2 weight of a row = sum_f64 of (float)((x-c)*(x-c)) with a FLOAT difference and a FLOAT square (:64-74,
+//             :126-134); the next seed is the first unselected row at which r = rand()/RAND_MAX * sum, reduced by the
+//             weights IN ROW ORDER, reaches <= 0 (:85-101).  Both the sum and the walk are sequential fp64 chains whose
+//             rounding decides the row, so they stay sequential here: one thread walks tiles the block stages in
+//             shared memory.  The weights themselves (n*dim work per seed) are one thread per row.
+//   assign  : argmin_c neurondb_l2_distance_squared (util/neurondb_simd_impl.c:36-104, the build without AVX2: double
+//             difference, double square, double sum), strict <, lowest index wins (:236-259)
+//   update  : float sums over the members in row order / count, empty clusters end at zero (:261-281) -- this is
+//             kmeans_update_dev of the IVF trainer, which has the same semantics
+// The caller supplies the k values rand() returned (the function draws exactly k, nothing else in between), so the
+// process's rand() stream stays where the reference leaves it.
+//
+// Layout: the rows live twice on the device, row-major (update: threads along the dimensions of one member) and
+// transposed [dim][n] (weights and assignment: threads along the rows, every load coalesced, each thread walking the
+// dimensions of its row in order).  Roofline of the assignment: 3 rounded fp64 instructions per (row, cluster,
+// dimension) -- fp64-issue bound like the operator scan (C1), not HBM bound (the transposed rows are re-read from L1/L2).
+#include <cfloat>
+
+#include "kmeans.cuh"
+
+namespace ndb {
+
+__global__ void __launch_bounds__(256) ckm_transpose_kernel(const float *__restrict__ X, int64_t n, int dim, float *__restrict__ XT)
+{
+    __shared__ float tile[32][33];
+    const int64_t r0 = (int64_t) blockIdx.x * 32;
+    const int d0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int64_t r = r0 + j;
+        const int d = d0 + threadIdx.x;
+        if (r < n && d < dim) tile[j][threadIdx.x] = X[(size_t) r * dim + d];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int d = d0 + j;
+        const int64_t r = r0 + threadIdx.x;
+        if (r < n && d < dim) XT[(size_t) d * n + r] = tile[threadIdx.x][j];
+    }
+}
+
+// D^2 weight against seed c (already in seeds[c]): dist[i] = acc for the first seed, min(dist[i], acc) afterwards
+__global__ void __launch_bounds__(256) ckm_weight_kernel(const float *__restrict__ XT, const float *__restrict__ X, int64_t n, int dim,
+                                                         const int *__restrict__ seeds, int c, double *__restrict__ dist)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *crow = X + (size_t) seeds[c] * dim;
+    double acc = 0.0;
+    for (int d = 0; d < dim; d++) {
+        const float diff = __fsub_rn(XT[(size_t) d * n + i], __ldg(crow + d));
+        acc = __dadd_rn(acc, (double) __fmul_rn(diff, diff));
+    }
+    if (c == 0 || acc < dist[i]) dist[i] = acc;
+}
+
+// seed c: c == 0 -> draws[0] % n (:59); otherwise the D^2-weighted draw (:78-119).  One block.
+constexpr int CKM_TILE = 4096;
+__global__ void __launch_bounds__(1024) ckm_pick_kernel(const double *__restrict__ dist, unsigned char *__restrict__ selected, int64_t n,
+                                                         const int *__restrict__ draws, double rand_max, int c, int *__restrict__ seeds)
+{
+    __shared__ double buf[CKM_TILE];
+    __shared__ unsigned char sel[CKM_TILE];
+    __shared__ long long s_picked;
+    __shared__ unsigned long long s_first;
+    if (c == 0) {
+        if (threadIdx.x == 0) {
+            const int first = draws[0] % (int) n;
+            seeds[0] = first;
+            selected[first] = 1;
+        }
+        return;
+    }
+    // sum of the unselected weights in row order (adding 0.0 for a selected row leaves a non-negative sum unchanged)
+    double sum = 0.0;
+    for (int64_t base = 0; base < n; base += CKM_TILE) {
+        const int m = (int) (n - base < CKM_TILE ? n - base : CKM_TILE);
+        for (int t = threadIdx.x; t < m; t += blockDim.x) buf[t] = selected[base + t] ? 0.0 : dist[base + t];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+#pragma unroll 8
+            for (int t = 0; t < m; t++) sum = __dadd_rn(sum, buf[t]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { s_picked = -1; s_first = ~0ull; }
+    double r = __dmul_rn(__ddiv_rn((double) draws[c], rand_max), sum);
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += CKM_TILE) {
+        const int m = (int) (n - base < CKM_TILE ? n - base : CKM_TILE);
+        for (int t = threadIdx.x; t < m; t += blockDim.x) { buf[t] = dist[base + t]; sel[t] = selected[base + t]; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int t = 0; t < m; t++) {
+                if (sel[t]) continue;
+                r = __dsub_rn(r, buf[t]);
+                if (r <= 0) { s_picked = base + t; break; }
+            }
+        }
+        __syncthreads();
+        if (s_picked >= 0) break;
+    }
+    if (s_picked < 0) {                                   // rounding left r > 0 after the last row: first unselected row (:103-113)
+        unsigned long long mine = ~0ull;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
+            if (!selected[i]) { mine = (unsigned long long) i; break; }
+        atomicMin(&s_first, mine);
+        __syncthreads();
+        if (threadIdx.x == 0) s_picked = (long long) s_first;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        seeds[c] = (int) s_picked;
+        selected[s_picked] = 1;
+    }
+}
+
+__global__ void ckm_gather_centers_kernel(const float *__restrict__ X, const int *__restrict__ seeds, int dim, float *__restrict__ C)
+{
+    const int c = blockIdx.x;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) C[(size_t) c * dim + d] = X[(size_t) seeds[c] * dim + d];
+}
+
+// nearest center of each row in fp64, CPT centers per pass over the row (independent chains hide the fp64 latency,
+// the row element is converted once for all of them)
+template <int CPT>
+__global__ void __launch_bounds__(128) ckm_assign_kernel(const float *__restrict__ XT, const float *__restrict__ C, int64_t n, int dim, int k,
+                                                         int *__restrict__ assign, int *__restrict__ changed)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t il = i < n ? i : n - 1;
+    int best = -1;
+    double min_dist = DBL_MAX;
+    for (int c0 = 0; c0 < k; c0 += CPT) {
+        double acc[CPT];
+        const float *crow[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            acc[j] = 0.0;
+            crow[j] = C + (size_t) (c0 + j < k ? c0 + j : k - 1) * dim;
+        }
+        for (int d = 0; d < dim; d++) {
+            const double x = (double) XT[(size_t) d * n + il];
+#pragma unroll
+            for (int j = 0; j < CPT; j++) {
+                const double diff = __dsub_rn(x, (double) __ldg(crow[j] + d));
+                acc[j] = __dadd_rn(acc[j], __dmul_rn(diff, diff));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CPT; j++)
+            if (c0 + j < k && acc[j] < min_dist) { min_dist = acc[j]; best = c0 + j; }
+    }
+    if (i < n && assign[i] != best) {
+        assign[i] = best;
+        *changed = 1;
+    }
+}
+
+}  // namespace ndb
+
+using namespace ndb;
+
+extern "C" {
+
+int ndb_b200_cluster_kmeans(const float *X, int n, int dim, int k, int max_iters, const int *rand_draws, int rand_max,
+                            int *labels, float *centers, int *iters, int *seeds)
+{
+    NDB_CHECK(require_init());
+    NDB_REQUIRE(X && labels && rand_draws && n > 0 && dim > 0 && rand_max > 0, NDB_B200_EINVAL, "cluster_kmeans: bad argument");
+    NDB_REQUIRE(k > 1, NDB_B200_EINVAL, "number of clusters must be at least 2");                                        // :170-174
+    NDB_REQUIRE(n >= k, NDB_B200_EINVAL, "not enough vectors for cluster count (need >= %d, have %d)", k, n);           // :180-186
+    for (int c = 0; c < k; c++) NDB_REQUIRE(rand_draws[c] >= 0, NDB_B200_EINVAL, "cluster_kmeans: rand() values are non-negative");
+    if (max_iters < 1) max_iters = 100;                                                                                 // :175-176
+    NDB_REQUIRE(find_nonfinite(X, (int64_t) n * dim) < 0, NDB_B200_EVECTOR, "cluster_kmeans: NaN/Inf in the vectors");
+    cudaStream_t s = ctx().stream;
+    KMeansWork w;
+    DevBuf XT, dist, selected, dseeds, ddraws, dchanged;
+    const size_t xb = (size_t) n * dim * 4, cb = (size_t) k * dim * 4;
+    NDB_CHECK(w.X.reserve(xb)); NDB_CHECK(XT.reserve(xb)); NDB_CHECK(w.C.reserve(cb));
+    NDB_CHECK(w.assign.reserve((size_t) n * 4)); NDB_CHECK(w.counts.reserve((size_t) k * 4));
+    NDB_CHECK(dist.reserve((size_t) n * 8)); NDB_CHECK(selected.reserve((size_t) n));
+    NDB_CHECK(dseeds.reserve((size_t) k * 4)); NDB_CHECK(ddraws.reserve((size_t) k * 4)); NDB_CHECK(dchanged.reserve(4));
+    NDB_CUDA(cudaMemcpyAsync(w.X.p, X, xb, cudaMemcpyHostToDevice, s));
+    NDB_CUDA(cudaMemcpyAsync(ddraws.p, rand_draws, (size_t) k * 4, cudaMemcpyHostToDevice, s));
+    NDB_CUDA(cudaMemsetAsync(selected.p, 0, (size_t) n, s));
+    const float *dX = w.X.as<float>();
+    ckm_transpose_kernel<<<dim3((unsigned) ((n + 31) / 32), (unsigned) ((dim + 31) / 32)), dim3(32, 8), 0, s>>>(dX, n, dim, XT.as<float>());
+    count_launch();
+    const unsigned rb = (unsigned) ((n + 255) / 256);
+    for (int c = 0; c < k; c++) {
+        ckm_pick_kernel<<<1, 1024, 0, s>>>(dist.as<double>(), selected.as<unsigned char>(), n, ddraws.as<int>(), (double) rand_max, c,
+                                          dseeds.as<int>());
+        if (c + 1 < k)            // the weights against the last seed are never read (:121-135 computes them all the same)
+            ckm_weight_kernel<<<rb, 256, 0, s>>>(XT.as<float>(), dX, n, dim, dseeds.as<int>(), c, dist.as<double>());
+        count_launch(2);
+    }
+    ckm_gather_centers_kernel<<<k, 128, 0, s>>>(dX, dseeds.as<int>(), dim, w.C.as<float>());
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    NDB_CUDA(cudaMemsetAsync(w.assign.p, 0xff, (size_t) n * 4, s));                                                    // assignments[i] = -1 (:206-207)
+    int changed = 1, iter = 0;
+    for (iter = 0; iter < max_iters && changed; iter++) {
+        NDB_CUDA(cudaMemsetAsync(dchanged.p, 0, 4, s));
+        ckm_assign_kernel<4><<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(XT.as<float>(), w.C.as<float>(), n, dim, k, w.assign.as<int>(),
+                                                                          dchanged.as<int>());
+        count_launch();
+        NDB_CUDA(cudaMemcpyAsync(&changed, dchanged.p, 4, cudaMemcpyDeviceToHost, s));
+        NDB_CHECK(kmeans_update_dev(w, dX, w.assign.as<int>(), n, dim, k, w.C.as<float>(), w.counts.as<int>(), s));
+        NDB_CUDA(cudaStreamSynchronize(s));
+    }
+    NDB_CUDA(cudaMemcpyAsync(labels, w.assign.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
+    if (centers) NDB_CUDA(cudaMemcpyAsync(centers, w.C.p, cb, cudaMemcpyDeviceToHost, s));
+    if (seeds) NDB_CUDA(cudaMemcpyAsync(seeds, dseeds.p, (size_t) k * 4, cudaMemcpyDeviceToHost, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; i++) labels[i] += 1;                                                                        // 1-based labels (:286)
+    if (iters) *iters = iter;
+    return NDB_B200_OK;
+}
+
+}  // extern "C"

@@ -21,6 +21,9 @@
  *     compiled with the reference's flags (oracle/_ref/libndb_ref_leafs.so), and
  *     against tests/golden/index_leafs.npz generated from it.
  *   - key extraction (orc_fp16_to_float): PINNED the same way (libndb_ref_fp16.so).
+ *   - knn_classify / knn_regress / cluster_kmeans (ndb_oracle_ml.c): PINNED against the reference's own
+ *     euclidean_distance, compare_samples, kmeanspp_init, neurondb_l2_distance_squared and the text of
+ *     cluster_kmeans' Lloyd loop (libndb_ref_leafs.so; golden tests/golden/ml_paths.npz).
  *   - the control flow around them (ivfSelectClusters, ivfCollectCandidates, the
  *     ivfinsert assignment loop, hnswSearch, hnswInsertNode): welded to the buffer
  *     manager, no results asserted by the reference's tests -- "parity unpinned";
@@ -147,6 +150,15 @@ void orc_keys_from_halfvec(const uint16_t *h, int64_t n, int dim, float *rows);
 void orc_keys_from_bits(const uint8_t *bits, int64_t n, int nbits, float *rows);
 void orc_keys_from_sparse(const int64_t *indptr, const int32_t *indices, const float *values,
                           int64_t n, int total_dim, float *rows);
+
+/* ---- SQL functions on the same kernels (ndb_oracle_ml.c; ml_knn.c, ml_kmeans.c) ---- */
+double orc_ml_euclidean(const float *a, const float *b, int dim);            /* ml_knn.c:76-90 */
+void orc_knn_ml(const float *X, const double *labels, int n, int dim, const float *q, int k, int *cls, double *mean,
+                int *rows_out);                                               /* ml_knn.c:264-333, 504-557 */
+double orc_l2_distance_squared(const float *a, const float *b, int n);       /* neurondb_simd_impl.c:36-104 */
+int orc_kmeanspp_init(const float *X, int nvec, int dim, int k, const int *draws, int rand_max, int *centroids);
+int orc_cluster_kmeans(const float *X, int nvec, int dim, int k, int max_iters, const int *draws, int rand_max,
+                       int *labels, float *centers_out, int *seeds_out);     /* ml_kmeans.c:45-139, 146-303 */
 
 /* sizes / field offsets used by the relation encoders (ndb_oracle_pages.c), in the order of the
  * reference-side ref_layout() built by oracle/extract_ref_leafs.py; returns the count */

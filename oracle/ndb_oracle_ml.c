@@ -1,0 +1,169 @@
+/*
+ * ndb_oracle_ml.c -- CPU oracle for the SQL functions that sit on the same kernels as the index path
+ * (SURVEY.md 8f-3): knn_classify / knn_regress and cluster_kmeans.
+ *
+ * TEST INFRASTRUCTURE ONLY (see ndb_oracle.h).  Restated over in-memory arrays from
+ *   NeuronDB/src/ml/ml_knn.c:63-90 (compare_samples, euclidean_distance), :264-333 (classify), :504-557 (regress)
+ *   NeuronDB/src/ml/ml_kmeans.c:45-139 (kmeanspp_init), :146-303 (cluster_kmeans)
+ *   NeuronDB/src/util/neurondb_simd_impl.c:36-104 (neurondb_l2_distance_squared, the build without -mavx2)
+ *
+ * Pinning: PINNED against the reference's own euclidean_distance / compare_samples / kmeanspp_init /
+ * neurondb_l2_distance_squared and the Lloyd loop of cluster_kmeans, cut out of those files by
+ * oracle/extract_ref_leafs.py (tests/test_oracle.py, golden tests/golden/ml_paths.npz).
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ndb_oracle.h"
+
+/* ml_knn.c:76-90: the difference is a float operation, its square and the sum are double */
+double orc_ml_euclidean(const float *a, const float *b, int dim)
+{
+    double sum = 0.0;
+    for (int i = 0; i < dim; i++) {
+        double diff = a[i] - b[i];
+        sum += diff * diff;
+    }
+    return sqrt(sum);
+}
+
+typedef struct { double distance; double label; int row; } OrcKnnSample;
+
+/* ml_knn.c:63-74 orders by distance alone; equal distances keep row order here (what glibc's merge-sorting qsort
+ * does for the reference; the C standard leaves it open, so the tests stay away from ties at the k-th place) */
+static int orc_knn_cmp(const void *a, const void *b)
+{
+    const OrcKnnSample *x = (const OrcKnnSample *) a, *y = (const OrcKnnSample *) b;
+    if (x->distance < y->distance) return -1;
+    if (x->distance > y->distance) return 1;
+    return x->row < y->row ? -1 : (x->row > y->row);
+}
+
+/* one query: class (:326-333; labels outside {0,1} do not vote, class 1 needs a strict majority), mean of the k
+ * labels in sorted order (:555-557), and the k nearest rows */
+void orc_knn_ml(const float *X, const double *labels, int n, int dim, const float *q, int k, int *cls, double *mean,
+                int *rows_out)
+{
+    OrcKnnSample *s = (OrcKnnSample *) malloc(sizeof(OrcKnnSample) * (size_t) n);
+    double votes[2] = {0.0, 0.0}, prediction = 0.0;
+    for (int i = 0; i < n; i++) {
+        s[i].distance = orc_ml_euclidean(q, X + (size_t) i * dim, dim);
+        s[i].label = labels[i];
+        s[i].row = i;
+    }
+    qsort(s, (size_t) n, sizeof(OrcKnnSample), orc_knn_cmp);
+    for (int i = 0; i < k && i < n; i++) {
+        int c = (int) s[i].label;
+        if (c >= 0 && c < 2) votes[c] += 1.0;
+        prediction += s[i].label;
+        if (rows_out) rows_out[i] = s[i].row;
+    }
+    *cls = votes[1] > votes[0] ? 1 : 0;
+    *mean = prediction / k;
+    free(s);
+}
+
+/* neurondb_simd_impl.c:94-101 (scalar tail = the whole loop without AVX2/NEON): all double */
+double orc_l2_distance_squared(const float *a, const float *b, int n)
+{
+    double sum = 0.0;
+    for (int i = 0; i < n; i++) {
+        double diff = (double) a[i] - (double) b[i];
+        sum += diff * diff;
+    }
+    return sum;
+}
+
+/* ml_kmeans.c:45-139.  draws[c] = the c-th value rand() returned (the function calls it once per seed, nothing
+ * else in between); rand_max = RAND_MAX of that libc.  D^2 weights: float difference, FLOAT square, double sum. */
+int orc_kmeanspp_init(const float *X, int nvec, int dim, int k, const int *draws, int rand_max, int *centroids)
+{
+    unsigned char *selected = (unsigned char *) calloc((size_t) nvec, 1);
+    double *dist = (double *) calloc((size_t) nvec, sizeof(double));
+    centroids[0] = draws[0] % nvec;
+    selected[centroids[0]] = 1;
+    for (int i = 0; i < nvec; i++) {
+        double acc = 0.0;
+        for (int d = 0; d < dim; d++) {
+            float diff = X[(size_t) i * dim + d] - X[(size_t) centroids[0] * dim + d];
+            acc += diff * diff;
+        }
+        dist[i] = acc;
+    }
+    for (int c = 1; c < k; c++) {
+        int picked = -1;
+        double sum = 0.0, r;
+        for (int i = 0; i < nvec; i++)
+            if (!selected[i]) sum += dist[i];
+        r = ((double) draws[c] / (double) rand_max) * sum;
+        for (int i = 0; i < nvec; i++) {
+            if (selected[i]) continue;
+            r -= dist[i];
+            if (r <= 0) { picked = i; break; }
+        }
+        if (picked < 0)
+            for (int i = 0; i < nvec; i++)
+                if (!selected[i]) { picked = i; break; }
+        if (picked < 0) { free(dist); free(selected); return -1; }
+        centroids[c] = picked;
+        selected[picked] = 1;
+        for (int i = 0; i < nvec; i++) {
+            double acc = 0.0;
+            for (int d = 0; d < dim; d++)
+                acc += (X[(size_t) i * dim + d] - X[(size_t) picked * dim + d]) * (X[(size_t) i * dim + d] - X[(size_t) picked * dim + d]);
+            if (acc < dist[i]) dist[i] = acc;
+        }
+    }
+    free(dist);
+    free(selected);
+    return 0;
+}
+
+/* ml_kmeans.c:146-303: seeds -> Lloyd until no assignment changes or max_iters (< 1 -> 100); assignment in double
+ * (strict <, lowest index wins), update = float sums in row order / count, empty clusters end at zero.
+ * labels are 1-based (:286).  Returns the number of iterations run, < 0 on the argument errors (:170-186). */
+int orc_cluster_kmeans(const float *X, int nvec, int dim, int k, int max_iters, const int *draws, int rand_max,
+                       int *labels, float *centers_out, int *seeds_out)
+{
+    if (k <= 1) return -1;                 /* "number of clusters must be at least 2" */
+    if (max_iters < 1) max_iters = 100;
+    if (nvec < k) return -2;               /* "not enough vectors for cluster count" */
+    int *idx = (int *) malloc(sizeof(int) * (size_t) k);
+    int *assign = (int *) malloc(sizeof(int) * (size_t) nvec);
+    int *counts = (int *) malloc(sizeof(int) * (size_t) k);
+    float *centers = (float *) malloc(sizeof(float) * (size_t) k * dim);
+    if (orc_kmeanspp_init(X, nvec, dim, k, draws, rand_max, idx) != 0) return -3;
+    for (int c = 0; c < k; c++) memcpy(centers + (size_t) c * dim, X + (size_t) idx[c] * dim, sizeof(float) * (size_t) dim);
+    if (seeds_out) memcpy(seeds_out, idx, sizeof(int) * (size_t) k);
+    for (int i = 0; i < nvec; i++) assign[i] = -1;
+    int changed = 1, iter;
+    for (iter = 0; iter < max_iters && changed; iter++) {
+        changed = 0;
+        for (int i = 0; i < nvec; i++) {
+            int best = -1;
+            double min_dist = DBL_MAX;
+            for (int c = 0; c < k; c++) {
+                double dist = orc_l2_distance_squared(X + (size_t) i * dim, centers + (size_t) c * dim, dim);
+                if (dist < min_dist) { min_dist = dist; best = c; }
+            }
+            if (assign[i] != best) { assign[i] = best; changed = 1; }
+        }
+        memset(centers, 0, sizeof(float) * (size_t) k * dim);
+        memset(counts, 0, sizeof(int) * (size_t) k);
+        for (int i = 0; i < nvec; i++) {
+            int c = assign[i];
+            for (int d = 0; d < dim; d++) centers[(size_t) c * dim + d] += X[(size_t) i * dim + d];
+            counts[c]++;
+        }
+        for (int c = 0; c < k; c++)
+            if (counts[c] > 0)
+                for (int d = 0; d < dim; d++) centers[(size_t) c * dim + d] /= counts[c];
+    }
+    for (int i = 0; i < nvec; i++) labels[i] = assign[i] + 1;
+    if (centers_out) memcpy(centers_out, centers, sizeof(float) * (size_t) k * dim);
+    free(idx); free(assign); free(counts); free(centers);
+    return iter;
+}

@@ -95,8 +95,33 @@ def main():
     np.savez_compressed(os.path.join(HERE, "index_leafs.npz"), ivf_bits=np.concatenate(ivf).view(np.uint32),
                         hnsw_bits=np.concatenate(hn).view(np.uint32), km_C_bits=kC.view(np.uint32), km_assign=ka, km_counts=kc,
                         page_layout=O.ref_page_layout())
+    ml_paths()
     print("wrote", sorted(os.listdir(HERE)))
 
 
+def ml_paths():
+    """ml_paths.npz: cluster_kmeans and knn_classify / knn_regress outputs of the REFERENCE's own functions
+    (kmeanspp_init, the Lloyd loop of cluster_kmeans, euclidean_distance / compare_samples -- oracle/_ref/
+    libndb_ref_leafs.so), with the rand() draws that seeded them.  `python make_golden.py ml` writes only this file."""
+    import test_oracle as T
+    assert O.ref_leafs_lib() is not None, "build oracle/_ref first (make -C oracle)"
+    out = {}
+    for n, dim, k, seed in T._ml_cases():
+        tag = "n%d" % n
+        X = W.mixture(n, dim, max(2, k // 2), seed)
+        out["draws_" + tag] = O.libc_rand_draws(seed, k)
+        labels, centers, it = O.ref_cluster_kmeans(X, k, 0, seed)
+        out["km_labels_" + tag], out["km_center_bits_" + tag], out["km_iters_" + tag] = labels, centers.view(np.uint32), np.int32(it)
+        rng = np.random.default_rng(seed)
+        Q = W.mixture(30, dim, 5, seed + 1, centers_seed=seed)
+        lab = rng.integers(0, 3, n).astype(np.float64)
+        cls, mean, _ = O.ref_knn_ml(X, lab, Q, min(k, n))
+        out["knn_cls_" + tag], out["knn_mean_" + tag] = cls, mean
+    np.savez_compressed(os.path.join(HERE, "ml_paths.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["ml"]:
+        ml_paths()
+    else:
+        main()

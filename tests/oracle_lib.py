@@ -21,6 +21,8 @@ _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
 _i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+RAND_MAX = 2147483647                      # glibc
 
 
 def build_oracle():
@@ -78,6 +80,14 @@ def _load(name="libndb_oracle.so"):
     f = lib.orc_recall_at_k; f.restype = C.c_double; f.argtypes = [_i64p, _i64p, C.c_int, C.c_int]
     f = lib.orc_merge_topk; f.restype = None
     f.argtypes = [_f32p, _i64p, C.c_int, C.c_int, C.c_int, _f32p, _i64p]
+    f = lib.orc_ml_euclidean; f.restype = C.c_double; f.argtypes = [_f32p, _f32p, C.c_int]
+    f = lib.orc_l2_distance_squared; f.restype = C.c_double; f.argtypes = [_f32p, _f32p, C.c_int]
+    f = lib.orc_knn_ml; f.restype = None
+    f.argtypes = [_f32p, _f64p, C.c_int, C.c_int, _f32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), _i32p]
+    f = lib.orc_kmeanspp_init; f.restype = C.c_int
+    f.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p]
+    f = lib.orc_cluster_kmeans; f.restype = C.c_int
+    f.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, C.c_void_p, C.c_void_p]
     f = lib.orc_fp16_to_float; f.restype = C.c_float; f.argtypes = [C.c_uint16]
     f = lib.orc_keys_from_halfvec; f.restype = None
     f.argtypes = [np.ctypeslib.ndpointer(np.uint16, flags="C"), C.c_int64, C.c_int, _f32p]
@@ -388,6 +398,13 @@ def ref_leafs_lib():
     l.ref_kmeans_train.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, _i32p, _i32p]
     l.ref_layout.restype = C.c_int
     l.ref_layout.argtypes = [_i64p]
+    l.ref_knn_ml.restype = None
+    l.ref_knn_ml.argtypes = [_f32p, _f64p, C.c_int, C.c_int, _f32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_void_p]
+    l.ref_ml_euclidean.restype = C.c_double; l.ref_ml_euclidean.argtypes = [_f32p, _f32p, C.c_int]
+    l.ref_l2_distance_squared.restype = C.c_double; l.ref_l2_distance_squared.argtypes = [_f32p, _f32p, C.c_int]
+    l.ref_kmeanspp_init.restype = None; l.ref_kmeanspp_init.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p]
+    l.ref_cluster_kmeans.restype = C.c_int
+    l.ref_cluster_kmeans.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_void_p]
     return l
 
 
@@ -416,3 +433,59 @@ def ref_kmeans_train(X, k):
     counts = np.zeros(k, np.int32)
     ref_leafs_lib().ref_kmeans_train(X, n, d, k, Cn, assign, counts)
     return Cn, assign, counts
+
+
+# ---- knn_classify / knn_regress / cluster_kmeans (oracle/ndb_oracle_ml.c) --------------------------------------
+def libc_rand_draws(seed, k):
+    """What rand() returns k times after srand(seed) in this libc (cluster_kmeans' kmeanspp_init draws exactly k)."""
+    libc = C.CDLL(None)
+    libc.srand(C.c_uint(seed))
+    libc.rand.restype = C.c_int
+    return np.array([libc.rand() for _ in range(k)], np.int32)
+
+
+def knn_ml(X, labels, Q, k):
+    """(class, mean, rows[k]) per query: the oracle's knn_classify / knn_regress over the resident rows."""
+    X, Q = f32(X), f32(Q)
+    labels = np.ascontiguousarray(labels, np.float64)
+    n, d = X.shape
+    cls, mean, rows = np.zeros(len(Q), np.int32), np.zeros(len(Q)), np.zeros((len(Q), min(k, n)), np.int32)
+    for j in range(len(Q)):
+        c, m = C.c_int(), C.c_double()
+        lib().orc_knn_ml(X, labels, n, d, Q[j], k, C.byref(c), C.byref(m), rows[j])
+        cls[j], mean[j] = c.value, m.value
+    return cls, mean, rows
+
+
+def ref_knn_ml(X, labels, Q, k):
+    """The same through the reference's own KNNSample / euclidean_distance / compare_samples / qsort; also the
+    n distances per query."""
+    X, Q = f32(X), f32(Q)
+    labels = np.ascontiguousarray(labels, np.float64)
+    n, d = X.shape
+    cls, mean, dist = np.zeros(len(Q), np.int32), np.zeros(len(Q)), np.zeros((len(Q), n))
+    for j in range(len(Q)):
+        c, m = C.c_int(), C.c_double()
+        ref_leafs_lib().ref_knn_ml(X, labels, n, d, Q[j], k, C.byref(c), C.byref(m), dist[j].ctypes.data)
+        cls[j], mean[j] = c.value, m.value
+    return cls, mean, dist
+
+
+def cluster_kmeans(X, k, max_iters, draws):
+    """(labels 1-based, centers, seeds, iterations): oracle restatement of cluster_kmeans with the given rand() draws."""
+    X = f32(X)
+    n, d = X.shape
+    labels, centers, seeds = np.zeros(n, np.int32), np.zeros((k, d), np.float32), np.zeros(k, np.int32)
+    draws = np.ascontiguousarray(draws, np.int32)
+    it = lib().orc_cluster_kmeans(X, n, d, k, max_iters, draws, RAND_MAX, labels, centers.ctypes.data, seeds.ctypes.data)
+    return labels, centers, seeds, it
+
+
+def ref_cluster_kmeans(X, k, max_iters, seed):
+    """The reference's kmeanspp_init + Lloyd loop after srand(seed): (labels, centers, iterations)."""
+    X = f32(X)
+    n, d = X.shape
+    labels, centers = np.zeros(n, np.int32), np.zeros((k, d), np.float32)
+    C.CDLL(None).srand(C.c_uint(seed))
+    it = ref_leafs_lib().ref_cluster_kmeans(X, n, d, k, max_iters, labels, centers.ctypes.data)
+    return labels, centers, it

@@ -1,0 +1,62 @@
+"""GPU: cluster_kmeans (NeuronDB/src/ml/ml_kmeans.c:146-303, kmeanspp_init :45-139) through the C ABI.
+
+Labels, centres (bit patterns), the seeds kmeanspp_init picked and the number of Lloyd iterations must equal (a) the
+committed outputs of the reference's OWN functions (tests/golden/ml_paths.npz, written from oracle/_ref/
+libndb_ref_leafs.so by tests/golden/make_golden.py) and (b) the oracle restatement on larger seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import workloads as W
+
+pytestmark = pytest.mark.gpu
+BITS = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ml_paths.npz")
+CASES = [(400, 8, 5, 3), (900, 33, 4, 7), (1500, 16, 12, 5), (60, 3, 6, 60)]          # test_oracle._ml_cases
+
+
+def test_cluster_kmeans_equals_the_reference_outputs(ndb):
+    g = np.load(GOLDEN)
+    for n, dim, k, seed in CASES:
+        tag = "n%d" % n
+        X = W.mixture(n, dim, max(2, k // 2), seed)
+        labels, centers, seeds, it = ndb.cluster_kmeans(X, k, 0, g["draws_" + tag])
+        assert it == int(g["km_iters_" + tag]), tag
+        assert np.array_equal(labels, g["km_labels_" + tag]), tag
+        assert np.array_equal(BITS(centers), g["km_center_bits_" + tag]), tag
+
+
+@pytest.mark.parametrize("n,dim,k,max_iters", [(20000, 32, 16, 0), (5000, 7, 64, 4), (3000, 130, 9, 2), (4097, 5, 2, 0), (64, 4, 64, 3)])
+def test_cluster_kmeans_equals_the_oracle(ndb, n, dim, k, max_iters):
+    X = W.mixture(n, dim, max(2, k // 3), n + k)
+    if n == 64:
+        X[5:9] = X[4]                          # duplicate rows: zero weights in the walk, clusters that end empty
+    draws = np.random.default_rng(n).integers(0, O.RAND_MAX, k, dtype=np.int64).astype(np.int32)
+    if n == 4097:
+        draws[1] = O.RAND_MAX                  # r = sum: the walk runs to the last rows (or past them: the :103-113 branch)
+    if n == 5000:
+        draws[2] = 0                           # r = 0: the first unselected row
+    want_l, want_c, want_s, want_it = O.cluster_kmeans(X, k, max_iters, draws)
+    labels, centers, seeds, it = ndb.cluster_kmeans(X, k, max_iters, draws)
+    assert np.array_equal(seeds, want_s)
+    assert it == want_it and np.array_equal(labels, want_l)
+    assert np.array_equal(BITS(centers), BITS(want_c))
+    assert labels.min() >= 1 and labels.max() <= k
+
+
+def test_cluster_kmeans_errors_are_the_sql_functions(ndb):
+    X = W.gaussian(10, 4, 1)
+    d = np.arange(12, dtype=np.int32)
+    with pytest.raises(ndb.NdbError) as e:
+        ndb.cluster_kmeans(X, 1, 5, d[:1])
+    assert e.value.code == -1 and "number of clusters must be at least 2" in str(e.value)
+    with pytest.raises(ndb.NdbError) as e:
+        ndb.cluster_kmeans(X, 11, 5, d[:11])
+    assert e.value.code == -1 and "not enough vectors for cluster count (need >= 11, have 10)" in str(e.value)
+    bad = X.copy()
+    bad[3, 1] = np.inf
+    with pytest.raises(ndb.NdbError) as e:
+        ndb.cluster_kmeans(bad, 2, 5, d[:2])
+    assert e.value.code == -4

@@ -354,3 +354,70 @@ def test_reference_index_fixture_t010():
     g.build(X, np.zeros(8, np.int32), 1)
     d, n, _ = g.search(q, 64, 8, 1, 1)
     assert np.array_equal(n[0], np.arange(8)) and np.array_equal(d[0], want_d)
+
+
+# ---- knn_classify / knn_regress / cluster_kmeans (oracle/ndb_oracle_ml.c) -------------------
+def _ml_cases():
+    return [(400, 8, 5, 3), (900, 33, 4, 7), (1500, 16, 12, 5), (60, 3, 6, 60)]     # n, dim, k (clusters / neighbours), seed
+
+
+@pytest.mark.skipif(O.ref_leafs_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_ml_distances_equal_the_reference_functions():
+    """orc_ml_euclidean against euclidean_distance (ml_knn.c:76-90) and orc_l2_distance_squared against
+    neurondb_l2_distance_squared (neurondb_simd_impl.c:36-104), both compiled from the reference source."""
+    ref = O.ref_leafs_lib()
+    for a, b in _leaf_inputs():
+        for i in range(a.shape[0]):
+            dim = a.shape[1]
+            assert O.lib().orc_ml_euclidean(a[i], b[i], dim) == ref.ref_ml_euclidean(a[i], b[i], dim)
+            assert O.lib().orc_l2_distance_squared(a[i], b[i], dim) == ref.ref_l2_distance_squared(a[i], b[i], dim)
+
+
+@pytest.mark.skipif(O.ref_leafs_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_knn_ml_equals_the_reference_functions():
+    for n, dim, k, seed in _ml_cases():
+        rng = np.random.default_rng(seed)
+        X = W.mixture(n, dim, 5, seed)
+        Q = W.mixture(30, dim, 5, seed + 1, centers_seed=seed)
+        labels = rng.integers(0, 3, n).astype(np.float64) + rng.integers(0, 2, n) * 0.5
+        cls, mean, rows = O.knn_ml(X, labels, Q, min(k, n))
+        rcls, rmean, rdist = O.ref_knn_ml(X, labels, Q, min(k, n))
+        assert np.array_equal(cls, rcls) and np.array_equal(mean, rmean)
+        for j in range(len(Q)):                                      # the rows are the k smallest reference distances
+            assert np.array_equal(np.sort(rdist[j])[:rows.shape[1]], rdist[j][rows[j]])
+
+
+@pytest.mark.skipif(O.ref_leafs_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_cluster_kmeans_equals_the_reference_functions():
+    """orc_cluster_kmeans against the reference's kmeanspp_init (ml_kmeans.c:45-139) and the text of cluster_kmeans'
+    Lloyd loop (:226-278) compiled from its source, with rand() seeded alike: labels, centers bit for bit, iterations."""
+    import ctypes
+    for n, dim, k, seed in _ml_cases():
+        X = W.mixture(n, dim, max(2, k // 2), seed)
+        if n == 60:
+            X[10:20] = X[0]                                           # duplicates: zero D^2 weights, empty clusters
+        for max_iters in (0, 3):
+            draws = O.libc_rand_draws(seed, k)
+            labels, centers, seeds, it = O.cluster_kmeans(X, k, max_iters, draws)
+            rl, rc, rit = O.ref_cluster_kmeans(X, k, max_iters, seed)
+            assert it == rit and np.array_equal(labels, rl) and np.array_equal(BITS(centers), BITS(rc)), (n, dim, k)
+            ctypes.CDLL(None).srand(seed)
+            rs = np.zeros(k, np.int32)
+            O.ref_leafs_lib().ref_kmeanspp_init(X, n, dim, k, rs)
+            assert np.array_equal(seeds, rs)
+
+
+def test_ml_golden_vectors():
+    """The same against tests/golden/ml_paths.npz (outputs of the reference's functions, written by make_golden.py)."""
+    g = np.load(os.path.join(HERE, "golden", "ml_paths.npz"))
+    for n, dim, k, seed in _ml_cases():
+        tag = "n%d" % n
+        X = W.mixture(n, dim, max(2, k // 2), seed)
+        labels, centers, seeds, it = O.cluster_kmeans(X, k, 0, g["draws_" + tag])
+        assert np.array_equal(labels, g["km_labels_" + tag]) and np.array_equal(BITS(centers), g["km_center_bits_" + tag])
+        assert it == int(g["km_iters_" + tag])
+        rng = np.random.default_rng(seed)
+        Q = W.mixture(30, dim, 5, seed + 1, centers_seed=seed)
+        lab = rng.integers(0, 3, n).astype(np.float64)
+        cls, mean, _ = O.knn_ml(X, lab, Q, min(k, n))
+        assert np.array_equal(cls, g["knn_cls_" + tag]) and np.array_equal(mean, g["knn_mean_" + tag])
