@@ -173,6 +173,36 @@ int ndb_b200_knn_regress(ndb_b200_dataset *ds, const double *targets, const floa
 int ndb_b200_cluster_kmeans(const float *X, int n, int dim, int k, int max_iters, const int *rand_draws, int rand_max,
                             int *labels, float *centers, int *iters, int *seeds);
 
+/* ---- product quantisation (src/ml/ml_product_quantization.c).  Codebooks are laid out as the reference's
+ *      bytea carries them after its three ints: float centroids[m][ksub][dsub], dsub = dim / m.  Arithmetic is the SQL
+ *      functions': double difference / square / sum, strict <, lowest code wins; results are bit-identical to them.
+ *      Shape errors carry the reference's messages: m outside 1..128 or ksub outside 2..65536 -> EINVAL (:218-227),
+ *      dim % m != 0 -> EDIM (:270-276), NaN / Inf -> EVECTOR. */
+/* train_pq_codebook (:195-415): per subspace train_subspace_kmeans (:80-190) -- seeds = rows rand() % n, Lloyd until no
+ * assignment changes or max_iters (the reference passes 100; < 0 -> 100).  rand_draws = the m*ksub values rand() returns,
+ * in call order (subspace-major). */
+int ndb_b200_pq_train(const float *X, int n, int dim, int m, int ksub, int max_iters, const int *rand_draws, float *codebooks);
+/* pq_encode_vector (:421-536) for n rows: int2 codes [n][m] as the SQL function returns them (ksub <= 32768) */
+int ndb_b200_pq_encode(const float *X, int64_t n, int dim, const float *codebooks, int m, int ksub, int16_t *codes);
+/* ndb_gpu_backend.launch_pq_encode (include/neurondb_gpu_backend.h:106-113; CUDA instance gpu_backend_cuda.c:711-732 ->
+ * gpu_pq_encode_batch, src/gpu/cuda/gpu_pq_kernels.cu:54-110, 163-213): the same signature, byte codes (ks <= 256) */
+int ndb_b200_launch_pq_encode(const float *X, const float *codebooks, uint8_t *codes, int n, int d, int m, int ks, void *stream);
+/* Resident encoded rows + the asymmetric-distance scan: ORDER BY pq_asymmetric_distance(q, codes, codebook) LIMIT k
+ * (:1003-1110; gpu_pq_asymmetric_distance_batch, gpu_pq_kernels.cu:127-158, 215-269).  ksub <= 256 (byte codes on the
+ * device), m * ksub * 8 bytes must fit shared memory.  add encodes and appends (codes_out optional, [n][m]); add_codes
+ * appends codes made elsewhere (a code outside 0..ksub-1 -> ERANGE with the reference's message, nothing appended);
+ * search returns the k nearest rows by (distance, row), +inf / -1 past the end; distances returns all nq * n of them
+ * (rechecked, optional: how many fell back from the table sum to the reference's chain). */
+typedef struct ndb_b200_pq ndb_b200_pq;
+int ndb_b200_pq_create(int dim, int m, int ksub, const float *codebooks, ndb_b200_pq **out);
+void ndb_b200_pq_free(ndb_b200_pq *pq);
+int64_t ndb_b200_pq_size(const ndb_b200_pq *pq);
+int ndb_b200_pq_add(ndb_b200_pq *pq, const float *X, int64_t n, int16_t *codes_out);
+int ndb_b200_pq_add_codes(ndb_b200_pq *pq, const int16_t *codes, int64_t n);
+int ndb_b200_pq_search(ndb_b200_pq *pq, const float *Q, int nq, int k, float *dist, int64_t *rows);
+int ndb_b200_pq_search_dev(ndb_b200_pq *pq, const float *Q_dev, int nq, int k, float *dist_dev, int64_t *rows_dev, void *stream);
+int ndb_b200_pq_distances(ndb_b200_pq *pq, const float *Q, int nq, float *dist, unsigned long long *rechecked);
+
 /* ---- IVF k-means: kmeans_init/run/assign/update_centroids/compute_cost
  *      (src/index/ivf_am.c:2070-2294).  Literal semantics: centroids := first k rows,
  *      <= max_iter Lloyd steps, stop when |prevCost - cost| < tol, f32 sequential sums.

@@ -71,6 +71,17 @@ SIGNATURES = {
     "ndb_b200_knn_classify": (_i, [_p, _p, _p, _i, _i, _p]),
     "ndb_b200_knn_regress": (_i, [_p, _p, _p, _i, _i, _p]),
     "ndb_b200_cluster_kmeans": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
+    "ndb_b200_pq_train": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "ndb_b200_pq_encode": (_i, [_p, _i64, _i, _p, _i, _i, _p]),
+    "ndb_b200_launch_pq_encode": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "ndb_b200_pq_create": (_i, [_i, _i, _i, _p, C.POINTER(_p)]),
+    "ndb_b200_pq_free": (None, [_p]),
+    "ndb_b200_pq_size": (_i64, [_p]),
+    "ndb_b200_pq_add": (_i, [_p, _p, _i64, _p]),
+    "ndb_b200_pq_add_codes": (_i, [_p, _p, _i64]),
+    "ndb_b200_pq_search": (_i, [_p, _p, _i, _i, _p, _p]),
+    "ndb_b200_pq_search_dev": (_i, [_p, _p, _i, _i, _p, _p, _p]),
+    "ndb_b200_pq_distances": (_i, [_p, _p, _i, _p, _p]),
     "ndb_b200_kmeans_train": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p, C.POINTER(_i), C.POINTER(_f)]),
     "ndb_b200_ivf_create": (_i, [_i, _i, _i, C.POINTER(_p)]),
     "ndb_b200_ivf_free": (None, [_p]),

@@ -290,6 +290,86 @@ class _Handle:
             pass
 
 
+def _pq_shape(cb):
+    cb = f32(cb)
+    if cb.ndim != 3:
+        raise L.NdbError(-1, "pq: codebooks are [m][ksub][dsub]")
+    m, ksub, dsub = cb.shape
+    return cb, m, ksub, dsub
+
+
+def pq_train(X, m, ksub, rand_draws, max_iters=100):
+    """train_pq_codebook (ml_product_quantization.c:195-415): codebooks [m][ksub][dim/m]; rand_draws = m*ksub rand() values."""
+    X = f32(X)
+    if X.ndim != 2:
+        raise L.NdbError(-1, "pq_train: a 2-d array of rows expected")
+    n, dim = X.shape
+    draws = np.ascontiguousarray(rand_draws, np.int32)
+    if draws.size != max(m, 0) * max(ksub, 0):
+        raise L.NdbError(-1, "pq_train: m * ksub rand() values expected")
+    cb = np.zeros((max(m, 1), max(ksub, 1), max(1, dim // max(m, 1))), np.float32)
+    check(L.load().ndb_b200_pq_train(ptr(X), n, dim, m, ksub, max_iters, ptr(draws), ptr(cb)))
+    return cb
+
+
+def pq_encode(X, codebooks):
+    """pq_encode_vector (:421-536) for every row: int16 codes [n][m]."""
+    cb, m, ksub, dsub = _pq_shape(codebooks)
+    X = _rows(X, m * dsub, "pq_encode")
+    codes = np.zeros((X.shape[0], m), np.int16)
+    check(L.load().ndb_b200_pq_encode(ptr(X), X.shape[0], m * dsub, ptr(cb), m, ksub, ptr(codes)))
+    return codes
+
+
+def launch_pq_encode(X, codebooks):
+    """The backend vtable's launch_pq_encode: byte codes [n][m]."""
+    cb, m, ksub, dsub = _pq_shape(codebooks)
+    X = _rows(X, m * dsub, "launch_pq_encode")
+    codes = np.zeros((X.shape[0], m), np.uint8)
+    check(L.load().ndb_b200_launch_pq_encode(ptr(X), ptr(cb), ptr(codes), X.shape[0], m * dsub, m, ksub, None))
+    return codes
+
+
+class PqIndex(_Handle):
+    """Encoded rows resident on the device + ORDER BY pq_asymmetric_distance(q, codes, codebook) LIMIT k (:1003-1110)."""
+    _free = "ndb_b200_pq_free"
+
+    def __init__(self, codebooks):
+        super().__init__()
+        cb, self.m, self.ksub, self.dsub = _pq_shape(codebooks)
+        self.dim = self.m * self.dsub
+        check(L.load().ndb_b200_pq_create(self.dim, self.m, self.ksub, ptr(cb), C.byref(self.h)))
+
+    def __len__(self):
+        return int(L.load().ndb_b200_pq_size(self.h))
+
+    def add(self, X, want_codes=False):
+        X = _rows(X, self.dim, "pq_add")
+        codes = np.zeros((X.shape[0], self.m), np.int16) if want_codes else None
+        check(L.load().ndb_b200_pq_add(self.h, ptr(X), X.shape[0], ptr(codes)))
+        return codes
+
+    def add_codes(self, codes):
+        codes = np.ascontiguousarray(codes, np.int16)
+        if codes.ndim != 2 or codes.shape[1] != self.m:
+            raise L.NdbError(-5, "pq_add_codes: codes are [n][m]")
+        check(L.load().ndb_b200_pq_add_codes(self.h, ptr(codes), codes.shape[0]))
+
+    def search(self, Q, k):
+        Q = _rows(Q, self.dim, "pq_search")
+        d = np.empty((Q.shape[0], k), np.float32)
+        r = np.empty((Q.shape[0], k), np.int64)
+        check(L.load().ndb_b200_pq_search(self.h, ptr(Q), Q.shape[0], k, ptr(d), ptr(r)))
+        return d, r
+
+    def distances(self, Q):
+        Q = _rows(Q, self.dim, "pq_distances")
+        d = np.empty((Q.shape[0], len(self)), np.float32)
+        cnt = C.c_ulonglong()
+        check(L.load().ndb_b200_pq_distances(self.h, ptr(Q), Q.shape[0], ptr(d), C.byref(cnt)))
+        return d, cnt.value
+
+
 class Dataset(_Handle):
     """The heap column a SeqScan reads; exact kNN = ORDER BY v <op> q LIMIT k."""
     _free = "ndb_b200_dataset_free"

@@ -160,6 +160,49 @@ __global__ void __launch_bounds__(128) ckm_assign_kernel(const float *__restrict
     }
 }
 
+int transpose_rows_dev(const float *dX, int64_t n, int dim, float *dXT, cudaStream_t s)
+{
+    ckm_transpose_kernel<<<dim3((unsigned) ((n + 31) / 32), (unsigned) ((dim + 31) / 32)), dim3(32, 8), 0, s>>>(dX, n, dim, dXT);
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
+}
+
+int gather_rows_dev(const float *dX, const int *rows_dev, int nrows, int dim, float *out, cudaStream_t s)
+{
+    ckm_gather_centers_kernel<<<nrows, 128, 0, s>>>(dX, rows_dev, dim, out);
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
+}
+
+int nearest_f64_dev(const float *dXT, const float *dC, int64_t n, int dim, int k, int *assign, int *changed, cudaStream_t s)
+{
+    ckm_assign_kernel<4><<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(dXT, dC, n, dim, k, assign, changed);
+    count_launch();
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
+}
+
+int lloyd_f64_dev(KMeansWork &w, const float *dX, const float *dXT, int64_t n, int dim, int k, int max_iters, bool stop_before_update,
+                  int *dchanged, int *iters, cudaStream_t s)
+{
+    int changed = 1, iter = 0;
+    for (iter = 0; iter < max_iters && (stop_before_update || changed); iter++) {
+        NDB_CUDA(cudaMemsetAsync(dchanged, 0, 4, s));
+        NDB_CHECK(nearest_f64_dev(dXT, w.C.as<float>(), n, dim, k, w.assign.as<int>(), dchanged, s));
+        NDB_CUDA(cudaMemcpyAsync(&changed, dchanged, 4, cudaMemcpyDeviceToHost, s));
+        if (stop_before_update) {
+            NDB_CUDA(cudaStreamSynchronize(s));
+            if (!changed) break;
+        }
+        NDB_CHECK(kmeans_update_dev(w, dX, w.assign.as<int>(), n, dim, k, w.C.as<float>(), w.counts.as<int>(), s));
+        NDB_CUDA(cudaStreamSynchronize(s));
+    }
+    if (iters) *iters = iter;
+    return NDB_B200_OK;
+}
+
 }  // namespace ndb
 
 using namespace ndb;
@@ -188,8 +231,7 @@ int ndb_b200_cluster_kmeans(const float *X, int n, int dim, int k, int max_iters
     NDB_CUDA(cudaMemcpyAsync(ddraws.p, rand_draws, (size_t) k * 4, cudaMemcpyHostToDevice, s));
     NDB_CUDA(cudaMemsetAsync(selected.p, 0, (size_t) n, s));
     const float *dX = w.X.as<float>();
-    ckm_transpose_kernel<<<dim3((unsigned) ((n + 31) / 32), (unsigned) ((dim + 31) / 32)), dim3(32, 8), 0, s>>>(dX, n, dim, XT.as<float>());
-    count_launch();
+    NDB_CHECK(transpose_rows_dev(dX, n, dim, XT.as<float>(), s));
     const unsigned rb = (unsigned) ((n + 255) / 256);
     for (int c = 0; c < k; c++) {
         ckm_pick_kernel<<<1, 1024, 0, s>>>(dist.as<double>(), selected.as<unsigned char>(), n, ddraws.as<int>(), (double) rand_max, c,
@@ -198,20 +240,10 @@ int ndb_b200_cluster_kmeans(const float *X, int n, int dim, int k, int max_iters
             ckm_weight_kernel<<<rb, 256, 0, s>>>(XT.as<float>(), dX, n, dim, dseeds.as<int>(), c, dist.as<double>());
         count_launch(2);
     }
-    ckm_gather_centers_kernel<<<k, 128, 0, s>>>(dX, dseeds.as<int>(), dim, w.C.as<float>());
-    count_launch();
-    NDB_CUDA(cudaGetLastError());
+    NDB_CHECK(gather_rows_dev(dX, dseeds.as<int>(), k, dim, w.C.as<float>(), s));
     NDB_CUDA(cudaMemsetAsync(w.assign.p, 0xff, (size_t) n * 4, s));                                                    // assignments[i] = -1 (:206-207)
-    int changed = 1, iter = 0;
-    for (iter = 0; iter < max_iters && changed; iter++) {
-        NDB_CUDA(cudaMemsetAsync(dchanged.p, 0, 4, s));
-        ckm_assign_kernel<4><<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(XT.as<float>(), w.C.as<float>(), n, dim, k, w.assign.as<int>(),
-                                                                          dchanged.as<int>());
-        count_launch();
-        NDB_CUDA(cudaMemcpyAsync(&changed, dchanged.p, 4, cudaMemcpyDeviceToHost, s));
-        NDB_CHECK(kmeans_update_dev(w, dX, w.assign.as<int>(), n, dim, k, w.C.as<float>(), w.counts.as<int>(), s));
-        NDB_CUDA(cudaStreamSynchronize(s));
-    }
+    int iter = 0;
+    NDB_CHECK(lloyd_f64_dev(w, dX, XT.as<float>(), n, dim, k, max_iters, false, dchanged.as<int>(), &iter, s));           // :226-278
     NDB_CUDA(cudaMemcpyAsync(labels, w.assign.p, (size_t) n * 4, cudaMemcpyDeviceToHost, s));
     if (centers) NDB_CUDA(cudaMemcpyAsync(centers, w.C.p, cb, cudaMemcpyDeviceToHost, s));
     if (seeds) NDB_CUDA(cudaMemcpyAsync(seeds, dseeds.p, (size_t) k * 4, cudaMemcpyDeviceToHost, s));

@@ -45,4 +45,15 @@ int kmeans_update_dev(KMeansWork &w, const float *dX, const int *d_assign, int64
 int kmeans_run_dev(KMeansWork &w, int n, int d, int k, int max_iter, float tol, int *iters, float *cost_out,
                    cudaStream_t s);
 
+// ---- fp64 Lloyd (cluster_kmeans.cu): the arithmetic of cluster_kmeans (ml_kmeans.c:226-278) and train_subspace_kmeans
+// (ml_product_quantization.c:108-186): double difference / square / sum, strict <, lowest index wins; ordered float update.
+// dXT = the rows transposed ([dim][n], row stride n).  w.C holds the k*dim centres, w.assign the current assignment.
+int transpose_rows_dev(const float *dX, int64_t n, int dim, float *dXT, cudaStream_t s);
+int gather_rows_dev(const float *dX, const int *rows_dev, int nrows, int dim, float *out, cudaStream_t s);
+int nearest_f64_dev(const float *dXT, const float *dC, int64_t n, int dim, int k, int *assign, int *changed, cudaStream_t s);
+// stop_before_update: leave the loop after an assignment pass that changed nothing (train_subspace_kmeans); otherwise the
+// update runs once more and the loop condition ends it (cluster_kmeans)
+int lloyd_f64_dev(KMeansWork &w, const float *dX, const float *dXT, int64_t n, int dim, int k, int max_iters, bool stop_before_update,
+                  int *dchanged, int *iters, cudaStream_t s);
+
 }  // namespace ndb

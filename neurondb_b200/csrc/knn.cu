@@ -4,6 +4,7 @@
 #include "scan.cuh"
 #include "tc.cuh"
 #include <vector>
+#include <algorithm>
 
 namespace ndb {
 
@@ -135,6 +136,24 @@ int dense_scan(const float *store, const void *vnorm, int64_t nvec, int dim, int
     return NDB_B200_OK;
 }
 
+// euclidean_distance as the double the reference sorts on: one thread per (query, candidate slot)
+__global__ void knn_ml_rescore_kernel(const float *__restrict__ store, int dim, int dimp, const float *__restrict__ Q,
+                                      const uint32_t *__restrict__ slots, int kq, int64_t total, double *__restrict__ out)
+{
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const uint32_t slot = slots[t];
+    if (slot == INVALID_SLOT) { out[t] = INFINITY; return; }
+    const float *q = Q + (size_t) (t / kq) * dim;
+    const float *v = store + (size_t) (slot >> 5) * IL * dimp + (size_t) (slot & 31) * 4;
+    double sum = 0.0;
+    for (int d = 0; d < dim; d++) {
+        const double diff = (double) __fsub_rn(q[d], v[(size_t) (d >> 2) * (IL * 4) + (d & 3)]);      // double diff = a[i] - b[i] (:84)
+        sum = __fma_rn(diff, diff, sum);                                                             // diff*diff is exact in fp64
+    }
+    out[t] = __dsqrt_rn(sum);
+}
+
 }  // namespace ndb
 
 extern "C" {
@@ -247,6 +266,10 @@ int ndb_b200_knn_exact(ndb_b200_dataset *ds, int metric, int arith, const float 
 // sum, sqrt) of every row to the query, qsort by distance and vote among / average the k nearest.  Here the rows are a
 // resident dataset, the distances and the top-k are the scan kernel's (NDB_ARITH_HNSW is that same arithmetic), and
 // only the vote over k labels is left to the host.  labels[i] belongs to the i-th appended row.
+// The scan kernel's top-k is ordered by the distance rounded to float; the reference sorts the doubles.  So kq = k +
+// margin candidates are taken, re-evaluated as doubles and ordered by (double distance, row); the answer is certified
+// when the float distance of the last candidate is strictly above that of the k-th (rounding is monotonic, so every row
+// outside the candidates is then farther than the k-th), otherwise the query is repeated with the widest list (128).
 static int knn_neighbours(ndb_b200_dataset *ds, const float *Q, int nq, int k, const char *who, std::vector<uint32_t> &slots)
 {
     using namespace ndb;
@@ -256,24 +279,69 @@ static int knn_neighbours(ndb_b200_dataset *ds, const float *Q, int nq, int k, c
     NDB_REQUIRE(k <= 128, NDB_B200_EINVAL, "%s: k=%d out of range 1..128", who, k);
     NDB_REQUIRE(ds->n >= k, NDB_B200_ERANGE, "neurondb: %s: need at least %d samples, got %lld", who, k, (long long) ds->n);  // :190-205
     cudaStream_t s = ctx().stream;
-    const size_t qb = (size_t) nq * ds->dim * sizeof(float), m = (size_t) nq * k;
+    const size_t qb = (size_t) nq * ds->dim * sizeof(float);
     NDB_CHECK(ds->qbuf.reserve(qb));
-    NDB_CHECK(ds->outd.reserve(m * sizeof(float)));
-    NDB_CHECK(ds->outi.reserve(m * sizeof(int64_t)));
-    DevBuf dslots;
-    NDB_CHECK(dslots.reserve(m * sizeof(uint32_t)));
     NDB_CUDA(cudaMemcpyAsync(ds->qbuf.p, Q, qb, cudaMemcpyHostToDevice, s));
     NDB_CHECK(validate_begin(ds->qbuf.as<float>(), (int64_t) nq * ds->dim, s));
-    int nparts = 1;
-    NDB_CHECK(dense_scan(ds->store.ptr(), nullptr, ds->n, ds->dim, ds->dimp, NDB_L2, NDB_ARITH_HNSW, ds->qbuf.as<float>(), nq, k,
-                         ds->scratch, &nparts, s));
-    NDB_CHECK(launch_merge_parts(ds->scratch.pdist.as<float>(), ds->scratch.pslot.as<uint32_t>(), ds->ids.as<int64_t>(), nq, nparts, k,
-                                 ds->outd.as<float>(), ds->outi.as<int64_t>(), dslots.as<uint32_t>(), s));
-    slots.resize(m);
-    NDB_CUDA(cudaMemcpyAsync(slots.data(), dslots.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    NDB_CUDA(cudaStreamSynchronize(s));
-    const int64_t bad = validate_end();
-    NDB_REQUIRE(bad < 0, NDB_B200_EVECTOR, "vector contains NaN or Infinity at index %lld", (long long) (bad % ds->dim));   // NDB_CHECK_VECTOR_VALID
+    slots.assign((size_t) nq * k, 0);
+    DevBuf dslots, dexact;
+    std::vector<uint32_t> cand;
+    std::vector<float> cand_f;
+    std::vector<double> cand_d;
+    std::vector<int> order;
+    std::vector<int> todo(nq), again;
+    for (int q = 0; q < nq; q++) todo[q] = q;
+    bool validated = false;
+    for (int pass = 0; pass < 2 && !todo.empty(); pass++) {
+        const int64_t cap = ds->n < 128 ? ds->n : 128;
+        const int kq = (int) (pass == 0 ? (k + 8 < cap ? k + 8 : cap) : cap);
+        const int m = (int) todo.size();
+        const float *dq = ds->qbuf.as<float>();
+        DevBuf qsub;
+        if (pass > 0) {                                   // gather the queries that were not certified
+            NDB_CHECK(qsub.reserve((size_t) m * ds->dim * sizeof(float)));
+            for (int j = 0; j < m; j++)
+                NDB_CUDA(cudaMemcpyAsync(qsub.as<float>() + (size_t) j * ds->dim, ds->qbuf.as<float>() + (size_t) todo[j] * ds->dim,
+                                         (size_t) ds->dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            dq = qsub.as<float>();
+        }
+        const size_t mk = (size_t) m * kq;
+        NDB_CHECK(ds->outd.reserve(mk * sizeof(float)));
+        NDB_CHECK(dslots.reserve(mk * sizeof(uint32_t)));
+        NDB_CHECK(dexact.reserve(mk * sizeof(double)));
+        int nparts = 1;
+        NDB_CHECK(dense_scan(ds->store.ptr(), nullptr, ds->n, ds->dim, ds->dimp, NDB_L2, NDB_ARITH_HNSW, dq, m, kq, ds->scratch, &nparts, s));
+        // (no id table: the merged keys are the slots themselves -- labels[] is indexed by the row's position)
+        NDB_CHECK(launch_merge_parts(ds->scratch.pdist.as<float>(), ds->scratch.pslot.as<uint32_t>(), nullptr, m, nparts, kq,
+                                     ds->outd.as<float>(), nullptr, dslots.as<uint32_t>(), s));
+        knn_ml_rescore_kernel<<<(unsigned) ((mk + 127) / 128), 128, 0, s>>>(ds->store.ptr(), ds->dim, ds->dimp, dq, dslots.as<uint32_t>(), kq,
+                                                                            (int64_t) mk, dexact.as<double>());
+        count_launch();
+        cand.resize(mk); cand_f.resize(mk); cand_d.resize(mk);
+        NDB_CUDA(cudaMemcpyAsync(cand.data(), dslots.p, mk * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        NDB_CUDA(cudaMemcpyAsync(cand_f.data(), ds->outd.p, mk * sizeof(float), cudaMemcpyDeviceToHost, s));
+        NDB_CUDA(cudaMemcpyAsync(cand_d.data(), dexact.p, mk * sizeof(double), cudaMemcpyDeviceToHost, s));
+        NDB_CUDA(cudaStreamSynchronize(s));
+        if (!validated) {
+            const int64_t bad = validate_end();
+            NDB_REQUIRE(bad < 0, NDB_B200_EVECTOR, "vector contains NaN or Infinity at index %lld", (long long) (bad % ds->dim));   // NDB_CHECK_VECTOR_VALID
+            validated = true;
+        }
+        again.clear();
+        order.resize(kq);
+        for (int j = 0; j < m; j++) {
+            const size_t b = (size_t) j * kq;
+            for (int i = 0; i < kq; i++) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](int x, int y) {
+                return cand_d[b + x] < cand_d[b + y] || (cand_d[b + x] == cand_d[b + y] && cand[b + x] < cand[b + y]);
+            });
+            const bool all_rows = kq >= ds->n;
+            const bool certified = all_rows || (kq > k && cand_f[b + kq - 1] > (float) cand_d[b + order[k - 1]]);
+            if (!certified && pass == 0 && kq < cap) { again.push_back(todo[j]); continue; }
+            for (int i = 0; i < k; i++) slots[(size_t) todo[j] * k + i] = cand[b + order[i]];
+        }
+        todo.swap(again);
+    }
     return NDB_B200_OK;
 }
 

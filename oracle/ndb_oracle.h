@@ -160,6 +160,14 @@ int orc_kmeanspp_init(const float *X, int nvec, int dim, int k, const int *draws
 int orc_cluster_kmeans(const float *X, int nvec, int dim, int k, int max_iters, const int *draws, int rand_max,
                        int *labels, float *centers_out, int *seeds_out);     /* ml_kmeans.c:45-139, 146-303 */
 
+/* product quantisation (ml_product_quantization.c:80-190, 195-415, 421-536, 1003-1110); codebooks [m][ksub][dsub] */
+void orc_pq_train_subspace(const float *S, int nvec, int dsub, int k, const int *draws, float *centroids, int max_iters);
+int orc_pq_train(const float *X, int nvec, int dim, int m, int ksub, const int *draws, int max_iters, float *codebooks);
+void orc_pq_encode(const float *X, int64_t n, int dim, const float *codebooks, int m, int ksub, int16_t *codes);
+float orc_pq_asymmetric_distance(const float *q, const int16_t *codes, const float *codebooks, int m, int ksub, int dsub);
+void orc_pq_knn(const float *Q, int nq, const int16_t *codes, int64_t n, const float *codebooks, int dim, int m, int ksub, int k,
+                float *dist, int64_t *rows, float *dist_all);
+
 /* sizes / field offsets used by the relation encoders (ndb_oracle_pages.c), in the order of the
  * reference-side ref_layout() built by oracle/extract_ref_leafs.py; returns the count */
 int orc_page_layout(int64_t *out);

@@ -167,3 +167,125 @@ int orc_cluster_kmeans(const float *X, int nvec, int dim, int k, int max_iters, 
     free(idx); free(assign); free(counts); free(centers);
     return iter;
 }
+
+/* ---- product quantisation: NeuronDB/src/ml/ml_product_quantization.c ------------------------------
+ * train_subspace_kmeans :80-190, train_pq_codebook :195-415, pq_encode_vector :421-536, pq_asymmetric_distance :1003-1110.
+ * Codebook layout as the bytea carries it: float centroids[m][ksub][dsub].  PINNED against the reference's own
+ * train_subspace_kmeans and the text of the encode / distance loops (oracle/extract_ref_leafs.py). */
+
+/* :80-190 on one subspace (rows of dsub floats, contiguous): seeds = rows draws[c] % nvec (duplicates allowed),
+ * assignments start at 0 (palloc0), the loop leaves before the update when nothing changed; empty clusters end at zero */
+void orc_pq_train_subspace(const float *S, int nvec, int dsub, int k, const int *draws, float *centroids, int max_iters)
+{
+    int *assign = (int *) calloc((size_t) nvec, sizeof(int));
+    int *counts = (int *) malloc(sizeof(int) * (size_t) k);
+    for (int c = 0; c < k; c++) memcpy(centroids + (size_t) c * dsub, S + (size_t) (draws[c] % nvec) * dsub, sizeof(float) * (size_t) dsub);
+    for (int iter = 0; iter < max_iters; iter++) {
+        int changed = 0;
+        for (int i = 0; i < nvec; i++) {
+            double min_dist = DBL_MAX;
+            int best = -1;
+            for (int c = 0; c < k; c++) {
+                double dist = 0.0;
+                for (int d = 0; d < dsub; d++) {
+                    double diff = (double) S[(size_t) i * dsub + d] - (double) centroids[(size_t) c * dsub + d];
+                    dist += diff * diff;
+                }
+                if (dist < min_dist) { min_dist = dist; best = c; }
+            }
+            if (assign[i] != best) { assign[i] = best; changed = 1; }
+        }
+        if (!changed) break;
+        memset(counts, 0, sizeof(int) * (size_t) k);
+        memset(centroids, 0, sizeof(float) * (size_t) k * dsub);
+        for (int i = 0; i < nvec; i++) {
+            int c = assign[i];
+            for (int d = 0; d < dsub; d++) centroids[(size_t) c * dsub + d] += S[(size_t) i * dsub + d];
+            counts[c]++;
+        }
+        for (int c = 0; c < k; c++)
+            if (counts[c] > 0)
+                for (int d = 0; d < dsub; d++) centroids[(size_t) c * dsub + d] /= counts[c];
+    }
+    free(assign); free(counts);
+}
+
+/* train_pq_codebook's loop over the subspaces (:303-352): draws[sub*ksub + c], 100 iterations */
+int orc_pq_train(const float *X, int nvec, int dim, int m, int ksub, const int *draws, int max_iters, float *codebooks)
+{
+    if (m < 1 || m > 128 || ksub < 2 || ksub > 65536 || dim <= 0 || dim % m != 0 || nvec < 1) return -1;
+    int dsub = dim / m;
+    float *S = (float *) malloc(sizeof(float) * (size_t) nvec * dsub);
+    for (int sub = 0; sub < m; sub++) {
+        for (int i = 0; i < nvec; i++) memcpy(S + (size_t) i * dsub, X + (size_t) i * dim + (size_t) sub * dsub, sizeof(float) * (size_t) dsub);
+        orc_pq_train_subspace(S, nvec, dsub, ksub, draws + (size_t) sub * ksub, codebooks + (size_t) sub * ksub * dsub, max_iters);
+    }
+    free(S);
+    return 0;
+}
+
+/* pq_encode_vector :479-503 for n rows */
+void orc_pq_encode(const float *X, int64_t n, int dim, const float *codebooks, int m, int ksub, int16_t *codes)
+{
+    int dsub = dim / m;
+    for (int64_t i = 0; i < n; i++)
+        for (int sub = 0; sub < m; sub++) {
+            int start_dim = sub * dsub, best = -1;
+            double min_dist = DBL_MAX;
+            for (int c = 0; c < ksub; c++) {
+                double dist = 0.0;
+                for (int d = 0; d < dsub; d++) {
+                    double diff = (double) X[(size_t) i * dim + start_dim + d] - (double) codebooks[((size_t) sub * ksub + c) * dsub + d];
+                    dist += diff * diff;
+                }
+                if (dist < min_dist) { min_dist = dist; best = c; }
+            }
+            codes[(size_t) i * m + sub] = (int16_t) best;
+        }
+}
+
+/* pq_asymmetric_distance :1063-1098: ONE double chain over all dimensions, then (float) sqrt; -1 on an invalid code */
+float orc_pq_asymmetric_distance(const float *q, const int16_t *codes, const float *codebooks, int m, int ksub, int dsub)
+{
+    double total_dist = 0.0;
+    for (int sub = 0; sub < m; sub++) {
+        int start_dim = sub * dsub, code = codes[sub];
+        if (code < 0 || code >= ksub) return -1.0f;
+        for (int d = 0; d < dsub; d++) {
+            double diff = (double) q[start_dim + d] - (double) codebooks[((size_t) sub * ksub + code) * dsub + d];
+            total_dist += diff * diff;
+        }
+    }
+    return (float) sqrt(total_dist);
+}
+
+/* ORDER BY pq_asymmetric_distance(q, codes, codebook) LIMIT k over n encoded rows: distances of every row (dist_all,
+ * optional nq*n) and the k nearest by (distance, row) */
+typedef struct { float d; int64_t row; } OrcPqHit;
+static int orc_pq_cmp(const void *a, const void *b)
+{
+    const OrcPqHit *x = (const OrcPqHit *) a, *y = (const OrcPqHit *) b;
+    if (x->d < y->d) return -1;
+    if (x->d > y->d) return 1;
+    return x->row < y->row ? -1 : (x->row > y->row);
+}
+void orc_pq_knn(const float *Q, int nq, const int16_t *codes, int64_t n, const float *codebooks, int dim, int m, int ksub, int k,
+                float *dist, int64_t *rows, float *dist_all)
+{
+    int dsub = dim / m;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int j = 0; j < nq; j++) {
+        OrcPqHit *h = (OrcPqHit *) malloc(sizeof(OrcPqHit) * (size_t) n);
+        for (int64_t i = 0; i < n; i++) {
+            h[i].d = orc_pq_asymmetric_distance(Q + (size_t) j * dim, codes + (size_t) i * m, codebooks, m, ksub, dsub);
+            h[i].row = i;
+            if (dist_all) dist_all[(size_t) j * n + i] = h[i].d;
+        }
+        qsort(h, (size_t) n, sizeof(OrcPqHit), orc_pq_cmp);
+        for (int i = 0; i < k; i++) {
+            dist[(size_t) j * k + i] = i < n ? h[i].d : INFINITY;
+            rows[(size_t) j * k + i] = i < n ? h[i].row : -1;
+        }
+        free(h);
+    }
+}

@@ -117,6 +117,16 @@ def ml_paths():
         lab = rng.integers(0, 3, n).astype(np.float64)
         cls, mean, _ = O.ref_knn_ml(X, lab, Q, min(k, n))
         out["knn_cls_" + tag], out["knn_mean_" + tag] = cls, mean
+    # product quantisation: the reference's train_subspace_kmeans and the loops of pq_encode_vector / pq_asymmetric_distance
+    for n, dim, m, ksub, seed in T._pq_cases():
+        tag = "pq%d" % n
+        X = W.mixture(n, dim, 6, seed)
+        Q = W.mixture(12, dim, 6, seed + 1, centers_seed=seed)
+        out["draws_" + tag] = O.libc_rand_draws(seed, m * ksub)
+        cb = O.ref_pq_train(X, m, ksub, seed, 5)
+        codes = O.ref_pq_encode(X, cb)
+        out["cb_bits_" + tag], out["codes_" + tag] = cb.view(np.uint32), codes
+        out["adc_bits_" + tag] = O.ref_pq_distances(Q, codes, cb).view(np.uint32)
     np.savez_compressed(os.path.join(HERE, "ml_paths.npz"), **out)
 
 

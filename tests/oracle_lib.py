@@ -86,6 +86,13 @@ def _load(name="libndb_oracle.so"):
     f.argtypes = [_f32p, _f64p, C.c_int, C.c_int, _f32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), _i32p]
     f = lib.orc_kmeanspp_init; f.restype = C.c_int
     f.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p]
+    f = lib.orc_pq_train; f.restype = C.c_int
+    f.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _f32p]
+    f = lib.orc_pq_encode; f.restype = None; f.argtypes = [_f32p, C.c_int64, C.c_int, _f32p, C.c_int, C.c_int, _i16p]
+    f = lib.orc_pq_asymmetric_distance; f.restype = C.c_float
+    f.argtypes = [_f32p, _i16p, _f32p, C.c_int, C.c_int, C.c_int]
+    f = lib.orc_pq_knn; f.restype = None
+    f.argtypes = [_f32p, C.c_int, _i16p, C.c_int64, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _i64p, C.c_void_p]
     f = lib.orc_cluster_kmeans; f.restype = C.c_int
     f.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p, C.c_void_p, C.c_void_p]
     f = lib.orc_fp16_to_float; f.restype = C.c_float; f.argtypes = [C.c_uint16]
@@ -405,6 +412,11 @@ def ref_leafs_lib():
     l.ref_kmeanspp_init.restype = None; l.ref_kmeanspp_init.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p]
     l.ref_cluster_kmeans.restype = C.c_int
     l.ref_cluster_kmeans.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_void_p]
+    l.ref_pq_train_subspace.restype = None
+    l.ref_pq_train_subspace.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int]
+    l.ref_pq_encode.restype = None; l.ref_pq_encode.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _i16p]
+    l.ref_pq_asymmetric_distance.restype = C.c_float
+    l.ref_pq_asymmetric_distance.argtypes = [_f32p, _i16p, _f32p, C.c_int, C.c_int, C.c_int]
     return l
 
 
@@ -489,3 +501,71 @@ def ref_cluster_kmeans(X, k, max_iters, seed):
     C.CDLL(None).srand(C.c_uint(seed))
     it = ref_leafs_lib().ref_cluster_kmeans(X, n, d, k, max_iters, labels, centers.ctypes.data)
     return labels, centers, it
+
+
+# ---- product quantisation (oracle/ndb_oracle_ml.c; ml_product_quantization.c) ------------------------------------
+def pq_train(X, m, ksub, draws, max_iters=100):
+    """train_pq_codebook's per-subspace k-means: codebooks [m][ksub][dsub]; draws = the m*ksub values of rand()."""
+    X = f32(X)
+    n, dim = X.shape
+    cb = np.zeros((m, ksub, dim // m), np.float32)
+    rc = lib().orc_pq_train(X, n, dim, m, ksub, np.ascontiguousarray(draws, np.int32), max_iters, cb.reshape(-1))
+    assert rc == 0
+    return cb
+
+
+def pq_encode(X, cb):
+    X = f32(X)
+    m, ksub, dsub = cb.shape
+    codes = np.zeros((len(X), m), np.int16)
+    lib().orc_pq_encode(X, len(X), X.shape[1], f32(cb).reshape(-1), m, ksub, codes.reshape(-1))
+    return codes
+
+
+def pq_knn(Q, codes, cb, k, want_all=False):
+    """(dist [nq,k], rows [nq,k], all distances or None): ORDER BY pq_asymmetric_distance LIMIT k, ties by row."""
+    Q = f32(Q)
+    m, ksub, dsub = cb.shape
+    codes = np.ascontiguousarray(codes, np.int16)
+    n = len(codes)
+    d, r = np.zeros((len(Q), k), np.float32), np.zeros((len(Q), k), np.int64)
+    al = np.zeros((len(Q), n), np.float32) if want_all else None
+    lib().orc_pq_knn(Q, len(Q), codes.reshape(-1), n, f32(cb).reshape(-1), m * dsub, m, ksub, k, d.reshape(-1), r.reshape(-1),
+                     None if al is None else al.ctypes.data)
+    return d, r, al
+
+
+def ref_pq_train(X, m, ksub, seed, max_iters=100):
+    """The reference's own train_subspace_kmeans per subspace after srand(seed), in train_pq_codebook's order."""
+    X = f32(X)
+    n, dim = X.shape
+    dsub = dim // m
+    cb = np.zeros((m, ksub, dsub), np.float32)
+    C.CDLL(None).srand(C.c_uint(seed))
+    for sub in range(m):
+        S = np.ascontiguousarray(X[:, sub * dsub:(sub + 1) * dsub])
+        ref_leafs_lib().ref_pq_train_subspace(S.reshape(-1), n, dsub, ksub, cb[sub].reshape(-1), max_iters)
+    return cb
+
+
+def ref_pq_encode(X, cb):
+    X = f32(X)
+    m, ksub, dsub = cb.shape
+    codes = np.zeros((len(X), m), np.int16)
+    flat = f32(cb).reshape(-1)
+    for i in range(len(X)):
+        ref_leafs_lib().ref_pq_encode(X[i], flat, m, ksub, dsub, codes[i])
+    return codes
+
+
+def ref_pq_distances(Q, codes, cb):
+    Q = f32(Q)
+    m, ksub, dsub = cb.shape
+    codes = np.ascontiguousarray(codes, np.int16)
+    flat = f32(cb).reshape(-1)
+    out = np.zeros((len(Q), len(codes)), np.float32)
+    f = ref_leafs_lib().ref_pq_asymmetric_distance
+    for j in range(len(Q)):
+        for i in range(len(codes)):
+            out[j, i] = f(Q[j], codes[i], flat, m, ksub, dsub)
+    return out

@@ -8,6 +8,7 @@ distances is unspecified in the reference itself)."""
 import numpy as np
 import pytest
 
+import oracle_lib as O
 import workloads as W
 
 pytestmark = pytest.mark.gpu
@@ -79,3 +80,37 @@ def test_knn_classify_errors_are_the_sql_functions(ndb):
     lab[:] = [i % 2 for i in range(20)]
     tie = ds.knn_classify(lab, X[:5], 20)                # 10 : 10 -> class 0 (strict majority for 1)
     assert tie.tolist() == [0] * 5
+
+
+def test_knn_classify_and_regress_equal_the_reference_outputs(ndb):
+    """tests/golden/ml_paths.npz: classes and means the reference's OWN KNNSample / euclidean_distance / compare_samples /
+    qsort produced (oracle/_ref/libndb_ref_leafs.so, written by tests/golden/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ml_paths.npz"))
+    for n, dim, k, seed in [(400, 8, 5, 3), (900, 33, 4, 7), (1500, 16, 12, 5), (60, 3, 6, 60)]:
+        X = W.mixture(n, dim, max(2, k // 2), seed)
+        Q = W.mixture(30, dim, 5, seed + 1, centers_seed=seed)
+        lab = np.random.default_rng(seed).integers(0, 3, n).astype(np.float64)
+        ds = ndb.Dataset(dim)
+        ds.append(X)
+        assert np.array_equal(ds.knn_classify(lab, Q, min(k, n)), g["knn_cls_n%d" % n])
+        assert np.array_equal(ds.knn_regress(lab, Q, min(k, n)), g["knn_mean_n%d" % n])
+
+
+def test_knn_order_is_the_order_of_the_doubles(ndb):
+    """Rows whose distances are distinct doubles but the same float: the reference sorts the doubles (KNNSample.distance),
+    so the neighbours are not the lowest row ids of the float tie."""
+    n_tied = 40
+    X = np.zeros((100, 2), np.float32)
+    X[:, 0] = 50.0 + np.arange(100)                                  # far rows
+    X[:n_tied, 0] = 1.0
+    X[:n_tied, 1] = (n_tied - np.arange(n_tied)) * 1e-6              # sqrt(1 + e^2): 1.0f for all of them, e decreasing with the row
+    q = np.zeros((1, 2), np.float32)
+    ds = ndb.Dataset(2)
+    ds.append(X, ids=np.arange(100, dtype=np.int64)[::-1] * 1000 + 7)   # labels follow the row position, not the id
+    targets = np.arange(100, dtype=np.float64)
+    assert ds.knn_regress(targets, q, 5)[0] == (39 + 38 + 37 + 36 + 35) / 5
+    lab = (np.arange(100) >= 37).astype(np.float64)                  # rows 37, 38, 39 vote 1, rows 35, 36 vote 0
+    assert ds.knn_classify(lab, q, 5)[0] == 1
+    cls, mean, rows = O.knn_ml(X, targets, q, 5)
+    assert rows[0].tolist() == [39, 38, 37, 36, 35]

@@ -421,3 +421,39 @@ def test_ml_golden_vectors():
         lab = rng.integers(0, 3, n).astype(np.float64)
         cls, mean, _ = O.knn_ml(X, lab, Q, min(k, n))
         assert np.array_equal(cls, g["knn_cls_" + tag]) and np.array_equal(mean, g["knn_mean_" + tag])
+
+
+# ---- product quantisation (oracle/ndb_oracle_ml.c) --------------------------------------------
+def _pq_cases():
+    return [(600, 16, 4, 16, 11), (900, 24, 8, 32, 12), (300, 12, 3, 256, 13), (50, 8, 8, 2, 14)]     # n, dim, m, ksub, seed
+
+
+@pytest.mark.skipif(O.ref_leafs_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_pq_equals_the_reference_functions():
+    """orc_pq_train / _encode / _asymmetric_distance against the reference's train_subspace_kmeans (ml_product_
+    quantization.c:80-190) and the text of the loops of pq_encode_vector (:479-503) and pq_asymmetric_distance
+    (:1063-1098), compiled from its source; rand() seeded alike."""
+    for n, dim, m, ksub, seed in _pq_cases():
+        X = W.mixture(n, dim, 6, seed)
+        Q = W.mixture(12, dim, 6, seed + 1, centers_seed=seed)
+        draws = O.libc_rand_draws(seed, m * ksub)
+        cb = O.pq_train(X, m, ksub, draws, 5)
+        assert np.array_equal(BITS(cb), BITS(O.ref_pq_train(X, m, ksub, seed, 5))), (n, dim, m, ksub)
+        codes = O.pq_encode(X, cb)
+        assert np.array_equal(codes, O.ref_pq_encode(X, cb))
+        d, r, al = O.pq_knn(Q, codes, cb, 5, want_all=True)
+        assert np.array_equal(BITS(al), BITS(O.ref_pq_distances(Q, codes, cb)))
+
+
+def test_pq_golden_vectors():
+    g = np.load(os.path.join(HERE, "golden", "ml_paths.npz"))
+    for n, dim, m, ksub, seed in _pq_cases():
+        tag = "pq%d" % n
+        X = W.mixture(n, dim, 6, seed)
+        Q = W.mixture(12, dim, 6, seed + 1, centers_seed=seed)
+        cb = O.pq_train(X, m, ksub, g["draws_" + tag], 5)
+        assert np.array_equal(BITS(cb), g["cb_bits_" + tag])
+        codes = O.pq_encode(X, cb)
+        assert np.array_equal(codes, g["codes_" + tag])
+        _, _, al = O.pq_knn(Q, codes, cb, 5, want_all=True)
+        assert np.array_equal(BITS(al), g["adc_bits_" + tag])
