@@ -5,8 +5,13 @@
 //   seeding : D^2 weight of a row = sum_f64 of (float)((x-c)*(x-c)) with a FLOAT difference and a FLOAT square (:64-74,
 //             :126-134); the next seed is the first unselected row at which r = rand()/RAND_MAX * sum, reduced by the
 //             weights IN ROW ORDER, reaches <= 0 (:85-101).  Both the sum and the walk are sequential fp64 chains whose
-//             rounding decides the row, so they stay sequential here: one thread walks tiles the block stages in
-//             shared memory.  The weights themselves (n*dim work per seed) are one thread per row.
+//             rounding decides the row.  They are NOT run sequentially in the common case: a parallel prefix sum of the
+//             weights gives every row's r within a proven distance (16 n 2^-53 of the total) of the value the
+//             sequential walk holds there, and the one row whose predecessor is above +eps and which itself is below
+//             -eps is the reference's pick (the walk's r never increases, so no earlier row can have stopped it).  Only
+//             when no row is that clear (r = 0, a total of 0, a crossing inside the band) does one thread walk the tiles
+//             the block stages in shared memory -- the literal loop.  The weights themselves (n*dim work per seed) are
+//             one thread per row.
 //   assign  : argmin_c neurondb_l2_distance_squared (util/neurondb_simd_impl.c:36-104, the build without AVX2: double
 //             difference, double square, double sum), strict <, lowest index wins (:236-259)
 //   update  : float sums over the members in row order / count, empty clusters end at zero (:261-281) -- this is
@@ -19,6 +24,8 @@
 // dimensions of its row in order).  Roofline of the assignment: 3 rounded fp64 instructions per (row, cluster,
 // dimension) -- fp64-issue bound like the operator scan (C1), not HBM bound (the transposed rows are re-read from L1/L2).
 #include <cfloat>
+#include <cstdlib>
+#include <cub/cub.cuh>
 
 #include "kmeans.cuh"
 
@@ -57,10 +64,36 @@ __global__ void __launch_bounds__(256) ckm_weight_kernel(const float *__restrict
     if (c == 0 || acc < dist[i]) dist[i] = acc;
 }
 
-// seed c: c == 0 -> draws[0] % n (:59); otherwise the D^2-weighted draw (:78-119).  One block.
+constexpr int CKM_NONE = 0x7f7f7f7f;
+
+__global__ void ckm_mask_kernel(const double *__restrict__ dist, const unsigned char *__restrict__ selected, int64_t n, double *__restrict__ w)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) w[i] = selected[i] ? 0.0 : dist[i];
+}
+
+// P = inclusive prefix sums of the masked weights (any association).  The sequential walk's r at row j and
+// q_j = r0 - P[j] differ by less than 8 n u T (u = 2^-53, T = the total), so a row with q_{i-1} >= eps and
+// q_i <= -eps, eps = 16 (n + 16) u T, is where the walk stops.  At most one row qualifies.
+__global__ void ckm_pick_cert_kernel(const double *__restrict__ P, const unsigned char *__restrict__ selected, int64_t n,
+                                     const int *__restrict__ draws, double rand_max, int c, double rel_eps, int *__restrict__ cert)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || selected[i]) return;
+    const double T = P[n - 1];
+    const double eps = rel_eps * T;
+    if (!(eps > 0.0)) return;
+    const double r0 = __dmul_rn(__ddiv_rn((double) draws[c], rand_max), T);
+    const double before = i > 0 ? P[i - 1] : 0.0;
+    if (r0 - before >= eps && P[i] - r0 >= eps) atomicMin(cert + c, (int) i);
+}
+
+// seed c: c == 0 -> draws[0] % n (:59); otherwise the D^2-weighted draw (:78-119): the certified row if there is one,
+// else the literal walk.  One block.
 constexpr int CKM_TILE = 4096;
 __global__ void __launch_bounds__(1024) ckm_pick_kernel(const double *__restrict__ dist, unsigned char *__restrict__ selected, int64_t n,
-                                                         const int *__restrict__ draws, double rand_max, int c, int *__restrict__ seeds)
+                                                         const int *__restrict__ draws, double rand_max, int c, int *__restrict__ seeds,
+                                                         const int *__restrict__ cert, unsigned long long *__restrict__ walked)
 {
     __shared__ double buf[CKM_TILE];
     __shared__ unsigned char sel[CKM_TILE];
@@ -74,6 +107,14 @@ __global__ void __launch_bounds__(1024) ckm_pick_kernel(const double *__restrict
         }
         return;
     }
+    if (cert && cert[c] != CKM_NONE) {
+        if (threadIdx.x == 0) {
+            seeds[c] = cert[c];
+            selected[cert[c]] = 1;
+        }
+        return;
+    }
+    if (threadIdx.x == 0 && walked) atomicAdd(walked, 1ull);
     // sum of the unselected weights in row order (adding 0.0 for a selected row leaves a non-negative sum unchanged)
     double sum = 0.0;
     for (int64_t base = 0; base < n; base += CKM_TILE) {
@@ -160,6 +201,17 @@ __global__ void __launch_bounds__(128) ckm_assign_kernel(const float *__restrict
     }
 }
 
+// host rows -> device, NaN / Inf scan on the device (the 2 * dim tests per row of the reference's check, off the host)
+int upload_rows_checked(DevBuf &dst, const float *X, size_t count, const char *who, cudaStream_t s)
+{
+    NDB_CHECK(dst.reserve(count * sizeof(float)));
+    NDB_CUDA(cudaMemcpyAsync(dst.p, X, count * sizeof(float), cudaMemcpyHostToDevice, s));
+    NDB_CHECK(validate_begin(dst.as<float>(), (int64_t) count, s));
+    NDB_CUDA(cudaStreamSynchronize(s));
+    NDB_REQUIRE(validate_end() < 0, NDB_B200_EVECTOR, "%s: NaN/Inf in the vectors", who);
+    return NDB_B200_OK;
+}
+
 int transpose_rows_dev(const float *dX, int64_t n, int dim, float *dXT, cudaStream_t s)
 {
     ckm_transpose_kernel<<<dim3((unsigned) ((n + 31) / 32), (unsigned) ((dim + 31) / 32)), dim3(32, 8), 0, s>>>(dX, n, dim, dXT);
@@ -218,28 +270,48 @@ int ndb_b200_cluster_kmeans(const float *X, int n, int dim, int k, int max_iters
     NDB_REQUIRE(n >= k, NDB_B200_EINVAL, "not enough vectors for cluster count (need >= %d, have %d)", k, n);           // :180-186
     for (int c = 0; c < k; c++) NDB_REQUIRE(rand_draws[c] >= 0, NDB_B200_EINVAL, "cluster_kmeans: rand() values are non-negative");
     if (max_iters < 1) max_iters = 100;                                                                                 // :175-176
-    NDB_REQUIRE(find_nonfinite(X, (int64_t) n * dim) < 0, NDB_B200_EVECTOR, "cluster_kmeans: NaN/Inf in the vectors");
     cudaStream_t s = ctx().stream;
     KMeansWork w;
     DevBuf XT, dist, selected, dseeds, ddraws, dchanged;
     const size_t xb = (size_t) n * dim * 4, cb = (size_t) k * dim * 4;
-    NDB_CHECK(w.X.reserve(xb)); NDB_CHECK(XT.reserve(xb)); NDB_CHECK(w.C.reserve(cb));
+    NDB_CHECK(upload_rows_checked(w.X, X, (size_t) n * dim, "cluster_kmeans", s));
+    NDB_CHECK(XT.reserve(xb)); NDB_CHECK(w.C.reserve(cb));
     NDB_CHECK(w.assign.reserve((size_t) n * 4)); NDB_CHECK(w.counts.reserve((size_t) k * 4));
     NDB_CHECK(dist.reserve((size_t) n * 8)); NDB_CHECK(selected.reserve((size_t) n));
     NDB_CHECK(dseeds.reserve((size_t) k * 4)); NDB_CHECK(ddraws.reserve((size_t) k * 4)); NDB_CHECK(dchanged.reserve(4));
-    NDB_CUDA(cudaMemcpyAsync(w.X.p, X, xb, cudaMemcpyHostToDevice, s));
     NDB_CUDA(cudaMemcpyAsync(ddraws.p, rand_draws, (size_t) k * 4, cudaMemcpyHostToDevice, s));
     NDB_CUDA(cudaMemsetAsync(selected.p, 0, (size_t) n, s));
     const float *dX = w.X.as<float>();
     NDB_CHECK(transpose_rows_dev(dX, n, dim, XT.as<float>(), s));
     const unsigned rb = (unsigned) ((n + 255) / 256);
+    const bool literal_walk = getenv("NDB_CKM_SEQUENTIAL") != nullptr;       // (test / measurement switch: always the literal loop)
+    DevBuf masked, prefix, cert, cub_tmp, walked;
+    size_t tmp_bytes = 0;
+    NDB_CHECK(walked.reserve(8));
+    NDB_CUDA(cudaMemsetAsync(walked.p, 0, 8, s));
+    if (!literal_walk) {
+        NDB_CHECK(masked.reserve((size_t) n * 8)); NDB_CHECK(prefix.reserve((size_t) n * 8)); NDB_CHECK(cert.reserve((size_t) k * 4));
+        NDB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, masked.as<double>(), prefix.as<double>(), n, s));
+        NDB_CHECK(cub_tmp.reserve(tmp_bytes));
+        NDB_CUDA(cudaMemsetAsync(cert.p, 0x7f, (size_t) k * 4, s));
+    }
+    const double rel_eps = 16.0 * (double) (n + 16) * 1.1102230246251565e-16;
     for (int c = 0; c < k; c++) {
+        if (c > 0 && !literal_walk) {
+            ckm_mask_kernel<<<rb, 256, 0, s>>>(dist.as<double>(), selected.as<unsigned char>(), n, masked.as<double>());
+            NDB_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp.p, tmp_bytes, masked.as<double>(), prefix.as<double>(), n, s));
+            ckm_pick_cert_kernel<<<rb, 256, 0, s>>>(prefix.as<double>(), selected.as<unsigned char>(), n, ddraws.as<int>(), (double) rand_max, c,
+                                                  rel_eps, cert.as<int>());
+            count_launch(4);
+        }
         ckm_pick_kernel<<<1, 1024, 0, s>>>(dist.as<double>(), selected.as<unsigned char>(), n, ddraws.as<int>(), (double) rand_max, c,
-                                          dseeds.as<int>());
+                                          dseeds.as<int>(), literal_walk ? nullptr : cert.as<int>(), walked.as<unsigned long long>());
         if (c + 1 < k)            // the weights against the last seed are never read (:121-135 computes them all the same)
             ckm_weight_kernel<<<rb, 256, 0, s>>>(XT.as<float>(), dX, n, dim, dseeds.as<int>(), c, dist.as<double>());
         count_launch(2);
     }
+    unsigned long long n_walked = 0;
+    NDB_CUDA(cudaMemcpyAsync(&n_walked, walked.p, 8, cudaMemcpyDeviceToHost, s));
     NDB_CHECK(gather_rows_dev(dX, dseeds.as<int>(), k, dim, w.C.as<float>(), s));
     NDB_CUDA(cudaMemsetAsync(w.assign.p, 0xff, (size_t) n * 4, s));                                                    // assignments[i] = -1 (:206-207)
     int iter = 0;
@@ -248,6 +320,8 @@ int ndb_b200_cluster_kmeans(const float *X, int n, int dim, int k, int max_iters
     if (centers) NDB_CUDA(cudaMemcpyAsync(centers, w.C.p, cb, cudaMemcpyDeviceToHost, s));
     if (seeds) NDB_CUDA(cudaMemcpyAsync(seeds, dseeds.p, (size_t) k * 4, cudaMemcpyDeviceToHost, s));
     NDB_CUDA(cudaStreamSynchronize(s));
+    ctx().last_ms = 0.0; ctx().last_bytes = 0.0; ctx().stats_src = nullptr;
+    ctx().last_evals = (int64_t) n_walked;                 // ndb_b200_last_kernel_stats: seeds that needed the literal walk
     for (int i = 0; i < n; i++) labels[i] += 1;                                                                        // 1-based labels (:286)
     if (iters) *iters = iter;
     return NDB_B200_OK;

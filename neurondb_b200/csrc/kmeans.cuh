@@ -48,6 +48,7 @@ int kmeans_run_dev(KMeansWork &w, int n, int d, int k, int max_iter, float tol, 
 // ---- fp64 Lloyd (cluster_kmeans.cu): the arithmetic of cluster_kmeans (ml_kmeans.c:226-278) and train_subspace_kmeans
 // (ml_product_quantization.c:108-186): double difference / square / sum, strict <, lowest index wins; ordered float update.
 // dXT = the rows transposed ([dim][n], row stride n).  w.C holds the k*dim centres, w.assign the current assignment.
+int upload_rows_checked(DevBuf &dst, const float *X, size_t count, const char *who, cudaStream_t s);
 int transpose_rows_dev(const float *dX, int64_t n, int dim, float *dXT, cudaStream_t s);
 int gather_rows_dev(const float *dX, const int *rows_dev, int nrows, int dim, float *out, cudaStream_t s);
 int nearest_f64_dev(const float *dXT, const float *dC, int64_t n, int dim, int k, int *assign, int *changed, cudaStream_t s);

@@ -232,17 +232,16 @@ int ndb_b200_pq_train(const float *X, int n, int dim, int m, int ksub, int max_i
     NDB_REQUIRE(X && rand_draws && codebooks, NDB_B200_EINVAL, "pq_train: NULL argument");
     NDB_CHECK(pq_check_shape(dim, m, ksub, "pq_train"));
     NDB_REQUIRE(n > 0, NDB_B200_EINVAL, "No training vectors found");                                                          // :243-249
-    NDB_REQUIRE(find_nonfinite(X, (int64_t) n * dim) < 0, NDB_B200_EVECTOR, "pq_train: NaN/Inf in the vectors");
     if (max_iters < 0) max_iters = 100;                                                                                        // the reference passes 100 (:340-346)
     const int dsub = dim / m;
     cudaStream_t s = ctx().stream;
     KMeansWork w;
     DevBuf X_all, XT, dseeds, dchanged, dcb;
     const size_t xb = (size_t) n * dim * 4, sb = (size_t) n * dsub * 4;
-    NDB_CHECK(X_all.reserve(xb)); NDB_CHECK(XT.reserve(xb)); NDB_CHECK(w.X.reserve(sb)); NDB_CHECK(w.C.reserve((size_t) ksub * dsub * 4));
+    NDB_CHECK(upload_rows_checked(X_all, X, (size_t) n * dim, "pq_train", s));
+    NDB_CHECK(XT.reserve(xb)); NDB_CHECK(w.X.reserve(sb)); NDB_CHECK(w.C.reserve((size_t) ksub * dsub * 4));
     NDB_CHECK(w.assign.reserve((size_t) n * 4)); NDB_CHECK(w.counts.reserve((size_t) ksub * 4));
     NDB_CHECK(dseeds.reserve((size_t) ksub * 4)); NDB_CHECK(dchanged.reserve(4)); NDB_CHECK(dcb.reserve((size_t) m * ksub * dsub * 4));
-    NDB_CUDA(cudaMemcpyAsync(X_all.p, X, xb, cudaMemcpyHostToDevice, s));
     NDB_CHECK(transpose_rows_dev(X_all.as<float>(), n, dim, XT.as<float>(), s));
     std::vector<int> seeds(ksub);
     for (int sub = 0; sub < m; sub++) {
@@ -274,13 +273,12 @@ static int pq_encode_host(const float *X, int64_t n, int dim, const float *codeb
     NDB_CHECK(pq_check_shape(dim, m, ksub, "pq_encode"));
     NDB_REQUIRE(!codes8 || ksub <= 256, NDB_B200_EINVAL, "pq_encode: byte codes need ksub <= 256");
     NDB_REQUIRE(!codes16 || ksub <= 32768, NDB_B200_EINVAL, "pq_encode: int2 codes need ksub <= 32768");
-    NDB_REQUIRE(find_nonfinite(X, n * dim) < 0, NDB_B200_EVECTOR, "pq_encode: NaN/Inf in the vectors");
     cudaStream_t s = ctx().stream;
     DevBuf dX, dXT, dcb, dassign, dchanged, dcodes;
     const size_t xb = (size_t) n * dim * 4, cbb = (size_t) m * ksub * (dim / m) * 4, ob = (size_t) n * m * (codes8 ? 1 : 2);
-    NDB_CHECK(dX.reserve(xb)); NDB_CHECK(dXT.reserve(xb)); NDB_CHECK(dcb.reserve(cbb)); NDB_CHECK(dassign.reserve((size_t) n * 4));
+    NDB_CHECK(upload_rows_checked(dX, X, (size_t) n * dim, "pq_encode", s));
+    NDB_CHECK(dXT.reserve(xb)); NDB_CHECK(dcb.reserve(cbb)); NDB_CHECK(dassign.reserve((size_t) n * 4));
     NDB_CHECK(dchanged.reserve(4)); NDB_CHECK(dcodes.reserve(ob));
-    NDB_CUDA(cudaMemcpyAsync(dX.p, X, xb, cudaMemcpyHostToDevice, s));
     NDB_CUDA(cudaMemcpyAsync(dcb.p, codebooks, cbb, cudaMemcpyHostToDevice, s));
     NDB_CHECK(transpose_rows_dev(dX.as<float>(), n, dim, dXT.as<float>(), s));
     NDB_CUDA(cudaMemsetAsync(dassign.p, 0xff, (size_t) n * 4, s));
@@ -332,14 +330,13 @@ int ndb_b200_pq_add(ndb_b200_pq *pq, const float *X, int64_t n, int16_t *codes_o
     NDB_CHECK(require_init());
     NDB_REQUIRE(pq && X && n > 0, NDB_B200_EINVAL, "pq_add: NULL or empty argument");
     NDB_REQUIRE(pq->n + n < (int64_t) 0xfffffff0ll, NDB_B200_EINVAL, "pq_add: too many rows for 32-bit slots");
-    NDB_REQUIRE(find_nonfinite(X, n * pq->dim) < 0, NDB_B200_EVECTOR, "pq_add: NaN/Inf in the vectors");
     cudaStream_t s = ctx().stream;
     DevBuf dX, dXT, dassign, dchanged, d16;
     const size_t xb = (size_t) n * pq->dim * 4;
-    NDB_CHECK(dX.reserve(xb)); NDB_CHECK(dXT.reserve(xb)); NDB_CHECK(dassign.reserve((size_t) n * 4)); NDB_CHECK(dchanged.reserve(4));
+    NDB_CHECK(upload_rows_checked(dX, X, (size_t) n * pq->dim, "pq_add", s));
+    NDB_CHECK(dXT.reserve(xb)); NDB_CHECK(dassign.reserve((size_t) n * 4)); NDB_CHECK(dchanged.reserve(4));
     if (codes_out) NDB_CHECK(d16.reserve((size_t) n * pq->m * 2));
     NDB_CHECK(pq->codes.grow((size_t) (pq->n + n) * pq->m, (size_t) pq->n * pq->m, s));
-    NDB_CUDA(cudaMemcpyAsync(dX.p, X, xb, cudaMemcpyHostToDevice, s));
     NDB_CHECK(transpose_rows_dev(dX.as<float>(), n, pq->dim, dXT.as<float>(), s));
     NDB_CUDA(cudaMemsetAsync(dassign.p, 0xff, (size_t) n * 4, s));
     NDB_CHECK(pq_encode_dev(dXT.as<float>(), n, pq->dim, pq->codebooks.as<float>(), pq->m, pq->ksub, dassign.as<int>(), dchanged.as<int>(),

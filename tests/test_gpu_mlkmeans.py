@@ -60,3 +60,25 @@ def test_cluster_kmeans_errors_are_the_sql_functions(ndb):
     with pytest.raises(ndb.NdbError) as e:
         ndb.cluster_kmeans(bad, 2, 5, d[:2])
     assert e.value.code == -4
+
+
+def test_cluster_kmeans_certified_pick_equals_the_literal_walk(ndb):
+    """The D^2-weighted draw is normally read off a parallel prefix sum with a certificate; NDB_CKM_SEQUENTIAL forces the
+    reference's loop (one thread, row order) for every seed.  Same seeds, labels and centres either way, and the default
+    path needs the walk only where the certificate cannot hold (r = 0: the draw of 0 below)."""
+    n, dim, k = 30000, 12, 24
+    X = W.mixture(n, dim, 8, 99)
+    draws = np.random.default_rng(99).integers(0, O.RAND_MAX, k, dtype=np.int64).astype(np.int32)
+    draws[5] = 0
+    want = O.cluster_kmeans(X, k, 3, draws)
+    got = ndb.cluster_kmeans(X, k, 3, draws)
+    walked = ndb.last_kernel_stats()[2]
+    os.environ["NDB_CKM_SEQUENTIAL"] = "1"
+    try:
+        lit = ndb.cluster_kmeans(X, k, 3, draws)
+        walked_lit = ndb.last_kernel_stats()[2]
+    finally:
+        del os.environ["NDB_CKM_SEQUENTIAL"]
+    for a, b, c in zip(want, got, lit):
+        assert np.array_equal(np.asarray(a), np.asarray(b)) and np.array_equal(np.asarray(a), np.asarray(c))
+    assert walked_lit == k - 1 and 1 <= walked <= 3
