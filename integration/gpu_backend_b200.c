@@ -112,7 +112,13 @@ b200_launch_kmeans_update(const float *X, const int *idx, float *C, int n, int d
 	return ndb_b200_launch_kmeans_update(X, idx, C, n, d, k, (void *) stream);
 }
 
-/* Members not named stay NULL: quantisation, PQ and the ML trainers are outside this path, and the
+static int
+b200_launch_pq_encode(const float *X, const float *codebooks, uint8_t *codes, int n, int d, int m, int ks, ndb_stream_t stream)
+{
+	return ndb_b200_launch_pq_encode(X, codebooks, codes, n, d, m, ks, (void *) stream);
+}
+
+/* Members not named stay NULL: scalar quantisation and the ML trainers are outside this path, and the
  * registry's callers treat a NULL launcher as "not supported by this backend". */
 static const ndb_gpu_backend ndb_b200_backend = {
 	.name = "b200",
@@ -134,6 +140,7 @@ static const ndb_gpu_backend ndb_b200_backend = {
 	.launch_cosine = b200_launch_cosine,
 	.launch_kmeans_assign = b200_launch_kmeans_assign,
 	.launch_kmeans_update = b200_launch_kmeans_update,
+	.launch_pq_encode = b200_launch_pq_encode,
 	.stream_create = b200_stream_create,
 	.stream_destroy = b200_stream_destroy,
 	.stream_synchronize = b200_stream_synchronize,
@@ -216,6 +223,10 @@ int ndb_b200_glue_kmeans_update(const float *X, const int *idx, float *C, int n,
 {
 	return glue_active()->launch_kmeans_update(X, idx, C, n, d, k, NULL);
 }
+int ndb_b200_glue_pq_encode(const float *X, const float *codebooks, uint8_t *codes, int n, int d, int m, int ks)
+{
+	return glue_active()->launch_pq_encode(X, codebooks, codes, n, d, m, ks, NULL);
+}
 int ndb_b200_glue_stream_roundtrip(void)
 {
 	ndb_stream_t s = NULL;
@@ -231,6 +242,6 @@ int ndb_b200_glue_unsupported_members_are_null(void)
 {
 	const ndb_gpu_backend *b = glue_active();
 
-	return b->launch_quant_fp16 == NULL && b->launch_pq_encode == NULL && b->rf_train == NULL;
+	return b->launch_quant_fp16 == NULL && b->launch_quant_binary == NULL && b->rf_train == NULL;
 }
 #endif

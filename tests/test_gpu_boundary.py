@@ -61,6 +61,11 @@ def test_launchers_through_the_backend_struct(ndb, orc, glue):
     C2 = np.zeros((8, 16), np.float32)
     assert glue.ndb_b200_glue_kmeans_update(p(X), p(idx), p(C2), 3000, 16, 8) == 0
     assert np.array_equal(BITS(C2), BITS(orc.kmeans_update(X, idx, 8)[0]))
+    # launch_pq_encode through the struct == pq_encode_vector's loop (byte codes)
+    cb = W.gaussian(4 * 16, 4, 7).reshape(4, 16, 4)
+    codes = np.zeros((3000, 4), np.uint8)
+    assert glue.ndb_b200_glue_pq_encode(p(X), p(cb), p(codes), 3000, 16, 4, 16) == 0
+    assert np.array_equal(codes.astype(np.int16), orc.pq_encode(X, cb))
     assert glue.ndb_b200_glue_stream_roundtrip() == 0
     name = C.create_string_buffer(256)
     total, major = C.c_size_t(), C.c_int()
