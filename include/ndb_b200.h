@@ -203,6 +203,28 @@ int ndb_b200_pq_search(ndb_b200_pq *pq, const float *Q, int nq, int k, float *di
 int ndb_b200_pq_search_dev(ndb_b200_pq *pq, const float *Q_dev, int nq, int k, float *dist_dev, int64_t *rows_dev, void *stream);
 int ndb_b200_pq_distances(ndb_b200_pq *pq, const float *Q, int nq, float *dist, unsigned long long *rechecked);
 
+/* ---- per-vector quantisers (src/types/quantization.c) for n rows at once, and the Hamming scan over binary rows.
+ *      out receives the data[] bytes of the varlena each function builds, rows packed (ndb_b200_quantized_row_bytes each):
+ *      INT8    quantize_vector_i8 :42-86 (rintf(x * 127 / max|x|), zero row -> zeros)
+ *      FP16    quantize_vector_f16 :220-236 / float4_to_fp16 :141-168 (mantissa truncated, subnormals flushed, overflow -> inf)
+ *      BINARY  quantize_vector_binary :284-312 (bit i%8 of byte i/8 = x > 0)
+ *      UINT8   quantize_vector_uint8 :1354-1402 (rintf((x - min) * 255 / (max - min)), constant row -> zeros)
+ *      TERNARY quantize_vector_ternary :1455-1503 (2 bits per dimension against max|x| / 3)
+ *      INT4    quantize_vector_int4 :1562-1641 (nibble 8 + rintf(x * 7 / max|x|), low nibble first, zero row -> zero bytes)
+ *      Bit-identical to those functions.  (The backend's launch_quant_* members are NOT bound to these: the reference's CUDA
+ *      kernels behind them round where the SQL functions truncate, take a caller-supplied scale, and so define other results.) */
+#define NDB_QUANT_INT8    1
+#define NDB_QUANT_FP16    2
+#define NDB_QUANT_BINARY  3
+#define NDB_QUANT_UINT8   4
+#define NDB_QUANT_TERNARY 5
+#define NDB_QUANT_INT4    6
+int64_t ndb_b200_quantized_row_bytes(int kind, int dim);
+int ndb_b200_quantize_rows(int kind, const float *X, int64_t n, int dim, void *out);
+/* ORDER BY binary_hamming_distance(bits, q) LIMIT k (:385-427): rows / Q are (nbits+7)/8 bytes each; the k nearest rows
+ * by (distance, row index); -1 / -1 past the end. */
+int ndb_b200_hamming_knn(const uint8_t *rows, int64_t n, int nbits, const uint8_t *Q, int nq, int k, int32_t *dist, int64_t *ids);
+
 /* ---- IVF k-means: kmeans_init/run/assign/update_centroids/compute_cost
  *      (src/index/ivf_am.c:2070-2294).  Literal semantics: centroids := first k rows,
  *      <= max_iter Lloyd steps, stop when |prevCost - cost| < tol, f32 sequential sums.

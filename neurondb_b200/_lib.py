@@ -16,6 +16,7 @@ L2, COSINE, IP = 1, 2, 3
 ARITH_OP_F64, ARITH_IVF_F32, ARITH_HNSW, ARITH_FAST, ARITH_TENSOR = 0, 3, 4, 5, 6
 ARITH_AVX2, ARITH_AVX512 = 1, 2
 IVF_FULL, IVF_LITERAL = 0, 1
+QUANT_INT8, QUANT_FP16, QUANT_BINARY, QUANT_UINT8, QUANT_TERNARY, QUANT_INT4 = 1, 2, 3, 4, 5, 6
 HNSW_LITERAL, HNSW_BESTFIRST = 0, 1
 HNSW_SELECT_CLOSEST, HNSW_SELECT_HEURISTIC = 0, 1
 
@@ -71,6 +72,9 @@ SIGNATURES = {
     "ndb_b200_knn_classify": (_i, [_p, _p, _p, _i, _i, _p]),
     "ndb_b200_knn_regress": (_i, [_p, _p, _p, _i, _i, _p]),
     "ndb_b200_cluster_kmeans": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
+    "ndb_b200_quantized_row_bytes": (_i64, [_i, _i]),
+    "ndb_b200_quantize_rows": (_i, [_i, _p, _i64, _i, _p]),
+    "ndb_b200_hamming_knn": (_i, [_p, _i64, _i, _p, _i, _i, _p, _p]),
     "ndb_b200_pq_train": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "ndb_b200_pq_encode": (_i, [_p, _i64, _i, _p, _i, _i, _p]),
     "ndb_b200_launch_pq_encode": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),

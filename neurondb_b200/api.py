@@ -12,7 +12,8 @@ from . import _lib as L
 from ._lib import (ARITH_AVX2, ARITH_AVX512, ARITH_FAST, ARITH_HNSW, ARITH_IVF_F32, ARITH_OP_F64, ARITH_TENSOR, COSINE,
                    HNSW_BESTFIRST, HNSW_LITERAL,
                    HNSW_SELECT_CLOSEST, HNSW_SELECT_HEURISTIC, IP,
-                   IVF_FULL, IVF_LITERAL, L2, NdbError, check, f32, ptr)
+                   IVF_FULL, IVF_LITERAL, L2, NdbError, check, f32, ptr,
+                   QUANT_BINARY, QUANT_FP16, QUANT_INT4, QUANT_INT8, QUANT_TERNARY, QUANT_UINT8)
 
 _initialised = {"device": None}
 
@@ -288,6 +289,32 @@ class _Handle:
             self.close()
         except Exception:
             pass
+
+
+def quantize_rows(kind, X):
+    """quantize_vector_i8 / _f16 / _binary / _uint8 / _ternary / _int4 (src/types/quantization.c) per row: uint8 [n][row_bytes]."""
+    X = f32(X)
+    if X.ndim != 2:
+        raise L.NdbError(-1, "quantize_rows: a 2-d array of rows expected")
+    n, dim = X.shape
+    rb = int(L.load().ndb_b200_quantized_row_bytes(kind, dim))
+    if rb <= 0:
+        raise L.NdbError(-1, "quantize_rows: unknown kind %d" % kind)
+    out = np.zeros((n, rb), np.uint8)
+    check(L.load().ndb_b200_quantize_rows(kind, ptr(X), n, dim, ptr(out)))
+    return out
+
+
+def hamming_knn(rows, nbits, Q, k):
+    """ORDER BY binary_hamming_distance(bits, q) LIMIT k: (dist int32 [nq][k], rows int64 [nq][k])."""
+    rows, Q = np.ascontiguousarray(rows, np.uint8), np.ascontiguousarray(Q, np.uint8)
+    nbytes = (nbits + 7) // 8
+    if rows.ndim != 2 or Q.ndim != 2 or rows.shape[1] != nbytes or Q.shape[1] != nbytes:
+        raise L.NdbError(-5, "binary vector dimensions must match")
+    d = np.empty((Q.shape[0], k), np.int32)
+    i = np.empty((Q.shape[0], k), np.int64)
+    check(L.load().ndb_b200_hamming_knn(ptr(rows), rows.shape[0], nbits, ptr(Q), Q.shape[0], k, ptr(d), ptr(i)))
+    return d, i
 
 
 def _pq_shape(cb):

@@ -20,6 +20,7 @@
 
 #include "kmeans.cuh"
 #include "scan.cuh"
+#include "block_topk.cuh"
 
 namespace ndb {
 
@@ -139,30 +140,8 @@ __global__ void __launch_bounds__(256) pq_adc_kernel(const float *__restrict__ Q
         if (KR > 0) top.offer(f, (uint32_t) row, valid, lane, k);
     }
     if (KR > 0) {
-        // the block's warps hold one list each: merge them through shared memory (the table is no longer needed)
-        __syncthreads();
-        float *sd = reinterpret_cast<float *>(lut);
-        uint32_t *ss = reinterpret_cast<uint32_t *>(sd + nwarps * KR * 32);
-#pragma unroll
-        for (int r = 0; r < KR; r++) {
-            sd[(warp * KR + r) * 32 + lane] = top.d[r];
-            ss[(warp * KR + r) * 32 + lane] = top.key[r];
-        }
-        __syncthreads();
-        if (warp == 0) {
-            for (int w = 1; w < nwarps; w++)
-                for (int r = 0; r < KR; r++) {
-                    const float cd = sd[(w * KR + r) * 32 + lane];
-                    const uint32_t ck = ss[(w * KR + r) * 32 + lane];
-                    top.offer(cd, ck, ck != INVALID_SLOT, lane, k);
-                }
-            const size_t ob = ((size_t) qi * gridDim.x + part) * k;
-#pragma unroll
-            for (int r = 0; r < KR; r++) {
-                const int e = r * 32 + lane;
-                if (e < k) { pdist[ob + e] = top.d[r]; pslot[ob + e] = top.key[r]; }
-            }
-        }
+        __syncthreads();                               // the table is no longer needed: its memory carries the merge
+        block_topk_write<(KR > 0 ? KR : 1)>(top, lut, warp, lane, nwarps, k, pdist, pslot, ((size_t) qi * gridDim.x + part) * k);
     }
 }
 

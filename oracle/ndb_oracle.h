@@ -168,6 +168,13 @@ float orc_pq_asymmetric_distance(const float *q, const int16_t *codes, const flo
 void orc_pq_knn(const float *Q, int nq, const int16_t *codes, int64_t n, const float *codebooks, int dim, int m, int ksub, int k,
                 float *dist, int64_t *rows, float *dist_all);
 
+/* per-vector quantisers and the Hamming scan (src/types/quantization.c); kinds 1 int8, 2 fp16, 3 binary, 4 uint8, 5 ternary, 6 int4 */
+int64_t orc_quantized_row_bytes(int kind, int dim);
+void orc_quantize_row(int kind, const float *v, int dim, uint8_t *out);
+void orc_quantize_rows(int kind, const float *X, int64_t n, int dim, uint8_t *out);
+int orc_hamming(const uint8_t *a, const uint8_t *b, int nbits);
+void orc_hamming_knn(const uint8_t *rows, int64_t n, int nbits, const uint8_t *Q, int nq, int k, int32_t *dist, int64_t *ids);
+
 /* sizes / field offsets used by the relation encoders (ndb_oracle_pages.c), in the order of the
  * reference-side ref_layout() built by oracle/extract_ref_leafs.py; returns the count */
 int orc_page_layout(int64_t *out);

@@ -289,3 +289,130 @@ void orc_pq_knn(const float *Q, int nq, const int16_t *codes, int64_t n, const f
         free(h);
     }
 }
+
+/* ---- per-vector quantisers: NeuronDB/src/types/quantization.c ---------------------------------------
+ * quantize_vector_i8 :42-86, float4_to_fp16 :141-168 / quantize_vector_f16 :220-236, quantize_vector_binary :284-312,
+ * binary_hamming_distance :385-427, quantize_vector_uint8 :1354-1402, quantize_vector_ternary :1455-1503,
+ * quantize_vector_int4 :1562-1641 (the CPU branch).  Output = the data[] bytes of the varlena, rows packed.
+ * PINNED against those functions compiled from the reference source (oracle/extract_ref_leafs.py). */
+enum { ORC_Q_INT8 = 1, ORC_Q_FP16 = 2, ORC_Q_BINARY = 3, ORC_Q_UINT8 = 4, ORC_Q_TERNARY = 5, ORC_Q_INT4 = 6 };
+
+int64_t orc_quantized_row_bytes(int kind, int dim)
+{
+    switch (kind) {
+    case ORC_Q_INT8: case ORC_Q_UINT8: return dim;
+    case ORC_Q_FP16: return 2 * (int64_t) dim;
+    case ORC_Q_BINARY: return (dim + 7) / 8;
+    case ORC_Q_TERNARY: return (dim * 2 + 7) / 8;
+    case ORC_Q_INT4: return (dim + 1) / 2;
+    }
+    return -1;
+}
+
+static uint16_t orc_float_to_fp16(float f)            /* :141-168: truncates the mantissa, flushes subnormals, NaN -> inf */
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    uint16_t sign = (u >> 16) & 0x8000;
+    uint32_t mantissa = u & 0x7fffff;
+    int16_t exp = (int16_t) (((u >> 23) & 0xff) - 127 + 15);
+    if (exp <= 0) return sign;
+    if (exp >= 31) return sign | 0x7c00;
+    return (uint16_t) (sign | (exp << 10) | (mantissa >> 13));
+}
+
+void orc_quantize_row(int kind, const float *v, int dim, uint8_t *out)
+{
+    int i;
+    memset(out, 0, (size_t) orc_quantized_row_bytes(kind, dim));
+    if (kind == ORC_Q_INT8) {
+        float max_abs = 0.0f;
+        for (i = 0; i < dim; i++) { float a = fabsf(v[i]); if (a > max_abs) max_abs = a; }
+        if (max_abs == 0.0f) return;
+        float scale = 127.0f / max_abs;
+        for (i = 0; i < dim; i++) {
+            float val = v[i] * scale;
+            if (val > 127.0f) val = 127.0f;
+            if (val < -128.0f) val = -128.0f;
+            ((int8_t *) out)[i] = (int8_t) rintf(val);
+        }
+    } else if (kind == ORC_Q_FP16) {
+        for (i = 0; i < dim; i++) { uint16_t h = orc_float_to_fp16(v[i]); memcpy(out + 2 * i, &h, 2); }
+    } else if (kind == ORC_Q_BINARY) {
+        for (i = 0; i < dim; i++) if (v[i] > 0.0f) out[i / 8] |= (uint8_t) (1 << (i % 8));
+    } else if (kind == ORC_Q_UINT8) {
+        float mn = 0.0f, mx = 0.0f;
+        for (i = 0; i < dim; i++) {
+            if (i == 0) mn = mx = v[i];
+            else { if (v[i] < mn) mn = v[i]; if (v[i] > mx) mx = v[i]; }
+        }
+        if (mx == mn) return;
+        float scale = 255.0f / (mx - mn);
+        for (i = 0; i < dim; i++) {
+            float nv = (v[i] - mn) * scale;
+            if (nv > 255.0f) nv = 255.0f;
+            if (nv < 0.0f) nv = 0.0f;
+            out[i] = (uint8_t) rintf(nv);
+        }
+    } else if (kind == ORC_Q_TERNARY) {
+        float max_abs = 0.0f;
+        for (i = 0; i < dim; i++) { float a = fabsf(v[i]); if (a > max_abs) max_abs = a; }
+        float threshold = max_abs / 3.0f;
+        for (i = 0; i < dim; i++) {
+            uint8_t value = v[i] > threshold ? 2 : (v[i] < -threshold ? 1 : 0);
+            out[(i * 2) / 8] |= (uint8_t) (value << ((i * 2) % 8));
+        }
+    } else if (kind == ORC_Q_INT4) {
+        float max_abs = 0.0f;
+        for (i = 0; i < dim; i++) { float a = fabsf(v[i]); if (a > max_abs) max_abs = a; }
+        if (max_abs == 0.0f) return;
+        float scale = 7.0f / max_abs;
+        for (i = 0; i < dim; i++) {
+            int8_t value;
+            float scaled = v[i] * scale;
+            if (scaled > 7.0f) value = 7;
+            else if (scaled < -8.0f) value = -8;
+            else value = (int8_t) rintf(scaled);
+            uint8_t uvalue = (uint8_t) (8 + value);
+            if (uvalue > 15) uvalue = 15;
+            out[i / 2] |= (uint8_t) (uvalue << ((i % 2) * 4));
+        }
+    }
+}
+
+void orc_quantize_rows(int kind, const float *X, int64_t n, int dim, uint8_t *out)
+{
+    int64_t rb = orc_quantized_row_bytes(kind, dim);
+    for (int64_t i = 0; i < n; i++) orc_quantize_row(kind, X + (size_t) i * dim, dim, out + (size_t) i * rb);
+}
+
+int orc_hamming(const uint8_t *a, const uint8_t *b, int nbits)                     /* :409-424 */
+{
+    int count = 0, nbytes = (nbits + 7) / 8;
+    for (int i = 0; i < nbytes; i++) count += __builtin_popcount((uint8_t) (a[i] ^ b[i]));
+    return count;
+}
+
+/* ORDER BY binary_hamming_distance(bits, q) LIMIT k: k nearest rows by (distance, row); -1 / -1 past the end */
+typedef struct { int d; int64_t row; } OrcHamHit;
+static int orc_ham_cmp(const void *a, const void *b)
+{
+    const OrcHamHit *x = (const OrcHamHit *) a, *y = (const OrcHamHit *) b;
+    if (x->d != y->d) return x->d < y->d ? -1 : 1;
+    return x->row < y->row ? -1 : (x->row > y->row);
+}
+void orc_hamming_knn(const uint8_t *rows, int64_t n, int nbits, const uint8_t *Q, int nq, int k, int32_t *dist, int64_t *ids)
+{
+    int nbytes = (nbits + 7) / 8;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int j = 0; j < nq; j++) {
+        OrcHamHit *h = (OrcHamHit *) malloc(sizeof(OrcHamHit) * (size_t) n);
+        for (int64_t i = 0; i < n; i++) { h[i].d = orc_hamming(rows + (size_t) i * nbytes, Q + (size_t) j * nbytes, nbits); h[i].row = i; }
+        qsort(h, (size_t) n, sizeof(OrcHamHit), orc_ham_cmp);
+        for (int i = 0; i < k; i++) {
+            dist[(size_t) j * k + i] = i < n ? h[i].d : -1;
+            ids[(size_t) j * k + i] = i < n ? h[i].row : -1;
+        }
+        free(h);
+    }
+}

@@ -127,6 +127,10 @@ def ml_paths():
         codes = O.ref_pq_encode(X, cb)
         out["cb_bits_" + tag], out["codes_" + tag] = cb.view(np.uint32), codes
         out["adc_bits_" + tag] = O.ref_pq_distances(Q, codes, cb).view(np.uint32)
+    # per-vector quantisers: the reference's own quantize_vector_* functions
+    for X in T._quant_inputs():
+        for kind in (1, 2, 3, 4, 5, 6):
+            out["quant_k%d_d%d" % (kind, X.shape[1])] = O.ref_quantize_rows(kind, X)
     np.savez_compressed(os.path.join(HERE, "ml_paths.npz"), **out)
 
 

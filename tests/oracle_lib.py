@@ -22,6 +22,8 @@ _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
 _i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+Q_INT8, Q_FP16, Q_BINARY, Q_UINT8, Q_TERNARY, Q_INT4 = 1, 2, 3, 4, 5, 6
 RAND_MAX = 2147483647                      # glibc
 
 
@@ -86,6 +88,11 @@ def _load(name="libndb_oracle.so"):
     f.argtypes = [_f32p, _f64p, C.c_int, C.c_int, _f32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), _i32p]
     f = lib.orc_kmeanspp_init; f.restype = C.c_int
     f.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p]
+    f = lib.orc_quantized_row_bytes; f.restype = C.c_int64; f.argtypes = [C.c_int, C.c_int]
+    f = lib.orc_quantize_rows; f.restype = None; f.argtypes = [C.c_int, _f32p, C.c_int64, C.c_int, _u8p]
+    f = lib.orc_hamming; f.restype = C.c_int; f.argtypes = [_u8p, _u8p, C.c_int]
+    f = lib.orc_hamming_knn; f.restype = None
+    f.argtypes = [_u8p, C.c_int64, C.c_int, _u8p, C.c_int, C.c_int, _i32p, _i64p]
     f = lib.orc_pq_train; f.restype = C.c_int
     f.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _f32p]
     f = lib.orc_pq_encode; f.restype = None; f.argtypes = [_f32p, C.c_int64, C.c_int, _f32p, C.c_int, C.c_int, _i16p]
@@ -412,6 +419,8 @@ def ref_leafs_lib():
     l.ref_kmeanspp_init.restype = None; l.ref_kmeanspp_init.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p]
     l.ref_cluster_kmeans.restype = C.c_int
     l.ref_cluster_kmeans.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_void_p]
+    l.ref_quantize_row.restype = C.c_int; l.ref_quantize_row.argtypes = [C.c_int, _f32p, C.c_int, _u8p, C.c_int]
+    l.ref_hamming.restype = C.c_int; l.ref_hamming.argtypes = [_u8p, _u8p, C.c_int]
     l.ref_pq_train_subspace.restype = None
     l.ref_pq_train_subspace.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int]
     l.ref_pq_encode.restype = None; l.ref_pq_encode.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _i16p]
@@ -569,3 +578,31 @@ def ref_pq_distances(Q, codes, cb):
         for i in range(len(codes)):
             out[j, i] = f(Q[j], codes[i], flat, m, ksub, dsub)
     return out
+
+
+# ---- per-vector quantisers and the Hamming scan (oracle/ndb_oracle_ml.c; src/types/quantization.c) ----------------
+def quantize_rows(kind, X):
+    X = f32(X)
+    n, dim = X.shape
+    rb = lib().orc_quantized_row_bytes(kind, dim)
+    out = np.zeros((n, rb), np.uint8)
+    lib().orc_quantize_rows(kind, X, n, dim, out.reshape(-1))
+    return out
+
+
+def ref_quantize_rows(kind, X):
+    """The reference's own quantize_vector_* per row (data[] bytes)."""
+    X = f32(X)
+    n, dim = X.shape
+    rb = lib().orc_quantized_row_bytes(kind, dim)
+    out = np.zeros((n, rb), np.uint8)
+    for i in range(n):
+        assert ref_leafs_lib().ref_quantize_row(kind, X[i], dim, out[i], rb) == 0
+    return out
+
+
+def hamming_knn(rows, nbits, Q, k):
+    rows, Q = np.ascontiguousarray(rows, np.uint8), np.ascontiguousarray(Q, np.uint8)
+    d, i = np.zeros((len(Q), k), np.int32), np.zeros((len(Q), k), np.int64)
+    lib().orc_hamming_knn(rows.reshape(-1), len(rows), nbits, Q.reshape(-1), len(Q), k, d.reshape(-1), i.reshape(-1))
+    return d, i

@@ -3,6 +3,8 @@ sources (when present) and the committed golden vectors."""
 import importlib.util
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -457,3 +459,39 @@ def test_pq_golden_vectors():
         assert np.array_equal(codes, g["codes_" + tag])
         _, _, al = O.pq_knn(Q, codes, cb, 5, want_all=True)
         assert np.array_equal(BITS(al), g["adc_bits_" + tag])
+
+
+# ---- per-vector quantisers (src/types/quantization.c) ------------------------------------------
+def _quant_inputs():
+    rng = np.random.default_rng(4242)
+    out = []
+    for dim in (1, 2, 3, 7, 8, 9, 16, 31, 64, 100, 128):
+        X = (rng.standard_normal((12, dim)) * rng.choice([1e-3, 1.0, 300.0], (12, 1))).astype(np.float32)
+        X[0] = 0.0                                            # all zeros: zero bytes in every format
+        X[1] = X[1, 0]                                        # constant row: uint8's max == min
+        X[2, ::2] = 0.0
+        X[3] *= 1e-6                                          # below fp16's normal range: flushed to zero
+        X[4] *= 1e6                                           # above it: inf
+        X[5] = np.round(X[5] * 4) / 4 + 0.5                   # .5 ties for rintf
+        out.append(X)
+    return out
+
+
+@pytest.mark.skipif(O.ref_leafs_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_quantisers_equal_the_reference_functions():
+    ref = O.ref_leafs_lib()
+    for X in _quant_inputs():
+        for kind in (O.Q_INT8, O.Q_FP16, O.Q_BINARY, O.Q_UINT8, O.Q_TERNARY, O.Q_INT4):
+            assert np.array_equal(O.quantize_rows(kind, X), O.ref_quantize_rows(kind, X)), (kind, X.shape)
+        bits = O.quantize_rows(O.Q_BINARY, X)
+        for i in range(len(bits)):
+            j = (i + 1) % len(bits)
+            want = ref.ref_hamming(bits[i], bits[j], X.shape[1])
+            assert O.lib().orc_hamming(bits[i], bits[j], X.shape[1]) == want == int(np.unpackbits(bits[i] ^ bits[j]).sum())
+
+
+def test_quantiser_golden_vectors():
+    g = np.load(os.path.join(HERE, "golden", "ml_paths.npz"))
+    for X in _quant_inputs():
+        for kind in (O.Q_INT8, O.Q_FP16, O.Q_BINARY, O.Q_UINT8, O.Q_TERNARY, O.Q_INT4):
+            assert np.array_equal(O.quantize_rows(kind, X), g["quant_k%d_d%d" % (kind, X.shape[1])])
