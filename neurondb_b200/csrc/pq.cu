@@ -171,6 +171,8 @@ static int pq_scan(PqIndex *pq, const float *Q_dev, int nq, int k, float *dist_d
                                                   pq->ksub, k, rows_per_part, eps, pq->pdist.as<float>(), pq->pslot.as<uint32_t>(),     \
                                                   all_dev, recheck_dev);                                                               \
     } while (0)
+    Context &c = ctx();
+    if (c.timing) NDB_CUDA(cudaEventRecord(c.ev0, s));
     if (kr == 0) NDB_PQ_LAUNCH(0);
     else {
         NDB_CHECK(pq->pdist.reserve((size_t) nq * nparts * k * sizeof(float)));
@@ -180,6 +182,13 @@ static int pq_scan(PqIndex *pq, const float *Q_dev, int nq, int k, float *dist_d
         else { set_error("pq_search: k=%d out of range (1..128)", k); return NDB_B200_EINVAL; }
     }
 #undef NDB_PQ_LAUNCH
+    if (c.timing) {                                    // ndb_b200_last_kernel_stats: the scan kernel alone
+        NDB_CUDA(cudaEventRecord(c.ev1, s));
+        c.last_bytes = (double) pq->n * pq->m * nq;    // m code bytes per (row, query)
+        c.last_evals = pq->n * (int64_t) nq;
+        c.stats_src = nullptr;
+        c.last_ms = -1.0;
+    }
     count_launch();
     NDB_CUDA(cudaGetLastError());
     if (kr > 0)

@@ -117,3 +117,24 @@ emit(what="pq_scan", rows=n, dim=dim, m=m, ksub=ksub, nq=nq, k=k, e2e_s=ts, e2e_
      same_as_device=bool(np.array_equal(dd.cpu().numpy(), d) and np.array_equal(rd.cpu().numpy(), r)),
      note="algorithmic bytes = m code bytes per (row, query): the codes are re-read from L2/HBM for every query block; "
           "the table lookups (m fp64 shared-memory reads + adds per row) are the issue bound")
+
+# ---- per-vector quantisers and the Hamming scan --------------------------------------------------------------------
+n, dim, nq, k = (50000, 64, 100, 10) if small else (1_000_000, 128, 1000, 10)
+X = W.gaussian(n, dim, 6)
+Qb = W.gaussian(nq, dim, 7)
+ndb.quantize_rows(ndb.QUANT_INT8, X[:1000])
+for kind, name in ((ndb.QUANT_INT8, "int8"), (ndb.QUANT_FP16, "fp16"), (ndb.QUANT_BINARY, "binary"), (ndb.QUANT_INT4, "int4")):
+    tq, out = wall(lambda: ndb.quantize_rows(kind, X), 2)
+    ncq = 20000
+    tqc, outc = wall(lambda: O.quantize_rows(kind, X[:ncq]))
+    emit(what="quantize_rows", kind=name, rows=n, dim=dim, gpu_s=tq, gpu_rows_per_s=n / tq, e2e_GBps=(X.nbytes + out.nbytes) / tq / 1e9,
+         cpu_sample_rows=ncq, cpu_rows_per_s=ncq / tqc, cpu_threads=1, same_bytes_on_sample=bool(np.array_equal(out[:ncq], outc)),
+         note="end to end with host buffers: the 4 * dim bytes per row cross PCIe, which bounds it")
+bits, qbits = ndb.quantize_rows(ndb.QUANT_BINARY, X), ndb.quantize_rows(ndb.QUANT_BINARY, Qb)
+ndb.hamming_knn(bits[:1000], dim, qbits[:8], k)
+th, (hd, hi) = wall(lambda: ndb.hamming_knn(bits, dim, qbits, k), 3)
+nqc = 8
+thc, (cd, ci) = wall(lambda: O.hamming_knn(bits, dim, qbits[:nqc], k))
+emit(what="hamming_knn", rows=n, nbits=dim, nq=nq, k=k, e2e_s=th, e2e_qps=nq / th, row_evals_per_s=float(n) * nq / th,
+     cpu_queries=nqc, cpu_s=thc, cpu_qps=nqc / thc, cpu_threads=cores, same_on_sample=bool(np.array_equal(hd[:nqc], cd) and np.array_equal(hi[:nqc], ci)),
+     note="rows uploaded per call (16 MB); algorithmic bytes = nbits / 8 per (row, query)")
