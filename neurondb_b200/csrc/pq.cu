@@ -81,15 +81,44 @@ __device__ __forceinline__ float pq_exact_distance(const float *__restrict__ q, 
     return __double2float_rn(__dsqrt_rn(total));
 }
 
+// sum over the subspaces of table[sub][code[sub]], in subspace order
+__device__ __forceinline__ double pq_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float pq_add(float a, float b) { return __fadd_rn(a, b); }
+template <class T>
+__device__ __forceinline__ T pq_table_sum(const T *__restrict__ table, const uint8_t *__restrict__ code, int m, int ksub)
+{
+    T total = (T) 0;
+    if ((m & 3) == 0) {
+        const uint32_t *c4 = reinterpret_cast<const uint32_t *>(code);
+        for (int sub = 0; sub < m; sub += 4) {
+            const uint32_t w = c4[sub >> 2];
+            total = pq_add(total, table[(sub + 0) * ksub + (w & 0xff)]);
+            total = pq_add(total, table[(sub + 1) * ksub + ((w >> 8) & 0xff)]);
+            total = pq_add(total, table[(sub + 2) * ksub + ((w >> 16) & 0xff)]);
+            total = pq_add(total, table[(sub + 3) * ksub + (w >> 24)]);
+        }
+    } else {
+        for (int sub = 0; sub < m; sub++) total = pq_add(total, table[sub * ksub + code[sub]]);
+    }
+    return total;
+}
+
 // grid (nparts, nq); every block builds its query's table, its warps walk the block's row range 32 rows at a time.
 // KR > 0: partial top-k lists pdist / pslot [nq][nparts][k]; KR == 0: all distances to out_all [nq][n].
-template <int KR>
+// FILTER (top-k only): a float copy of the table screens the rows.  Its sum t32 bounds the true sum from below
+// (t32 (1 - delta), delta = (m + 8) 2^-23 covering the entries' and the additions' roundings), and the smallest k-th
+// distance any warp of the block holds bounds what can still enter the block's result, so a row with
+// t32 (1 - delta) > bound^2 (1 + 2^-22) is dropped after m 4-byte reads; everything else takes the exact path below.  The
+// 4-byte reads cost about half the bank conflicts of the 8-byte ones, and the fp64 work disappears from the common case.
+template <int KR, bool FILTER>
 __global__ void __launch_bounds__(256) pq_adc_kernel(const float *__restrict__ Q, const uint8_t *__restrict__ codes, const float *__restrict__ cb,
                                                      int64_t n, int dim, int m, int ksub, int k, int64_t rows_per_part, double eps,
                                                      float *__restrict__ pdist, uint32_t *__restrict__ pslot, float *__restrict__ out_all,
                                                      unsigned long long *__restrict__ recheck_count)
 {
-    extern __shared__ double lut[];                    // [m][ksub]
+    extern __shared__ double lut[];                    // [m][ksub] doubles, then (FILTER) [m][ksub] floats
+    __shared__ unsigned int s_bound;                   // float bits of the block's smallest k-th distance
+    float *lut32 = reinterpret_cast<float *>(lut + (size_t) m * ksub);
     const int dsub = dim / m;
     const int qi = blockIdx.y, part = blockIdx.x;
     const float *q = Q + (size_t) qi * dim;
@@ -102,32 +131,36 @@ __global__ void __launch_bounds__(256) pq_adc_kernel(const float *__restrict__ Q
             t = __dadd_rn(t, __dmul_rn(diff, diff));
         }
         lut[e] = t;
+        if (FILTER) lut32[e] = __double2float_rn(t);
     }
+    if (threadIdx.x == 0) s_bound = 0x7f800000u;       // +inf
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int64_t r0 = (int64_t) part * rows_per_part;
     const int64_t r1 = r0 + rows_per_part < n ? r0 + rows_per_part : n;
+    const float one_minus_delta = 1.0f - (float) (m + 8) * 1.1920928955078125e-07f;       // exact: a multiple of 2^-23 below 1
+    unsigned int bound_seen = 0x7f800000u;
+    float limit = INFINITY;                            // bound^2 (1 + 2^-22), rounded up
     WarpTopK<(KR > 0 ? KR : 1), uint32_t> top;
     if (KR > 0) top.init();
     for (int64_t base = r0 + (int64_t) warp * 32; base < r1; base += (int64_t) nwarps * 32) {
         const int64_t row = base + lane;
         const bool valid = row < r1;
-        float f = INFINITY;
-        if (valid) {
-            const uint8_t *code = codes + (size_t) row * m;
-            double total = 0.0;
-            if ((m & 3) == 0) {
-                const uint32_t *c4 = reinterpret_cast<const uint32_t *>(code);
-                for (int sub = 0; sub < m; sub += 4) {
-                    const uint32_t w = c4[sub >> 2];
-                    total = __dadd_rn(total, lut[(sub + 0) * ksub + (w & 0xff)]);
-                    total = __dadd_rn(total, lut[(sub + 1) * ksub + ((w >> 8) & 0xff)]);
-                    total = __dadd_rn(total, lut[(sub + 2) * ksub + ((w >> 16) & 0xff)]);
-                    total = __dadd_rn(total, lut[(sub + 3) * ksub + (w >> 24)]);
-                }
-            } else {
-                for (int sub = 0; sub < m; sub++) total = __dadd_rn(total, lut[sub * ksub + code[sub]]);
+        const uint8_t *code = codes + (size_t) (valid ? row : r0) * m;
+        bool pass = valid;
+        if (FILTER) {
+            const unsigned int b = *(volatile unsigned int *) &s_bound;
+            if (b != bound_seen) {
+                bound_seen = b;
+                const double bd = (double) __uint_as_float(b);
+                limit = __double2float_ru(bd * bd * (1.0 + 2.384185791015625e-07));
             }
+            const float t32 = pq_table_sum<float>(lut32, code, m, ksub);
+            pass = valid && (__fmul_rd(t32, one_minus_delta) <= limit || t32 < 1e-30f);      // (below: float subnormals carry no bound)
+        }
+        float f = INFINITY;
+        if (pass) {
+            const double total = pq_table_sum<double>(lut, code, m, ksub);
             const double d = __dsqrt_rn(total);
             const float lo = __double2float_rn(d * (1.0 - eps)), hi = __double2float_rn(d * (1.0 + eps));
             if (lo == hi) f = lo;
@@ -137,10 +170,14 @@ __global__ void __launch_bounds__(256) pq_adc_kernel(const float *__restrict__ Q
             }
             if (KR == 0) out_all[(size_t) qi * n + row] = f;
         }
-        if (KR > 0) top.offer(f, (uint32_t) row, valid, lane, k);
+        if (KR > 0) {
+            const float td_before = top.td;
+            top.offer(f, (uint32_t) row, pass, lane, k);
+            if (FILTER && lane == 0 && top.td < td_before) atomicMin(&s_bound, __float_as_uint(top.td));
+        }
     }
     if (KR > 0) {
-        __syncthreads();                               // the table is no longer needed: its memory carries the merge
+        __syncthreads();                               // the tables are no longer needed: their memory carries the merge
         block_topk_write<(KR > 0 ? KR : 1)>(top, lut, warp, lane, nwarps, k, pdist, pslot, ((size_t) qi * gridDim.x + part) * k);
     }
 }
@@ -151,6 +188,10 @@ static int pq_scan(PqIndex *pq, const float *Q_dev, int nq, int k, float *dist_d
     const size_t lut_bytes = (size_t) pq->m * pq->ksub * sizeof(double);
     const int kr = k <= 0 ? 0 : (k <= 32 ? 1 : (k <= 128 ? 4 : -1));
     size_t smem = lut_bytes;
+    // the float screen needs half as much again; without it (table too large, or NDB_PQ_NO_FILTER for comparison) every row
+    // takes the exact path
+    const bool filter = kr > 0 && lut_bytes + lut_bytes / 2 <= ctx().smem_optin && !getenv("NDB_PQ_NO_FILTER");
+    if (filter) smem += lut_bytes / 2;
     if (kr > 0 && (size_t) 8 * kr * 32 * 8 > smem) smem = (size_t) 8 * kr * 32 * 8;
     NDB_REQUIRE(smem <= ctx().smem_optin, NDB_B200_EINVAL, "pq: m * ksub = %d table entries do not fit shared memory", pq->m * pq->ksub);
     // rows per block: enough to amortise the table (ksub * dim * 3 fp64 operations) over the rows (m reads each), and about
@@ -164,16 +205,21 @@ static int pq_scan(PqIndex *pq, const float *Q_dev, int nq, int k, float *dist_d
     double eps = (double) (pq->dim + pq->m + 8) * 4.0 * 1.1102230246251565e-16;
     if (const char *e = getenv("NDB_PQ_EPS")) eps = atof(e) > eps ? atof(e) : eps;      // (test switch: widen the band to exercise the re-evaluation)
     dim3 grid((unsigned) nparts, (unsigned) nq);
+#define NDB_PQ_LAUNCH1(KR, F)                                                                                                          \
+    do {                                                                                                                               \
+        NDB_CUDA(cudaFuncSetAttribute(pq_adc_kernel<KR, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));                 \
+        pq_adc_kernel<KR, F><<<grid, 256, smem, s>>>(Q_dev, pq->codes.as<uint8_t>(), pq->codebooks.as<float>(), pq->n, pq->dim, pq->m,  \
+                                                     pq->ksub, k, rows_per_part, eps, pq->pdist.as<float>(), pq->pslot.as<uint32_t>(),  \
+                                                     all_dev, recheck_dev);                                                            \
+    } while (0)
 #define NDB_PQ_LAUNCH(KR)                                                                                                              \
     do {                                                                                                                               \
-        NDB_CUDA(cudaFuncSetAttribute(pq_adc_kernel<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));                    \
-        pq_adc_kernel<KR><<<grid, 256, smem, s>>>(Q_dev, pq->codes.as<uint8_t>(), pq->codebooks.as<float>(), pq->n, pq->dim, pq->m,     \
-                                                  pq->ksub, k, rows_per_part, eps, pq->pdist.as<float>(), pq->pslot.as<uint32_t>(),     \
-                                                  all_dev, recheck_dev);                                                               \
+        if (filter) NDB_PQ_LAUNCH1(KR, true);                                                                                          \
+        else NDB_PQ_LAUNCH1(KR, false);                                                                                                \
     } while (0)
     Context &c = ctx();
     if (c.timing) NDB_CUDA(cudaEventRecord(c.ev0, s));
-    if (kr == 0) NDB_PQ_LAUNCH(0);
+    if (kr == 0) NDB_PQ_LAUNCH1(0, false);
     else {
         NDB_CHECK(pq->pdist.reserve((size_t) nq * nparts * k * sizeof(float)));
         NDB_CHECK(pq->pslot.reserve((size_t) nq * nparts * k * sizeof(uint32_t)));
@@ -182,6 +228,7 @@ static int pq_scan(PqIndex *pq, const float *Q_dev, int nq, int k, float *dist_d
         else { set_error("pq_search: k=%d out of range (1..128)", k); return NDB_B200_EINVAL; }
     }
 #undef NDB_PQ_LAUNCH
+#undef NDB_PQ_LAUNCH1
     if (c.timing) {                                    // ndb_b200_last_kernel_stats: the scan kernel alone
         NDB_CUDA(cudaEventRecord(c.ev1, s));
         c.last_bytes = (double) pq->n * pq->m * nq;    // m code bytes per (row, query)

@@ -87,6 +87,38 @@ def test_pq_scan_recheck_path_is_exact(ndb):
     assert 0 < seen[0] < seen[1] and seen[1] > da.size // 2
 
 
+def test_pq_scan_float_screen_changes_nothing(ndb):
+    """The top-k scan screens rows with a float copy of the table against the block's best k-th distance; NDB_PQ_NO_FILTER
+    sends every row down the exact path.  Same distances and rows either way -- also when the rows arrive in descending
+    distance (every row passes the screen), with duplicates (ties at the k-th place) and with tiny distances."""
+    m, ksub, dim = 8, 256, 32
+    X = W.mixture(40000, dim, 10, 5)
+    draws = np.random.default_rng(8).integers(0, O.RAND_MAX, m * ksub, dtype=np.int64).astype(np.int32)
+    cb = ndb.pq_train(X[:3000], m, ksub, draws, 3)
+    codes = O.pq_encode(X, cb)
+    Q = W.mixture(12, dim, 10, 6, centers_seed=5)
+    Q[1] = X[7]
+    _, _, al = O.pq_knn(Q[:1], codes, cb, 1, want_all=True)
+    order = np.argsort(-al[0], kind="stable")                        # descending distance to query 0
+    codes_desc = np.ascontiguousarray(codes[order])
+    codes_desc[100:160] = codes_desc[39990]                          # 60 copies of a near row: ties at the k-th place
+    cb_tiny = (cb * np.float32(1e-20)).astype(np.float32)            # squared distances around 1e-40: float subnormals
+    for cbk, cd, qs in ((cb, codes_desc, Q), (cb_tiny, codes_desc, (Q * np.float32(1e-20)).astype(np.float32))):
+        for k in (10, 70):
+            wd, wr, _ = O.pq_knn(qs, cd, cbk, k)
+            got = {}
+            for mode in ("screen", "exact"):
+                if mode == "exact":
+                    os.environ["NDB_PQ_NO_FILTER"] = "1"
+                try:
+                    pq = ndb.PqIndex(cbk)
+                    pq.add_codes(cd)
+                    got[mode] = pq.search(qs, k)
+                finally:
+                    os.environ.pop("NDB_PQ_NO_FILTER", None)
+                assert np.array_equal(BITS(got[mode][0]), BITS(wd)) and np.array_equal(got[mode][1], wr), (mode, k)
+
+
 def test_pq_errors_are_the_sql_functions(ndb):
     X = W.gaussian(64, 12, 1)
     draws = np.arange(4096, dtype=np.int32)
