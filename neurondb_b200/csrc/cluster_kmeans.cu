@@ -165,10 +165,17 @@ __global__ void ckm_gather_centers_kernel(const float *__restrict__ X, const int
     for (int d = threadIdx.x; d < dim; d += blockDim.x) C[(size_t) c * dim + d] = X[(size_t) seeds[c] * dim + d];
 }
 
+__global__ void ckm_widen_kernel(const float *__restrict__ in, int64_t n, double *__restrict__ out)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double) in[i];
+}
+
 // nearest center of each row in fp64, CPT centers per pass over the row (independent chains hide the fp64 latency,
-// the row element is converted once for all of them)
+// the row element is converted once for all of them; the centres arrive already widened -- the conversion of a centre
+// element is the same for every row, and F2F shares the slow pipe with the fp64 arithmetic)
 template <int CPT>
-__global__ void __launch_bounds__(128) ckm_assign_kernel(const float *__restrict__ XT, const float *__restrict__ C, int64_t n, int dim, int k,
+__global__ void __launch_bounds__(128) ckm_assign_kernel(const float *__restrict__ XT, const double *__restrict__ C, int64_t n, int dim, int k,
                                                          int *__restrict__ assign, int *__restrict__ changed)
 {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(128) ckm_assign_kernel(const float *__restrict
     double min_dist = DBL_MAX;
     for (int c0 = 0; c0 < k; c0 += CPT) {
         double acc[CPT];
-        const float *crow[CPT];
+        const double *crow[CPT];
 #pragma unroll
         for (int j = 0; j < CPT; j++) {
             acc[j] = 0.0;
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(128) ckm_assign_kernel(const float *__restrict
             const double x = (double) XT[(size_t) d * n + il];
 #pragma unroll
             for (int j = 0; j < CPT; j++) {
-                const double diff = __dsub_rn(x, (double) __ldg(crow[j] + d));
+                const double diff = __dsub_rn(x, __ldg(crow[j] + d));
                 acc[j] = __dadd_rn(acc[j], __dmul_rn(diff, diff));
             }
         }
@@ -228,10 +235,13 @@ int gather_rows_dev(const float *dX, const int *rows_dev, int nrows, int dim, fl
     return NDB_B200_OK;
 }
 
-int nearest_f64_dev(const float *dXT, const float *dC, int64_t n, int dim, int k, int *assign, int *changed, cudaStream_t s)
+int nearest_f64_dev(const float *dXT, const float *dC, int64_t n, int dim, int k, int *assign, int *changed, DevBuf &wide, cudaStream_t s)
 {
-    ckm_assign_kernel<4><<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(dXT, dC, n, dim, k, assign, changed);
-    count_launch();
+    const int64_t cn = (int64_t) k * dim;
+    NDB_CHECK(wide.reserve((size_t) cn * sizeof(double)));
+    ckm_widen_kernel<<<(unsigned) ((cn + 255) / 256), 256, 0, s>>>(dC, cn, wide.as<double>());
+    ckm_assign_kernel<4><<<(unsigned) ((n + 127) / 128), 128, 0, s>>>(dXT, wide.as<double>(), n, dim, k, assign, changed);
+    count_launch(2);
     NDB_CUDA(cudaGetLastError());
     return NDB_B200_OK;
 }
@@ -242,7 +252,7 @@ int lloyd_f64_dev(KMeansWork &w, const float *dX, const float *dXT, int64_t n, i
     int changed = 1, iter = 0;
     for (iter = 0; iter < max_iters && (stop_before_update || changed); iter++) {
         NDB_CUDA(cudaMemsetAsync(dchanged, 0, 4, s));
-        NDB_CHECK(nearest_f64_dev(dXT, w.C.as<float>(), n, dim, k, w.assign.as<int>(), dchanged, s));
+        NDB_CHECK(nearest_f64_dev(dXT, w.C.as<float>(), n, dim, k, w.assign.as<int>(), dchanged, w.dcost, s));
         NDB_CUDA(cudaMemcpyAsync(&changed, dchanged, 4, cudaMemcpyDeviceToHost, s));
         if (stop_before_update) {
             NDB_CUDA(cudaStreamSynchronize(s));

@@ -51,7 +51,8 @@ int kmeans_run_dev(KMeansWork &w, int n, int d, int k, int max_iter, float tol, 
 int upload_rows_checked(DevBuf &dst, const float *X, size_t count, const char *who, cudaStream_t s);
 int transpose_rows_dev(const float *dX, int64_t n, int dim, float *dXT, cudaStream_t s);
 int gather_rows_dev(const float *dX, const int *rows_dev, int nrows, int dim, float *out, cudaStream_t s);
-int nearest_f64_dev(const float *dXT, const float *dC, int64_t n, int dim, int k, int *assign, int *changed, cudaStream_t s);
+// (wide: scratch for the k*dim centres widened to double)
+int nearest_f64_dev(const float *dXT, const float *dC, int64_t n, int dim, int k, int *assign, int *changed, DevBuf &wide, cudaStream_t s);
 // stop_before_update: leave the loop after an assignment pass that changed nothing (train_subspace_kmeans); otherwise the
 // update runs once more and the loop condition ends it (cluster_kmeans)
 int lloyd_f64_dev(KMeansWork &w, const float *dX, const float *dXT, int64_t n, int dim, int k, int max_iters, bool stop_before_update,

@@ -48,8 +48,9 @@ static int pq_encode_dev(const float *dXT, int64_t n, int dim, const float *dcb,
                          uint8_t *codes8, int16_t *codes16, cudaStream_t s)
 {
     const int dsub = dim / m;
+    DevBuf wide;
     for (int sub = 0; sub < m; sub++) {
-        NDB_CHECK(nearest_f64_dev(dXT + (size_t) sub * dsub * n, dcb + (size_t) sub * ksub * dsub, n, dsub, ksub, dassign, dchanged, s));
+        NDB_CHECK(nearest_f64_dev(dXT + (size_t) sub * dsub * n, dcb + (size_t) sub * ksub * dsub, n, dsub, ksub, dassign, dchanged, wide, s));
         pq_store_codes_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(dassign, n, m, sub, codes8, codes16);
         count_launch();
     }
@@ -84,9 +85,11 @@ __device__ __forceinline__ float pq_exact_distance(const float *__restrict__ q, 
 // sum over the subspaces of table[sub][code[sub]], in subspace order
 __device__ __forceinline__ double pq_add(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float pq_add(float a, float b) { return __fadd_rn(a, b); }
-template <class T>
-__device__ __forceinline__ T pq_table_sum(const T *__restrict__ table, const uint8_t *__restrict__ code, int m, int ksub)
+// (KSUB = 256: the usual 8-bit codebook, table rows at a constant stride -- the index arithmetic folds into the loads)
+template <class T, int KSUB>
+__device__ __forceinline__ T pq_table_sum(const T *__restrict__ table, const uint8_t *__restrict__ code, int m, int ksub_rt)
 {
+    const int ksub = KSUB > 0 ? KSUB : ksub_rt;
     T total = (T) 0;
     if ((m & 3) == 0) {
         const uint32_t *c4 = reinterpret_cast<const uint32_t *>(code);
@@ -110,7 +113,7 @@ __device__ __forceinline__ T pq_table_sum(const T *__restrict__ table, const uin
 // distance any warp of the block holds bounds what can still enter the block's result, so a row with
 // t32 (1 - delta) > bound^2 (1 + 2^-22) is dropped after m 4-byte reads; everything else takes the exact path below.  The
 // 4-byte reads cost about half the bank conflicts of the 8-byte ones, and the fp64 work disappears from the common case.
-template <int KR, bool FILTER>
+template <int KR, bool FILTER, int KSUB>
 __global__ void __launch_bounds__(256) pq_adc_kernel(const float *__restrict__ Q, const uint8_t *__restrict__ codes, const float *__restrict__ cb,
                                                      int64_t n, int dim, int m, int ksub, int k, int64_t rows_per_part, double eps,
                                                      float *__restrict__ pdist, uint32_t *__restrict__ pslot, float *__restrict__ out_all,
@@ -155,12 +158,12 @@ __global__ void __launch_bounds__(256) pq_adc_kernel(const float *__restrict__ Q
                 const double bd = (double) __uint_as_float(b);
                 limit = __double2float_ru(bd * bd * (1.0 + 2.384185791015625e-07));
             }
-            const float t32 = pq_table_sum<float>(lut32, code, m, ksub);
+            const float t32 = pq_table_sum<float, KSUB>(lut32, code, m, ksub);
             pass = valid && (__fmul_rd(t32, one_minus_delta) <= limit || t32 < 1e-30f);      // (below: float subnormals carry no bound)
         }
         float f = INFINITY;
         if (pass) {
-            const double total = pq_table_sum<double>(lut, code, m, ksub);
+            const double total = pq_table_sum<double, KSUB>(lut, code, m, ksub);
             const double d = __dsqrt_rn(total);
             const float lo = __double2float_rn(d * (1.0 - eps)), hi = __double2float_rn(d * (1.0 + eps));
             if (lo == hi) f = lo;
@@ -205,12 +208,17 @@ static int pq_scan(PqIndex *pq, const float *Q_dev, int nq, int k, float *dist_d
     double eps = (double) (pq->dim + pq->m + 8) * 4.0 * 1.1102230246251565e-16;
     if (const char *e = getenv("NDB_PQ_EPS")) eps = atof(e) > eps ? atof(e) : eps;      // (test switch: widen the band to exercise the re-evaluation)
     dim3 grid((unsigned) nparts, (unsigned) nq);
+#define NDB_PQ_LAUNCH2(KR, F, KS)                                                                                                      \
+    do {                                                                                                                               \
+        NDB_CUDA(cudaFuncSetAttribute(pq_adc_kernel<KR, F, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));             \
+        pq_adc_kernel<KR, F, KS><<<grid, 256, smem, s>>>(Q_dev, pq->codes.as<uint8_t>(), pq->codebooks.as<float>(), pq->n, pq->dim,     \
+                                                         pq->m, pq->ksub, k, rows_per_part, eps, pq->pdist.as<float>(),                \
+                                                         pq->pslot.as<uint32_t>(), all_dev, recheck_dev);                              \
+    } while (0)
 #define NDB_PQ_LAUNCH1(KR, F)                                                                                                          \
     do {                                                                                                                               \
-        NDB_CUDA(cudaFuncSetAttribute(pq_adc_kernel<KR, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));                 \
-        pq_adc_kernel<KR, F><<<grid, 256, smem, s>>>(Q_dev, pq->codes.as<uint8_t>(), pq->codebooks.as<float>(), pq->n, pq->dim, pq->m,  \
-                                                     pq->ksub, k, rows_per_part, eps, pq->pdist.as<float>(), pq->pslot.as<uint32_t>(),  \
-                                                     all_dev, recheck_dev);                                                            \
+        if (pq->ksub == 256) NDB_PQ_LAUNCH2(KR, F, 256);                                                                               \
+        else NDB_PQ_LAUNCH2(KR, F, 0);                                                                                                 \
     } while (0)
 #define NDB_PQ_LAUNCH(KR)                                                                                                              \
     do {                                                                                                                               \
@@ -229,6 +237,7 @@ static int pq_scan(PqIndex *pq, const float *Q_dev, int nq, int k, float *dist_d
     }
 #undef NDB_PQ_LAUNCH
 #undef NDB_PQ_LAUNCH1
+#undef NDB_PQ_LAUNCH2
     if (c.timing) {                                    // ndb_b200_last_kernel_stats: the scan kernel alone
         NDB_CUDA(cudaEventRecord(c.ev1, s));
         c.last_bytes = (double) pq->n * pq->m * nq;    // m code bytes per (row, query)

@@ -17,8 +17,10 @@
 // are the explicit round-to-nearest intrinsics, rintf = the default rounding mode's round-half-even on both sides.
 // The Hamming scan keeps a block's queries in shared memory and reads each row's words once per query block; its top-k
 // is the scan kernels' (distance as an exactly representable float, row as key).
+#include <cstdlib>
 #include "layout.cuh"
 #include "arith.cuh"
+#include "block_topk.cuh"
 
 namespace ndb {
 
@@ -186,6 +188,64 @@ __global__ void __launch_bounds__(256) hamming_topk_kernel(const uint8_t *__rest
     (void) nwarps;
 }
 
+// k <= 32: a lane loads its row ONCE and scores it against all HAM_QB queries of the block (their words broadcast from
+// shared memory), one WarpTopK list per query in registers; the warps split the block's rows and their lists are merged
+// per query at the end.  L2 -> SM traffic is the row bytes once per block of 8 queries instead of once per query.
+__global__ void __launch_bounds__(256) hamming_topk_mq_kernel(const uint8_t *__restrict__ rows, int64_t n, int nbytes, const uint8_t *__restrict__ Q,
+                                                              int nq, int k, int64_t rows_per_part, float *__restrict__ pdist,
+                                                              uint32_t *__restrict__ pslot)
+{
+    extern __shared__ __align__(16) unsigned char hsm[];          // HAM_QB queries of nwords words, then the merge area (2 KB)
+    const int nwords = (nbytes + 3) >> 2;
+    const uint32_t *qs = reinterpret_cast<const uint32_t *>(hsm);
+    void *merge = hsm + (((size_t) HAM_QB * nwords * 4 + 15) & ~(size_t) 15);
+    const int q0 = blockIdx.y * HAM_QB, part = blockIdx.x;
+    for (int e = threadIdx.x; e < HAM_QB * nwords * 4; e += blockDim.x) {
+        const int qq = e / (nwords * 4), b = e % (nwords * 4);
+        hsm[e] = (q0 + qq < nq && b < nbytes) ? Q[(size_t) (q0 + qq) * nbytes + b] : (unsigned char) 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t r0 = (int64_t) part * rows_per_part;
+    const int64_t r1 = r0 + rows_per_part < n ? r0 + rows_per_part : n;
+    const bool words = (nbytes & 3) == 0;
+    WarpTopK<1, uint32_t> top[HAM_QB];
+#pragma unroll
+    for (int j = 0; j < HAM_QB; j++) top[j].init();
+    for (int64_t base = r0 + (int64_t) warp * 32; base < r1; base += (int64_t) nwarps * 32) {
+        const int64_t row = base + lane;
+        const bool valid = row < r1;
+        int cnt[HAM_QB];
+#pragma unroll
+        for (int j = 0; j < HAM_QB; j++) cnt[j] = 0;
+        if (valid) {
+            if (words) {
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(rows + (size_t) row * nbytes);
+                for (int w = 0; w < nwords; w++) {
+                    const uint32_t x = rw[w];
+#pragma unroll
+                    for (int j = 0; j < HAM_QB; j++) cnt[j] += __popc(x ^ qs[j * nwords + w]);
+                }
+            } else {
+                const uint8_t *rb = rows + (size_t) row * nbytes;
+                const uint8_t *qb = reinterpret_cast<const uint8_t *>(qs);
+                for (int b = 0; b < nbytes; b++) {
+                    const uint32_t x = rb[b];
+#pragma unroll
+                    for (int j = 0; j < HAM_QB; j++) cnt[j] += __popc(x ^ (uint32_t) qb[j * nwords * 4 + b]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < HAM_QB; j++) top[j].offer((float) cnt[j], (uint32_t) row, valid, lane, k);
+    }
+#pragma unroll
+    for (int j = 0; j < HAM_QB; j++) {
+        __syncthreads();
+        if (q0 + j < nq) block_topk_write<1>(top[j], merge, warp, lane, nwarps, k, pdist, pslot, ((size_t) (q0 + j) * gridDim.x + part) * k);
+    }
+}
+
 __global__ void hamming_finish_kernel(const float *__restrict__ d, const int64_t *__restrict__ ids, int64_t total, int32_t *__restrict__ out)
 {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,8 +330,11 @@ int ndb_b200_hamming_knn(const uint8_t *rows, int64_t n, int nbits, const uint8_
     NDB_CHECK(pdist.reserve(m * nparts * 4)); NDB_CHECK(pslot.reserve(m * nparts * 4));
     NDB_CHECK(od.reserve(m * 4)); NDB_CHECK(oi.reserve(m * 8)); NDB_CHECK(o32.reserve(m * 4));
     const size_t smem = (size_t) HAM_QB * nwords * 4;
+    const size_t smem_mq = ((smem + 15) & ~(size_t) 15) + 8 * 32 * 8;
     dim3 grid((unsigned) nparts, (unsigned) qblocks);
-    if (k <= 32) hamming_topk_kernel<1><<<grid, 256, smem, s>>>(drows.as<uint8_t>(), n, nbytes, dq.as<uint8_t>(), nq, k, rows_per_part, pdist.as<float>(), pslot.as<uint32_t>());
+    if (k <= 32 && !getenv("NDB_HAMMING_PER_QUERY"))      // (switch: the warp-per-query kernel, for comparison)
+        hamming_topk_mq_kernel<<<grid, 256, smem_mq, s>>>(drows.as<uint8_t>(), n, nbytes, dq.as<uint8_t>(), nq, k, rows_per_part, pdist.as<float>(), pslot.as<uint32_t>());
+    else if (k <= 32) hamming_topk_kernel<1><<<grid, 256, smem, s>>>(drows.as<uint8_t>(), n, nbytes, dq.as<uint8_t>(), nq, k, rows_per_part, pdist.as<float>(), pslot.as<uint32_t>());
     else hamming_topk_kernel<4><<<grid, 256, smem, s>>>(drows.as<uint8_t>(), n, nbytes, dq.as<uint8_t>(), nq, k, rows_per_part, pdist.as<float>(), pslot.as<uint32_t>());
     count_launch();
     NDB_CUDA(cudaGetLastError());

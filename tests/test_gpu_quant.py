@@ -48,6 +48,12 @@ def test_hamming_scan_equals_the_oracle(ndb, n, nbits, nq, k):
     d, i = ndb.hamming_knn(rows, nbits, qs, k)
     assert np.array_equal(d, wd) and np.array_equal(i, wi)                            # ties by row, -1 / -1 past the end
     assert d[0, 0] == 0 and i[0, 0] <= n // 2
+    os.environ["NDB_HAMMING_PER_QUERY"] = "1"                                         # the warp-per-query kernel gives the same
+    try:
+        d2, i2 = ndb.hamming_knn(rows, nbits, qs, k)
+    finally:
+        del os.environ["NDB_HAMMING_PER_QUERY"]
+    assert np.array_equal(d2, wd) and np.array_equal(i2, wi)
 
 
 def test_quantiser_errors(ndb):
