@@ -173,6 +173,17 @@ int ndb_b200_knn_regress(ndb_b200_dataset *ds, const double *targets, const floa
 int ndb_b200_cluster_kmeans(const float *X, int n, int dim, int k, int max_iters, const int *rand_draws, int rand_max,
                             int *labels, float *centers, int *iters, int *seeds);
 
+/* cluster_minibatch_kmeans (src/ml/ml_minibatch_kmeans.c:206-449; seeding minibatch_kmeans_pp_init :67-198, all-double
+ * weights, stops early when the remaining weights sum below 1e-10 -- centroids it never reaches stay zero).  Per iteration
+ * batch_size rows rand() % n, nearest centroid in double, then sequentially over the batch: count++, eta = 1 / count,
+ * c = (float) ((1 - eta) c + eta x); finally every row's nearest centroid, labels 1-based.  How often the reference calls
+ * rand() depends on the data, so the caller passes the function: next_rand(rand_state) is called exactly when and as
+ * often as the reference calls rand() (the glue passes a wrapper around rand() itself).  batch_size > n -> n, max_iters < 1
+ * -> 100; k < 2, batch_size < 1, n < k -> EINVAL with the reference's messages; NaN / Inf -> EVECTOR. */
+typedef int (*ndb_b200_rand_fn)(void *state);
+int ndb_b200_cluster_minibatch_kmeans(const float *X, int n, int dim, int k, int batch_size, int max_iters, ndb_b200_rand_fn next_rand,
+                                      void *rand_state, int rand_max, int *labels, float *centers);
+
 /* ---- product quantisation (src/ml/ml_product_quantization.c).  Codebooks are laid out as the reference's
  *      bytea carries them after its three ints: float centroids[m][ksub][dsub], dsub = dim / m.  Arithmetic is the SQL
  *      functions': double difference / square / sum, strict <, lowest code wins; results are bit-identical to them.

@@ -72,6 +72,7 @@ SIGNATURES = {
     "ndb_b200_knn_classify": (_i, [_p, _p, _p, _i, _i, _p]),
     "ndb_b200_knn_regress": (_i, [_p, _p, _p, _i, _i, _p]),
     "ndb_b200_cluster_kmeans": (_i, [_p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p]),
+    "ndb_b200_cluster_minibatch_kmeans": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p]),
     "ndb_b200_quantized_row_bytes": (_i64, [_i, _i]),
     "ndb_b200_quantize_rows": (_i, [_i, _p, _i64, _i, _p]),
     "ndb_b200_hamming_knn": (_i, [_p, _i64, _i, _p, _i, _i, _p, _p]),

@@ -291,6 +291,31 @@ class _Handle:
             pass
 
 
+RAND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)          # ndb_b200_rand_fn
+
+
+def cluster_minibatch_kmeans(X, k, batch_size, max_iters, rand_draws, rand_max=2147483647):
+    """cluster_minibatch_kmeans (ml_minibatch_kmeans.c:206-449): (labels 1-based, centers, rand() values consumed).  The
+    library calls back for every rand() the reference would make; here the values come from `rand_draws` in order."""
+    X = f32(X)
+    if X.ndim != 2:
+        raise L.NdbError(-1, "cluster_minibatch_kmeans: a 2-d array of rows expected")
+    n, d = X.shape
+    draws = [int(v) for v in np.asarray(rand_draws).reshape(-1)]
+    used = [0]
+
+    def nxt(_state):
+        i = used[0]
+        used[0] += 1
+        return draws[i] if i < len(draws) else -1
+
+    cb = RAND_FN(nxt)
+    labels = np.zeros(n, np.int32)
+    Cn = np.zeros((max(k, 0), d), np.float32)
+    check(L.load().ndb_b200_cluster_minibatch_kmeans(ptr(X), n, d, k, batch_size, max_iters, cb, None, rand_max, ptr(labels), ptr(Cn)))
+    return labels, Cn, used[0]
+
+
 def quantize_rows(kind, X):
     """quantize_vector_i8 / _f16 / _binary / _uint8 / _ternary / _int4 (src/types/quantization.c) per row: uint8 [n][row_bytes]."""
     X = f32(X)

@@ -335,8 +335,9 @@ int kmeans_assign_dev(KMeansWork &w, const float *dX, int64_t n, int dim, int k,
     return NDB_B200_OK;
 }
 
-int kmeans_update_dev(KMeansWork &w, const float *dX, const int *d_assign, int64_t n, int dim, int k, float *dC,
-                      int *d_counts, cudaStream_t s, bool sums_only)
+// members of every cluster in ascending row order: w.vals_sorted = the row indices grouped by cluster (stable radix
+// sort), w.start[c] .. w.start[c + 1] = the group of cluster c
+int group_by_cluster_dev(KMeansWork &w, const int *d_assign, int64_t n, int k, cudaStream_t s)
 {
     NDB_REQUIRE(n < (int64_t) 0x7fffffff, NDB_B200_EINVAL, "kmeans_update: n too large");
     NDB_CHECK(w.keys_sorted.reserve((size_t) n * 4));
@@ -357,6 +358,14 @@ int kmeans_update_dev(KMeansWork &w, const float *dX, const int *d_assign, int64
     count_launch(3);
     segment_starts_kernel<<<(unsigned) ((n + 1 + 255) / 256), 256, 0, s>>>(w.keys_sorted.as<int>(), n, k, w.start.as<int>());
     count_launch();
+    NDB_CUDA(cudaGetLastError());
+    return NDB_B200_OK;
+}
+
+int kmeans_update_dev(KMeansWork &w, const float *dX, const int *d_assign, int64_t n, int dim, int k, float *dC,
+                      int *d_counts, cudaStream_t s, bool sums_only)
+{
+    NDB_CHECK(group_by_cluster_dev(w, d_assign, n, k, s));
     dim3 grid((unsigned) k, (unsigned) ((dim + 127) / 128));
     if (sums_only && n > KMEANS_FAST_ROWS)
         kmeans_update_fast_kernel<<<grid, 128, 0, s>>>(dX, w.vals_sorted.as<uint32_t>(), w.start.as<int>(), dim, k, dC, d_counts, sums_only);

@@ -38,6 +38,7 @@ int dense_scan(const float *store, const void *vnorm, int64_t nvec, int dim, int
 // w.C must hold the k*dim row-major centroids on the device
 int kmeans_assign_dev(KMeansWork &w, const float *dX, int64_t n, int dim, int k, int metric, int *d_assign,
                       cudaStream_t s);
+int group_by_cluster_dev(KMeansWork &w, const int *d_assign, int64_t n, int k, cudaStream_t s);
 // sums_only: leave the per-cluster sums instead of the means (row-sharded training)
 int kmeans_update_dev(KMeansWork &w, const float *dX, const int *d_assign, int64_t n, int dim, int k, float *dC,
                       int *d_counts, cudaStream_t s, bool sums_only = false);

@@ -160,6 +160,8 @@ int orc_kmeanspp_init(const float *X, int nvec, int dim, int k, const int *draws
 int orc_cluster_kmeans(const float *X, int nvec, int dim, int k, int max_iters, const int *draws, int rand_max,
                        int *labels, float *centers_out, int *seeds_out);     /* ml_kmeans.c:45-139, 146-303 */
 
+int orc_cluster_minibatch_kmeans(const float *X, int nvec, int dim, int k, int batch_size, int max_iters, const int *draws, int ndraws,
+                                 int rand_max, int *consumed, int *labels, float *centers_out);   /* ml_minibatch_kmeans.c:67-198, 206-449 */
 /* product quantisation (ml_product_quantization.c:80-190, 195-415, 421-536, 1003-1110); codebooks [m][ksub][dsub] */
 void orc_pq_train_subspace(const float *S, int nvec, int dsub, int k, const int *draws, float *centroids, int max_iters);
 int orc_pq_train(const float *X, int nvec, int dim, int m, int ksub, const int *draws, int max_iters, float *codebooks);

@@ -416,3 +416,93 @@ void orc_hamming_knn(const uint8_t *rows, int64_t n, int nbits, const uint8_t *Q
         free(h);
     }
 }
+
+/* ---- cluster_minibatch_kmeans (NeuronDB/src/ml/ml_minibatch_kmeans.c:67-198 minibatch_kmeans_pp_init, :206-449) ----------
+ * draws = the values rand() returns, in call order; *consumed = how many the function took (the seeding stops early when
+ * the remaining weights sum below 1e-10, so the count is data dependent).  All-double arithmetic; the centroid update is
+ * sequential over the batch: count++, eta = 1/count, c = (float)((1 - eta) c + eta x).  labels 1-based.
+ * Returns 0, -1 / -2 / -3 on the argument errors (:238-300), -4 when the draws run out.
+ * PINNED against the reference's own minibatch_kmeans_pp_init and the text of the main loop (oracle/extract_ref_leafs.py). */
+int orc_cluster_minibatch_kmeans(const float *X, int nvec, int dim, int k, int batch_size, int max_iters, const int *draws, int ndraws,
+                                 int rand_max, int *consumed, int *labels, float *centers_out)
+{
+    if (k < 2) return -1;                          /* "num_clusters must be at least 2" */
+    if (batch_size < 1) return -2;                 /* "batch_size must be at least 1" */
+    if (max_iters < 1) max_iters = 100;
+    if (nvec < k) return -3;                       /* "Not enough vectors (%d) for %d clusters" */
+    if (batch_size > nvec) batch_size = nvec;
+    int cur = 0;
+#define ORC_NEXT_RAND() (cur < ndraws ? draws[cur++] : (cur++, -1))
+    float *C = (float *) calloc((size_t) k * dim, sizeof(float));
+    unsigned char *selected = (unsigned char *) calloc((size_t) nvec, 1);
+    double *dist = (double *) calloc((size_t) nvec, sizeof(double));
+    int *counts = (int *) calloc((size_t) k, sizeof(int));
+    int *bidx = (int *) malloc(sizeof(int) * (size_t) batch_size), *bass = (int *) malloc(sizeof(int) * (size_t) batch_size);
+    {   /* minibatch_kmeans_pp_init */
+        int first = ORC_NEXT_RAND() % nvec;
+        memcpy(C, X + (size_t) first * dim, sizeof(float) * (size_t) dim);
+        selected[first] = 1;
+        for (int i = 0; i < nvec; i++) {
+            double acc = 0.0;
+            for (int d = 0; d < dim; d++) { double diff = (double) X[(size_t) i * dim + d] - (double) C[d]; acc += diff * diff; }
+            dist[i] = acc;
+        }
+        for (int c = 1; c < k; c++) {
+            double sum = 0.0, r;
+            int picked = -1;
+            for (int i = 0; i < nvec; i++) if (!selected[i]) sum += dist[i];
+            if (sum < 1e-10) break;
+            r = ((double) ORC_NEXT_RAND() / rand_max) * sum;
+            for (int i = 0; i < nvec; i++) {
+                if (selected[i]) continue;
+                r -= dist[i];
+                if (r <= 0.0) { picked = i; break; }
+            }
+            if (picked < 0) for (int i = 0; i < nvec; i++) if (!selected[i]) { picked = i; break; }
+            if (picked < 0) break;
+            memcpy(C + (size_t) c * dim, X + (size_t) picked * dim, sizeof(float) * (size_t) dim);
+            selected[picked] = 1;
+            for (int i = 0; i < nvec; i++) {
+                if (selected[i]) continue;
+                double acc = 0.0;
+                for (int d = 0; d < dim; d++) { double diff = (double) X[(size_t) i * dim + d] - (double) C[(size_t) c * dim + d]; acc += diff * diff; }
+                if (acc < dist[i]) dist[i] = acc;
+            }
+        }
+    }
+    for (int iter = 0; iter < max_iters; iter++) {
+        for (int i = 0; i < batch_size; i++) bidx[i] = ORC_NEXT_RAND() % nvec;
+        for (int i = 0; i < batch_size; i++) {
+            double min_dist = DBL_MAX;
+            int best = 0;
+            for (int c = 0; c < k; c++) {
+                double d2 = 0.0;
+                for (int d = 0; d < dim; d++) { double diff = (double) X[(size_t) bidx[i] * dim + d] - (double) C[(size_t) c * dim + d]; d2 += diff * diff; }
+                if (d2 < min_dist) { min_dist = d2; best = c; }
+            }
+            bass[i] = best;
+        }
+        for (int i = 0; i < batch_size; i++) {
+            int cl = bass[i];
+            counts[cl]++;
+            double lr = 1.0 / counts[cl];
+            for (int d = 0; d < dim; d++)
+                C[(size_t) cl * dim + d] = (float) ((1.0 - lr) * C[(size_t) cl * dim + d] + lr * X[(size_t) bidx[i] * dim + d]);
+        }
+    }
+    for (int i = 0; i < nvec; i++) {
+        double min_dist = DBL_MAX;
+        int best = 0;
+        for (int c = 0; c < k; c++) {
+            double d2 = 0.0;
+            for (int d = 0; d < dim; d++) { double diff = (double) X[(size_t) i * dim + d] - (double) C[(size_t) c * dim + d]; d2 += diff * diff; }
+            if (d2 < min_dist) { min_dist = d2; best = c; }
+        }
+        labels[i] = best + 1;
+    }
+#undef ORC_NEXT_RAND
+    if (centers_out) memcpy(centers_out, C, sizeof(float) * (size_t) k * dim);
+    if (consumed) *consumed = cur;
+    free(C); free(selected); free(dist); free(counts); free(bidx); free(bass);
+    return cur > ndraws ? -4 : 0;
+}

@@ -127,6 +127,12 @@ def ml_paths():
         codes = O.ref_pq_encode(X, cb)
         out["cb_bits_" + tag], out["codes_" + tag] = cb.view(np.uint32), codes
         out["adc_bits_" + tag] = O.ref_pq_distances(Q, codes, cb).view(np.uint32)
+    # cluster_minibatch_kmeans: the reference's own seeding function and main-loop text
+    for n, dim, k, batch, iters, seed in T._minibatch_cases():
+        X = T._minibatch_rows(n, dim, k, seed)
+        out["mb_draws_n%d" % n] = O.libc_rand_draws(seed, k + batch * iters)
+        labels, centers = O.ref_cluster_minibatch_kmeans(X, k, batch, iters, seed)
+        out["mb_labels_n%d" % n], out["mb_center_bits_n%d" % n] = labels, centers.view(np.uint32)
     # per-vector quantisers: the reference's own quantize_vector_* functions
     for X in T._quant_inputs():
         for kind in (1, 2, 3, 4, 5, 6):

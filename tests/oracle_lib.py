@@ -88,6 +88,8 @@ def _load(name="libndb_oracle.so"):
     f.argtypes = [_f32p, _f64p, C.c_int, C.c_int, _f32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), _i32p]
     f = lib.orc_kmeanspp_init; f.restype = C.c_int
     f.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i32p]
+    f = lib.orc_cluster_minibatch_kmeans; f.restype = C.c_int
+    f.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, C.c_int, C.POINTER(C.c_int), _i32p, C.c_void_p]
     f = lib.orc_quantized_row_bytes; f.restype = C.c_int64; f.argtypes = [C.c_int, C.c_int]
     f = lib.orc_quantize_rows; f.restype = None; f.argtypes = [C.c_int, _f32p, C.c_int64, C.c_int, _u8p]
     f = lib.orc_hamming; f.restype = C.c_int; f.argtypes = [_u8p, _u8p, C.c_int]
@@ -419,6 +421,8 @@ def ref_leafs_lib():
     l.ref_kmeanspp_init.restype = None; l.ref_kmeanspp_init.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _i32p]
     l.ref_cluster_kmeans.restype = C.c_int
     l.ref_cluster_kmeans.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_void_p]
+    l.ref_cluster_minibatch_kmeans.restype = None
+    l.ref_cluster_minibatch_kmeans.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_void_p]
     l.ref_quantize_row.restype = C.c_int; l.ref_quantize_row.argtypes = [C.c_int, _f32p, C.c_int, _u8p, C.c_int]
     l.ref_hamming.restype = C.c_int; l.ref_hamming.argtypes = [_u8p, _u8p, C.c_int]
     l.ref_pq_train_subspace.restype = None
@@ -606,3 +610,27 @@ def hamming_knn(rows, nbits, Q, k):
     d, i = np.zeros((len(Q), k), np.int32), np.zeros((len(Q), k), np.int64)
     lib().orc_hamming_knn(rows.reshape(-1), len(rows), nbits, Q.reshape(-1), len(Q), k, d.reshape(-1), i.reshape(-1))
     return d, i
+
+
+# ---- cluster_minibatch_kmeans (oracle/ndb_oracle_ml.c; ml_minibatch_kmeans.c) --------------------------------------
+def cluster_minibatch_kmeans(X, k, batch_size, max_iters, draws):
+    """(labels 1-based, centers, draws consumed): oracle restatement with the given rand() values."""
+    X = f32(X)
+    n, d = X.shape
+    labels, centers = np.zeros(n, np.int32), np.zeros((k, d), np.float32)
+    draws = np.ascontiguousarray(draws, np.int32)
+    used = C.c_int()
+    rc = lib().orc_cluster_minibatch_kmeans(X, n, d, k, batch_size, max_iters, draws, len(draws), RAND_MAX, C.byref(used), labels,
+                                            centers.ctypes.data)
+    assert rc == 0, rc
+    return labels, centers, used.value
+
+
+def ref_cluster_minibatch_kmeans(X, k, batch_size, max_iters, seed):
+    """The reference's minibatch_kmeans_pp_init + main loop after srand(seed): (labels, centers)."""
+    X = f32(X)
+    n, d = X.shape
+    labels, centers = np.zeros(n, np.int32), np.zeros((k, d), np.float32)
+    C.CDLL(None).srand(C.c_uint(seed))
+    ref_leafs_lib().ref_cluster_minibatch_kmeans(X, n, d, k, batch_size, max_iters, labels, centers.ctypes.data)
+    return labels, centers

@@ -82,3 +82,48 @@ def test_cluster_kmeans_certified_pick_equals_the_literal_walk(ndb):
     for a, b, c in zip(want, got, lit):
         assert np.array_equal(np.asarray(a), np.asarray(b)) and np.array_equal(np.asarray(a), np.asarray(c))
     assert walked_lit == k - 1 and 1 <= walked <= 3
+
+
+# ---- cluster_minibatch_kmeans (ml_minibatch_kmeans.c:67-198, 206-449) ---------------------------------------
+MB_CASES = [(800, 8, 5, 50, 20, 21), (1500, 24, 12, 100, 30, 22), (300, 6, 7, 1000, 5, 23), (40, 3, 8, 16, 12, 24)]   # test_oracle._minibatch_cases
+
+
+def _mb_rows(n, dim, k, seed):
+    X = W.mixture(n, dim, max(2, k // 2), seed)
+    if n == 40:
+        X[:] = X[:4].repeat(10, axis=0)          # 4 distinct rows for 8 clusters: the seeding stops early, 4 centroids stay zero
+    return X
+
+
+def test_cluster_minibatch_kmeans_equals_the_reference_outputs(ndb):
+    """Labels and centre bits the reference's OWN minibatch_kmeans_pp_init + main-loop text produced (golden ml_paths.npz),
+    and the number of rand() calls it made."""
+    g = np.load(GOLDEN)
+    for n, dim, k, batch, iters, seed in MB_CASES:
+        X = _mb_rows(n, dim, k, seed)
+        labels, centers, used = ndb.cluster_minibatch_kmeans(X, k, batch, iters, g["mb_draws_n%d" % n])
+        assert np.array_equal(labels, g["mb_labels_n%d" % n]), n
+        assert np.array_equal(BITS(centers), g["mb_center_bits_n%d" % n]), n
+        assert used == (k if n != 40 else 4) + min(batch, n) * iters
+
+
+@pytest.mark.parametrize("n,dim,k,batch,iters", [(30000, 32, 16, 100, 100), (5000, 130, 40, 256, 7), (2000, 5, 3, 1, 50)])
+def test_cluster_minibatch_kmeans_equals_the_oracle(ndb, n, dim, k, batch, iters):
+    X = W.mixture(n, dim, max(2, k // 3), n + k)
+    draws = np.random.default_rng(n).integers(0, O.RAND_MAX, k + batch * iters, dtype=np.int64).astype(np.int32)
+    want_l, want_c, want_used = O.cluster_minibatch_kmeans(X, k, batch, iters, draws)
+    labels, centers, used = ndb.cluster_minibatch_kmeans(X, k, batch, iters, draws)
+    assert used == want_used and np.array_equal(labels, want_l) and np.array_equal(BITS(centers), BITS(want_c))
+
+
+def test_cluster_minibatch_kmeans_errors_are_the_sql_functions(ndb):
+    X = W.gaussian(10, 4, 1)
+    d = np.arange(64, dtype=np.int32)
+    for k, batch, msg in ((1, 5, "num_clusters must be at least 2"), (3, 0, "batch_size must be at least 1"),
+                          (11, 5, "Not enough vectors (10) for 11 clusters")):
+        with pytest.raises(ndb.NdbError) as e:
+            ndb.cluster_minibatch_kmeans(X, k, batch, 2, d)
+        assert e.value.code == -1 and msg in str(e.value)
+    with pytest.raises(ndb.NdbError) as e:
+        ndb.cluster_minibatch_kmeans(X, 2, 5, 2, d[:3])          # the draws run out: the callback reports it
+    assert e.value.code == -1

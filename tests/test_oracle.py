@@ -495,3 +495,36 @@ def test_quantiser_golden_vectors():
     for X in _quant_inputs():
         for kind in (O.Q_INT8, O.Q_FP16, O.Q_BINARY, O.Q_UINT8, O.Q_TERNARY, O.Q_INT4):
             assert np.array_equal(O.quantize_rows(kind, X), g["quant_k%d_d%d" % (kind, X.shape[1])])
+
+
+# ---- cluster_minibatch_kmeans (ml_minibatch_kmeans.c) ------------------------------------------
+def _minibatch_cases():
+    return [(800, 8, 5, 50, 20, 21), (1500, 24, 12, 100, 30, 22), (300, 6, 7, 1000, 5, 23), (40, 3, 8, 16, 12, 24)]   # n, dim, k, batch, iters, seed
+
+
+def _minibatch_rows(n, dim, k, seed):
+    X = W.mixture(n, dim, max(2, k // 2), seed)
+    if n == 40:
+        X[:] = X[:4].repeat(10, axis=0)          # 4 distinct rows for 8 clusters: the seeding stops early (sum < 1e-10)
+    return X
+
+
+@pytest.mark.skipif(O.ref_leafs_lib() is None, reason="oracle/_ref not built (reference tree absent)")
+def test_cluster_minibatch_kmeans_equals_the_reference_functions():
+    """orc_cluster_minibatch_kmeans against the reference's minibatch_kmeans_pp_init (ml_minibatch_kmeans.c:67-198) and the
+    text of cluster_minibatch_kmeans' main loop and final assignment (:347-425), rand() seeded alike."""
+    for n, dim, k, batch, iters, seed in _minibatch_cases():
+        X = _minibatch_rows(n, dim, k, seed)
+        draws = O.libc_rand_draws(seed, k + batch * iters)
+        labels, centers, used = O.cluster_minibatch_kmeans(X, k, batch, iters, draws)
+        rl, rc = O.ref_cluster_minibatch_kmeans(X, k, batch, iters, seed)
+        assert np.array_equal(labels, rl) and np.array_equal(BITS(centers), BITS(rc)), (n, dim, k)
+        assert used == (k if n != 40 else 4) + min(batch, n) * iters
+
+
+def test_cluster_minibatch_kmeans_golden_vectors():
+    g = np.load(os.path.join(HERE, "golden", "ml_paths.npz"))
+    for n, dim, k, batch, iters, seed in _minibatch_cases():
+        X = _minibatch_rows(n, dim, k, seed)
+        labels, centers, used = O.cluster_minibatch_kmeans(X, k, batch, iters, g["mb_draws_n%d" % n])
+        assert np.array_equal(labels, g["mb_labels_n%d" % n]) and np.array_equal(BITS(centers), g["mb_center_bits_n%d" % n])
