@@ -50,6 +50,16 @@ emit(what="cluster_kmeans", n=n, dim=dim, k=k, lloyd_iterations=it, gpu_s=tg, gp
      seeds_that_needed_the_literal_walk=walked, gpu_s_literal_walk_for_every_seed=tg_lit, cpu_sample_rows=nc, cpu_s=tc, cpu_iterations=cit, cpu_s_scaled_to_n=tc * n / nc * (it / max(cit, 1)), cpu_threads=1,
      note="end to end through ndb_b200_cluster_kmeans (host buffers); CPU = orc_cluster_kmeans (the reference's loops) on n/10 rows, scaled linearly")
 
+# ---- cluster_minibatch_kmeans ------------------------------------------------------------------------------------
+mb_k, mb_batch, mb_iters = (16, 100, 20) if small else (64, 100, 100)
+mdraws = np.random.default_rng(9).integers(0, O.RAND_MAX, mb_k + mb_batch * mb_iters, dtype=np.int64).astype(np.int32)
+ndb.cluster_minibatch_kmeans(X[:5000], mb_k, mb_batch, 3, mdraws)
+tg, (ml, mc, mused) = wall(lambda: ndb.cluster_minibatch_kmeans(X, mb_k, mb_batch, mb_iters, mdraws), 2)
+tc, (cl2, cc2, cused) = wall(lambda: O.cluster_minibatch_kmeans(X[:nc], mb_k, mb_batch, mb_iters, mdraws))
+emit(what="cluster_minibatch_kmeans", n=n, dim=dim, k=mb_k, batch=mb_batch, iters=mb_iters, gpu_s=tg, rand_calls=mused,
+     cpu_sample_rows=nc, cpu_s=tc, cpu_threads=1,
+     note="CPU = orc_cluster_minibatch_kmeans on n/10 rows: its seeding and final assignment scale with n (x10), its %d mini-batch steps do not" % mb_iters)
+
 # ---- knn_classify ------------------------------------------------------------------------------------------------
 n, dim, nq, k = (20000, 32, 200, 5) if small else (1_000_000, 64, 2000, 10)
 X = W.mixture(n, dim, 64, 2)
