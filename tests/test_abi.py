@@ -57,6 +57,43 @@ def test_no_cpu_fallback_without_a_device():
     assert e.value.code == -3
 
 
+def test_next_rows_fail_loudly_without_a_device_and_check_their_arguments_first():
+    """The SURVEY 8f entry points (cluster_kmeans, minibatch, PQ, quantisers, Hamming scan): ENOTINIT without a device, and
+    the host-side mirror rejects malformed arrays before anything reaches the library."""
+    import numpy as np
+    import neurondb_b200 as ndb
+    lib = ndb._lib.load()
+    X = np.zeros((8, 4), np.float32)
+    d = np.arange(16, dtype=np.int32)
+    # argument shapes: caught by the mirror, device or not
+    for call in (lambda: ndb.cluster_kmeans(X, 3, 2, d[:2]),                       # k draws expected
+                 lambda: ndb.cluster_kmeans(X[0], 2, 2, d[:2]),                    # rows are 2-d
+                 lambda: ndb.pq_train(X, 2, 4, d[:3]),                             # m * ksub draws expected
+                 lambda: ndb.pq_encode(X, np.zeros((2, 4), np.float32)),           # codebooks are [m][ksub][dsub]
+                 lambda: ndb.quantize_rows(ndb.QUANT_INT8, X[0])):
+        with pytest.raises(ndb.NdbError) as e:
+            call()
+        assert e.value.code == -1
+    with pytest.raises(ndb.NdbError) as e:
+        ndb.pq_encode(X, np.zeros((2, 4, 3), np.float32))                          # 2 * 3 != 4 columns
+    assert e.value.code == -5
+    with pytest.raises(ndb.NdbError) as e:
+        ndb.hamming_knn(np.zeros((4, 2), np.uint8), 16, np.zeros((1, 3), np.uint8), 2)
+    assert e.value.code == -5 and "binary vector dimensions must match" in str(e.value)
+    assert lib.ndb_b200_quantized_row_bytes(ndb.QUANT_TERNARY, 9) == 3 and lib.ndb_b200_quantized_row_bytes(ndb.QUANT_INT4, 9) == 5
+    assert lib.ndb_b200_quantized_row_bytes(ndb.QUANT_FP16, 9) == 18 and lib.ndb_b200_quantized_row_bytes(7, 9) == -1
+    if lib.ndb_b200_device_count() > 0:
+        return
+    cb = np.zeros((2, 4, 2), np.float32)
+    for call in (lambda: ndb.cluster_kmeans(X, 2, 2, d[:2]), lambda: ndb.cluster_minibatch_kmeans(X, 2, 4, 2, d),
+                 lambda: ndb.pq_train(X, 2, 4, d[:8]), lambda: ndb.pq_encode(X, cb), lambda: ndb.launch_pq_encode(X, cb),
+                 lambda: ndb.PqIndex(cb), lambda: ndb.quantize_rows(ndb.QUANT_BINARY, X),
+                 lambda: ndb.hamming_knn(np.zeros((4, 2), np.uint8), 16, np.zeros((1, 2), np.uint8), 2)):
+        with pytest.raises(ndb.NdbError) as e:
+            call()
+        assert e.value.code == -3, e.value
+
+
 def test_product_does_not_import_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may touch oracle/."""
     pkg = os.path.join(ROOT, "neurondb_b200")
