@@ -47,3 +47,35 @@ def test_without_a_gpu_the_backend_fails_loudly():
     a = (C.c_float * 4)(1, 2, 3, 4)
     out = (C.c_float * 1)()
     assert g.ndb_b200_glue_l2(a, a, out, 1, 4) < 0
+
+
+def test_sql_function_glue_helpers():
+    """integration/ml_sql_b200.c: the float ** rows of neurondb_fetch_vectors_from_table flatten to the array the ABI takes,
+    the draws are the backend's rand() values in order, and without a device the functions fail loudly."""
+    import numpy as np
+    g = glue()
+    for sym in ("ndb_b200_sql_cluster_kmeans", "ndb_b200_sql_cluster_minibatch_kmeans", "ndb_b200_sql_train_pq_codebook",
+                "ndb_b200_sql_pq_encode_vector", "ndb_b200_sql_flatten_rows", "ndb_b200_sql_draw"):
+        assert hasattr(g, sym), sym
+    X = np.random.default_rng(3).standard_normal((37, 5)).astype(np.float32)
+    assert g.ndb_b200_glue_flatten_check(X.ctypes.data_as(C.c_void_p), 37, 5) == 1
+    libc = C.CDLL(None)
+    libc.srand(77)
+    libc.rand.restype = C.c_int
+    want = [libc.rand() for _ in range(9)]
+    libc.srand(77)
+    got = (C.c_int * 9)()
+    g.ndb_b200_glue_draw(9, got)
+    assert list(got) == want
+    import torch
+    if torch.cuda.is_available():
+        return
+    labels = (C.c_int * 37)()
+    assert g.ndb_b200_glue_cluster_kmeans(X.ctypes.data_as(C.c_void_p), 37, 5, 3, 4, labels) == -3          # ENOTINIT
+    assert g.ndb_b200_glue_cluster_minibatch_kmeans(X.ctypes.data_as(C.c_void_p), 37, 5, 3, 8, 4, labels) == -3
+    cb = np.zeros((1, 4, 5), np.float32)
+    assert g.ndb_b200_glue_train_pq_codebook(X.ctypes.data_as(C.c_void_p), 37, 5, 1, 4, cb.ctypes.data_as(C.c_void_p)) == -3
+    assert g.ndb_b200_glue_train_pq_codebook(X.ctypes.data_as(C.c_void_p), 37, 5, 2, 4, cb.ctypes.data_as(C.c_void_p)) == -1   # 5 % 2
+    payload = np.array([1, 4, 4], np.int32).tobytes() + cb.tobytes()                                           # dsub 4 != dim 5
+    codes = (C.c_int16 * 1)()
+    assert g.ndb_b200_glue_pq_encode_vector(X.ctypes.data_as(C.c_void_p), 5, payload, codes) == -5           # EDIM

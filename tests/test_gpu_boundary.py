@@ -150,3 +150,4 @@ def test_hnsw_scan_state_machine_over_a_staged_relation(ndb, orc, glue):
             assert np.array_equal(got_t, tids[on[qi][want].astype(np.int64)]), (mode, qi)
             assert np.array_equal(BITS(got_d), BITS(od[qi][want]))
         glue.ndb_b200_am_endscan(so)
+
