@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(256) pq_adc_kernel(const float *__restrict__ Q
 static int pq_scan(PqIndex *pq, const float *Q_dev, int nq, int k, float *dist_dev, int64_t *rows_dev, float *all_dev,
                    unsigned long long *recheck_dev, cudaStream_t s)
 {
+    NDB_REQUIRE(nq <= 65535, NDB_B200_EINVAL, "pq: at most 65535 queries per call (got %d); split the batch", nq);     // grid.y
     const size_t lut_bytes = (size_t) pq->m * pq->ksub * sizeof(double);
     const int kr = k <= 0 ? 0 : (k <= 32 ? 1 : (k <= 128 ? 4 : -1));
     size_t smem = lut_bytes;

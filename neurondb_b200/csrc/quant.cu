@@ -316,6 +316,7 @@ int ndb_b200_hamming_knn(const uint8_t *rows, int64_t n, int nbits, const uint8_
     NDB_REQUIRE(nbits >= 1 && nbits <= 32767, NDB_B200_EINVAL, "hamming_knn: nbits %d out of range 1..32767", nbits);
     NDB_REQUIRE(k >= 1 && k <= 128, NDB_B200_EINVAL, "hamming_knn: k=%d out of range 1..128", k);
     NDB_REQUIRE(n < (int64_t) 0xfffffff0ll, NDB_B200_EINVAL, "hamming_knn: too many rows for 32-bit slots");
+    NDB_REQUIRE(nq <= 65535 * HAM_QB, NDB_B200_EINVAL, "hamming_knn: at most %d queries per call (got %d); split the batch", 65535 * HAM_QB, nq);
     const int nbytes = (nbits + 7) / 8, nwords = (nbytes + 3) / 4;
     cudaStream_t s = ctx().stream;
     DevBuf drows, dq, pdist, pslot, od, oi, o32;
