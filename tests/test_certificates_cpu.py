@@ -159,3 +159,28 @@ def test_pq_table_sum_certificate_and_float_screen():
     # (one-dimensional vectors are the exception: |q - c| of two floats is often a 25-bit number, i.e. exactly halfway between
     # two floats -- those go down the reference's chain, as they must)
     assert certified > 0.99 * checked
+
+
+def test_knn_double_order_certificate():
+    """knn_classify / knn_regress (csrc/knn.cu: knn_neighbours): candidates are the kq smallest by (float distance, row); after
+    re-sorting them by (double distance, row), the first k are the reference's neighbours whenever the float distance of the last
+    candidate is strictly above that of the k-th -- rounding to float is monotonic."""
+    rng = np.random.default_rng(11)
+    certified = total = 0
+    for trial in range(300):
+        n, k = int(rng.integers(20, 2000)), int(rng.integers(1, 12))
+        d = np.abs(rng.standard_normal(n)) + 1.0
+        if trial % 3 == 0:                                   # clumps of doubles that share one float
+            base = np.float32(d[rng.integers(0, n)])
+            idx = rng.integers(0, n, int(rng.integers(2, 30)))
+            d[idx] = float(base) * (1.0 + rng.uniform(-2e-8, 2e-8, len(idx)))
+        f = d.astype(np.float32)
+        kq = min(n, k + 8)
+        cand = np.lexsort((np.arange(n), f))[:kq]
+        order = cand[np.lexsort((cand, d[cand]))]
+        want = np.lexsort((np.arange(n), d))[:k]
+        total += 1
+        if kq >= n or f[cand[-1]] > np.float32(d[order[k - 1]]):
+            certified += 1
+            assert np.array_equal(order[:k], want), trial
+    assert certified > 0.8 * total
