@@ -1,0 +1,166 @@
+"""CPU: the rounding-error bounds of the certified tensor-core selection (neurondb_b200/csrc/cert_bound.cuh), restated in
+numpy float32 and attacked with random rows and queries.  For every (query, row) the key the tensor path would hold --
+bf16-rounded inputs, fp32 accumulation (emulated both rounding to nearest and truncating, the worst a tensor core does),
+the 12-bit packing at both ends of its range -- must satisfy
+
+    cert_lower_bound(key) <= reference distance (ivfComputeDistance's f32 loop, from the oracle) <= cert_upper_bound(key)
+
+and cert_relax(key) must be a key whose lower bound lies strictly above the upper bound of `key`.  These are the
+inequalities the certified finish relies on; a violation here would be a wrong answer on the GPU."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+F = np.float32
+IDX_MASK = np.uint32((1 << 11) - 1)
+
+
+def bf16(a):
+    """round-to-nearest-even to bfloat16, back as float32"""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32)
+
+
+def acc32(terms, truncate):
+    """fp32 accumulation of exact products in the given order; truncate = round toward zero after every addition"""
+    s = F(0.0)
+    for t in terms:
+        e = float(s) + float(t)
+        r = F(e)
+        if truncate and abs(float(r)) > abs(e):
+            r = np.nextafter(r, F(0.0))
+        s = r
+    return s
+
+
+def pack_ends(key):
+    """tc_pack: the low 11 mantissa bits are replaced by an index -- both extremes"""
+    u = np.array([key], np.float32).view(np.uint32)
+    lo = (u & ~IDX_MASK).view(np.float32)[0]
+    hi = (u | IDX_MASK).view(np.float32)[0]
+    return (lo, hi) if key >= 0 else (hi, lo)
+
+
+class CertQ:
+    def __init__(self, q):
+        r = bf16(q)
+        q64, r64 = q.astype(np.float64), r.astype(np.float64)
+        self.eq = F(np.sqrt(F(np.sum((q64 - r64) ** 2)))) * F(1.0002)
+        self.qn = F(np.sqrt(F(np.sum(q64 ** 2)))) * F(1.0002)
+        self.qnr = F(np.sqrt(F(np.sum(r64 ** 2)))) * F(1.0002)
+        self.qn_lo = F(np.sqrt(F(np.sum(q64 ** 2)))) * F(0.9998)
+
+
+def stats_of(X):
+    R = bf16(X).astype(np.float64)
+    X64 = X.astype(np.float64)
+    e2, x2, r2 = ((X64 - R) ** 2).sum(1), (X64 ** 2).sum(1), (R ** 2).sum(1)
+    ok = r2 > 0
+    return np.array([F(e2.max()) * F(1.0001), F(x2.max()) * F(1.0001),
+                     F((e2[ok] / r2[ok]).max() if ok.any() else 0.0) * F(1.0002),
+                     F((x2[ok] / r2[ok]).max() if ok.any() else 0.0) * F(1.0002)], np.float32)
+
+
+def slack(metric, st, c, dim):
+    exm, xm = F(np.sqrt(st[0])) * F(1.0002), F(np.sqrt(st[1])) * F(1.0002)
+    gam = F(dim + 8) * F(1.1920929e-7)
+    xr = xm + exm
+    if metric == 1:
+        return exm + c.eq, gam * (xr + c.qnr) * (xr + c.qnr), gam
+    if metric == 3:
+        return exm * c.qnr + xm * c.eq + gam * xm * c.qn, gam * xr * c.qnr, gam
+    rho, kap = F(np.sqrt(st[2])) * F(1.0002), F(np.sqrt(st[3])) * F(1.0002)
+    return rho * (c.qnr + c.qn) + kap * c.eq, gam * c.qnr, gam
+
+
+def lower_bound(metric, key, st, c, dim):
+    E, D, gam = slack(metric, st, c, dim)
+    kv = key - abs(key) * F(4.8828125e-4) - D
+    if metric == 1:
+        r = F(np.sqrt(max(kv, F(0.0)))) - E
+        return r - abs(r) * gam
+    if metric == 3:
+        return kv - E
+    if not c.qn_lo > 0:
+        return F(-np.inf)
+    u = kv - E
+    return F(1.0) + (u / c.qn_lo if u < 0 else u / c.qn) - F(8.0) * gam
+
+
+def upper_bound(metric, key, st, c, dim):
+    E, D, gam = slack(metric, st, c, dim)
+    kv = key + abs(key) * F(4.8828125e-4) + D
+    if metric == 1:
+        r = F(np.sqrt(max(kv, F(0.0)))) + E
+        return r + abs(r) * gam
+    if metric == 3:
+        return kv + E
+    if not c.qn_lo > 0:
+        return F(np.inf)
+    u = kv + E
+    return F(1.0) + (u / c.qn_lo if u > 0 else u / c.qn) + F(8.0) * gam
+
+
+def relax(metric, key, st, c, dim):
+    E, D, gam = slack(metric, st, c, dim)
+    ub = upper_bound(metric, key, st, c, dim)
+    if metric == 1:
+        t = (ub + abs(ub) * F(2.0) * gam) + E
+        R = t * t + D
+    elif metric == 3:
+        R = ub + E + D
+    else:
+        if not c.qn_lo > 0:
+            return F(np.inf)
+        v = ub - F(1.0) + F(16.0) * gam
+        u = v * c.qn if v > 0 else v * c.qn_lo
+        R = u + E + D
+    return R + abs(R) * F(9.765625e-4) + F(1e-30)
+
+
+def keys_of(metric, x, q, truncate):
+    """the candidate value the epilogue forms for one (query, row) pair (tc_knn.cu: candidates())"""
+    xr, qr = bf16(x).astype(np.float64), bf16(q).astype(np.float64)
+    dot = acc32(xr * qr, truncate)                                    # bf16 x bf16 products are exact
+    xn = acc32(xr * xr, False)                                        # tc_row_norms_kernel: an fmaf chain
+    qn = F(np.sum((qr * qr).astype(np.float32)))                      # a fixed tree in the kernel; any order is within the bound
+    if metric == 1:
+        return F(F(F(-2.0) * dot + xn) + qn)                          # fmaf(-2, dot, ||x~||^2) + ||q~||^2
+    if metric == 3:
+        return -dot
+    rinv = F(1.0) / F(np.sqrt(xn)) if xn > 0 else F(0.0)
+    return -dot * rinv
+
+
+@pytest.mark.parametrize("metric", [1, 2, 3])
+def test_bounds_enclose_the_reference_distance(metric):
+    rng = np.random.default_rng(100 + metric)
+    with np.errstate(over="ignore", invalid="ignore"):
+        for trial in range(40):
+            dim = int(rng.choice([1, 3, 8, 32, 96, 128, 200, 768]))
+            scale = float(10.0 ** rng.integers(-3, 4))
+            n = 24
+            X = (rng.standard_normal((n, dim)) * scale).astype(np.float32)
+            q = (rng.standard_normal(dim) * scale).astype(np.float32)
+            if trial % 4 == 0:
+                X[:6] = q + (rng.standard_normal((6, dim)) * scale * 1e-3).astype(np.float32)      # near the query: tiny distances
+            if trial % 5 == 0:
+                X[6:9] *= np.float32(1e-4)                                                         # short rows (cosine: small norms)
+            if trial % 7 == 0:
+                X[9] = 0.0
+            st = stats_of(X)
+            c = CertQ(q)
+            ref = O.distance_pairs(np.repeat(q[None, :], n, 0), X, metric, O.ARITH_IVF_F32)        # vec1 = query, vec2 = row
+            for i in range(n):
+                if metric == 2 and not np.any(bf16(X[i])):
+                    continue                                            # a zero row packs as an empty key in the kernel
+                for truncate in (False, True):
+                    key = keys_of(metric, X[i], q, truncate)
+                    for pk in pack_ends(key):
+                        lo, hi = lower_bound(metric, pk, st, c, dim), upper_bound(metric, pk, st, c, dim)
+                        assert lo <= ref[i] <= hi, (trial, dim, scale, i, truncate, float(pk), float(lo), float(ref[i]), float(hi))
+                        R = relax(metric, pk, st, c, dim)
+                        if np.isfinite(R) and np.isfinite(hi):
+                            assert lower_bound(metric, R, st, c, dim) > hi, (trial, dim, i, float(pk), float(R))
