@@ -138,7 +138,7 @@ def keys_of(metric, x, q, truncate):
 def test_bounds_enclose_the_reference_distance(metric):
     rng = np.random.default_rng(100 + metric)
     with np.errstate(over="ignore", invalid="ignore"):
-        for trial in range(40):
+        for trial in range(140):
             dim = int(rng.choice([1, 3, 8, 32, 96, 128, 200, 768]))
             scale = float(10.0 ** rng.integers(-3, 4))
             n = 24
