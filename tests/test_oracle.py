@@ -528,3 +528,19 @@ def test_cluster_minibatch_kmeans_golden_vectors():
         X = _minibatch_rows(n, dim, k, seed)
         labels, centers, used = O.cluster_minibatch_kmeans(X, k, batch, iters, g["mb_draws_n%d" % n])
         assert np.array_equal(labels, g["mb_labels_n%d" % n]) and np.array_equal(BITS(centers), g["mb_center_bits_n%d" % n])
+
+
+def test_quantisation_fixture_of_the_reference_sql_tests():
+    """sql/11_quantization_detail.sql quantises '[1,-1,0,3]' with every method and states the sizes ("4 dimensions use 1 byte"
+    for binary and ternary, 2 bytes for int4, 1 / 2 bytes per dimension for int8 / uint8 / fp16); the bytes follow from the
+    functions' definitions."""
+    v = np.array([[1, -1, 0, 3]], np.float32)
+    sizes = {O.Q_INT8: 4, O.Q_FP16: 8, O.Q_BINARY: 1, O.Q_UINT8: 4, O.Q_TERNARY: 1, O.Q_INT4: 2}
+    for kind, nbytes in sizes.items():
+        assert O.lib().orc_quantized_row_bytes(kind, 4) == nbytes
+    assert O.quantize_rows(O.Q_BINARY, v)[0].tolist() == [0b1001]                       # bits 0 and 3: the components > 0
+    assert O.quantize_rows(O.Q_INT8, v)[0].view(np.int8).tolist() == [42, -42, 0, 127]  # rintf(x * 127 / 3)
+    assert O.quantize_rows(O.Q_UINT8, v)[0].tolist() == [128, 0, 64, 255]               # rintf((x + 1) * 255 / 4): 127.5 -> 128, 63.75 -> 64
+    assert O.quantize_rows(O.Q_TERNARY, v)[0].tolist() == [0b10000000]                  # threshold 3/3 = 1, strict: 1 and -1 are 0; 3 -> 2 in bits 6-7
+    assert O.quantize_rows(O.Q_FP16, v)[0].view(np.uint16).tolist() == [0x3C00, 0xBC00, 0x0000, 0x4200]
+    assert O.quantize_rows(O.Q_INT4, v)[0].tolist() == [(8 - 2) << 4 | (8 + 2), (8 + 7) << 4 | 8]
