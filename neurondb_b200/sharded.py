@@ -8,6 +8,8 @@ Which paths shard, and how:
   replicated, same all-gather + merge;
 * k-means training -- rows split, centroids replicated, one all-reduce of the k*d partial sums and
   k counts (+ one of the cost) per Lloyd iteration;
+* quantised scans (PQ asymmetric distance, Hamming) -- encoded rows split into contiguous ranges, codebook / queries
+  replicated, per-rank top-k with the local row indices shifted to global ones, the same all-gather + merge;
 * HNSW search -- does not shard (graph traversal is global): replicas, queries split, results
   gathered.  HNSW build: one rank builds, the graph is broadcast.
 
@@ -191,6 +193,24 @@ def gpu_knn_sharded(ds, Q_t, k, metric, arith):
     i_t = torch.empty((nq, k), dtype=torch.int64, device=Q_t.device)
     _on_side_stream(lambda st: ds.knn_dev(Q_t.data_ptr(), nq, k, d_t.data_ptr(), i_t.data_ptr(), metric, arith, st))
     return gather_merge(d_t, i_t, gpu_merge)
+
+
+def global_rows(rows_t, lo):
+    """Local row indices of a rank's top-k -> global ones (rows [lo, hi) live on this rank); -1 (past the end) stays."""
+    return torch.where(rows_t >= 0, rows_t + lo, rows_t)
+
+
+def gpu_pq_search_sharded(pq, Q_t, k, lo):
+    """ORDER BY pq_asymmetric_distance LIMIT k over row-sharded codes: `pq` holds the codes of rows [lo, hi) of the table,
+    Q_t the replicated [nq, dim] float32 CUDA queries.  Local scan -> global rows -> all-gather -> (dist, row) merge."""
+    from . import _lib as L
+    from ._lib import check, ptr
+    nq = Q_t.shape[0]
+    d_t = torch.empty((nq, k), dtype=torch.float32, device=Q_t.device)
+    r_t = torch.empty((nq, k), dtype=torch.int64, device=Q_t.device)
+    _on_side_stream(lambda st: check(L.load().ndb_b200_pq_search_dev(pq.h, ptr(Q_t.data_ptr()), nq, k, ptr(d_t.data_ptr()),
+                                                                     ptr(r_t.data_ptr()), ptr(st))))
+    return gather_merge(d_t, global_rows(r_t, lo), gpu_merge)
 
 
 def gpu_hnsw_replicas(h, Q_t, ef, k, mode):

@@ -153,6 +153,17 @@ def _worker_sharded(rank, world, port, out):
     d, i = O.knn_exact(X[lo:hi], Q, 10, O.L2, O.ARITH_OP_F64, ids=np.arange(lo, hi, dtype=np.int64), nthreads=1)
     md, mi = S.gather_merge(torch.from_numpy(d), torch.from_numpy(i),
                             lambda ad, ai: tuple(torch.from_numpy(a) for a in O.merge_topk(ad.numpy(), ai.numpy())))
+    # quantised scans over row shards (PQ codes, binary rows): local top-k with local rows -> global rows -> gather -> merge
+    draws = np.random.default_rng(5).integers(0, O.RAND_MAX, 2 * 16, dtype=np.int64).astype(np.int32)
+    cb = O.pq_train(X[:500], 2, 16, draws, 3)
+    codes = O.pq_encode(X, cb)
+    pd_, pr_, _ = O.pq_knn(Q, codes[lo:hi], cb, 10)
+    pmd, pmi = S.gather_merge(torch.from_numpy(pd_), S.global_rows(torch.from_numpy(pr_), lo),
+                              lambda ad, ai: tuple(torch.from_numpy(a) for a in O.merge_topk(ad.numpy(), ai.numpy())))
+    bits, qbits = O.quantize_rows(O.Q_BINARY, X), O.quantize_rows(O.Q_BINARY, Q)
+    hd_, hi_ = O.hamming_knn(bits[lo:hi], 8, qbits, 10)
+    hmd, hmi = S.gather_merge(torch.from_numpy(hd_.astype(np.float32)), S.global_rows(torch.from_numpy(hi_), lo),
+                              lambda ad, ai: tuple(torch.from_numpy(a) for a in O.merge_topk(ad.numpy(), ai.numpy())))
     # HNSW replicas: each rank answers a slice of the queries, everyone ends up with all of them
     qlo, qhi = S.query_range(Q.shape[0], rank, world)
     fake_d = torch.arange(qlo, qhi, dtype=torch.float32).unsqueeze(1).repeat(1, 3)
@@ -175,6 +186,11 @@ def _worker_sharded(rank, world, port, out):
         wd, wi = O.knn_exact(X, Q, 10, O.L2, O.ARITH_OP_F64, nthreads=1)
         ok["knn_ids"] = np.array_equal(mi.numpy(), wi)
         ok["knn_dist"] = np.array_equal(md.numpy().view(np.uint32), wd.view(np.uint32))
+        wpd, wpr, _ = O.pq_knn(Q, codes, cb, 10)
+        ok["pq_rows"] = np.array_equal(pmi.numpy(), wpr)
+        ok["pq_dist"] = np.array_equal(pmd.numpy().view(np.uint32), wpd.view(np.uint32))
+        whd, whi = O.hamming_knn(bits, 8, qbits, 10)
+        ok["hamming"] = np.array_equal(hmi.numpy(), whi) and np.array_equal(hmd.numpy().astype(np.int32), whd)
         ok["replicas"] = bool(torch.equal(gi[:, 0], torch.arange(Q.shape[0])) and gd.shape == (Q.shape[0], 3))
         out.put(ok)
     dist.barrier()
