@@ -164,3 +164,70 @@ def test_bounds_enclose_the_reference_distance(metric):
                         R = relax(metric, pk, st, c, dim)
                         if np.isfinite(R) and np.isfinite(hi):
                             assert lower_bound(metric, R, st, c, dim) > hi, (trial, dim, i, float(pk), float(R))
+
+
+# ---- the certified selection built on those bounds (cert_common.cuh: ivf_coarse_cert_kernel + cert_rerank) ----------
+def _certified_nearest(keys, exact, st, c, dim, np_, nparts, kc, cap):
+    """The decision logic of the certified coarse stage, restated: per-range partial lists of the kc smallest keys, the
+    `cap` smallest of their union as candidates, exact re-evaluation 16 at a time in key order, certificate after every
+    chunk.  Returns the certified top-np_ (list of row indices) or None (the kernel would send the query to the exact path)."""
+    L = len(keys)
+    bounds = np.linspace(0, L, nparts + 1).astype(int)
+    G = np.inf
+    union = []
+    for p in range(nparts):
+        idx = np.arange(bounds[p], bounds[p + 1])
+        order = idx[np.lexsort((idx, keys[idx]))][:kc]
+        if len(order) == kc:
+            G = min(G, float(keys[order[-1]]))                       # a full list: rows it may have dropped have keys >= its last one
+        union.extend(order.tolist())
+    union = np.array(union)
+    union = union[keys[union] <= G]                                  # entries above G are outranked by rows nobody kept
+    union = union[np.lexsort((union, keys[union]))]
+    cand = union[:cap]
+    g_rest = float(keys[cand[-1]]) if len(union) > cap else G
+    complete = G == np.inf and len(union) <= cap
+    top = []                                                         # (exact distance, row), ascending
+    for c0 in range(0, len(cand), 16):
+        for r in cand[c0:c0 + 16]:
+            top.append((float(exact[r]), int(r)))
+        top = sorted(top)[:np_]
+        more = c0 + 16 < len(cand)
+        g = min(float(keys[cand[c0 + 16]]), g_rest) if more else g_rest
+        td = top[np_ - 1][0] if len(top) >= np_ else np.inf
+        certified = (complete and not more) or (np.isfinite(g) and lower_bound(1, F(g), st, c, dim) > F(td))
+        if certified:
+            return [r for _, r in top]
+        if not more:
+            return None
+    return None
+
+
+def test_certified_nearest_centroids_are_the_exact_ones():
+    """Whenever the restated certificate accepts, the answer is the reference's (ivfSelectClusters: the np nearest centroids
+    by (f32 L2, index)) -- on clustered centroids, near-duplicates and exact ties -- and it accepts most of the time.
+    (The `keys <= G` filter of the candidate set is load-bearing: without it this test finds a clump of 75 near-identical
+    centroids where a dropped row outranks an accepted answer.)"""
+    rng = np.random.default_rng(77)
+    accepted = total = 0
+    with np.errstate(over="ignore", invalid="ignore"):
+        for trial in range(60):
+            dim = int(rng.choice([8, 32, 128]))
+            L = int(rng.choice([64, 300, 1024]))
+            C = rng.standard_normal((L, dim)).astype(np.float32)
+            if trial % 3 == 0:
+                C[: L // 4] = C[0] + (rng.standard_normal((L // 4, dim)) * 1e-3).astype(np.float32)    # a tight clump
+            if trial % 4 == 0:
+                C[5] = C[3]                                                                               # exact duplicates: ties by index
+            q = (C[rng.integers(0, L)] + rng.standard_normal(dim).astype(np.float32) * np.float32(0.3)).astype(np.float32)
+            st, cq = stats_of(C), CertQ(q)
+            exact = O.distance_pairs(np.repeat(q[None, :], L, 0), C, 1, O.ARITH_IVF_F32)
+            keys = np.array([pack_ends(keys_of(1, C[i], q, bool(i & 1)))[i >> 1 & 1] for i in range(L)], np.float32)
+            want = np.lexsort((np.arange(L), exact))
+            for np_, nparts, kc, cap in ((1, 4, 7, 32), (8, 8, 14, 32), (16, 2, 16, 128), (32, 16, 16, 128)):
+                got = _certified_nearest(keys, exact, st, cq, dim, np_, nparts, kc, cap)
+                total += 1
+                if got is not None:
+                    accepted += 1
+                    assert got == want[:np_].tolist(), (trial, dim, L, np_, nparts, kc, cap)
+    assert accepted > 0.5 * total
