@@ -231,3 +231,99 @@ def test_certified_nearest_centroids_are_the_exact_ones():
                     accepted += 1
                     assert got == want[:np_].tolist(), (trial, dim, L, np_, nparts, kc, cap)
     assert accepted > 0.5 * total
+
+
+# ---- the tensor IVF search as a whole: scan with the relaxed shared bound, then the certified finish --------------------
+# A model of what tc_knn.cu's list mode leaves behind and of ivf_tc_finish_cert_kernel's decision (ivf_cert.cuh), per query:
+#   * the probed rows are split into units (probed list x segment x column half); a unit keeps its kc smallest packed keys;
+#   * a row enters a unit's list only if its key is below the unit's threshold = min(own kc-th key, next_up(shared bound as last
+#     read -- possibly stale, i.e. larger));
+#   * a unit whose list holds >= k entries publishes R = cert_relax(upper end of its k-th key) into the shared bound (min);
+#   * finish: candidates = the 32 KRC smallest entries over all units; rows elsewhere have keys >= g_rest =
+#     min(last candidate key if the entries overflow, R, smallest kc-th key of a full list); re-evaluate 16 at a time; accept when
+#     lower_bound(g) > tau.
+# Property: an accepted answer is the reference's top k by (ivfComputeDistance, id) over ALL probed rows.
+BIG = F(1.7014118346046923e38)
+
+
+def _model_scan(metric, keys_raw, units, kc, k, st, cq, dim, rng):
+    shared, history = F(np.inf), [F(np.inf)]
+    lists = [[] for _ in units]
+    published = [F(np.inf)] * len(units)
+    gcap = [F(np.inf)] * len(units)
+    sched = [(u, c0) for u, rows in enumerate(units) for c0 in range(0, len(rows), 32)]
+    order = rng.permutation(len(sched))
+    order = sorted(order, key=lambda i: (sched[i][1] + rng.integers(0, 96), sched[i][0]))     # roughly in step, like concurrent CTAs
+    for i in order:
+        u, c0 = sched[i]
+        seen = history[max(0, len(history) - 1 - int(rng.integers(0, 3)))]                   # a stale read is a larger bound
+        gcap[u] = min(gcap[u], np.nextafter(seen, F(np.inf)))
+        L = lists[u]
+        changed = False
+        for j, row in enumerate(units[u][c0:c0 + 32]):
+            thr = min(L[-1][0] if len(L) == kc else F(np.inf), gcap[u])
+            if keys_raw[row] < thr:
+                u32 = np.array([min(keys_raw[row], BIG)], np.float32).view(np.uint32)
+                packed = ((u32 & ~IDX_MASK) | np.uint32((c0 + j) & 0x7FF)).view(np.float32)[0]
+                L.append((packed, int(row)))
+                L.sort()
+                del L[kc:]
+                changed = True
+        if changed and len(L) >= k and L[k - 1][0] < published[u]:
+            published[u] = L[k - 1][0]
+            pub = pack_ends(published[u])[1]                        # upper end of the value the packed key stands for
+            if pub < BIG:
+                shared = min(shared, relax(metric, pub, st, cq, dim))
+                history.append(shared)
+    return lists, shared
+
+
+def _model_finish(metric, lists, R, exact, kc, k, cap, st, cq, dim):
+    entries = sorted(e for L in lists for e in L)
+    own_min = min([L[-1][0] for L in lists if len(L) == kc], default=F(np.inf))
+    cand = entries[:cap]
+    g_rest = min(cand[-1][0] if len(entries) > cap else F(np.inf), R, own_min)
+    complete = not (R < F(1.0e38)) and own_min == np.inf and len(entries) <= cap
+    top = []
+    for c0 in range(0, len(cand), 16):
+        top = sorted(top + [(float(exact[r]), r) for _, r in cand[c0:c0 + 16]])[:k]
+        more = c0 + 16 < len(cand)
+        g = min(cand[c0 + 16][0], g_rest) if more else g_rest
+        tau = top[k - 1][0] if len(top) >= k else np.inf
+        if (complete and not more) or (np.isfinite(g) and lower_bound(metric, F(g), st, cq, dim) > F(tau)):
+            return [r for _, r in top]
+        if not more:
+            return None
+    return None if cand else ([] if complete else None)
+
+
+@pytest.mark.parametrize("metric", [1, 2, 3])
+def test_model_of_the_tensor_ivf_search_accepts_only_exact_answers(metric):
+    rng = np.random.default_rng(500 + metric)
+    accepted = total = 0
+    with np.errstate(over="ignore", invalid="ignore"):
+        for trial in range(36):
+            dim = int(rng.choice([16, 96, 128]))
+            n = int(rng.choice([200, 900, 2500]))
+            centre = rng.standard_normal(dim).astype(np.float32)
+            X = (centre + rng.standard_normal((n, dim)).astype(np.float32) * np.float32(rng.choice([0.05, 0.3, 1.0]))).astype(np.float32)
+            if trial % 3 == 0:
+                X[: n // 5] = X[0] + (rng.standard_normal((n // 5, dim)) * 1e-3).astype(np.float32)      # near-duplicates: keys cannot order them
+            if trial % 4 == 0:
+                X[7] = X[3]                                                                                # an exact tie, decided by id
+            q = (X[rng.integers(0, n)] + rng.standard_normal(dim).astype(np.float32) * np.float32(0.2)).astype(np.float32)
+            st, cq = stats_of(X), CertQ(q)
+            exact = O.distance_pairs(np.repeat(q[None, :], n, 0), X, metric, O.ARITH_IVF_F32)
+            keys_raw = np.array([keys_of(metric, X[i], q, bool(i & 1)) for i in range(n)], np.float32)
+            want = np.lexsort((np.arange(n), exact))
+            # units of uneven size, as probed lists of uneven length cut into segments and column halves
+            cuts = np.sort(rng.choice(np.arange(1, n), size=min(n - 1, int(rng.integers(3, 24))), replace=False))
+            units = [u for u in np.split(rng.permutation(n), cuts) if len(u)]
+            for k, kc, cap in ((1, 7, 32), (10, 16, 32), (24, 16, 64)):
+                lists, R = _model_scan(metric, keys_raw, units, kc, min(k, kc), st, cq, dim, rng)
+                got = _model_finish(metric, lists, R, exact, kc, k, cap, st, cq, dim)
+                total += 1
+                if got is not None:
+                    accepted += 1
+                    assert got == want[:k].tolist(), (trial, metric, dim, n, k, kc, cap)
+    assert accepted > 0.3 * total
